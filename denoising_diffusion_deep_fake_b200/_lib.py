@@ -1,0 +1,212 @@
+"""ctypes binding of libd3fk.so (include/d3fk.h).  There is no fallback: if the shared library is
+missing, or the device is not sm_100, every product entry point raises."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libd3fk.so")
+
+F32, BF16 = 0, 1
+
+i32, i64, u64, f32, vp = C.c_int32, C.c_int64, C.c_uint64, C.c_float, C.c_void_p
+
+
+class ConvParams(C.Structure):
+    _fields_ = [("dtype", i32), ("mode", i32), ("src0", vp), ("src1", vp),
+                ("c0", i32), ("c1", i32), ("ld0", i32), ("ld1", i32), ("up0", i32),
+                ("B", i32), ("Hi", i32), ("Wi", i32), ("Ho", i32), ("Wo", i32),
+                ("kh", i32), ("kw", i32), ("stride", i32), ("pad", i32),
+                ("w", vp), ("Cout", i32), ("_pad0", i32),
+                ("out", vp), ("out_nchw", vp), ("scale", vp), ("shift", vp), ("res", vp), ("stats", vp),
+                ("ldo", i32), ("ldr", i32), ("relu", i32), ("_pad1", i32)]
+
+
+class WgradParams(C.Structure):
+    _fields_ = [("dtype", i32), ("_pad0", i32), ("src0", vp), ("src1", vp),
+                ("c0", i32), ("c1", i32), ("ld0", i32), ("ld1", i32), ("up0", i32),
+                ("B", i32), ("Hi", i32), ("Wi", i32), ("Ho", i32), ("Wo", i32),
+                ("kh", i32), ("kw", i32), ("stride", i32), ("pad", i32),
+                ("dy", vp), ("dw", vp), ("ldy", i32), ("Cout", i32), ("cin_real", i32), ("cout_real", i32)]
+
+
+class PackParams(C.Structure):
+    _fields_ = [("dtype", i32), ("Cout", i32), ("Cin", i32), ("kh", i32), ("kw", i32), ("cin_pad", i32),
+                ("cout_pad", i32), ("_pad0", i32), ("w", vp), ("w_fwd", vp), ("w_dgrad", vp)]
+
+
+class BnParams(C.Structure):
+    _fields_ = [("dtype", i32), ("C", i32), ("relu", i32), ("_pad0", i32), ("count", i64),
+                ("x", vp), ("y", vp), ("res", vp),
+                ("ldx", i32), ("ldy", i32), ("ldr", i32), ("_pad1", i32),
+                ("stats", vp), ("gamma", vp), ("beta", vp),
+                ("running_mean", vp), ("running_var", vp), ("num_batches_tracked", vp),
+                ("eps", f32), ("momentum", f32),
+                ("scale", vp), ("shift", vp), ("mean", vp), ("invstd", vp),
+                ("dy", vp), ("act", vp), ("dx", vp), ("dres", vp),
+                ("lddy", i32), ("ldact", i32), ("lddx", i32), ("lddres", i32),
+                ("bstats", vp), ("dgamma", vp), ("dbeta", vp), ("coef", vp)]
+
+
+class PoolParams(C.Structure):
+    _fields_ = [("dtype", i32), ("B", i32), ("H", i32), ("W", i32), ("C", i32), ("accumulate", i32),
+                ("x", vp), ("y", vp), ("idx", vp), ("dy", vp), ("dx", vp),
+                ("ldx", i32), ("ldy", i32), ("lddy", i32), ("lddx", i32)]
+
+
+class LayoutParams(C.Structure):
+    _fields_ = [("dtype", i32), ("B", i32), ("C", i32), ("H", i32), ("W", i32), ("cpad", i32), ("src", vp), ("dst", vp)]
+
+
+class ChansumParams(C.Structure):
+    _fields_ = [("dtype", i32), ("C", i32), ("ld", i32), ("_pad0", i32), ("count", i64), ("x", vp), ("out", vp)]
+
+
+class QsampleParams(C.Structure):
+    _fields_ = [("B", i32), ("chw", i32), ("lam", f32), ("fixed_r", f32), ("x", vp), ("noise", vp), ("y", vp),
+                ("out", vp), ("r_out", vp), ("noise_out", vp), ("seed", u64), ("offset", u64)]
+
+
+class PosteriorParams(C.Structure):
+    _fields_ = [("n", i64), ("x", vp), ("x0_hat", vp), ("z", vp), ("coef_table", vp), ("step", vp),
+                ("k_xi", f32), ("k_x0", f32), ("sigma", f32), ("_pad0", f32), ("seed", u64), ("offset", u64)]
+
+
+class MiscParams(C.Structure):
+    _fields_ = [("p0", vp), ("n", i64)]
+
+
+class AdamParams(C.Structure):
+    _fields_ = [("n", i64), ("p", vp), ("g", vp), ("m", vp), ("v", vp), ("ema", vp),
+                ("lr", f32), ("beta1", f32), ("beta2", f32), ("eps", f32), ("bias1", f32), ("bias2", f32),
+                ("ema_decay", f32), ("grad_scale", f32)]
+
+
+class _OpUnion(C.Union):
+    _fields_ = [("conv", ConvParams), ("wgrad", WgradParams), ("pack", PackParams), ("bn", BnParams),
+                ("pool", PoolParams), ("layout", LayoutParams), ("chansum", ChansumParams),
+                ("qsample", QsampleParams), ("posterior", PosteriorParams), ("misc", MiscParams),
+                ("adam", AdamParams)]
+
+
+class Op(C.Structure):
+    _fields_ = [("kind", i32), ("_pad", i32), ("u", _OpUnion)]
+
+
+# op kinds (enum d3fk_op_kind)
+(OP_CONV, OP_WGRAD, OP_PACK, OP_NCHW2NHWC, OP_BN_FINALIZE, OP_BN_APPLY, OP_BN_FOLD, OP_BN_BWD_REDUCE,
+ OP_BN_BWD_FINALIZE, OP_BN_BWD_APPLY, OP_MAXPOOL_FWD, OP_MAXPOOL_BWD, OP_SUMPOOL2, OP_CHANSUM, OP_QSAMPLE,
+ OP_POSTERIOR, OP_MEMSET, OP_INC, OP_ADAM) = range(1, 20)
+
+_UNION_FIELD = {OP_CONV: "conv", OP_WGRAD: "wgrad", OP_PACK: "pack", OP_NCHW2NHWC: "layout",
+                OP_BN_FINALIZE: "bn", OP_BN_APPLY: "bn", OP_BN_FOLD: "bn", OP_BN_BWD_REDUCE: "bn",
+                OP_BN_BWD_FINALIZE: "bn", OP_BN_BWD_APPLY: "bn", OP_MAXPOOL_FWD: "pool", OP_MAXPOOL_BWD: "pool",
+                OP_SUMPOOL2: "pool", OP_CHANSUM: "chansum", OP_QSAMPLE: "qsample", OP_POSTERIOR: "posterior",
+                OP_MEMSET: "misc", OP_INC: "misc", OP_ADAM: "adam"}
+_PARAM_CLS = {"conv": ConvParams, "wgrad": WgradParams, "pack": PackParams, "bn": BnParams, "pool": PoolParams,
+              "layout": LayoutParams, "chansum": ChansumParams, "qsample": QsampleParams,
+              "posterior": PosteriorParams, "misc": MiscParams, "adam": AdamParams}
+
+SINGLE_ENTRY = {OP_CONV: "d3fk_conv", OP_WGRAD: "d3fk_wgrad", OP_PACK: "d3fk_pack_weights",
+                OP_NCHW2NHWC: "d3fk_nchw_to_nhwc", OP_BN_FINALIZE: "d3fk_bn_finalize", OP_BN_APPLY: "d3fk_bn_apply",
+                OP_BN_FOLD: "d3fk_bn_fold", OP_BN_BWD_REDUCE: "d3fk_bn_bwd_reduce",
+                OP_BN_BWD_FINALIZE: "d3fk_bn_bwd_finalize", OP_BN_BWD_APPLY: "d3fk_bn_bwd_apply",
+                OP_MAXPOOL_FWD: "d3fk_maxpool_fwd", OP_MAXPOOL_BWD: "d3fk_maxpool_bwd", OP_SUMPOOL2: "d3fk_sumpool2",
+                OP_CHANSUM: "d3fk_chansum", OP_QSAMPLE: "d3fk_q_sample", OP_POSTERIOR: "d3fk_posterior_step",
+                OP_ADAM: "d3fk_adam"}
+EXPORTS = ["d3fk_version", "d3fk_sizeof_op", "d3fk_init", "d3fk_last_error", "d3fk_device_error_flag", "d3fk_run",
+           "d3fk_launch_count"] + sorted(set(SINGLE_ENTRY.values()))
+
+
+def make_op(kind, **fields):
+    """Build one d3fk_op record.  Pointer fields take ints (tensor.data_ptr()) or None."""
+    op = Op()
+    op.kind = kind
+    name = _UNION_FIELD[kind]
+    params = getattr(op.u, name)
+    valid = {f[0] for f in _PARAM_CLS[name]._fields_}
+    for k, v in fields.items():
+        if k not in valid:
+            raise KeyError(f"{name} params have no field {k!r}")
+        setattr(params, k, v)
+    return op
+
+
+def op_params(op):
+    return getattr(op.u, _UNION_FIELD[op.kind])
+
+
+class D3fkError(RuntimeError):
+    pass
+
+
+_lib = None
+_inited = set()
+
+
+def load():
+    """Load libd3fk.so (no device needed).  Raises if the library has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise D3fkError(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                        f"(there is no CPU or PyTorch fallback for the d3fk hot path)")
+    lib = C.CDLL(LIB_PATH)
+    lib.d3fk_last_error.restype = C.c_char_p
+    lib.d3fk_launch_count.restype = C.c_int64
+    lib.d3fk_run.argtypes = [C.POINTER(Op), C.c_int, vp]
+    lib.d3fk_init.argtypes = [C.c_int]
+    for kind, name in SINGLE_ENTRY.items():
+        getattr(lib, name).argtypes = [C.POINTER(_PARAM_CLS[_UNION_FIELD[kind]]), vp]
+    if lib.d3fk_sizeof_op() != C.sizeof(Op):
+        raise D3fkError(f"ABI mismatch: sizeof(d3fk_op) = {lib.d3fk_sizeof_op()} in the library, "
+                        f"{C.sizeof(Op)} in the Python mirror")
+    _lib = lib
+    return lib
+
+
+def init(device_index):
+    lib = load()
+    if device_index in _inited:
+        return lib
+    rc = lib.d3fk_init(int(device_index))
+    if rc != 0:
+        raise D3fkError(f"d3fk_init({device_index}) failed ({rc}): {lib.d3fk_last_error().decode()}")
+    _inited.add(device_index)
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        raise D3fkError(f"libd3fk error {rc}: {_lib.d3fk_last_error().decode()}")
+
+
+class OpList:
+    """A recorded op list: a contiguous ctypes array handed to d3fk_run in one call."""
+
+    def __init__(self, ops):
+        self.n = len(ops)
+        self.array = (Op * max(self.n, 1))(*ops)
+
+    def run(self, stream_ptr):
+        check(_lib.d3fk_run(self.array, self.n, stream_ptr))
+
+    def __len__(self):
+        return self.n
+
+    def __iter__(self):
+        return (self.array[i] for i in range(self.n))
+
+
+def run_single(op, stream_ptr):
+    """Run one op through its dedicated extern "C" entry point (per-op parity tests)."""
+    if op.kind in SINGLE_ENTRY:
+        fn = getattr(_lib, SINGLE_ENTRY[op.kind])
+        check(fn(C.byref(op_params(op)), stream_ptr))
+    else:
+        arr = (Op * 1)(op)
+        check(_lib.d3fk_run(arr, 1, stream_ptr))
+
+
+def launch_count():
+    return int(load().d3fk_launch_count())

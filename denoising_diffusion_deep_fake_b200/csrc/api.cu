@@ -1,0 +1,178 @@
+// api.cu — the extern "C" surface of libd3fk (declared in include/d3fk.h) and the op-list runner.
+#include <stdarg.h>
+#include <string.h>
+#include "common.cuh"
+
+namespace d3fk {
+
+int64_t g_launch_count = 0;
+char g_last_error[512] = "";
+int* g_dev_error_flag = nullptr;
+static int g_inited_device = -1;
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return set_error(D3FK_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+  }
+  return D3FK_OK;
+}
+
+// launchers implemented in the other translation units
+int launch_conv_ffma(const d3fk_conv_params*, cudaStream_t);
+int launch_wgrad_ffma(const d3fk_wgrad_params*, cudaStream_t);
+int launch_conv_tc(const d3fk_conv_params*, cudaStream_t);
+int launch_wgrad_tc(const d3fk_wgrad_params*, cudaStream_t);
+int launch_pack(const d3fk_pack_params*, cudaStream_t);
+int launch_nchw_to_nhwc(const d3fk_layout_params*, cudaStream_t);
+int launch_bn_finalize(const d3fk_bn_params*, cudaStream_t);
+int launch_bn_fold(const d3fk_bn_params*, cudaStream_t);
+int launch_bn_apply(const d3fk_bn_params*, cudaStream_t);
+int launch_bn_bwd_reduce(const d3fk_bn_params*, cudaStream_t);
+int launch_bn_bwd_finalize(const d3fk_bn_params*, cudaStream_t);
+int launch_bn_bwd_apply(const d3fk_bn_params*, cudaStream_t);
+int launch_maxpool_fwd(const d3fk_pool_params*, cudaStream_t);
+int launch_maxpool_bwd(const d3fk_pool_params*, cudaStream_t);
+int launch_sumpool2(const d3fk_pool_params*, cudaStream_t);
+int launch_chansum(const d3fk_chansum_params*, cudaStream_t);
+int launch_qsample(const d3fk_qsample_params*, cudaStream_t);
+int launch_posterior(const d3fk_posterior_params*, cudaStream_t);
+int launch_inc(const d3fk_misc_params*, cudaStream_t);
+int launch_adam(const d3fk_adam_params*, cudaStream_t);
+int tc_init();
+
+static int require_init() {
+  if (g_inited_device < 0) return set_error(D3FK_ERR_ARCH, "d3fk_init() has not succeeded on an sm_100 device");
+  return D3FK_OK;
+}
+
+static int conv_dispatch(const d3fk_conv_params* p, cudaStream_t s) {
+  if (p->dtype == D3FK_F32) return launch_conv_ffma(p, s);
+  if (p->dtype == D3FK_BF16) return launch_conv_tc(p, s);
+  return set_error(D3FK_ERR_ARG, "conv: bad dtype %d", p->dtype);
+}
+static int wgrad_dispatch(const d3fk_wgrad_params* p, cudaStream_t s) {
+  if (p->dtype == D3FK_F32) return launch_wgrad_ffma(p, s);
+  if (p->dtype == D3FK_BF16) return launch_wgrad_tc(p, s);
+  return set_error(D3FK_ERR_ARG, "wgrad: bad dtype %d", p->dtype);
+}
+
+static int run_one(const d3fk_op* op, cudaStream_t s) {
+  switch (op->kind) {
+    case D3FK_OP_CONV: return conv_dispatch(&op->u.conv, s);
+    case D3FK_OP_WGRAD: return wgrad_dispatch(&op->u.wgrad, s);
+    case D3FK_OP_PACK: return launch_pack(&op->u.pack, s);
+    case D3FK_OP_NCHW2NHWC: return launch_nchw_to_nhwc(&op->u.layout, s);
+    case D3FK_OP_BN_FINALIZE: return launch_bn_finalize(&op->u.bn, s);
+    case D3FK_OP_BN_APPLY: return launch_bn_apply(&op->u.bn, s);
+    case D3FK_OP_BN_FOLD: return launch_bn_fold(&op->u.bn, s);
+    case D3FK_OP_BN_BWD_REDUCE: return launch_bn_bwd_reduce(&op->u.bn, s);
+    case D3FK_OP_BN_BWD_FINALIZE: return launch_bn_bwd_finalize(&op->u.bn, s);
+    case D3FK_OP_BN_BWD_APPLY: return launch_bn_bwd_apply(&op->u.bn, s);
+    case D3FK_OP_MAXPOOL_FWD: return launch_maxpool_fwd(&op->u.pool, s);
+    case D3FK_OP_MAXPOOL_BWD: return launch_maxpool_bwd(&op->u.pool, s);
+    case D3FK_OP_SUMPOOL2: return launch_sumpool2(&op->u.pool, s);
+    case D3FK_OP_CHANSUM: return launch_chansum(&op->u.chansum, s);
+    case D3FK_OP_QSAMPLE: return launch_qsample(&op->u.qsample, s);
+    case D3FK_OP_POSTERIOR: return launch_posterior(&op->u.posterior, s);
+    case D3FK_OP_MEMSET: {
+      cudaError_t e = cudaMemsetAsync(op->u.misc.p0, 0, (size_t)op->u.misc.n, s);
+      if (e != cudaSuccess) return set_error(D3FK_ERR_CUDA, "memset: %s", cudaGetErrorString(e));
+      return D3FK_OK;
+    }
+    case D3FK_OP_INC: return launch_inc(&op->u.misc, s);
+    case D3FK_OP_ADAM: return launch_adam(&op->u.adam, s);
+    default: return set_error(D3FK_ERR_ARG, "unknown op kind %d", op->kind);
+  }
+}
+
+}  // namespace d3fk
+
+using namespace d3fk;
+
+extern "C" {
+
+int d3fk_version(void) { return 1; }
+int d3fk_sizeof_op(void) { return (int)sizeof(d3fk_op); }
+const char* d3fk_last_error(void) { return g_last_error; }
+int64_t d3fk_launch_count(void) { return g_launch_count; }
+
+int d3fk_init(int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return set_error(D3FK_ERR_ARCH, "no CUDA device (%s); libd3fk has no CPU path", cudaGetErrorString(e));
+  }
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) return set_error(D3FK_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+  if (prop.major != 10) return set_error(D3FK_ERR_ARCH, "device %d is sm_%d%d; libd3fk is sm_100a only", device, prop.major, prop.minor);
+  if (!g_dev_error_flag) {
+    e = cudaMalloc(&g_dev_error_flag, sizeof(int));
+    if (e != cudaSuccess) return set_error(D3FK_ERR_CUDA, "cudaMalloc: %s", cudaGetErrorString(e));
+    cudaMemset(g_dev_error_flag, 0, sizeof(int));
+  }
+  int rc = tc_init();
+  if (rc) return rc;
+  g_inited_device = device;
+  return D3FK_OK;
+}
+
+int d3fk_device_error_flag(void) {
+  if (!g_dev_error_flag) return 0;
+  int v = 0;
+  cudaMemcpy(&v, g_dev_error_flag, sizeof(int), cudaMemcpyDeviceToHost);
+  return v;
+}
+
+int d3fk_run(const d3fk_op* ops, int n_ops, d3fk_stream stream) {
+  int rc = require_init();
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  for (int i = 0; i < n_ops; ++i) {
+    rc = run_one(&ops[i], s);
+    if (rc) {
+      char tmp[400];
+      strncpy(tmp, g_last_error, sizeof(tmp) - 1);
+      tmp[sizeof(tmp) - 1] = 0;
+      return set_error(rc, "op %d (kind %d): %s", i, ops[i].kind, tmp);
+    }
+  }
+  return D3FK_OK;
+}
+
+#define SINGLE(name, type, fn)                                   \
+  int name(const type* p, d3fk_stream stream) {                  \
+    int rc = require_init();                                     \
+    if (rc) return rc;                                           \
+    return fn(p, (cudaStream_t)stream);                          \
+  }
+SINGLE(d3fk_conv, d3fk_conv_params, conv_dispatch)
+SINGLE(d3fk_wgrad, d3fk_wgrad_params, wgrad_dispatch)
+SINGLE(d3fk_pack_weights, d3fk_pack_params, launch_pack)
+SINGLE(d3fk_nchw_to_nhwc, d3fk_layout_params, launch_nchw_to_nhwc)
+SINGLE(d3fk_bn_finalize, d3fk_bn_params, launch_bn_finalize)
+SINGLE(d3fk_bn_apply, d3fk_bn_params, launch_bn_apply)
+SINGLE(d3fk_bn_fold, d3fk_bn_params, launch_bn_fold)
+SINGLE(d3fk_bn_bwd_reduce, d3fk_bn_params, launch_bn_bwd_reduce)
+SINGLE(d3fk_bn_bwd_finalize, d3fk_bn_params, launch_bn_bwd_finalize)
+SINGLE(d3fk_bn_bwd_apply, d3fk_bn_params, launch_bn_bwd_apply)
+SINGLE(d3fk_maxpool_fwd, d3fk_pool_params, launch_maxpool_fwd)
+SINGLE(d3fk_maxpool_bwd, d3fk_pool_params, launch_maxpool_bwd)
+SINGLE(d3fk_sumpool2, d3fk_pool_params, launch_sumpool2)
+SINGLE(d3fk_chansum, d3fk_chansum_params, launch_chansum)
+SINGLE(d3fk_q_sample, d3fk_qsample_params, launch_qsample)
+SINGLE(d3fk_posterior_step, d3fk_posterior_params, launch_posterior)
+SINGLE(d3fk_adam, d3fk_adam_params, launch_adam)
+
+}  // extern "C"

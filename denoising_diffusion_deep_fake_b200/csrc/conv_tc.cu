@@ -1,0 +1,629 @@
+// conv_tc.cu — bf16 implicit-GEMM convolution, dgrad and wgrad on the Blackwell 5th-gen tensor
+// cores: tcgen05.mma issued by one elected thread, accumulators in TMEM, operands staged in
+// 128B-swizzled shared memory by an asynchronous gather (cp.async completing on mbarriers),
+// tcgen05.ld epilogue fused with BN-statistics / folded-BN affine / residual / ReLU.
+//
+// Forward / dgrad:  D[M = B*Ho*Wo pixels, N = Cout] = A[M, K = taps*Cin] x W[N, K]^T     (both K-major)
+// Weight gradient:  D[M = 128 k-rows, N = Cout]     = A[pixels, k]^T x dY[pixels, Cout]  (both MN-major)
+//
+// Warp roles (160 threads): warps 0-3 = gather producers, then epilogue (TMEM lane quarter = warp);
+// warp 4 = TMEM allocator + single-thread MMA issuer.
+#include "common.cuh"
+
+namespace d3fk {
+
+typedef __nv_bfloat16 bf16;
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// arrive-on triggered when all prior cp.async of this thread have landed (pending count +1 now, -1 then)
+__device__ __forceinline__ void cp_async_mbar_arrive(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+// bounded wait: a barrier that never completes sets the device error flag instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* errflag) {
+  for (uint32_t it = 0;; ++it) {
+    if (mbar_try_wait(bar, parity)) return;
+    if (it > (1u << 20)) {
+      atomicExch(errflag, 1);
+      return;
+    }
+  }
+}
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint32_t bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrive once all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout), SWIZZLE_128B, version 1.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+  return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): bf16 x bf16 -> f32, M x N, majors selectable.
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// transpose-reduce: on return lane l holds the sum over the 32 lanes of v[l]
+__device__ __forceinline__ float warp_colsum32(float* v, int lane) {
+#pragma unroll
+  for (int ofs = 16, n = 32; ofs >= 1; ofs >>= 1, n >>= 1) {
+    const bool up = (lane & ofs) != 0;
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) {
+      float send = up ? v[i] : v[i + n / 2];
+      float keep = up ? v[i + n / 2] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, ofs);
+    }
+  }
+  return v[0];
+}
+// 16 columns: lanes l and l+16 both end with the sum of column (l & 15)
+__device__ __forceinline__ float warp_colsum16(float* v, int lane) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], 16);
+#pragma unroll
+  for (int ofs = 8, n = 16; ofs >= 1; ofs >>= 1, n >>= 1) {
+    const bool up = (lane & ofs) != 0;
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) {
+      float send = up ? v[i] : v[i + n / 2];
+      float keep = up ? v[i + n / 2] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, ofs);
+    }
+  }
+  return v[0];
+}
+
+struct EpiTC {
+  bf16* out; float* out_nchw; const float* scale; const float* shift; const bf16* res; double* stats;
+  int ldo, ldr, relu, Cout, Ho, Wo;
+};
+
+constexpr int TC_THREADS = 160;
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;                 // bf16 elements = 128 bytes = one swizzle row
+constexpr int A_STAGE_BYTES = TC_BM * 128;
+
+template <int BN> struct ConvCfg {
+  static constexpr int STAGES = BN >= 128 ? 3 : 4;
+  static constexpr int B_STAGE_BYTES = BN * 128;
+  static constexpr int SMEM = 1024 + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256 + 2 * BN * 4;
+  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+};
+
+// ------------------------------------------------------------------------------------------
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(Gather g, const bf16* __restrict__ w, EpiTC e, int* errflag) {
+  using Cfg = ConvCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_base = base;
+  const uint32_t b_base = base + STAGES * A_STAGE_BYTES;
+  const uint32_t bar_base = b_base + STAGES * Cfg::B_STAGE_BYTES;  // full[S], empty[S], accum, tmem ptr
+  uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+  uint8_t* gen_bar = gen_base + STAGES * (A_STAGE_BYTES + Cfg::B_STAGE_BYTES);
+  volatile uint32_t* tmem_ptr_slot = reinterpret_cast<volatile uint32_t*>(gen_bar + 8 * (2 * STAGES + 1));
+  float* s_stat = reinterpret_cast<float*>(gen_bar + 256);  // [2][BN]
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  const uint32_t accum_bar = bar_base + 8u * (2 * STAGES);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * BN;
+  const int nkb = (g.K + TC_BK - 1) / TC_BK;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 128);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(accum_bar, 1);
+    fence_barrier_init();
+  }
+  if (tid < 2 * BN) s_stat[tid] = 0.f;
+  if (BN > 64 && tid + TC_THREADS < 2 * BN) s_stat[tid + TC_THREADS] = 0.f;
+  if (warp == 4) tmem_alloc(smem_u32((const void*)tmem_ptr_slot), Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_ptr_slot;
+
+  if (warp < 4) {
+    // ===================== producers: asynchronous swizzled gather =====================
+    const int j = tid & 7;    // 16-byte chunk (8 channels) within the 128-byte k-row
+    const int rb = tid >> 3;  // rows rb + 16*i
+    const uint32_t sw = (uint32_t)((j ^ (rb & 7)) << 4);
+    int rn[8], rh[8], rw[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int m = m0 + rb + 16 * i;
+      if (m < g.M) {
+        int wo = m % g.Wo;
+        int t = m / g.Wo;
+        int ho = t % g.Ho;
+        rn[i] = t / g.Ho;
+        if (g.mode == 0) { rh[i] = ho * g.stride - g.pad; rw[i] = wo * g.stride - g.pad; }
+        else { rh[i] = ho + g.pad; rw[i] = wo + g.pad; }
+      } else {
+        rn[i] = -1; rh[i] = 0; rw[i] = 0;
+      }
+    }
+    int k = j * 8;
+    int tap = k / g.ctot;
+    int c = k - tap * g.ctot;
+    int khi = tap / g.kw, kwi = tap - khi * g.kw;
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % STAGES;
+      if (kb >= STAGES) mbar_wait(empty_bar(s), ((kb / STAGES) - 1) & 1, errflag);
+      const bool k_ok = k < g.K;
+      const uint32_t a_dst = a_base + s * A_STAGE_BYTES + rb * 128 + sw;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const void* src = g.src0;
+        uint32_t bytes = 0;
+        if (k_ok && rn[i] >= 0) {
+          int which;
+          long long off = gather_offset(g, rn[i], rh[i], rw[i], khi, kwi, c, which);
+          if (off >= 0) {
+            src = (which ? (const bf16*)g.src1 : (const bf16*)g.src0) + off;
+            bytes = 16;
+          }
+        }
+        cp_async_16(a_dst + i * (16 * 128), src, bytes);
+      }
+      const uint32_t b_dst = b_base + s * Cfg::B_STAGE_BYTES + rb * 128 + sw;
+#pragma unroll
+      for (int i = 0; i < BN / 16; ++i) {
+        int n = n0 + rb + 16 * i;
+        bool ok = k_ok && n < e.Cout;
+        const void* src = ok ? (const void*)(w + (long long)n * g.K + k) : (const void*)w;
+        cp_async_16(b_dst + i * (16 * 128), src, ok ? 16u : 0u);
+      }
+      cp_async_mbar_arrive(full_bar(s));
+      mbar_arrive(full_bar(s));
+      // advance the k state by one 64-wide block
+      k += TC_BK;
+      c += TC_BK;
+      while (c >= g.ctot) {
+        c -= g.ctot;
+        if (++kwi == g.kw) { kwi = 0; ++khi; }
+      }
+    }
+
+    // ===================== epilogue: TMEM -> registers -> global =====================
+    mbar_wait(accum_bar, 0, errflag);
+    tc_fence_after();
+    const int row = warp * 32 + lane;
+    const int m = m0 + row;
+    const bool row_ok = m < g.M;
+    constexpr int CW = BN >= 32 ? 32 : 16;
+    int on = 0, oh = 0, ow = 0;
+    if (e.out_nchw && row_ok) {
+      ow = m % e.Wo;
+      int t = m / e.Wo;
+      oh = t % e.Ho;
+      on = t / e.Ho;
+    }
+#pragma unroll 1
+    for (int cc = 0; cc < BN; cc += CW) {
+      uint32_t raw[CW];
+      const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)cc;
+      if (CW == 32) tmem_ld32(taddr, raw); else tmem_ld16(taddr, raw);
+      tmem_ld_wait();
+      float f[CW];
+#pragma unroll
+      for (int i = 0; i < CW; ++i) f[i] = __uint_as_float(raw[i]);
+      const int cbase = n0 + cc;
+      if (e.scale) {
+#pragma unroll
+        for (int i = 0; i < CW; ++i)
+          if (cbase + i < e.Cout) f[i] = fmaf(f[i], __ldg(e.scale + cbase + i), __ldg(e.shift + cbase + i));
+      } else if (e.shift) {
+#pragma unroll
+        for (int i = 0; i < CW; ++i)
+          if (cbase + i < e.Cout) f[i] += __ldg(e.shift + cbase + i);
+      }
+      if (e.res && row_ok) {
+        const uint4* rp = reinterpret_cast<const uint4*>(e.res + (long long)m * e.ldr + cbase);
+#pragma unroll
+        for (int q = 0; q < CW / 8; ++q) {
+          uint4 rr = __ldg(rp + q);
+          const bf16* rb16 = reinterpret_cast<const bf16*>(&rr);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[q * 8 + i] += __bfloat162float(rb16[i]);
+        }
+      }
+      if (e.relu) {
+#pragma unroll
+        for (int i = 0; i < CW; ++i) f[i] = fmaxf(f[i], 0.f);
+      }
+      if (row_ok) {
+        if (e.out_nchw) {
+#pragma unroll
+          for (int i = 0; i < CW; ++i)
+            if (cbase + i < e.Cout) e.out_nchw[(((long long)on * e.Cout + cbase + i) * e.Ho + oh) * e.Wo + ow] = f[i];
+        } else {
+          uint4* op = reinterpret_cast<uint4*>(e.out + (long long)m * e.ldo + cbase);
+#pragma unroll
+          for (int q = 0; q < CW / 8; ++q) {
+            uint4 o;
+            __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o2[i] = __floats2bfloat162_rn(f[q * 8 + 2 * i], f[q * 8 + 2 * i + 1]);
+            op[q] = o;
+          }
+        }
+      }
+      if (e.stats) {
+        float sq[CW];
+#pragma unroll
+        for (int i = 0; i < CW; ++i) {
+          if (!row_ok) f[i] = 0.f;
+          sq[i] = f[i] * f[i];
+        }
+        float cs, cq;
+        if (CW == 32) { cs = warp_colsum32(f, lane); cq = warp_colsum32(sq, lane); }
+        else { cs = warp_colsum16(f, lane); cq = warp_colsum16(sq, lane); }
+        if (lane < CW) {
+          atomicAdd(&s_stat[cc + lane], cs);
+          atomicAdd(&s_stat[BN + cc + lane], cq);
+        }
+      }
+    }
+    if (e.stats) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (tid < BN && n0 + tid < e.Cout) {
+        atomicAdd(&e.stats[n0 + tid], (double)s_stat[tid]);
+        atomicAdd(&e.stats[e.Cout + n0 + tid], (double)s_stat[BN + tid]);
+      }
+    }
+  } else {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(TC_BM, BN, 0, 0);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        mbar_wait(full_bar(s), (kb / STAGES) & 1, errflag);
+        fence_proxy_async();
+        tc_fence_after();
+        const uint32_t a_addr = a_base + s * A_STAGE_BYTES;
+        const uint32_t b_addr = b_base + s * Cfg::B_STAGE_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < TC_BK / 16; ++kk) {
+          uint64_t ad = make_smem_desc(a_addr + kk * 32, 16, 1024);
+          uint64_t bd = make_smem_desc(b_addr + kk * 32, 16, 1024);
+          umma_f16(tmem_d, ad, bd, idesc, (kb | kk) ? 1u : 0u);
+        }
+        umma_commit(empty_bar(s));
+      }
+      umma_commit(accum_bar);
+    }
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_d, Cfg::TMEM_COLS);
+}
+
+template <int BN>
+static int launch_conv_tc_bn(const Gather& g, const d3fk_conv_params* p, cudaStream_t s) {
+  EpiTC e{(bf16*)p->out, p->out_nchw, p->scale, p->shift, (const bf16*)p->res, p->stats, p->ldo, p->ldr, p->relu, p->Cout, p->Ho, p->Wo};
+  dim3 grid(cdiv(g.M, TC_BM), cdiv(p->Cout, BN));
+  conv_tc_kernel<BN><<<grid, TC_THREADS, ConvCfg<BN>::SMEM, s>>>(g, (const bf16*)p->w, e, g_dev_error_flag);
+  count_launch();
+  return check_launch("conv_tc");
+}
+
+int launch_conv_tc(const d3fk_conv_params* p, cudaStream_t s) {
+  Gather g;
+  int rc = make_gather(g, p->src0, p->src1, p->c0, p->c1, p->ld0, p->ld1, p->up0, p->B, p->Hi, p->Wi, p->Ho, p->Wo, p->kh,
+                       p->kw, p->stride, p->pad, p->mode);
+  if (rc) return rc;
+  D3FK_CHECK_ARG(p->out || p->out_nchw, "no output");
+  D3FK_CHECK_ARG(p->out_nchw || (p->ldo % 8 == 0), "ldo must be a multiple of 8");
+  D3FK_CHECK_ARG(!p->scale || p->shift, "scale requires shift");
+  const int C = p->Cout;
+  if (C <= 16) return launch_conv_tc_bn<16>(g, p, s);
+  D3FK_CHECK_ARG(p->out_nchw == nullptr, "out_nchw only for Cout <= 16");
+  if (C % 128 == 0) return launch_conv_tc_bn<128>(g, p, s);
+  if (C % 64 == 0) return launch_conv_tc_bn<64>(g, p, s);
+  if (C % 32 == 0) return launch_conv_tc_bn<32>(g, p, s);
+  return set_error(D3FK_ERR_UNSUPPORTED, "conv_tc: Cout=%d (need <=16 or a multiple of 32)", C);
+}
+
+// ------------------------------------------------------------------------------------------
+// weight gradient.  Stage = 64 pixels (the MMA K dimension, 4 x K16).
+//   A stage: 2 column blocks (64 k-columns each) x [64 pixels x 128 B]   (MN-major, M = k index)
+//   B stage: BN/64 column blocks (64 channels each) x [64 pixels x 128 B] (MN-major, N = co)
+struct FastDiv {
+  uint32_t mul, shr;
+};
+static FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f;
+  uint32_t l = 0;
+  while ((1ull << l) < d) ++l;
+  f.shr = l;
+  f.mul = (uint32_t)(((1ull << 32) * ((1ull << l) - d)) / d + 1);
+  return f;
+}
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, FastDiv f) { return (__umulhi(f.mul, n) + n) >> f.shr; }
+
+constexpr int WG_PIX = 64;
+constexpr int WG_A_STAGE = 2 * WG_PIX * 128;
+template <int BN> struct WgradCfg {
+  static constexpr int STAGES = 4;
+  static constexpr int NCB = BN / 64;
+  static constexpr int B_STAGE = NCB * WG_PIX * 128;
+  static constexpr int SMEM = 1024 + STAGES * (WG_A_STAGE + B_STAGE) + 256;
+  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS) wgrad_tc_kernel(Gather g, FastDiv dWo, FastDiv dHo, const bf16* __restrict__ dy,
+                                                              int ldy, int Cout, float* __restrict__ dw, int cin_real,
+                                                              int cout_real, int blocks_per_split, int lbo_a, int lbo_b,
+                                                              int* errflag) {
+  using Cfg = WgradCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_base = base;
+  const uint32_t b_base = base + STAGES * WG_A_STAGE;
+  const uint32_t bar_base = b_base + STAGES * Cfg::B_STAGE;
+  uint8_t* gen_bar = smem_raw + (base - smem_u32(smem_raw)) + STAGES * (WG_A_STAGE + Cfg::B_STAGE);
+  volatile uint32_t* tmem_ptr_slot = reinterpret_cast<volatile uint32_t*>(gen_bar + 8 * (2 * STAGES + 1));
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  const uint32_t accum_bar = bar_base + 8u * (2 * STAGES);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int k0 = blockIdx.x * 128, co0 = blockIdx.y * BN;
+  const int nblk_total = (g.M + WG_PIX - 1) / WG_PIX;
+  const int blk_beg = blockIdx.z * blocks_per_split;
+  const int blk_end = min(nblk_total, blk_beg + blocks_per_split);
+  const int nblk = max(0, blk_end - blk_beg);
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 128);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(accum_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc(smem_u32((const void*)tmem_ptr_slot), Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_ptr_slot;
+
+  if (warp < 4) {
+    const int j = tid & 7;
+    const int rb = tid >> 3;  // pixel rows rb + 16*i, i < 4
+    const uint32_t sw = (uint32_t)((j ^ (rb & 7)) << 4);
+    // the two k chunks (column blocks 0/1) this thread gathers are fixed for the whole kernel
+    int kc[2], kkh[2], kkw[2];
+    bool kok[2];
+#pragma unroll
+    for (int cb = 0; cb < 2; ++cb) {
+      int k = k0 + cb * 64 + j * 8;
+      kok[cb] = k < g.K;
+      int tap = kok[cb] ? k / g.ctot : 0;
+      kc[cb] = kok[cb] ? k - tap * g.ctot : 0;
+      kkh[cb] = tap / g.kw;
+      kkw[cb] = tap - kkh[cb] * g.kw;
+    }
+    for (int it = 0; it < nblk; ++it) {
+      const int s = it % STAGES;
+      if (it >= STAGES) mbar_wait(empty_bar(s), ((it / STAGES) - 1) & 1, errflag);
+      const int mbase = (blk_beg + it) * WG_PIX;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int prow = rb + 16 * i;
+        const int m = mbase + prow;
+        const bool m_ok = m < g.M;
+        int n = 0, ho = 0, wo = 0;
+        if (m_ok) {
+          uint32_t t = fdiv((uint32_t)m, dWo);
+          wo = m - (int)t * g.Wo;
+          n = (int)fdiv(t, dHo);
+          ho = (int)t - n * g.Ho;
+        }
+        const int h0 = ho * g.stride - g.pad, w0 = wo * g.stride - g.pad;
+#pragma unroll
+        for (int cb = 0; cb < 2; ++cb) {
+          const void* src = g.src0;
+          uint32_t bytes = 0;
+          if (m_ok && kok[cb]) {
+            int which;
+            long long off = gather_offset(g, n, h0, w0, kkh[cb], kkw[cb], kc[cb], which);
+            if (off >= 0) {
+              src = (which ? (const bf16*)g.src1 : (const bf16*)g.src0) + off;
+              bytes = 16;
+            }
+          }
+          cp_async_16(a_base + s * WG_A_STAGE + cb * (WG_PIX * 128) + prow * 128 + sw, src, bytes);
+        }
+#pragma unroll
+        for (int cb = 0; cb < Cfg::NCB; ++cb) {
+          const int co = co0 + cb * 64 + j * 8;
+          const bool ok = m_ok && co < Cout;
+          const void* src = ok ? (const void*)(dy + (long long)m * ldy + co) : (const void*)dy;
+          cp_async_16(b_base + s * Cfg::B_STAGE + cb * (WG_PIX * 128) + prow * 128 + sw, src, ok ? 16u : 0u);
+        }
+      }
+      cp_async_mbar_arrive(full_bar(s));
+      mbar_arrive(full_bar(s));
+    }
+
+    // epilogue: D[k row][co col] -> atomic add into fp32 OIHW dw
+    if (nblk > 0) {
+      mbar_wait(accum_bar, 0, errflag);
+      tc_fence_after();
+      const int k = k0 + warp * 32 + lane;
+      const bool k_ok = k < g.K;
+      int tap = 0, ci = 0;
+      if (k_ok) { tap = k / g.ctot; ci = k - tap * g.ctot; }
+      const bool row_ok = k_ok && ci < cin_real;
+      const int taps = g.kh * g.kw;
+      constexpr int CW = BN >= 32 ? 32 : 16;
+#pragma unroll 1
+      for (int cc = 0; cc < BN; cc += CW) {
+        uint32_t raw[CW];
+        const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)cc;
+        if (CW == 32) tmem_ld32(taddr, raw); else tmem_ld16(taddr, raw);
+        tmem_ld_wait();
+        if (row_ok) {
+#pragma unroll
+          for (int i = 0; i < CW; ++i) {
+            int co = co0 + cc + i;
+            if (co < cout_real) atomicAdd(dw + ((long long)co * cin_real + ci) * taps + tap, __uint_as_float(raw[i]));
+          }
+        }
+      }
+    }
+  } else {
+    if (lane == 0 && nblk > 0) {
+      constexpr uint32_t idesc = make_idesc(128, BN, 1, 1);
+      for (int it = 0; it < nblk; ++it) {
+        const int s = it % STAGES;
+        mbar_wait(full_bar(s), (it / STAGES) & 1, errflag);
+        fence_proxy_async();
+        tc_fence_after();
+        const uint32_t a_addr = a_base + s * WG_A_STAGE;
+        const uint32_t b_addr = b_base + s * Cfg::B_STAGE;
+#pragma unroll
+        for (int kk = 0; kk < WG_PIX / 16; ++kk) {
+          uint64_t ad = make_smem_desc(a_addr + kk * (16 * 128), (uint32_t)lbo_a, 1024);
+          uint64_t bd = make_smem_desc(b_addr + kk * (16 * 128), (uint32_t)lbo_b, 1024);
+          umma_f16(tmem_d, ad, bd, idesc, (it | kk) ? 1u : 0u);
+        }
+        umma_commit(empty_bar(s));
+      }
+      umma_commit(accum_bar);
+    }
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_d, Cfg::TMEM_COLS);
+}
+
+template <int BN>
+static int launch_wgrad_tc_bn(const Gather& g, const d3fk_wgrad_params* p, cudaStream_t s) {
+  const int gx = cdiv(g.K, 128), gy = cdiv(p->Cout, BN);
+  const int nblk = cdiv(g.M, WG_PIX);
+  int splits = cdiv(148 * 2, gx * gy);
+  if (splits > nblk) splits = nblk;
+  if (splits < 1) splits = 1;
+  int bps = cdiv(nblk, splits);
+  splits = cdiv(nblk, bps);
+  dim3 grid(gx, gy, splits);
+  wgrad_tc_kernel<BN><<<grid, TC_THREADS, WgradCfg<BN>::SMEM, s>>>(
+      g, make_fastdiv((uint32_t)g.Wo), make_fastdiv((uint32_t)g.Ho), (const bf16*)p->dy, p->ldy, p->Cout, p->dw, p->cin_real,
+      p->cout_real, bps, WG_PIX * 128, WG_PIX * 128, g_dev_error_flag);
+  count_launch();
+  return check_launch("wgrad_tc");
+}
+
+int launch_wgrad_tc(const d3fk_wgrad_params* p, cudaStream_t s) {
+  Gather g;
+  int rc = make_gather(g, p->src0, p->src1, p->c0, p->c1, p->ld0, p->ld1, p->up0, p->B, p->Hi, p->Wi, p->Ho, p->Wo, p->kh,
+                       p->kw, p->stride, p->pad, 0);
+  if (rc) return rc;
+  D3FK_CHECK_ARG(p->Cout % 8 == 0 && p->ldy % 8 == 0, "Cout and ldy must be multiples of 8");
+  if (p->Cout > 64) return launch_wgrad_tc_bn<128>(g, p, s);
+  return launch_wgrad_tc_bn<64>(g, p, s);
+}
+
+int tc_init() {
+  cudaError_t e = cudaSuccess;
+#define SET_SMEM(k, bytes)                                                                          \
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  SET_SMEM(conv_tc_kernel<16>, ConvCfg<16>::SMEM)
+  SET_SMEM(conv_tc_kernel<32>, ConvCfg<32>::SMEM)
+  SET_SMEM(conv_tc_kernel<64>, ConvCfg<64>::SMEM)
+  SET_SMEM(conv_tc_kernel<128>, ConvCfg<128>::SMEM)
+  SET_SMEM(wgrad_tc_kernel<64>, WgradCfg<64>::SMEM)
+  SET_SMEM(wgrad_tc_kernel<128>, WgradCfg<128>::SMEM)
+#undef SET_SMEM
+  if (e != cudaSuccess) return set_error(D3FK_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  return D3FK_OK;
+}
+
+}  // namespace d3fk

@@ -1,0 +1,529 @@
+// elementwise.cu — bandwidth-bound passes of the d3f U-Net hot path (sm_100a).
+//   BatchNorm(+residual)+ReLU apply / backward, statistics finalisation, max-pool, 2x2 sum-pool,
+//   layout conversion, q_sample, posterior update, fused Adam(+EMA).
+// All tensors are NHWC with 16-byte vector access (C is a multiple of 8); grids are sized in
+// multiples of the SM count and loop grid-stride.
+#include "common.cuh"
+
+namespace d3fk {
+
+static constexpr int kSMs = 148;
+static inline int grid_for(long long work_items, int threads, int max_waves = 8) {
+  long long blocks = (work_items + threads - 1) / threads;
+  long long cap = (long long)kSMs * max_waves;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+// ---------------------------------------------------------------------------------------------
+// NCHW fp32 -> NHWC T, channels zero-padded to cpad (a multiple of 8)
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, T* __restrict__ dst, int B, int C, int HW, int cpad) {
+  long long total = (long long)B * HW;
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < total; p += (long long)gridDim.x * blockDim.x) {
+    long long n = p / HW;
+    long long hw = p - n * HW;
+    const float* s = src + (n * C) * HW + hw;
+    T* d = dst + p * cpad;
+    constexpr int V = Vec<T>::N;
+    for (int c0 = 0; c0 < cpad; c0 += V) {
+      float v[V];
+#pragma unroll
+      for (int i = 0; i < V; ++i) v[i] = (c0 + i < C) ? __ldg(s + (long long)(c0 + i) * HW) : 0.f;
+      store_vec<T>(d + c0, v);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// BN statistics -> scale/shift, saved mean/invstd, running-stat update (momentum, unbiased var)
+__global__ void bn_finalize_kernel(d3fk_bn_params p) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= p.C) return;
+  double n = (double)p.count;
+  double mean = p.stats[c] / n;
+  double var = p.stats[p.C + c] / n - mean * mean;
+  if (var < 0) var = 0;
+  double invstd = 1.0 / sqrt(var + (double)p.eps);
+  float g = p.gamma[c], b = p.beta[c];
+  float sc = (float)((double)g * invstd);
+  p.scale[c] = sc;
+  p.shift[c] = (float)((double)b - mean * (double)g * invstd);
+  p.mean[c] = (float)mean;
+  p.invstd[c] = (float)invstd;
+  if (p.running_mean) {
+    double unbiased = n > 1 ? var * n / (n - 1) : var;
+    p.running_mean[c] = (float)((1.0 - p.momentum) * p.running_mean[c] + p.momentum * mean);
+    p.running_var[c] = (float)((1.0 - p.momentum) * p.running_var[c] + p.momentum * unbiased);
+  }
+  if (c == 0 && p.num_batches_tracked) *p.num_batches_tracked += 1;
+}
+
+// eval mode: scale/shift from running statistics (folded into the conv epilogue)
+__global__ void bn_fold_kernel(d3fk_bn_params p) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= p.C) return;
+  float invstd = 1.0f / sqrtf(p.running_var[c] + p.eps);
+  float sc = p.gamma[c] * invstd;
+  p.scale[c] = sc;
+  p.shift[c] = p.beta[c] - p.running_mean[c] * sc;
+}
+
+// y = relu?(x*scale + shift + res)
+template <typename T>
+__global__ void bn_apply_kernel(d3fk_bn_params p) {
+  constexpr int V = Vec<T>::N;
+  const int cvs = p.C / V;
+  const long long total = p.count * cvs;
+  const T* x = (const T*)p.x;
+  T* y = (T*)p.y;
+  const T* res = (const T*)p.res;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    long long pix = e / cvs;
+    int c = (int)(e - pix * cvs) * V;
+    float v[V], r[V];
+    load_vec<T>(x + pix * p.ldx + c, v);
+    float4 sc[V / 4], sh[V / 4];
+#pragma unroll
+    for (int i = 0; i < V / 4; ++i) {
+      sc[i] = __ldg(reinterpret_cast<const float4*>(p.scale + c) + i);
+      sh[i] = __ldg(reinterpret_cast<const float4*>(p.shift + c) + i);
+    }
+    const float* scf = reinterpret_cast<const float*>(sc);
+    const float* shf = reinterpret_cast<const float*>(sh);
+    if (res) load_vec<T>(res + pix * p.ldr + c, r);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      float t = fmaf(v[i], scf[i], shf[i]);
+      if (res) t += r[i];
+      if (p.relu) t = fmaxf(t, 0.f);
+      v[i] = t;
+    }
+    store_vec<T>(y + pix * p.ldy + c, v);
+  }
+}
+
+// per-channel sums of dy' and dy'*xhat ; dy' = relu ? (act>0 ? dy : 0) : dy
+template <typename T, typename Acc>
+__global__ void bn_bwd_reduce_kernel(d3fk_bn_params p) {
+  constexpr int V = Vec<T>::N;
+  extern __shared__ double sred[];  // [2][C]
+  const int C = p.C, cvs = C / V;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sred[i] = 0.0;
+  __syncthreads();
+  const int rows_per_iter = blockDim.x / cvs;
+  const int cv = threadIdx.x % cvs, prow = threadIdx.x / cvs;
+  const int c = cv * V;
+  Acc s1[V], s2[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) { s1[i] = 0; s2[i] = 0; }
+  if (prow < rows_per_iter) {
+    float mean[V], istd[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) { mean[i] = p.mean[c + i]; istd[i] = p.invstd[c + i]; }
+    const T* x = (const T*)p.x;
+    const T* dy = (const T*)p.dy;
+    const T* act = (const T*)p.act;
+    for (long long pix = (long long)blockIdx.x * rows_per_iter + prow; pix < p.count;
+         pix += (long long)gridDim.x * rows_per_iter) {
+      float xv[V], gv[V], av[V];
+      load_vec<T>(x + pix * p.ldx + c, xv);
+      load_vec<T>(dy + pix * p.lddy + c, gv);
+      if (p.relu) load_vec<T>(act + pix * p.ldact + c, av);
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        float g = gv[i];
+        if (p.relu && !(av[i] > 0.f)) g = 0.f;
+        float xh = (xv[i] - mean[i]) * istd[i];
+        s1[i] += (Acc)g;
+        s2[i] += (Acc)(g * xh);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      atomicAdd(&sred[c + i], (double)s1[i]);
+      atomicAdd(&sred[C + c + i], (double)s2[i]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&p.bstats[i], sred[i]);
+}
+
+__global__ void bn_bwd_finalize_kernel(d3fk_bn_params p) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= p.C) return;
+  double n = (double)p.count;
+  double s1 = p.bstats[c], s2 = p.bstats[p.C + c];
+  if (p.dbeta) p.dbeta[c] = (float)s1;
+  if (p.dgamma) p.dgamma[c] = (float)s2;
+  p.coef[c] = p.gamma[c] * p.invstd[c];
+  p.coef[p.C + c] = (float)(s1 / n);
+  p.coef[2 * p.C + c] = (float)(s2 / n);
+}
+
+// dx = c0*(dy' - c1 - xhat*c2); optionally dres = dy'
+template <typename T>
+__global__ void bn_bwd_apply_kernel(d3fk_bn_params p) {
+  constexpr int V = Vec<T>::N;
+  const int cvs = p.C / V;
+  const long long total = p.count * cvs;
+  const T* x = (const T*)p.x;
+  const T* dy = (const T*)p.dy;
+  const T* act = (const T*)p.act;
+  T* dx = (T*)p.dx;
+  T* dres = (T*)p.dres;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    long long pix = e / cvs;
+    int c = (int)(e - pix * cvs) * V;
+    float xv[V], gv[V], av[V], o[V];
+    load_vec<T>(x + pix * p.ldx + c, xv);
+    load_vec<T>(dy + pix * p.lddy + c, gv);
+    if (p.relu) load_vec<T>(act + pix * p.ldact + c, av);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      float g = gv[i];
+      if (p.relu && !(av[i] > 0.f)) g = 0.f;
+      gv[i] = g;
+      float xh = (xv[i] - __ldg(p.mean + c + i)) * __ldg(p.invstd + c + i);
+      o[i] = __ldg(p.coef + c + i) * (g - __ldg(p.coef + p.C + c + i) - xh * __ldg(p.coef + 2 * p.C + c + i));
+    }
+    store_vec<T>(dx + pix * p.lddx + c, o);
+    if (dres) store_vec<T>(dres + pix * p.lddres + c, gv);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// MaxPool2d(kernel 3, stride 2, pad 1): first-max tie-break in window scan order (ATen semantics)
+template <typename T>
+__global__ void maxpool_fwd_kernel(d3fk_pool_params p) {
+  constexpr int V = Vec<T>::N;
+  const int Ho = p.H / 2, Wo = p.W / 2, cvs = p.C / V;
+  const long long total = (long long)p.B * Ho * Wo * cvs;
+  const T* x = (const T*)p.x;
+  T* y = (T*)p.y;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    long long pix = e / cvs;
+    int c = (int)(e - pix * cvs) * V;
+    int wo = (int)(pix % Wo);
+    long long t = pix / Wo;
+    int ho = (int)(t % Ho);
+    int n = (int)(t / Ho);
+    float best[V];
+    unsigned char bi[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) { best[i] = -INFINITY; bi[i] = 0; }
+    bool first = true;
+    for (int kh = 0; kh < 3; ++kh) {
+      int h = 2 * ho - 1 + kh;
+      if ((unsigned)h >= (unsigned)p.H) continue;
+      for (int kw = 0; kw < 3; ++kw) {
+        int w = 2 * wo - 1 + kw;
+        if ((unsigned)w >= (unsigned)p.W) continue;
+        float v[V];
+        load_vec<T>(x + ((long long)(n * p.H + h) * p.W + w) * p.ldx + c, v);
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          if (first || v[i] > best[i] || v[i] != v[i]) { best[i] = v[i]; bi[i] = (unsigned char)(kh * 3 + kw); }
+        }
+        first = false;
+      }
+    }
+    store_vec<T>(y + pix * p.ldy + c, best);
+    if (p.idx) {
+      unsigned char* ip = p.idx + pix * p.C + c;
+#pragma unroll
+      for (int i = 0; i < V; ++i) ip[i] = bi[i];
+    }
+  }
+}
+
+template <typename T>
+__global__ void maxpool_bwd_kernel(d3fk_pool_params p) {
+  constexpr int V = Vec<T>::N;
+  const int Ho = p.H / 2, Wo = p.W / 2, cvs = p.C / V;
+  const long long total = (long long)p.B * p.H * p.W * cvs;
+  const T* dy = (const T*)p.dy;
+  T* dx = (T*)p.dx;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    long long pix = e / cvs;
+    int c = (int)(e - pix * cvs) * V;
+    int w = (int)(pix % p.W);
+    long long t = pix / p.W;
+    int h = (int)(t % p.H);
+    int n = (int)(t / p.H);
+    float g[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) g[i] = 0.f;
+    if (p.accumulate) load_vec<T>(dx + pix * p.lddx + c, g);
+    for (int ho = h / 2; ho <= (h + 1) / 2; ++ho) {
+      if (ho >= Ho) continue;
+      int kh = h - (2 * ho - 1);
+      for (int wo = w / 2; wo <= (w + 1) / 2; ++wo) {
+        if (wo >= Wo) continue;
+        int kw = w - (2 * wo - 1);
+        int tap = kh * 3 + kw;
+        long long op = (long long)(n * Ho + ho) * Wo + wo;
+        float d[V];
+        load_vec<T>(dy + op * p.lddy + c, d);
+        const unsigned char* ip = p.idx + op * p.C + c;
+#pragma unroll
+        for (int i = 0; i < V; ++i)
+          if (ip[i] == tap) g[i] += d[i];
+      }
+    }
+    store_vec<T>(dx + pix * p.lddx + c, g);
+  }
+}
+
+// backward of nearest 2x upsample: dx[n,h,w,c] = sum of the 2x2 block of dy (H,W = low-res extent)
+template <typename T>
+__global__ void sumpool2_kernel(d3fk_pool_params p) {
+  constexpr int V = Vec<T>::N;
+  const int cvs = p.C / V;
+  const long long total = (long long)p.B * p.H * p.W * cvs;
+  const T* dy = (const T*)p.dy;
+  T* dx = (T*)p.dx;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    long long pix = e / cvs;
+    int c = (int)(e - pix * cvs) * V;
+    int w = (int)(pix % p.W);
+    long long t = pix / p.W;
+    int h = (int)(t % p.H);
+    int n = (int)(t / p.H);
+    float g[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) g[i] = 0.f;
+    if (p.accumulate) load_vec<T>(dx + pix * p.lddx + c, g);
+#pragma unroll
+    for (int dh = 0; dh < 2; ++dh)
+#pragma unroll
+      for (int dw = 0; dw < 2; ++dw) {
+        float d[V];
+        load_vec<T>(dy + ((long long)(n * 2 * p.H + 2 * h + dh) * (2 * p.W) + 2 * w + dw) * p.lddy + c, d);
+#pragma unroll
+        for (int i = 0; i < V; ++i) g[i] += d[i];
+      }
+    store_vec<T>(dx + pix * p.lddx + c, g);
+  }
+}
+
+// out[c] += sum over pixels x[pix*ld + c], c < C <= 8
+template <typename T>
+__global__ void chansum_kernel(d3fk_chansum_params p) {
+  constexpr int V = Vec<T>::N;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  const T* x = (const T*)p.x;
+  for (long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x; pix < p.count; pix += (long long)gridDim.x * blockDim.x) {
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = 0.f;
+    load_vec<T>(x + pix * p.ld, v);
+    if (V == 4 && p.C > 4) load_vec<T>(x + pix * p.ld + 4, v + 4);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] += v[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float a = acc[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if ((threadIdx.x & 31) == 0 && i < p.C) atomicAdd(p.out + i, a);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// q_sample: out = sqrt(1-r_b) x + sqrt(r_b) eps   (d3f/train_denoiser/lit_module.py:128-153)
+__global__ void qsample_kernel(d3fk_qsample_params p) {
+  const long long nvec = (long long)p.B * p.chw / 4;
+  const int vec_per_sample = p.chw / 4;
+  const float cexp = __expf(-p.lam);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    int b = (int)(i / vec_per_sample);
+    float r;
+    if (p.fixed_r >= 0.f) {
+      r = p.fixed_r;
+    } else {
+      float y;
+      if (p.y) y = __ldg(p.y + b);
+      else {
+        uint4 u = philox4x32_10(make_uint4((uint32_t)b, 0u, (uint32_t)p.offset, 0x9E3779B9u),
+                                make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
+        y = (float)(u.x >> 8) * (1.0f / 16777216.0f);  // U[0,1) like torch.rand
+      }
+      r = (1.0f / p.lam) * logf(1.0f / (y * (1.0f - cexp) + cexp));
+    }
+    float a = sqrtf(1.0f - r), s = sqrtf(r);
+    float4 x = __ldg(reinterpret_cast<const float4*>(p.x) + i);
+    float4 n;
+    if (p.noise) n = __ldg(reinterpret_cast<const float4*>(p.noise) + i);
+    else n = philox_normal4(p.seed, (uint64_t)i, p.offset);
+    float4 o = make_float4(a * x.x + s * n.x, a * x.y + s * n.y, a * x.z + s * n.z, a * x.w + s * n.w);
+    reinterpret_cast<float4*>(p.out)[i] = o;
+    if (p.noise_out) reinterpret_cast<float4*>(p.noise_out)[i] = n;
+    if (p.r_out && i == (long long)b * vec_per_sample) p.r_out[b] = r;
+  }
+}
+
+// posterior: x = k_xi*x + k_x0*x0_hat + sigma*z
+__global__ void posterior_kernel(d3fk_posterior_params p) {
+  float k_xi = p.k_xi, k_x0 = p.k_x0, sigma = p.sigma;
+  uint64_t off = p.offset;
+  if (p.coef_table) {
+    int s = *p.step;
+    k_xi = p.coef_table[4 * s];
+    k_x0 = p.coef_table[4 * s + 1];
+    sigma = p.coef_table[4 * s + 2];
+    off += (uint64_t)s;
+  }
+  const long long nvec = p.n / 4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    float4 x = reinterpret_cast<const float4*>(p.x)[i];
+    float4 h = __ldg(reinterpret_cast<const float4*>(p.x0_hat) + i);
+    float4 o = make_float4(k_xi * x.x + k_x0 * h.x, k_xi * x.y + k_x0 * h.y, k_xi * x.z + k_x0 * h.z, k_xi * x.w + k_x0 * h.w);
+    if (sigma != 0.f) {
+      float4 z;
+      if (p.z) z = __ldg(reinterpret_cast<const float4*>(p.z) + i);
+      else z = philox_normal4(p.seed, (uint64_t)i, off);
+      o.x += sigma * z.x; o.y += sigma * z.y; o.z += sigma * z.z; o.w += sigma * z.w;
+    }
+    reinterpret_cast<float4*>(p.x)[i] = o;
+  }
+}
+
+__global__ void inc_kernel(int* p) { *p += 1; }
+
+// fused Adam (+ optional EMA lerp) over a flat arena
+__global__ void adam_kernel(d3fk_adam_params p) {
+  const float step = p.lr / p.bias1;
+  const float rsb2 = rsqrtf(p.bias2);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < p.n; i += (long long)gridDim.x * blockDim.x) {
+    float g = p.g[i] * p.grad_scale;
+    float m = p.m[i], v = p.v[i], w = p.p[i];
+    m = m + (1.f - p.beta1) * (g - m);
+    v = p.beta2 * v + (1.f - p.beta2) * g * g;
+    float denom = sqrtf(v) * rsb2 + p.eps;
+    w = w - step * (m / denom);
+    p.m[i] = m; p.v[i] = v; p.p[i] = w;
+    if (p.ema) { float e = p.ema[i]; p.ema[i] = e + (1.f - p.ema_decay) * (w - e); }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// launchers
+#define DISPATCH_T(dtype, ...)                                   \
+  if ((dtype) == D3FK_F32) { using T = float; __VA_ARGS__; }     \
+  else if ((dtype) == D3FK_BF16) { using T = __nv_bfloat16; __VA_ARGS__; } \
+  else return set_error(D3FK_ERR_ARG, "bad dtype %d", (int)(dtype));
+
+int launch_nchw_to_nhwc(const d3fk_layout_params* p, cudaStream_t s) {
+  D3FK_CHECK_ARG(p->cpad % 8 == 0 && p->C <= p->cpad, "cpad must be a multiple of 8 and >= C");
+  long long total = (long long)p->B * p->H * p->W;
+  DISPATCH_T(p->dtype, nchw_to_nhwc_kernel<T><<<grid_for(total, 256), 256, 0, s>>>(p->src, (T*)p->dst, p->B, p->C, p->H * p->W, p->cpad));
+  count_launch();
+  return check_launch("nchw_to_nhwc");
+}
+int launch_bn_finalize(const d3fk_bn_params* p, cudaStream_t s) {
+  bn_finalize_kernel<<<cdiv(p->C, 128), 128, 0, s>>>(*p);
+  count_launch();
+  return check_launch("bn_finalize");
+}
+int launch_bn_fold(const d3fk_bn_params* p, cudaStream_t s) {
+  bn_fold_kernel<<<cdiv(p->C, 128), 128, 0, s>>>(*p);
+  count_launch();
+  return check_launch("bn_fold");
+}
+int launch_bn_apply(const d3fk_bn_params* p, cudaStream_t s) {
+  D3FK_CHECK_ARG(p->C % 8 == 0, "C must be a multiple of 8");
+  int V = p->dtype == D3FK_F32 ? 4 : 8;
+  long long total = p->count * (p->C / V);
+  DISPATCH_T(p->dtype, bn_apply_kernel<T><<<grid_for(total, 256), 256, 0, s>>>(*p));
+  count_launch();
+  return check_launch("bn_apply");
+}
+int launch_bn_bwd_reduce(const d3fk_bn_params* p, cudaStream_t s) {
+  D3FK_CHECK_ARG(p->C % 8 == 0 && p->C <= 2048, "C must be a multiple of 8, <= 2048");
+  int V = p->dtype == D3FK_F32 ? 4 : 8;
+  int cvs = p->C / V;
+  int threads = 256;
+  if (cvs > threads) threads = cvs;
+  int rows = threads / cvs;
+  int grid = grid_for(cdiv(p->count, 4) * (long long)cvs, threads, 4);
+  (void)rows;
+  size_t smem = 2 * p->C * sizeof(double);
+  if (p->dtype == D3FK_F32) bn_bwd_reduce_kernel<float, double><<<grid, threads, smem, s>>>(*p);
+  else if (p->dtype == D3FK_BF16) bn_bwd_reduce_kernel<__nv_bfloat16, float><<<grid, threads, smem, s>>>(*p);
+  else return set_error(D3FK_ERR_ARG, "bad dtype");
+  count_launch();
+  return check_launch("bn_bwd_reduce");
+}
+int launch_bn_bwd_finalize(const d3fk_bn_params* p, cudaStream_t s) {
+  bn_bwd_finalize_kernel<<<cdiv(p->C, 128), 128, 0, s>>>(*p);
+  count_launch();
+  return check_launch("bn_bwd_finalize");
+}
+int launch_bn_bwd_apply(const d3fk_bn_params* p, cudaStream_t s) {
+  D3FK_CHECK_ARG(p->C % 8 == 0, "C must be a multiple of 8");
+  int V = p->dtype == D3FK_F32 ? 4 : 8;
+  long long total = p->count * (p->C / V);
+  DISPATCH_T(p->dtype, bn_bwd_apply_kernel<T><<<grid_for(total, 256), 256, 0, s>>>(*p));
+  count_launch();
+  return check_launch("bn_bwd_apply");
+}
+int launch_maxpool_fwd(const d3fk_pool_params* p, cudaStream_t s) {
+  D3FK_CHECK_ARG(p->C % 8 == 0 && p->H % 2 == 0 && p->W % 2 == 0, "C%8, H%2, W%2");
+  int V = p->dtype == D3FK_F32 ? 4 : 8;
+  long long total = (long long)p->B * (p->H / 2) * (p->W / 2) * (p->C / V);
+  DISPATCH_T(p->dtype, maxpool_fwd_kernel<T><<<grid_for(total, 256), 256, 0, s>>>(*p));
+  count_launch();
+  return check_launch("maxpool_fwd");
+}
+int launch_maxpool_bwd(const d3fk_pool_params* p, cudaStream_t s) {
+  D3FK_CHECK_ARG(p->C % 8 == 0 && p->idx, "C%8 and idx required");
+  int V = p->dtype == D3FK_F32 ? 4 : 8;
+  long long total = (long long)p->B * p->H * p->W * (p->C / V);
+  DISPATCH_T(p->dtype, maxpool_bwd_kernel<T><<<grid_for(total, 256), 256, 0, s>>>(*p));
+  count_launch();
+  return check_launch("maxpool_bwd");
+}
+int launch_sumpool2(const d3fk_pool_params* p, cudaStream_t s) {
+  D3FK_CHECK_ARG(p->C % 8 == 0, "C%8");
+  int V = p->dtype == D3FK_F32 ? 4 : 8;
+  long long total = (long long)p->B * p->H * p->W * (p->C / V);
+  DISPATCH_T(p->dtype, sumpool2_kernel<T><<<grid_for(total, 256), 256, 0, s>>>(*p));
+  count_launch();
+  return check_launch("sumpool2");
+}
+int launch_chansum(const d3fk_chansum_params* p, cudaStream_t s) {
+  D3FK_CHECK_ARG(p->C <= 8 && p->ld % 8 == 0, "C<=8, ld%8");
+  DISPATCH_T(p->dtype, chansum_kernel<T><<<grid_for(p->count, 256, 2), 256, 0, s>>>(*p));
+  count_launch();
+  return check_launch("chansum");
+}
+int launch_qsample(const d3fk_qsample_params* p, cudaStream_t s) {
+  D3FK_CHECK_ARG(p->chw % 4 == 0, "C*H*W must be a multiple of 4");
+  long long nvec = (long long)p->B * p->chw / 4;
+  qsample_kernel<<<grid_for(nvec, 256), 256, 0, s>>>(*p);
+  count_launch();
+  return check_launch("q_sample");
+}
+int launch_posterior(const d3fk_posterior_params* p, cudaStream_t s) {
+  D3FK_CHECK_ARG(p->n % 4 == 0, "n must be a multiple of 4");
+  posterior_kernel<<<grid_for(p->n / 4, 256), 256, 0, s>>>(*p);
+  count_launch();
+  return check_launch("posterior_step");
+}
+int launch_inc(const d3fk_misc_params* p, cudaStream_t s) {
+  inc_kernel<<<1, 1, 0, s>>>((int*)p->p0);
+  count_launch();
+  return check_launch("inc");
+}
+int launch_adam(const d3fk_adam_params* p, cudaStream_t s) {
+  adam_kernel<<<grid_for(p->n, 256), 256, 0, s>>>(*p);
+  count_launch();
+  return check_launch("adam");
+}
+
+}  // namespace d3fk

@@ -1,0 +1,91 @@
+"""Fused elementwise entry points of the hot path: noising (q_sample) and the posterior update.
+
+q_sample replaces `LitModule.blend_random_amount_of_noise_with_each_sample` +
+`sample_random_number_from_exponential_distribution` (d3f/train_denoiser/lit_module.py:128-153,
+duplicated at d3f/train_deep_fake/lit_module.py:208-233) — ~10 eager launches -> 1 kernel.
+posterior_step is the sampler update of SURVEY §8a row S (no reference counterpart)."""
+import math
+
+import torch
+
+from . import _lib
+from ._lib import make_op
+
+
+def _stream(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _require_cuda_f32(t, name):
+    if not t.is_cuda:
+        raise _lib.D3fkError(f"{name}: d3fk kernels need a CUDA (sm_100a) tensor; there is no CPU path")
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32")
+    _lib.init(t.device.index)
+
+
+def q_sample(batch, lam, noise=None, y=None, seed=0, offset=0, fixed_r=None, return_aux=False):
+    """noisy = sqrt(1-r)*batch + sqrt(r)*noise with per-sample r = 1/lam*log(1/(y(1-c)+c)), c = e^-lam.
+    noise / y: optional tensors (parity with the reference's torch.randn_like / torch.rand draws);
+    otherwise drawn in-kernel from Philox4x32-10(seed, offset)."""
+    _require_cuda_f32(batch, "batch")
+    batch = batch.contiguous()
+    B = batch.shape[0]
+    out = torch.empty_like(batch)
+    r_out = torch.empty(B, dtype=torch.float32, device=batch.device) if return_aux else None
+    n_out = torch.empty_like(batch) if (return_aux and noise is None) else None
+    if noise is not None:
+        noise = noise.contiguous()
+    if y is not None:
+        y = y.reshape(B).contiguous()
+    op = make_op(_lib.OP_QSAMPLE, B=B, chw=batch[0].numel(), lam=float(lam),
+                 fixed_r=-1.0 if fixed_r is None else float(fixed_r), x=batch.data_ptr(),
+                 noise=None if noise is None else noise.data_ptr(), y=None if y is None else y.data_ptr(),
+                 out=out.data_ptr(), r_out=None if r_out is None else r_out.data_ptr(),
+                 noise_out=None if n_out is None else n_out.data_ptr(), seed=int(seed), offset=int(offset))
+    _lib.run_single(op, _stream(batch))
+    if return_aux:
+        return out, (noise if noise is not None else n_out), r_out.view(B, 1, 1, 1)
+    return out
+
+
+def noise_ratio_grid(n_steps, r_start=1.0):
+    """r_N = r_start > ... > r_0 = 0, linear in r (alpha_bar = 1 - r)."""
+    return [r_start * (1.0 - i / n_steps) for i in range(n_steps + 1)]
+
+
+def posterior_coeffs(r_i, r_prev, eta):
+    """Coefficients (k_xi, k_x0, sigma) of x_prev = k_xi*x_i + k_x0*x0_hat + sigma*z for
+    x_prev = sqrt(1-r_prev) x0_hat + sqrt(r_prev - sigma^2) eps_hat + sigma z,
+    eps_hat = (x_i - sqrt(1-r_i) x0_hat)/sqrt(r_i), sigma = eta*sqrt(r_prev/r_i)*sqrt(1-(1-r_i)/(1-r_prev))."""
+    if r_prev <= 0.0:
+        return 0.0, 1.0, 0.0
+    var_ratio = 1.0 if r_i >= 1.0 else 1.0 - (1.0 - r_i) / (1.0 - r_prev)
+    sigma = eta * math.sqrt(r_prev / r_i) * math.sqrt(max(var_ratio, 0.0))
+    c_eps = math.sqrt(max(r_prev - sigma * sigma, 0.0))
+    k_xi = c_eps / math.sqrt(r_i)
+    k_x0 = math.sqrt(1.0 - r_prev) - c_eps * math.sqrt(1.0 - r_i) / math.sqrt(r_i)
+    return k_xi, k_x0, sigma
+
+
+def posterior_step_(x_i, x0_hat, r_i, r_prev, z=None, eta=0.0, seed=0, offset=0):
+    """In-place posterior update of x_i (one fused kernel)."""
+    _require_cuda_f32(x_i, "x_i")
+    if not x_i.is_contiguous() or not x0_hat.is_contiguous():
+        raise ValueError("posterior_step_ needs contiguous tensors")
+    k_xi, k_x0, sigma = posterior_coeffs(float(r_i), float(r_prev), eta)
+    op = make_op(_lib.OP_POSTERIOR, n=x_i.numel(), x=x_i.data_ptr(), x0_hat=x0_hat.data_ptr(),
+                 z=None if z is None else z.contiguous().data_ptr(), k_xi=k_xi, k_x0=k_x0, sigma=sigma,
+                 seed=int(seed), offset=int(offset))
+    _lib.run_single(op, _stream(x_i))
+    return x_i
+
+
+def adam_step_(p, g, m, v, lr, beta1, beta2, eps, step, ema=None, ema_decay=0.0, grad_scale=1.0):
+    """Fused torch.optim.Adam update (+optional EMA lerp) over flat fp32 arenas."""
+    _require_cuda_f32(p, "p")
+    op = make_op(_lib.OP_ADAM, n=p.numel(), p=p.data_ptr(), g=g.data_ptr(), m=m.data_ptr(), v=v.data_ptr(),
+                 ema=None if ema is None else ema.data_ptr(), lr=float(lr), beta1=float(beta1), beta2=float(beta2),
+                 eps=float(eps), bias1=1.0 - beta1 ** step, bias2=1.0 - beta2 ** step, ema_decay=float(ema_decay),
+                 grad_scale=float(grad_scale))
+    _lib.run_single(op, _stream(p))

@@ -1,0 +1,470 @@
+"""Op-list plans for the resnet34 U-Net (smp.Unet restated in SURVEY Appendix A).
+
+A plan is built once per (batch, H, W, dtype, train/eval) and owns every intermediate buffer; running
+it is ONE call into libd3fk (`d3fk_run`) that enqueues the whole forward (or backward) on the
+current CUDA stream — no tracing compiler, no per-layer Python in the hot loop, CUDA-graph safe.
+
+Topology follows torchvision/models/resnet.py:89-105,197-205,266-278 (encoder) and smp's
+UnetDecoder / DecoderBlock / SegmentationHead; the call being replaced is
+`self.model(image_noisy)` at d3f/train_denoiser/lit_module.py:117 and its autograd backward.
+"""
+import torch
+
+from . import _lib
+from ._lib import make_op, op_params
+
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+CIN_PAD = 8  # RGB input / 3-channel head gradient are zero padded to 8 channels (16-byte bf16 gather chunks)
+
+
+class ConvSpec:
+    def __init__(self, name, cin, cout, k, stride, pad, bn=None, bias=False):
+        self.name, self.cin, self.cout, self.k, self.stride, self.pad = name, cin, cout, k, stride, pad
+        self.bn = bn          # state_dict prefix of the BatchNorm2d that follows (None for the head)
+        self.bias = bias
+
+
+def unet_layers():
+    """Static description of the 47 convolutions in forward order, grouped by stage."""
+    stem = ConvSpec("encoder.conv1", 3, 64, 7, 2, 3, bn="encoder.bn1")
+    stages = []
+    cin = 64
+    for li, (cout, nblocks) in enumerate(((64, 3), (128, 4), (256, 6), (512, 3)), start=1):
+        blocks = []
+        for bi in range(nblocks):
+            stride = 2 if (bi == 0 and li > 1) else 1
+            p = f"encoder.layer{li}.{bi}"
+            blk = {
+                "conv1": ConvSpec(f"{p}.conv1", cin, cout, 3, stride, 1, bn=f"{p}.bn1"),
+                "conv2": ConvSpec(f"{p}.conv2", cout, cout, 3, 1, 1, bn=f"{p}.bn2"),
+                "down": ConvSpec(f"{p}.downsample.0", cin, cout, 1, stride, 0, bn=f"{p}.downsample.1")
+                if (stride != 1 or cin != cout) else None,
+            }
+            blocks.append(blk)
+            cin = cout
+        stages.append(blocks)
+    dec = []
+    for i, (ci, cs, co) in enumerate(((512, 256, 256), (256, 128, 128), (128, 64, 64), (64, 64, 32), (32, 0, 16))):
+        p = f"decoder.blocks.{i}"
+        dec.append({
+            "cin": ci, "cskip": cs, "cout": co,
+            "conv1": ConvSpec(f"{p}.conv1.0", ci + cs, co, 3, 1, 1, bn=f"{p}.conv1.1"),
+            "conv2": ConvSpec(f"{p}.conv2.0", co, co, 3, 1, 1, bn=f"{p}.conv2.1"),
+        })
+    head = ConvSpec("segmentation_head.0", 16, 3, 3, 1, 1, bias=True)
+    return stem, stages, dec, head
+
+
+def all_convs():
+    stem, stages, dec, head = unet_layers()
+    out = [stem]
+    for blocks in stages:
+        for b in blocks:
+            out.append(b["conv1"])
+            out.append(b["conv2"])
+            if b["down"] is not None:
+                out.append(b["down"])
+    for d in dec:
+        out += [d["conv1"], d["conv2"]]
+    out.append(head)
+    return out
+
+
+def backward_param_order():
+    """Parameter names in the order their gradients become final during backward
+    (head, decoder 4..0, layer4..layer1 reversed, stem) — the flat gradient arena and the
+    data-parallel allreduce buckets follow this order."""
+    stem, stages, dec, head = unet_layers()
+    names = [head.name + ".weight", head.name + ".bias"]
+
+    def conv_bn(c):
+        return [c.name + ".weight", c.bn + ".weight", c.bn + ".bias"]
+
+    for d in reversed(dec):
+        names += conv_bn(d["conv2"]) + conv_bn(d["conv1"])
+    for blocks in reversed(stages):
+        for b in reversed(blocks):
+            names += conv_bn(b["conv2"])
+            if b["down"] is not None:
+                names += conv_bn(b["down"])
+            names += conv_bn(b["conv1"])
+    names += conv_bn(stem)
+    return names
+
+
+class T:
+    """An NHWC activation buffer owned by the plan."""
+
+    def __init__(self, plan, B, H, W, C, dtype=None):
+        self.B, self.H, self.W, self.C = B, H, W, C
+        self.t = torch.empty((B, H, W, C), dtype=dtype or plan.tdtype, device=plan.device)
+        self.ptr = self.t.data_ptr()
+        self.ld = C
+        self.count = B * H * W
+
+
+class UnetPlan:
+    def __init__(self, params, buffers, B, H, W, dtype, device, training, grad_arena=None, grad_offsets=None):
+        """params/buffers: dict name -> tensor (the module's own parameters / BN buffers, fp32)."""
+        if H % 32 or W % 32:
+            raise RuntimeError(f"Wrong input shape height={H}, width={W}. Expected image height and width "
+                               f"divisible by 32.")
+        self.B, self.H, self.W = B, H, W
+        self.dtype = dtype
+        self.tdtype = torch.float32 if dtype == _lib.F32 else torch.bfloat16
+        self.device = torch.device(device)
+        self.training = training
+        self.params, self.buffers = params, buffers
+        self.keep = []          # every tensor the op lists point into
+        self.generation = 0
+        self.pending_backward = False
+        self.stem, self.stages, self.dec, self.head = unet_layers()
+        self.convs = all_convs()
+        self.param_ptrs = {}
+        self._alloc_weights()
+        self._alloc_bn()
+        self.pack_ops = _lib.OpList(self._build_pack())
+        self.saved = {}
+        fwd = self._build_forward()
+        self.fwd_ops = _lib.OpList(fwd)
+        self.bwd_segments = None
+        if training:
+            self.grad_arena, self.grad_offsets = grad_arena, grad_offsets
+            self.bwd_segments = [_lib.OpList(seg) for seg in self._build_backward()]
+        self._record_param_ptrs()
+
+    # ------------------------------------------------------------------ allocation helpers
+    def _new(self, shape, dtype):
+        t = torch.zeros(shape, dtype=dtype, device=self.device)
+        self.keep.append(t)
+        return t
+
+    def _alloc_weights(self):
+        self.w_fwd, self.w_dgrad = {}, {}
+        for c in self.convs:
+            cin_pad = CIN_PAD if c.cin == 3 else c.cin
+            cout_pad = CIN_PAD if c.cout == 3 else c.cout
+            taps = c.k * c.k
+            self.w_fwd[c.name] = self._new((c.cout, taps * cin_pad), self.tdtype)
+            if self.training and c is not self.stem:
+                self.w_dgrad[c.name] = self._new((c.cin, taps * cout_pad), self.tdtype)
+
+    def _alloc_bn(self):
+        bns = [c for c in self.convs if c.bn]
+        total = sum(c.cout for c in bns)
+        self.bn_f32 = self._new((8, total), torch.float32)      # scale, shift, mean, invstd, coef[3], spare
+        self.stats = self._new((2, 2 * total), torch.float64)   # [fwd|bwd][per-BN (sum, sumsq)]
+        self.bn_off = {}
+        off = 0
+        for c in bns:
+            self.bn_off[c.bn] = off
+            off += c.cout
+
+    def _bnptr(self, bn, row, C):
+        return self.bn_f32[row].data_ptr() + 4 * self.bn_off[bn]
+
+    def _bn_common(self, c):
+        bn, C = c.bn, c.cout
+        off = self.bn_off[bn]
+        coef = self._new((3, C), torch.float32)
+        return dict(
+            dtype=self.dtype, C=C, eps=BN_EPS, momentum=BN_MOMENTUM,
+            gamma=self.params[bn + ".weight"].data_ptr(), beta=self.params[bn + ".bias"].data_ptr(),
+            running_mean=self.buffers[bn + ".running_mean"].data_ptr(),
+            running_var=self.buffers[bn + ".running_var"].data_ptr(),
+            num_batches_tracked=self.buffers[bn + ".num_batches_tracked"].data_ptr(),
+            scale=self._bnptr(bn, 0, C), shift=self._bnptr(bn, 1, C), mean=self._bnptr(bn, 2, C),
+            invstd=self._bnptr(bn, 3, C), coef=coef.data_ptr(),
+            stats=self.stats[0].data_ptr() + 8 * 2 * off, bstats=self.stats[1].data_ptr() + 8 * 2 * off,
+        )
+
+    def _record_param_ptrs(self):
+        self.param_ptrs = {n: p.data_ptr() for n, p in self.params.items()}
+        self.param_ptrs.update({n: b.data_ptr() for n, b in self.buffers.items()})
+
+    def params_moved(self):
+        for n, p in self.params.items():
+            if self.param_ptrs.get(n) != p.data_ptr():
+                return True
+        for n, b in self.buffers.items():
+            if self.param_ptrs.get(n) != b.data_ptr():
+                return True
+        return False
+
+    # ------------------------------------------------------------------ weight packing / BN folding
+    def _build_pack(self):
+        ops = []
+        for c in self.convs:
+            cin_pad = CIN_PAD if c.cin == 3 else c.cin
+            cout_pad = CIN_PAD if c.cout == 3 else c.cout
+            wd = self.w_dgrad.get(c.name)
+            ops.append(make_op(_lib.OP_PACK, dtype=self.dtype, Cout=c.cout, Cin=c.cin, kh=c.k, kw=c.k,
+                               cin_pad=cin_pad, cout_pad=cout_pad, w=self.params[c.name + ".weight"].data_ptr(),
+                               w_fwd=self.w_fwd[c.name].data_ptr(), w_dgrad=wd.data_ptr() if wd is not None else None))
+        if not self.training:
+            for c in self.convs:
+                if c.bn:
+                    ops.append(make_op(_lib.OP_BN_FOLD, **{k: v for k, v in self._bn_common(c).items()
+                                                          if k in ("dtype", "C", "eps", "gamma", "beta", "running_mean",
+                                                                   "running_var", "scale", "shift")}))
+        return ops
+
+    # ------------------------------------------------------------------ forward
+    def _conv_op(self, c, src0, src1=None, up0=0, out=None, relu=0, res=None, stats=False, out_nchw=None,
+                 affine=False):
+        Hi = src0.H * (2 if up0 else 1)
+        Wi = src0.W * (2 if up0 else 1)
+        Ho = (Hi + 2 * c.pad - c.k) // c.stride + 1
+        Wo = (Wi + 2 * c.pad - c.k) // c.stride + 1
+        f = dict(dtype=self.dtype, mode=0, src0=src0.ptr, c0=src0.C, ld0=src0.ld, up0=up0,
+                 B=self.B, Hi=Hi, Wi=Wi, Ho=Ho, Wo=Wo, kh=c.k, kw=c.k, stride=c.stride, pad=c.pad,
+                 w=self.w_fwd[c.name].data_ptr(), Cout=c.cout, relu=relu)
+        if src1 is not None:
+            f.update(src1=src1.ptr, c1=src1.C, ld1=src1.ld)
+        if out is not None:
+            f.update(out=out.ptr, ldo=out.ld)
+        if out_nchw is not None:
+            f.update(out_nchw=out_nchw)
+        if res is not None:
+            f.update(res=res.ptr, ldr=res.ld)
+        if stats:
+            f.update(stats=self.stats[0].data_ptr() + 8 * 2 * self.bn_off[c.bn])
+        if affine:
+            f.update(scale=self._bnptr(c.bn, 0, c.cout), shift=self._bnptr(c.bn, 1, c.cout))
+        return make_op(_lib.OP_CONV, **f), Ho, Wo
+
+    def _conv_bn_act(self, ops, c, src0, src1=None, up0=0, relu=1, res=None):
+        """conv -> BN -> (+res) -> ReLU.  Train: raw conv output + batch statistics in the conv epilogue,
+        finalize, one fused apply pass.  Eval: BN folded into the conv epilogue.  Returns the activation."""
+        Hi = src0.H * (2 if up0 else 1)
+        Ho = (Hi + 2 * c.pad - c.k) // c.stride + 1
+        Wi = src0.W * (2 if up0 else 1)
+        Wo = (Wi + 2 * c.pad - c.k) // c.stride + 1
+        act = T(self, self.B, Ho, Wo, c.cout)
+        self.keep.append(act.t)
+        if not self.training:
+            op, _, _ = self._conv_op(c, src0, src1, up0, out=act, relu=relu, res=res, affine=True)
+            ops.append(op)
+            return act
+        raw = T(self, self.B, Ho, Wo, c.cout)
+        self.keep.append(raw.t)
+        op, _, _ = self._conv_op(c, src0, src1, up0, out=raw, stats=True)
+        ops.append(op)
+        bn = self._bn_common(c)
+        bn.update(count=raw.count, relu=relu, x=raw.ptr, ldx=raw.ld, y=act.ptr, ldy=act.ld)
+        if res is not None:
+            bn.update(res=res.ptr, ldr=res.ld)
+        fwd_fields = {k: v for k, v in bn.items() if k not in ("bstats", "coef")}
+        ops.append(make_op(_lib.OP_BN_FINALIZE, **fwd_fields))
+        ops.append(make_op(_lib.OP_BN_APPLY, **fwd_fields))
+        self.saved[c.name] = dict(src0=src0, src1=src1, up0=up0, raw=raw, act=act, relu=relu, bn=bn, res=res)
+        return act
+
+    def _build_forward(self):
+        ops = []
+        B, H, W = self.B, self.H, self.W
+        if self.training:
+            ops.append(make_op(_lib.OP_MEMSET, p0=self.stats[0].data_ptr(), n=self.stats[0].numel() * 8))
+        self.x8 = T(self, B, H, W, CIN_PAD)
+        self.keep.append(self.x8.t)
+        self.in_op_index = len(ops)
+        ops.append(make_op(_lib.OP_NCHW2NHWC, dtype=self.dtype, B=B, C=3, H=H, W=W, cpad=CIN_PAD, src=None,
+                           dst=self.x8.ptr))
+        f1 = self._conv_bn_act(ops, self.stem, self.x8)
+        p1 = T(self, B, f1.H // 2, f1.W // 2, 64)
+        self.keep.append(p1.t)
+        self.pool_idx = self._new((B, p1.H, p1.W, 64), torch.uint8) if self.training else None
+        ops.append(make_op(_lib.OP_MAXPOOL_FWD, dtype=self.dtype, B=B, H=f1.H, W=f1.W, C=64, x=f1.ptr, ldx=f1.ld,
+                           y=p1.ptr, ldy=p1.ld, idx=self.pool_idx.data_ptr() if self.training else None))
+        self.f1, self.p1 = f1, p1
+        x = p1
+        feats = [f1]
+        self.block_io = []
+        for blocks in self.stages:
+            for b in blocks:
+                a1 = self._conv_bn_act(ops, b["conv1"], x)
+                idn = x
+                if b["down"] is not None:
+                    idn = self._conv_bn_act(ops, b["down"], x, relu=0)
+                if self.training:
+                    out = self._conv_bn_act(ops, b["conv2"], a1, relu=1, res=idn)
+                else:
+                    out = self._conv_bn_act(ops, b["conv2"], a1, relu=1, res=idn)
+                self.block_io.append((b, x, a1, idn, out))
+                x = out
+            feats.append(x)
+        # feats = [f1, f2, f3, f4, f5]
+        self.feats = feats
+        skips = [feats[3], feats[2], feats[1], feats[0], None]
+        x = feats[4]
+        self.dec_io = []
+        for d, skip in zip(self.dec, skips):
+            a1 = self._conv_bn_act(ops, d["conv1"], x, src1=skip, up0=1)
+            out = self._conv_bn_act(ops, d["conv2"], a1)
+            self.dec_io.append((d, x, skip, a1, out))
+            x = out
+        self.dec_out = x
+        self.out_op_index = len(ops)
+        op, _, _ = self._conv_op(self.head, x, out_nchw=0)
+        op_params(op).shift = self.params[self.head.name + ".bias"].data_ptr()
+        ops.append(op)
+        return ops
+
+    # ------------------------------------------------------------------ backward
+    def _gptr(self, name):
+        return self.grad_arena.data_ptr() + 4 * self.grad_offsets[name]
+
+    def _wgrad_op(self, c, src0, src1, up0, dy, cout_buf=None):
+        Hi = src0.H * (2 if up0 else 1)
+        Wi = src0.W * (2 if up0 else 1)
+        f = dict(dtype=self.dtype, src0=src0.ptr, c0=src0.C, ld0=src0.ld, up0=up0, B=self.B, Hi=Hi, Wi=Wi,
+                 Ho=dy.H, Wo=dy.W, kh=c.k, kw=c.k, stride=c.stride, pad=c.pad, dy=dy.ptr, ldy=dy.ld,
+                 Cout=dy.C, cin_real=c.cin, cout_real=c.cout, dw=self._gptr(c.name + ".weight"))
+        if src1 is not None:
+            f.update(src1=src1.ptr, c1=src1.C, ld1=src1.ld)
+        return make_op(_lib.OP_WGRAD, **f)
+
+    def _dgrad_op(self, c, dy, out, res=None, row0=0, rows=None):
+        """dX (= out, channels [row0, row0+rows) of the conv input) from dY through conv c."""
+        cout_pad = dy.C
+        rows = out.C if rows is None else rows
+        wbytes = 4 if self.dtype == _lib.F32 else 2
+        f = dict(dtype=self.dtype, mode=1, src0=dy.ptr, c0=dy.C, ld0=dy.ld, B=self.B, Hi=dy.H, Wi=dy.W,
+                 Ho=out.H, Wo=out.W, kh=c.k, kw=c.k, stride=c.stride, pad=c.pad,
+                 w=self.w_dgrad[c.name].data_ptr() + row0 * c.k * c.k * cout_pad * wbytes, Cout=rows,
+                 out=out.ptr, ldo=out.ld)
+        if res is not None:
+            f.update(res=res.ptr, ldr=res.ld)
+        return make_op(_lib.OP_CONV, **f)
+
+    def _bn_bwd(self, ops, c, g_act, want_dres=False):
+        """Backward through BN(+ReLU) of conv c given grad wrt its activation.  Returns (d_raw, g_masked)."""
+        sv = self.saved[c.name]
+        raw, act = sv["raw"], sv["act"]
+        d_raw = T(self, raw.B, raw.H, raw.W, raw.C)
+        self.keep.append(d_raw.t)
+        bn = dict(sv["bn"])
+        bn.update(dy=g_act.ptr, lddy=g_act.ld, act=act.ptr, ldact=act.ld, dx=d_raw.ptr, lddx=d_raw.ld,
+                  dgamma=self._gptr(c.bn + ".weight"), dbeta=self._gptr(c.bn + ".bias"))
+        g_masked = None
+        if want_dres:
+            g_masked = T(self, raw.B, raw.H, raw.W, raw.C)
+            self.keep.append(g_masked.t)
+            bn.update(dres=g_masked.ptr, lddres=g_masked.ld)
+        bn.pop("res", None)
+        bn.pop("ldr", None)
+        ops.append(make_op(_lib.OP_BN_BWD_REDUCE, **bn))
+        ops.append(make_op(_lib.OP_BN_BWD_FINALIZE, **bn))
+        ops.append(make_op(_lib.OP_BN_BWD_APPLY, **bn))
+        return d_raw, g_masked
+
+    def _newT(self, like, C=None, H=None, W=None):
+        t = T(self, like.B, H or like.H, W or like.W, C or like.C)
+        self.keep.append(t.t)
+        return t
+
+    def _build_backward(self):
+        """Returns a list of op-list segments; segment i completes the gradients of bucket i of the flat
+        gradient arena (see backward_param_order / Unet.grad_buckets)."""
+        B = self.B
+        segs = []
+        ops = []
+        ops.append(make_op(_lib.OP_MEMSET, p0=self.grad_arena.data_ptr(), n=self.grad_arena.numel() * 4))
+        ops.append(make_op(_lib.OP_MEMSET, p0=self.stats[1].data_ptr(), n=self.stats[1].numel() * 8))
+        # ---- head
+        self.dy8 = T(self, B, self.H, self.W, CIN_PAD)
+        self.keep.append(self.dy8.t)
+        self.dy_op_index = len(ops)
+        ops.append(make_op(_lib.OP_NCHW2NHWC, dtype=self.dtype, B=B, C=3, H=self.H, W=self.W, cpad=CIN_PAD, src=None,
+                           dst=self.dy8.ptr))
+        ops.append(make_op(_lib.OP_CHANSUM, dtype=self.dtype, C=3, ld=CIN_PAD, count=self.dy8.count, x=self.dy8.ptr,
+                           out=self._gptr(self.head.name + ".bias")))
+        ops.append(self._wgrad_op(self.head, self.dec_out, None, 0, self.dy8))
+        g = self._newT(self.dec_out)
+        ops.append(self._dgrad_op(self.head, self.dy8, g))
+        grad = {id(self.dec_out): g}   # activation buffer -> its (so far accumulated) gradient buffer
+
+        def add_grad(ops, conv, dy, target, row0=0, rows=None, tmp=None):
+            """dgrad of `conv` into the gradient of `target` (accumulating if one exists)."""
+            if tmp is not None:
+                ops.append(self._dgrad_op(conv, dy, tmp, row0=row0, rows=rows))
+                return
+            if id(target) in grad:
+                gbuf = grad[id(target)]
+                ops.append(self._dgrad_op(conv, dy, gbuf, res=gbuf, row0=row0, rows=rows))
+            else:
+                gbuf = self._newT(target)
+                grad[id(target)] = gbuf
+                ops.append(self._dgrad_op(conv, dy, gbuf, row0=row0, rows=rows))
+
+        # ---- decoder, last block first
+        for d, x, skip, a1, out in reversed(self.dec_io):
+            d_r2, _ = self._bn_bwd(ops, d["conv2"], grad[id(out)])
+            ops.append(self._wgrad_op(d["conv2"], a1, None, 0, d_r2))
+            add_grad(ops, d["conv2"], d_r2, a1)
+            d_r1, _ = self._bn_bwd(ops, d["conv1"], grad[id(a1)])
+            ops.append(self._wgrad_op(d["conv1"], x, skip, 1, d_r1))
+            up_tmp = T(self, B, 2 * x.H, 2 * x.W, x.C)
+            self.keep.append(up_tmp.t)
+            add_grad(ops, d["conv1"], d_r1, None, row0=0, rows=x.C, tmp=up_tmp)
+            gx = self._newT(x)
+            grad[id(x)] = gx
+            ops.append(make_op(_lib.OP_SUMPOOL2, dtype=self.dtype, B=B, H=x.H, W=x.W, C=x.C, dy=up_tmp.ptr,
+                               lddy=up_tmp.ld, dx=gx.ptr, lddx=gx.ld))
+            if skip is not None:
+                add_grad(ops, d["conv1"], d_r1, skip, row0=x.C, rows=skip.C)
+        segs.append(ops)
+        # ---- encoder, last block first; one segment per resnet layer
+        ops = []
+        nblocks_per_stage = [len(s) for s in self.stages]
+        boundaries = set()
+        acc = 0
+        for n in nblocks_per_stage:
+            acc += n
+            boundaries.add(acc)
+        for bi in range(len(self.block_io) - 1, -1, -1):
+            b, x, a1, idn, out = self.block_io[bi]
+            d_r2, g_masked = self._bn_bwd(ops, b["conv2"], grad[id(out)], want_dres=True)
+            ops.append(self._wgrad_op(b["conv2"], a1, None, 0, d_r2))
+            add_grad(ops, b["conv2"], d_r2, a1)
+            d_r1, _ = self._bn_bwd(ops, b["conv1"], grad[id(a1)])
+            ops.append(self._wgrad_op(b["conv1"], x, None, 0, d_r1))
+            if b["down"] is not None:
+                d_rd, _ = self._bn_bwd(ops, b["down"], g_masked)
+                ops.append(self._wgrad_op(b["down"], x, None, 0, d_rd))
+                add_grad(ops, b["down"], d_rd, x)
+                add_grad(ops, b["conv1"], d_r1, x)
+            else:
+                assert id(x) not in grad
+                gx = self._newT(x)
+                grad[id(x)] = gx
+                ops.append(self._dgrad_op(b["conv1"], d_r1, gx, res=g_masked))
+            if bi in boundaries and bi != len(self.block_io):
+                segs.append(ops)
+                ops = []
+        # ---- maxpool + stem
+        g_f1 = grad[id(self.f1)]
+        ops.append(make_op(_lib.OP_MAXPOOL_BWD, dtype=self.dtype, B=B, H=self.f1.H, W=self.f1.W, C=64,
+                           dy=grad[id(self.p1)].ptr, lddy=grad[id(self.p1)].ld, idx=self.pool_idx.data_ptr(),
+                           dx=g_f1.ptr, lddx=g_f1.ld, accumulate=1))
+        d_r, _ = self._bn_bwd(ops, self.stem, g_f1)
+        ops.append(self._wgrad_op(self.stem, self.x8, None, 0, d_r))
+        segs.append(ops)
+        return segs
+
+    # ------------------------------------------------------------------ execution
+    def run_pack(self, stream):
+        self.pack_ops.run(stream)
+
+    def run_forward(self, x, y, stream):
+        op_params(self.fwd_ops.array[self.in_op_index]).src = x.data_ptr()
+        op_params(self.fwd_ops.array[self.out_op_index]).out_nchw = y.data_ptr()
+        self.fwd_ops.run(stream)
+
+    def run_backward(self, dy, stream, after_segment=None):
+        op_params(self.bwd_segments[0].array[self.dy_op_index]).src = dy.data_ptr()
+        for i, seg in enumerate(self.bwd_segments):
+            seg.run(stream)
+            if after_segment is not None:
+                after_segment(i)

@@ -1,0 +1,212 @@
+/*
+ * d3fk.h — C ABI of the B200-native (sm_100a) hot path for the d3f denoiser U-Net.
+ *
+ * The reference (ChainBreak/denoising_diffusion_deep_fake) has no FFI of its own: its hot path is
+ * reached through a Python nn.Module call, `self.model(image_noisy)`
+ * (d3f/train_denoiser/lit_module.py:117, d3f/train_deep_fake/lit_module.py:173,189,195,266), the
+ * noising helper (train_denoiser/lit_module.py:128-153) and loss.backward().  Those calls bottom out
+ * in ATen/cuDNN library ops; every entry point below replaces one family of those ops.  The Python
+ * host (denoising_diffusion_deep_fake_b200/unet.py) builds a flat list of `d3fk_op` records once per
+ * (batch, H, W, mode) and hands it to d3fk_run(); see INTEGRATION.md for the reference-side binding.
+ *
+ * Conventions: plain pointers and sizes only; the caller owns every buffer (activations, packed
+ * weights, statistics, workspaces); nothing here allocates, synchronises or throws; all work is
+ * enqueued on the given stream and is CUDA-graph-capture safe; return 0 or a negative D3FK_ERR_*.
+ * There is no CPU path: on a device that is not sm_100 every launcher returns D3FK_ERR_ARCH.
+ *
+ * Tensors are NHWC ("pixel rows") inside the library: element (n,h,w,c) of a tensor with pixel
+ * stride ld lives at ((n*H+h)*W+w)*ld + c.  dtype is D3FK_F32 (parity mode, CUDA-core FFMA
+ * implicit GEMM) or D3FK_BF16 (tcgen05/TMEM implicit GEMM, fp32 accumulate).
+ */
+#ifndef D3FK_H
+#define D3FK_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define D3FK_OK 0
+#define D3FK_ERR_ARG (-1)
+#define D3FK_ERR_ARCH (-2)
+#define D3FK_ERR_CUDA (-3)
+#define D3FK_ERR_UNSUPPORTED (-4)
+
+#define D3FK_F32 0
+#define D3FK_BF16 1
+
+typedef void* d3fk_stream; /* cudaStream_t */
+
+/* ---- convolution as implicit GEMM (replaces nn.Conv2d fwd and its dgrad) ----
+ * mode 0: out[n,ho,wo,co] = sum_{kh,kw,c} A[n, ho*stride-pad+kh, wo*stride-pad+kw, c] * w[co][kh][kw][c]
+ * mode 1 (transposed gather = dgrad of a conv with the same kh/kw/stride/pad):
+ *         out[n,h,w,ci] = sum_{kh,kw,co} A[n,(h+pad-kh)/stride,(w+pad-kw)/stride,co] * w[ci][kh][kw][co]
+ *         (terms whose coordinate is not divisible by stride or out of range are zero).
+ * A is the channel concatenation of src0 (c0 channels, optionally read through a nearest 2x upsample:
+ * F.interpolate(scale_factor=2) + torch.cat of smp's DecoderBlock) and src1 (c1 channels).
+ * Epilogue: v = acc; v = v*scale[c]+shift[c] (if scale); v += res (if res); v = max(v,0) (if relu);
+ * stats[c] += v, stats[Cout+c] += v*v (if stats; per-channel batch statistics for train-mode BN);
+ * store to `out` (NHWC dtype) or, if out_nchw is set, to fp32 NCHW (the U-Net's output tensor). */
+typedef struct d3fk_conv_params {
+  int32_t dtype, mode;
+  const void* src0; const void* src1;
+  int32_t c0, c1, ld0, ld1, up0;
+  int32_t B, Hi, Wi, Ho, Wo;
+  int32_t kh, kw, stride, pad;
+  const void* w; int32_t Cout, _pad0;
+  void* out; float* out_nchw;
+  const float* scale; const float* shift;
+  const void* res;
+  double* stats;
+  int32_t ldo, ldr, relu, _pad1;
+} d3fk_conv_params;
+
+/* ---- weight gradient (replaces cuDNN wgrad): dw[co][ci][kh][kw] += sum_{n,ho,wo} dy[n,ho,wo,co] * A[...]
+ * with the same mode-0 gather as the forward conv.  dw is the fp32 OIHW master-gradient tensor
+ * (cin_real input channels); contributions are added with atomics, the caller zeroes it first. */
+typedef struct d3fk_wgrad_params {
+  int32_t dtype, _pad0;
+  const void* src0; const void* src1;
+  int32_t c0, c1, ld0, ld1, up0;
+  int32_t B, Hi, Wi, Ho, Wo;
+  int32_t kh, kw, stride, pad;
+  const void* dy; float* dw;
+  int32_t ldy, Cout, cin_real, cout_real;
+} d3fk_wgrad_params;
+
+/* ---- weight packing: fp32 OIHW master -> [Cout][kh][kw][cin_pad] (forward) and/or
+ * [Cin][kh][kw][cout_pad] (dgrad) in dtype, zero padded. */
+typedef struct d3fk_pack_params {
+  int32_t dtype, Cout, Cin, kh, kw, cin_pad, cout_pad, _pad0;
+  const float* w; void* w_fwd; void* w_dgrad;
+} d3fk_pack_params;
+
+/* ---- BatchNorm2d (+residual) + ReLU, train and eval, forward and backward
+ * (replaces nn.BatchNorm2d / ReLU / BasicBlock `out += identity`). */
+typedef struct d3fk_bn_params {
+  int32_t dtype, C, relu, _pad0;
+  int64_t count;                        /* B*H*W */
+  const void* x; void* y; const void* res;
+  int32_t ldx, ldy, ldr, _pad1;
+  double* stats;                        /* [2][C] sum, sumsq of x (from the conv epilogue) */
+  const float* gamma; const float* beta;
+  float* running_mean; float* running_var; int64_t* num_batches_tracked;
+  float eps, momentum;
+  float* scale; float* shift;           /* y = x*scale + shift */
+  float* mean; float* invstd;
+  /* backward */
+  const void* dy; const void* act;      /* grad wrt y; y itself (ReLU mask = act > 0) */
+  void* dx; void* dres;                 /* grad wrt x; masked grad for the residual branch (nullable) */
+  int32_t lddy, ldact, lddx, lddres;
+  double* bstats;                       /* [2][C] sum dy', sum dy'*xhat */
+  float* dgamma; float* dbeta;
+  float* coef;                          /* [3][C] scratch written by bn_bwd_finalize */
+} d3fk_bn_params;
+
+/* ---- MaxPool2d(3,2,1) fwd/bwd, 2x2 sum pool (= backward of nearest 2x upsample), NCHW fp32 -> NHWC */
+typedef struct d3fk_pool_params {
+  int32_t dtype, B, H, W, C, accumulate;  /* H,W: input extent of the forward op */
+  const void* x; void* y; uint8_t* idx;
+  const void* dy; void* dx;
+  int32_t ldx, ldy, lddy, lddx;
+} d3fk_pool_params;
+
+typedef struct d3fk_layout_params {
+  int32_t dtype, B, C, H, W, cpad;
+  const float* src; void* dst;            /* src fp32 NCHW [B,C,H,W] -> dst NHWC dtype [B,H,W,cpad] */
+} d3fk_layout_params;
+
+/* per-channel sum over (n,h,w) of an NHWC tensor into fp32 out[c] (head bias gradient) */
+typedef struct d3fk_chansum_params {
+  int32_t dtype, C, ld, _pad0; int64_t count;
+  const void* x; float* out;
+} d3fk_chansum_params;
+
+/* ---- noising q_sample (d3f/train_denoiser/lit_module.py:128-153) -------------------------------
+ * r_b = 1/lam * log(1/(y_b*(1-c)+c)), c = e^-lam;  out = sqrt(1-r_b)*x + sqrt(r_b)*noise.
+ * noise / y may be supplied (parity runs) or drawn in-kernel from Philox4x32-10(seed, offset).
+ * fixed_r >= 0 overrides the draw (balance_training_images/lit_module.py:109-120 uses 0.7). */
+typedef struct d3fk_qsample_params {
+  int32_t B, chw; float lam, fixed_r;
+  const float* x; const float* noise; const float* y;
+  float* out; float* r_out; float* noise_out;
+  uint64_t seed, offset;
+} d3fk_qsample_params;
+
+/* ---- posterior update x_{i-1} = k_xi*x_i + k_x0*x0_hat + sigma*z ------------
+ * Coefficients come from coef_table[*step][0..2] when coef_table is set (CUDA-graph replay: the
+ * graph is step-independent), else from the immediates. z supplied or Philox(seed, offset+*step). */
+typedef struct d3fk_posterior_params {
+  int64_t n;
+  float* x; const float* x0_hat; const float* z;
+  const float* coef_table; const int32_t* step;
+  float k_xi, k_x0, sigma, _pad0;
+  uint64_t seed, offset;
+} d3fk_posterior_params;
+
+typedef struct d3fk_misc_params {          /* MEMSET: p0[0..n) bytes = 0; INC: *(int32*)p0 += 1 */
+  void* p0; int64_t n;
+} d3fk_misc_params;
+
+/* ---- fused Adam (+EMA lerp) over a flat fp32 arena (torch.optim.Adam semantics: eps outside sqrt,
+ * no weight decay, no amsgrad; d3f/train_denoiser/lit_module.py:95, train_deep_fake/lit_module.py:116-120) */
+typedef struct d3fk_adam_params {
+  int64_t n;
+  float* p; const float* g; float* m; float* v; float* ema;
+  float lr, beta1, beta2, eps, bias1, bias2, ema_decay, grad_scale;
+} d3fk_adam_params;
+
+enum d3fk_op_kind {
+  D3FK_OP_CONV = 1, D3FK_OP_WGRAD = 2, D3FK_OP_PACK = 3, D3FK_OP_NCHW2NHWC = 4,
+  D3FK_OP_BN_FINALIZE = 5, D3FK_OP_BN_APPLY = 6, D3FK_OP_BN_FOLD = 7,
+  D3FK_OP_BN_BWD_REDUCE = 8, D3FK_OP_BN_BWD_FINALIZE = 9, D3FK_OP_BN_BWD_APPLY = 10,
+  D3FK_OP_MAXPOOL_FWD = 11, D3FK_OP_MAXPOOL_BWD = 12, D3FK_OP_SUMPOOL2 = 13,
+  D3FK_OP_CHANSUM = 14, D3FK_OP_QSAMPLE = 15, D3FK_OP_POSTERIOR = 16,
+  D3FK_OP_MEMSET = 17, D3FK_OP_INC = 18, D3FK_OP_ADAM = 19
+};
+
+typedef struct d3fk_op {
+  int32_t kind, _pad;
+  union {
+    d3fk_conv_params conv; d3fk_wgrad_params wgrad; d3fk_pack_params pack; d3fk_bn_params bn;
+    d3fk_pool_params pool; d3fk_layout_params layout; d3fk_chansum_params chansum;
+    d3fk_qsample_params qsample; d3fk_posterior_params posterior; d3fk_misc_params misc;
+    d3fk_adam_params adam;
+  } u;
+} d3fk_op;
+
+/* library / device */
+int d3fk_version(void);
+int d3fk_sizeof_op(void);                 /* ABI check for the host-side struct mirror */
+int d3fk_init(int device);                /* D3FK_ERR_ARCH unless the device is sm_100 */
+const char* d3fk_last_error(void);
+int d3fk_device_error_flag(void);         /* non-zero if a kernel hit its barrier watchdog (debug) */
+
+/* run a recorded op list on `stream` (the hot path: one call per U-Net forward / backward) */
+int d3fk_run(const d3fk_op* ops, int n_ops, d3fk_stream stream);
+
+/* single-op entry points (same launchers; used by the per-op parity tests) */
+int d3fk_conv(const d3fk_conv_params* p, d3fk_stream stream);
+int d3fk_wgrad(const d3fk_wgrad_params* p, d3fk_stream stream);
+int d3fk_pack_weights(const d3fk_pack_params* p, d3fk_stream stream);
+int d3fk_nchw_to_nhwc(const d3fk_layout_params* p, d3fk_stream stream);
+int d3fk_bn_finalize(const d3fk_bn_params* p, d3fk_stream stream);
+int d3fk_bn_apply(const d3fk_bn_params* p, d3fk_stream stream);
+int d3fk_bn_fold(const d3fk_bn_params* p, d3fk_stream stream);
+int d3fk_bn_bwd_reduce(const d3fk_bn_params* p, d3fk_stream stream);
+int d3fk_bn_bwd_finalize(const d3fk_bn_params* p, d3fk_stream stream);
+int d3fk_bn_bwd_apply(const d3fk_bn_params* p, d3fk_stream stream);
+int d3fk_maxpool_fwd(const d3fk_pool_params* p, d3fk_stream stream);
+int d3fk_maxpool_bwd(const d3fk_pool_params* p, d3fk_stream stream);
+int d3fk_sumpool2(const d3fk_pool_params* p, d3fk_stream stream);
+int d3fk_chansum(const d3fk_chansum_params* p, d3fk_stream stream);
+int d3fk_q_sample(const d3fk_qsample_params* p, d3fk_stream stream);
+int d3fk_posterior_step(const d3fk_posterior_params* p, d3fk_stream stream);
+int d3fk_adam(const d3fk_adam_params* p, d3fk_stream stream);
+
+/* number of kernels launched by this library since load (bench.py's gpu_launches) */
+int64_t d3fk_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

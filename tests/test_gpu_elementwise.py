@@ -1,0 +1,57 @@
+"""q_sample / posterior_step parity (-m gpu) against the oracle formulas
+(d3f/train_denoiser/lit_module.py:128-153).  fp32, tolerance 1e-6."""
+import pytest
+import torch
+
+import oracle
+import denoising_diffusion_deep_fake_b200 as d3
+from gpu_harness import rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.mark.parametrize("lam", [3.0, 5.0, 8.0])
+@pytest.mark.parametrize("shape", [(8, 3, 64, 64), (1, 3, 32, 32), (5, 3, 128, 96)])
+def test_q_sample_given_noise(lam, shape):
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(shape, generator=g).clamp(-1, 1)
+    noise = torch.randn(shape, generator=g)
+    y = torch.rand(shape[0], 1, 1, 1, generator=g)
+    r_ref = oracle.sample_noise_ratio(y, lam)
+    ref = oracle.blend_noise(x, noise, r_ref)
+    out, n_used, r = d3.q_sample(x.to(DEV), lam, noise=noise.to(DEV), y=y.to(DEV), return_aux=True)
+    assert rel_err(out.cpu(), ref) < 1e-6
+    assert rel_err(r.cpu(), r_ref) < 1e-6
+    assert (r_ref > 0).all() and (r_ref <= 1).all()
+
+
+def test_q_sample_philox_statistics():
+    x = torch.zeros(64, 3, 64, 64, device=DEV)
+    out, noise, r = d3.q_sample(x, 5.0, seed=123, offset=7, return_aux=True)
+    # with x = 0: out = sqrt(r) * eps
+    assert abs(noise.mean().item()) < 5e-3 and abs(noise.std().item() - 1.0) < 5e-3
+    assert rel_err(out.cpu(), (torch.sqrt(r) * noise).cpu()) < 1e-6
+    assert (r > 0).all() and (r <= 1).all()
+    out2 = d3.q_sample(x, 5.0, seed=123, offset=7)
+    assert torch.equal(out, out2)                     # deterministic given (seed, offset)
+    out3 = d3.q_sample(x, 5.0, seed=124, offset=7)
+    assert not torch.equal(out, out3)
+    # fixed ratio variant (balance_training_images/lit_module.py:109-120)
+    o4, n4, r4 = d3.q_sample(x + 1.0, 5.0, seed=1, fixed_r=0.7, return_aux=True)
+    assert rel_err(o4.cpu(), ((0.3 ** 0.5) * 1.0 + (0.7 ** 0.5) * n4).cpu()) < 1e-6
+
+
+@pytest.mark.parametrize("eta", [0.0, 1.0])
+def test_posterior_step(eta):
+    g = torch.Generator().manual_seed(1)
+    shape = (4, 3, 64, 64)
+    grid = oracle.noise_ratio_grid(10).tolist()
+    for i in (0, 4, 9):
+        x = torch.randn(shape, generator=g)
+        x0 = torch.randn(shape, generator=g)
+        z = torch.randn(shape, generator=g)
+        ref = oracle.posterior_step(x, x0, grid[i], grid[i + 1], z, eta)
+        xd = x.to(DEV).clone()
+        d3.posterior_step_(xd, x0.to(DEV), grid[i], grid[i + 1], z=z.to(DEV), eta=eta)
+        assert rel_err(xd.cpu(), ref) < 1e-6, i

@@ -1,0 +1,200 @@
+"""Per-op parity (-m gpu): every libd3fk kernel, called through its extern "C" entry point, against the
+torch-CPU semantics of the same op on identical inputs.  Tolerances: fp32 engine 1e-5 (norm-relative),
+bf16 engine 1e-2 on bf16-rounded inputs (fp32 accumulate, bf16 output rounding = 2^-9)."""
+import math
+
+import pytest
+import torch
+
+from denoising_diffusion_deep_fake_b200 import _lib
+from gpu_harness import run_both, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = {_lib.F32: 1e-5, _lib.BF16: 1e-2}
+DTYPES = [_lib.F32, _lib.BF16]
+
+
+def _conv_case(dtype, B, Hi, Wi, c0, c1, up0, Cout, k, stride, pad, mode, relu=0, res=False, affine=False,
+               stats=False, nchw=False, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    ctot = c0 + c1
+    if mode == 0:
+        Ho = (Hi + 2 * pad - k) // stride + 1
+        Wo = (Wi + 2 * pad - k) // stride + 1
+    else:
+        Ho, Wo = Hi * stride, Wi * stride
+    hs, ws = (Hi >> up0), (Wi >> up0)
+    t = {"src0": torch.randn(B, hs, ws, c0, generator=g), "w": torch.randn(Cout, k * k * ctot, generator=g) / math.sqrt(k * k * ctot)}
+    if c1:
+        t["src1"] = torch.randn(B, Hi, Wi, c1, generator=g)
+    sc = dict(mode=mode, c0=c0, c1=c1, ld0=c0, ld1=c1, up0=up0, B=B, Hi=Hi, Wi=Wi, Ho=Ho, Wo=Wo, kh=k, kw=k,
+              stride=stride, pad=pad, Cout=Cout, relu=relu)
+    outs = []
+    if nchw:
+        t["out_nchw"] = torch.zeros(B, Cout, Ho, Wo)
+        outs.append("out_nchw")
+    else:
+        t["out"] = torch.zeros(B, Ho, Wo, Cout)
+        sc["ldo"] = Cout
+        outs.append("out")
+    if res:
+        t["res"] = torch.randn(B, Ho, Wo, Cout, generator=g)
+        sc["ldr"] = Cout
+    if affine:
+        t["scale"] = torch.rand(Cout, generator=g) + 0.5
+        t["shift"] = torch.randn(Cout, generator=g)
+    if stats:
+        t["stats"] = torch.zeros(2, Cout, dtype=torch.float64)
+        outs.append("stats")
+    return run_both(_lib.OP_CONV, dtype, t, sc, outs)
+
+
+CONV_CASES = [
+    # B, Hi, Wi, c0, c1, up0, Cout, k, stride, pad, mode, extras
+    dict(B=2, Hi=16, Wi=16, c0=64, c1=0, up0=0, Cout=64, k=3, stride=1, pad=1, mode=0, stats=True),
+    dict(B=3, Hi=8, Wi=8, c0=128, c1=0, up0=0, Cout=128, k=3, stride=1, pad=1, mode=0, relu=1, res=True, affine=True),
+    dict(B=2, Hi=16, Wi=16, c0=64, c1=0, up0=0, Cout=128, k=3, stride=2, pad=1, mode=0, stats=True),
+    dict(B=2, Hi=16, Wi=16, c0=64, c1=0, up0=0, Cout=128, k=1, stride=2, pad=0, mode=0),
+    dict(B=2, Hi=64, Wi=64, c0=8, c1=0, up0=0, Cout=64, k=7, stride=2, pad=3, mode=0, stats=True),
+    dict(B=2, Hi=8, Wi=8, c0=256, c1=128, up0=1, Cout=128, k=3, stride=1, pad=1, mode=0, stats=True),
+    dict(B=1, Hi=32, Wi=32, c0=64, c1=64, up0=1, Cout=32, k=3, stride=1, pad=1, mode=0, relu=1, affine=True),
+    dict(B=1, Hi=64, Wi=64, c0=32, c1=0, up0=1, Cout=16, k=3, stride=1, pad=1, mode=0, stats=True),
+    dict(B=2, Hi=32, Wi=32, c0=16, c1=0, up0=0, Cout=3, k=3, stride=1, pad=1, mode=0, nchw=True),
+    dict(B=5, Hi=2, Wi=2, c0=512, c1=0, up0=0, Cout=512, k=3, stride=1, pad=1, mode=0),
+    dict(B=1, Hi=96, Wi=32, c0=16, c1=0, up0=0, Cout=16, k=3, stride=1, pad=1, mode=0, stats=True),   # ragged M tail
+    # dgrad (transposed gather)
+    dict(B=2, Hi=16, Wi=16, c0=64, c1=0, up0=0, Cout=64, k=3, stride=1, pad=1, mode=1, res=True),
+    dict(B=2, Hi=8, Wi=8, c0=128, c1=0, up0=0, Cout=64, k=3, stride=2, pad=1, mode=1),
+    dict(B=2, Hi=8, Wi=8, c0=128, c1=0, up0=0, Cout=64, k=1, stride=2, pad=0, mode=1, res=True),
+    dict(B=2, Hi=32, Wi=32, c0=8, c1=0, up0=0, Cout=16, k=3, stride=1, pad=1, mode=1),
+]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv(dtype, case):
+    r = _conv_case(dtype, **case)
+    for name, (g, c) in r.items():
+        tol = TOL[dtype] if name != "stats" else (1e-5 if dtype == _lib.F32 else 2e-2)
+        assert rel_err(g, c) < tol, (name, rel_err(g, c))
+
+
+WGRAD_CASES = [
+    dict(B=2, Hi=16, Wi=16, c0=64, c1=0, up0=0, Cout=64, k=3, stride=1, pad=1),
+    dict(B=2, Hi=16, Wi=16, c0=64, c1=0, up0=0, Cout=128, k=3, stride=2, pad=1),
+    dict(B=2, Hi=16, Wi=16, c0=64, c1=0, up0=0, Cout=128, k=1, stride=2, pad=0),
+    dict(B=2, Hi=64, Wi=64, c0=8, c1=0, up0=0, Cout=64, k=7, stride=2, pad=3, cin_real=3),
+    dict(B=2, Hi=8, Wi=8, c0=256, c1=128, up0=1, Cout=128, k=3, stride=1, pad=1),
+    dict(B=1, Hi=64, Wi=64, c0=32, c1=0, up0=1, Cout=16, k=3, stride=1, pad=1),
+    dict(B=2, Hi=32, Wi=32, c0=16, c1=0, up0=0, Cout=8, k=3, stride=1, pad=1, cout_real=3),
+    dict(B=7, Hi=2, Wi=2, c0=512, c1=0, up0=0, Cout=512, k=3, stride=1, pad=1),
+    dict(B=3, Hi=24, Wi=8, c0=16, c1=0, up0=0, Cout=16, k=3, stride=1, pad=1),
+]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("case", WGRAD_CASES)
+def test_wgrad(dtype, case):
+    c = dict(case)
+    B, Hi, Wi, c0, c1, up0, Cout, k, stride, pad = (c[x] for x in ("B", "Hi", "Wi", "c0", "c1", "up0", "Cout", "k", "stride", "pad"))
+    cin_real = c.get("cin_real", c0 + c1)
+    cout_real = c.get("cout_real", Cout)
+    g = torch.Generator().manual_seed(1)
+    Ho = (Hi + 2 * pad - k) // stride + 1
+    Wo = (Wi + 2 * pad - k) // stride + 1
+    t = {"src0": torch.randn(B, Hi >> up0, Wi >> up0, c0, generator=g), "dy": torch.randn(B, Ho, Wo, Cout, generator=g),
+         "dw": torch.zeros(cout_real, cin_real, k, k)}
+    if c1:
+        t["src1"] = torch.randn(B, Hi, Wi, c1, generator=g)
+    sc = dict(c0=c0, c1=c1, ld0=c0, ld1=c1, up0=up0, B=B, Hi=Hi, Wi=Wi, Ho=Ho, Wo=Wo, kh=k, kw=k, stride=stride, pad=pad,
+              ldy=Cout, Cout=Cout, cin_real=cin_real, cout_real=cout_real)
+    r = run_both(_lib.OP_WGRAD, dtype, t, sc, ["dw"])
+    gpu, cpu = r["dw"]
+    assert rel_err(gpu, cpu) < (2e-5 if dtype == _lib.F32 else 1e-2), rel_err(gpu, cpu)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_pack_and_layout(dtype):
+    g = torch.Generator().manual_seed(2)
+    t = {"w": torch.randn(64, 3, 7, 7, generator=g), "w_fwd": torch.zeros(64, 49 * 8), "w_dgrad": torch.zeros(3, 49 * 64)}
+    r = run_both(_lib.OP_PACK, dtype, t, dict(Cout=64, Cin=3, kh=7, kw=7, cin_pad=8, cout_pad=64), ["w_fwd", "w_dgrad"])
+    for n, (a, b) in r.items():
+        assert rel_err(a, b) < (1e-7 if dtype == _lib.F32 else 4e-3), n
+    t = {"src": torch.randn(3, 3, 32, 64, generator=g), "dst": torch.ones(3, 32, 64, 8)}
+    r = run_both(_lib.OP_NCHW2NHWC, dtype, t, dict(B=3, C=3, H=32, W=64, cpad=8), ["dst"])
+    assert rel_err(*r["dst"]) < (1e-7 if dtype == _lib.F32 else 4e-3)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("C,count,relu,res", [(64, 2 * 16 * 16, 1, True), (16, 3 * 64 * 64, 1, False), (512, 8, 0, False)])
+def test_bn_train_fwd_bwd(dtype, C, count, relu, res):
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(count, C, generator=g) * 2 + 0.5
+    xr = x if dtype == _lib.F32 else x.bfloat16().float()
+    stats = torch.stack([xr.double().sum(0), (xr.double() ** 2).sum(0)])
+    t = {"x": x, "y": torch.zeros(count, C), "stats": stats, "gamma": torch.rand(C, generator=g) + 0.5,
+         "beta": torch.randn(C, generator=g), "running_mean": torch.zeros(C), "running_var": torch.ones(C),
+         "num_batches_tracked": torch.zeros(1, dtype=torch.int64), "scale": torch.zeros(C), "shift": torch.zeros(C),
+         "mean": torch.zeros(C), "invstd": torch.zeros(C)}
+    sc = dict(C=C, relu=relu, count=count, ldx=C, ldy=C, eps=1e-5, momentum=0.1)
+    if res:
+        t["res"] = torch.randn(count, C, generator=g)
+        sc["ldr"] = C
+    r = run_both(_lib.OP_BN_FINALIZE, dtype, t, sc, ["scale", "shift", "mean", "invstd", "running_mean", "running_var", "num_batches_tracked"])
+    for n, (a, b) in r.items():
+        assert rel_err(a, b) < 1e-6, n
+    t["scale"], t["shift"], t["mean"], t["invstd"] = (r[k][1] for k in ("scale", "shift", "mean", "invstd"))
+    r = run_both(_lib.OP_BN_APPLY, dtype, t, sc, ["y"])
+    assert rel_err(*r["y"]) < (1e-6 if dtype == _lib.F32 else 4e-3)
+    # backward
+    t["act"] = r["y"][1]
+    t["dy"] = torch.randn(count, C, generator=g)
+    t["bstats"] = torch.zeros(2, C, dtype=torch.float64)
+    t["dgamma"], t["dbeta"], t["coef"] = torch.zeros(C), torch.zeros(C), torch.zeros(3, C)
+    t["dx"], t["dres"] = torch.zeros(count, C), torch.zeros(count, C)
+    sc.update(lddy=C, ldact=C, lddx=C, lddres=C)
+    t.pop("res", None), t.pop("y")
+    sc.pop("ldr", None)
+    r = run_both(_lib.OP_BN_BWD_REDUCE, dtype, t, sc, ["bstats"])
+    assert rel_err(*r["bstats"]) < (1e-6 if dtype == _lib.F32 else 1e-4)
+    t["bstats"] = r["bstats"][1].double()
+    r = run_both(_lib.OP_BN_BWD_FINALIZE, dtype, t, sc, ["dgamma", "dbeta", "coef"])
+    for n, (a, b) in r.items():
+        assert rel_err(a, b) < 1e-6, n
+    t["coef"] = r["coef"][1]
+    r = run_both(_lib.OP_BN_BWD_APPLY, dtype, t, sc, ["dx", "dres"])
+    for n, (a, b) in r.items():
+        assert rel_err(a, b) < (1e-5 if dtype == _lib.F32 else 6e-3), n
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_bn_fold(dtype):
+    C = 128
+    g = torch.Generator().manual_seed(4)
+    t = {"gamma": torch.rand(C, generator=g) + 0.5, "beta": torch.randn(C, generator=g), "running_mean": torch.randn(C, generator=g),
+         "running_var": torch.rand(C, generator=g) + 0.1, "scale": torch.zeros(C), "shift": torch.zeros(C)}
+    r = run_both(_lib.OP_BN_FOLD, dtype, t, dict(C=C, eps=1e-5), ["scale", "shift"])
+    for n, (a, b) in r.items():
+        assert rel_err(a, b) < 1e-6, n
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_pools(dtype):
+    g = torch.Generator().manual_seed(5)
+    B, H, W, C = 2, 32, 32, 64
+    x = torch.relu(torch.randn(B, H, W, C, generator=g))         # many exact ties at 0, like post-ReLU features
+    t = {"x": x, "y": torch.zeros(B, H // 2, W // 2, C), "idx": torch.zeros(B, H // 2, W // 2, C, dtype=torch.uint8)}
+    sc = dict(B=B, H=H, W=W, C=C, ldx=C, ldy=C)
+    r = run_both(_lib.OP_MAXPOOL_FWD, dtype, t, sc, ["y", "idx"])
+    assert rel_err(*r["y"]) == 0.0
+    assert torch.equal(r["idx"][0], r["idx"][1])
+    t = {"dy": torch.randn(B, H // 2, W // 2, C, generator=g), "idx": r["idx"][1].to(torch.uint8), "dx": torch.randn(B, H, W, C, generator=g)}
+    for acc in (0, 1):
+        r2 = run_both(_lib.OP_MAXPOOL_BWD, dtype, t, dict(B=B, H=H, W=W, C=C, lddy=C, lddx=C, accumulate=acc), ["dx"])
+        assert rel_err(*r2["dx"]) < (1e-6 if dtype == _lib.F32 else 5e-3)
+    t = {"dy": torch.randn(B, H, W, C, generator=g), "dx": torch.zeros(B, H // 2, W // 2, C)}
+    r3 = run_both(_lib.OP_SUMPOOL2, dtype, t, dict(B=B, H=H // 2, W=W // 2, C=C, lddy=C, lddx=C, accumulate=0), ["dx"])
+    assert rel_err(*r3["dx"]) < (1e-6 if dtype == _lib.F32 else 5e-3)
+    t = {"x": torch.randn(B * H * W, 8, generator=g), "out": torch.zeros(3)}
+    r4 = run_both(_lib.OP_CHANSUM, dtype, t, dict(C=3, ld=8, count=B * H * W), ["out"])
+    assert rel_err(*r4["out"]) < 1e-4
