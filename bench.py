@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the d3fk hot path (contract in the task statement, tier ④).
+
+Workload (BASELINE.json configs[1]): the d3f denoiser U-Net (smp resnet34 U-Net restated) at 64x64,
+bf16 tensor-core compute, batch 256 per GPU: one full training step = q_sample + U-Net forward +
+MSE/SSIM loss + U-Net backward + Adam, data-parallel over N GPUs with the NCCL gradient allreduce
+overlapped with backward.  metric = train img/s (whole job).  The same JSON line carries the sampling
+metric (img-steps/s, configs[2] shape: 128x128, batch 64 per GPU, CUDA-graph replayed steps) under
+"sample", the roofline of the dominant kernel family (tcgen05 implicit-GEMM convolutions) under
+"roofline", and the oracle's CPU step under "cpu_baseline".
+
+`--impl reference` times the reference path's CPU restatement (oracle/) on the host cores."""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FWD_GFLOP_PER_IMG_64 = 0.97910          # SURVEY §8d (2*MAC, convs only)
+STEM_DGRAD_GFLOP_64 = 0.01927
+METRIC = "train_img_per_s"
+UNIT = "img/s"
+
+
+def synthetic_faces(B, H, W, seed, device):
+    """Low-pass Gaussian field in [-1,1] (SURVEY §8d 'Synthetic inputs')."""
+    import torch
+    g = torch.Generator(device=device).manual_seed(seed)
+    x = 0.5 * torch.randn(B, 3, H, W, generator=g, device=device)
+    x = torch.nn.functional.avg_pool2d(x, 5, stride=1, padding=2) * 2.5
+    return x.clamp(-1, 1).contiguous()
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for n, v in zip(names, out[2:]):
+                    if v.strip().lower() == "active":
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons)}
+
+
+def cpu_train_step_rate(batch, H, W, steps, warmup, lam=5.0):
+    """The reference path restated (oracle/): q_sample + U-Net fwd/bwd + MSE/SSIM + Adam, fp32 eager on all
+    host threads.  Returns (img/s, threads)."""
+    import torch
+    import oracle
+    torch.set_num_threads(os.cpu_count())
+    torch.manual_seed(0)
+    model = oracle.Unet().train()
+    crit = oracle.MseStructuralSimilarityLoss(-1.0, 1.0)
+    opt = torch.optim.Adam(model.parameters(), lr=0.02)
+    x = synthetic_faces(batch, H, W, 1234, "cpu")
+    gen = torch.Generator().manual_seed(1)
+
+    def step():
+        noisy, _, _ = oracle.blend_random_amount_of_noise_with_each_sample(x, lam, gen)
+        loss = crit(model(noisy), x)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        return float(loss)
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return batch * steps / dt, torch.get_num_threads(), dt / steps
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample_batch = 32
+    rate, threads, spt = cpu_train_step_rate(sample_batch, 64, 64, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": spt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "d3f denoiser train step, resnet34 U-Net 64x64, batch 256/GPU (configs[1])",
+                   "sample": f"batch {sample_batch} of the 256 per step on the host CPU"},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{args.steps} steps of batch {sample_batch} @64x64 fp32 (oracle restatement; the "
+                                   f"reference's own modules need smp/piqa/lightning, not installed)"},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def conv_only_oplist(plan):
+    from denoising_diffusion_deep_fake_b200 import _lib
+    ops = [op for op in plan.fwd_ops if op.kind in (_lib.OP_CONV, _lib.OP_WGRAD)]
+    for seg in plan.bwd_segments or []:
+        ops += [op for op in seg if op.kind in (_lib.OP_CONV, _lib.OP_WGRAD)]
+    copies = []
+    import ctypes
+    for op in ops:                       # detach from the plan's arrays
+        c = _lib.Op()
+        ctypes.memmove(ctypes.byref(c), ctypes.byref(op), ctypes.sizeof(_lib.Op))
+        copies.append(c)
+    return _lib.OpList(copies), len(copies)
+
+
+def run_d3fk(args):
+    import torch
+    import torch.distributed as dist
+    import denoising_diffusion_deep_fake_b200 as d3
+    from denoising_diffusion_deep_fake_b200 import _lib
+    from denoising_diffusion_deep_fake_b200.train import DenoiserModule
+    from denoising_diffusion_deep_fake_b200.sampler import Sampler
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    B, H, W = args.batch, args.size, args.size
+    torch.manual_seed(0)
+    mod = DenoiserModule(encoder_name="resnet34", learning_rate=0.02, noise_exponential_sampling_lambda=5,
+                         cosine_scheduler_max_epoch=100, precision=args.precision, seed=1234 + rank).to(dev)
+    mod.train()
+    mod.configure_optimizers(fused=True)
+    if world > 1:
+        with torch.no_grad():                      # identical replicas
+            dist.broadcast(mod.optimizer.flat_p, src=0)
+        mod.enable_data_parallel()
+    x = synthetic_faces(B, H, W, 1234 + rank, dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident throughput ("value")
+    for _ in range(max(args.warmup, 3)):
+        loss = mod.training_step(x)
+    barrier()
+    clocks = ClockSampler(local)
+    clocks.start()
+    launches0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        loss = mod.training_step(x)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count() - launches0
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    value = world * B * args.steps / (ms / 1e3)
+    final_loss = float(loss)
+
+    # ---------------- end to end through the public API with host buffers ("e2e")
+    host = torch.empty((B, 3, H, W), dtype=torch.float32).pin_memory()
+    host.copy_(x)
+    xin = torch.empty_like(x)
+    for _ in range(2):
+        xin.copy_(host, non_blocking=True)
+        float(mod.training_step(xin))
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        xin.copy_(host, non_blocking=True)
+        l = mod.training_step(xin)
+        _ = float(l)                                # device->host read of the step's result
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_e2e], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = t.item()
+    e2e = world * B * args.steps / (ms_e2e / 1e3)
+    clocks.stop_flag = True
+    clocks.join(timeout=2)
+
+    # ---------------- roofline of the dominant kernel family: tcgen05 convolutions (fwd + dgrad + wgrad)
+    plan = next(p for plans in mod.model._plans.values() for p in plans if p.training)
+    conv_ops, n_conv = conv_only_oplist(plan)
+    stream = torch.cuda.current_stream().cuda_stream
+    for _ in range(2):
+        conv_ops.run(stream)
+    torch.cuda.synchronize()
+    reps = max(3, min(10, args.steps))
+    e0.record()
+    for _ in range(reps):
+        conv_ops.run(stream)
+    e1.record()
+    torch.cuda.synchronize()
+    conv_ms = e0.elapsed_time(e1) / reps
+    scale = (H * W) / (64.0 * 64.0)
+    conv_gflop = B * (3 * FWD_GFLOP_PER_IMG_64 - STEM_DGRAD_GFLOP_64) * scale
+    achieved = conv_gflop / conv_ms            # GFLOP/ms == TFLOP/s
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "conv_tc_kernel + wgrad_tc_kernel (tcgen05 implicit GEMM)",
+                "launches_per_step": n_conv, "ms_per_step": conv_ms,
+                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback",
+                "share_of_step": conv_ms / (ms / args.steps)}
+
+    # ---------------- sampling (configs[2] shape), batch-sharded, CUDA-graph replayed
+    sample = None
+    if not args.no_sample:
+        sb, ss, n_steps = args.sample_batch, args.sample_size, args.sample_steps
+        mod.model.eval()
+        smp = Sampler(mod.model, sb, ss, ss, n_steps, r_start=1.0, eta=1.0, seed=7 + rank, use_graph=True)
+        smp.run()
+        barrier()
+        e0.record()
+        smp.run()
+        e1.record()
+        barrier()
+        sms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([sms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            sms = t.item()
+        sample = {"metric": "sample_img_steps_per_s", "value": world * sb * n_steps / (sms / 1e3), "unit": "img-steps/s",
+                  "config": {"workload": f"{n_steps}-step DDPM sampling @{ss}x{ss}, batch {sb}/GPU, CUDA-graph replay"},
+                  "ms_per_step": sms / n_steps, "kernels_per_step": smp.kernels_per_step}
+        mod.model.train()
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        rate, threads, spt = cpu_train_step_rate(8, 64, 64, steps=10, warmup=3)
+        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": "10 steps of batch 8 @64x64 fp32 (BASELINE configs[0]) through oracle/ on the host cores"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "config": {"workload": f"d3f denoiser train step (q_sample+U-Net fwd/bwd+MSE/SSIM+Adam), resnet34 U-Net "
+                                   f"{H}x{W}, batch {B}/GPU (BASELINE configs[1])",
+                       "global_batch": world * B, "parallelism": f"dp{world}",
+                       "l2": "per-step working set (activations+gradients > 1 GB) exceeds the 126 MB L2"},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": host.numel() * 4, "d2h_bytes_per_step": 4},
+            "gpu_launches": int(launches), "clocks": clocks.summary(), "roofline": roofline, "cpu_baseline": cpu,
+            "sample": sample, "final_loss": final_loss,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="d3fk", choices=["d3fk", "reference"])
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--size", type=int, default=64)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--sample-batch", type=int, default=64)
+    ap.add_argument("--sample-size", type=int, default=128)
+    ap.add_argument("--sample-steps", type=int, default=50)
+    ap.add_argument("--no-sample", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_d3fk(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -114,7 +114,7 @@ SINGLE_ENTRY = {OP_CONV: "d3fk_conv", OP_WGRAD: "d3fk_wgrad", OP_PACK: "d3fk_pac
                 OP_CHANSUM: "d3fk_chansum", OP_QSAMPLE: "d3fk_q_sample", OP_POSTERIOR: "d3fk_posterior_step",
                 OP_ADAM: "d3fk_adam"}
 EXPORTS = ["d3fk_version", "d3fk_sizeof_op", "d3fk_init", "d3fk_last_error", "d3fk_device_error_flag", "d3fk_run",
-           "d3fk_launch_count"] + sorted(set(SINGLE_ENTRY.values()))
+           "d3fk_run_profile", "d3fk_launch_count"] + sorted(set(SINGLE_ENTRY.values()))
 
 
 def make_op(kind, **fields):
@@ -156,6 +156,7 @@ def load():
     lib.d3fk_launch_count.restype = C.c_int64
     lib.d3fk_run.argtypes = [C.POINTER(Op), C.c_int, vp]
     lib.d3fk_init.argtypes = [C.c_int]
+    lib.d3fk_run_profile.argtypes = [C.POINTER(Op), C.c_int, vp, C.POINTER(C.c_float)]
     for kind, name in SINGLE_ENTRY.items():
         getattr(lib, name).argtypes = [C.POINTER(_PARAM_CLS[_UNION_FIELD[kind]]), vp]
     if lib.d3fk_sizeof_op() != C.sizeof(Op):
@@ -190,6 +191,12 @@ class OpList:
 
     def run(self, stream_ptr):
         check(_lib.d3fk_run(self.array, self.n, stream_ptr))
+
+    def profile(self, stream_ptr):
+        """Per-op device milliseconds (CUDA events around every op; synchronises)."""
+        ms = (C.c_float * max(self.n, 1))()
+        check(_lib.d3fk_run_profile(self.array, self.n, stream_ptr, ms))
+        return list(ms)[:self.n]
 
     def __len__(self):
         return self.n

@@ -151,6 +151,27 @@ int d3fk_run(const d3fk_op* ops, int n_ops, d3fk_stream stream) {
   return D3FK_OK;
 }
 
+// profiling aid: per-op device time with CUDA events (allocates events; not for the hot path)
+int d3fk_run_profile(const d3fk_op* ops, int n_ops, d3fk_stream stream, float* ms_per_op) {
+  int rc = require_init();
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaEvent_t* ev = new cudaEvent_t[n_ops + 1];
+  for (int i = 0; i <= n_ops; ++i) cudaEventCreate(&ev[i]);
+  for (int i = 0; i < n_ops; ++i) {
+    cudaEventRecord(ev[i], s);
+    rc = run_one(&ops[i], s);
+    if (rc) break;
+  }
+  cudaEventRecord(ev[n_ops], s);
+  cudaStreamSynchronize(s);
+  if (!rc)
+    for (int i = 0; i < n_ops; ++i) cudaEventElapsedTime(&ms_per_op[i], ev[i], ev[i + 1]);
+  for (int i = 0; i <= n_ops; ++i) cudaEventDestroy(ev[i]);
+  delete[] ev;
+  return rc;
+}
+
 #define SINGLE(name, type, fn)                                   \
   int name(const type* p, d3fk_stream stream) {                  \
     int rc = require_init();                                     \

@@ -59,11 +59,13 @@ __global__ void __launch_bounds__(256) conv_ffma_kernel(Gather g, const float* _
   const int bn = n0 + lrow;
   const bool brow_ok = bn < e.Cout;
 
-  float acc[4][4];
+  // parity mode: each 16-deep chunk is summed in fp32 and folded into a double accumulator, so the
+  // result is the correctly rounded fp32 value for all practical purposes
+  double acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
 
   for (int kb = 0; kb < g.K; kb += FBK) {
     int k = kb + lk;
@@ -82,6 +84,11 @@ __global__ void __launch_bounds__(256) conv_ffma_kernel(Gather g, const float* _
     As[lk + 0][lrow] = av.x; As[lk + 1][lrow] = av.y; As[lk + 2][lrow] = av.z; As[lk + 3][lrow] = av.w;
     Bs[lk + 0][lrow] = bv.x; Bs[lk + 1][lrow] = bv.y; Bs[lk + 2][lrow] = bv.z; Bs[lk + 3][lrow] = bv.w;
     __syncthreads();
+    float part[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) part[i][j] = 0.f;
 #pragma unroll
     for (int kk = 0; kk < FBK; ++kk) {
       float a[4], b[4];
@@ -92,8 +99,12 @@ __global__ void __launch_bounds__(256) conv_ffma_kernel(Gather g, const float* _
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < 4; ++j) part[i][j] = fmaf(a[i], b[j], part[i][j]);
     }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] += (double)part[i][j];
     __syncthreads();
   }
 
@@ -107,7 +118,7 @@ __global__ void __launch_bounds__(256) conv_ffma_kernel(Gather g, const float* _
     for (int j = 0; j < 4; ++j) {
       int c = n0 + tx * 4 + j;
       if (c >= e.Cout) continue;
-      float v = acc[i][j];
+      float v = (float)acc[i][j];
       if (e.scale) v = fmaf(v, e.scale[c], e.shift ? e.shift[c] : 0.f);
       else if (e.shift) v += e.shift[c];
       if (e.res) v += ((const float*)e.res)[(long long)m * e.ldr + c];
@@ -175,11 +186,11 @@ __global__ void __launch_bounds__(256) wgrad_ffma_kernel(Gather g, const float* 
     khi = tap / g.kw;
     kwi = tap - khi * g.kw;
   }
-  float acc[4][4];
+  double acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
 
   for (int mb = mbeg; mb < mend; mb += FBK) {
     int m = mb + lm;
@@ -199,6 +210,11 @@ __global__ void __launch_bounds__(256) wgrad_ffma_kernel(Gather g, const float* 
     *reinterpret_cast<float4*>(&Ys[lm][lc]) = yv;
     *reinterpret_cast<float4*>(&As[lm][lc]) = av;
     __syncthreads();
+    float part[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) part[i][j] = 0.f;
 #pragma unroll
     for (int mm = 0; mm < FBK; ++mm) {
       float a[4], b[4];
@@ -209,8 +225,12 @@ __global__ void __launch_bounds__(256) wgrad_ffma_kernel(Gather g, const float* 
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < 4; ++j) part[i][j] = fmaf(a[i], b[j], part[i][j]);
     }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] += (double)part[i][j];
     __syncthreads();
   }
 #pragma unroll
@@ -224,7 +244,7 @@ __global__ void __launch_bounds__(256) wgrad_ffma_kernel(Gather g, const float* 
       int tap = kk / g.ctot;
       int ci = kk - tap * g.ctot;
       if (ci >= cin_real) continue;
-      atomicAdd(dw + ((long long)co * cin_real + ci) * (g.kh * g.kw) + tap, acc[i][j]);
+      atomicAdd(dw + ((long long)co * cin_real + ci) * (g.kh * g.kw) + tap, (float)acc[i][j]);
     }
   }
 }

@@ -1,0 +1,301 @@
+"""Training steps of the reference, re-hosted on the d3fk hot path (plain loop instead of Lightning).
+
+DenoiserModule mirrors d3f/train_denoiser/lit_module.py (training_step :107-126, noising :128-153,
+Adam + per-epoch cosine LR :92-100); DeepFakeModule mirrors d3f/train_deep_fake/lit_module.py
+(two models + EMA copies, `denoise` and `swap` modes :142-206, two Adam optimisers :113-125).
+Data-parallel training (new; the reference is single-GPU) follows PL-DDP semantics: per-rank BN
+statistics, mean-reduced gradients — one NCCL allreduce per backward segment, launched on a side
+stream as soon as that segment's gradients are final so it overlaps the rest of backward."""
+import copy
+import math
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .functional import adam_step_, q_sample
+from .loss import MseStructuralSimilarityLoss
+from .unet import Unet
+
+
+class FlatAdam:
+    """torch.optim.Adam semantics (eps outside the sqrt, no weight decay) as ONE fused kernel over the
+    model's flat parameter / gradient arenas; optional fused EMA lerp target."""
+
+    def __init__(self, model, lr, betas=(0.9, 0.999), eps=1e-8):
+        self.model = model
+        self.lr, self.betas, self.eps = lr, betas, eps
+        self.base_lr = lr
+        self.step_count = 0
+        dev = next(model.parameters()).device
+        model._ensure_grad_arena(dev)
+        n = model._grad_numel
+        self.flat_p = torch.zeros(n, dtype=torch.float32, device=dev)
+        for name, p in model._param_dict.items():
+            off = model._grad_offsets[name]
+            self.flat_p[off:off + p.numel()].copy_(p.data.reshape(-1))
+            p.data = self.flat_p[off:off + p.numel()].view(p.shape)
+        model.bind_flat_grads()
+        self.m = torch.zeros_like(self.flat_p)
+        self.v = torch.zeros_like(self.flat_p)
+
+    def check_aliasing(self):
+        name = self.model._param_names[0]
+        p = self.model._param_dict[name]
+        if p.data_ptr() != self.flat_p.data_ptr() + 4 * self.model._grad_offsets[name]:
+            raise RuntimeError("model parameters were re-allocated (.to()/.cuda()) after FlatAdam was built")
+
+    def step(self, ema_flat=None, ema_decay=0.0, grad_scale=1.0):
+        self.check_aliasing()
+        self.step_count += 1
+        adam_step_(self.flat_p, self.model._grad_arena, self.m, self.v, self.lr, self.betas[0], self.betas[1],
+                   self.eps, self.step_count, ema=ema_flat, ema_decay=ema_decay, grad_scale=grad_scale)
+        for p in self.model.parameters():       # in-place update invisible to autograd's version counters
+            break
+        self.model.__dict__["_stat_updates"] = self.model.__dict__.get("_stat_updates", 0) + 1
+
+    def state_dict(self):
+        return {"m": self.m, "v": self.v, "step": self.step_count, "lr": self.lr}
+
+    def load_state_dict(self, sd):
+        self.m.copy_(sd["m"]), self.v.copy_(sd["v"])
+        self.step_count, self.lr = sd["step"], sd["lr"]
+
+
+def cosine_lr(base_lr, epoch, t_max):
+    """torch CosineAnnealingLR closed form (eta_min = 0)."""
+    return base_lr * (1 + math.cos(math.pi * epoch / t_max)) / 2
+
+
+class GradAllReduce:
+    """Bucketed gradient mean over the data-parallel group, overlapped with backward."""
+
+    def __init__(self, model, group=None):
+        import torch.distributed as dist
+        self.dist, self.group, self.model = dist, group, model
+        dev = next(model.parameters()).device
+        self.comm = torch.cuda.Stream(dev)
+        self.buckets = model.grad_buckets()
+        model.__dict__["_dp_hook"] = self.after_segment
+        self.world = dist.get_world_size(group)
+
+    def after_segment(self, i):
+        cur = torch.cuda.current_stream()
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        self.comm.wait_event(ev)
+        s, e = self.buckets[i]
+        with torch.cuda.stream(self.comm):
+            self.dist.all_reduce(self.model._grad_arena[s:e], op=self.dist.ReduceOp.AVG, group=self.group)
+
+    def wait(self):
+        torch.cuda.current_stream().wait_stream(self.comm)
+
+
+class DenoiserModule(nn.Module):
+    """train_denoiser LitModule, minus Lightning.  hparams: encoder_name, learning_rate,
+    noise_exponential_sampling_lambda, cosine_scheduler_max_epoch (+ precision, seed: new)."""
+
+    def __init__(self, **hparams):
+        super().__init__()
+        self.hparams = dict(hparams)
+        p = self.hparams
+        self.model = Unet(encoder_name=p["encoder_name"], encoder_weights=None, in_channels=3, classes=3,
+                          activation=None, precision=p.get("precision", "bf16"))
+        self.training_criterion = MseStructuralSimilarityLoss(-1.0, 1.0)
+        self.global_step = 0
+        self.current_epoch = 0
+        self.optimizer = None
+        self.allreduce = None
+
+    def forward(self, image):
+        return self.model(image)
+
+    def configure_optimizers(self, fused=True):
+        p = self.hparams
+        if fused:
+            self.optimizer = FlatAdam(self.model, lr=p["learning_rate"])
+        else:
+            self.optimizer = torch.optim.Adam(self.model.parameters(), lr=p["learning_rate"])
+        return self.optimizer
+
+    def enable_data_parallel(self, group=None):
+        self.allreduce = GradAllReduce(self.model, group)
+
+    def blend_random_amount_of_noise_with_each_sample(self, batch, noise=None, y=None):
+        p = self.hparams
+        return q_sample(batch, p["noise_exponential_sampling_lambda"], noise=noise, y=y,
+                        seed=p.get("seed", 0), offset=self.global_step)
+
+    def training_step(self, image, noise=None, y=None):
+        """noising -> U-Net -> MSE+SSIM loss -> backward -> Adam (lit_module.py:107-126 + the optimiser step
+        Lightning would take).  Returns the loss tensor (no host sync)."""
+        image_noisy = self.blend_random_amount_of_noise_with_each_sample(image, noise, y)
+        image_prediction = self.model(image_noisy)
+        loss = self.training_criterion(image_prediction, image)
+        if not isinstance(self.optimizer, FlatAdam):
+            self.optimizer.zero_grad(set_to_none=True)
+        loss.backward()
+        if self.allreduce is not None:
+            self.allreduce.wait()
+        self.optimizer.step()
+        self.global_step += 1
+        return loss
+
+    def on_epoch_end(self):
+        self.current_epoch += 1
+        lr = cosine_lr(self.hparams["learning_rate"], self.current_epoch, self.hparams["cosine_scheduler_max_epoch"])
+        if isinstance(self.optimizer, FlatAdam):
+            self.optimizer.lr = lr
+        else:
+            for g in self.optimizer.param_groups:
+                g["lr"] = lr
+
+
+class EMA(nn.Module):
+    """ema_pytorch.EMA(model, beta, update_every, include_online_model=False) semantics:
+    copy for the first `update_after_step` updates, then lerp with decay
+    clamp(1-(1+(step-101)/inv_gamma)^-power, 0, beta) over float params and buffers."""
+
+    def __init__(self, model, beta=0.9999, update_after_step=100, update_every=10, inv_gamma=1.0, power=2 / 3,
+                 min_value=0.0, include_online_model=True):
+        super().__init__()
+        self.beta, self.update_after_step, self.update_every = beta, update_after_step, update_every
+        self.inv_gamma, self.power, self.min_value = inv_gamma, power, min_value
+        if include_online_model:
+            self.online_model = model
+        else:
+            self.online_model = [model]
+        self.ema_model = copy.deepcopy(model)
+        self.ema_model.requires_grad_(False)
+        self.register_buffer("initted", torch.tensor(False))
+        self.register_buffer("step", torch.tensor(0))
+        self._step_host = 0
+        self._initted_host = False
+
+    @property
+    def model(self):
+        return self.online_model if isinstance(self.online_model, nn.Module) else self.online_model[0]
+
+    def get_current_decay(self, step):
+        epoch = max(step - self.update_after_step - 1, 0)
+        if epoch <= 0:
+            return 0.0
+        value = 1 - (1 + epoch / self.inv_gamma) ** -self.power
+        return min(max(value, self.min_value), self.beta)
+
+    @torch.no_grad()
+    def _copy(self):
+        for e, m in zip(self.ema_model.parameters(), self.model.parameters()):
+            e.copy_(m)
+        for e, m in zip(self.ema_model.buffers(), self.model.buffers()):
+            e.copy_(m)
+
+    @torch.no_grad()
+    def update(self):
+        step = self._step_host
+        self._step_host += 1
+        self.step += 1
+        if step % self.update_every != 0:
+            return
+        if step <= self.update_after_step:
+            self._copy()
+            return
+        if not self._initted_host:
+            self._copy()
+            self._initted_host = True
+            self.initted.fill_(True)
+        decay = self.get_current_decay(self._step_host)
+        ep = [e for e in self.ema_model.parameters() if e.is_floating_point()]
+        mp = [m for e, m in zip(self.ema_model.parameters(), self.model.parameters()) if e.is_floating_point()]
+        eb = [e for e in self.ema_model.buffers() if e.is_floating_point()]
+        mb = [m for e, m in zip(self.ema_model.buffers(), self.model.buffers()) if e.is_floating_point()]
+        torch._foreach_lerp_(ep + eb, mp + mb, 1 - decay)
+
+    def forward(self, *a, **k):
+        return self.ema_model(*a, **k)
+
+
+class DeepFakeModule(nn.Module):
+    """train_deep_fake LitModule, minus Lightning: model_a/model_b (+ EMA copies in swap mode)."""
+
+    def __init__(self, **hparams):
+        super().__init__()
+        self.hparams = dict(hparams)
+        p = self.hparams
+        prec = p.get("precision", "bf16")
+        self.model_a = Unet(encoder_name=p["encoder_name"], precision=prec)
+        self.model_b = Unet(encoder_name=p["encoder_name"], precision=prec)
+        self.ema_model_a = self.create_ema_model(self.model_a)
+        self.ema_model_b = self.create_ema_model(self.model_b)
+        self.criterion = MseStructuralSimilarityLoss(-1.0, 1.0)
+        self.global_step = 0
+        self.current_epoch = 0
+        self.logged = {}
+
+    def create_ema_model(self, model):
+        p = self.hparams
+        if p["mode"] == "swap":
+            return EMA(model, beta=p["ema_beta"], update_every=p["ema_update_every"], include_online_model=False)
+        return None
+
+    def configure_optimizers(self):
+        p = self.hparams
+        betas = (p["adam_b1"], p["adam_b2"])
+        self.optimizer_a = torch.optim.Adam(self.model_a.parameters(), lr=p["learning_rate"], betas=betas)
+        self.optimizer_b = torch.optim.Adam(self.model_b.parameters(), lr=p["learning_rate"], betas=betas)
+        return [self.optimizer_a, self.optimizer_b]
+
+    def blend_random_amount_of_noise_with_each_sample(self, batch):
+        p = self.hparams
+        self._noise_calls = getattr(self, "_noise_calls", 0) + 1
+        return q_sample(batch, p["noise_exponential_sampling_lambda"], seed=p.get("seed", 0), offset=self._noise_calls)
+
+    def training_step(self, batch_a, batch_b):
+        """Both optimiser passes of one Lightning batch (lit_module.py:142-156)."""
+        out = {}
+        for name, real, real_model, fake_model, opt in (
+                ("a", batch_a, self.model_a, self.ema_model_b, self.optimizer_a),
+                ("b", batch_b, self.model_b, self.ema_model_a, self.optimizer_b)):
+            opt.zero_grad(set_to_none=True)
+            loss = self.training_step_for_one_model(name, real, real_model, fake_model)
+            loss.backward()
+            opt.step()
+            out[name] = loss
+        self.global_step += 1
+        return out
+
+    def training_step_for_one_model(self, name, real, real_model, fake_model):
+        if self.hparams["mode"] == "denoise":
+            return self.training_denoise_step_for_one_model(name, real, real_model)
+        return self.training_swap_step_for_one_model(name, real, real_model, fake_model)
+
+    def training_denoise_step_for_one_model(self, name, real, real_model):
+        with torch.no_grad():
+            noisy_real = self.blend_random_amount_of_noise_with_each_sample(real)
+        real_prediction = real_model(noisy_real)
+        loss = self.criterion(real_prediction, real)
+        self.logged[f"loss_denoise/train_{name}"] = loss.detach()
+        return loss
+
+    def training_swap_step_for_one_model(self, name, real, real_model, fake_model):
+        fake_model.update()
+        with torch.no_grad():
+            fake = fake_model(real)                        # one pass, BN in train mode as in the reference
+            swap_diff = nn.functional.mse_loss(real, fake)
+            noisy_fake = self.blend_random_amount_of_noise_with_each_sample(fake)
+        real_prediction = real_model(noisy_fake)
+        loss = self.criterion(real_prediction, real)
+        self.logged[f"swap_difference/{name}"] = swap_diff
+        self.logged[f"loss_swap/train_{name}"] = loss.detach()
+        return loss
+
+    @torch.no_grad()
+    def predict_fake(self, real, model_a_or_b):
+        """Batched tensor-level predict_fake (lit_module.py:251-270): normalised [B,3,H,W] in, same out."""
+        model = self.model_a if model_a_or_b == "a" else self.model_b
+        was = model.training
+        model.eval()
+        out = model(real)
+        model.train(was)
+        return out

@@ -184,6 +184,10 @@ int d3fk_device_error_flag(void);         /* non-zero if a kernel hit its barrie
 /* run a recorded op list on `stream` (the hot path: one call per U-Net forward / backward) */
 int d3fk_run(const d3fk_op* ops, int n_ops, d3fk_stream stream);
 
+/* profiling aid: as d3fk_run, but brackets every op with CUDA events and returns per-op milliseconds
+ * (synchronises the stream; allocates events — never used on the hot path) */
+int d3fk_run_profile(const d3fk_op* ops, int n_ops, d3fk_stream stream, float* ms_per_op);
+
 /* single-op entry points (same launchers; used by the per-op parity tests) */
 int d3fk_conv(const d3fk_conv_params* p, d3fk_stream stream);
 int d3fk_wgrad(const d3fk_wgrad_params* p, d3fk_stream stream);

@@ -8,7 +8,7 @@ import op_interpreter as I
 
 T_FIELDS = {"src0", "src1", "w", "out", "res", "dy", "x", "y", "act", "dx", "dres", "dst", "w_fwd", "w_dgrad"}
 # fields that are dtype-typed only for some ops
-_NOT_T = {(_lib.OP_PACK, "w"), (_lib.OP_NCHW2NHWC, "src")}
+_NOT_T = {(_lib.OP_PACK, "w"), (_lib.OP_NCHW2NHWC, "src"), (_lib.OP_CHANSUM, "out")}
 
 
 def _is_t(kind, name):
