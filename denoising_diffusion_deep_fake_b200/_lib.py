@@ -18,7 +18,7 @@ class ConvParams(C.Structure):
                 ("kh", i32), ("kw", i32), ("stride", i32), ("pad", i32),
                 ("w", vp), ("Cout", i32), ("_pad0", i32),
                 ("out", vp), ("out_nchw", vp), ("scale", vp), ("shift", vp), ("res", vp), ("stats", vp),
-                ("ldo", i32), ("ldr", i32), ("relu", i32), ("_pad1", i32)]
+                ("ldo", i32), ("ldr", i32), ("relu", i32), ("_pad1", i32), ("ws", vp), ("ws_bytes", i64)]
 
 
 class WgradParams(C.Structure):

@@ -8,6 +8,7 @@
 //
 // Warp roles (160 threads): warps 0-3 = gather producers, then epilogue (TMEM lane quarter = warp);
 // warp 4 = TMEM allocator + single-thread MMA issuer.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace d3fk {
@@ -152,264 +153,6 @@ struct EpiTC {
   int ldo, ldr, relu, Cout, Ho, Wo;
 };
 
-constexpr int TC_THREADS = 160;
-constexpr int TC_BM = 128;
-constexpr int TC_BK = 64;                 // bf16 elements = 128 bytes = one swizzle row
-constexpr int A_STAGE_BYTES = TC_BM * 128;
-
-template <int BN> struct ConvCfg {
-  static constexpr int STAGES = BN >= 128 ? 3 : 4;
-  static constexpr int B_STAGE_BYTES = BN * 128;
-  static constexpr int SMEM = 1024 + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256 + 2 * BN * 4;
-  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
-};
-
-// ------------------------------------------------------------------------------------------
-template <int BN>
-__global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(Gather g, const bf16* __restrict__ w, EpiTC e, int* errflag) {
-  using Cfg = ConvCfg<BN>;
-  constexpr int STAGES = Cfg::STAGES;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t a_base = base;
-  const uint32_t b_base = base + STAGES * A_STAGE_BYTES;
-  const uint32_t bar_base = b_base + STAGES * Cfg::B_STAGE_BYTES;  // full[S], empty[S], accum, tmem ptr
-  uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
-  uint8_t* gen_bar = gen_base + STAGES * (A_STAGE_BYTES + Cfg::B_STAGE_BYTES);
-  volatile uint32_t* tmem_ptr_slot = reinterpret_cast<volatile uint32_t*>(gen_bar + 8 * (2 * STAGES + 1));
-  float* s_stat = reinterpret_cast<float*>(gen_bar + 256);  // [2][BN]
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-  const uint32_t accum_bar = bar_base + 8u * (2 * STAGES);
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * BN;
-  const int nkb = (g.K + TC_BK - 1) / TC_BK;
-
-  if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar(s), 128);
-      mbar_init(empty_bar(s), 1);
-    }
-    mbar_init(accum_bar, 1);
-    fence_barrier_init();
-  }
-  if (tid < 2 * BN) s_stat[tid] = 0.f;
-  if (BN > 64 && tid + TC_THREADS < 2 * BN) s_stat[tid + TC_THREADS] = 0.f;
-  if (warp == 4) tmem_alloc(smem_u32((const void*)tmem_ptr_slot), Cfg::TMEM_COLS);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_d = *tmem_ptr_slot;
-
-  if (warp < 4) {
-    // ===================== producers: asynchronous swizzled gather =====================
-    const int j = tid & 7;    // 16-byte chunk (8 channels) within the 128-byte k-row
-    const int rb = tid >> 3;  // rows rb + 16*i
-    const uint32_t sw = (uint32_t)((j ^ (rb & 7)) << 4);
-    int rn[8], rh[8], rw[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      int m = m0 + rb + 16 * i;
-      if (m < g.M) {
-        int wo = m % g.Wo;
-        int t = m / g.Wo;
-        int ho = t % g.Ho;
-        rn[i] = t / g.Ho;
-        if (g.mode == 0) { rh[i] = ho * g.stride - g.pad; rw[i] = wo * g.stride - g.pad; }
-        else { rh[i] = ho + g.pad; rw[i] = wo + g.pad; }
-      } else {
-        rn[i] = -1; rh[i] = 0; rw[i] = 0;
-      }
-    }
-    int k = j * 8;
-    int tap = k / g.ctot;
-    int c = k - tap * g.ctot;
-    int khi = tap / g.kw, kwi = tap - khi * g.kw;
-    for (int kb = 0; kb < nkb; ++kb) {
-      const int s = kb % STAGES;
-      if (kb >= STAGES) mbar_wait(empty_bar(s), ((kb / STAGES) - 1) & 1, errflag);
-      const bool k_ok = k < g.K;
-      const uint32_t a_dst = a_base + s * A_STAGE_BYTES + rb * 128 + sw;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const void* src = g.src0;
-        uint32_t bytes = 0;
-        if (k_ok && rn[i] >= 0) {
-          int which;
-          long long off = gather_offset(g, rn[i], rh[i], rw[i], khi, kwi, c, which);
-          if (off >= 0) {
-            src = (which ? (const bf16*)g.src1 : (const bf16*)g.src0) + off;
-            bytes = 16;
-          }
-        }
-        cp_async_16(a_dst + i * (16 * 128), src, bytes);
-      }
-      const uint32_t b_dst = b_base + s * Cfg::B_STAGE_BYTES + rb * 128 + sw;
-#pragma unroll
-      for (int i = 0; i < BN / 16; ++i) {
-        int n = n0 + rb + 16 * i;
-        bool ok = k_ok && n < e.Cout;
-        const void* src = ok ? (const void*)(w + (long long)n * g.K + k) : (const void*)w;
-        cp_async_16(b_dst + i * (16 * 128), src, ok ? 16u : 0u);
-      }
-      cp_async_mbar_arrive(full_bar(s));
-      mbar_arrive(full_bar(s));
-      // advance the k state by one 64-wide block
-      k += TC_BK;
-      c += TC_BK;
-      while (c >= g.ctot) {
-        c -= g.ctot;
-        if (++kwi == g.kw) { kwi = 0; ++khi; }
-      }
-    }
-
-    // ===================== epilogue: TMEM -> registers -> global =====================
-    mbar_wait(accum_bar, 0, errflag);
-    tc_fence_after();
-    const int row = warp * 32 + lane;
-    const int m = m0 + row;
-    const bool row_ok = m < g.M;
-    constexpr int CW = BN >= 32 ? 32 : 16;
-    int on = 0, oh = 0, ow = 0;
-    if (e.out_nchw && row_ok) {
-      ow = m % e.Wo;
-      int t = m / e.Wo;
-      oh = t % e.Ho;
-      on = t / e.Ho;
-    }
-#pragma unroll 1
-    for (int cc = 0; cc < BN; cc += CW) {
-      uint32_t raw[CW];
-      const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)cc;
-      if (CW == 32) tmem_ld32(taddr, raw); else tmem_ld16(taddr, raw);
-      tmem_ld_wait();
-      float f[CW];
-#pragma unroll
-      for (int i = 0; i < CW; ++i) f[i] = __uint_as_float(raw[i]);
-      const int cbase = n0 + cc;
-      if (e.scale) {
-#pragma unroll
-        for (int i = 0; i < CW; ++i)
-          if (cbase + i < e.Cout) f[i] = fmaf(f[i], __ldg(e.scale + cbase + i), __ldg(e.shift + cbase + i));
-      } else if (e.shift) {
-#pragma unroll
-        for (int i = 0; i < CW; ++i)
-          if (cbase + i < e.Cout) f[i] += __ldg(e.shift + cbase + i);
-      }
-      if (e.res && row_ok) {
-        const uint4* rp = reinterpret_cast<const uint4*>(e.res + (long long)m * e.ldr + cbase);
-#pragma unroll
-        for (int q = 0; q < CW / 8; ++q) {
-          uint4 rr = __ldg(rp + q);
-          const bf16* rb16 = reinterpret_cast<const bf16*>(&rr);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) f[q * 8 + i] += __bfloat162float(rb16[i]);
-        }
-      }
-      if (e.relu) {
-#pragma unroll
-        for (int i = 0; i < CW; ++i) f[i] = fmaxf(f[i], 0.f);
-      }
-      if (row_ok) {
-        if (e.out_nchw) {
-#pragma unroll
-          for (int i = 0; i < CW; ++i)
-            if (cbase + i < e.Cout) e.out_nchw[(((long long)on * e.Cout + cbase + i) * e.Ho + oh) * e.Wo + ow] = f[i];
-        } else {
-          uint4* op = reinterpret_cast<uint4*>(e.out + (long long)m * e.ldo + cbase);
-#pragma unroll
-          for (int q = 0; q < CW / 8; ++q) {
-            uint4 o;
-            __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) o2[i] = __floats2bfloat162_rn(f[q * 8 + 2 * i], f[q * 8 + 2 * i + 1]);
-            op[q] = o;
-          }
-        }
-      }
-      if (e.stats) {
-        float sq[CW];
-#pragma unroll
-        for (int i = 0; i < CW; ++i) {
-          if (!row_ok) f[i] = 0.f;
-          sq[i] = f[i] * f[i];
-        }
-        float cs, cq;
-        if (CW == 32) { cs = warp_colsum32(f, lane); cq = warp_colsum32(sq, lane); }
-        else { cs = warp_colsum16(f, lane); cq = warp_colsum16(sq, lane); }
-        if (lane < CW) {
-          atomicAdd(&s_stat[cc + lane], cs);
-          atomicAdd(&s_stat[BN + cc + lane], cq);
-        }
-      }
-    }
-    if (e.stats) {
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (tid < BN && n0 + tid < e.Cout) {
-        atomicAdd(&e.stats[n0 + tid], (double)s_stat[tid]);
-        atomicAdd(&e.stats[e.Cout + n0 + tid], (double)s_stat[BN + tid]);
-      }
-    }
-  } else {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(TC_BM, BN, 0, 0);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES;
-        mbar_wait(full_bar(s), (kb / STAGES) & 1, errflag);
-        fence_proxy_async();
-        tc_fence_after();
-        const uint32_t a_addr = a_base + s * A_STAGE_BYTES;
-        const uint32_t b_addr = b_base + s * Cfg::B_STAGE_BYTES;
-#pragma unroll
-        for (int kk = 0; kk < TC_BK / 16; ++kk) {
-          uint64_t ad = make_smem_desc(a_addr + kk * 32, 16, 1024);
-          uint64_t bd = make_smem_desc(b_addr + kk * 32, 16, 1024);
-          umma_f16(tmem_d, ad, bd, idesc, (kb | kk) ? 1u : 0u);
-        }
-        umma_commit(empty_bar(s));
-      }
-      umma_commit(accum_bar);
-    }
-    __syncwarp();
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_d, Cfg::TMEM_COLS);
-}
-
-template <int BN>
-static int launch_conv_tc_bn(const Gather& g, const d3fk_conv_params* p, cudaStream_t s) {
-  EpiTC e{(bf16*)p->out, p->out_nchw, p->scale, p->shift, (const bf16*)p->res, p->stats, p->ldo, p->ldr, p->relu, p->Cout, p->Ho, p->Wo};
-  dim3 grid(cdiv(g.M, TC_BM), cdiv(p->Cout, BN));
-  conv_tc_kernel<BN><<<grid, TC_THREADS, ConvCfg<BN>::SMEM, s>>>(g, (const bf16*)p->w, e, g_dev_error_flag);
-  count_launch();
-  return check_launch("conv_tc");
-}
-
-int launch_conv_tc(const d3fk_conv_params* p, cudaStream_t s) {
-  Gather g;
-  int rc = make_gather(g, p->src0, p->src1, p->c0, p->c1, p->ld0, p->ld1, p->up0, p->B, p->Hi, p->Wi, p->Ho, p->Wo, p->kh,
-                       p->kw, p->stride, p->pad, p->mode);
-  if (rc) return rc;
-  D3FK_CHECK_ARG(p->out || p->out_nchw, "no output");
-  D3FK_CHECK_ARG(p->out_nchw || (p->ldo % 8 == 0), "ldo must be a multiple of 8");
-  D3FK_CHECK_ARG(!p->scale || p->shift, "scale requires shift");
-  const int C = p->Cout;
-  if (C <= 16) return launch_conv_tc_bn<16>(g, p, s);
-  D3FK_CHECK_ARG(p->out_nchw == nullptr, "out_nchw only for Cout <= 16");
-  if (C % 128 == 0) return launch_conv_tc_bn<128>(g, p, s);
-  if (C % 64 == 0) return launch_conv_tc_bn<64>(g, p, s);
-  if (C % 32 == 0) return launch_conv_tc_bn<32>(g, p, s);
-  return set_error(D3FK_ERR_UNSUPPORTED, "conv_tc: Cout=%d (need <=16 or a multiple of 32)", C);
-}
-
-// ------------------------------------------------------------------------------------------
-// weight gradient.  Stage = 64 pixels (the MMA K dimension, 4 x K16).
-//   A stage: 2 column blocks (64 k-columns each) x [64 pixels x 128 B]   (MN-major, M = k index)
-//   B stage: BN/64 column blocks (64 channels each) x [64 pixels x 128 B] (MN-major, N = co)
 struct FastDiv {
   uint32_t mul, shr;
 };
@@ -423,6 +166,425 @@ static FastDiv make_fastdiv(uint32_t d) {
 }
 __device__ __forceinline__ uint32_t fdiv(uint32_t n, FastDiv f) { return (__umulhi(f.mul, n) + n) >> f.shr; }
 
+constexpr int TC_THREADS = 160;
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;                 // bf16 elements = 128 bytes = one swizzle row
+constexpr int A_STAGE_BYTES = TC_BM * 128;
+
+template <int BN> struct ConvCfg {
+  static constexpr int STAGES = BN >= 128 ? 3 : 4;
+  static constexpr int B_STAGE_BYTES = BN * 128;
+  static constexpr int SMEM = 1024 + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256 + 8 * BN * 4;
+  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+};
+
+// Tile schedule: tile t -> (m tile, k split, n tile); consecutive CTAs walk consecutive m tiles.
+struct TileSched {
+  int MT, NT, KS, kb_per_split, nkb, total;
+};
+
+// PATH 0 (LINEAR): one source, no upsample, forward gather or stride-1 transposed gather — the tap
+//   offset is the same for every row, so a row costs two compares, one 64-bit add and the cp.async.
+// PATH 1 (GENERIC): nearest-2x upsample + channel concat (decoder conv1) and stride-2 transposed gather.
+template <int BN, int PATH>
+__global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(Gather g, FastDiv dWo, FastDiv dHo, const bf16* __restrict__ w,
+                                                             EpiTC e, TileSched ts, float* __restrict__ ws, int* errflag) {
+  using Cfg = ConvCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_base = base;
+  const uint32_t b_base = base + STAGES * A_STAGE_BYTES;
+  const uint32_t bar_base = b_base + STAGES * Cfg::B_STAGE_BYTES;  // full[S], empty[S], accum, tmem ptr
+  uint8_t* gen_bar = smem_raw + (base - smem_u32(smem_raw)) + STAGES * (A_STAGE_BYTES + Cfg::B_STAGE_BYTES);
+  volatile uint32_t* tmem_ptr_slot = reinterpret_cast<volatile uint32_t*>(gen_bar + 8 * (2 * STAGES + 1));
+  float* s_stat = reinterpret_cast<float*>(gen_bar + 256);  // [4 warps][2][BN]
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  const uint32_t accum_bar = bar_base + 8u * (2 * STAGES);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 128);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(accum_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc(smem_u32((const void*)tmem_ptr_slot), Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_ptr_slot;
+
+  if (warp < 4) {
+    const int j = tid & 7;    // 16-byte chunk (8 channels) within the 128-byte k-row
+    const int rb = tid >> 3;  // rows rb + 16*i
+    const uint32_t sw = (uint32_t)((j ^ (rb & 7)) << 4);
+    const int sgn = g.mode ? -1 : 1;
+    const uint32_t smask = g.mode ? (uint32_t)(g.stride - 1) : 0u;   // transposed gather: coordinate must be a multiple
+    const int sshift = g.mode ? g.sshift : 0;                        // of the stride (forward folds it into h0/w0)
+    uint32_t kbg = 0;  // k-blocks issued by this CTA so far (pipeline stage / phase bookkeeping)
+    uint32_t tile_iter = 0;
+    for (int t = blockIdx.x; t < ts.total; t += gridDim.x, ++tile_iter) {
+      const int mt = t % ts.MT;
+      const int r_ = t / ts.MT;
+      const int ks = r_ % ts.KS;
+      const int nt = r_ / ts.KS;
+      const int m0 = mt * TC_BM, n0 = nt * BN;
+      const int kb0 = ks * ts.kb_per_split;
+      const int kb1 = min(ts.nkb, kb0 + ts.kb_per_split);
+
+      // ---- per-row state
+      int rh[8], rw[8];
+      int rn[8];                    // GENERIC: image index
+      const bf16* rp[8];            // LINEAR: pointer of (n, h0, w0, channel 0) in src0
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int m = m0 + rb + 16 * i;
+        int n = 0, h0 = -(1 << 28), w0 = 0;
+        if (m < g.M) {
+          const uint32_t q = fdiv((uint32_t)m, dWo);
+          const int wo = m - (int)q * g.Wo;
+          n = (int)fdiv(q, dHo);
+          const int ho = (int)q - n * g.Ho;
+          if (g.mode == 0) { h0 = ho * g.stride - g.pad; w0 = wo * g.stride - g.pad; }
+          else { h0 = ho + g.pad; w0 = wo + g.pad; }
+        }
+        rh[i] = h0; rw[i] = w0;
+        if (PATH == 0) rp[i] = (const bf16*)g.src0 + ((long long)(n * g.Hi + h0) * g.Wi + w0) * g.ld0;
+        else rn[i] = n;
+      }
+      // ---- k state of this thread's chunk at the first k-block of the split
+      int k = kb0 * TC_BK + j * 8;
+      int tap = k / g.ctot;
+      int c = k - tap * g.ctot;
+      int khi = tap / g.kw, kwi = tap - khi * g.kw;
+      // B rows of this thread
+      const bf16* wp = w + (long long)(n0 + rb) * g.K;
+
+      for (int kb = kb0; kb < kb1; ++kb, ++kbg) {
+        const int s = kbg % STAGES;
+        if (kbg >= STAGES) mbar_wait(empty_bar(s), ((kbg / STAGES) - 1) & 1, errflag);
+        const bool k_ok = k < g.K;
+        const uint32_t a_dst = a_base + s * A_STAGE_BYTES + rb * 128 + sw;
+        const int dkh = sgn * khi, dkw = sgn * kwi;
+        if (PATH == 0) {
+          const long long koff = (long long)(dkh * g.Wi + dkw) * g.ld0 + c;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const bool ok = k_ok && (unsigned)(rh[i] + dkh) < (unsigned)g.Hi && (unsigned)(rw[i] + dkw) < (unsigned)g.Wi;
+            const void* src = ok ? (const void*)(rp[i] + koff) : g.src0;
+            cp_async_16(a_dst + i * (16 * 128), src, ok ? 16u : 0u);
+          }
+        } else {
+          const bool second = c >= g.c0;
+          const bf16* sb = second ? (const bf16*)g.src1 + (c - g.c0) : (const bf16*)g.src0 + c;
+          const int ld = second ? g.ld1 : g.ld0;
+          const int up = second ? 0 : g.up0;
+          const int hs = g.Hi >> up, wsz = g.Wi >> up;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int th = rh[i] + dkh, tw = rw[i] + dkw;
+            const int hi = th >> sshift, wi = tw >> sshift;
+            const bool ok = k_ok && (((uint32_t)(th | tw)) & (0x80000000u | smask)) == 0 && hi < g.Hi && wi < g.Wi;
+            const long long pix = (long long)((rn[i] * hs + (hi >> up)) * wsz + (wi >> up));
+            const void* src = ok ? (const void*)(sb + pix * ld) : g.src0;
+            cp_async_16(a_dst + i * (16 * 128), src, ok ? 16u : 0u);
+          }
+        }
+        const uint32_t b_dst = b_base + s * Cfg::B_STAGE_BYTES + rb * 128 + sw;
+#pragma unroll
+        for (int i = 0; i < BN / 16; ++i) {
+          const bool ok = k_ok && (n0 + rb + 16 * i) < e.Cout;
+          const void* src = ok ? (const void*)(wp + (long long)(16 * i) * g.K + k) : (const void*)w;
+          cp_async_16(b_dst + i * (16 * 128), src, ok ? 16u : 0u);
+        }
+        cp_async_mbar_arrive(full_bar(s));
+        mbar_arrive(full_bar(s));
+        k += TC_BK;
+        c += TC_BK;
+        while (c >= g.ctot) {
+          c -= g.ctot;
+          if (++kwi == g.kw) { kwi = 0; ++khi; }
+        }
+      }
+
+      // ===================== epilogue: TMEM -> registers -> global =====================
+      mbar_wait(accum_bar, tile_iter & 1, errflag);
+      tc_fence_after();
+      const int row = warp * 32 + lane;
+      const int m = m0 + row;
+      const bool row_ok = m < g.M;
+      constexpr int CW = BN >= 32 ? 32 : 16;
+      const bool split = ts.KS > 1;
+      const bool do_stats = e.stats != nullptr && !split;
+      int on = 0, oh = 0, ow = 0;
+      if (e.out_nchw && row_ok) {
+        const uint32_t q = fdiv((uint32_t)m, dWo);
+        ow = m - (int)q * e.Wo;
+        on = (int)fdiv(q, dHo);
+        oh = (int)q - on * e.Ho;
+      }
+#pragma unroll 1
+      for (int cc = 0; cc < BN; cc += CW) {
+        uint32_t raw[CW];
+        const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)cc;
+        if (CW == 32) tmem_ld32(taddr, raw); else tmem_ld16(taddr, raw);
+        tmem_ld_wait();
+        const int cbase = n0 + cc;
+        if (split) {
+          // split-K: plain fp32 partial tile; conv_splitk_finish sums the splits and runs the epilogue
+          if (row_ok) {
+            float4* wp4 = reinterpret_cast<float4*>(ws + ((long long)ks * g.M + m) * e.Cout + cbase);
+#pragma unroll
+            for (int q = 0; q < CW / 4; ++q)
+              wp4[q] = make_float4(__uint_as_float(raw[4 * q]), __uint_as_float(raw[4 * q + 1]),
+                                   __uint_as_float(raw[4 * q + 2]), __uint_as_float(raw[4 * q + 3]));
+          }
+          continue;
+        }
+        float f[CW];
+#pragma unroll
+        for (int i = 0; i < CW; ++i) f[i] = __uint_as_float(raw[i]);
+        if (e.scale) {
+#pragma unroll
+          for (int i = 0; i < CW; ++i)
+            if (cbase + i < e.Cout) f[i] = fmaf(f[i], __ldg(e.scale + cbase + i), __ldg(e.shift + cbase + i));
+        } else if (e.shift) {
+#pragma unroll
+          for (int i = 0; i < CW; ++i)
+            if (cbase + i < e.Cout) f[i] += __ldg(e.shift + cbase + i);
+        }
+        if (e.res && row_ok) {
+          const uint4* rp4 = reinterpret_cast<const uint4*>(e.res + (long long)m * e.ldr + cbase);
+#pragma unroll
+          for (int q = 0; q < CW / 8; ++q) {
+            uint4 rr = __ldg(rp4 + q);
+            const bf16* rb16 = reinterpret_cast<const bf16*>(&rr);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[q * 8 + i] += __bfloat162float(rb16[i]);
+          }
+        }
+        if (e.relu) {
+#pragma unroll
+          for (int i = 0; i < CW; ++i) f[i] = fmaxf(f[i], 0.f);
+        }
+        if (row_ok) {
+          if (e.out_nchw) {
+#pragma unroll
+            for (int i = 0; i < CW; ++i)
+              if (cbase + i < e.Cout) e.out_nchw[(((long long)on * e.Cout + cbase + i) * e.Ho + oh) * e.Wo + ow] = f[i];
+          } else {
+            uint4* op = reinterpret_cast<uint4*>(e.out + (long long)m * e.ldo + cbase);
+#pragma unroll
+            for (int q = 0; q < CW / 8; ++q) {
+              uint4 o;
+              __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) o2[i] = __floats2bfloat162_rn(f[q * 8 + 2 * i], f[q * 8 + 2 * i + 1]);
+              op[q] = o;
+            }
+          }
+        }
+        if (do_stats) {
+          float sq[CW];
+#pragma unroll
+          for (int i = 0; i < CW; ++i) {
+            if (!row_ok) f[i] = 0.f;
+            sq[i] = f[i] * f[i];
+          }
+          float cs, cq;
+          if (CW == 32) { cs = warp_colsum32(f, lane); cq = warp_colsum32(sq, lane); }
+          else { cs = warp_colsum16(f, lane); cq = warp_colsum16(sq, lane); }
+          if (lane < CW) {           // per-warp slots: no shared-memory atomics, deterministic
+            s_stat[warp * 2 * BN + cc + lane] = cs;
+            s_stat[warp * 2 * BN + BN + cc + lane] = cq;
+          }
+        }
+      }
+      if (do_stats) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (tid < BN && n0 + tid < e.Cout) {
+          const float a = (s_stat[tid] + s_stat[2 * BN + tid]) + (s_stat[4 * BN + tid] + s_stat[6 * BN + tid]);
+          const float b = (s_stat[BN + tid] + s_stat[3 * BN + tid]) + (s_stat[5 * BN + tid] + s_stat[7 * BN + tid]);
+          atomicAdd(&e.stats[n0 + tid], (double)a);
+          atomicAdd(&e.stats[e.Cout + n0 + tid], (double)b);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");   // slots are rewritten by the next tile
+      }
+      tc_fence_before();   // order this tile's TMEM reads before the next tile's first full-barrier arrival
+    }
+  } else {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(TC_BM, BN, 0, 0);
+      uint32_t kbg = 0;
+      for (int t = blockIdx.x; t < ts.total; t += gridDim.x) {
+        const int ks = (t / ts.MT) % ts.KS;
+        const int kb0 = ks * ts.kb_per_split;
+        const int kb1 = min(ts.nkb, kb0 + ts.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb, ++kbg) {
+          const int s = kbg % STAGES;
+          mbar_wait(full_bar(s), (kbg / STAGES) & 1, errflag);
+          fence_proxy_async();
+          tc_fence_after();
+          const uint32_t a_addr = a_base + s * A_STAGE_BYTES;
+          const uint32_t b_addr = b_base + s * Cfg::B_STAGE_BYTES;
+#pragma unroll
+          for (int kk = 0; kk < TC_BK / 16; ++kk) {
+            uint64_t ad = make_smem_desc(a_addr + kk * 32, 16, 1024);
+            uint64_t bd = make_smem_desc(b_addr + kk * 32, 16, 1024);
+            umma_f16(tmem_d, ad, bd, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(s));
+        }
+        umma_commit(accum_bar);
+      }
+    }
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_d, Cfg::TMEM_COLS);
+}
+
+// split-K second pass: sum the fp32 partial tiles, run the conv epilogue, emit BN statistics
+__global__ void __launch_bounds__(256) conv_splitk_finish_kernel(const float* __restrict__ ws, int KS, int M, EpiTC e) {
+  extern __shared__ float s_red[];  // [2][Cout]
+  const int N = e.Cout, cvs = N / 8;
+  const bool do_stats = e.stats != nullptr;
+  if (do_stats) {
+    for (int i = threadIdx.x; i < 2 * N; i += blockDim.x) s_red[i] = 0.f;
+    __syncthreads();
+  }
+  const int rows_per_iter = blockDim.x / cvs;
+  const int cv = threadIdx.x % cvs, prow = threadIdx.x / cvs;
+  const int c = cv * 8;
+  float s1[8], s2[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
+  if (prow < rows_per_iter) {
+    for (int m = blockIdx.x * rows_per_iter + prow; m < M; m += gridDim.x * rows_per_iter) {
+      float f[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] = 0.f;
+      for (int ks = 0; ks < KS; ++ks) {
+        const float4* p = reinterpret_cast<const float4*>(ws + ((long long)ks * M + m) * N + c);
+        float4 a = __ldg(p), b = __ldg(p + 1);
+        f[0] += a.x; f[1] += a.y; f[2] += a.z; f[3] += a.w; f[4] += b.x; f[5] += b.y; f[6] += b.z; f[7] += b.w;
+      }
+      if (e.scale) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i], __ldg(e.scale + c + i), __ldg(e.shift + c + i));
+      } else if (e.shift) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] += __ldg(e.shift + c + i);
+      }
+      if (e.res) {
+        uint4 rr = __ldg(reinterpret_cast<const uint4*>(e.res + (long long)m * e.ldr + c));
+        const bf16* rb16 = reinterpret_cast<const bf16*>(&rr);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] += __bfloat162float(rb16[i]);
+      }
+      if (e.relu) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
+      }
+      uint4 o;
+      __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o2[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+      *reinterpret_cast<uint4*>(e.out + (long long)m * e.ldo + c) = o;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { s1[i] += f[i]; s2[i] += f[i] * f[i]; }
+    }
+    if (do_stats) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        atomicAdd(&s_red[c + i], s1[i]);
+        atomicAdd(&s_red[N + c + i], s2[i]);
+      }
+    }
+  }
+  if (do_stats) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * N; i += blockDim.x) atomicAdd(&e.stats[i], (double)s_red[i]);
+  }
+}
+
+static int g_num_sms = 148;
+static int g_tile_loop = 1;   // D3FK_TILE_LOOP=0: one CTA per tile (debug aid)
+
+template <int BN, int PATH>
+static int launch_conv_tc_bn(const Gather& g, const d3fk_conv_params* p, cudaStream_t s) {
+  EpiTC e{(bf16*)p->out, p->out_nchw, p->scale, p->shift, (const bf16*)p->res, p->stats, p->ldo, p->ldr, p->relu, p->Cout, p->Ho, p->Wo};
+  TileSched ts;
+  ts.MT = cdiv(g.M, TC_BM);
+  ts.NT = cdiv(p->Cout, BN);
+  ts.nkb = cdiv(g.K, TC_BK);
+  ts.KS = 1;
+  const int tiles = ts.MT * ts.NT;
+  // split K when the output tiles cannot fill the chip and the reduction is long
+  if (p->ws && !p->out_nchw && p->Cout % BN == 0 && tiles < g_num_sms && ts.nkb >= 8) {
+    int ks = cdiv(2 * g_num_sms, tiles);
+    if (ks > ts.nkb / 4) ks = ts.nkb / 4;
+    if (ks > 16) ks = 16;
+    while (ks > 1 && (long long)ks * g.M * p->Cout * 4 > p->ws_bytes) --ks;
+    if (ks > 1) ts.KS = ks;
+  }
+  ts.kb_per_split = cdiv(ts.nkb, ts.KS);
+  ts.KS = cdiv(ts.nkb, ts.kb_per_split);
+  ts.total = tiles * ts.KS;
+  const int occ = (227 * 1024) / (ConvCfg<BN>::SMEM + 1024);
+  int grid = ts.total < g_num_sms * occ ? ts.total : g_num_sms * occ;
+  if (!g_tile_loop) grid = ts.total;
+  conv_tc_kernel<BN, PATH><<<grid, TC_THREADS, ConvCfg<BN>::SMEM, s>>>(g, make_fastdiv((uint32_t)g.Wo), make_fastdiv((uint32_t)g.Ho),
+                                                                    (const bf16*)p->w, e, ts, (float*)p->ws, g_dev_error_flag);
+  count_launch();
+  int rc = check_launch("conv_tc");
+  if (rc || ts.KS == 1) return rc;
+  const int cvs = p->Cout / 8;
+  int threads = 256;
+  if (cvs > threads) threads = cvs;
+  const int rows = threads / cvs;
+  int fgrid = cdiv(g.M, rows * 4);
+  if (fgrid > g_num_sms * 8) fgrid = g_num_sms * 8;
+  conv_splitk_finish_kernel<<<fgrid, threads, 2 * p->Cout * sizeof(float), s>>>((const float*)p->ws, ts.KS, g.M, e);
+  count_launch();
+  return check_launch("conv_splitk_finish");
+}
+
+template <int PATH>
+static int launch_conv_tc_path(const Gather& g, const d3fk_conv_params* p, cudaStream_t s) {
+  const int C = p->Cout;
+  if (C <= 16) return launch_conv_tc_bn<16, PATH>(g, p, s);
+  D3FK_CHECK_ARG(p->out_nchw == nullptr, "out_nchw only for Cout <= 16");
+  if (C % 128 == 0) return launch_conv_tc_bn<128, PATH>(g, p, s);
+  if (C % 64 == 0) return launch_conv_tc_bn<64, PATH>(g, p, s);
+  if (C % 32 == 0) return launch_conv_tc_bn<32, PATH>(g, p, s);
+  return set_error(D3FK_ERR_UNSUPPORTED, "conv_tc: Cout=%d (need <=16 or a multiple of 32)", C);
+}
+
+int launch_conv_tc(const d3fk_conv_params* p, cudaStream_t s) {
+  Gather g;
+  int rc = make_gather(g, p->src0, p->src1, p->c0, p->c1, p->ld0, p->ld1, p->up0, p->B, p->Hi, p->Wi, p->Ho, p->Wo, p->kh,
+                       p->kw, p->stride, p->pad, p->mode);
+  if (rc) return rc;
+  D3FK_CHECK_ARG(p->out || p->out_nchw, "no output");
+  D3FK_CHECK_ARG(p->out_nchw || (p->ldo % 8 == 0), "ldo must be a multiple of 8");
+  D3FK_CHECK_ARG(!p->scale || p->shift, "scale requires shift");
+  const bool linear = p->c1 == 0 && p->up0 == 0 && (p->mode == 0 || p->stride == 1);
+  return linear ? launch_conv_tc_path<0>(g, p, s) : launch_conv_tc_path<1>(g, p, s);
+}
+
+// ------------------------------------------------------------------------------------------
+// weight gradient.  Stage = 64 pixels (the MMA K dimension, 4 x K16).
+//   A stage: 2 column blocks (64 k-columns each) x [64 pixels x 128 B]   (MN-major, M = k index)
+//   B stage: BN/64 column blocks (64 channels each) x [64 pixels x 128 B] (MN-major, N = co)
 constexpr int WG_PIX = 64;
 constexpr int WG_A_STAGE = 2 * WG_PIX * 128;
 template <int BN> struct WgradCfg {
@@ -477,16 +639,23 @@ __global__ void __launch_bounds__(TC_THREADS) wgrad_tc_kernel(Gather g, FastDiv 
     const int rb = tid >> 3;  // pixel rows rb + 16*i, i < 4
     const uint32_t sw = (uint32_t)((j ^ (rb & 7)) << 4);
     // the two k chunks (column blocks 0/1) this thread gathers are fixed for the whole kernel
-    int kc[2], kkh[2], kkw[2];
+    const bf16* sb[2];
+    int kkh[2], kkw[2], sld[2], sup[2], shs[2], sws[2];
     bool kok[2];
 #pragma unroll
     for (int cb = 0; cb < 2; ++cb) {
-      int k = k0 + cb * 64 + j * 8;
+      const int k = k0 + cb * 64 + j * 8;
       kok[cb] = k < g.K;
-      int tap = kok[cb] ? k / g.ctot : 0;
-      kc[cb] = kok[cb] ? k - tap * g.ctot : 0;
+      const int tap = kok[cb] ? k / g.ctot : 0;
+      const int kc = kok[cb] ? k - tap * g.ctot : 0;
       kkh[cb] = tap / g.kw;
       kkw[cb] = tap - kkh[cb] * g.kw;
+      const bool second = kc >= g.c0;
+      sb[cb] = second ? (const bf16*)g.src1 + (kc - g.c0) : (const bf16*)g.src0 + kc;
+      sld[cb] = second ? g.ld1 : g.ld0;
+      sup[cb] = second ? 0 : g.up0;
+      shs[cb] = g.Hi >> sup[cb];
+      sws[cb] = g.Wi >> sup[cb];
     }
     for (int it = 0; it < nblk; ++it) {
       const int s = it % STAGES;
@@ -497,27 +666,22 @@ __global__ void __launch_bounds__(TC_THREADS) wgrad_tc_kernel(Gather g, FastDiv 
         const int prow = rb + 16 * i;
         const int m = mbase + prow;
         const bool m_ok = m < g.M;
-        int n = 0, ho = 0, wo = 0;
+        int n = 0, h0 = -(1 << 28), w0 = 0;
         if (m_ok) {
-          uint32_t t = fdiv((uint32_t)m, dWo);
-          wo = m - (int)t * g.Wo;
+          const uint32_t t = fdiv((uint32_t)m, dWo);
+          const int wo = m - (int)t * g.Wo;
           n = (int)fdiv(t, dHo);
-          ho = (int)t - n * g.Ho;
+          const int ho = (int)t - n * g.Ho;
+          h0 = ho * g.stride - g.pad;
+          w0 = wo * g.stride - g.pad;
         }
-        const int h0 = ho * g.stride - g.pad, w0 = wo * g.stride - g.pad;
 #pragma unroll
         for (int cb = 0; cb < 2; ++cb) {
-          const void* src = g.src0;
-          uint32_t bytes = 0;
-          if (m_ok && kok[cb]) {
-            int which;
-            long long off = gather_offset(g, n, h0, w0, kkh[cb], kkw[cb], kc[cb], which);
-            if (off >= 0) {
-              src = (which ? (const bf16*)g.src1 : (const bf16*)g.src0) + off;
-              bytes = 16;
-            }
-          }
-          cp_async_16(a_base + s * WG_A_STAGE + cb * (WG_PIX * 128) + prow * 128 + sw, src, bytes);
+          const int hi = h0 + kkh[cb], wi = w0 + kkw[cb];
+          const bool ok = kok[cb] && (unsigned)hi < (unsigned)g.Hi && (unsigned)wi < (unsigned)g.Wi;
+          const long long pix = (long long)((n * shs[cb] + (hi >> sup[cb])) * sws[cb] + (wi >> sup[cb]));
+          const void* src = ok ? (const void*)(sb[cb] + pix * sld[cb]) : g.src0;
+          cp_async_16(a_base + s * WG_A_STAGE + cb * (WG_PIX * 128) + prow * 128 + sw, src, ok ? 16u : 0u);
         }
 #pragma unroll
         for (int cb = 0; cb < Cfg::NCB; ++cb) {
@@ -613,12 +777,21 @@ int launch_wgrad_tc(const d3fk_wgrad_params* p, cudaStream_t s) {
 
 int tc_init() {
   cudaError_t e = cudaSuccess;
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
+    g_num_sms = sms;
+  const char* tl = getenv("D3FK_TILE_LOOP");
+  if (tl) g_tile_loop = atoi(tl);
 #define SET_SMEM(k, bytes)                                                                          \
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-  SET_SMEM(conv_tc_kernel<16>, ConvCfg<16>::SMEM)
-  SET_SMEM(conv_tc_kernel<32>, ConvCfg<32>::SMEM)
-  SET_SMEM(conv_tc_kernel<64>, ConvCfg<64>::SMEM)
-  SET_SMEM(conv_tc_kernel<128>, ConvCfg<128>::SMEM)
+  SET_SMEM((conv_tc_kernel<16, 0>), ConvCfg<16>::SMEM)
+  SET_SMEM((conv_tc_kernel<32, 0>), ConvCfg<32>::SMEM)
+  SET_SMEM((conv_tc_kernel<64, 0>), ConvCfg<64>::SMEM)
+  SET_SMEM((conv_tc_kernel<128, 0>), ConvCfg<128>::SMEM)
+  SET_SMEM((conv_tc_kernel<16, 1>), ConvCfg<16>::SMEM)
+  SET_SMEM((conv_tc_kernel<32, 1>), ConvCfg<32>::SMEM)
+  SET_SMEM((conv_tc_kernel<64, 1>), ConvCfg<64>::SMEM)
+  SET_SMEM((conv_tc_kernel<128, 1>), ConvCfg<128>::SMEM)
   SET_SMEM(wgrad_tc_kernel<64>, WgradCfg<64>::SMEM)
   SET_SMEM(wgrad_tc_kernel<128>, WgradCfg<128>::SMEM)
 #undef SET_SMEM

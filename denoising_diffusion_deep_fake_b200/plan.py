@@ -15,6 +15,7 @@ from ._lib import make_op, op_params
 
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
+SPLITK_WS_BYTES = 64 << 20
 CIN_PAD = 8  # RGB input / 3-channel head gradient are zero padded to 8 channels (16-byte bf16 gather chunks)
 
 
@@ -124,6 +125,8 @@ class UnetPlan:
         self.param_ptrs = {}
         self._alloc_weights()
         self._alloc_bn()
+        # fp32 scratch for split-K convolutions (deep layers whose output tiles cannot fill 148 SMs)
+        self.ws = self._new((SPLITK_WS_BYTES // 4,), torch.float32) if dtype == _lib.BF16 else None
         self.pack_ops = _lib.OpList(self._build_pack())
         self.saved = {}
         fwd = self._build_forward()
@@ -220,6 +223,8 @@ class UnetPlan:
         f = dict(dtype=self.dtype, mode=0, src0=src0.ptr, c0=src0.C, ld0=src0.ld, up0=up0,
                  B=self.B, Hi=Hi, Wi=Wi, Ho=Ho, Wo=Wo, kh=c.k, kw=c.k, stride=c.stride, pad=c.pad,
                  w=self.w_fwd[c.name].data_ptr(), Cout=c.cout, relu=relu)
+        if self.ws is not None:
+            f.update(ws=self.ws.data_ptr(), ws_bytes=SPLITK_WS_BYTES)
         if src1 is not None:
             f.update(src1=src1.ptr, c1=src1.C, ld1=src1.ld)
         if out is not None:
@@ -334,6 +339,8 @@ class UnetPlan:
                  Ho=out.H, Wo=out.W, kh=c.k, kw=c.k, stride=c.stride, pad=c.pad,
                  w=self.w_dgrad[c.name].data_ptr() + row0 * c.k * c.k * cout_pad * wbytes, Cout=rows,
                  out=out.ptr, ldo=out.ld)
+        if self.ws is not None:
+            f.update(ws=self.ws.data_ptr(), ws_bytes=SPLITK_WS_BYTES)
         if res is not None:
             f.update(res=res.ptr, ldr=res.ld)
         return make_op(_lib.OP_CONV, **f)

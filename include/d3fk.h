@@ -58,6 +58,7 @@ typedef struct d3fk_conv_params {
   const void* res;
   double* stats;
   int32_t ldo, ldr, relu, _pad1;
+  void* ws; int64_t ws_bytes;   /* optional fp32 scratch for split-K (layers whose tiles cannot fill the chip) */
 } d3fk_conv_params;
 
 /* ---- weight gradient (replaces cuDNN wgrad): dw[co][ci][kh][kw] += sum_{n,ho,wo} dy[n,ho,wo,co] * A[...]

@@ -15,7 +15,7 @@ DTYPES = [_lib.F32, _lib.BF16]
 
 
 def _conv_case(dtype, B, Hi, Wi, c0, c1, up0, Cout, k, stride, pad, mode, relu=0, res=False, affine=False,
-               stats=False, nchw=False, seed=0):
+               stats=False, nchw=False, seed=0, splitk=False):
     g = torch.Generator().manual_seed(seed)
     ctot = c0 + c1
     if mode == 0:
@@ -46,6 +46,9 @@ def _conv_case(dtype, B, Hi, Wi, c0, c1, up0, Cout, k, stride, pad, mode, relu=0
     if stats:
         t["stats"] = torch.zeros(2, Cout, dtype=torch.float64)
         outs.append("stats")
+    if splitk:
+        t["ws"] = torch.zeros(4 << 20)
+        sc["ws_bytes"] = 16 << 20
     return run_both(_lib.OP_CONV, dtype, t, sc, outs)
 
 
@@ -62,6 +65,13 @@ CONV_CASES = [
     dict(B=2, Hi=32, Wi=32, c0=16, c1=0, up0=0, Cout=3, k=3, stride=1, pad=1, mode=0, nchw=True),
     dict(B=5, Hi=2, Wi=2, c0=512, c1=0, up0=0, Cout=512, k=3, stride=1, pad=1, mode=0),
     dict(B=1, Hi=96, Wi=32, c0=16, c1=0, up0=0, Cout=16, k=3, stride=1, pad=1, mode=0, stats=True),   # ragged M tail
+    # split-K (deep layers: few output tiles, long reduction)
+    dict(B=16, Hi=4, Wi=4, c0=256, c1=0, up0=0, Cout=256, k=3, stride=1, pad=1, mode=0, stats=True, splitk=True),
+    dict(B=9, Hi=2, Wi=2, c0=512, c1=0, up0=0, Cout=512, k=3, stride=1, pad=1, mode=0, relu=1, res=True, affine=True, splitk=True),
+    dict(B=4, Hi=4, Wi=4, c0=512, c1=256, up0=1, Cout=256, k=3, stride=1, pad=1, mode=0, stats=True, splitk=True),
+    dict(B=8, Hi=2, Wi=2, c0=512, c1=0, up0=0, Cout=256, k=3, stride=2, pad=1, mode=1, res=True, splitk=True),
+    # many tiles per CTA (persistent tile loop)
+    dict(B=16, Hi=64, Wi=64, c0=16, c1=0, up0=0, Cout=16, k=3, stride=1, pad=1, mode=0, stats=True),
     # dgrad (transposed gather)
     dict(B=2, Hi=16, Wi=16, c0=64, c1=0, up0=0, Cout=64, k=3, stride=1, pad=1, mode=1, res=True),
     dict(B=2, Hi=8, Wi=8, c0=128, c1=0, up0=0, Cout=64, k=3, stride=2, pad=1, mode=1),
