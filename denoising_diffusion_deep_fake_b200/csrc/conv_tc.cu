@@ -9,7 +9,9 @@
 // Warp roles (160 threads): warps 0-3 = gather producers, then epilogue (TMEM lane quarter = warp);
 // warp 4 = TMEM allocator + single-thread MMA issuer.
 #include <stdlib.h>
+#include <string.h>
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace d3fk {
 
@@ -40,6 +42,9 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
       : "memory");
   return ok;
 }
+// NOTE: no fence.proxy.async between the full-barrier wait and tcgen05.mma: cp.async completion is tracked by
+// the mbarrier itself (ARRIVES.LDGSTSBAR), as in CUTLASS's sm100 cp.async mainloop; the fence lowers to
+// MEMBAR.ALL.CTA, which drains every in-flight LDGSTS of the CTA and serialises the whole pipeline.
 // bounded wait: a barrier that never completes sets the device error flag instead of hanging the GPU
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* errflag) {
   for (uint32_t it = 0;; ++it) {
@@ -52,6 +57,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* er
 }
 __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint32_t bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+}
+// L1-allocating variant: the 3x3 taps of a tile re-read the same input lines, so the activation gather can hit L1
+__device__ __forceinline__ void cp_async_16_ca(uint32_t dst, const void* src, uint32_t bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -166,7 +175,8 @@ static FastDiv make_fastdiv(uint32_t d) {
 }
 __device__ __forceinline__ uint32_t fdiv(uint32_t n, FastDiv f) { return (__umulhi(f.mul, n) + n) >> f.shr; }
 
-constexpr int TC_THREADS = 160;
+constexpr int TC_THREADS = 192;   // warps 0-3 gather/epilogue, warp 4 MMA issuer, warp 5 TMA producer
+constexpr int WG_THREADS = 160;   // weight-gradient kernel: warps 0-3 gather/epilogue, warp 4 MMA issuer
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;                 // bf16 elements = 128 bytes = one swizzle row
 constexpr int A_STAGE_BYTES = TC_BM * 128;
@@ -175,43 +185,58 @@ template <int BN> struct ConvCfg {
   static constexpr int STAGES = BN >= 128 ? 3 : 4;
   static constexpr int B_STAGE_BYTES = BN * 128;
   static constexpr int SMEM = 1024 + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256 + 8 * BN * 4;
-  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  static constexpr int ACC_COLS = BN < 32 ? 32 : BN;   // one accumulator buffer
+  static constexpr int TMEM_COLS = 2 * ACC_COLS;        // double buffered: epilogue of tile i overlaps MMAs of tile i+1
 };
 
 // Tile schedule: tile t -> (m tile, k split, n tile); consecutive CTAs walk consecutive m tiles.
 struct TileSched {
-  int MT, NT, KS, kb_per_split, nkb, total;
+  int MT, NT, KS, kb_per_split, nkb, total, a_ca;
+  int bw, bh, bn, wt, ht;   // PATH 2: the 128-pixel M tile as a (w, h, n) box and the tile grid along w / h
 };
 
 // PATH 0 (LINEAR): one source, no upsample, forward gather or stride-1 transposed gather — the tap
 //   offset is the same for every row, so a row costs two compares, one 64-bit add and the cp.async.
 // PATH 1 (GENERIC): nearest-2x upsample + channel concat (decoder conv1) and stride-2 transposed gather.
+// PATH 2 (TMA): stride-1 "same" convolutions with Cin % 64 == 0 and power-of-two extents: the A tile of tap (kh,kw)
+//   is the NHWC box {64 channels, bw, bh, bn} shifted by the tap offset, loaded by ONE cp.async.bulk.tensor.4d with
+//   hardware zero fill for the padding halo — no per-thread address arithmetic at all.
+// The weight tile is always a TMA 2-D box {64, BN} of the packed [Cout][K] matrix (OOB rows / K tail zero filled).
 template <int BN, int PATH>
-__global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(Gather g, FastDiv dWo, FastDiv dHo, const bf16* __restrict__ w,
-                                                             EpiTC e, TileSched ts, float* __restrict__ ws, int* errflag) {
+__global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(Gather g, FastDiv dWo, FastDiv dHo, const __grid_constant__ CUtensorMap tmA,
+                                                             const __grid_constant__ CUtensorMap tmB, EpiTC e, TileSched ts,
+                                                             float* __restrict__ ws, int* errflag) {
   using Cfg = ConvCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = base;
   const uint32_t b_base = base + STAGES * A_STAGE_BYTES;
-  const uint32_t bar_base = b_base + STAGES * Cfg::B_STAGE_BYTES;  // full[S], empty[S], accum, tmem ptr
+  const uint32_t bar_base = b_base + STAGES * Cfg::B_STAGE_BYTES;  // full[S], empty[S], acc_full[2], acc_empty[2], tmem ptr
   uint8_t* gen_bar = smem_raw + (base - smem_u32(smem_raw)) + STAGES * (A_STAGE_BYTES + Cfg::B_STAGE_BYTES);
-  volatile uint32_t* tmem_ptr_slot = reinterpret_cast<volatile uint32_t*>(gen_bar + 8 * (2 * STAGES + 1));
+  volatile uint32_t* tmem_ptr_slot = reinterpret_cast<volatile uint32_t*>(gen_bar + 8 * (2 * STAGES + 4));
   float* s_stat = reinterpret_cast<float*>(gen_bar + 256);  // [4 warps][2][BN]
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-  const uint32_t accum_bar = bar_base + 8u * (2 * STAGES);
+  auto acc_full_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + b); };
+  auto acc_empty_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar(s), 128);
+      mbar_init(full_bar(s), PATH == 2 ? 1 : 129);   // 128 gather threads + the TMA thread's expect_tx arrive
       mbar_init(empty_bar(s), 1);
     }
-    mbar_init(accum_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(acc_full_bar(b), 1);
+      mbar_init(acc_empty_bar(b), 128);
+    }
     fence_barrier_init();
+  }
+  if (warp == 5 && lane == 0) {
+    tma_prefetch_desc(&tmB);
+    if (PATH == 2) tma_prefetch_desc(&tmA);
   }
   if (warp == 4) tmem_alloc(smem_u32((const void*)tmem_ptr_slot), Cfg::TMEM_COLS);
   tc_fence_before();
@@ -219,7 +244,50 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(Gather g, FastDiv d
   tc_fence_after();
   const uint32_t tmem_d = *tmem_ptr_slot;
 
-  if (warp < 4) {
+  if (warp == 5) {
+    // ===================== TMA producer (one thread) =====================
+    if (lane == 0) {
+      uint32_t kbg = 0;
+      const int sgn = g.mode ? -1 : 1;
+      const int off = g.mode ? g.pad : -g.pad;
+      for (int t = blockIdx.x; t < ts.total; t += gridDim.x) {
+        const int mt = t % ts.MT;
+        const int r_ = t / ts.MT;
+        const int ks = r_ % ts.KS;
+        const int nt = r_ / ts.KS;
+        const int kb0 = ks * ts.kb_per_split;
+        const int kb1 = min(ts.nkb, kb0 + ts.kb_per_split);
+        int w0 = 0, h0 = 0, i0 = 0, tap = 0, c = 0, khi = 0, kwi = 0;
+        if (PATH == 2) {
+          const int tw = mt % ts.wt;
+          const int r2 = mt / ts.wt;
+          w0 = tw * ts.bw + off;
+          h0 = (r2 % ts.ht) * ts.bh + off;
+          i0 = (r2 / ts.ht) * ts.bn;
+          const int k = kb0 * TC_BK;
+          tap = k / g.ctot;
+          c = k - tap * g.ctot;
+          khi = tap / g.kw;
+          kwi = tap - khi * g.kw;
+        }
+        for (int kb = kb0; kb < kb1; ++kb, ++kbg) {
+          const int s = kbg % STAGES;
+          if (kbg >= STAGES) mbar_wait(empty_bar(s), ((kbg / STAGES) - 1) & 1, errflag);
+          mbar_arrive_expect_tx(full_bar(s), Cfg::B_STAGE_BYTES + (PATH == 2 ? A_STAGE_BYTES : 0));
+          tma_load_2d(b_base + s * Cfg::B_STAGE_BYTES, &tmB, kb * TC_BK, nt * BN, full_bar(s));
+          if (PATH == 2) {
+            tma_load_4d(a_base + s * A_STAGE_BYTES, &tmA, c, w0 + sgn * kwi, h0 + sgn * khi, i0, full_bar(s));
+            c += TC_BK;
+            if (c >= g.ctot) {
+              c = 0;
+              if (++kwi == g.kw) { kwi = 0; ++khi; }
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp < 4) {
     const int j = tid & 7;    // 16-byte chunk (8 channels) within the 128-byte k-row
     const int rb = tid >> 3;  // rows rb + 16*i
     const uint32_t sw = (uint32_t)((j ^ (rb & 7)) << 4);
@@ -237,83 +305,79 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(Gather g, FastDiv d
       const int kb0 = ks * ts.kb_per_split;
       const int kb1 = min(ts.nkb, kb0 + ts.kb_per_split);
 
-      // ---- per-row state
-      int rh[8], rw[8];
-      int rn[8];                    // GENERIC: image index
-      const bf16* rp[8];            // LINEAR: pointer of (n, h0, w0, channel 0) in src0
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int m = m0 + rb + 16 * i;
-        int n = 0, h0 = -(1 << 28), w0 = 0;
-        if (m < g.M) {
-          const uint32_t q = fdiv((uint32_t)m, dWo);
-          const int wo = m - (int)q * g.Wo;
-          n = (int)fdiv(q, dHo);
-          const int ho = (int)q - n * g.Ho;
-          if (g.mode == 0) { h0 = ho * g.stride - g.pad; w0 = wo * g.stride - g.pad; }
-          else { h0 = ho + g.pad; w0 = wo + g.pad; }
+      if (PATH != 2) {
+        // ---- per-row state
+        int rh[8], rw[8];
+        int rn[8];                    // GENERIC: image index
+        const bf16* rp[8];            // LINEAR: pointer of (n, h0, w0, channel 0) in src0
+  #pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int m = m0 + rb + 16 * i;
+          int n = 0, h0 = -(1 << 28), w0 = 0;
+          if (m < g.M) {
+            const uint32_t q = fdiv((uint32_t)m, dWo);
+            const int wo = m - (int)q * g.Wo;
+            n = (int)fdiv(q, dHo);
+            const int ho = (int)q - n * g.Ho;
+            if (g.mode == 0) { h0 = ho * g.stride - g.pad; w0 = wo * g.stride - g.pad; }
+            else { h0 = ho + g.pad; w0 = wo + g.pad; }
+          }
+          rh[i] = h0; rw[i] = w0;
+          if (PATH == 0) rp[i] = (const bf16*)g.src0 + ((long long)(n * g.Hi + h0) * g.Wi + w0) * g.ld0;
+          else rn[i] = n;
         }
-        rh[i] = h0; rw[i] = w0;
-        if (PATH == 0) rp[i] = (const bf16*)g.src0 + ((long long)(n * g.Hi + h0) * g.Wi + w0) * g.ld0;
-        else rn[i] = n;
-      }
-      // ---- k state of this thread's chunk at the first k-block of the split
-      int k = kb0 * TC_BK + j * 8;
-      int tap = k / g.ctot;
-      int c = k - tap * g.ctot;
-      int khi = tap / g.kw, kwi = tap - khi * g.kw;
-      // B rows of this thread
-      const bf16* wp = w + (long long)(n0 + rb) * g.K;
+        // ---- k state of this thread's chunk at the first k-block of the split
+        int k = kb0 * TC_BK + j * 8;
+        int tap = k / g.ctot;
+        int c = k - tap * g.ctot;
+        int khi = tap / g.kw, kwi = tap - khi * g.kw;
 
-      for (int kb = kb0; kb < kb1; ++kb, ++kbg) {
-        const int s = kbg % STAGES;
-        if (kbg >= STAGES) mbar_wait(empty_bar(s), ((kbg / STAGES) - 1) & 1, errflag);
-        const bool k_ok = k < g.K;
-        const uint32_t a_dst = a_base + s * A_STAGE_BYTES + rb * 128 + sw;
-        const int dkh = sgn * khi, dkw = sgn * kwi;
-        if (PATH == 0) {
-          const long long koff = (long long)(dkh * g.Wi + dkw) * g.ld0 + c;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const bool ok = k_ok && (unsigned)(rh[i] + dkh) < (unsigned)g.Hi && (unsigned)(rw[i] + dkw) < (unsigned)g.Wi;
-            const void* src = ok ? (const void*)(rp[i] + koff) : g.src0;
-            cp_async_16(a_dst + i * (16 * 128), src, ok ? 16u : 0u);
+        for (int kb = kb0; kb < kb1; ++kb, ++kbg) {
+          const int s = kbg % STAGES;
+          if (kbg >= STAGES) mbar_wait(empty_bar(s), ((kbg / STAGES) - 1) & 1, errflag);
+          const bool k_ok = k < g.K;
+          const uint32_t a_dst = a_base + s * A_STAGE_BYTES + rb * 128 + sw;
+          const int dkh = sgn * khi, dkw = sgn * kwi;
+          if (PATH == 0) {
+            const long long koff = (long long)(dkh * g.Wi + dkw) * g.ld0 + c;
+  #pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const bool ok = k_ok && (unsigned)(rh[i] + dkh) < (unsigned)g.Hi && (unsigned)(rw[i] + dkw) < (unsigned)g.Wi;
+              const void* src = ok ? (const void*)(rp[i] + koff) : g.src0;
+              if (ts.a_ca) cp_async_16_ca(a_dst + i * (16 * 128), src, ok ? 16u : 0u);
+              else cp_async_16(a_dst + i * (16 * 128), src, ok ? 16u : 0u);
+            }
+          } else {
+            const bool second = c >= g.c0;
+            const bf16* sb = second ? (const bf16*)g.src1 + (c - g.c0) : (const bf16*)g.src0 + c;
+            const int ld = second ? g.ld1 : g.ld0;
+            const int up = second ? 0 : g.up0;
+            const int hs = g.Hi >> up, wsz = g.Wi >> up;
+  #pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int th = rh[i] + dkh, tw = rw[i] + dkw;
+              const int hi = th >> sshift, wi = tw >> sshift;
+              const bool ok = k_ok && (((uint32_t)(th | tw)) & (0x80000000u | smask)) == 0 && hi < g.Hi && wi < g.Wi;
+              const long long pix = (long long)((rn[i] * hs + (hi >> up)) * wsz + (wi >> up));
+              const void* src = ok ? (const void*)(sb + pix * ld) : g.src0;
+              if (ts.a_ca) cp_async_16_ca(a_dst + i * (16 * 128), src, ok ? 16u : 0u);
+              else cp_async_16(a_dst + i * (16 * 128), src, ok ? 16u : 0u);
+            }
           }
-        } else {
-          const bool second = c >= g.c0;
-          const bf16* sb = second ? (const bf16*)g.src1 + (c - g.c0) : (const bf16*)g.src0 + c;
-          const int ld = second ? g.ld1 : g.ld0;
-          const int up = second ? 0 : g.up0;
-          const int hs = g.Hi >> up, wsz = g.Wi >> up;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int th = rh[i] + dkh, tw = rw[i] + dkw;
-            const int hi = th >> sshift, wi = tw >> sshift;
-            const bool ok = k_ok && (((uint32_t)(th | tw)) & (0x80000000u | smask)) == 0 && hi < g.Hi && wi < g.Wi;
-            const long long pix = (long long)((rn[i] * hs + (hi >> up)) * wsz + (wi >> up));
-            const void* src = ok ? (const void*)(sb + pix * ld) : g.src0;
-            cp_async_16(a_dst + i * (16 * 128), src, ok ? 16u : 0u);
+          cp_async_mbar_arrive(full_bar(s));
+          mbar_arrive(full_bar(s));
+          k += TC_BK;
+          c += TC_BK;
+          while (c >= g.ctot) {
+            c -= g.ctot;
+            if (++kwi == g.kw) { kwi = 0; ++khi; }
           }
-        }
-        const uint32_t b_dst = b_base + s * Cfg::B_STAGE_BYTES + rb * 128 + sw;
-#pragma unroll
-        for (int i = 0; i < BN / 16; ++i) {
-          const bool ok = k_ok && (n0 + rb + 16 * i) < e.Cout;
-          const void* src = ok ? (const void*)(wp + (long long)(16 * i) * g.K + k) : (const void*)w;
-          cp_async_16(b_dst + i * (16 * 128), src, ok ? 16u : 0u);
-        }
-        cp_async_mbar_arrive(full_bar(s));
-        mbar_arrive(full_bar(s));
-        k += TC_BK;
-        c += TC_BK;
-        while (c >= g.ctot) {
-          c -= g.ctot;
-          if (++kwi == g.kw) { kwi = 0; ++khi; }
         }
       }
 
       // ===================== epilogue: TMEM -> registers -> global =====================
-      mbar_wait(accum_bar, tile_iter & 1, errflag);
+      const uint32_t abuf = tile_iter & 1;
+      mbar_wait(acc_full_bar(abuf), (tile_iter >> 1) & 1, errflag);
       tc_fence_after();
       const int row = warp * 32 + lane;
       const int m = m0 + row;
@@ -331,7 +395,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(Gather g, FastDiv d
 #pragma unroll 1
       for (int cc = 0; cc < BN; cc += CW) {
         uint32_t raw[CW];
-        const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)cc;
+        const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + abuf * Cfg::ACC_COLS + (uint32_t)cc;
         if (CW == 32) tmem_ld32(taddr, raw); else tmem_ld16(taddr, raw);
         tmem_ld_wait();
         const int cbase = n0 + cc;
@@ -415,21 +479,27 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(Gather g, FastDiv d
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");   // slots are rewritten by the next tile
       }
-      tc_fence_before();   // order this tile's TMEM reads before the next tile's first full-barrier arrival
+      tc_fence_before();   // this tile's TMEM reads are done: hand the accumulator buffer back to the MMA issuer
+      mbar_arrive(acc_empty_bar(abuf));
     }
-  } else {
+  } else if (warp == 4) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(TC_BM, BN, 0, 0);
-      uint32_t kbg = 0;
-      for (int t = blockIdx.x; t < ts.total; t += gridDim.x) {
+      uint32_t kbg = 0, tile_iter = 0;
+      for (int t = blockIdx.x; t < ts.total; t += gridDim.x, ++tile_iter) {
         const int ks = (t / ts.MT) % ts.KS;
         const int kb0 = ks * ts.kb_per_split;
         const int kb1 = min(ts.nkb, kb0 + ts.kb_per_split);
+        const uint32_t abuf = tile_iter & 1;
+        if (tile_iter >= 2) {   // the epilogue must have drained this accumulator buffer (two tiles ago)
+          mbar_wait(acc_empty_bar(abuf), ((tile_iter >> 1) - 1) & 1, errflag);
+          tc_fence_after();
+        }
+        const uint32_t d_addr = tmem_d + abuf * Cfg::ACC_COLS;
         for (int kb = kb0; kb < kb1; ++kb, ++kbg) {
           const int s = kbg % STAGES;
           mbar_wait(full_bar(s), (kbg / STAGES) & 1, errflag);
-          fence_proxy_async();
           tc_fence_after();
           const uint32_t a_addr = a_base + s * A_STAGE_BYTES;
           const uint32_t b_addr = b_base + s * Cfg::B_STAGE_BYTES;
@@ -437,11 +507,11 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(Gather g, FastDiv d
           for (int kk = 0; kk < TC_BK / 16; ++kk) {
             uint64_t ad = make_smem_desc(a_addr + kk * 32, 16, 1024);
             uint64_t bd = make_smem_desc(b_addr + kk * 32, 16, 1024);
-            umma_f16(tmem_d, ad, bd, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+            umma_f16(d_addr, ad, bd, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
           }
           umma_commit(empty_bar(s));
         }
-        umma_commit(accum_bar);
+        umma_commit(acc_full_bar(abuf));
       }
     }
     __syncwarp();
@@ -518,18 +588,23 @@ __global__ void __launch_bounds__(256) conv_splitk_finish_kernel(const float* __
 
 static int g_num_sms = 148;
 static int g_tile_loop = 1;   // D3FK_TILE_LOOP=0: one CTA per tile (debug aid)
+static int g_a_ca = 0;        // D3FK_A_CA=1: L1-allocating activation gather
+static int g_occ_cap = 0;     // D3FK_OCC=n: cap CTAs per SM
+static int g_use_tma_a = 1;   // D3FK_TMA_A=0: force the gather producers (debug aid)
+static int g_split_tiles = 74;  // split K only when the output tiles fill at most this many SMs
 
 template <int BN, int PATH>
-static int launch_conv_tc_bn(const Gather& g, const d3fk_conv_params* p, cudaStream_t s) {
+static int launch_conv_tc_bn(const Gather& g, const d3fk_conv_params* p, cudaStream_t s, const TileSched& box) {
   EpiTC e{(bf16*)p->out, p->out_nchw, p->scale, p->shift, (const bf16*)p->res, p->stats, p->ldo, p->ldr, p->relu, p->Cout, p->Ho, p->Wo};
-  TileSched ts;
+  TileSched ts = box;
   ts.MT = cdiv(g.M, TC_BM);
   ts.NT = cdiv(p->Cout, BN);
   ts.nkb = cdiv(g.K, TC_BK);
   ts.KS = 1;
   const int tiles = ts.MT * ts.NT;
+  ts.a_ca = g_a_ca && p->kh > 1;
   // split K when the output tiles cannot fill the chip and the reduction is long
-  if (p->ws && !p->out_nchw && p->Cout % BN == 0 && tiles < g_num_sms && ts.nkb >= 8) {
+  if (p->ws && !p->out_nchw && p->Cout % BN == 0 && tiles <= g_split_tiles && ts.nkb >= 8) {
     int ks = cdiv(2 * g_num_sms, tiles);
     if (ks > ts.nkb / 4) ks = ts.nkb / 4;
     if (ks > 16) ks = 16;
@@ -539,11 +614,31 @@ static int launch_conv_tc_bn(const Gather& g, const d3fk_conv_params* p, cudaStr
   ts.kb_per_split = cdiv(ts.nkb, ts.KS);
   ts.KS = cdiv(ts.nkb, ts.kb_per_split);
   ts.total = tiles * ts.KS;
-  const int occ = (227 * 1024) / (ConvCfg<BN>::SMEM + 1024);
+  int occ = (227 * 1024) / (ConvCfg<BN>::SMEM + 1024);
+  if (occ * ConvCfg<BN>::TMEM_COLS > 512) occ = 512 / ConvCfg<BN>::TMEM_COLS;
+  if (g_occ_cap > 0 && occ > g_occ_cap) occ = g_occ_cap;
   int grid = ts.total < g_num_sms * occ ? ts.total : g_num_sms * occ;
   if (!g_tile_loop) grid = ts.total;
+
+  // TMA descriptors: weights [Cout][K] as a {64, BN} box; PATH 2 also the activation tensor as a 4-D NHWC box
+  alignas(64) CUtensorMap tmA, tmB;
+  memset(&tmA, 0, sizeof(tmA));
+  {
+    uint64_t dims[2] = {(uint64_t)g.K, (uint64_t)p->Cout};
+    uint64_t strides[1] = {(uint64_t)g.K * 2};
+    uint32_t bx[2] = {TC_BK, (uint32_t)BN};
+    int rc = get_tensor_map(&tmB, p->w, 2, dims, strides, bx, 128);
+    if (rc) return rc;
+  }
+  if (PATH == 2) {
+    uint64_t dims[4] = {(uint64_t)g.c0, (uint64_t)g.Wi, (uint64_t)g.Hi, (uint64_t)g.B};
+    uint64_t strides[3] = {(uint64_t)g.ld0 * 2, (uint64_t)g.Wi * g.ld0 * 2, (uint64_t)g.Hi * g.Wi * g.ld0 * 2};
+    uint32_t bx[4] = {TC_BK, (uint32_t)ts.bw, (uint32_t)ts.bh, (uint32_t)ts.bn};
+    int rc = get_tensor_map(&tmA, p->src0, 4, dims, strides, bx, 128);
+    if (rc) return rc;
+  }
   conv_tc_kernel<BN, PATH><<<grid, TC_THREADS, ConvCfg<BN>::SMEM, s>>>(g, make_fastdiv((uint32_t)g.Wo), make_fastdiv((uint32_t)g.Ho),
-                                                                    (const bf16*)p->w, e, ts, (float*)p->ws, g_dev_error_flag);
+                                                                    tmA, tmB, e, ts, (float*)p->ws, g_dev_error_flag);
   count_launch();
   int rc = check_launch("conv_tc");
   if (rc || ts.KS == 1) return rc;
@@ -559,14 +654,35 @@ static int launch_conv_tc_bn(const Gather& g, const d3fk_conv_params* p, cudaStr
 }
 
 template <int PATH>
-static int launch_conv_tc_path(const Gather& g, const d3fk_conv_params* p, cudaStream_t s) {
+static int launch_conv_tc_path(const Gather& g, const d3fk_conv_params* p, cudaStream_t s, const TileSched& box) {
   const int C = p->Cout;
-  if (C <= 16) return launch_conv_tc_bn<16, PATH>(g, p, s);
+  if (C <= 16) return launch_conv_tc_bn<16, PATH>(g, p, s, box);
   D3FK_CHECK_ARG(p->out_nchw == nullptr, "out_nchw only for Cout <= 16");
-  if (C % 128 == 0) return launch_conv_tc_bn<128, PATH>(g, p, s);
-  if (C % 64 == 0) return launch_conv_tc_bn<64, PATH>(g, p, s);
-  if (C % 32 == 0) return launch_conv_tc_bn<32, PATH>(g, p, s);
+  if (C % 128 == 0) return launch_conv_tc_bn<128, PATH>(g, p, s, box);
+  if (C % 64 == 0) return launch_conv_tc_bn<64, PATH>(g, p, s, box);
+  if (C % 32 == 0) return launch_conv_tc_bn<32, PATH>(g, p, s, box);
   return set_error(D3FK_ERR_UNSUPPORTED, "conv_tc: Cout=%d (need <=16 or a multiple of 32)", C);
+}
+
+// PATH 2 eligibility: the 128-pixel M tile must be an axis-aligned (w, h, n) box whose pixel order equals the linear
+// output-pixel order: bw = min(W,128) columns, then bh rows, then bn images, each level fully covered before the next.
+static bool tma_box(const Gather& g, const d3fk_conv_params* p, TileSched& ts) {
+  if (!g_use_tma_a) return false;
+  if (p->c1 != 0 || p->up0 != 0 || p->stride != 1 || g.ctot % TC_BK != 0) return false;
+  if (p->Ho != p->Hi || p->Wo != p->Wi || 2 * p->pad != p->kh - 1 || p->kh != p->kw) return false;
+  if (((uintptr_t)p->src0 & 15) || (g.ld0 % 8)) return false;
+  const int W = p->Wi, H = p->Hi;
+  int bw = W < TC_BM ? W : TC_BM;
+  if (TC_BM % bw || W % bw) return false;
+  int bh = TC_BM / bw;
+  if (bh > H) bh = H;
+  if ((TC_BM / bw) % bh || H % bh) return false;
+  int bn = TC_BM / (bw * bh);
+  if (bw < W && bh != 1) return false;
+  if (bh < H && bn != 1) return false;
+  if (bn > 256) return false;
+  ts.bw = bw; ts.bh = bh; ts.bn = bn; ts.wt = W / bw; ts.ht = H / bh;
+  return true;
 }
 
 int launch_conv_tc(const d3fk_conv_params* p, cudaStream_t s) {
@@ -577,8 +693,12 @@ int launch_conv_tc(const d3fk_conv_params* p, cudaStream_t s) {
   D3FK_CHECK_ARG(p->out || p->out_nchw, "no output");
   D3FK_CHECK_ARG(p->out_nchw || (p->ldo % 8 == 0), "ldo must be a multiple of 8");
   D3FK_CHECK_ARG(!p->scale || p->shift, "scale requires shift");
+  D3FK_CHECK_ARG(((uintptr_t)p->w & 15) == 0, "weights must be 16-byte aligned");
+  TileSched box;
+  memset(&box, 0, sizeof(box));
+  if (tma_box(g, p, box)) return launch_conv_tc_path<2>(g, p, s, box);
   const bool linear = p->c1 == 0 && p->up0 == 0 && (p->mode == 0 || p->stride == 1);
-  return linear ? launch_conv_tc_path<0>(g, p, s) : launch_conv_tc_path<1>(g, p, s);
+  return linear ? launch_conv_tc_path<0>(g, p, s, box) : launch_conv_tc_path<1>(g, p, s, box);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -596,7 +716,7 @@ template <int BN> struct WgradCfg {
 };
 
 template <int BN>
-__global__ void __launch_bounds__(TC_THREADS) wgrad_tc_kernel(Gather g, FastDiv dWo, FastDiv dHo, const bf16* __restrict__ dy,
+__global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(Gather g, FastDiv dWo, FastDiv dHo, const bf16* __restrict__ dy,
                                                               int ldy, int Cout, float* __restrict__ dw, int cin_real,
                                                               int cout_real, int blocks_per_split, int lbo_a, int lbo_b,
                                                               int* errflag) {
@@ -727,7 +847,6 @@ __global__ void __launch_bounds__(TC_THREADS) wgrad_tc_kernel(Gather g, FastDiv 
       for (int it = 0; it < nblk; ++it) {
         const int s = it % STAGES;
         mbar_wait(full_bar(s), (it / STAGES) & 1, errflag);
-        fence_proxy_async();
         tc_fence_after();
         const uint32_t a_addr = a_base + s * WG_A_STAGE;
         const uint32_t b_addr = b_base + s * Cfg::B_STAGE;
@@ -758,7 +877,7 @@ static int launch_wgrad_tc_bn(const Gather& g, const d3fk_wgrad_params* p, cudaS
   int bps = cdiv(nblk, splits);
   splits = cdiv(nblk, bps);
   dim3 grid(gx, gy, splits);
-  wgrad_tc_kernel<BN><<<grid, TC_THREADS, WgradCfg<BN>::SMEM, s>>>(
+  wgrad_tc_kernel<BN><<<grid, WG_THREADS, WgradCfg<BN>::SMEM, s>>>(
       g, make_fastdiv((uint32_t)g.Wo), make_fastdiv((uint32_t)g.Ho), (const bf16*)p->dy, p->ldy, p->Cout, p->dw, p->cin_real,
       p->cout_real, bps, WG_PIX * 128, WG_PIX * 128, g_dev_error_flag);
   count_launch();
@@ -782,6 +901,10 @@ int tc_init() {
     g_num_sms = sms;
   const char* tl = getenv("D3FK_TILE_LOOP");
   if (tl) g_tile_loop = atoi(tl);
+  if (const char* v = getenv("D3FK_A_CA")) g_a_ca = atoi(v);
+  if (const char* v = getenv("D3FK_OCC")) g_occ_cap = atoi(v);
+  if (const char* v = getenv("D3FK_TMA_A")) g_use_tma_a = atoi(v);
+  if (const char* v = getenv("D3FK_SPLIT_TILES")) g_split_tiles = atoi(v);
 #define SET_SMEM(k, bytes)                                                                          \
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   SET_SMEM((conv_tc_kernel<16, 0>), ConvCfg<16>::SMEM)
@@ -792,6 +915,10 @@ int tc_init() {
   SET_SMEM((conv_tc_kernel<32, 1>), ConvCfg<32>::SMEM)
   SET_SMEM((conv_tc_kernel<64, 1>), ConvCfg<64>::SMEM)
   SET_SMEM((conv_tc_kernel<128, 1>), ConvCfg<128>::SMEM)
+  SET_SMEM((conv_tc_kernel<16, 2>), ConvCfg<16>::SMEM)
+  SET_SMEM((conv_tc_kernel<32, 2>), ConvCfg<32>::SMEM)
+  SET_SMEM((conv_tc_kernel<64, 2>), ConvCfg<64>::SMEM)
+  SET_SMEM((conv_tc_kernel<128, 2>), ConvCfg<128>::SMEM)
   SET_SMEM(wgrad_tc_kernel<64>, WgradCfg<64>::SMEM)
   SET_SMEM(wgrad_tc_kernel<128>, WgradCfg<128>::SMEM)
 #undef SET_SMEM
