@@ -70,7 +70,9 @@ __global__ void bn_fold_kernel(d3fk_bn_params p) {
   p.shift[c] = p.beta[c] - p.running_mean[c] * sc;
 }
 
-// y = relu?(x*scale + shift + res)
+// y = relu?(x*scale + shift + res).  With p.stats set (train forward) the batch statistics are finalised here:
+// every thread derives scale/shift of its own 8 (4) channels from the conv-epilogue sums, and the first C/V
+// threads of block 0 publish mean / invstd / running statistics — no separate finalize launch.
 template <typename T>
 __global__ void bn_apply_kernel(d3fk_bn_params p) {
   constexpr int V = Vec<T>::N;
@@ -79,19 +81,40 @@ __global__ void bn_apply_kernel(d3fk_bn_params p) {
   const T* x = (const T*)p.x;
   T* y = (T*)p.y;
   const T* res = (const T*)p.res;
-  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    long long pix = e / cvs;
-    int c = (int)(e - pix * cvs) * V;
+  const long long e0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;   // multiple of cvs: the channel vector is loop invariant
+  const int c = (int)(e0 % cvs) * V;
+  float scf[V], shf[V];
+  if (p.stats) {
+    const double n = (double)p.count;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const double mean = p.stats[c + i] / n;
+      double var = p.stats[p.C + c + i] / n - mean * mean;
+      if (var < 0) var = 0;
+      const double invstd = 1.0 / sqrt(var + (double)p.eps);
+      const float g = p.gamma[c + i], b = p.beta[c + i];
+      scf[i] = (float)((double)g * invstd);
+      shf[i] = (float)((double)b - mean * (double)g * invstd);
+      if (e0 < cvs) {
+        p.mean[c + i] = (float)mean;
+        p.invstd[c + i] = (float)invstd;
+        if (p.running_mean) {
+          const double unbiased = n > 1 ? var * n / (n - 1) : var;
+          p.running_mean[c + i] = (float)((1.0 - p.momentum) * p.running_mean[c + i] + p.momentum * mean);
+          p.running_var[c + i] = (float)((1.0 - p.momentum) * p.running_var[c + i] + p.momentum * unbiased);
+        }
+      }
+    }
+    if (e0 == 0 && p.num_batches_tracked) *p.num_batches_tracked += 1;
+  } else {
+#pragma unroll
+    for (int i = 0; i < V; ++i) { scf[i] = __ldg(p.scale + c + i); shf[i] = __ldg(p.shift + c + i); }
+  }
+  for (long long e = e0; e < total; e += stride) {
+    const long long pix = e / cvs;
     float v[V], r[V];
     load_vec<T>(x + pix * p.ldx + c, v);
-    float4 sc[V / 4], sh[V / 4];
-#pragma unroll
-    for (int i = 0; i < V / 4; ++i) {
-      sc[i] = __ldg(reinterpret_cast<const float4*>(p.scale + c) + i);
-      sh[i] = __ldg(reinterpret_cast<const float4*>(p.shift + c) + i);
-    }
-    const float* scf = reinterpret_cast<const float*>(sc);
-    const float* shf = reinterpret_cast<const float*>(sh);
     if (res) load_vec<T>(res + pix * p.ldr + c, r);
 #pragma unroll
     for (int i = 0; i < V; ++i) {
@@ -104,14 +127,15 @@ __global__ void bn_apply_kernel(d3fk_bn_params p) {
   }
 }
 
-// per-channel sums of dy' and dy'*xhat ; dy' = relu ? (act>0 ? dy : 0) : dy
+// per-channel sums of dy' and dy'*xhat ; dy' = relu ? (act>0 ? dy : 0) : dy.
+// Lanes of a warp that own the same channel vector are folded with shuffles, warps with one shared-memory
+// slot each, the block with one double atomic per channel.
 template <typename T, typename Acc>
-__global__ void bn_bwd_reduce_kernel(d3fk_bn_params p) {
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(d3fk_bn_params p) {
   constexpr int V = Vec<T>::N;
-  extern __shared__ double sred[];  // [2][C]
+  extern __shared__ double sred[];  // [warps][2][C]
   const int C = p.C, cvs = C / V;
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sred[i] = 0.0;
-  __syncthreads();
+  const int nwarp = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rows_per_iter = blockDim.x / cvs;
   const int cv = threadIdx.x % cvs, prow = threadIdx.x / cvs;
   const int c = cv * V;
@@ -140,14 +164,44 @@ __global__ void bn_bwd_reduce_kernel(d3fk_bn_params p) {
         s2[i] += (Acc)(g * xh);
       }
     }
+  }
+  // fold lanes that share cv (lane stride cvs) when a warp holds several pixel rows
+  if (cvs < 32) {
 #pragma unroll
     for (int i = 0; i < V; ++i) {
-      atomicAdd(&sred[c + i], (double)s1[i]);
-      atomicAdd(&sred[C + c + i], (double)s2[i]);
+      for (int o = 16; o >= cvs; o >>= 1) {
+        s1[i] += __shfl_xor_sync(0xffffffffu, s1[i], o);
+        s2[i] += __shfl_xor_sync(0xffffffffu, s2[i], o);
+      }
+    }
+  }
+  // shared slots: cvs < 32: [warp][2][C]; cvs >= 32: a warp covers 32 consecutive channel vectors -> [warp][2][32*V]
+  const int slotC = cvs < 32 ? C : 32 * V;
+  if (cvs < 32) {
+    if (lane < cvs) {
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        sred[(warp * 2 + 0) * slotC + c + i] = (double)s1[i];
+        sred[(warp * 2 + 1) * slotC + c + i] = (double)s2[i];
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      sred[(warp * 2 + 0) * slotC + lane * V + i] = (double)s1[i];
+      sred[(warp * 2 + 1) * slotC + lane * V + i] = (double)s2[i];
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&p.bstats[i], sred[i]);
+  const int groups = cvs < 32 ? 1 : cvs / 32;   // warps w, w+groups, ... hold the same channel range
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    const int which = i / C, ch = i - which * C;
+    const int grp = cvs < 32 ? 0 : ch / slotC;
+    const int within = cvs < 32 ? ch : ch % slotC;
+    double a = 0;
+    for (int w = grp; w < nwarp; w += groups) a += sred[(w * 2 + which) * slotC + within];
+    atomicAdd(&p.bstats[which * C + ch], a);
+  }
 }
 
 __global__ void bn_bwd_finalize_kernel(d3fk_bn_params p) {
@@ -162,7 +216,9 @@ __global__ void bn_bwd_finalize_kernel(d3fk_bn_params p) {
   p.coef[2 * p.C + c] = (float)(s2 / n);
 }
 
-// dx = c0*(dy' - c1 - xhat*c2); optionally dres = dy'
+// dx = c0*(dy' - c1 - xhat*c2), c0 = gamma*invstd, c1 = sum(dy')/n, c2 = sum(dy'*xhat)/n; optionally dres = dy'.
+// The coefficients are derived in-kernel from the reduction sums; the first C/V threads of block 0 also write
+// dgamma / dbeta (no separate finalize launch).
 template <typename T>
 __global__ void bn_bwd_apply_kernel(d3fk_bn_params p) {
   constexpr int V = Vec<T>::N;
@@ -173,9 +229,26 @@ __global__ void bn_bwd_apply_kernel(d3fk_bn_params p) {
   const T* act = (const T*)p.act;
   T* dx = (T*)p.dx;
   T* dres = (T*)p.dres;
-  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    long long pix = e / cvs;
-    int c = (int)(e - pix * cvs) * V;
+  const long long e0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const int c = (int)(e0 % cvs) * V;
+  float k0[V], k1[V], k2[V], mean[V], istd[V];
+  const double n = (double)p.count;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const double s1 = p.bstats[c + i], s2 = p.bstats[p.C + c + i];
+    mean[i] = __ldg(p.mean + c + i);
+    istd[i] = __ldg(p.invstd + c + i);
+    k0[i] = __ldg(p.gamma + c + i) * istd[i];
+    k1[i] = (float)(s1 / n);
+    k2[i] = (float)(s2 / n);
+    if (e0 < cvs) {
+      if (p.dbeta) p.dbeta[c + i] = (float)s1;
+      if (p.dgamma) p.dgamma[c + i] = (float)s2;
+    }
+  }
+  for (long long e = e0; e < total; e += stride) {
+    const long long pix = e / cvs;
     float xv[V], gv[V], av[V], o[V];
     load_vec<T>(x + pix * p.ldx + c, xv);
     load_vec<T>(dy + pix * p.lddy + c, gv);
@@ -185,8 +258,8 @@ __global__ void bn_bwd_apply_kernel(d3fk_bn_params p) {
       float g = gv[i];
       if (p.relu && !(av[i] > 0.f)) g = 0.f;
       gv[i] = g;
-      float xh = (xv[i] - __ldg(p.mean + c + i)) * __ldg(p.invstd + c + i);
-      o[i] = __ldg(p.coef + c + i) * (g - __ldg(p.coef + p.C + c + i) - xh * __ldg(p.coef + 2 * p.C + c + i));
+      const float xh = (xv[i] - mean[i]) * istd[i];
+      o[i] = k0[i] * (g - k1[i] - xh * k2[i]);
     }
     store_vec<T>(dx + pix * p.lddx + c, o);
     if (dres) store_vec<T>(dres + pix * p.lddres + c, gv);
@@ -395,6 +468,35 @@ __global__ void posterior_kernel(d3fk_posterior_params p) {
 
 __global__ void inc_kernel(int* p) { *p += 1; }
 
+// one launch packs every convolution's weights: blockIdx.y selects the layer descriptor (device table)
+template <typename T>
+__global__ void pack_all_kernel(const d3fk_pack_params* __restrict__ tab) {
+  const d3fk_pack_params p = tab[blockIdx.y];
+  const int taps = p.kh * p.kw;
+  if (p.w_fwd) {
+    const long long total = (long long)p.Cout * taps * p.cin_pad;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+      const int ci = (int)(i % p.cin_pad);
+      const long long t = i / p.cin_pad;
+      const int tap = (int)(t % taps);
+      const int co = (int)(t / taps);
+      const float v = ci < p.Cin ? __ldg(p.w + ((long long)co * p.Cin + ci) * taps + tap) : 0.f;
+      ((T*)p.w_fwd)[i] = from_f<T>(v);
+    }
+  }
+  if (p.w_dgrad) {
+    const long long total = (long long)p.Cin * taps * p.cout_pad;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+      const int co = (int)(i % p.cout_pad);
+      const long long t = i / p.cout_pad;
+      const int tap = (int)(t % taps);
+      const int ci = (int)(t / taps);
+      const float v = co < p.Cout ? __ldg(p.w + ((long long)co * p.Cin + ci) * taps + tap) : 0.f;
+      ((T*)p.w_dgrad)[i] = from_f<T>(v);
+    }
+  }
+}
+
 // fused Adam (+ optional EMA lerp) over a flat arena
 __global__ void adam_kernel(d3fk_adam_params p) {
   const float step = p.lr / p.bias1;
@@ -444,15 +546,17 @@ int launch_bn_apply(const d3fk_bn_params* p, cudaStream_t s) {
   return check_launch("bn_apply");
 }
 int launch_bn_bwd_reduce(const d3fk_bn_params* p, cudaStream_t s) {
-  D3FK_CHECK_ARG(p->C % 8 == 0 && p->C <= 2048, "C must be a multiple of 8, <= 2048");
+  D3FK_CHECK_ARG(p->C % 8 == 0 && p->C <= 1024, "C must be a multiple of 8, <= 1024");
   int V = p->dtype == D3FK_F32 ? 4 : 8;
   int cvs = p->C / V;
-  int threads = 256;
-  if (cvs > threads) threads = cvs;
-  int rows = threads / cvs;
-  int grid = grid_for(cdiv(p->count, 4) * (long long)cvs, threads, 4);
-  (void)rows;
-  size_t smem = 2 * p->C * sizeof(double);
+  D3FK_CHECK_ARG((cvs & (cvs - 1)) == 0 && cvs <= 256, "C/V must be a power of two <= 256");
+  const int threads = 256;
+  const int rows = threads / cvs;
+  int grid = cdiv(p->count, (long long)rows * 8);
+  if (grid > kSMs * 8) grid = kSMs * 8;
+  if (grid < 1) grid = 1;
+  const int slotC = cvs < 32 ? p->C : 32 * V;
+  size_t smem = (size_t)(threads / 32) * 2 * slotC * sizeof(double);
   if (p->dtype == D3FK_F32) bn_bwd_reduce_kernel<float, double><<<grid, threads, smem, s>>>(*p);
   else if (p->dtype == D3FK_BF16) bn_bwd_reduce_kernel<__nv_bfloat16, float><<<grid, threads, smem, s>>>(*p);
   else return set_error(D3FK_ERR_ARG, "bad dtype");
@@ -519,6 +623,16 @@ int launch_inc(const d3fk_misc_params* p, cudaStream_t s) {
   inc_kernel<<<1, 1, 0, s>>>((int*)p->p0);
   count_launch();
   return check_launch("inc");
+}
+int launch_pack_all(const d3fk_misc_params* p, cudaStream_t s) {
+  // p0: device array of d3fk_pack_params (all with the same dtype); n = (count << 1) | (dtype == bf16)
+  const int count = (int)(p->n >> 1);
+  D3FK_CHECK_ARG(count > 0 && count < 65536, "bad pack table size");
+  dim3 grid(96, count);
+  if (p->n & 1) pack_all_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const d3fk_pack_params*)p->p0);
+  else pack_all_kernel<float><<<grid, 256, 0, s>>>((const d3fk_pack_params*)p->p0);
+  count_launch();
+  return check_launch("pack_all");
 }
 int launch_adam(const d3fk_adam_params* p, cudaStream_t s) {
   adam_kernel<<<grid_for(p->n, 256), 256, 0, s>>>(*p);

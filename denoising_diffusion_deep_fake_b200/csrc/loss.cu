@@ -1,0 +1,170 @@
+// loss.cu — fused MSE + (1 - SSIM) criterion, forward AND gradient in one kernel.
+// Reference: d3f/loss_functions/structural_similarity_loss.py:14-26 with piqa.SSIM() defaults (11-tap Gaussian,
+// sigma 1.5, valid window, k1 = 0.01, k2 = 0.03, value_range 1).  ~30 eager launches -> 1.
+//
+// One block owns a 32x32 pixel tile of one (n, c) plane.  It stages the clipped, normalised inputs with a 10-pixel
+// halo (52x52), runs the separable Gaussian over {x, y, x^2, y^2, xy} for the 42x42 windows that touch the tile,
+// forms ss and its partials a = d ss/d mu_x, b = d ss/d E[x^2], c = d ss/d E[xy], pushes them back through the
+// transposed separable filter and emits dL/dpred for its 32x32 pixels.  Everything between load and store lives in
+// shared memory; HBM traffic is one read of pred/target and one write of the gradient.
+#include "common.cuh"
+
+namespace d3fk {
+
+constexpr int LT = 32;            // tile edge
+constexpr int LW = 11;            // window
+constexpr int LH = LW - 1;        // halo
+constexpr int LI = LT + 2 * LH;   // 52: staged input edge
+constexpr int LM = LT + LH;       // 42: windows (map pixels) touching the tile
+constexpr int LOSS_SMEM = (2 * LI * LI + 5 * LI * LM + 3 * LM * LM) * 4;
+
+__global__ void __launch_bounds__(256) mse_ssim_loss_kernel(d3fk_loss_params p) {
+  extern __shared__ float sm[];
+  float* xs = sm;                       // [LI][LI] normalised clipped prediction (0 outside the image)
+  float* ys = xs + LI * LI;             // [LI][LI] target
+  float* hs = ys + LI * LI;             // [5][LI][LM] horizontal pass; later [3][LM][LT] transposed horizontal pass
+  float* ms = hs + 5 * LI * LM;         // [3][LM][LM] a, b, c maps
+  __shared__ float g[LW];
+  __shared__ double red[2][8];
+  const int tid = threadIdx.x;
+  if (tid < LW) g[tid] = p.win[tid];
+  const int tiles_w = p.W / LT, tiles_h = p.H / LT;
+  int b = blockIdx.x;
+  const int tw = b % tiles_w; b /= tiles_w;
+  const int th = b % tiles_h; b /= tiles_h;
+  const long long plane = (long long)b * p.H * p.W;     // b = n*C + c
+  const int r0 = th * LT - LH, c0 = tw * LT - LH;       // image coords of staged (0,0)
+  const float inv_range = 1.0f / (p.hi - p.lo);
+  const int Hm = p.H - LH, Wm = p.W - LH;               // valid window (map) extent
+
+  // 1. stage inputs
+  for (int i = tid; i < LI * LI; i += 256) {
+    const int r = i / LI, c = i - r * LI;
+    const int gr = r0 + r, gc = c0 + c;
+    float x = 0.f, y = 0.f;
+    if ((unsigned)gr < (unsigned)p.H && (unsigned)gc < (unsigned)p.W) {
+      const long long o = plane + (long long)gr * p.W + gc;
+      x = fminf(fmaxf((__ldg(p.pred + o) - p.lo) * inv_range, 0.f), 1.f);
+      y = fminf(fmaxf((__ldg(p.target + o) - p.lo) * inv_range, 0.f), 1.f);
+    }
+    xs[i] = x; ys[i] = y;
+  }
+  __syncthreads();
+  // 2. horizontal Gaussian of x, y, xx, yy, xy : hs[q][r][jc], window columns jc..jc+10
+  for (int i = tid; i < LI * LM; i += 256) {
+    const int r = i / LM, jc = i - r * LM;
+    float sx = 0.f, sy = 0.f, sxx = 0.f, syy = 0.f, sxy = 0.f;
+#pragma unroll
+    for (int k = 0; k < LW; ++k) {
+      const float x = xs[r * LI + jc + k], y = ys[r * LI + jc + k], w = g[k];
+      sx = fmaf(w, x, sx); sy = fmaf(w, y, sy);
+      sxx = fmaf(w, x * x, sxx); syy = fmaf(w, y * y, syy); sxy = fmaf(w, x * y, sxy);
+    }
+    hs[0 * LI * LM + i] = sx; hs[1 * LI * LM + i] = sy; hs[2 * LI * LM + i] = sxx;
+    hs[3 * LI * LM + i] = syy; hs[4 * LI * LM + i] = sxy;
+  }
+  __syncthreads();
+  // 3. vertical Gaussian -> ss and its partial derivatives at every window that touches the tile
+  const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
+  double ss_sum = 0.0;
+  for (int i = tid; i < LM * LM; i += 256) {
+    const int jr = i / LM, jc = i - jr * LM;
+    const int gr = r0 + jr, gc = c0 + jc;                // window origin in the image
+    float a = 0.f, bb = 0.f, cc = 0.f;
+    if ((unsigned)gr < (unsigned)Hm && (unsigned)gc < (unsigned)Wm) {
+      float mx = 0.f, my = 0.f, exx = 0.f, eyy = 0.f, exy = 0.f;
+#pragma unroll
+      for (int k = 0; k < LW; ++k) {
+        const int o = (jr + k) * LM + jc;
+        const float w = g[k];
+        mx = fmaf(w, hs[o], mx); my = fmaf(w, hs[LI * LM + o], my);
+        exx = fmaf(w, hs[2 * LI * LM + o], exx); eyy = fmaf(w, hs[3 * LI * LM + o], eyy);
+        exy = fmaf(w, hs[4 * LI * LM + o], exy);
+      }
+      const float mxx = mx * mx, myy = my * my, mxy = mx * my;
+      const float sxx = exx - mxx, syy = eyy - myy, sxy = exy - mxy;
+      const float A1 = 2.f * mxy + C1, A2 = 2.f * sxy + C2, B1 = mxx + myy + C1, B2 = sxx + syy + C2;
+      const float S1 = A1 / B1, S2 = A2 / B2;
+      // windows whose origin lies inside the tile are owned (counted) by this block
+      if (jr >= LH && jc >= LH) ss_sum += (double)(S1 * S2);
+      a = S2 * 2.f * (my - S1 * mx) / B1 + S1 * 2.f * (S2 * mx - my) / B2;
+      bb = -S1 * S2 / B2;
+      cc = 2.f * S1 / B2;
+    }
+    ms[i] = a; ms[LM * LM + i] = bb; ms[2 * LM * LM + i] = cc;
+  }
+  __syncthreads();
+  double mse_sum = 0.0;
+  if (p.grad) {
+    // 4. transposed horizontal pass: th[q][jr][ic] = sum_{jc = ic..ic+10} g[ic+10-jc] * map[q][jr][jc]
+    float* ths = hs;
+    for (int i = tid; i < 3 * LM * LT; i += 256) {
+      const int q = i / (LM * LT);
+      const int rem = i - q * LM * LT;
+      const int jr = rem / LT, ic = rem - jr * LT;
+      float s = 0.f;
+#pragma unroll
+      for (int k = 0; k < LW; ++k) s = fmaf(g[LH - k], ms[q * LM * LM + jr * LM + ic + k], s);
+      ths[i] = s;
+    }
+    __syncthreads();
+  }
+  // 5. transposed vertical pass + combination + MSE term
+  const long long ntot = (long long)p.B * p.C * p.H * p.W;
+  const double nmap = (double)p.B * p.C * (double)Hm * Wm;
+  const float k_mse = p.grad_scale * 0.5f * 2.0f / (float)ntot;
+  const float k_ssim = p.grad_scale * 0.5f * inv_range / (float)nmap;
+  for (int i = tid; i < LT * LT; i += 256) {
+    const int ir = i / LT, ic = i - ir * LT;
+    const long long o = plane + (long long)(th * LT + ir) * p.W + tw * LT + ic;
+    const float pr = __ldg(p.pred + o), tg = __ldg(p.target + o);
+    const float d = pr - tg;
+    mse_sum += (double)d * d;
+    if (p.grad) {
+      const float* ths = hs;
+      float A = 0.f, Bm = 0.f, Cm = 0.f;
+#pragma unroll
+      for (int k = 0; k < LW; ++k) {
+        const int o2 = (ir + k) * LT + ic;
+        const float w = g[LH - k];
+        A = fmaf(w, ths[o2], A); Bm = fmaf(w, ths[LM * LT + o2], Bm); Cm = fmaf(w, ths[2 * LM * LT + o2], Cm);
+      }
+      const float x = xs[(ir + LH) * LI + ic + LH], y = ys[(ir + LH) * LI + ic + LH];
+      const float xn = (pr - p.lo) * inv_range;
+      const float inside = (xn > 0.f && xn < 1.f) ? 1.f : 0.f;   // clip() passes no gradient outside [lo, hi]
+      const float dss = A + 2.f * x * Bm + y * Cm;
+      p.grad[o] = k_mse * d - k_ssim * inside * dss;
+    }
+  }
+  // block reduction of the two sums
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mse_sum += __shfl_xor_sync(0xffffffffu, mse_sum, o);
+    ss_sum += __shfl_xor_sync(0xffffffffu, ss_sum, o);
+  }
+  if ((tid & 31) == 0) { red[0][tid >> 5] = mse_sum; red[1][tid >> 5] = ss_sum; }
+  __syncthreads();
+  if (tid < 2) {
+    double a = 0;
+    for (int w = 0; w < 8; ++w) a += red[tid][w];
+    atomicAdd(&p.acc[tid], a);
+  }
+}
+
+int loss_init() {
+  cudaError_t e = cudaFuncSetAttribute(mse_ssim_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LOSS_SMEM);
+  if (e != cudaSuccess) return set_error(D3FK_ERR_CUDA, "loss smem attribute: %s", cudaGetErrorString(e));
+  return D3FK_OK;
+}
+
+int launch_loss(const d3fk_loss_params* p, cudaStream_t s) {
+  D3FK_CHECK_ARG(p->H % LT == 0 && p->W % LT == 0, "H and W must be multiples of 32");
+  D3FK_CHECK_ARG(p->hi > p->lo, "bad value range");
+  long long blocks = (long long)p->B * p->C * (p->H / LT) * (p->W / LT);
+  D3FK_CHECK_ARG(blocks < (1ll << 31), "too many tiles");
+  mse_ssim_loss_kernel<<<(int)blocks, 256, LOSS_SMEM, s>>>(*p);
+  count_launch();
+  return check_launch("mse_ssim_loss");
+}
+
+}  // namespace d3fk

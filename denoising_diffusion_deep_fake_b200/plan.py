@@ -198,13 +198,23 @@ class UnetPlan:
     # ------------------------------------------------------------------ weight packing / BN folding
     def _build_pack(self):
         ops = []
+        packs = []
         for c in self.convs:
             cin_pad = CIN_PAD if c.cin == 3 else c.cin
             cout_pad = CIN_PAD if c.cout == 3 else c.cout
             wd = self.w_dgrad.get(c.name)
-            ops.append(make_op(_lib.OP_PACK, dtype=self.dtype, Cout=c.cout, Cin=c.cin, kh=c.k, kw=c.k,
-                               cin_pad=cin_pad, cout_pad=cout_pad, w=self.params[c.name + ".weight"].data_ptr(),
-                               w_fwd=self.w_fwd[c.name].data_ptr(), w_dgrad=wd.data_ptr() if wd is not None else None))
+            packs.append(make_op(_lib.OP_PACK, dtype=self.dtype, Cout=c.cout, Cin=c.cin, kh=c.k, kw=c.k,
+                                 cin_pad=cin_pad, cout_pad=cout_pad, w=self.params[c.name + ".weight"].data_ptr(),
+                                 w_fwd=self.w_fwd[c.name].data_ptr(),
+                                 w_dgrad=wd.data_ptr() if wd is not None else None))
+        # one launch for all 47 layers: the descriptors live in a device table
+        import ctypes
+        table = (_lib.PackParams * len(packs))(*[op_params(o) for o in packs])
+        raw = torch.frombuffer(bytearray(bytes(table)), dtype=torch.uint8).clone()
+        self.pack_table = raw.to(self.device)
+        self.keep.append(self.pack_table)
+        ops.append(make_op(_lib.OP_PACK_ALL, p0=self.pack_table.data_ptr(),
+                           n=(len(packs) << 1) | (1 if self.dtype == _lib.BF16 else 0)))
         if not self.training:
             for c in self.convs:
                 if c.bn:
@@ -261,8 +271,7 @@ class UnetPlan:
         if res is not None:
             bn.update(res=res.ptr, ldr=res.ld)
         fwd_fields = {k: v for k, v in bn.items() if k not in ("bstats", "coef")}
-        ops.append(make_op(_lib.OP_BN_FINALIZE, **fwd_fields))
-        ops.append(make_op(_lib.OP_BN_APPLY, **fwd_fields))
+        ops.append(make_op(_lib.OP_BN_APPLY, **fwd_fields))   # finalises the batch statistics itself (stats set)
         self.saved[c.name] = dict(src0=src0, src1=src1, up0=up0, raw=raw, act=act, relu=relu, bn=bn, res=res)
         return act
 
@@ -362,8 +371,7 @@ class UnetPlan:
         bn.pop("res", None)
         bn.pop("ldr", None)
         ops.append(make_op(_lib.OP_BN_BWD_REDUCE, **bn))
-        ops.append(make_op(_lib.OP_BN_BWD_FINALIZE, **bn))
-        ops.append(make_op(_lib.OP_BN_BWD_APPLY, **bn))
+        ops.append(make_op(_lib.OP_BN_BWD_APPLY, **bn))       # derives its coefficients, writes dgamma/dbeta
         return d_raw, g_masked
 
     def _newT(self, like, C=None, H=None, W=None):

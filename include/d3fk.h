@@ -82,7 +82,11 @@ typedef struct d3fk_pack_params {
 } d3fk_pack_params;
 
 /* ---- BatchNorm2d (+residual) + ReLU, train and eval, forward and backward
- * (replaces nn.BatchNorm2d / ReLU / BasicBlock `out += identity`). */
+ * (replaces nn.BatchNorm2d / ReLU / BasicBlock `out += identity`).
+ * bn_apply with `stats` set finalises the batch statistics itself (mean/invstd/running stats written by block 0)
+ * and ignores scale/shift; with stats == NULL it applies the given scale/shift.  bn_bwd_apply derives its
+ * coefficients from bstats/mean/invstd/gamma and writes dgamma/dbeta; bn_finalize / bn_bwd_finalize remain as
+ * stand-alone entry points. */
 typedef struct d3fk_bn_params {
   int32_t dtype, C, relu, _pad0;
   int64_t count;                        /* B*H*W */
@@ -144,7 +148,7 @@ typedef struct d3fk_posterior_params {
   uint64_t seed, offset;
 } d3fk_posterior_params;
 
-typedef struct d3fk_misc_params {          /* MEMSET: p0[0..n) bytes = 0; INC: *(int32*)p0 += 1 */
+typedef struct d3fk_misc_params {          /* MEMSET: p0[0..n) bytes = 0; INC: *(int32*)p0 += 1; PACK_ALL: see enum */
   void* p0; int64_t n;
 } d3fk_misc_params;
 
@@ -156,13 +160,27 @@ typedef struct d3fk_adam_params {
   float lr, beta1, beta2, eps, bias1, bias2, ema_decay, grad_scale;
 } d3fk_adam_params;
 
+/* ---- fused MSE + (1 - SSIM) criterion, forward and gradient
+ * (d3f/loss_functions/structural_similarity_loss.py:14-26 + piqa.SSIM defaults).
+ * acc[0] += sum (pred-target)^2 ; acc[1] += sum of the SSIM map; the caller zeroes acc and forms
+ * loss = (acc[0]/numel + 1 - acc[1]/(B*C*(H-10)*(W-10))) / 2.  grad (nullable) receives grad_scale * dL/dpred. */
+typedef struct d3fk_loss_params {
+  int32_t B, C, H, W;
+  const float* pred; const float* target;   /* fp32 NCHW */
+  float* grad; double* acc;
+  float lo, hi, grad_scale, _pad0;
+  float win[12];                             /* 11-tap normalised Gaussian (+1 pad) */
+} d3fk_loss_params;
+
 enum d3fk_op_kind {
   D3FK_OP_CONV = 1, D3FK_OP_WGRAD = 2, D3FK_OP_PACK = 3, D3FK_OP_NCHW2NHWC = 4,
   D3FK_OP_BN_FINALIZE = 5, D3FK_OP_BN_APPLY = 6, D3FK_OP_BN_FOLD = 7,
   D3FK_OP_BN_BWD_REDUCE = 8, D3FK_OP_BN_BWD_FINALIZE = 9, D3FK_OP_BN_BWD_APPLY = 10,
   D3FK_OP_MAXPOOL_FWD = 11, D3FK_OP_MAXPOOL_BWD = 12, D3FK_OP_SUMPOOL2 = 13,
   D3FK_OP_CHANSUM = 14, D3FK_OP_QSAMPLE = 15, D3FK_OP_POSTERIOR = 16,
-  D3FK_OP_MEMSET = 17, D3FK_OP_INC = 18, D3FK_OP_ADAM = 19
+  D3FK_OP_MEMSET = 17, D3FK_OP_INC = 18, D3FK_OP_ADAM = 19,
+  D3FK_OP_PACK_ALL = 20, /* misc: p0 = device array of d3fk_pack_params, n = (count << 1) | is_bf16 */
+  D3FK_OP_LOSS = 21
 };
 
 typedef struct d3fk_op {
@@ -171,7 +189,7 @@ typedef struct d3fk_op {
     d3fk_conv_params conv; d3fk_wgrad_params wgrad; d3fk_pack_params pack; d3fk_bn_params bn;
     d3fk_pool_params pool; d3fk_layout_params layout; d3fk_chansum_params chansum;
     d3fk_qsample_params qsample; d3fk_posterior_params posterior; d3fk_misc_params misc;
-    d3fk_adam_params adam;
+    d3fk_adam_params adam; d3fk_loss_params loss;
   } u;
 } d3fk_op;
 
@@ -207,6 +225,7 @@ int d3fk_chansum(const d3fk_chansum_params* p, d3fk_stream stream);
 int d3fk_q_sample(const d3fk_qsample_params* p, d3fk_stream stream);
 int d3fk_posterior_step(const d3fk_posterior_params* p, d3fk_stream stream);
 int d3fk_adam(const d3fk_adam_params* p, d3fk_stream stream);
+int d3fk_mse_ssim_loss(const d3fk_loss_params* p, d3fk_stream stream);
 
 /* number of kernels launched by this library since load (bench.py's gpu_launches) */
 int64_t d3fk_launch_count(void);

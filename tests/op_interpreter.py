@@ -135,6 +135,8 @@ def _rows(ptr, count, ld, C_):
 
 def run_bn_apply(p):
     x = _rows(p.x, p.count, p.ldx, p.C)
+    if p.stats:                     # fused finalize (train forward)
+        run_bn_finalize(p)
     v = x * view(p.scale, (p.C,)) + view(p.shift, (p.C,))
     if p.res:
         v = v + _rows(p.res, p.count, p.ldr, p.C)
@@ -172,6 +174,7 @@ def run_bn_bwd_finalize(p):
 
 
 def run_bn_bwd_apply(p):
+    run_bn_bwd_finalize(p)          # the kernel derives its coefficients and writes dgamma/dbeta itself
     dy = _masked_dy(p)
     xh = (_rows(p.x, p.count, p.ldx, p.C) - view(p.mean, (p.C,))) * view(p.invstd, (p.C,))
     coef = view(p.coef, (3, p.C))
@@ -232,6 +235,13 @@ def run_chansum(p):
     view(p.out, (p.C,)).add_(x.sum(0))
 
 
+def run_pack_all(p):
+    n = p.n >> 1
+    table = (_lib.PackParams * n).from_address(p.p0)
+    for i in range(n):
+        run_pack(table[i])
+
+
 def run_memset(p):
     view(p.p0, (p.n,), torch.uint8).zero_()
 
@@ -242,6 +252,7 @@ _DISPATCH = {
     _lib.OP_BN_BWD_REDUCE: run_bn_bwd_reduce, _lib.OP_BN_BWD_FINALIZE: run_bn_bwd_finalize,
     _lib.OP_BN_BWD_APPLY: run_bn_bwd_apply, _lib.OP_MAXPOOL_FWD: run_maxpool_fwd, _lib.OP_MAXPOOL_BWD: run_maxpool_bwd,
     _lib.OP_SUMPOOL2: run_sumpool2, _lib.OP_CHANSUM: run_chansum, _lib.OP_MEMSET: run_memset,
+    _lib.OP_PACK_ALL: run_pack_all,
 }
 
 

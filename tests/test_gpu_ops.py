@@ -136,7 +136,8 @@ def test_pack_and_layout(dtype):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
-@pytest.mark.parametrize("C,count,relu,res", [(64, 2 * 16 * 16, 1, True), (16, 3 * 64 * 64, 1, False), (512, 8, 0, False)])
+@pytest.mark.parametrize("C,count,relu,res", [(64, 2 * 16 * 16, 1, True), (16, 3 * 64 * 64, 1, False), (512, 8, 0, False),
+                                               (256, 1000, 1, False), (32, 50000, 1, True)])
 def test_bn_train_fwd_bwd(dtype, C, count, relu, res):
     g = torch.Generator().manual_seed(3)
     x = torch.randn(count, C, generator=g) * 2 + 0.5
@@ -153,9 +154,18 @@ def test_bn_train_fwd_bwd(dtype, C, count, relu, res):
     r = run_both(_lib.OP_BN_FINALIZE, dtype, t, sc, ["scale", "shift", "mean", "invstd", "running_mean", "running_var", "num_batches_tracked"])
     for n, (a, b) in r.items():
         assert rel_err(a, b) < 1e-6, n
-    t["scale"], t["shift"], t["mean"], t["invstd"] = (r[k][1] for k in ("scale", "shift", "mean", "invstd"))
-    r = run_both(_lib.OP_BN_APPLY, dtype, t, sc, ["y"])
+    # fused finalize + apply (what the plans run): statistics in, activation + saved mean/invstd + running stats out
+    r = run_both(_lib.OP_BN_APPLY, dtype, t, sc, ["y", "mean", "invstd", "running_mean", "running_var", "num_batches_tracked"])
     assert rel_err(*r["y"]) < (1e-6 if dtype == _lib.F32 else 4e-3)
+    for n in ("mean", "invstd", "running_mean", "running_var", "num_batches_tracked"):
+        assert rel_err(*r[n]) < 1e-6, n
+    # stand-alone apply with explicit scale/shift (eval-style)
+    t2 = dict(t)
+    t2.pop("stats")
+    t2["scale"], t2["shift"] = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g)
+    r2 = run_both(_lib.OP_BN_APPLY, dtype, t2, sc, ["y"])
+    assert rel_err(*r2["y"]) < (1e-6 if dtype == _lib.F32 else 4e-3)
+    t["mean"], t["invstd"] = r["mean"][1], r["invstd"][1]
     # backward
     t["act"] = r["y"][1]
     t["dy"] = torch.randn(count, C, generator=g)
@@ -163,7 +173,7 @@ def test_bn_train_fwd_bwd(dtype, C, count, relu, res):
     t["dgamma"], t["dbeta"], t["coef"] = torch.zeros(C), torch.zeros(C), torch.zeros(3, C)
     t["dx"], t["dres"] = torch.zeros(count, C), torch.zeros(count, C)
     sc.update(lddy=C, ldact=C, lddx=C, lddres=C)
-    t.pop("res", None), t.pop("y")
+    t.pop("res", None), t.pop("y"), t.pop("stats")
     sc.pop("ldr", None)
     r = run_both(_lib.OP_BN_BWD_REDUCE, dtype, t, sc, ["bstats"])
     assert rel_err(*r["bstats"]) < (1e-6 if dtype == _lib.F32 else 1e-4)
@@ -171,8 +181,8 @@ def test_bn_train_fwd_bwd(dtype, C, count, relu, res):
     r = run_both(_lib.OP_BN_BWD_FINALIZE, dtype, t, sc, ["dgamma", "dbeta", "coef"])
     for n, (a, b) in r.items():
         assert rel_err(a, b) < 1e-6, n
-    t["coef"] = r["coef"][1]
-    r = run_both(_lib.OP_BN_BWD_APPLY, dtype, t, sc, ["dx", "dres"])
+    t["dgamma"], t["dbeta"] = torch.zeros(C), torch.zeros(C)
+    r = run_both(_lib.OP_BN_BWD_APPLY, dtype, t, sc, ["dx", "dres", "dgamma", "dbeta"])
     for n, (a, b) in r.items():
         assert rel_err(a, b) < (1e-5 if dtype == _lib.F32 else 6e-3), n
 
