@@ -84,33 +84,39 @@ __global__ void bn_apply_kernel(d3fk_bn_params p) {
   const long long e0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;   // multiple of cvs: the channel vector is loop invariant
   const int c = (int)(e0 % cvs) * V;
-  float scf[V], shf[V];
-  if (p.stats) {
-    const double n = (double)p.count;
-#pragma unroll
-    for (int i = 0; i < V; ++i) {
-      const double mean = p.stats[c + i] / n;
-      double var = p.stats[p.C + c + i] / n - mean * mean;
+  extern __shared__ float s_aff[];   // [2][C] scale, shift — derived once per block
+  for (int ch = threadIdx.x; ch < p.C; ch += blockDim.x) {
+    float sc, sh;
+    if (p.stats) {
+      const double n = (double)p.count;
+      const double mean = p.stats[ch] / n;
+      double var = p.stats[p.C + ch] / n - mean * mean;
       if (var < 0) var = 0;
-      const double invstd = 1.0 / sqrt(var + (double)p.eps);
-      const float g = p.gamma[c + i], b = p.beta[c + i];
-      scf[i] = (float)((double)g * invstd);
-      shf[i] = (float)((double)b - mean * (double)g * invstd);
-      if (e0 < cvs) {
-        p.mean[c + i] = (float)mean;
-        p.invstd[c + i] = (float)invstd;
+      const double invstd = rsqrt(var + (double)p.eps);
+      const double g = (double)p.gamma[ch], b = (double)p.beta[ch];
+      sc = (float)(g * invstd);
+      sh = (float)(b - mean * g * invstd);
+      if (blockIdx.x == 0) {
+        p.mean[ch] = (float)mean;
+        p.invstd[ch] = (float)invstd;
         if (p.running_mean) {
           const double unbiased = n > 1 ? var * n / (n - 1) : var;
-          p.running_mean[c + i] = (float)((1.0 - p.momentum) * p.running_mean[c + i] + p.momentum * mean);
-          p.running_var[c + i] = (float)((1.0 - p.momentum) * p.running_var[c + i] + p.momentum * unbiased);
+          p.running_mean[ch] = (float)((1.0 - p.momentum) * p.running_mean[ch] + p.momentum * mean);
+          p.running_var[ch] = (float)((1.0 - p.momentum) * p.running_var[ch] + p.momentum * unbiased);
         }
+        if (ch == 0 && p.num_batches_tracked) *p.num_batches_tracked += 1;
       }
+    } else {
+      sc = __ldg(p.scale + ch);
+      sh = __ldg(p.shift + ch);
     }
-    if (e0 == 0 && p.num_batches_tracked) *p.num_batches_tracked += 1;
-  } else {
-#pragma unroll
-    for (int i = 0; i < V; ++i) { scf[i] = __ldg(p.scale + c + i); shf[i] = __ldg(p.shift + c + i); }
+    s_aff[ch] = sc;
+    s_aff[p.C + ch] = sh;
   }
+  __syncthreads();
+  float scf[V], shf[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) { scf[i] = s_aff[c + i]; shf[i] = s_aff[p.C + c + i]; }
   for (long long e = e0; e < total; e += stride) {
     const long long pix = e / cvs;
     float v[V], r[V];
@@ -232,20 +238,27 @@ __global__ void bn_bwd_apply_kernel(d3fk_bn_params p) {
   const long long e0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
   const int c = (int)(e0 % cvs) * V;
+  extern __shared__ float s_k[];     // [5][C]: k0, k1, k2, mean, invstd — derived once per block
+  for (int ch = threadIdx.x; ch < p.C; ch += blockDim.x) {
+    const double n = (double)p.count;
+    const double s1 = p.bstats[ch], s2 = p.bstats[p.C + ch];
+    const float is = __ldg(p.invstd + ch);
+    s_k[ch] = __ldg(p.gamma + ch) * is;
+    s_k[p.C + ch] = (float)(s1 / n);
+    s_k[2 * p.C + ch] = (float)(s2 / n);
+    s_k[3 * p.C + ch] = __ldg(p.mean + ch);
+    s_k[4 * p.C + ch] = is;
+    if (blockIdx.x == 0) {
+      if (p.dbeta) p.dbeta[ch] = (float)s1;
+      if (p.dgamma) p.dgamma[ch] = (float)s2;
+    }
+  }
+  __syncthreads();
   float k0[V], k1[V], k2[V], mean[V], istd[V];
-  const double n = (double)p.count;
 #pragma unroll
   for (int i = 0; i < V; ++i) {
-    const double s1 = p.bstats[c + i], s2 = p.bstats[p.C + c + i];
-    mean[i] = __ldg(p.mean + c + i);
-    istd[i] = __ldg(p.invstd + c + i);
-    k0[i] = __ldg(p.gamma + c + i) * istd[i];
-    k1[i] = (float)(s1 / n);
-    k2[i] = (float)(s2 / n);
-    if (e0 < cvs) {
-      if (p.dbeta) p.dbeta[c + i] = (float)s1;
-      if (p.dgamma) p.dgamma[c + i] = (float)s2;
-    }
+    k0[i] = s_k[c + i]; k1[i] = s_k[p.C + c + i]; k2[i] = s_k[2 * p.C + c + i];
+    mean[i] = s_k[3 * p.C + c + i]; istd[i] = s_k[4 * p.C + c + i];
   }
   for (long long e = e0; e < total; e += stride) {
     const long long pix = e / cvs;
@@ -541,7 +554,7 @@ int launch_bn_apply(const d3fk_bn_params* p, cudaStream_t s) {
   D3FK_CHECK_ARG(p->C % 8 == 0, "C must be a multiple of 8");
   int V = p->dtype == D3FK_F32 ? 4 : 8;
   long long total = p->count * (p->C / V);
-  DISPATCH_T(p->dtype, bn_apply_kernel<T><<<grid_for(total, 256), 256, 0, s>>>(*p));
+  DISPATCH_T(p->dtype, bn_apply_kernel<T><<<grid_for(total, 256 * 4, 4), 256, 2 * p->C * sizeof(float), s>>>(*p));
   count_launch();
   return check_launch("bn_apply");
 }
@@ -572,7 +585,7 @@ int launch_bn_bwd_apply(const d3fk_bn_params* p, cudaStream_t s) {
   D3FK_CHECK_ARG(p->C % 8 == 0, "C must be a multiple of 8");
   int V = p->dtype == D3FK_F32 ? 4 : 8;
   long long total = p->count * (p->C / V);
-  DISPATCH_T(p->dtype, bn_bwd_apply_kernel<T><<<grid_for(total, 256), 256, 0, s>>>(*p));
+  DISPATCH_T(p->dtype, bn_bwd_apply_kernel<T><<<grid_for(total, 256 * 4, 4), 256, 5 * p->C * sizeof(float), s>>>(*p));
   count_launch();
   return check_launch("bn_bwd_apply");
 }
