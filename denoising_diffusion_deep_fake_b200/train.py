@@ -14,6 +14,7 @@ import torch.nn as nn
 
 from . import _lib
 from .functional import adam_step_, q_sample
+from .parallel import allreduce_bucket_
 from .loss import MseStructuralSimilarityLoss
 from .unet import Unet
 
@@ -86,7 +87,7 @@ class GradAllReduce:
         self.comm.wait_event(ev)
         s, e = self.buckets[i]
         with torch.cuda.stream(self.comm):
-            self.dist.all_reduce(self.model._grad_arena[s:e], op=self.dist.ReduceOp.AVG, group=self.group)
+            allreduce_bucket_(self.model._grad_arena, s, e, self.group)
 
     def wait(self):
         torch.cuda.current_stream().wait_stream(self.comm)

@@ -1,0 +1,61 @@
+"""CPU suite: the C-ABI library loads, exports every symbol include/d3fk.h declares, the Python struct mirror
+matches, and the product fails loudly (no fallback) when there is no sm_100 device."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import denoising_diffusion_deep_fake_b200 as d3
+from denoising_diffusion_deep_fake_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HAS_GPU = torch.cuda.is_available()
+
+
+def header_functions():
+    text = open(os.path.join(ROOT, "include", "d3fk.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(d3fk_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    names = header_functions()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), f"libd3fk.so does not export {n}"
+    assert set(_lib.EXPORTS) <= set(names)
+
+
+def test_struct_mirror_matches_library():
+    lib = _lib.load()
+    assert lib.d3fk_sizeof_op() == ctypes.sizeof(_lib.Op)
+    assert lib.d3fk_version() >= 1
+    op = _lib.make_op(_lib.OP_CONV, B=2, Hi=8, Wi=8, Cout=16, src0=1234)
+    assert op.kind == _lib.OP_CONV and _lib.op_params(op).Cout == 16 and _lib.op_params(op).src0 == 1234
+    with pytest.raises(KeyError):
+        _lib.make_op(_lib.OP_CONV, not_a_field=1)
+
+
+@pytest.mark.skipif(HAS_GPU, reason="checks the no-GPU failure path")
+def test_no_device_is_an_error_not_a_fallback():
+    lib = _lib.load()
+    assert lib.d3fk_init(0) == -2                                   # D3FK_ERR_ARCH
+    assert b"no CPU path" in lib.d3fk_last_error() or b"sm_100" in lib.d3fk_last_error()
+    arr = (_lib.Op * 1)(_lib.make_op(_lib.OP_INC, p0=0, n=1))
+    assert lib.d3fk_run(arr, 1, None) == -2                          # refuses to run uninitialised
+    with pytest.raises(d3.D3fkError):
+        d3.Unet(precision="fp32")(torch.randn(1, 3, 32, 32))
+    with pytest.raises(d3.D3fkError):
+        d3.q_sample(torch.randn(1, 3, 32, 32), 5.0)
+
+
+def test_product_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "denoising_diffusion_deep_fake_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f

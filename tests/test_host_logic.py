@@ -1,0 +1,104 @@
+"""CPU suite: schedules, posterior coefficients, EMA semantics, CLI surface, sharding helpers and a
+world_size-2 gloo run of the gradient bucket allreduce (the N>1 path of bench.py / train.py)."""
+import math
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import oracle
+import denoising_diffusion_deep_fake_b200 as d3
+from denoising_diffusion_deep_fake_b200 import parallel
+from denoising_diffusion_deep_fake_b200.train import EMA, cosine_lr
+
+
+def test_posterior_coefficients_match_oracle():
+    for eta in (0.0, 0.5, 1.0):
+        grid = d3.noise_ratio_grid(17, r_start=1.0)
+        gref = oracle.noise_ratio_grid(17).tolist()
+        assert max(abs(a - b) for a, b in zip(grid, gref)) < 1e-12
+        for i in range(17):
+            a = d3.posterior_coeffs(grid[i], grid[i + 1], eta)
+            b = oracle.sampler.posterior_coeffs(gref[i], gref[i + 1], eta)
+            assert max(abs(u - v) for u, v in zip(a, b)) < 1e-12
+    assert d3.posterior_coeffs(0.3, 0.0, 1.0) == (0.0, 1.0, 0.0)             # last step returns x0_hat
+
+
+def test_cosine_lr_matches_torch_scheduler():
+    p = torch.nn.Parameter(torch.zeros(1))
+    opt = torch.optim.Adam([p], lr=0.02)
+    sch = torch.optim.lr_scheduler.CosineAnnealingLR(opt, T_max=100)
+    for epoch in range(1, 50):
+        opt.step()
+        sch.step()
+        assert abs(opt.param_groups[0]["lr"] - cosine_lr(0.02, epoch, 100)) < 1e-9
+
+
+def test_product_ema_matches_oracle_ema():
+    torch.manual_seed(0)
+    a, b = torch.nn.Linear(6, 6), torch.nn.Linear(6, 6)
+    b.load_state_dict(a.state_dict())
+    ea = oracle.EMA(a, beta=0.999, update_every=1, include_online_model=False)
+    eb = EMA(b, beta=0.999, update_every=1, include_online_model=False)
+    for _ in range(130):
+        with torch.no_grad():
+            d = torch.randn(6, 6) * 0.1
+            a.weight.add_(d), b.weight.add_(d)
+        ea.update(), eb.update()
+        assert torch.allclose(ea.ema_model.weight, eb.ema_model.weight, atol=1e-6)
+    assert set(ea.state_dict()) == set(eb.state_dict())                       # ema_model.*, initted, step
+
+
+def test_cli_surface():
+    from click.testing import CliRunner
+    from denoising_diffusion_deep_fake_b200.main import cli
+    out = CliRunner().invoke(cli, ["--help"]).output
+    for cmd in ("denoise", "train", "sample"):
+        assert cmd in out
+    out = CliRunner().invoke(cli, ["train", "--help"]).output
+    for cmd in ("new", "resume", "modify"):
+        assert cmd in out
+    assert "--config_path" in CliRunner().invoke(cli, ["train", "new", "--help"]).output
+    assert "--input_list" in CliRunner().invoke(cli, ["denoise", "--help"]).output
+
+
+def test_shard_range_partitions():
+    for total in (0, 1, 7, 64, 257):
+        for world in (1, 2, 3, 8):
+            spans = [parallel.shard_range(total, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert max(e - s for s, e in spans) - min(e - s for s, e in spans) <= 1
+
+
+def _dp_worker(rank, world, port, buckets, n):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(100 + rank)
+        arena = torch.randn(n, generator=g)
+        expect = sum(torch.randn(n, generator=torch.Generator().manual_seed(100 + r)) for r in range(world)) / world
+        for s, e in buckets:                                  # one allreduce per backward segment, as in training
+            parallel.allreduce_bucket_(arena, s, e)
+        assert torch.allclose(arena, expect, atol=1e-6)
+        flat = torch.full((5,), float(rank))
+        parallel.broadcast_flat_(flat, src=0)
+        assert torch.equal(flat, torch.zeros(5))
+        x = torch.arange(10.0).view(10, 1)
+        mine = parallel.shard_batch(x, world, rank)
+        allx = parallel.gather_shards(mine.contiguous(), world)
+        assert torch.equal(allx, x)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gradient_bucket_allreduce_gloo_world2():
+    m = d3.Unet(precision="fp32")
+    m._ensure_param_tables()
+    buckets = m.grad_buckets()
+    n = m._grad_numel
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_dp_worker, args=(2, port, buckets, n), nprocs=2, join=True)

@@ -1,0 +1,126 @@
+"""CPU suite: the host logic of the hot path.  The exact op lists the product hands to libd3fk are executed by
+the torch-CPU interpreter (tests/op_interpreter.py) and compared with the oracle: forward (train / eval),
+BN running statistics, every parameter gradient, plan bookkeeping."""
+import copy
+
+import pytest
+import torch
+
+import oracle
+import denoising_diffusion_deep_fake_b200 as d3
+from denoising_diffusion_deep_fake_b200 import _lib
+from denoising_diffusion_deep_fake_b200.plan import UnetPlan, all_convs, backward_param_order, unet_layers
+import op_interpreter as I
+
+
+def rel(a, b):
+    return ((a.double() - b.double()).norm() / (b.double().norm() + 1e-30)).item()
+
+
+def make_pair(seed=0):
+    torch.manual_seed(seed)
+    ref = oracle.Unet()
+    with torch.no_grad():
+        for n, p in ref.named_parameters():
+            if p.dim() == 1 and "segmentation_head" not in n:
+                p.uniform_(0.5, 1.5) if n.endswith("weight") else p.uniform_(-0.3, 0.3)
+    m = d3.Unet(precision="fp32")
+    m.load_state_dict(ref.state_dict())
+    return ref, m
+
+
+def cpu_plan(m, B, H, W, training):
+    m._ensure_grad_arena(torch.device("cpu"))
+    return UnetPlan(dict(m.named_parameters()), dict(m.named_buffers()), B, H, W, _lib.F32, "cpu", training,
+                    grad_arena=m._grad_arena, grad_offsets=m._grad_offsets)
+
+
+def run_forward(plan, x):
+    y = torch.empty_like(x)
+    I.run_ops(plan.pack_ops)
+    _lib.op_params(plan.fwd_ops.array[plan.in_op_index]).src = x.data_ptr()
+    _lib.op_params(plan.fwd_ops.array[plan.out_op_index]).out_nchw = y.data_ptr()
+    I.run_ops(plan.fwd_ops)
+    return y
+
+
+def test_topology_tables():
+    convs = all_convs()
+    assert len(convs) == 47 and sum(1 for c in convs if c.bn) == 46
+    ref, m = make_pair()
+    names = backward_param_order()
+    assert sorted(names) == sorted(n for n, _ in m.named_parameters())
+    assert names[0] == "segmentation_head.0.weight" and names[-1] == "encoder.bn1.bias"
+    buckets = m.grad_buckets()
+    assert buckets[0][0] == 0 and buckets[-1][1] == m._grad_numel
+    assert all(a[1] == b[0] for a, b in zip(buckets, buckets[1:])) and len(buckets) == 5
+    sizes = [e - s for s, e in buckets]
+    assert sizes[1] >= 13_114_368 and sizes[2] >= 6_822_400      # layer4 / layer3 parameters
+    stem, stages, dec, head = unet_layers()
+    assert [len(s) for s in stages] == [3, 4, 6, 3] and dec[0]["conv1"].cin == 768 and head.cout == 3
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 64, 64), (3, 32, 96)])
+def test_train_plan_matches_oracle(B, H, W):
+    ref, m = make_pair()
+    x = torch.randn(B, 3, H, W)
+    dy = torch.randn(B, 3, H, W)
+    plan = cpu_plan(m, B, H, W, True)
+    assert len(plan.pack_ops) == 1 and len(plan.bwd_segments) == 5
+    y = run_forward(plan, x)
+    ref.train()
+    y_ref = ref(x)
+    assert rel(y, y_ref.detach()) < 1e-4        # tiny-batch BN in the 1x3 bottleneck amplifies fp32 rounding
+    sd, sd_ref = m.state_dict(), ref.state_dict()
+    for k in sd_ref:
+        if "running_" in k:
+            assert torch.allclose(sd[k], sd_ref[k], atol=2e-5, rtol=1e-4), k
+        if k.endswith("num_batches_tracked"):
+            assert int(sd[k]) == 1
+    y_ref.backward(dy)
+    _lib.op_params(plan.bwd_segments[0].array[plan.dy_op_index]).src = dy.data_ptr()
+    for seg in plan.bwd_segments:
+        I.run_ops(seg)
+    errs = {}
+    for n, p in ref.named_parameters():
+        off = m._grad_offsets[n]
+        errs[n] = rel(m._grad_arena[off:off + p.numel()].view(p.shape), p.grad)
+    # exact up to ReLU-mask flips (a single flipped element moves a layer's gradient by ~1e-3)
+    assert errs["segmentation_head.0.weight"] < 1e-5 and errs["segmentation_head.0.bias"] < 1e-5
+    assert max(errs.values()) < 2e-2, max(errs, key=errs.get)
+    vals = sorted(errs.values())
+    assert vals[len(vals) // 2] < 5e-3
+
+
+def test_eval_plan_matches_oracle():
+    ref, m = make_pair(seed=1)
+    ref.train()
+    with torch.no_grad():
+        ref(torch.randn(4, 3, 64, 64))
+    m.load_state_dict(ref.state_dict())
+    ref.eval()
+    x = torch.randn(2, 3, 64, 32)
+    plan = cpu_plan(m, 2, 64, 32, False)
+    assert sum(1 for op in plan.fwd_ops if op.kind == _lib.OP_CONV) == 47
+    assert len(plan.fwd_ops) == 49                                  # 47 convs (BN folded) + layout + maxpool
+    y = run_forward(plan, x)
+    with torch.no_grad():
+        assert rel(y, ref(x)) < 1e-5
+
+
+def test_module_contract_on_cpu():
+    ref, m = make_pair()
+    assert set(m.state_dict()) == set(ref.state_dict())
+    assert sum(p.numel() for p in m.parameters()) == 24436659
+    m2 = copy.deepcopy(m)
+    assert all(torch.equal(a, b) for a, b in zip(m.state_dict().values(), m2.state_dict().values()))
+    assert m2._plans == {} and m2 is not m
+    with pytest.raises(ValueError):
+        d3.Unet(encoder_name="resnet50")
+    with pytest.raises(RuntimeError):
+        cpu_plan(m, 1, 48, 64, False)
+    # init distributions follow torchvision (encoder) / smp (decoder, head)
+    fresh = d3.Unet()
+    w = fresh.encoder.layer1[0].conv1.weight
+    assert abs(w.std().item() - (2.0 / (64 * 9)) ** 0.5) < 5e-3       # kaiming_normal_(fan_out)
+    assert float(fresh.segmentation_head[0].bias.abs().max()) == 0.0
