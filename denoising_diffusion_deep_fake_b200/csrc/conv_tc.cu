@@ -110,6 +110,30 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---- thread-block cluster / distributed shared memory helpers (split-K reduction across the CTAs of a cluster)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// all threads of all CTAs of the cluster; release/acquire orders the DSMEM traffic around it
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_f4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout), SWIZZLE_128B, version 1.
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
@@ -189,11 +213,90 @@ template <int BN> struct ConvCfg {
   static constexpr int TMEM_COLS = 2 * ACC_COLS;        // double buffered: epilogue of tile i overlaps MMAs of tile i+1
 };
 
-// Tile schedule: tile t -> (m tile, k split, n tile); consecutive CTAs walk consecutive m tiles.
+// Tile schedule.  KS == 1: tile t -> (m tile, n tile), consecutive CTAs walk consecutive m tiles, persistent loop.
+// KS > 1 (split K over a thread-block cluster of KS CTAs): one tile per CTA, t -> (k split = cluster rank, m tile, n tile);
+// the KS partial accumulators are reduce-scattered through distributed shared memory (no workspace, no second kernel).
 struct TileSched {
   int MT, NT, KS, kb_per_split, nkb, total, a_ca;
   int bw, bh, bn, wt, ht;   // PATH 2: the 128-pixel M tile as a (w, h, n) box and the tile grid along w / h
 };
+
+__device__ __forceinline__ void decode_tile(const TileSched& ts, int t, int& mt, int& nt, int& ks) {
+  if (ts.KS > 1) {
+    ks = t % ts.KS;
+    const int r = t / ts.KS;
+    mt = r % ts.MT;
+    nt = r / ts.MT;
+  } else {
+    ks = 0;
+    mt = t % ts.MT;
+    nt = t / ts.MT;
+  }
+}
+
+// Epilogue of CW accumulator columns [cbase, cbase+CW) of output row m held in f[]: folded-BN affine / bias, residual,
+// ReLU, store (bf16 NHWC or fp32 NCHW) and per-channel batch statistics.  The statistics are folded over the 32 rows of
+// the warp with a transpose-reduce and ACCUMULATED into this warp's shared-memory slots (sstat_warp[col], [BN + col]);
+// the CTA flushes the slots to global memory with one double atomic per channel when its n tile changes / at the end.
+template <int CW>
+__device__ __forceinline__ void epilogue_chunk(float (&f)[CW], const EpiTC& e, long long m, bool row_ok, int cbase, int on,
+                                               int oh, int ow, bool do_stats, float* sstat_sum, float* sstat_sq, int lane) {
+  if (e.scale) {
+#pragma unroll
+    for (int i = 0; i < CW; ++i)
+      if (cbase + i < e.Cout) f[i] = fmaf(f[i], __ldg(e.scale + cbase + i), __ldg(e.shift + cbase + i));
+  } else if (e.shift) {
+#pragma unroll
+    for (int i = 0; i < CW; ++i)
+      if (cbase + i < e.Cout) f[i] += __ldg(e.shift + cbase + i);
+  }
+  if (e.res && row_ok) {
+    const uint4* rp4 = reinterpret_cast<const uint4*>(e.res + m * e.ldr + cbase);
+#pragma unroll
+    for (int q = 0; q < CW / 8; ++q) {
+      uint4 rr = __ldg(rp4 + q);
+      const bf16* rb16 = reinterpret_cast<const bf16*>(&rr);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[q * 8 + i] += __bfloat162float(rb16[i]);
+    }
+  }
+  if (e.relu) {
+#pragma unroll
+    for (int i = 0; i < CW; ++i) f[i] = fmaxf(f[i], 0.f);
+  }
+  if (row_ok) {
+    if (e.out_nchw) {
+#pragma unroll
+      for (int i = 0; i < CW; ++i)
+        if (cbase + i < e.Cout) e.out_nchw[(((long long)on * e.Cout + cbase + i) * e.Ho + oh) * e.Wo + ow] = f[i];
+    } else {
+      uint4* op = reinterpret_cast<uint4*>(e.out + m * e.ldo + cbase);
+#pragma unroll
+      for (int q = 0; q < CW / 8; ++q) {
+        uint4 o;
+        __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o2[i] = __floats2bfloat162_rn(f[q * 8 + 2 * i], f[q * 8 + 2 * i + 1]);
+        op[q] = o;
+      }
+    }
+  }
+  if (do_stats) {
+    float sq[CW];
+#pragma unroll
+    for (int i = 0; i < CW; ++i) {
+      if (!row_ok) f[i] = 0.f;
+      sq[i] = f[i] * f[i];
+    }
+    float cs, cq;
+    if (CW == 32) { cs = warp_colsum32(f, lane); cq = warp_colsum32(sq, lane); }
+    else { cs = warp_colsum16(f, lane); cq = warp_colsum16(sq, lane); }
+    if (lane < CW) {           // one writer per (warp, column) slot: no shared-memory atomics, deterministic
+      sstat_sum[lane] += cs;
+      sstat_sq[lane] += cq;
+    }
+  }
+}
 
 // PATH 0 (LINEAR): one source, no upsample, forward gather or stride-1 transposed gather — the tap
 //   offset is the same for every row, so a row costs two compares, one 64-bit add and the cp.async.
@@ -205,9 +308,10 @@ struct TileSched {
 template <int BN, int PATH>
 __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(Gather g, FastDiv dWo, FastDiv dHo, const __grid_constant__ CUtensorMap tmA,
                                                              const __grid_constant__ CUtensorMap tmB, EpiTC e, TileSched ts,
-                                                             float* __restrict__ ws, int* errflag) {
+                                                             int* errflag) {
   using Cfg = ConvCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
+  constexpr int CW = BN >= 32 ? 32 : 16;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = base;
@@ -222,6 +326,8 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(Gather g, FastDiv d
   auto acc_empty_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool clus = ts.KS > 1;
+  const bool do_stats = e.stats != nullptr;
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -234,6 +340,9 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(Gather g, FastDiv d
     }
     fence_barrier_init();
   }
+  if (tid < 128) {
+    for (int i = tid; i < 8 * BN; i += 128) s_stat[i] = 0.f;
+  }
   if (warp == 5 && lane == 0) {
     tma_prefetch_desc(&tmB);
     if (PATH == 2) tma_prefetch_desc(&tmA);
@@ -244,6 +353,26 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(Gather g, FastDiv d
   tc_fence_after();
   const uint32_t tmem_d = *tmem_ptr_slot;
 
+  // flush this CTA's accumulated statistics of n tile `nt` (epilogue warps only)
+  auto flush_stats = [&](int nt) {
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    const int n0 = nt * BN;
+    if (tid < BN && n0 + tid < e.Cout) {
+      const float a = (s_stat[tid] + s_stat[2 * BN + tid]) + (s_stat[4 * BN + tid] + s_stat[6 * BN + tid]);
+      const float b = (s_stat[BN + tid] + s_stat[3 * BN + tid]) + (s_stat[5 * BN + tid] + s_stat[7 * BN + tid]);
+      if (a != 0.f || b != 0.f) {
+        atomicAdd(&e.stats[n0 + tid], (double)a);
+        atomicAdd(&e.stats[e.Cout + n0 + tid], (double)b);
+      }
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    for (int i = tid; i < 8 * BN; i += 128) s_stat[i] = 0.f;
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+  };
+
+  int my_mt = 0, my_nt = 0, my_ks = 0;   // cluster mode: the single tile of this CTA
+  if (clus) decode_tile(ts, blockIdx.x, my_mt, my_nt, my_ks);
+
   if (warp == 5) {
     // ===================== TMA producer (one thread) =====================
     if (lane == 0) {
@@ -251,10 +380,8 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(Gather g, FastDiv d
       const int sgn = g.mode ? -1 : 1;
       const int off = g.mode ? g.pad : -g.pad;
       for (int t = blockIdx.x; t < ts.total; t += gridDim.x) {
-        const int mt = t % ts.MT;
-        const int r_ = t / ts.MT;
-        const int ks = r_ % ts.KS;
-        const int nt = r_ / ts.KS;
+        int mt, nt, ks;
+        decode_tile(ts, t, mt, nt, ks);
         const int kb0 = ks * ts.kb_per_split;
         const int kb1 = min(ts.nkb, kb0 + ts.kb_per_split);
         int w0 = 0, h0 = 0, i0 = 0, tap = 0, c = 0, khi = 0, kwi = 0;
@@ -296,11 +423,10 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(Gather g, FastDiv d
     const int sshift = g.mode ? g.sshift : 0;                        // of the stride (forward folds it into h0/w0)
     uint32_t kbg = 0;  // k-blocks issued by this CTA so far (pipeline stage / phase bookkeeping)
     uint32_t tile_iter = 0;
+    int cur_nt = -1;
     for (int t = blockIdx.x; t < ts.total; t += gridDim.x, ++tile_iter) {
-      const int mt = t % ts.MT;
-      const int r_ = t / ts.MT;
-      const int ks = r_ % ts.KS;
-      const int nt = r_ / ts.KS;
+      int mt, nt, ks;
+      decode_tile(ts, t, mt, nt, ks);
       const int m0 = mt * TC_BM, n0 = nt * BN;
       const int kb0 = ks * ts.kb_per_split;
       const int kb1 = min(ts.nkb, kb0 + ts.kb_per_split);
@@ -379,12 +505,14 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(Gather g, FastDiv d
       const uint32_t abuf = tile_iter & 1;
       mbar_wait(acc_full_bar(abuf), (tile_iter >> 1) & 1, errflag);
       tc_fence_after();
+      if (clus) break;   // split K: the accumulator is reduced across the cluster below
+      if (do_stats && cur_nt != nt) {
+        if (cur_nt >= 0) flush_stats(cur_nt);
+        cur_nt = nt;
+      }
       const int row = warp * 32 + lane;
       const int m = m0 + row;
       const bool row_ok = m < g.M;
-      constexpr int CW = BN >= 32 ? 32 : 16;
-      const bool split = ts.KS > 1;
-      const bool do_stats = e.stats != nullptr && !split;
       int on = 0, oh = 0, ow = 0;
       if (e.out_nchw && row_ok) {
         const uint32_t q = fdiv((uint32_t)m, dWo);
@@ -398,97 +526,24 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(Gather g, FastDiv d
         const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + abuf * Cfg::ACC_COLS + (uint32_t)cc;
         if (CW == 32) tmem_ld32(taddr, raw); else tmem_ld16(taddr, raw);
         tmem_ld_wait();
-        const int cbase = n0 + cc;
-        if (split) {
-          // split-K: plain fp32 partial tile; conv_splitk_finish sums the splits and runs the epilogue
-          if (row_ok) {
-            float4* wp4 = reinterpret_cast<float4*>(ws + ((long long)ks * g.M + m) * e.Cout + cbase);
-#pragma unroll
-            for (int q = 0; q < CW / 4; ++q)
-              wp4[q] = make_float4(__uint_as_float(raw[4 * q]), __uint_as_float(raw[4 * q + 1]),
-                                   __uint_as_float(raw[4 * q + 2]), __uint_as_float(raw[4 * q + 3]));
-          }
-          continue;
-        }
         float f[CW];
 #pragma unroll
         for (int i = 0; i < CW; ++i) f[i] = __uint_as_float(raw[i]);
-        if (e.scale) {
-#pragma unroll
-          for (int i = 0; i < CW; ++i)
-            if (cbase + i < e.Cout) f[i] = fmaf(f[i], __ldg(e.scale + cbase + i), __ldg(e.shift + cbase + i));
-        } else if (e.shift) {
-#pragma unroll
-          for (int i = 0; i < CW; ++i)
-            if (cbase + i < e.Cout) f[i] += __ldg(e.shift + cbase + i);
-        }
-        if (e.res && row_ok) {
-          const uint4* rp4 = reinterpret_cast<const uint4*>(e.res + (long long)m * e.ldr + cbase);
-#pragma unroll
-          for (int q = 0; q < CW / 8; ++q) {
-            uint4 rr = __ldg(rp4 + q);
-            const bf16* rb16 = reinterpret_cast<const bf16*>(&rr);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) f[q * 8 + i] += __bfloat162float(rb16[i]);
-          }
-        }
-        if (e.relu) {
-#pragma unroll
-          for (int i = 0; i < CW; ++i) f[i] = fmaxf(f[i], 0.f);
-        }
-        if (row_ok) {
-          if (e.out_nchw) {
-#pragma unroll
-            for (int i = 0; i < CW; ++i)
-              if (cbase + i < e.Cout) e.out_nchw[(((long long)on * e.Cout + cbase + i) * e.Ho + oh) * e.Wo + ow] = f[i];
-          } else {
-            uint4* op = reinterpret_cast<uint4*>(e.out + (long long)m * e.ldo + cbase);
-#pragma unroll
-            for (int q = 0; q < CW / 8; ++q) {
-              uint4 o;
-              __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) o2[i] = __floats2bfloat162_rn(f[q * 8 + 2 * i], f[q * 8 + 2 * i + 1]);
-              op[q] = o;
-            }
-          }
-        }
-        if (do_stats) {
-          float sq[CW];
-#pragma unroll
-          for (int i = 0; i < CW; ++i) {
-            if (!row_ok) f[i] = 0.f;
-            sq[i] = f[i] * f[i];
-          }
-          float cs, cq;
-          if (CW == 32) { cs = warp_colsum32(f, lane); cq = warp_colsum32(sq, lane); }
-          else { cs = warp_colsum16(f, lane); cq = warp_colsum16(sq, lane); }
-          if (lane < CW) {           // per-warp slots: no shared-memory atomics, deterministic
-            s_stat[warp * 2 * BN + cc + lane] = cs;
-            s_stat[warp * 2 * BN + BN + cc + lane] = cq;
-          }
-        }
-      }
-      if (do_stats) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (tid < BN && n0 + tid < e.Cout) {
-          const float a = (s_stat[tid] + s_stat[2 * BN + tid]) + (s_stat[4 * BN + tid] + s_stat[6 * BN + tid]);
-          const float b = (s_stat[BN + tid] + s_stat[3 * BN + tid]) + (s_stat[5 * BN + tid] + s_stat[7 * BN + tid]);
-          atomicAdd(&e.stats[n0 + tid], (double)a);
-          atomicAdd(&e.stats[e.Cout + n0 + tid], (double)b);
-        }
-        asm volatile("bar.sync 1, 128;" ::: "memory");   // slots are rewritten by the next tile
+        epilogue_chunk<CW>(f, e, (long long)m, row_ok, n0 + cc, on, oh, ow, do_stats, s_stat + warp * 2 * BN + cc,
+                           s_stat + warp * 2 * BN + BN + cc, lane);
       }
       tc_fence_before();   // this tile's TMEM reads are done: hand the accumulator buffer back to the MMA issuer
       mbar_arrive(acc_empty_bar(abuf));
     }
+    if (!clus && do_stats && cur_nt >= 0) flush_stats(cur_nt);
   } else if (warp == 4) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(TC_BM, BN, 0, 0);
       uint32_t kbg = 0, tile_iter = 0;
       for (int t = blockIdx.x; t < ts.total; t += gridDim.x, ++tile_iter) {
-        const int ks = (t / ts.MT) % ts.KS;
+        int mt, nt, ks;
+        decode_tile(ts, t, mt, nt, ks);
         const int kb0 = ks * ts.kb_per_split;
         const int kb1 = min(ts.nkb, kb0 + ts.kb_per_split);
         const uint32_t abuf = tile_iter & 1;
@@ -517,73 +572,62 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(Gather g, FastDiv d
     __syncwarp();
   }
 
+  if (clus) {
+    // ===================== split-K reduction across the cluster (KS CTAs, one k slice each) =====================
+    // Every CTA holds a 128 x BN fp32 partial tile in TMEM.  Column slice j (SL = BN/KS columns) is owned by rank j:
+    // each CTA writes its partial of slice j into slot [own rank] of rank j's receive buffer (the pipeline stages are
+    // dead once every CTA has finished its main loop), then each owner sums KS slots and runs the epilogue on its slice.
+    const int KS = ts.KS, SL = BN / KS, sl4 = SL >> 2;
+    const uint32_t rank = cluster_ctarank();
+    const uint32_t recv = a_base;   // [KS][SL/4][128 rows] float4
+    const int row = warp * 32 + lane;
+    tc_fence_before();
+    cluster_sync_all();             // #1: all main loops done (every epilogue warp saw acc_full)
+    tc_fence_after();
+    if (warp < 4) {
+#pragma unroll 1
+      for (int cc = 0; cc < BN; cc += CW) {
+        uint32_t raw[CW];
+        const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)cc;
+        if (CW == 32) tmem_ld32(taddr, raw); else tmem_ld16(taddr, raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < CW / 4; ++q) {
+          const int col = cc + 4 * q;
+          const int owner = col / SL, within = col - owner * SL;
+          const uint32_t la = recv + (uint32_t)((((int)rank * sl4 + (within >> 2)) * 128 + row) * 16);
+          st_cluster_f4(mapa_shared(la, (uint32_t)owner), raw[4 * q], raw[4 * q + 1], raw[4 * q + 2], raw[4 * q + 3]);
+        }
+      }
+    }
+    cluster_sync_all();             // #2: all partials have landed
+    if (warp < 4) {
+      const int m = my_mt * TC_BM + row;
+      const bool row_ok = m < g.M;
+      const int cslice = (int)rank * SL;     // first column of my slice within the tile
+#pragma unroll 1
+      for (int ch = 0; ch < SL; ch += 16) {
+        float f[16];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int r = 0; r < KS; ++r) {
+            const float4 v = ld_shared_f4(recv + (uint32_t)(((r * sl4 + (ch >> 2) + q) * 128 + row) * 16));
+            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+          }
+          f[4 * q] = a.x; f[4 * q + 1] = a.y; f[4 * q + 2] = a.z; f[4 * q + 3] = a.w;
+        }
+        const int ct = cslice + ch;          // column within the tile
+        epilogue_chunk<16>(f, e, (long long)m, row_ok, my_nt * BN + ct, 0, 0, 0, do_stats, s_stat + warp * 2 * BN + ct,
+                           s_stat + warp * 2 * BN + BN + ct, lane);
+      }
+      if (do_stats) flush_stats(my_nt);
+    }
+  }
+
   tc_fence_before();
   __syncthreads();
   if (warp == 4) tmem_dealloc(tmem_d, Cfg::TMEM_COLS);
-}
-
-// split-K second pass: sum the fp32 partial tiles, run the conv epilogue, emit BN statistics
-__global__ void __launch_bounds__(256) conv_splitk_finish_kernel(const float* __restrict__ ws, int KS, int M, EpiTC e) {
-  extern __shared__ float s_red[];  // [2][Cout]
-  const int N = e.Cout, cvs = N / 8;
-  const bool do_stats = e.stats != nullptr;
-  if (do_stats) {
-    for (int i = threadIdx.x; i < 2 * N; i += blockDim.x) s_red[i] = 0.f;
-    __syncthreads();
-  }
-  const int rows_per_iter = blockDim.x / cvs;
-  const int cv = threadIdx.x % cvs, prow = threadIdx.x / cvs;
-  const int c = cv * 8;
-  float s1[8], s2[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
-  if (prow < rows_per_iter) {
-    for (int m = blockIdx.x * rows_per_iter + prow; m < M; m += gridDim.x * rows_per_iter) {
-      float f[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) f[i] = 0.f;
-      for (int ks = 0; ks < KS; ++ks) {
-        const float4* p = reinterpret_cast<const float4*>(ws + ((long long)ks * M + m) * N + c);
-        float4 a = __ldg(p), b = __ldg(p + 1);
-        f[0] += a.x; f[1] += a.y; f[2] += a.z; f[3] += a.w; f[4] += b.x; f[5] += b.y; f[6] += b.z; f[7] += b.w;
-      }
-      if (e.scale) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i], __ldg(e.scale + c + i), __ldg(e.shift + c + i));
-      } else if (e.shift) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) f[i] += __ldg(e.shift + c + i);
-      }
-      if (e.res) {
-        uint4 rr = __ldg(reinterpret_cast<const uint4*>(e.res + (long long)m * e.ldr + c));
-        const bf16* rb16 = reinterpret_cast<const bf16*>(&rr);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) f[i] += __bfloat162float(rb16[i]);
-      }
-      if (e.relu) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
-      }
-      uint4 o;
-      __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) o2[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-      *reinterpret_cast<uint4*>(e.out + (long long)m * e.ldo + c) = o;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) { s1[i] += f[i]; s2[i] += f[i] * f[i]; }
-    }
-    if (do_stats) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        atomicAdd(&s_red[c + i], s1[i]);
-        atomicAdd(&s_red[N + c + i], s2[i]);
-      }
-    }
-  }
-  if (do_stats) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < 2 * N; i += blockDim.x) atomicAdd(&e.stats[i], (double)s_red[i]);
-  }
 }
 
 static int g_num_sms = 148;
@@ -592,6 +636,26 @@ static int g_a_ca = 0;        // D3FK_A_CA=1: L1-allocating activation gather
 static int g_occ_cap = 0;     // D3FK_OCC=n: cap CTAs per SM
 static int g_use_tma_a = 1;   // D3FK_TMA_A=0: force the gather producers (debug aid)
 static int g_split_tiles = 74;  // split K only when the output tiles fill at most this many SMs
+static int g_max_cluster = 8;   // D3FK_CLUSTER=n: cap the split-K cluster size (1 disables split K)
+
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, dim3 cluster,
+                                  Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster.x;
+  attr[0].val.clusterDim.y = cluster.y;
+  attr[0].val.clusterDim.z = cluster.z;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 template <int BN, int PATH>
 static int launch_conv_tc_bn(const Gather& g, const d3fk_conv_params* p, cudaStream_t s, const TileSched& box) {
@@ -603,22 +667,23 @@ static int launch_conv_tc_bn(const Gather& g, const d3fk_conv_params* p, cudaStr
   ts.KS = 1;
   const int tiles = ts.MT * ts.NT;
   ts.a_ca = g_a_ca && p->kh > 1;
-  // split K when the output tiles cannot fill the chip and the reduction is long
-  if (p->ws && !p->out_nchw && p->Cout % BN == 0 && tiles <= g_split_tiles && ts.nkb >= 8) {
-    int ks = cdiv(2 * g_num_sms, tiles);
-    if (ks > ts.nkb / 4) ks = ts.nkb / 4;
-    if (ks > 16) ks = 16;
-    while (ks > 1 && (long long)ks * g.M * p->Cout * 4 > p->ws_bytes) --ks;
-    if (ks > 1) ts.KS = ks;
+  // split K over a cluster when the output tiles cannot fill the chip and the reduction is long
+  if (BN == 128 && !p->out_nchw && p->Cout % BN == 0 && tiles <= g_split_tiles && ts.nkb >= 8 && g_max_cluster > 1) {
+    int ks = 1;
+    while (ks * 2 <= g_max_cluster && ks * 2 <= 8 && tiles * ks * 2 <= 2 * g_num_sms && ts.nkb / (ks * 2) >= 4) ks *= 2;
+    ts.KS = ks;
   }
   ts.kb_per_split = cdiv(ts.nkb, ts.KS);
-  ts.KS = cdiv(ts.nkb, ts.kb_per_split);
+  if (ts.KS > 1 && (ts.KS - 1) * ts.kb_per_split >= ts.nkb) {   // every rank needs at least one k-block
+    ts.KS = 1;
+    ts.kb_per_split = ts.nkb;
+  }
   ts.total = tiles * ts.KS;
   int occ = (227 * 1024) / (ConvCfg<BN>::SMEM + 1024);
   if (occ * ConvCfg<BN>::TMEM_COLS > 512) occ = 512 / ConvCfg<BN>::TMEM_COLS;
   if (g_occ_cap > 0 && occ > g_occ_cap) occ = g_occ_cap;
   int grid = ts.total < g_num_sms * occ ? ts.total : g_num_sms * occ;
-  if (!g_tile_loop) grid = ts.total;
+  if (!g_tile_loop || ts.KS > 1) grid = ts.total;
 
   // TMA descriptors: weights [Cout][K] as a {64, BN} box; PATH 2 also the activation tensor as a 4-D NHWC box
   alignas(64) CUtensorMap tmA, tmB;
@@ -637,20 +702,16 @@ static int launch_conv_tc_bn(const Gather& g, const d3fk_conv_params* p, cudaStr
     int rc = get_tensor_map(&tmA, p->src0, 4, dims, strides, bx, 128);
     if (rc) return rc;
   }
-  conv_tc_kernel<BN, PATH><<<grid, TC_THREADS, ConvCfg<BN>::SMEM, s>>>(g, make_fastdiv((uint32_t)g.Wo), make_fastdiv((uint32_t)g.Ho),
-                                                                    tmA, tmB, e, ts, (float*)p->ws, g_dev_error_flag);
+  if (ts.KS > 1) {
+    cudaError_t le = launch_cluster(conv_tc_kernel<BN, PATH>, dim3(grid), dim3(TC_THREADS), ConvCfg<BN>::SMEM, s, dim3(ts.KS, 1, 1), g,
+                                    make_fastdiv((uint32_t)g.Wo), make_fastdiv((uint32_t)g.Ho), tmA, tmB, e, ts, g_dev_error_flag);
+    if (le != cudaSuccess) return set_error(D3FK_ERR_CUDA, "conv_tc cluster launch: %s", cudaGetErrorString(le));
+  } else {
+    conv_tc_kernel<BN, PATH><<<grid, TC_THREADS, ConvCfg<BN>::SMEM, s>>>(g, make_fastdiv((uint32_t)g.Wo), make_fastdiv((uint32_t)g.Ho),
+                                                                      tmA, tmB, e, ts, g_dev_error_flag);
+  }
   count_launch();
-  int rc = check_launch("conv_tc");
-  if (rc || ts.KS == 1) return rc;
-  const int cvs = p->Cout / 8;
-  int threads = 256;
-  if (cvs > threads) threads = cvs;
-  const int rows = threads / cvs;
-  int fgrid = cdiv(g.M, rows * 4);
-  if (fgrid > g_num_sms * 8) fgrid = g_num_sms * 8;
-  conv_splitk_finish_kernel<<<fgrid, threads, 2 * p->Cout * sizeof(float), s>>>((const float*)p->ws, ts.KS, g.M, e);
-  count_launch();
-  return check_launch("conv_splitk_finish");
+  return check_launch("conv_tc");
 }
 
 template <int PATH>
@@ -705,10 +766,13 @@ int launch_conv_tc(const d3fk_conv_params* p, cudaStream_t s) {
 // weight gradient.  Stage = 64 pixels (the MMA K dimension, 4 x K16).
 //   A stage: 2 column blocks (64 k-columns each) x [64 pixels x 128 B]   (MN-major, M = k index)
 //   B stage: BN/64 column blocks (64 channels each) x [64 pixels x 128 B] (MN-major, N = co)
+// Grid (k tiles, cout tiles, pixel splits); the splits of one output tile form thread-block clusters of CL CTAs whose
+// partial tiles are reduce-scattered through distributed shared memory, so a tile costs (splits / CL) atomic passes
+// (none when splits == CL) instead of `splits`.
 constexpr int WG_PIX = 64;
 constexpr int WG_A_STAGE = 2 * WG_PIX * 128;
 template <int BN> struct WgradCfg {
-  static constexpr int STAGES = 4;
+  static constexpr int STAGES = BN >= 128 ? 3 : 4;
   static constexpr int NCB = BN / 64;
   static constexpr int B_STAGE = NCB * WG_PIX * 128;
   static constexpr int SMEM = 1024 + STAGES * (WG_A_STAGE + B_STAGE) + 256;
@@ -719,9 +783,10 @@ template <int BN>
 __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(Gather g, FastDiv dWo, FastDiv dHo, const bf16* __restrict__ dy,
                                                               int ldy, int Cout, float* __restrict__ dw, int cin_real,
                                                               int cout_real, int blocks_per_split, int lbo_a, int lbo_b,
-                                                              int* errflag) {
+                                                              int CL, int* errflag) {
   using Cfg = WgradCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
+  constexpr int CW = 32;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = base;
@@ -739,6 +804,7 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(Gather g, FastDiv 
   const int blk_beg = blockIdx.z * blocks_per_split;
   const int blk_end = min(nblk_total, blk_beg + blocks_per_split);
   const int nblk = max(0, blk_end - blk_beg);
+  const bool use_atomic = (int)gridDim.z > CL;
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -753,6 +819,24 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(Gather g, FastDiv 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = *tmem_ptr_slot;
+
+  // output row of this thread (epilogue): k index -> (tap, ci)
+  const int krow = k0 + (warp & 3) * 32 + lane;
+  int tap_o = 0, ci_o = 0;
+  if (krow < g.K) { tap_o = krow / g.ctot; ci_o = krow - tap_o * g.ctot; }
+  const bool row_ok = krow < g.K && ci_o < cin_real;
+  const int taps = g.kh * g.kw;
+  auto emit4 = [&](int co, float a, float b, float c, float d) {   // columns co..co+3 of this thread's row
+    float v[4] = {a, b, c, d};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (co + i < cout_real) {
+        float* dst = dw + ((long long)(co + i) * cin_real + ci_o) * taps + tap_o;
+        if (use_atomic) atomicAdd(dst, v[i]);
+        else *dst = v[i];
+      }
+    }
+  };
 
   if (warp < 4) {
     const int j = tid & 7;
@@ -814,34 +898,26 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(Gather g, FastDiv 
       cp_async_mbar_arrive(full_bar(s));
       mbar_arrive(full_bar(s));
     }
-
-    // epilogue: D[k row][co col] -> atomic add into fp32 OIHW dw
     if (nblk > 0) {
       mbar_wait(accum_bar, 0, errflag);
       tc_fence_after();
-      const int k = k0 + warp * 32 + lane;
-      const bool k_ok = k < g.K;
-      int tap = 0, ci = 0;
-      if (k_ok) { tap = k / g.ctot; ci = k - tap * g.ctot; }
-      const bool row_ok = k_ok && ci < cin_real;
-      const int taps = g.kh * g.kw;
-      constexpr int CW = BN >= 32 ? 32 : 16;
+    }
+    if (CL == 1 && nblk > 0) {
+      // no cluster: D[k row][co col] straight from TMEM (atomic when the pixels are split over several CTAs)
 #pragma unroll 1
       for (int cc = 0; cc < BN; cc += CW) {
         uint32_t raw[CW];
-        const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)cc;
-        if (CW == 32) tmem_ld32(taddr, raw); else tmem_ld16(taddr, raw);
+        tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)cc, raw);
         tmem_ld_wait();
         if (row_ok) {
 #pragma unroll
-          for (int i = 0; i < CW; ++i) {
-            int co = co0 + cc + i;
-            if (co < cout_real) atomicAdd(dw + ((long long)co * cin_real + ci) * taps + tap, __uint_as_float(raw[i]));
-          }
+          for (int q = 0; q < CW / 4; ++q)
+            emit4(co0 + cc + 4 * q, __uint_as_float(raw[4 * q]), __uint_as_float(raw[4 * q + 1]), __uint_as_float(raw[4 * q + 2]),
+                  __uint_as_float(raw[4 * q + 3]));
         }
       }
     }
-  } else {
+  } else if (warp == 4) {
     if (lane == 0 && nblk > 0) {
       constexpr uint32_t idesc = make_idesc(128, BN, 1, 1);
       for (int it = 0; it < nblk; ++it) {
@@ -862,24 +938,73 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(Gather g, FastDiv 
     }
     __syncwarp();
   }
+
+  if (CL > 1) {
+    // reduce-scatter the CL partial tiles through distributed shared memory (see conv_tc_kernel)
+    const int SL = BN / CL, sl4 = SL >> 2;
+    const uint32_t rank = cluster_ctarank();
+    const uint32_t recv = a_base;   // [CL][SL/4][128 rows] float4 over the dead pipeline stages
+    const int row = (warp & 3) * 32 + lane;
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    if (warp < 4) {
+#pragma unroll 1
+      for (int cc = 0; cc < BN; cc += CW) {
+        uint32_t raw[CW];
+        if (nblk > 0) {
+          tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)cc, raw);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int i = 0; i < CW; ++i) raw[i] = 0u;   // a split with no pixel blocks contributes zeros
+        }
+#pragma unroll
+        for (int q = 0; q < CW / 4; ++q) {
+          const int col = cc + 4 * q;
+          const int owner = col / SL, within = col - owner * SL;
+          const uint32_t la = recv + (uint32_t)((((int)rank * sl4 + (within >> 2)) * 128 + row) * 16);
+          st_cluster_f4(mapa_shared(la, (uint32_t)owner), raw[4 * q], raw[4 * q + 1], raw[4 * q + 2], raw[4 * q + 3]);
+        }
+      }
+    }
+    cluster_sync_all();
+    if (warp < 4 && row_ok) {
+      for (int c4 = 0; c4 < sl4; ++c4) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int r = 0; r < CL; ++r) {
+          const float4 v = ld_shared_f4(recv + (uint32_t)(((r * sl4 + c4) * 128 + row) * 16));
+          a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        }
+        emit4(co0 + (int)rank * SL + 4 * c4, a.x, a.y, a.z, a.w);
+      }
+    }
+  }
+
   tc_fence_before();
   __syncthreads();
   if (warp == 4) tmem_dealloc(tmem_d, Cfg::TMEM_COLS);
 }
 
+static int g_wg_ctas_per_sm = 2;
+
 template <int BN>
 static int launch_wgrad_tc_bn(const Gather& g, const d3fk_wgrad_params* p, cudaStream_t s) {
   const int gx = cdiv(g.K, 128), gy = cdiv(p->Cout, BN);
   const int nblk = cdiv(g.M, WG_PIX);
-  int splits = cdiv(148 * 2, gx * gy);
+  const int tiles = gx * gy;
+  int splits = (g_num_sms * g_wg_ctas_per_sm) / tiles;
   if (splits > nblk) splits = nblk;
   if (splits < 1) splits = 1;
-  int bps = cdiv(nblk, splits);
-  splits = cdiv(nblk, bps);
+  int cl = 1;
+  while (cl * 2 <= splits && cl * 2 <= g_max_cluster && cl * 2 <= 8) cl *= 2;
+  splits = (splits / cl) * cl;
+  const int bps = cdiv(nblk, splits);
   dim3 grid(gx, gy, splits);
-  wgrad_tc_kernel<BN><<<grid, WG_THREADS, WgradCfg<BN>::SMEM, s>>>(
-      g, make_fastdiv((uint32_t)g.Wo), make_fastdiv((uint32_t)g.Ho), (const bf16*)p->dy, p->ldy, p->Cout, p->dw, p->cin_real,
-      p->cout_real, bps, WG_PIX * 128, WG_PIX * 128, g_dev_error_flag);
+  cudaError_t le = launch_cluster(wgrad_tc_kernel<BN>, grid, dim3(WG_THREADS), WgradCfg<BN>::SMEM, s, dim3(1, 1, cl), g,
+                                  make_fastdiv((uint32_t)g.Wo), make_fastdiv((uint32_t)g.Ho), (const bf16*)p->dy, p->ldy, p->Cout,
+                                  p->dw, p->cin_real, p->cout_real, bps, WG_PIX * 128, WG_PIX * 128, cl, g_dev_error_flag);
+  if (le != cudaSuccess) return set_error(D3FK_ERR_CUDA, "wgrad_tc launch: %s", cudaGetErrorString(le));
   count_launch();
   return check_launch("wgrad_tc");
 }
@@ -905,6 +1030,8 @@ int tc_init() {
   if (const char* v = getenv("D3FK_OCC")) g_occ_cap = atoi(v);
   if (const char* v = getenv("D3FK_TMA_A")) g_use_tma_a = atoi(v);
   if (const char* v = getenv("D3FK_SPLIT_TILES")) g_split_tiles = atoi(v);
+  if (const char* v = getenv("D3FK_CLUSTER")) g_max_cluster = atoi(v);
+  if (const char* v = getenv("D3FK_WG_OCC")) g_wg_ctas_per_sm = atoi(v);
 #define SET_SMEM(k, bytes)                                                                          \
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   SET_SMEM((conv_tc_kernel<16, 0>), ConvCfg<16>::SMEM)
