@@ -636,6 +636,7 @@ static int g_a_ca = 0;        // D3FK_A_CA=1: L1-allocating activation gather
 static int g_occ_cap = 0;     // D3FK_OCC=n: cap CTAs per SM
 static int g_use_tma_a = 1;   // D3FK_TMA_A=0: force the gather producers (debug aid)
 static int g_split_tiles = 74;  // split K only when the output tiles fill at most this many SMs
+static int g_verbose = 0;      // D3FK_VERBOSE=1: print launch geometry
 static int g_max_cluster = 8;   // D3FK_CLUSTER=n: cap the split-K cluster size (1 disables split K)
 
 template <typename... KArgs, typename... Args>
@@ -657,6 +658,14 @@ static cudaError_t launch_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 bloc
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// Co-resident CTA capacity of a cluster launch, per CTAs-per-SM.  cudaOccupancyMaxActiveClusters reports one CTA per SM
+// for kernels that allocate tensor memory; tools/probes/cluster_residency.cu measured, on B200 at 2 CTAs/SM, 296 CTAs for
+// cluster sizes 1-2, 284 for 4 and 264 for 8 (GPC boundaries strand a few SMs) — the table below keeps a safety margin.
+static int cluster_capacity(int cl, int ctas_per_sm) {
+  const int per_sm = cl >= 8 ? 120 : cl >= 4 ? 138 : g_num_sms;   // usable SMs (of 148) for this cluster size
+  return per_sm * ctas_per_sm;
+}
+
 template <int BN, int PATH>
 static int launch_conv_tc_bn(const Gather& g, const d3fk_conv_params* p, cudaStream_t s, const TileSched& box) {
   EpiTC e{(bf16*)p->out, p->out_nchw, p->scale, p->shift, (const bf16*)p->res, p->stats, p->ldo, p->ldr, p->relu, p->Cout, p->Ho, p->Wo};
@@ -671,6 +680,7 @@ static int launch_conv_tc_bn(const Gather& g, const d3fk_conv_params* p, cudaStr
   if (BN == 128 && !p->out_nchw && p->Cout % BN == 0 && tiles <= g_split_tiles && ts.nkb >= 8 && g_max_cluster > 1) {
     int ks = 1;
     while (ks * 2 <= g_max_cluster && ks * 2 <= 8 && tiles * ks * 2 <= 2 * g_num_sms && ts.nkb / (ks * 2) >= 4) ks *= 2;
+    while (ks > 1 && tiles * ks > cluster_capacity(ks, 2)) ks >>= 1;
     ts.KS = ks;
   }
   ts.kb_per_split = cdiv(ts.nkb, ts.KS);
@@ -702,6 +712,7 @@ static int launch_conv_tc_bn(const Gather& g, const d3fk_conv_params* p, cudaStr
     int rc = get_tensor_map(&tmA, p->src0, 4, dims, strides, bx, 128);
     if (rc) return rc;
   }
+  if (g_verbose) fprintf(stderr, "[d3fk] conv<%d,%d> mode=%d M=%d K=%d Cout=%d tiles=%d KS=%d kbps=%d grid=%d\n", BN, PATH, g.mode, g.M, g.K, p->Cout, tiles, ts.KS, ts.kb_per_split, grid);
   if (ts.KS > 1) {
     cudaError_t le = launch_cluster(conv_tc_kernel<BN, PATH>, dim3(grid), dim3(TC_THREADS), ConvCfg<BN>::SMEM, s, dim3(ts.KS, 1, 1), g,
                                     make_fastdiv((uint32_t)g.Wo), make_fastdiv((uint32_t)g.Ho), tmA, tmB, e, ts, g_dev_error_flag);
@@ -987,24 +998,47 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(Gather g, FastDiv 
 }
 
 static int g_wg_ctas_per_sm = 2;
+static int g_wg_cap = 0;     // D3FK_WG_CAP=n: override the co-resident CTA capacity used to size the pixel splits
+static int g_wg_plain = 1;   // D3FK_WG_PLAIN=0: launch cluster-size-1 grids through cudaLaunchKernelEx too
 
 template <int BN>
 static int launch_wgrad_tc_bn(const Gather& g, const d3fk_wgrad_params* p, cudaStream_t s) {
   const int gx = cdiv(g.K, 128), gy = cdiv(p->Cout, BN);
   const int nblk = cdiv(g.M, WG_PIX);
   const int tiles = gx * gy;
-  int splits = (g_num_sms * g_wg_ctas_per_sm) / tiles;
-  if (splits > nblk) splits = nblk;
-  if (splits < 1) splits = 1;
-  int cl = 1;
-  while (cl * 2 <= splits && cl * 2 <= g_max_cluster && cl * 2 <= 8) cl *= 2;
-  splits = (splits / cl) * cl;
+  // Pixel splits and cluster size: one wave of co-resident CTAs.  Cost model (us): pipeline stages per CTA, plus the atomic
+  // passes over the K x Cout outputs when a tile's splits span several clusters, plus the cluster reduction itself.
+  const double elems = (double)g.K * p->cout_real;
+  const int max_cl = g_max_cluster < 8 ? (g_max_cluster < 1 ? 1 : g_max_cluster) : 8;
+  int cl = 1, splits = 1;
+  double best = 1e30;
+  for (int c = 1; c <= max_cl; c *= 2) {
+    int cap = g_wg_cap > 0 ? g_wg_cap : cluster_capacity(c, g_wg_ctas_per_sm);
+    int smax = cap / tiles;
+    if (smax > nblk) smax = nblk;
+    smax = (smax / c) * c;
+    if (smax < c) continue;
+    const int cand[2] = {smax, c};
+    for (int i = 0; i < 2; ++i) {
+      const int sp = cand[i];
+      const double est = (double)cdiv(nblk, sp) * 0.4 + (sp > c ? (sp / c) * elems / 216e3 : 0.0) + (c > 1 ? 1.0 : 0.0);
+      if (est < best) { best = est; cl = c; splits = sp; }
+    }
+  }
+  const int want = splits, cap = 0;
   const int bps = cdiv(nblk, splits);
   dim3 grid(gx, gy, splits);
-  cudaError_t le = launch_cluster(wgrad_tc_kernel<BN>, grid, dim3(WG_THREADS), WgradCfg<BN>::SMEM, s, dim3(1, 1, cl), g,
-                                  make_fastdiv((uint32_t)g.Wo), make_fastdiv((uint32_t)g.Ho), (const bf16*)p->dy, p->ldy, p->Cout,
-                                  p->dw, p->cin_real, p->cout_real, bps, WG_PIX * 128, WG_PIX * 128, cl, g_dev_error_flag);
-  if (le != cudaSuccess) return set_error(D3FK_ERR_CUDA, "wgrad_tc launch: %s", cudaGetErrorString(le));
+  if (g_verbose) fprintf(stderr, "[d3fk] wgrad<%d> M=%d K=%d Cout=%d tiles=%d want=%d cl=%d cap=%d splits=%d bps=%d\n", BN, g.M, g.K, p->Cout, tiles, want, cl, cap, splits, bps);
+  if (cl == 1 && g_wg_plain) {
+    wgrad_tc_kernel<BN><<<grid, WG_THREADS, WgradCfg<BN>::SMEM, s>>>(g, make_fastdiv((uint32_t)g.Wo), make_fastdiv((uint32_t)g.Ho),
+                                                                  (const bf16*)p->dy, p->ldy, p->Cout, p->dw, p->cin_real, p->cout_real,
+                                                                  bps, WG_PIX * 128, WG_PIX * 128, cl, g_dev_error_flag);
+  } else {
+    cudaError_t le = launch_cluster(wgrad_tc_kernel<BN>, grid, dim3(WG_THREADS), WgradCfg<BN>::SMEM, s, dim3(1, 1, cl), g,
+                                    make_fastdiv((uint32_t)g.Wo), make_fastdiv((uint32_t)g.Ho), (const bf16*)p->dy, p->ldy, p->Cout,
+                                    p->dw, p->cin_real, p->cout_real, bps, WG_PIX * 128, WG_PIX * 128, cl, g_dev_error_flag);
+    if (le != cudaSuccess) return set_error(D3FK_ERR_CUDA, "wgrad_tc launch: %s", cudaGetErrorString(le));
+  }
   count_launch();
   return check_launch("wgrad_tc");
 }
@@ -1031,9 +1065,13 @@ int tc_init() {
   if (const char* v = getenv("D3FK_TMA_A")) g_use_tma_a = atoi(v);
   if (const char* v = getenv("D3FK_SPLIT_TILES")) g_split_tiles = atoi(v);
   if (const char* v = getenv("D3FK_CLUSTER")) g_max_cluster = atoi(v);
+  if (const char* v = getenv("D3FK_VERBOSE")) g_verbose = atoi(v);
   if (const char* v = getenv("D3FK_WG_OCC")) g_wg_ctas_per_sm = atoi(v);
+  if (const char* v = getenv("D3FK_WG_CAP")) g_wg_cap = atoi(v);
+  if (const char* v = getenv("D3FK_WG_PLAIN")) g_wg_plain = atoi(v);
 #define SET_SMEM(k, bytes)                                                                          \
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);               \
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   SET_SMEM((conv_tc_kernel<16, 0>), ConvCfg<16>::SMEM)
   SET_SMEM((conv_tc_kernel<32, 0>), ConvCfg<32>::SMEM)
   SET_SMEM((conv_tc_kernel<64, 0>), ConvCfg<64>::SMEM)

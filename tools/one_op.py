@@ -1,0 +1,36 @@
+"""Run ONE op of the training plan a few times (for ncu captures): python tools/one_op.py wgrad 4096 256 2304"""
+import os, sys, ctypes
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from denoising_diffusion_deep_fake_b200 import _lib
+from denoising_diffusion_deep_fake_b200.train import DenoiserModule
+kind_name, M, N, K = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
+mode = int(sys.argv[5]) if len(sys.argv) > 5 else 0
+dev = torch.device("cuda:0")
+mod = DenoiserModule(encoder_name="resnet34", learning_rate=0.02, noise_exponential_sampling_lambda=5,
+                     cosine_scheduler_max_epoch=100, precision="bf16").to(dev).train()
+mod.configure_optimizers(fused=True)
+x = torch.randn(256, 3, 64, 64, device=dev).clamp(-1, 1)
+mod.training_step(x)
+torch.cuda.synchronize()
+plan = next(p for plans in mod.model._plans.values() for p in plans if p.training)
+s = torch.cuda.current_stream().cuda_stream
+kind = _lib.OP_WGRAD if kind_name == "wgrad" else _lib.OP_CONV
+ops = list(plan.fwd_ops) + [op for seg in plan.bwd_segments for op in seg]
+for op in ops:
+    if op.kind != kind:
+        continue
+    p = _lib.op_params(op)
+    if (p.B * p.Ho * p.Wo, p.Cout, p.kh * p.kw * (p.c0 + p.c1)) != (M, N, K):
+        continue
+    if kind == _lib.OP_CONV and p.mode != mode:
+        continue
+    c = _lib.Op(); ctypes.memmove(ctypes.byref(c), ctypes.byref(op), ctypes.sizeof(_lib.Op))
+    ol = _lib.OpList([c] * 1)
+    for _ in range(5):
+        ol.run(s)
+    torch.cuda.synchronize()
+    print("ran", kind_name, M, N, K)
+    break
+else:
+    print("op not found")

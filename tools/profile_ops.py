@@ -21,9 +21,35 @@ def describe(op):
         return f"count={p.count} C={p.C}", 0.0
     return "", 0.0
 
+def repeat_ms(oplist, stream, reps):
+    """Steady-state time of every op: `reps` back-to-back launches of the same op between two events
+    (warm L2, launch latency pipelined) — the per-op event profile has a ~8 us floor per op."""
+    import ctypes
+    out = []
+    for op in oplist:
+        copies = []
+        for _ in range(reps):
+            c = _lib.Op()
+            ctypes.memmove(ctypes.byref(c), ctypes.byref(op), ctypes.sizeof(_lib.Op))
+            copies.append(c)
+        ol = _lib.OpList(copies)
+        ol.run(stream)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ol.run(stream)
+        e1.record()
+        torch.cuda.synchronize()
+        out.append(e0.elapsed_time(e1) / reps)
+    return out
+
+
 def report(name, oplist, stream, top=25):
-    oplist.profile(stream)
-    ms = oplist.profile(stream)
+    if REPEAT:
+        ms = repeat_ms(oplist, stream, REPEAT)
+    else:
+        oplist.profile(stream)
+        ms = oplist.profile(stream)
     rows = []
     by_kind = collections.defaultdict(float)
     for op, t in zip(oplist, ms):
@@ -44,7 +70,9 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=256)
 ap.add_argument("--size", type=int, default=64)
 ap.add_argument("--top", type=int, default=25)
+ap.add_argument("--repeat", type=int, default=0, help="time each op as N back-to-back launches (steady state)")
 a = ap.parse_args()
+REPEAT = a.repeat
 dev = torch.device("cuda:0")
 mod = DenoiserModule(encoder_name="resnet34", learning_rate=0.02, noise_exponential_sampling_lambda=5,
                      cosine_scheduler_max_epoch=100, precision="bf16").to(dev).train()
