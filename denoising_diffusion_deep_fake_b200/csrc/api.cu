@@ -1,6 +1,7 @@
 // api.cu — the extern "C" surface of libd3fk (declared in include/d3fk.h) and the op-list runner.
 #include <stdarg.h>
 #include <string.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace d3fk {
@@ -8,6 +9,7 @@ namespace d3fk {
 int64_t g_launch_count = 0;
 char g_last_error[512] = "";
 int* g_dev_error_flag = nullptr;
+int g_use_pdl = 1;
 static int g_inited_device = -1;
 
 int set_error(int code, const char* fmt, ...) {
@@ -127,6 +129,7 @@ int d3fk_init(int device) {
     if (e != cudaSuccess) return set_error(D3FK_ERR_CUDA, "cudaMalloc: %s", cudaGetErrorString(e));
     cudaMemset(g_dev_error_flag, 0, sizeof(int));
   }
+  if (const char* v = getenv("D3FK_PDL")) g_use_pdl = atoi(v);
   int rc = tc_init();
   if (rc) return rc;
   rc = loss_init();

@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 #include "../../include/d3fk.h"
 
 namespace d3fk {
@@ -23,6 +24,46 @@ inline void count_launch(int n = 1) { g_launch_count += n; }
   } while (0)
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---- kernel launch: every libd3fk kernel goes through launch_k --------------------------------
+// Programmatic dependent launch (PDL): the kernel may begin launching while its predecessor in the stream is still
+// draining; every kernel therefore starts with pdl_enter() (griddepcontrol.wait = the predecessor has completed and its
+// memory is visible; then griddepcontrol.launch_dependents = the successor may start its own launch / prologue).
+// D3FK_PDL=0 turns the attribute off (the device-side instructions are then no-ops).
+extern int g_use_pdl;
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, dim3 cluster,
+                                   Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (cluster.x * cluster.y * cluster.z > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = cluster.x;
+    attr[na].val.clusterDim.y = cluster.y;
+    attr[na].val.clusterDim.z = cluster.z;
+    ++na;
+  }
+  if (g_use_pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_enter() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+#endif
 
 // ---- dtype traits ----------------------------------------------------------------------------
 template <typename T> struct Vec;  // 16-byte vector of T

@@ -35,6 +35,7 @@ struct Epi {
 constexpr int FBM = 64, FBN = 64, FBK = 16;
 
 __global__ void __launch_bounds__(256) conv_ffma_kernel(Gather g, const float* __restrict__ w, Epi e) {
+  pdl_enter();
   __shared__ float As[FBK][FBM + 4];
   __shared__ float Bs[FBK][FBN + 4];
   __shared__ double sstat[2][FBN];
@@ -158,7 +159,7 @@ int launch_conv_ffma(const d3fk_conv_params* p, cudaStream_t s) {
   D3FK_CHECK_ARG(p->out || p->out_nchw, "no output");
   Epi e{p->out, p->out_nchw, p->scale, p->shift, p->res, p->stats, p->ldo, p->ldr, p->relu, p->Cout, p->Ho, p->Wo};
   dim3 grid(cdiv(g.M, FBM), cdiv(p->Cout, FBN));
-  conv_ffma_kernel<<<grid, 256, 0, s>>>(g, (const float*)p->w, e);
+  launch_k(conv_ffma_kernel, dim3(grid), dim3(256), 0, s, dim3(1, 1, 1), g, (const float*)p->w, e);
   count_launch();
   return check_launch("conv_ffma");
 }
@@ -167,6 +168,7 @@ int launch_conv_ffma(const d3fk_conv_params* p, cudaStream_t s) {
 // wgrad: dw[co][ci][kh][kw] += sum_m dy[m][co] * A[m][k]; tile 64 (co) x 64 (k), split over m
 __global__ void __launch_bounds__(256) wgrad_ffma_kernel(Gather g, const float* __restrict__ dy, int ldy, int Cout,
                                                          float* __restrict__ dw, int cin_real, int cout_real, int m_per_split) {
+  pdl_enter();
   __shared__ float Ys[FBK][FBM + 4];  // [m][co]
   __shared__ float As[FBK][FBN + 4];  // [m][k]
   const int tid = threadIdx.x;
@@ -260,7 +262,7 @@ int launch_wgrad_ffma(const d3fk_wgrad_params* p, cudaStream_t s) {
   int m_per_split = cdiv(cdiv(g.M, splits), FBK) * FBK;
   splits = cdiv(g.M, m_per_split);
   dim3 grid(cdiv(p->Cout, 64), cdiv(g.K, 64), splits);
-  wgrad_ffma_kernel<<<grid, 256, 0, s>>>(g, (const float*)p->dy, p->ldy, p->Cout, p->dw, p->cin_real, p->cout_real, m_per_split);
+  launch_k(wgrad_ffma_kernel, dim3(grid), dim3(256), 0, s, dim3(1, 1, 1), g, (const float*)p->dy, p->ldy, p->Cout, p->dw, p->cin_real, p->cout_real, m_per_split);
   count_launch();
   return check_launch("wgrad_ffma");
 }
@@ -269,6 +271,7 @@ int launch_wgrad_ffma(const d3fk_wgrad_params* p, cudaStream_t s) {
 // weight packing: OIHW fp32 -> [Cout][kh][kw][cin_pad] and/or [Cin][kh][kw][cout_pad]
 template <typename T>
 __global__ void pack_weights_kernel(d3fk_pack_params p) {
+  pdl_enter();
   const int taps = p.kh * p.kw;
   if (p.w_fwd) {
     long long total = (long long)p.Cout * taps * p.cin_pad;
@@ -302,8 +305,8 @@ int launch_pack(const d3fk_pack_params* p, cudaStream_t s) {
   }
   int grid = (int)((total + 255) / 256);
   if (grid > 148 * 8) grid = 148 * 8;
-  if (p->dtype == D3FK_F32) pack_weights_kernel<float><<<grid, 256, 0, s>>>(*p);
-  else if (p->dtype == D3FK_BF16) pack_weights_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(*p);
+  if (p->dtype == D3FK_F32) launch_k(pack_weights_kernel<float>, dim3(grid), dim3(256), 0, s, dim3(1, 1, 1), *p);
+  else if (p->dtype == D3FK_BF16) launch_k(pack_weights_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, s, dim3(1, 1, 1), *p);
   else return set_error(D3FK_ERR_ARG, "bad dtype");
   count_launch();
   return check_launch("pack_weights");

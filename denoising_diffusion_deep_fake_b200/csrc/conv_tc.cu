@@ -352,6 +352,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(Gather g, FastDiv d
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = *tmem_ptr_slot;
+  pdl_enter();   // prologue above overlaps the previous kernel; from here on its results are visible
 
   // flush this CTA's accumulated statistics of n tile `nt` (epilogue warps only)
   auto flush_stats = [&](int nt) {
@@ -639,25 +640,6 @@ static int g_split_tiles = 74;  // split K only when the output tiles fill at mo
 static int g_verbose = 0;      // D3FK_VERBOSE=1: print launch geometry
 static int g_max_cluster = 8;   // D3FK_CLUSTER=n: cap the split-K cluster size (1 disables split K)
 
-template <typename... KArgs, typename... Args>
-static cudaError_t launch_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, dim3 cluster,
-                                  Args&&... args) {
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = grid;
-  cfg.blockDim = block;
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = cluster.x;
-  attr[0].val.clusterDim.y = cluster.y;
-  attr[0].val.clusterDim.z = cluster.z;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
-}
-
 // Co-resident CTA capacity of a cluster launch, per CTAs-per-SM.  cudaOccupancyMaxActiveClusters reports one CTA per SM
 // for kernels that allocate tensor memory; tools/probes/cluster_residency.cu measured, on B200 at 2 CTAs/SM, 296 CTAs for
 // cluster sizes 1-2, 284 for 4 and 264 for 8 (GPC boundaries strand a few SMs) — the table below keeps a safety margin.
@@ -714,11 +696,11 @@ static int launch_conv_tc_bn(const Gather& g, const d3fk_conv_params* p, cudaStr
   }
   if (g_verbose) fprintf(stderr, "[d3fk] conv<%d,%d> mode=%d M=%d K=%d Cout=%d tiles=%d KS=%d kbps=%d grid=%d\n", BN, PATH, g.mode, g.M, g.K, p->Cout, tiles, ts.KS, ts.kb_per_split, grid);
   if (ts.KS > 1) {
-    cudaError_t le = launch_cluster(conv_tc_kernel<BN, PATH>, dim3(grid), dim3(TC_THREADS), ConvCfg<BN>::SMEM, s, dim3(ts.KS, 1, 1), g,
+    cudaError_t le = launch_k(conv_tc_kernel<BN, PATH>, dim3(grid), dim3(TC_THREADS), ConvCfg<BN>::SMEM, s, dim3(ts.KS, 1, 1), g,
                                     make_fastdiv((uint32_t)g.Wo), make_fastdiv((uint32_t)g.Ho), tmA, tmB, e, ts, g_dev_error_flag);
     if (le != cudaSuccess) return set_error(D3FK_ERR_CUDA, "conv_tc cluster launch: %s", cudaGetErrorString(le));
   } else {
-    conv_tc_kernel<BN, PATH><<<grid, TC_THREADS, ConvCfg<BN>::SMEM, s>>>(g, make_fastdiv((uint32_t)g.Wo), make_fastdiv((uint32_t)g.Ho),
+    launch_k(conv_tc_kernel<BN, PATH>, dim3(grid), dim3(TC_THREADS), ConvCfg<BN>::SMEM, s, dim3(1, 1, 1), g, make_fastdiv((uint32_t)g.Wo), make_fastdiv((uint32_t)g.Ho),
                                                                       tmA, tmB, e, ts, g_dev_error_flag);
   }
   count_launch();
@@ -830,6 +812,7 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(Gather g, FastDiv 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = *tmem_ptr_slot;
+  pdl_enter();   // prologue above overlaps the previous kernel; from here on its results are visible
 
   // output row of this thread (epilogue): k index -> (tap, ci)
   const int krow = k0 + (warp & 3) * 32 + lane;
@@ -1030,11 +1013,11 @@ static int launch_wgrad_tc_bn(const Gather& g, const d3fk_wgrad_params* p, cudaS
   dim3 grid(gx, gy, splits);
   if (g_verbose) fprintf(stderr, "[d3fk] wgrad<%d> M=%d K=%d Cout=%d tiles=%d want=%d cl=%d cap=%d splits=%d bps=%d\n", BN, g.M, g.K, p->Cout, tiles, want, cl, cap, splits, bps);
   if (cl == 1 && g_wg_plain) {
-    wgrad_tc_kernel<BN><<<grid, WG_THREADS, WgradCfg<BN>::SMEM, s>>>(g, make_fastdiv((uint32_t)g.Wo), make_fastdiv((uint32_t)g.Ho),
+    launch_k(wgrad_tc_kernel<BN>, dim3(grid), dim3(WG_THREADS), WgradCfg<BN>::SMEM, s, dim3(1, 1, 1), g, make_fastdiv((uint32_t)g.Wo), make_fastdiv((uint32_t)g.Ho),
                                                                   (const bf16*)p->dy, p->ldy, p->Cout, p->dw, p->cin_real, p->cout_real,
                                                                   bps, WG_PIX * 128, WG_PIX * 128, cl, g_dev_error_flag);
   } else {
-    cudaError_t le = launch_cluster(wgrad_tc_kernel<BN>, grid, dim3(WG_THREADS), WgradCfg<BN>::SMEM, s, dim3(1, 1, cl), g,
+    cudaError_t le = launch_k(wgrad_tc_kernel<BN>, grid, dim3(WG_THREADS), WgradCfg<BN>::SMEM, s, dim3(1, 1, cl), g,
                                     make_fastdiv((uint32_t)g.Wo), make_fastdiv((uint32_t)g.Ho), (const bf16*)p->dy, p->ldy, p->Cout,
                                     p->dw, p->cin_real, p->cout_real, bps, WG_PIX * 128, WG_PIX * 128, cl, g_dev_error_flag);
     if (le != cudaSuccess) return set_error(D3FK_ERR_CUDA, "wgrad_tc launch: %s", cudaGetErrorString(le));

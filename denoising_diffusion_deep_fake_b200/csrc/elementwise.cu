@@ -20,6 +20,7 @@ static inline int grid_for(long long work_items, int threads, int max_waves = 8)
 // NCHW fp32 -> NHWC T, channels zero-padded to cpad (a multiple of 8)
 template <typename T>
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, T* __restrict__ dst, int B, int C, int HW, int cpad) {
+  pdl_enter();
   long long total = (long long)B * HW;
   for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < total; p += (long long)gridDim.x * blockDim.x) {
     long long n = p / HW;
@@ -39,6 +40,7 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, T* __restrict
 // ---------------------------------------------------------------------------------------------
 // BN statistics -> scale/shift, saved mean/invstd, running-stat update (momentum, unbiased var)
 __global__ void bn_finalize_kernel(d3fk_bn_params p) {
+  pdl_enter();
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= p.C) return;
   double n = (double)p.count;
@@ -62,6 +64,7 @@ __global__ void bn_finalize_kernel(d3fk_bn_params p) {
 
 // eval mode: scale/shift from running statistics (folded into the conv epilogue)
 __global__ void bn_fold_kernel(d3fk_bn_params p) {
+  pdl_enter();
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= p.C) return;
   float invstd = 1.0f / sqrtf(p.running_var[c] + p.eps);
@@ -75,6 +78,7 @@ __global__ void bn_fold_kernel(d3fk_bn_params p) {
 // threads of block 0 publish mean / invstd / running statistics — no separate finalize launch.
 template <typename T>
 __global__ void bn_apply_kernel(d3fk_bn_params p) {
+  pdl_enter();
   constexpr int V = Vec<T>::N;
   const int cvs = p.C / V;
   const long long total = p.count * cvs;
@@ -138,6 +142,7 @@ __global__ void bn_apply_kernel(d3fk_bn_params p) {
 // slot each, the block with one double atomic per channel.
 template <typename T, typename Acc>
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(d3fk_bn_params p) {
+  pdl_enter();
   constexpr int V = Vec<T>::N;
   extern __shared__ double sred[];  // [warps][2][C]
   const int C = p.C, cvs = C / V;
@@ -211,6 +216,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(d3fk_bn_params p) {
 }
 
 __global__ void bn_bwd_finalize_kernel(d3fk_bn_params p) {
+  pdl_enter();
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= p.C) return;
   double n = (double)p.count;
@@ -227,6 +233,7 @@ __global__ void bn_bwd_finalize_kernel(d3fk_bn_params p) {
 // dgamma / dbeta (no separate finalize launch).
 template <typename T>
 __global__ void bn_bwd_apply_kernel(d3fk_bn_params p) {
+  pdl_enter();
   constexpr int V = Vec<T>::N;
   const int cvs = p.C / V;
   const long long total = p.count * cvs;
@@ -283,6 +290,7 @@ __global__ void bn_bwd_apply_kernel(d3fk_bn_params p) {
 // MaxPool2d(kernel 3, stride 2, pad 1): first-max tie-break in window scan order (ATen semantics)
 template <typename T>
 __global__ void maxpool_fwd_kernel(d3fk_pool_params p) {
+  pdl_enter();
   constexpr int V = Vec<T>::N;
   const int Ho = p.H / 2, Wo = p.W / 2, cvs = p.C / V;
   const long long total = (long long)p.B * Ho * Wo * cvs;
@@ -326,6 +334,7 @@ __global__ void maxpool_fwd_kernel(d3fk_pool_params p) {
 
 template <typename T>
 __global__ void maxpool_bwd_kernel(d3fk_pool_params p) {
+  pdl_enter();
   constexpr int V = Vec<T>::N;
   const int Ho = p.H / 2, Wo = p.W / 2, cvs = p.C / V;
   const long long total = (long long)p.B * p.H * p.W * cvs;
@@ -365,6 +374,7 @@ __global__ void maxpool_bwd_kernel(d3fk_pool_params p) {
 // backward of nearest 2x upsample: dx[n,h,w,c] = sum of the 2x2 block of dy (H,W = low-res extent)
 template <typename T>
 __global__ void sumpool2_kernel(d3fk_pool_params p) {
+  pdl_enter();
   constexpr int V = Vec<T>::N;
   const int cvs = p.C / V;
   const long long total = (long long)p.B * p.H * p.W * cvs;
@@ -397,6 +407,7 @@ __global__ void sumpool2_kernel(d3fk_pool_params p) {
 // out[c] += sum over pixels x[pix*ld + c], c < C <= 8
 template <typename T>
 __global__ void chansum_kernel(d3fk_chansum_params p) {
+  pdl_enter();
   constexpr int V = Vec<T>::N;
   float acc[8];
 #pragma unroll
@@ -423,6 +434,7 @@ __global__ void chansum_kernel(d3fk_chansum_params p) {
 // ---------------------------------------------------------------------------------------------
 // q_sample: out = sqrt(1-r_b) x + sqrt(r_b) eps   (d3f/train_denoiser/lit_module.py:128-153)
 __global__ void qsample_kernel(d3fk_qsample_params p) {
+  pdl_enter();
   const long long nvec = (long long)p.B * p.chw / 4;
   const int vec_per_sample = p.chw / 4;
   const float cexp = __expf(-p.lam);
@@ -455,6 +467,7 @@ __global__ void qsample_kernel(d3fk_qsample_params p) {
 
 // posterior: x = k_xi*x + k_x0*x0_hat + sigma*z
 __global__ void posterior_kernel(d3fk_posterior_params p) {
+  pdl_enter();
   float k_xi = p.k_xi, k_x0 = p.k_x0, sigma = p.sigma;
   uint64_t off = p.offset;
   if (p.coef_table) {
@@ -479,11 +492,13 @@ __global__ void posterior_kernel(d3fk_posterior_params p) {
   }
 }
 
-__global__ void inc_kernel(int* p) { *p += 1; }
+__global__ void inc_kernel(int* p) {
+  pdl_enter(); *p += 1; }
 
 // one launch packs every convolution's weights: blockIdx.y selects the layer descriptor (device table)
 template <typename T>
 __global__ void pack_all_kernel(const d3fk_pack_params* __restrict__ tab) {
+  pdl_enter();
   const d3fk_pack_params p = tab[blockIdx.y];
   const int taps = p.kh * p.kw;
   if (p.w_fwd) {
@@ -512,6 +527,7 @@ __global__ void pack_all_kernel(const d3fk_pack_params* __restrict__ tab) {
 
 // fused Adam (+ optional EMA lerp) over a flat arena
 __global__ void adam_kernel(d3fk_adam_params p) {
+  pdl_enter();
   const float step = p.lr / p.bias1;
   const float rsb2 = rsqrtf(p.bias2);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < p.n; i += (long long)gridDim.x * blockDim.x) {
@@ -536,17 +552,17 @@ __global__ void adam_kernel(d3fk_adam_params p) {
 int launch_nchw_to_nhwc(const d3fk_layout_params* p, cudaStream_t s) {
   D3FK_CHECK_ARG(p->cpad % 8 == 0 && p->C <= p->cpad, "cpad must be a multiple of 8 and >= C");
   long long total = (long long)p->B * p->H * p->W;
-  DISPATCH_T(p->dtype, nchw_to_nhwc_kernel<T><<<grid_for(total, 256), 256, 0, s>>>(p->src, (T*)p->dst, p->B, p->C, p->H * p->W, p->cpad));
+  DISPATCH_T(p->dtype, launch_k(nchw_to_nhwc_kernel<T>, dim3(grid_for(total, 256)), dim3(256), 0, s, dim3(1, 1, 1), p->src, (T*)p->dst, p->B, p->C, p->H * p->W, p->cpad));
   count_launch();
   return check_launch("nchw_to_nhwc");
 }
 int launch_bn_finalize(const d3fk_bn_params* p, cudaStream_t s) {
-  bn_finalize_kernel<<<cdiv(p->C, 128), 128, 0, s>>>(*p);
+  launch_k(bn_finalize_kernel, dim3(cdiv(p->C, 128)), dim3(128), 0, s, dim3(1, 1, 1), *p);
   count_launch();
   return check_launch("bn_finalize");
 }
 int launch_bn_fold(const d3fk_bn_params* p, cudaStream_t s) {
-  bn_fold_kernel<<<cdiv(p->C, 128), 128, 0, s>>>(*p);
+  launch_k(bn_fold_kernel, dim3(cdiv(p->C, 128)), dim3(128), 0, s, dim3(1, 1, 1), *p);
   count_launch();
   return check_launch("bn_fold");
 }
@@ -554,7 +570,7 @@ int launch_bn_apply(const d3fk_bn_params* p, cudaStream_t s) {
   D3FK_CHECK_ARG(p->C % 8 == 0, "C must be a multiple of 8");
   int V = p->dtype == D3FK_F32 ? 4 : 8;
   long long total = p->count * (p->C / V);
-  DISPATCH_T(p->dtype, bn_apply_kernel<T><<<grid_for(total, 256 * 4, 4), 256, 2 * p->C * sizeof(float), s>>>(*p));
+  DISPATCH_T(p->dtype, launch_k(bn_apply_kernel<T>, dim3(grid_for(total, 256 * 4, 4)), dim3(256), 2 * p->C * sizeof(float), s, dim3(1, 1, 1), *p));
   count_launch();
   return check_launch("bn_apply");
 }
@@ -570,14 +586,14 @@ int launch_bn_bwd_reduce(const d3fk_bn_params* p, cudaStream_t s) {
   if (grid < 1) grid = 1;
   const int slotC = cvs < 32 ? p->C : 32 * V;
   size_t smem = (size_t)(threads / 32) * 2 * slotC * sizeof(double);
-  if (p->dtype == D3FK_F32) bn_bwd_reduce_kernel<float, double><<<grid, threads, smem, s>>>(*p);
-  else if (p->dtype == D3FK_BF16) bn_bwd_reduce_kernel<__nv_bfloat16, float><<<grid, threads, smem, s>>>(*p);
+  if (p->dtype == D3FK_F32) launch_k(bn_bwd_reduce_kernel<float, double>, dim3(grid), dim3(threads), smem, s, dim3(1, 1, 1), *p);
+  else if (p->dtype == D3FK_BF16) launch_k(bn_bwd_reduce_kernel<__nv_bfloat16, float>, dim3(grid), dim3(threads), smem, s, dim3(1, 1, 1), *p);
   else return set_error(D3FK_ERR_ARG, "bad dtype");
   count_launch();
   return check_launch("bn_bwd_reduce");
 }
 int launch_bn_bwd_finalize(const d3fk_bn_params* p, cudaStream_t s) {
-  bn_bwd_finalize_kernel<<<cdiv(p->C, 128), 128, 0, s>>>(*p);
+  launch_k(bn_bwd_finalize_kernel, dim3(cdiv(p->C, 128)), dim3(128), 0, s, dim3(1, 1, 1), *p);
   count_launch();
   return check_launch("bn_bwd_finalize");
 }
@@ -585,7 +601,7 @@ int launch_bn_bwd_apply(const d3fk_bn_params* p, cudaStream_t s) {
   D3FK_CHECK_ARG(p->C % 8 == 0, "C must be a multiple of 8");
   int V = p->dtype == D3FK_F32 ? 4 : 8;
   long long total = p->count * (p->C / V);
-  DISPATCH_T(p->dtype, bn_bwd_apply_kernel<T><<<grid_for(total, 256 * 4, 4), 256, 5 * p->C * sizeof(float), s>>>(*p));
+  DISPATCH_T(p->dtype, launch_k(bn_bwd_apply_kernel<T>, dim3(grid_for(total, 256 * 4, 4)), dim3(256), 5 * p->C * sizeof(float), s, dim3(1, 1, 1), *p));
   count_launch();
   return check_launch("bn_bwd_apply");
 }
@@ -593,7 +609,7 @@ int launch_maxpool_fwd(const d3fk_pool_params* p, cudaStream_t s) {
   D3FK_CHECK_ARG(p->C % 8 == 0 && p->H % 2 == 0 && p->W % 2 == 0, "C%8, H%2, W%2");
   int V = p->dtype == D3FK_F32 ? 4 : 8;
   long long total = (long long)p->B * (p->H / 2) * (p->W / 2) * (p->C / V);
-  DISPATCH_T(p->dtype, maxpool_fwd_kernel<T><<<grid_for(total, 256), 256, 0, s>>>(*p));
+  DISPATCH_T(p->dtype, launch_k(maxpool_fwd_kernel<T>, dim3(grid_for(total, 256)), dim3(256), 0, s, dim3(1, 1, 1), *p));
   count_launch();
   return check_launch("maxpool_fwd");
 }
@@ -601,7 +617,7 @@ int launch_maxpool_bwd(const d3fk_pool_params* p, cudaStream_t s) {
   D3FK_CHECK_ARG(p->C % 8 == 0 && p->idx, "C%8 and idx required");
   int V = p->dtype == D3FK_F32 ? 4 : 8;
   long long total = (long long)p->B * p->H * p->W * (p->C / V);
-  DISPATCH_T(p->dtype, maxpool_bwd_kernel<T><<<grid_for(total, 256), 256, 0, s>>>(*p));
+  DISPATCH_T(p->dtype, launch_k(maxpool_bwd_kernel<T>, dim3(grid_for(total, 256)), dim3(256), 0, s, dim3(1, 1, 1), *p));
   count_launch();
   return check_launch("maxpool_bwd");
 }
@@ -609,31 +625,31 @@ int launch_sumpool2(const d3fk_pool_params* p, cudaStream_t s) {
   D3FK_CHECK_ARG(p->C % 8 == 0, "C%8");
   int V = p->dtype == D3FK_F32 ? 4 : 8;
   long long total = (long long)p->B * p->H * p->W * (p->C / V);
-  DISPATCH_T(p->dtype, sumpool2_kernel<T><<<grid_for(total, 256), 256, 0, s>>>(*p));
+  DISPATCH_T(p->dtype, launch_k(sumpool2_kernel<T>, dim3(grid_for(total, 256)), dim3(256), 0, s, dim3(1, 1, 1), *p));
   count_launch();
   return check_launch("sumpool2");
 }
 int launch_chansum(const d3fk_chansum_params* p, cudaStream_t s) {
   D3FK_CHECK_ARG(p->C <= 8 && p->ld % 8 == 0, "C<=8, ld%8");
-  DISPATCH_T(p->dtype, chansum_kernel<T><<<grid_for(p->count, 256, 2), 256, 0, s>>>(*p));
+  DISPATCH_T(p->dtype, launch_k(chansum_kernel<T>, dim3(grid_for(p->count, 256, 2)), dim3(256), 0, s, dim3(1, 1, 1), *p));
   count_launch();
   return check_launch("chansum");
 }
 int launch_qsample(const d3fk_qsample_params* p, cudaStream_t s) {
   D3FK_CHECK_ARG(p->chw % 4 == 0, "C*H*W must be a multiple of 4");
   long long nvec = (long long)p->B * p->chw / 4;
-  qsample_kernel<<<grid_for(nvec, 256), 256, 0, s>>>(*p);
+  launch_k(qsample_kernel, dim3(grid_for(nvec, 256)), dim3(256), 0, s, dim3(1, 1, 1), *p);
   count_launch();
   return check_launch("q_sample");
 }
 int launch_posterior(const d3fk_posterior_params* p, cudaStream_t s) {
   D3FK_CHECK_ARG(p->n % 4 == 0, "n must be a multiple of 4");
-  posterior_kernel<<<grid_for(p->n / 4, 256), 256, 0, s>>>(*p);
+  launch_k(posterior_kernel, dim3(grid_for(p->n / 4, 256)), dim3(256), 0, s, dim3(1, 1, 1), *p);
   count_launch();
   return check_launch("posterior_step");
 }
 int launch_inc(const d3fk_misc_params* p, cudaStream_t s) {
-  inc_kernel<<<1, 1, 0, s>>>((int*)p->p0);
+  launch_k(inc_kernel, dim3(1), dim3(1), 0, s, dim3(1, 1, 1), (int*)p->p0);
   count_launch();
   return check_launch("inc");
 }
@@ -642,13 +658,13 @@ int launch_pack_all(const d3fk_misc_params* p, cudaStream_t s) {
   const int count = (int)(p->n >> 1);
   D3FK_CHECK_ARG(count > 0 && count < 65536, "bad pack table size");
   dim3 grid(96, count);
-  if (p->n & 1) pack_all_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const d3fk_pack_params*)p->p0);
-  else pack_all_kernel<float><<<grid, 256, 0, s>>>((const d3fk_pack_params*)p->p0);
+  if (p->n & 1) launch_k(pack_all_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, s, dim3(1, 1, 1), (const d3fk_pack_params*)p->p0);
+  else launch_k(pack_all_kernel<float>, dim3(grid), dim3(256), 0, s, dim3(1, 1, 1), (const d3fk_pack_params*)p->p0);
   count_launch();
   return check_launch("pack_all");
 }
 int launch_adam(const d3fk_adam_params* p, cudaStream_t s) {
-  adam_kernel<<<grid_for(p->n, 256), 256, 0, s>>>(*p);
+  launch_k(adam_kernel, dim3(grid_for(p->n, 256)), dim3(256), 0, s, dim3(1, 1, 1), *p);
   count_launch();
   return check_launch("adam");
 }

@@ -19,6 +19,7 @@ constexpr int LM = LT + LH;       // 42: windows (map pixels) touching the tile
 constexpr int LOSS_SMEM = (2 * LI * LI + 5 * LI * LM + 3 * LM * LM) * 4;
 
 __global__ void __launch_bounds__(256) mse_ssim_loss_kernel(d3fk_loss_params p) {
+  pdl_enter();
   extern __shared__ float sm[];
   float* xs = sm;                       // [LI][LI] normalised clipped prediction (0 outside the image)
   float* ys = xs + LI * LI;             // [LI][LI] target
@@ -162,7 +163,7 @@ int launch_loss(const d3fk_loss_params* p, cudaStream_t s) {
   D3FK_CHECK_ARG(p->hi > p->lo, "bad value range");
   long long blocks = (long long)p->B * p->C * (p->H / LT) * (p->W / LT);
   D3FK_CHECK_ARG(blocks < (1ll << 31), "too many tiles");
-  mse_ssim_loss_kernel<<<(int)blocks, 256, LOSS_SMEM, s>>>(*p);
+  launch_k(mse_ssim_loss_kernel, dim3((int)blocks), dim3(256), LOSS_SMEM, s, dim3(1, 1, 1), *p);
   count_launch();
   return check_launch("mse_ssim_loss");
 }
