@@ -145,18 +145,55 @@ int d3fk_device_error_flag(void) {
   return v;
 }
 
+// Weight gradients are off the backward critical path (dgrad_L -> BN-backward_{L-1} -> dgrad_{L-1} ...): d3fk_run forks
+// every OP_WGRAD onto a side stream behind an event recorded after its producer and joins the side stream at the end of
+// the op list, so the latency-bound deep-layer kernels of the two chains overlap.  Event record / wait are capture-safe.
+static cudaStream_t g_side_stream = nullptr;
+static cudaEvent_t g_fork_events[64];
+static cudaEvent_t g_join_event = nullptr;
+static int g_n_fork_events = 0;
+static int g_fork_wgrad = 1;   // D3FK_FORK_WGRAD=0: everything in stream order
+
+static int ensure_side_stream() {
+  if (g_side_stream) return D3FK_OK;
+  if (const char* v = getenv("D3FK_FORK_WGRAD")) g_fork_wgrad = atoi(v);
+  cudaError_t e = cudaStreamCreateWithFlags(&g_side_stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) return set_error(D3FK_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+  for (int i = 0; i < 64 && e == cudaSuccess; ++i) { e = cudaEventCreateWithFlags(&g_fork_events[i], cudaEventDisableTiming); g_n_fork_events = i + 1; }
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g_join_event, cudaEventDisableTiming);
+  if (e != cudaSuccess) return set_error(D3FK_ERR_CUDA, "cudaEventCreate: %s", cudaGetErrorString(e));
+  return D3FK_OK;
+}
+
 int d3fk_run(const d3fk_op* ops, int n_ops, d3fk_stream stream) {
   int rc = require_init();
   if (rc) return rc;
+  rc = ensure_side_stream();
+  if (rc) return rc;
   cudaStream_t s = (cudaStream_t)stream;
+  int forks = 0;
   for (int i = 0; i < n_ops; ++i) {
-    rc = run_one(&ops[i], s);
+    if (ops[i].kind == D3FK_OP_WGRAD && g_fork_wgrad && n_ops > 1) {
+      cudaEvent_t ev = g_fork_events[forks % g_n_fork_events];
+      cudaError_t e = cudaEventRecord(ev, s);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(g_side_stream, ev, 0);
+      if (e != cudaSuccess) return set_error(D3FK_ERR_CUDA, "fork: %s", cudaGetErrorString(e));
+      ++forks;
+      rc = run_one(&ops[i], g_side_stream);
+    } else {
+      rc = run_one(&ops[i], s);
+    }
     if (rc) {
       char tmp[400];
       strncpy(tmp, g_last_error, sizeof(tmp) - 1);
       tmp[sizeof(tmp) - 1] = 0;
       return set_error(rc, "op %d (kind %d): %s", i, ops[i].kind, tmp);
     }
+  }
+  if (forks) {
+    cudaError_t e = cudaEventRecord(g_join_event, g_side_stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(s, g_join_event, 0);
+    if (e != cudaSuccess) return set_error(D3FK_ERR_CUDA, "join: %s", cudaGetErrorString(e));
   }
   return D3FK_OK;
 }
