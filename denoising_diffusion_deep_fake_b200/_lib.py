@@ -31,7 +31,7 @@ class WgradParams(C.Structure):
 
 class PackParams(C.Structure):
     _fields_ = [("dtype", i32), ("Cout", i32), ("Cin", i32), ("kh", i32), ("kw", i32), ("cin_pad", i32),
-                ("cout_pad", i32), ("_pad0", i32), ("w", vp), ("w_fwd", vp), ("w_dgrad", vp)]
+                ("cout_pad", i32), ("blk0", i32), ("w", vp), ("w_fwd", vp), ("w_dgrad", vp)]
 
 
 class BnParams(C.Structure):

@@ -199,14 +199,18 @@ class UnetPlan:
     def _build_pack(self):
         ops = []
         packs = []
+        blocks = 0
         for c in self.convs:
             cin_pad = CIN_PAD if c.cin == 3 else c.cin
             cout_pad = CIN_PAD if c.cout == 3 else c.cout
             wd = self.w_dgrad.get(c.name)
+            assert c.k * c.k * min(c.cin, 32) <= 288, "pack_all tile: taps * min(Cin, 32) must be <= 288"
             packs.append(make_op(_lib.OP_PACK, dtype=self.dtype, Cout=c.cout, Cin=c.cin, kh=c.k, kw=c.k,
-                                 cin_pad=cin_pad, cout_pad=cout_pad, w=self.params[c.name + ".weight"].data_ptr(),
+                                 cin_pad=cin_pad, cout_pad=cout_pad, blk0=blocks,
+                                 w=self.params[c.name + ".weight"].data_ptr(),
                                  w_fwd=self.w_fwd[c.name].data_ptr(),
                                  w_dgrad=wd.data_ptr() if wd is not None else None))
+            blocks += -(-c.cout // 32) * -(-c.cin // 32)
         # one launch for all 47 layers: the descriptors live in a device table
         import ctypes
         table = (_lib.PackParams * len(packs))(*[op_params(o) for o in packs])
@@ -214,7 +218,7 @@ class UnetPlan:
         self.pack_table = raw.to(self.device)
         self.keep.append(self.pack_table)
         ops.append(make_op(_lib.OP_PACK_ALL, p0=self.pack_table.data_ptr(),
-                           n=(len(packs) << 1) | (1 if self.dtype == _lib.BF16 else 0)))
+                           n=(blocks << 17) | (len(packs) << 1) | (1 if self.dtype == _lib.BF16 else 0)))
         if not self.training:
             for c in self.convs:
                 if c.bn:

@@ -77,7 +77,7 @@ typedef struct d3fk_wgrad_params {
 /* ---- weight packing: fp32 OIHW master -> [Cout][kh][kw][cin_pad] (forward) and/or
  * [Cin][kh][kw][cout_pad] (dgrad) in dtype, zero padded. */
 typedef struct d3fk_pack_params {
-  int32_t dtype, Cout, Cin, kh, kw, cin_pad, cout_pad, _pad0;
+  int32_t dtype, Cout, Cin, kh, kw, cin_pad, cout_pad, blk0;   /* blk0: PACK_ALL only — first 32x32 block of this layer */
   const float* w; void* w_fwd; void* w_dgrad;
 } d3fk_pack_params;
 
@@ -179,7 +179,7 @@ enum d3fk_op_kind {
   D3FK_OP_MAXPOOL_FWD = 11, D3FK_OP_MAXPOOL_BWD = 12, D3FK_OP_SUMPOOL2 = 13,
   D3FK_OP_CHANSUM = 14, D3FK_OP_QSAMPLE = 15, D3FK_OP_POSTERIOR = 16,
   D3FK_OP_MEMSET = 17, D3FK_OP_INC = 18, D3FK_OP_ADAM = 19,
-  D3FK_OP_PACK_ALL = 20, /* misc: p0 = device array of d3fk_pack_params, n = (count << 1) | is_bf16 */
+  D3FK_OP_PACK_ALL = 20, /* misc: p0 = device array of d3fk_pack_params, n = (blocks << 17) | (count << 1) | is_bf16 */
   D3FK_OP_LOSS = 21
 };
 

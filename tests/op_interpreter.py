@@ -236,7 +236,7 @@ def run_chansum(p):
 
 
 def run_pack_all(p):
-    n = p.n >> 1
+    n = (p.n >> 1) & 0xFFFF
     table = (_lib.PackParams * n).from_address(p.p0)
     for i in range(n):
         run_pack(table[i])

@@ -76,3 +76,30 @@ def test_fused_mse_ssim_loss(shape):
     with torch.no_grad():
         l2 = d3.loss.ssim(pd.clamp(-1, 1) * 0.5 + 0.5, target.to(DEV).clamp(-1, 1) * 0.5 + 0.5)
         assert abs(l2.item() - oracle.ssim(pred.detach().clamp(-1, 1) * 0.5 + 0.5, target.clamp(-1, 1) * 0.5 + 0.5).item()) < 1e-5
+
+
+@pytest.mark.parametrize("n,betas,with_ema", [(1000003, (0.9, 0.999), False), (4096, (0.5, 0.999), True), (37, (0.9, 0.999), True)])
+def test_fused_adam_matches_torch_optim(n, betas, with_ema):
+    """d3fk_adam vs torch.optim.Adam (d3f/train_denoiser/lit_module.py:95, train_deep_fake/lit_module.py:116-120) and the
+    ema_pytorch lerp, three steps, odd sizes exercise the scalar tail."""
+    from denoising_diffusion_deep_fake_b200.functional import adam_step_
+    g = torch.Generator().manual_seed(11)
+    npad = (n + 3) // 4 * 4 + 4
+    p0 = torch.randn(n, generator=g)
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([ref], lr=0.02, betas=betas)
+    flat = torch.zeros(npad, device=DEV)
+    p = flat[:n]
+    p.copy_(p0)
+    m, v = torch.zeros(npad, device=DEV)[:n], torch.zeros(npad, device=DEV)[:n]
+    ema = torch.zeros(npad, device=DEV)[:n] if with_ema else None
+    ema_ref = torch.zeros(n)
+    for step in range(1, 4):
+        grad = torch.randn(n, generator=g)
+        ref.grad = grad.clone()
+        opt.step()
+        adam_step_(p, grad.to(DEV), m, v, 0.02, betas[0], betas[1], 1e-8, step, ema=ema, ema_decay=0.9)
+        ema_ref.lerp_(ref.detach(), 1 - 0.9)
+    assert rel_err(p.cpu(), ref.detach()) < 1e-6
+    if with_ema:
+        assert rel_err(ema.cpu(), ema_ref) < 1e-6
