@@ -77,9 +77,10 @@ __global__ void bn_fold_kernel(d3fk_bn_params p) {
 // every thread derives scale/shift of its own 8 (4) channels from the conv-epilogue sums, and the first C/V
 // threads of block 0 publish mean / invstd / running statistics — no separate finalize launch.
 template <typename T>
-__global__ void bn_apply_kernel(d3fk_bn_params p) {
+__global__ void __launch_bounds__(256, 2) bn_apply_kernel(d3fk_bn_params p) {
   pdl_enter();
   constexpr int V = Vec<T>::N;
+  constexpr int U = 4;               // independent 16-byte loads in flight per thread
   const int cvs = p.C / V;
   const long long total = p.count * cvs;
   const T* x = (const T*)p.x;
@@ -88,6 +89,19 @@ __global__ void bn_apply_kernel(d3fk_bn_params p) {
   const long long e0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;   // multiple of cvs: the channel vector is loop invariant
   const int c = (int)(e0 % cvs) * V;
+  float v[U][V], r[U][V];
+  auto load_batch = [&](long long e) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long eu = e + u * stride;
+      if (eu < total) {
+        const long long pix = eu / cvs;
+        load_vec<T>(x + pix * p.ldx + c, v[u]);
+        if (res) load_vec<T>(res + pix * p.ldr + c, r[u]);
+      }
+    }
+  };
+  load_batch(e0);                    // first loads are in flight while the block derives scale / shift
   extern __shared__ float s_aff[];   // [2][C] scale, shift — derived once per block
   for (int ch = threadIdx.x; ch < p.C; ch += blockDim.x) {
     float sc, sh;
@@ -121,19 +135,24 @@ __global__ void bn_apply_kernel(d3fk_bn_params p) {
   float scf[V], shf[V];
 #pragma unroll
   for (int i = 0; i < V; ++i) { scf[i] = s_aff[c + i]; shf[i] = s_aff[p.C + c + i]; }
-  for (long long e = e0; e < total; e += stride) {
-    const long long pix = e / cvs;
-    float v[V], r[V];
-    load_vec<T>(x + pix * p.ldx + c, v);
-    if (res) load_vec<T>(res + pix * p.ldr + c, r);
+  for (long long e = e0; e < total;) {
 #pragma unroll
-    for (int i = 0; i < V; ++i) {
-      float t = fmaf(v[i], scf[i], shf[i]);
-      if (res) t += r[i];
-      if (p.relu) t = fmaxf(t, 0.f);
-      v[i] = t;
+    for (int u = 0; u < U; ++u) {
+      const long long eu = e + u * stride;
+      if (eu < total) {
+        const long long pix = eu / cvs;
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          float t = fmaf(v[u][i], scf[i], shf[i]);
+          if (res) t += r[u][i];
+          if (p.relu) t = fmaxf(t, 0.f);
+          v[u][i] = t;
+        }
+        store_vec<T>(y + pix * p.ldy + c, v[u]);
+      }
     }
-    store_vec<T>(y + pix * p.ldy + c, v);
+    e += U * stride;
+    if (e < total) load_batch(e);
   }
 }
 
@@ -160,19 +179,31 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(d3fk_bn_params p) {
     const T* x = (const T*)p.x;
     const T* dy = (const T*)p.dy;
     const T* act = (const T*)p.act;
-    for (long long pix = (long long)blockIdx.x * rows_per_iter + prow; pix < p.count;
-         pix += (long long)gridDim.x * rows_per_iter) {
-      float xv[V], gv[V], av[V];
-      load_vec<T>(x + pix * p.ldx + c, xv);
-      load_vec<T>(dy + pix * p.lddy + c, gv);
-      if (p.relu) load_vec<T>(act + pix * p.ldact + c, av);
+    constexpr int U = 2;   // independent pixel rows in flight per thread
+    const long long pstride = (long long)gridDim.x * rows_per_iter;
+    for (long long pix0 = (long long)blockIdx.x * rows_per_iter + prow; pix0 < p.count; pix0 += U * pstride) {
+      float xv[U][V], gv[U][V], av[U][V];
 #pragma unroll
-      for (int i = 0; i < V; ++i) {
-        float g = gv[i];
-        if (p.relu && !(av[i] > 0.f)) g = 0.f;
-        float xh = (xv[i] - mean[i]) * istd[i];
-        s1[i] += (Acc)g;
-        s2[i] += (Acc)(g * xh);
+      for (int u = 0; u < U; ++u) {
+        const long long pix = pix0 + u * pstride;
+        if (pix < p.count) {
+          load_vec<T>(x + pix * p.ldx + c, xv[u]);
+          load_vec<T>(dy + pix * p.lddy + c, gv[u]);
+          if (p.relu) load_vec<T>(act + pix * p.ldact + c, av[u]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (pix0 + u * pstride < p.count) {
+#pragma unroll
+          for (int i = 0; i < V; ++i) {
+            float g = gv[u][i];
+            if (p.relu && !(av[u][i] > 0.f)) g = 0.f;
+            float xh = (xv[u][i] - mean[i]) * istd[i];
+            s1[i] += (Acc)g;
+            s2[i] += (Acc)(g * xh);
+          }
+        }
       }
     }
   }
@@ -267,22 +298,37 @@ __global__ void bn_bwd_apply_kernel(d3fk_bn_params p) {
     k0[i] = s_k[c + i]; k1[i] = s_k[p.C + c + i]; k2[i] = s_k[2 * p.C + c + i];
     mean[i] = s_k[3 * p.C + c + i]; istd[i] = s_k[4 * p.C + c + i];
   }
-  for (long long e = e0; e < total; e += stride) {
-    const long long pix = e / cvs;
-    float xv[V], gv[V], av[V], o[V];
-    load_vec<T>(x + pix * p.ldx + c, xv);
-    load_vec<T>(dy + pix * p.lddy + c, gv);
-    if (p.relu) load_vec<T>(act + pix * p.ldact + c, av);
+  constexpr int U = 2;   // independent pixel vectors in flight per thread (3 loads each)
+  for (long long e = e0; e < total; e += U * stride) {
+    float xv[U][V], gv[U][V], av[U][V];
 #pragma unroll
-    for (int i = 0; i < V; ++i) {
-      float g = gv[i];
-      if (p.relu && !(av[i] > 0.f)) g = 0.f;
-      gv[i] = g;
-      const float xh = (xv[i] - mean[i]) * istd[i];
-      o[i] = k0[i] * (g - k1[i] - xh * k2[i]);
+    for (int u = 0; u < U; ++u) {
+      const long long eu = e + u * stride;
+      if (eu < total) {
+        const long long pix = eu / cvs;
+        load_vec<T>(x + pix * p.ldx + c, xv[u]);
+        load_vec<T>(dy + pix * p.lddy + c, gv[u]);
+        if (p.relu) load_vec<T>(act + pix * p.ldact + c, av[u]);
+      }
     }
-    store_vec<T>(dx + pix * p.lddx + c, o);
-    if (dres) store_vec<T>(dres + pix * p.lddres + c, gv);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long eu = e + u * stride;
+      if (eu < total) {
+        const long long pix = eu / cvs;
+        float o[V];
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          float g = gv[u][i];
+          if (p.relu && !(av[u][i] > 0.f)) g = 0.f;
+          gv[u][i] = g;
+          const float xh = (xv[u][i] - mean[i]) * istd[i];
+          o[i] = k0[i] * (g - k1[i] - xh * k2[i]);
+        }
+        store_vec<T>(dx + pix * p.lddx + c, o);
+        if (dres) store_vec<T>(dres + pix * p.lddres + c, gv[u]);
+      }
+    }
   }
 }
 
@@ -523,27 +569,25 @@ __global__ void __launch_bounds__(256) pack_all_kernel(const d3fk_pack_params* _
   const int co0 = (local / cib) * PK_T, ci0 = (local % cib) * PK_T;
   const int nco = min(PK_T, p.Cout - co0), nci = min(PK_T, p.Cin - ci0);
   const int ncol = nci * taps;
-  for (int i = threadIdx.x; i < nco * ncol; i += blockDim.x) {
-    const int r = i / ncol, c = i - r * ncol;
-    tile[r][c] = __ldg(p.w + ((long long)(co0 + r) * p.Cin + ci0) * taps + c);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  for (int r = warp; r < nco; r += nwarp) {
+    const float* src = p.w + ((long long)(co0 + r) * p.Cin + ci0) * taps;
+    for (int c = lane; c < ncol; c += 32) tile[r][c] = __ldg(src + c);
   }
   __syncthreads();
+  // one (row, tap) pair per warp iteration, lanes along the contiguous output channel: no per-element index division
   if (p.w_fwd) {
     T* dst = (T*)p.w_fwd;
-    for (int i = threadIdx.x; i < nco * ncol; i += blockDim.x) {
-      const int c = i % nci;
-      const int t = (i / nci) % taps;
-      const int r = i / ncol;
-      dst[((long long)(co0 + r) * taps + t) * p.cin_pad + ci0 + c] = from_f<T>(tile[r][c * taps + t]);
+    for (int q = warp; q < nco * taps; q += nwarp) {
+      const int r = q / taps, t = q - r * taps;
+      if (lane < nci) dst[((long long)(co0 + r) * taps + t) * p.cin_pad + ci0 + lane] = from_f<T>(tile[r][lane * taps + t]);
     }
   }
   if (p.w_dgrad) {
     T* dst = (T*)p.w_dgrad;
-    for (int i = threadIdx.x; i < nco * ncol; i += blockDim.x) {
-      const int r = i % nco;
-      const int t = (i / nco) % taps;
-      const int c = i / (nco * taps);
-      dst[((long long)(ci0 + c) * taps + t) * p.cout_pad + co0 + r] = from_f<T>(tile[r][c * taps + t]);
+    for (int q = warp; q < nci * taps; q += nwarp) {
+      const int c = q / taps, t = q - c * taps;
+      if (lane < nco) dst[((long long)(ci0 + c) * taps + t) * p.cout_pad + co0 + lane] = from_f<T>(tile[lane][c * taps + t]);
     }
   }
 }
@@ -618,7 +662,7 @@ int launch_bn_apply(const d3fk_bn_params* p, cudaStream_t s) {
   D3FK_CHECK_ARG(p->C % 8 == 0, "C must be a multiple of 8");
   int V = p->dtype == D3FK_F32 ? 4 : 8;
   long long total = p->count * (p->C / V);
-  DISPATCH_T(p->dtype, launch_k(bn_apply_kernel<T>, dim3(grid_for(total, 256 * 4, 4)), dim3(256), 2 * p->C * sizeof(float), s, dim3(1, 1, 1), *p));
+  DISPATCH_T(p->dtype, launch_k(bn_apply_kernel<T>, dim3(grid_for(total, 256 * 4, 2)), dim3(256), 2 * p->C * sizeof(float), s, dim3(1, 1, 1), *p));
   count_launch();
   return check_launch("bn_apply");
 }
