@@ -77,6 +77,18 @@ CONV_CASES = [
     dict(B=2, Hi=8, Wi=8, c0=128, c1=0, up0=0, Cout=64, k=3, stride=2, pad=1, mode=1),
     dict(B=2, Hi=8, Wi=8, c0=128, c1=0, up0=0, Cout=64, k=1, stride=2, pad=0, mode=1, res=True),
     dict(B=2, Hi=32, Wi=32, c0=8, c1=0, up0=0, Cout=16, k=3, stride=1, pad=1, mode=1),
+    # slab path (3x3 s1, Cin in {16,32,64}, W in {16,32,64}): every swizzle width, forward and dgrad, all epilogues
+    dict(B=3, Hi=32, Wi=32, c0=32, c1=0, up0=0, Cout=32, k=3, stride=1, pad=1, mode=0, stats=True),
+    dict(B=3, Hi=32, Wi=32, c0=32, c1=0, up0=0, Cout=32, k=3, stride=1, pad=1, mode=1, res=True),
+    dict(B=2, Hi=32, Wi=32, c0=32, c1=0, up0=0, Cout=64, k=3, stride=1, pad=1, mode=1),
+    dict(B=2, Hi=64, Wi=64, c0=16, c1=0, up0=0, Cout=32, k=3, stride=1, pad=1, mode=1),
+    dict(B=2, Hi=64, Wi=64, c0=16, c1=0, up0=0, Cout=16, k=3, stride=1, pad=1, mode=0, relu=1, res=True, affine=True),
+    dict(B=5, Hi=16, Wi=16, c0=64, c1=0, up0=0, Cout=128, k=3, stride=1, pad=1, mode=1),
+    dict(B=5, Hi=16, Wi=16, c0=64, c1=0, up0=0, Cout=64, k=3, stride=1, pad=1, mode=0, stats=True, seed=3),
+    dict(B=40, Hi=16, Wi=16, c0=64, c1=0, up0=0, Cout=64, k=3, stride=1, pad=1, mode=0, stats=True, seed=4),   # > 1 tile per CTA
+    dict(B=3, Hi=6, Wi=64, c0=16, c1=0, up0=0, Cout=16, k=3, stride=1, pad=1, mode=0, stats=True),            # S = 1 fallback
+    dict(B=1, Hi=24, Wi=32, c0=32, c1=0, up0=0, Cout=32, k=3, stride=1, pad=1, mode=0, stats=True),           # S = 2
+    dict(B=2, Hi=64, Wi=64, c0=16, c1=0, up0=0, Cout=3, k=3, stride=1, pad=1, mode=0, nchw=True),
 ]
 
 
