@@ -152,11 +152,13 @@ static cudaStream_t g_side_stream = nullptr;
 static cudaEvent_t g_fork_events[64];
 static cudaEvent_t g_join_event = nullptr;
 static int g_n_fork_events = 0;
+static int g_skip_wgrad = 0;
 static int g_fork_wgrad = 1;   // D3FK_FORK_WGRAD=0: everything in stream order
 
 static int ensure_side_stream() {
   if (g_side_stream) return D3FK_OK;
   if (const char* v = getenv("D3FK_FORK_WGRAD")) g_fork_wgrad = atoi(v);
+  if (const char* v = getenv("D3FK_SKIP_WGRAD")) g_skip_wgrad = atoi(v);
   cudaError_t e = cudaStreamCreateWithFlags(&g_side_stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) return set_error(D3FK_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
   for (int i = 0; i < 64 && e == cudaSuccess; ++i) { e = cudaEventCreateWithFlags(&g_fork_events[i], cudaEventDisableTiming); g_n_fork_events = i + 1; }
@@ -173,6 +175,7 @@ int d3fk_run(const d3fk_op* ops, int n_ops, d3fk_stream stream) {
   cudaStream_t s = (cudaStream_t)stream;
   int forks = 0;
   for (int i = 0; i < n_ops; ++i) {
+    if (ops[i].kind == D3FK_OP_WGRAD && g_skip_wgrad) continue;   // timing experiment only (D3FK_SKIP_WGRAD=1)
     if (ops[i].kind == D3FK_OP_WGRAD && g_fork_wgrad && n_ops > 1) {
       cudaEvent_t ev = g_fork_events[forks % g_n_fork_events];
       cudaError_t e = cudaEventRecord(ev, s);

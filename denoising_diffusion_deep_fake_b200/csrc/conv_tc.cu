@@ -762,6 +762,7 @@ static bool tma_box(const Gather& g, const d3fk_conv_params* p, TileSched& ts) {
 // the epilogue (double-buffered TMEM accumulators), so load, MMA and epilogue of consecutive super-tiles overlap.
 struct SlabSched {
   int W, H, R, S;         // image extent; rows per 128-pixel sub-tile; sub-tiles per super-tile
+  int Wt, wtiles;         // tile width min(W, 128) and tiles across the image width
   int row_bytes;          // Cin * 2 = bytes of one pixel row of the K-major operand = TMA / UMMA swizzle span (32/64/128)
   int slab_bytes;         // (S*R + 2) * W * row_bytes rounded up to 1 KB
   int slab_tx;            // bytes one slab load delivers
@@ -847,12 +848,14 @@ __global__ void __launch_bounds__(TC_THREADS) conv_slab_kernel(const __grid_cons
       uint32_t it = 0;
       for (int t = blockIdx.x; t < ss.total; t += gridDim.x, ++it) {
         const int n = t / ss.tiles_per_img;
-        const int h0 = (t - n * ss.tiles_per_img) * rows;
+        const int rem = t - n * ss.tiles_per_img;
+        const int hb = rem / ss.wtiles;
+        const int h0 = hb * rows, w0 = (rem - hb * ss.wtiles) * ss.Wt;
         const int st = it % ss.stages;
         if (it >= (uint32_t)ss.stages) mbar_wait(empty_bar(st), ((it / ss.stages) - 1) & 1, errflag);
         mbar_arrive_expect_tx(full_bar(st), 3u * ss.slab_tx);
         for (int sx = 0; sx < 3; ++sx)
-          tma_load_4d(slab_base + st * stage_bytes + sx * ss.slab_bytes, &tmA, 0, sx - 1, h0 - 1, n, full_bar(st));
+          tma_load_4d(slab_base + st * stage_bytes + sx * ss.slab_bytes, &tmA, 0, w0 + sx - 1, h0 - 1, n, full_bar(st));
       }
     }
     __syncwarp();
@@ -865,7 +868,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_slab_kernel(const __grid_cons
       const uint32_t sbo = 8u * ss.row_bytes;
       const uint64_t dtempl = make_smem_desc_sw(0, sbo, ss.layout);
       const uint32_t dhi = (uint32_t)(dtempl >> 32), dlo = (uint32_t)dtempl;
-      const uint32_t img_row16 = (uint32_t)(ss.W * ss.row_bytes) >> 4;   // one image row of the slab, in 16-byte units
+      const uint32_t img_row16 = (uint32_t)(ss.Wt * ss.row_bytes) >> 4;  // one image row of the slab, in 16-byte units
       uint32_t a_off[9], b_lo[9];
 #pragma unroll
       for (int tap = 0; tap < 9; ++tap) {
@@ -901,16 +904,25 @@ __global__ void __launch_bounds__(TC_THREADS) conv_slab_kernel(const __grid_cons
     __syncwarp();
   } else {
     // ===================== epilogue warps =====================
+    // Narrow layers (BN <= 32) keep their batch statistics in registers: a thread owns row (warp*32+lane) of every
+    // sub-tile, so it accumulates its own per-column sums over the whole kernel and the 128 rows are folded ONCE at
+    // the end (instead of a shuffle transpose-reduce per tile).
+    constexpr bool REG_STATS = BN <= 32;
+    float rs[REG_STATS ? BN : 1], rq[REG_STATS ? BN : 1];
+#pragma unroll
+    for (int i = 0; i < (REG_STATS ? BN : 1); ++i) { rs[i] = 0.f; rq[i] = 0.f; }
     uint32_t it = 0;
     const int row = warp * 32 + lane;
     for (int t = blockIdx.x; t < ss.total; t += gridDim.x, ++it) {
       const uint32_t abuf = it & 1;
       const int n = t / ss.tiles_per_img;
-      const int h0 = (t - n * ss.tiles_per_img) * S * ss.R;
+      const int rem = t - n * ss.tiles_per_img;
+      const int hb = rem / ss.wtiles;
+      const int h0 = hb * S * ss.R, w0 = (rem - hb * ss.wtiles) * ss.Wt;
       mbar_wait(acc_full_bar(abuf), (it >> 1) & 1, errflag);
       tc_fence_after();
       for (int s = 0; s < S; ++s) {
-        const long long m = ((long long)n * ss.H + h0 + s * ss.R) * ss.W + row;   // 128 consecutive pixels
+        const long long m = ((long long)n * ss.H + h0 + s * ss.R) * ss.W + w0 + row;   // 128 consecutive pixels
         const bool row_ok = m < ss.M;
         int on = 0, oh = 0, ow = 0;
         if (e.out_nchw && row_ok) {
@@ -919,7 +931,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_slab_kernel(const __grid_cons
           on = (int)fdiv(q, dHo);
           oh = (int)q - on * e.Ho;
         }
-#pragma unroll 1
+#pragma unroll
         for (int cc = 0; cc < BN; cc += CW) {
           uint32_t raw[CW];
           const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + abuf * (uint32_t)(S * ACC) + (uint32_t)(s * ACC + cc);
@@ -928,14 +940,33 @@ __global__ void __launch_bounds__(TC_THREADS) conv_slab_kernel(const __grid_cons
           float f[CW];
 #pragma unroll
           for (int i = 0; i < CW; ++i) f[i] = __uint_as_float(raw[i]);
-          epilogue_chunk<CW>(f, e, m, row_ok, cc, on, oh, ow, do_stats, s_stat + warp * 2 * BN + cc, s_stat + warp * 2 * BN + BN + cc,
-                             lane);
+          epilogue_chunk<CW>(f, e, m, row_ok, cc, on, oh, ow, do_stats && !REG_STATS, s_stat + warp * 2 * BN + cc,
+                             s_stat + warp * 2 * BN + BN + cc, lane);
+          if (REG_STATS && do_stats) {
+#pragma unroll
+            for (int i = 0; i < CW; ++i) { rs[cc + i] += f[i]; rq[cc + i] = fmaf(f[i], f[i], rq[cc + i]); }
+          }
         }
       }
       tc_fence_before();
       mbar_arrive(acc_empty_bar(abuf));
     }
     if (do_stats) {
+      if (REG_STATS) {
+#pragma unroll
+        for (int cc = 0; cc < BN; cc += CW) {
+          float a[CW], b[CW];
+#pragma unroll
+          for (int i = 0; i < CW; ++i) { a[i] = rs[cc + i]; b[i] = rq[cc + i]; }
+          float cs, cq;
+          if (CW == 32) { cs = warp_colsum32(a, lane); cq = warp_colsum32(b, lane); }
+          else { cs = warp_colsum16(a, lane); cq = warp_colsum16(b, lane); }
+          if (lane < CW) {
+            s_stat[warp * 2 * BN + cc + lane] = cs;
+            s_stat[warp * 2 * BN + BN + cc + lane] = cq;
+          }
+        }
+      }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (tid < BN && tid < e.Cout) {
         const float a = (s_stat[tid] + s_stat[2 * BN + tid]) + (s_stat[4 * BN + tid] + s_stat[6 * BN + tid]);
@@ -961,12 +992,13 @@ static bool slab_plan(const Gather& g, const d3fk_conv_params* p, int BN, SlabSc
   if (p->Ho != p->Hi || p->Wo != p->Wi) return false;
   const int C = g.ctot, W = p->Wi, H = p->Hi;
   if (C != 16 && C != 32 && C != 64) return false;
-  if (W != 16 && W != 32 && W != 64) return false;
+  if (W != 16 && W != 32 && W != 64 && (W % 128)) return false;
   if (p->Cout > BN || (!p->out_nchw && p->Cout != BN)) return false;
   if (((uintptr_t)p->src0 & 15) || (g.ld0 % 8)) return false;
-  const int R = TC_BM / W;
+  const int Wt = W < TC_BM ? W : TC_BM;
+  const int R = TC_BM / Wt;
   if (H % R) return false;
-  ss.W = W; ss.H = H; ss.R = R;
+  ss.W = W; ss.H = H; ss.R = R; ss.Wt = Wt; ss.wtiles = W / Wt;
   ss.row_bytes = C * 2;
   ss.layout = C == 64 ? 2u : C == 32 ? 4u : 6u;
   ss.ksteps = C / 16;
@@ -979,15 +1011,15 @@ static bool slab_plan(const Gather& g, const d3fk_conv_params* p, int BN, SlabSc
   for (int S = 4; S >= 1; S >>= 1) {
     if (2 * S * ACC > 512) continue;
     if (H % (S * R)) continue;
-    const int slab = ((S * R + 2) * W * ss.row_bytes + 1023) & ~1023;
+    const int slab = ((S * R + 2) * Wt * ss.row_bytes + 1023) & ~1023;
     for (int stages = 3; stages >= 2; --stages) {
       const int need = 1024 + w_bytes + stages * 3 * slab + 128 + 8 * BN * 4;
       if (need > SLAB_MAX_SMEM) continue;
       ss.S = S;
       ss.slab_bytes = slab;
-      ss.slab_tx = (S * R + 2) * W * ss.row_bytes;
+      ss.slab_tx = (S * R + 2) * Wt * ss.row_bytes;
       ss.stages = stages;
-      ss.tiles_per_img = H / (S * R);
+      ss.tiles_per_img = (H / (S * R)) * ss.wtiles;
       ss.total = p->B * ss.tiles_per_img;
       smem = need;
       return true;
@@ -1011,7 +1043,7 @@ static int launch_conv_slab_bn(const Gather& g, const d3fk_conv_params* p, cudaS
   {
     uint64_t dims[4] = {(uint64_t)C, (uint64_t)g.Wi, (uint64_t)g.Hi, (uint64_t)g.B};
     uint64_t strides[3] = {(uint64_t)g.ld0 * 2, (uint64_t)g.Wi * g.ld0 * 2, (uint64_t)g.Hi * g.Wi * g.ld0 * 2};
-    uint32_t bx[4] = {(uint32_t)C, (uint32_t)ss.W, (uint32_t)(ss.S * ss.R + 2), 1u};
+    uint32_t bx[4] = {(uint32_t)C, (uint32_t)ss.Wt, (uint32_t)(ss.S * ss.R + 2), 1u};
     int rc = get_tensor_map(&tmA, p->src0, 4, dims, strides, bx, ss.row_bytes);
     if (rc) return rc;
   }

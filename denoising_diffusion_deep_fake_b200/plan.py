@@ -16,7 +16,8 @@ from ._lib import make_op, op_params
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
 SPLITK_WS_BYTES = 64 << 20
-CIN_PAD = 8  # RGB input / 3-channel head gradient are zero padded to 8 channels (16-byte bf16 gather chunks)
+CIN_PAD = 8  # the RGB input is zero padded to 8 channels (16-byte bf16 gather chunks)
+DY_PAD = 16  # the 3-channel head gradient is zero padded to 16 channels (one UMMA K step: the slab dgrad path)
 
 
 class ConvSpec:
@@ -147,7 +148,7 @@ class UnetPlan:
         self.w_fwd, self.w_dgrad = {}, {}
         for c in self.convs:
             cin_pad = CIN_PAD if c.cin == 3 else c.cin
-            cout_pad = CIN_PAD if c.cout == 3 else c.cout
+            cout_pad = DY_PAD if c.cout == 3 else c.cout
             taps = c.k * c.k
             self.w_fwd[c.name] = self._new((c.cout, taps * cin_pad), self.tdtype)
             if self.training and c is not self.stem:
@@ -202,7 +203,7 @@ class UnetPlan:
         blocks = 0
         for c in self.convs:
             cin_pad = CIN_PAD if c.cin == 3 else c.cin
-            cout_pad = CIN_PAD if c.cout == 3 else c.cout
+            cout_pad = DY_PAD if c.cout == 3 else c.cout
             wd = self.w_dgrad.get(c.name)
             assert c.k * c.k * min(c.cin, 32) <= 288, "pack_all tile: taps * min(Cin, 32) must be <= 288"
             packs.append(make_op(_lib.OP_PACK, dtype=self.dtype, Cout=c.cout, Cin=c.cin, kh=c.k, kw=c.k,
@@ -392,12 +393,12 @@ class UnetPlan:
         ops.append(make_op(_lib.OP_MEMSET, p0=self.grad_arena.data_ptr(), n=self.grad_arena.numel() * 4))
         ops.append(make_op(_lib.OP_MEMSET, p0=self.stats[1].data_ptr(), n=self.stats[1].numel() * 8))
         # ---- head
-        self.dy8 = T(self, B, self.H, self.W, CIN_PAD)
+        self.dy8 = T(self, B, self.H, self.W, DY_PAD)
         self.keep.append(self.dy8.t)
         self.dy_op_index = len(ops)
-        ops.append(make_op(_lib.OP_NCHW2NHWC, dtype=self.dtype, B=B, C=3, H=self.H, W=self.W, cpad=CIN_PAD, src=None,
+        ops.append(make_op(_lib.OP_NCHW2NHWC, dtype=self.dtype, B=B, C=3, H=self.H, W=self.W, cpad=DY_PAD, src=None,
                            dst=self.dy8.ptr))
-        ops.append(make_op(_lib.OP_CHANSUM, dtype=self.dtype, C=3, ld=CIN_PAD, count=self.dy8.count, x=self.dy8.ptr,
+        ops.append(make_op(_lib.OP_CHANSUM, dtype=self.dtype, C=3, ld=DY_PAD, count=self.dy8.count, x=self.dy8.ptr,
                            out=self._gptr(self.head.name + ".bias")))
         ops.append(self._wgrad_op(self.head, self.dec_out, None, 0, self.dy8))
         g = self._newT(self.dec_out)

@@ -89,6 +89,10 @@ CONV_CASES = [
     dict(B=3, Hi=6, Wi=64, c0=16, c1=0, up0=0, Cout=16, k=3, stride=1, pad=1, mode=0, stats=True),            # S = 1 fallback
     dict(B=1, Hi=24, Wi=32, c0=32, c1=0, up0=0, Cout=32, k=3, stride=1, pad=1, mode=0, stats=True),           # S = 2
     dict(B=2, Hi=64, Wi=64, c0=16, c1=0, up0=0, Cout=3, k=3, stride=1, pad=1, mode=0, nchw=True),
+    dict(B=2, Hi=8, Wi=128, c0=16, c1=0, up0=0, Cout=16, k=3, stride=1, pad=1, mode=0, stats=True),            # W = 128: one row per sub-tile
+    dict(B=1, Hi=12, Wi=256, c0=32, c1=0, up0=0, Cout=32, k=3, stride=1, pad=1, mode=1, res=True),             # two tiles across W
+    dict(B=1, Hi=4, Wi=256, c0=16, c1=0, up0=0, Cout=3, k=3, stride=1, pad=1, mode=0, nchw=True),
+    dict(B=2, Hi=32, Wi=32, c0=16, c1=0, up0=0, Cout=16, k=3, stride=1, pad=1, mode=1),                        # head dgrad (dy padded to 16)
 ]
 
 
