@@ -83,7 +83,7 @@ class AdamParams(C.Structure):
 
 class LossParams(C.Structure):
     _fields_ = [("B", i32), ("C", i32), ("H", i32), ("W", i32), ("pred", vp), ("target", vp), ("grad", vp), ("acc", vp),
-                ("lo", f32), ("hi", f32), ("grad_scale", f32), ("_pad0", f32), ("win", f32 * 12)]
+                ("lo", f32), ("hi", f32), ("grad_scale", f32), ("_pad0", f32), ("win", f32 * 12), ("loss_out", vp)]
 
 
 class _OpUnion(C.Union):

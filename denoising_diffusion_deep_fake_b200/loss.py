@@ -1,7 +1,7 @@
 """MSE + (1 - SSIM) training criterion of the reference
 (d3f/loss_functions/structural_similarity_loss.py:5-26 with piqa.SSIM() defaults).
-On CUDA the forward value AND dL/dprediction come from one fused libd3fk kernel;
-`ssim()` below is the same computation composed of torch ops (used for logging / non-fp32 inputs)."""
+The forward value AND dL/dprediction come from ONE fused libd3fk kernel launch; there is no
+CPU or torch fallback for the criterion.  `ssim()` is a CUDA logging helper composed of torch ops."""
 import math
 
 import torch
@@ -17,6 +17,17 @@ def _window(size=11, sigma=1.5):
     return [v / s for v in g]
 
 
+_WORKSPACE = {}   # device -> 3 zeroed doubles (sum of squared errors, sum of the SSIM map, block ticket); self-resetting
+
+
+def _workspace(device):
+    ws = _WORKSPACE.get(device)
+    if ws is None:
+        ws = torch.zeros(4, dtype=torch.float64, device=device)
+        _WORKSPACE[device] = ws
+    return ws
+
+
 class _FusedMseSsim(torch.autograd.Function):
     @staticmethod
     def forward(ctx, prediction, target, lo, hi):
@@ -26,15 +37,12 @@ class _FusedMseSsim(torch.autograd.Function):
         B, C, H, W = pred.shape
         need_grad = prediction.requires_grad
         grad = torch.empty_like(pred) if need_grad else None
-        acc = torch.zeros(2, dtype=torch.float64, device=pred.device)
+        loss = torch.empty((), dtype=torch.float32, device=pred.device)
         win = (_lib.f32 * 12)(*(_window() + [0.0]))
         op = _lib.make_op(_lib.OP_LOSS, B=B, C=C, H=H, W=W, pred=pred.data_ptr(), target=tgt.data_ptr(),
-                          grad=None if grad is None else grad.data_ptr(), acc=acc.data_ptr(), lo=float(lo), hi=float(hi),
-                          grad_scale=1.0, win=win)
-        _lib.run_single(op, torch.cuda.current_stream(pred.device).cuda_stream)
-        n_tot = pred.numel()
-        n_map = B * C * (H - 10) * (W - 10)
-        loss = ((acc[0] / n_tot + 1.0 - acc[1] / n_map) * 0.5).to(torch.float32)
+                          grad=None if grad is None else grad.data_ptr(), acc=_workspace(pred.device).data_ptr(),
+                          lo=float(lo), hi=float(hi), grad_scale=1.0, win=win, loss_out=loss.data_ptr())
+        _lib.run_single(op, torch.cuda.current_stream(pred.device).cuda_stream)   # ONE launch: value and gradient
         ctx.save_for_backward(grad) if need_grad else None
         ctx.has_grad = need_grad
         return loss
@@ -54,6 +62,10 @@ def _gaussian_1d(size, sigma, dtype, device):
 
 
 def ssim(x, y, window_size=11, sigma=1.5, value_range=1.0, k1=0.01, k2=0.03):
+    """piqa.SSIM value composed of torch CUDA ops — a logging / diagnostic helper, never on the training hot path
+    (the criterion below is the fused kernel)."""
+    if not x.is_cuda:
+        raise _lib.D3fkError("d3fk.ssim is a CUDA logging helper; there is no CPU path")
     c = x.shape[1]
     g = _gaussian_1d(window_size, sigma, x.dtype, x.device)
     kh = g.view(1, 1, -1, 1).expand(c, 1, -1, 1).contiguous()
@@ -80,11 +92,13 @@ class MseStructuralSimilarityLoss(nn.Module):
         return x.clip(0.0, 1.0)
 
     def forward(self, prediction, target):
-        if (prediction.is_cuda and prediction.dtype == torch.float32 and target.dtype == torch.float32
-                and prediction.dim() == 4 and prediction.shape[-1] % 32 == 0 and prediction.shape[-2] % 32 == 0
-                and not target.requires_grad):
-            return _FusedMseSsim.apply(prediction, target, self.input_min_value, self.input_max_value)
-        mse_loss = F.mse_loss(prediction, target)
-        p = self.normalise_between_zero_and_one(prediction)
-        t = self.normalise_between_zero_and_one(target)
-        return (mse_loss + (1.0 - ssim(p, t))) / 2.0
+        if not (prediction.is_cuda and target.is_cuda):
+            raise _lib.D3fkError("d3fk.MseStructuralSimilarityLoss runs only on a B200 (sm_100a) CUDA device; "
+                                 "there is no CPU path")
+        if (prediction.dtype != torch.float32 or target.dtype != torch.float32 or prediction.dim() != 4
+                or prediction.shape != target.shape or prediction.shape[-1] % 32 or prediction.shape[-2] % 32):
+            raise ValueError("expected float32 [B,C,H,W] prediction and target of equal shape with H and W multiples of 32 "
+                             f"(the U-Net's own constraint), got {tuple(prediction.shape)} {prediction.dtype}")
+        if target.requires_grad:
+            raise NotImplementedError("the criterion does not back-propagate into the target (the reference never does)")
+        return _FusedMseSsim.apply(prediction, target, self.input_min_value, self.input_max_value)

@@ -170,6 +170,8 @@ typedef struct d3fk_loss_params {
   float* grad; double* acc;
   float lo, hi, grad_scale, _pad0;
   float win[12];                             /* 11-tap normalised Gaussian (+1 pad) */
+  float* loss_out;                           /* nullable.  When set, acc must hold 3 zeroed doubles: the last block writes the
+                                                finished scalar loss here and re-zeroes acc (self-resetting workspace) */
 } d3fk_loss_params;
 
 enum d3fk_op_kind {
