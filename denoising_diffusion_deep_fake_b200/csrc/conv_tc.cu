@@ -1367,12 +1367,243 @@ static int launch_wgrad_tc_bn(const Gather& g, const d3fk_wgrad_params* p, cudaS
   return check_launch("wgrad_tc");
 }
 
+// ------------------------------------------------------------------------------------------
+// Slab weight gradient: 3x3 / stride 1 / pad 1, one source, Cin in {16, 32, 64}, Cout in {16, 32}, large images.
+// dW[kh][kw][ci][co] = sum_pix A[pix + (kh-1, kw-1)][ci] * dY[pix][co].  A persistent CTA walks super-tiles of S*128
+// pixels; per super-tile it lands the same three column-shifted activation slabs as conv_slab_kernel plus the dY tile.
+// Both operands are MN-major (pixel rows are the MMA K dimension).  The A operand of ONE tcgen05.mma is M = 128 =
+// (128 / Cin) "atoms" of Cin channels whose leading-dimension stride is one image row of the slab — i.e. one MMA covers
+// the taps kh = 0, 1, 2 (... surplus atoms read further rows and land in accumulator rows nobody reads) of one kw for 16
+// pixels.  The 3 (x2 for Cin = 64) accumulators stay in TMEM for the whole kernel: no per-tile epilogue at all, one
+// atomic pass per CTA at the end.  L2 -> SM traffic per pixel: 3*(S*R+2)/(S*R) activation reads + 1 dY read instead of 9 + 9.
+struct WgSlabSched {
+  int W, H, R, S, Wt, wtiles;
+  int C;                  // input channels (16/32/64); a_row_bytes = 2*C
+  int a_row_bytes, b_row_bytes;
+  int slab_bytes, slab_tx, dy_bytes, stage_bytes, stages;
+  int total, tiles_per_img;
+  int MB;                 // accumulator row blocks per kw: 1 (Cin <= 32: kh 0..2 in one M = 128) or 2 (Cin = 64)
+  uint32_t a_layout, b_layout;
+};
+
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;   // stride between M (N) atoms of one swizzle width
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;   // stride between 8-row (K) groups
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)layout << 61;
+  return d;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS) wgrad_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmD,
+                                                                WgSlabSched ss, float* __restrict__ dw, int cin_real, int cout_real,
+                                                                int* errflag) {
+  constexpr int ACC = BN < 32 ? 32 : BN;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t stage_base = base;                                      // [stages][3 slabs | dY tile]
+  const uint32_t bar_base = stage_base + ss.stages * ss.stage_bytes;     // full[4], empty[4], acc_full
+  uint8_t* gen_bar = smem_raw + (bar_base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_ptr_slot = reinterpret_cast<volatile uint32_t*>(gen_bar + 8 * 9);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (4 + s); };
+  const uint32_t acc_full = bar_base + 8u * 8;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nacc = 3 * ss.MB;
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < nacc * ACC) tmem_cols <<= 1;
+  const bool has_work = (int)blockIdx.x < ss.total;
+
+  if (tid == 0) {
+    for (int s = 0; s < 4; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 5 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmD);
+  }
+  if (warp == 4) tmem_alloc(smem_u32((const void*)tmem_ptr_slot), tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_ptr_slot;
+  pdl_enter();
+
+  if (warp == 5) {
+    if (lane == 0) {
+      const int rows = ss.S * ss.R;
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < ss.total; t += gridDim.x, ++it) {
+        const int n = t / ss.tiles_per_img;
+        const int rem = t - n * ss.tiles_per_img;
+        const int hb = rem / ss.wtiles;
+        const int h0 = hb * rows, w0 = (rem - hb * ss.wtiles) * ss.Wt;
+        const int st = it % ss.stages;
+        if (it >= (uint32_t)ss.stages) mbar_wait(empty_bar(st), ((it / ss.stages) - 1) & 1, errflag);
+        mbar_arrive_expect_tx(full_bar(st), 3u * ss.slab_tx + (uint32_t)ss.dy_bytes);
+        const uint32_t sb = stage_base + st * ss.stage_bytes;
+        for (int sx = 0; sx < 3; ++sx) tma_load_4d(sb + sx * ss.slab_bytes, &tmA, 0, w0 + sx - 1, h0 - 1, n, full_bar(st));
+        tma_load_4d(sb + 3 * ss.slab_bytes, &tmD, 0, w0, h0, n, full_bar(st));
+      }
+    }
+    __syncwarp();
+  } else if (warp == 4) {
+    if (lane == 0 && has_work) {
+      constexpr uint32_t idesc = make_idesc(128, BN, 1, 1);
+      const uint32_t img_row = (uint32_t)(ss.Wt * ss.a_row_bytes);       // M-atom stride of the A operand = one tap row (kh)
+      const uint64_t a_t = make_smem_desc_mn(0, img_row, 8u * ss.a_row_bytes, ss.a_layout);
+      const uint64_t b_t = make_smem_desc_mn(0, 8u * ss.b_row_bytes, 8u * ss.b_row_bytes, ss.b_layout);
+      const uint32_t ahi = (uint32_t)(a_t >> 32), alo0 = (uint32_t)a_t, bhi = (uint32_t)(b_t >> 32), blo0 = (uint32_t)b_t;
+      const uint32_t a_step = (16u * ss.a_row_bytes) >> 4, b_step = (16u * ss.b_row_bytes) >> 4;   // 16 pixels per MMA
+      const uint32_t mb_off = ((uint32_t)(128 / ss.C) * img_row) >> 4;   // second row block (Cin = 64): taps kh = 2, (3)
+      const int ksteps = ss.S * 8;
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < ss.total; t += gridDim.x, ++it) {
+        const int st = it % ss.stages;
+        mbar_wait(full_bar(st), (it / ss.stages) & 1, errflag);
+        tc_fence_after();
+        const uint32_t sb = stage_base + st * ss.stage_bytes;
+        const uint32_t b_lo = blo0 | ((sb + 3u * ss.slab_bytes) >> 4);
+        for (int sx = 0; sx < 3; ++sx) {
+          const uint32_t a_lo = alo0 | ((sb + (uint32_t)(sx * ss.slab_bytes)) >> 4);
+          for (int mb = 0; mb < ss.MB; ++mb) {
+            const uint32_t d_addr = tmem_d + (uint32_t)((sx * ss.MB + mb) * ACC);
+            const uint32_t a_mb = a_lo + (uint32_t)mb * mb_off;
+#pragma unroll 4
+            for (int j = 0; j < ksteps; ++j)
+              umma_f16_lohi(d_addr, a_mb + (uint32_t)j * a_step, ahi, b_lo + (uint32_t)j * b_step, bhi, idesc, (it | (uint32_t)j) ? 1u : 0u);
+          }
+        }
+        umma_commit(empty_bar(st));
+      }
+      umma_commit(acc_full);
+    }
+    __syncwarp();
+  } else if (has_work) {
+    // epilogue (once per CTA): accumulator row r of (kw, row block mb) = tap kh = mb*(128/C) + r / C, channel ci = r % C
+    mbar_wait(acc_full, 0, errflag);
+    tc_fence_after();
+    const int r = warp * 32 + lane;
+    const int apm = 128 / ss.C;
+    for (int sx = 0; sx < 3; ++sx) {
+      for (int mb = 0; mb < ss.MB; ++mb) {
+        const int kh = mb * apm + r / ss.C, ci = r % ss.C;
+        const bool ok = kh < 3 && ci < cin_real;
+#pragma unroll 1
+        for (int cc = 0; cc < BN; cc += 16) {
+          uint32_t raw[16];
+          tmem_ld16(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)((sx * ss.MB + mb) * ACC + cc), raw);
+          tmem_ld_wait();
+          if (ok) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int co = cc + i;
+              if (co < cout_real) atomicAdd(dw + ((long long)co * cin_real + ci) * 9 + kh * 3 + sx, __uint_as_float(raw[i]));
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_d, tmem_cols);
+}
+
+static int g_use_wg_slab = 1;   // D3FK_WG_SLAB=0: never take the slab weight-gradient path
+
+template <int BN>
+static int launch_wgrad_slab_bn(const Gather& g, const d3fk_wgrad_params* p, cudaStream_t s, WgSlabSched& ss) {
+  const int C = g.ctot, W = p->Wi, H = p->Hi;
+  const int Wt = W < 128 ? W : 128, R = 128 / Wt;
+  ss.W = W; ss.H = H; ss.R = R; ss.Wt = Wt; ss.wtiles = W / Wt; ss.C = C;
+  ss.a_row_bytes = 2 * C;
+  ss.b_row_bytes = 2 * BN;
+  ss.a_layout = C == 64 ? 2u : C == 32 ? 4u : 6u;
+  ss.b_layout = BN == 64 ? 2u : BN == 32 ? 4u : 6u;
+  ss.MB = C == 64 ? 2 : 1;
+  const int ACC = BN < 32 ? 32 : BN;
+  if (3 * ss.MB * ACC > 512) return 0;
+  int smem = 0;
+  bool found = false;
+  for (int S = 4; S >= 1 && !found; S >>= 1) {
+    if (H % (S * R)) continue;
+    const int slab = ((S * R + 2) * Wt * ss.a_row_bytes + 1023) & ~1023;
+    const int dyb = (S * 128 * ss.b_row_bytes + 1023) & ~1023;
+    // surplus M atoms (Cin < 64: 128/C - 3 of them) read up to (128/C - 3) image rows past the last slab: they must stay
+    // inside the stage (the dY tile that follows the slabs absorbs them)
+    const int overrun = (128 / C > 3 ? 128 / C - 3 : (C == 64 ? 1 : 0)) * Wt * ss.a_row_bytes;
+    if (overrun > dyb) continue;
+    for (int stages = 3; stages >= 2; --stages) {
+      const int need = 1024 + stages * (3 * slab + dyb) + 128;
+      if (need > SLAB_MAX_SMEM) continue;
+      ss.S = S; ss.slab_bytes = slab; ss.slab_tx = (S * R + 2) * Wt * ss.a_row_bytes; ss.dy_bytes = S * 128 * ss.b_row_bytes;
+      ss.stage_bytes = 3 * slab + dyb; ss.stages = stages;
+      ss.tiles_per_img = (H / (S * R)) * ss.wtiles;
+      ss.total = p->B * ss.tiles_per_img;
+      smem = need;
+      found = true;
+      break;
+    }
+  }
+  if (!found) return 0;
+  alignas(64) CUtensorMap tmA, tmD;
+  {
+    uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)p->B};
+    uint64_t strides[3] = {(uint64_t)p->ld0 * 2, (uint64_t)W * p->ld0 * 2, (uint64_t)H * W * p->ld0 * 2};
+    uint32_t bx[4] = {(uint32_t)C, (uint32_t)Wt, (uint32_t)(ss.S * R + 2), 1u};
+    int rc = get_tensor_map(&tmA, p->src0, 4, dims, strides, bx, ss.a_row_bytes);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[4] = {(uint64_t)BN, (uint64_t)W, (uint64_t)H, (uint64_t)p->B};
+    uint64_t strides[3] = {(uint64_t)p->ldy * 2, (uint64_t)W * p->ldy * 2, (uint64_t)H * W * p->ldy * 2};
+    uint32_t bx[4] = {(uint32_t)BN, (uint32_t)Wt, (uint32_t)(ss.S * R), 1u};
+    int rc = get_tensor_map(&tmD, p->dy, 4, dims, strides, bx, ss.b_row_bytes);
+    if (rc) return rc;
+  }
+  int grid = ss.total < g_num_sms ? ss.total : g_num_sms;
+  if (g_verbose) fprintf(stderr, "[d3fk] wgrad_slab<%d> M=%d C=%d W=%d S=%d stages=%d smem=%d grid=%d total=%d\n", BN, g.M, C, W, ss.S, ss.stages, smem, grid, ss.total);
+  launch_k(wgrad_slab_kernel<BN>, dim3(grid), dim3(TC_THREADS), (size_t)smem, s, dim3(1, 1, 1), tmA, tmD, ss, p->dw, p->cin_real,
+           p->cout_real, g_dev_error_flag);
+  count_launch();
+  int rc = check_launch("wgrad_slab");
+  return rc ? rc : 1;
+}
+
+// returns 1 when taken, 0 when not eligible, < 0 on error
+static int try_launch_wgrad_slab(const Gather& g, const d3fk_wgrad_params* p, cudaStream_t s) {
+  if (!g_use_wg_slab) return 0;
+  if (p->kh != 3 || p->kw != 3 || p->stride != 1 || p->pad != 1 || p->c1 != 0 || p->up0 != 0) return 0;
+  if (p->Ho != p->Hi || p->Wo != p->Wi) return 0;
+  const int C = g.ctot, W = p->Wi;
+  if (C != 16 && C != 32 && C != 64) return 0;
+  if (p->Cout != 16 && p->Cout != 32) return 0;
+  if (W != 16 && W != 32 && W != 64 && (W % 128)) return 0;
+  if (((uintptr_t)p->src0 & 15) || ((uintptr_t)p->dy & 15) || (p->ld0 % 8) || (p->ldy % 8)) return 0;
+  if ((long long)g.M < 128ll * 148 * 4) return 0;   // small problems: the per-CTA atomic pass would dominate
+  WgSlabSched ss;
+  memset(&ss, 0, sizeof(ss));
+  if (p->Cout == 16) return launch_wgrad_slab_bn<16>(g, p, s, ss);
+  return launch_wgrad_slab_bn<32>(g, p, s, ss);
+}
+
 int launch_wgrad_tc(const d3fk_wgrad_params* p, cudaStream_t s) {
   Gather g;
   int rc = make_gather(g, p->src0, p->src1, p->c0, p->c1, p->ld0, p->ld1, p->up0, p->B, p->Hi, p->Wi, p->Ho, p->Wo, p->kh,
                        p->kw, p->stride, p->pad, 0);
   if (rc) return rc;
   D3FK_CHECK_ARG(p->Cout % 8 == 0 && p->ldy % 8 == 0, "Cout and ldy must be multiples of 8");
+  const int slab = try_launch_wgrad_slab(g, p, s);
+  if (slab) return slab < 0 ? slab : D3FK_OK;
   if (p->Cout > 64) return launch_wgrad_tc_bn<128>(g, p, s);
   return launch_wgrad_tc_bn<64>(g, p, s);
 }
@@ -1391,6 +1622,7 @@ int tc_init() {
   if (const char* v = getenv("D3FK_CLUSTER")) g_max_cluster = atoi(v);
   if (const char* v = getenv("D3FK_VERBOSE")) g_verbose = atoi(v);
   if (const char* v = getenv("D3FK_SLAB")) g_use_slab = atoi(v);
+  if (const char* v = getenv("D3FK_WG_SLAB")) g_use_wg_slab = atoi(v);
   if (const char* v = getenv("D3FK_WG_OCC")) g_wg_ctas_per_sm = atoi(v);
   if (const char* v = getenv("D3FK_WG_CAP")) g_wg_cap = atoi(v);
   if (const char* v = getenv("D3FK_WG_PLAIN")) g_wg_plain = atoi(v);
@@ -1421,6 +1653,8 @@ int tc_init() {
   SET_SMEM((conv_slab_kernel<128, 1>), SLAB_MAX_SMEM)
   SET_SMEM((conv_slab_kernel<128, 2>), SLAB_MAX_SMEM)
   SET_SMEM((conv_slab_kernel<128, 4>), SLAB_MAX_SMEM)
+  SET_SMEM(wgrad_slab_kernel<16>, SLAB_MAX_SMEM)
+  SET_SMEM(wgrad_slab_kernel<32>, SLAB_MAX_SMEM)
   SET_SMEM(wgrad_tc_kernel<64>, WgradCfg<64>::SMEM)
   SET_SMEM(wgrad_tc_kernel<128>, WgradCfg<128>::SMEM)
 #undef SET_SMEM

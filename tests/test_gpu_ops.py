@@ -115,6 +115,13 @@ WGRAD_CASES = [
     dict(B=2, Hi=32, Wi=32, c0=16, c1=0, up0=0, Cout=8, k=3, stride=1, pad=1, cout_real=3),
     dict(B=7, Hi=2, Wi=2, c0=512, c1=0, up0=0, Cout=512, k=3, stride=1, pad=1),
     dict(B=3, Hi=24, Wi=8, c0=16, c1=0, up0=0, Cout=16, k=3, stride=1, pad=1),
+    # slab weight-gradient path (3x3 s1, Cin in {16,32,64}, Cout in {16,32}, >= 75 776 pixels)
+    dict(B=19, Hi=64, Wi=64, c0=16, c1=0, up0=0, Cout=16, k=3, stride=1, pad=1),
+    dict(B=19, Hi=64, Wi=64, c0=16, c1=0, up0=0, Cout=16, k=3, stride=1, pad=1, cout_real=3),
+    dict(B=76, Hi=32, Wi=32, c0=32, c1=0, up0=0, Cout=32, k=3, stride=1, pad=1),
+    dict(B=76, Hi=32, Wi=32, c0=64, c1=0, up0=0, Cout=32, k=3, stride=1, pad=1),
+    dict(B=5, Hi=128, Wi=128, c0=16, c1=0, up0=0, Cout=32, k=3, stride=1, pad=1),
+    dict(B=300, Hi=16, Wi=16, c0=64, c1=0, up0=0, Cout=16, k=3, stride=1, pad=1),
 ]
 
 
