@@ -95,6 +95,26 @@ __device__ __forceinline__ void umma_f16_lohi(uint32_t d_tmem, uint32_t alo, uin
       ::"r"(d_tmem), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Warp-uniform issue: the whole MMA warp runs the loop and only the leader lane's instruction takes effect (inside an
+// `if (lane == 0)` region ptxas wraps every tcgen05.mma in an ELECT / R2UR serialisation loop).
+__device__ __forceinline__ void umma_f16_lohi_p(uint32_t d_tmem, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t idesc,
+                                                uint32_t accumulate, uint32_t leader) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "setp.ne.b32 q, %7, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(d_tmem), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate), "r"(leader)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_p(uint32_t bar, uint32_t leader) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar), "r"(leader)
+      : "memory");
+}
 // mbarrier arrive once all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -785,11 +805,22 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw(uint32_t saddr, uint32_t s
   return d;
 }
 
+// Warps: 0-3 epilogue, 4 TMA producer, 5..5+NW-1 MMA issuers.  A single thread sustains only one of these small MMAs
+// per ~90 cycles (descriptor moves into uniform registers + the issue itself are a dependent chain), so the 9*KSTEPS*S
+// MMAs of a super-tile are spread over NW warps: warp w owns sub-tile w % S and every P-th tap (P = NW / S) in a private
+// accumulator; the epilogue adds the P partial accumulators of a sub-tile.
+template <int BN> struct SlabCfg {
+  static constexpr int NW = BN >= 128 ? 2 : 4;
+  static constexpr int THREADS = (5 + NW) * 32;
+  static constexpr int ACC = BN < 32 ? 32 : BN;
+  static constexpr int TMEM_COLS = 2 * NW * ACC;       // double buffered
+};
 template <int BN, int KSTEPS>
-__global__ void __launch_bounds__(TC_THREADS) conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+__global__ void __launch_bounds__(SlabCfg<BN>::THREADS) conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                                EpiTC e, SlabSched ss, FastDiv dWo, FastDiv dHo, int* errflag) {
   constexpr int CW = BN >= 32 ? 32 : 16;
-  constexpr int ACC = BN < 32 ? 32 : BN;
+  constexpr int ACC = SlabCfg<BN>::ACC;
+  constexpr int NW = SlabCfg<BN>::NW;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t w_base = base;                                         // [9 taps][BN rows][row_bytes]
@@ -809,15 +840,16 @@ __global__ void __launch_bounds__(TC_THREADS) conv_slab_kernel(const __grid_cons
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool do_stats = e.stats != nullptr;
   const int S = ss.S;
-  const uint32_t tmem_cols = (uint32_t)(2 * S * ACC);   // power of two: S in {1,2,4}, ACC in {32,64,128}
+  const int P = NW / S;                                 // partial accumulators (tap subsets) per sub-tile
+  constexpr uint32_t tmem_cols = (uint32_t)SlabCfg<BN>::TMEM_COLS;
 
   if (tid == 0) {
     for (int s = 0; s < 4; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), NW);
     }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(acc_full_bar(b), 1);
+      mbar_init(acc_full_bar(b), NW);
       mbar_init(acc_empty_bar(b), 128);
     }
     mbar_init(wbar, 1);
@@ -826,18 +858,18 @@ __global__ void __launch_bounds__(TC_THREADS) conv_slab_kernel(const __grid_cons
   if (tid < 128) {
     for (int i = tid; i < 8 * BN; i += 128) s_stat[i] = 0.f;
   }
-  if (warp == 5 && lane == 0) {
+  if (warp == 4 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
   }
-  if (warp == 4) tmem_alloc(smem_u32((const void*)tmem_ptr_slot), tmem_cols);
+  if (warp == 5) tmem_alloc(smem_u32((const void*)tmem_ptr_slot), tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = *tmem_ptr_slot;
   pdl_enter();
 
-  if (warp == 5) {
+  if (warp == 4) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       // resident weights: 9 boxes {Cin, BN} of the packed [Cout][9*Cin] matrix (rows >= Cout zero filled)
@@ -859,11 +891,14 @@ __global__ void __launch_bounds__(TC_THREADS) conv_slab_kernel(const __grid_cons
       }
     }
     __syncwarp();
-  } else if (warp == 4) {
-    // ===================== MMA issuer =====================
-    // One thread issues S * 9 * KSTEPS tiny MMAs per super-tile, so the loop is kept to two adds per MMA: every
-    // descriptor is (constant high word, low word = constant | address >> 4) and the 9 tap offsets live in registers.
-    if (lane == 0) {
+  } else if (warp >= 5) {
+    // ===================== MMA issuers =====================
+    // The loop is kept to two adds per MMA: every descriptor is (constant high word, low word = constant | address >> 4)
+    // and this warp's tap offsets live in registers.  Warp-uniform loop, leader-predicated issue.
+    {
+      const int w = warp - 5;
+      const int my_s = w % S, my_p = w / S;            // sub-tile and tap subset of this warp
+      const uint32_t leader = lane == 0 ? 1u : 0u;
       constexpr uint32_t idesc = make_idesc(TC_BM, BN, 0, 0);
       const uint32_t sbo = 8u * ss.row_bytes;
       const uint64_t dtempl = make_smem_desc_sw(0, sbo, ss.layout);
@@ -875,10 +910,10 @@ __global__ void __launch_bounds__(TC_THREADS) conv_slab_kernel(const __grid_cons
         const int kh = tap / 3, kw = tap - kh * 3;
         const int sy = ss.sgn > 0 ? kh : 2 - kh;
         const int sx = ss.sgn > 0 ? kw : 2 - kw;
-        a_off[tap] = ((uint32_t)(sx * ss.slab_bytes) >> 4) + (uint32_t)sy * img_row16;
+        a_off[tap] = ((uint32_t)(sx * ss.slab_bytes) >> 4) + (uint32_t)(sy + my_s * ss.R) * img_row16;
         b_lo[tap] = dlo | ((w_base + (uint32_t)(tap * ss.w_tile_bytes)) >> 4);
       }
-      const uint32_t sub16 = (uint32_t)ss.R * img_row16;                 // one 128-pixel sub-tile, in 16-byte units
+      const bool active = my_p < P;                     // S * P == NW: always true; kept for clarity
       mbar_wait(wbar, 0, errflag);
       uint32_t it = 0;
       for (int t = blockIdx.x; t < ss.total; t += gridDim.x, ++it) {
@@ -887,18 +922,23 @@ __global__ void __launch_bounds__(TC_THREADS) conv_slab_kernel(const __grid_cons
         if (it >= 2) mbar_wait(acc_empty_bar(abuf), ((it >> 1) - 1) & 1, errflag);
         mbar_wait(full_bar(st), (it / ss.stages) & 1, errflag);
         tc_fence_after();
-        uint32_t sub_lo = dlo | ((slab_base + st * stage_bytes) >> 4);
-        uint32_t d_addr = tmem_d + abuf * (uint32_t)(S * ACC);
-        for (int s = 0; s < S; ++s, sub_lo += sub16, d_addr += ACC) {
+        const uint32_t sub_lo = dlo | ((slab_base + st * stage_bytes) >> 4);
+        const uint32_t d_addr = tmem_d + abuf * (uint32_t)(NW * ACC) + (uint32_t)((my_s * P + my_p) * ACC);
+        uint32_t first = 0u;
+        if (active) {
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
+            if (tap % P == my_p) {                      // P in {1, 2, 4}
 #pragma unroll
-            for (int kk = 0; kk < KSTEPS; ++kk)
-              umma_f16_lohi(d_addr, sub_lo + a_off[tap] + 2u * kk, dhi, b_lo[tap] + 2u * kk, dhi, idesc, (tap | kk) ? 1u : 0u);
+              for (int kk = 0; kk < KSTEPS; ++kk) {
+                umma_f16_lohi_p(d_addr, sub_lo + a_off[tap] + 2u * kk, dhi, b_lo[tap] + 2u * kk, dhi, idesc, first, leader);
+                first = 1u;
+              }
+            }
           }
         }
-        umma_commit(empty_bar(st));
-        umma_commit(acc_full_bar(abuf));
+        umma_commit_p(empty_bar(st), leader);
+        umma_commit_p(acc_full_bar(abuf), leader);
       }
     }
     __syncwarp();
@@ -934,12 +974,18 @@ __global__ void __launch_bounds__(TC_THREADS) conv_slab_kernel(const __grid_cons
 #pragma unroll
         for (int cc = 0; cc < BN; cc += CW) {
           uint32_t raw[CW];
-          const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + abuf * (uint32_t)(S * ACC) + (uint32_t)(s * ACC + cc);
+          const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + abuf * (uint32_t)(NW * ACC) + (uint32_t)(s * P * ACC + cc);
           if (CW == 32) tmem_ld32(taddr, raw); else tmem_ld16(taddr, raw);
           tmem_ld_wait();
           float f[CW];
 #pragma unroll
           for (int i = 0; i < CW; ++i) f[i] = __uint_as_float(raw[i]);
+          for (int pp = 1; pp < P; ++pp) {              // add the other tap subsets' partial accumulators
+            if (CW == 32) tmem_ld32(taddr + (uint32_t)(pp * ACC), raw); else tmem_ld16(taddr + (uint32_t)(pp * ACC), raw);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < CW; ++i) f[i] += __uint_as_float(raw[i]);
+          }
           epilogue_chunk<CW>(f, e, m, row_ok, cc, on, oh, ow, do_stats && !REG_STATS, s_stat + warp * 2 * BN + cc,
                              s_stat + warp * 2 * BN + BN + cc, lane);
           if (REG_STATS && do_stats) {
@@ -979,7 +1025,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_slab_kernel(const __grid_cons
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_d, tmem_cols);
+  if (warp == 5) tmem_dealloc(tmem_d, tmem_cols);
 }
 
 constexpr int SLAB_MAX_SMEM = 225 * 1024;
@@ -1005,11 +1051,10 @@ static bool slab_plan(const Gather& g, const d3fk_conv_params* p, int BN, SlabSc
   ss.w_tile_bytes = BN * ss.row_bytes;
   ss.sgn = p->mode ? -1 : 1;
   ss.M = g.M;
-  const int ACC = BN < 32 ? 32 : BN;
   const int w_bytes = (9 * ss.w_tile_bytes + 1023) & ~1023;
   // largest super-tile whose double-buffered accumulators fit TMEM and whose 2-stage slabs fit shared memory
-  for (int S = 4; S >= 1; S >>= 1) {
-    if (2 * S * ACC > 512) continue;
+  const int NW = BN >= 128 ? 2 : 4;                    // MMA warps (SlabCfg<BN>::NW): S must divide it
+  for (int S = NW; S >= 1; S >>= 1) {
     if (H % (S * R)) continue;
     const int slab = ((S * R + 2) * Wt * ss.row_bytes + 1023) & ~1023;
     for (int stages = 3; stages >= 2; --stages) {
@@ -1048,12 +1093,12 @@ static int launch_conv_slab_bn(const Gather& g, const d3fk_conv_params* p, cudaS
     if (rc) return rc;
   }
   int occ = (227 * 1024) / (smem + 1024);
-  const int tmem_cols = 2 * ss.S * (BN < 32 ? 32 : BN);
+  const int tmem_cols = SlabCfg<BN>::TMEM_COLS;
   if (occ * tmem_cols > 512) occ = 512 / tmem_cols;
   if (occ < 1) occ = 1;
   int grid = ss.total < g_num_sms * occ ? ss.total : g_num_sms * occ;
   if (g_verbose) fprintf(stderr, "[d3fk] slab<%d> mode=%d M=%d C=%d Cout=%d W=%d S=%d stages=%d smem=%d grid=%d total=%d\n", BN, g.mode, g.M, C, p->Cout, ss.W, ss.S, ss.stages, smem, grid, ss.total);
-  launch_k(conv_slab_kernel<BN, KSTEPS>, dim3(grid), dim3(TC_THREADS), (size_t)smem, s, dim3(1, 1, 1), tmA, tmB, e, ss,
+  launch_k(conv_slab_kernel<BN, KSTEPS>, dim3(grid), dim3(SlabCfg<BN>::THREADS), (size_t)smem, s, dim3(1, 1, 1), tmA, tmB, e, ss,
            make_fastdiv((uint32_t)g.Wo), make_fastdiv((uint32_t)g.Ho), g_dev_error_flag);
   count_launch();
   return check_launch("conv_slab");
@@ -1396,8 +1441,10 @@ __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr, uint32_t l
   return d;
 }
 
+constexpr int WGS_NW = 6;                      // MMA-issuing warps of wgrad_slab_kernel
+constexpr int WGS_THREADS = (5 + WGS_NW) * 32;  // warps 0-3 epilogue, 4 TMA producer, 5-10 MMA issuers
 template <int BN>
-__global__ void __launch_bounds__(TC_THREADS) wgrad_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmD,
+__global__ void __launch_bounds__(WGS_THREADS) wgrad_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmD,
                                                                 WgSlabSched ss, float* __restrict__ dw, int cin_real, int cout_real,
                                                                 int* errflag) {
   constexpr int ACC = BN < 32 ? 32 : BN;
@@ -1412,31 +1459,31 @@ __global__ void __launch_bounds__(TC_THREADS) wgrad_slab_kernel(const __grid_con
   const uint32_t acc_full = bar_base + 8u * 8;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int nacc = 3 * ss.MB;
+  const int nacc = 3 * ss.MB;                       // accumulators per K-step parity set
   uint32_t tmem_cols = 32;
-  while ((int)tmem_cols < nacc * ACC) tmem_cols <<= 1;
+  while ((int)tmem_cols < 2 * nacc * ACC) tmem_cols <<= 1;
   const bool has_work = (int)blockIdx.x < ss.total;
 
   if (tid == 0) {
     for (int s = 0; s < 4; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), WGS_NW);
     }
-    mbar_init(acc_full, 1);
+    mbar_init(acc_full, WGS_NW);
     fence_barrier_init();
   }
-  if (warp == 5 && lane == 0) {
+  if (warp == 4 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmD);
   }
-  if (warp == 4) tmem_alloc(smem_u32((const void*)tmem_ptr_slot), tmem_cols);
+  if (warp == 5) tmem_alloc(smem_u32((const void*)tmem_ptr_slot), tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = *tmem_ptr_slot;
   pdl_enter();
 
-  if (warp == 5) {
+  if (warp == 4) {
     if (lane == 0) {
       const int rows = ss.S * ss.R;
       uint32_t it = 0;
@@ -1454,36 +1501,45 @@ __global__ void __launch_bounds__(TC_THREADS) wgrad_slab_kernel(const __grid_con
       }
     }
     __syncwarp();
-  } else if (warp == 4) {
-    if (lane == 0 && has_work) {
+  } else if (warp >= 5) {
+    // MMA issuers: warp w owns kw = w % 3 and the K steps (16-pixel groups) of parity w / 3, in its own accumulators —
+    // six independent issue streams (one thread sustains only ~1 small MMA per 90 cycles).
+    if (has_work) {
+      const int w = warp - 5;
+      const int sx = w % 3, par = w / 3;
+      const uint32_t leader = lane == 0 ? 1u : 0u;
       constexpr uint32_t idesc = make_idesc(128, BN, 1, 1);
       const uint32_t img_row = (uint32_t)(ss.Wt * ss.a_row_bytes);       // M-atom stride of the A operand = one tap row (kh)
       const uint64_t a_t = make_smem_desc_mn(0, img_row, 8u * ss.a_row_bytes, ss.a_layout);
       const uint64_t b_t = make_smem_desc_mn(0, 8u * ss.b_row_bytes, 8u * ss.b_row_bytes, ss.b_layout);
       const uint32_t ahi = (uint32_t)(a_t >> 32), alo0 = (uint32_t)a_t, bhi = (uint32_t)(b_t >> 32), blo0 = (uint32_t)b_t;
-      const uint32_t a_step = (16u * ss.a_row_bytes) >> 4, b_step = (16u * ss.b_row_bytes) >> 4;   // 16 pixels per MMA
+      const uint32_t a_step2 = (32u * ss.a_row_bytes) >> 4, b_step2 = (32u * ss.b_row_bytes) >> 4;   // two K steps
+      const uint32_t a_par = (uint32_t)par * ((16u * ss.a_row_bytes) >> 4), b_par = (uint32_t)par * ((16u * ss.b_row_bytes) >> 4);
       const uint32_t mb_off = ((uint32_t)(128 / ss.C) * img_row) >> 4;   // second row block (Cin = 64): taps kh = 2, (3)
-      const int ksteps = ss.S * 8;
+      const int ksteps2 = ss.S * 4;                                       // K steps of this parity per super-tile
+      const uint32_t d_base = tmem_d + (uint32_t)((par * nacc + sx * ss.MB) * ACC);
       uint32_t it = 0;
       for (int t = blockIdx.x; t < ss.total; t += gridDim.x, ++it) {
         const int st = it % ss.stages;
         mbar_wait(full_bar(st), (it / ss.stages) & 1, errflag);
         tc_fence_after();
         const uint32_t sb = stage_base + st * ss.stage_bytes;
-        const uint32_t b_lo = blo0 | ((sb + 3u * ss.slab_bytes) >> 4);
-        for (int sx = 0; sx < 3; ++sx) {
-          const uint32_t a_lo = alo0 | ((sb + (uint32_t)(sx * ss.slab_bytes)) >> 4);
-          for (int mb = 0; mb < ss.MB; ++mb) {
-            const uint32_t d_addr = tmem_d + (uint32_t)((sx * ss.MB + mb) * ACC);
-            const uint32_t a_mb = a_lo + (uint32_t)mb * mb_off;
+        const uint32_t b_lo = (blo0 | ((sb + 3u * ss.slab_bytes) >> 4)) + b_par;
+        const uint32_t a_lo = (alo0 | ((sb + (uint32_t)(sx * ss.slab_bytes)) >> 4)) + a_par;
+        for (int mb = 0; mb < ss.MB; ++mb) {
+          const uint32_t d_addr = d_base + (uint32_t)(mb * ACC);
+          uint32_t a_cur = a_lo + (uint32_t)mb * mb_off, b_cur = b_lo;
+          umma_f16_lohi_p(d_addr, a_cur, ahi, b_cur, bhi, idesc, it ? 1u : 0u, leader);
 #pragma unroll 4
-            for (int j = 0; j < ksteps; ++j)
-              umma_f16_lohi(d_addr, a_mb + (uint32_t)j * a_step, ahi, b_lo + (uint32_t)j * b_step, bhi, idesc, (it | (uint32_t)j) ? 1u : 0u);
+          for (int j = 1; j < ksteps2; ++j) {
+            a_cur += a_step2;
+            b_cur += b_step2;
+            umma_f16_lohi_p(d_addr, a_cur, ahi, b_cur, bhi, idesc, 1u, leader);
           }
         }
-        umma_commit(empty_bar(st));
+        umma_commit_p(empty_bar(st), leader);
       }
-      umma_commit(acc_full);
+      umma_commit_p(acc_full, leader);
     }
     __syncwarp();
   } else if (has_work) {
@@ -1498,14 +1554,17 @@ __global__ void __launch_bounds__(TC_THREADS) wgrad_slab_kernel(const __grid_con
         const bool ok = kh < 3 && ci < cin_real;
 #pragma unroll 1
         for (int cc = 0; cc < BN; cc += 16) {
-          uint32_t raw[16];
-          tmem_ld16(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)((sx * ss.MB + mb) * ACC + cc), raw);
+          uint32_t raw[16], raw2[16];
+          const uint32_t ta = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)((sx * ss.MB + mb) * ACC + cc);
+          tmem_ld16(ta, raw);
+          tmem_ld16(ta + (uint32_t)(nacc * ACC), raw2);     // the odd-K-step accumulator set
           tmem_ld_wait();
           if (ok) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               const int co = cc + i;
-              if (co < cout_real) atomicAdd(dw + ((long long)co * cin_real + ci) * 9 + kh * 3 + sx, __uint_as_float(raw[i]));
+              if (co < cout_real)
+                atomicAdd(dw + ((long long)co * cin_real + ci) * 9 + kh * 3 + sx, __uint_as_float(raw[i]) + __uint_as_float(raw2[i]));
             }
           }
         }
@@ -1515,7 +1574,7 @@ __global__ void __launch_bounds__(TC_THREADS) wgrad_slab_kernel(const __grid_con
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_d, tmem_cols);
+  if (warp == 5) tmem_dealloc(tmem_d, tmem_cols);
 }
 
 static int g_use_wg_slab = 1;   // D3FK_WG_SLAB=0: never take the slab weight-gradient path
@@ -1531,7 +1590,7 @@ static int launch_wgrad_slab_bn(const Gather& g, const d3fk_wgrad_params* p, cud
   ss.b_layout = BN == 64 ? 2u : BN == 32 ? 4u : 6u;
   ss.MB = C == 64 ? 2 : 1;
   const int ACC = BN < 32 ? 32 : BN;
-  if (3 * ss.MB * ACC > 512) return 0;
+  if (2 * 3 * ss.MB * ACC > 512) return 0;
   int smem = 0;
   bool found = false;
   for (int S = 4; S >= 1 && !found; S >>= 1) {
@@ -1572,7 +1631,7 @@ static int launch_wgrad_slab_bn(const Gather& g, const d3fk_wgrad_params* p, cud
   }
   int grid = ss.total < g_num_sms ? ss.total : g_num_sms;
   if (g_verbose) fprintf(stderr, "[d3fk] wgrad_slab<%d> M=%d C=%d W=%d S=%d stages=%d smem=%d grid=%d total=%d\n", BN, g.M, C, W, ss.S, ss.stages, smem, grid, ss.total);
-  launch_k(wgrad_slab_kernel<BN>, dim3(grid), dim3(TC_THREADS), (size_t)smem, s, dim3(1, 1, 1), tmA, tmD, ss, p->dw, p->cin_real,
+  launch_k(wgrad_slab_kernel<BN>, dim3(grid), dim3(WGS_THREADS), (size_t)smem, s, dim3(1, 1, 1), tmA, tmD, ss, p->dw, p->cin_real,
            p->cout_real, g_dev_error_flag);
   count_launch();
   int rc = check_launch("wgrad_slab");
