@@ -116,15 +116,20 @@ def run_reference(args):
 
 
 def conv_only_oplist(plan):
+    """Every convolution / weight-gradient launch of one training step as a stand-alone op list (the fused conv+BN ops
+    contribute their convolution only: d3fk_convbn_params starts with the d3fk_conv_params)."""
     from denoising_diffusion_deep_fake_b200 import _lib
-    ops = [op for op in plan.fwd_ops if op.kind in (_lib.OP_CONV, _lib.OP_WGRAD)]
-    for seg in plan.bwd_segments or []:
-        ops += [op for op in seg if op.kind in (_lib.OP_CONV, _lib.OP_WGRAD)]
-    copies = []
     import ctypes
+    kinds = (_lib.OP_CONV, _lib.OP_WGRAD, _lib.OP_CONV_BN)
+    ops = [op for op in plan.fwd_ops if op.kind in kinds]
+    for seg in plan.bwd_segments or []:
+        ops += [op for op in seg if op.kind in kinds]
+    copies = []
     for op in ops:                       # detach from the plan's arrays
         c = _lib.Op()
         ctypes.memmove(ctypes.byref(c), ctypes.byref(op), ctypes.sizeof(_lib.Op))
+        if c.kind == _lib.OP_CONV_BN:
+            c.kind = _lib.OP_CONV
         copies.append(c)
     return _lib.OpList(copies), len(copies)
 

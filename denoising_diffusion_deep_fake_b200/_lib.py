@@ -86,11 +86,15 @@ class LossParams(C.Structure):
                 ("lo", f32), ("hi", f32), ("grad_scale", f32), ("_pad0", f32), ("win", f32 * 12), ("loss_out", vp)]
 
 
+class ConvBnParams(C.Structure):
+    _fields_ = [("conv", ConvParams), ("bn", BnParams), ("barrier", vp)]
+
+
 class _OpUnion(C.Union):
     _fields_ = [("conv", ConvParams), ("wgrad", WgradParams), ("pack", PackParams), ("bn", BnParams),
                 ("pool", PoolParams), ("layout", LayoutParams), ("chansum", ChansumParams),
                 ("qsample", QsampleParams), ("posterior", PosteriorParams), ("misc", MiscParams),
-                ("adam", AdamParams), ("loss", LossParams)]
+                ("adam", AdamParams), ("loss", LossParams), ("convbn", ConvBnParams)]
 
 
 class Op(C.Structure):
@@ -100,17 +104,18 @@ class Op(C.Structure):
 # op kinds (enum d3fk_op_kind)
 (OP_CONV, OP_WGRAD, OP_PACK, OP_NCHW2NHWC, OP_BN_FINALIZE, OP_BN_APPLY, OP_BN_FOLD, OP_BN_BWD_REDUCE,
  OP_BN_BWD_FINALIZE, OP_BN_BWD_APPLY, OP_MAXPOOL_FWD, OP_MAXPOOL_BWD, OP_SUMPOOL2, OP_CHANSUM, OP_QSAMPLE,
- OP_POSTERIOR, OP_MEMSET, OP_INC, OP_ADAM, OP_PACK_ALL, OP_LOSS) = range(1, 22)
+ OP_POSTERIOR, OP_MEMSET, OP_INC, OP_ADAM, OP_PACK_ALL, OP_LOSS, OP_CONV_BN) = range(1, 23)
 
 _UNION_FIELD = {OP_CONV: "conv", OP_WGRAD: "wgrad", OP_PACK: "pack", OP_NCHW2NHWC: "layout",
                 OP_BN_FINALIZE: "bn", OP_BN_APPLY: "bn", OP_BN_FOLD: "bn", OP_BN_BWD_REDUCE: "bn",
                 OP_BN_BWD_FINALIZE: "bn", OP_BN_BWD_APPLY: "bn", OP_MAXPOOL_FWD: "pool", OP_MAXPOOL_BWD: "pool",
                 OP_SUMPOOL2: "pool", OP_CHANSUM: "chansum", OP_QSAMPLE: "qsample", OP_POSTERIOR: "posterior",
                 OP_MEMSET: "misc", OP_INC: "misc", OP_ADAM: "adam", OP_PACK_ALL: "misc",
-                OP_LOSS: "loss"}
+                OP_LOSS: "loss", OP_CONV_BN: "convbn"}
 _PARAM_CLS = {"conv": ConvParams, "wgrad": WgradParams, "pack": PackParams, "bn": BnParams, "pool": PoolParams,
               "layout": LayoutParams, "chansum": ChansumParams, "qsample": QsampleParams,
-              "posterior": PosteriorParams, "misc": MiscParams, "adam": AdamParams, "loss": LossParams}
+              "posterior": PosteriorParams, "misc": MiscParams, "adam": AdamParams, "loss": LossParams,
+              "convbn": ConvBnParams}
 
 SINGLE_ENTRY = {OP_CONV: "d3fk_conv", OP_WGRAD: "d3fk_wgrad", OP_PACK: "d3fk_pack_weights",
                 OP_NCHW2NHWC: "d3fk_nchw_to_nhwc", OP_BN_FINALIZE: "d3fk_bn_finalize", OP_BN_APPLY: "d3fk_bn_apply",
@@ -118,22 +123,27 @@ SINGLE_ENTRY = {OP_CONV: "d3fk_conv", OP_WGRAD: "d3fk_wgrad", OP_PACK: "d3fk_pac
                 OP_BN_BWD_FINALIZE: "d3fk_bn_bwd_finalize", OP_BN_BWD_APPLY: "d3fk_bn_bwd_apply",
                 OP_MAXPOOL_FWD: "d3fk_maxpool_fwd", OP_MAXPOOL_BWD: "d3fk_maxpool_bwd", OP_SUMPOOL2: "d3fk_sumpool2",
                 OP_CHANSUM: "d3fk_chansum", OP_QSAMPLE: "d3fk_q_sample", OP_POSTERIOR: "d3fk_posterior_step",
-                OP_ADAM: "d3fk_adam", OP_LOSS: "d3fk_mse_ssim_loss"}
+                OP_ADAM: "d3fk_adam", OP_LOSS: "d3fk_mse_ssim_loss", OP_CONV_BN: "d3fk_conv_bn"}
 EXPORTS = ["d3fk_version", "d3fk_sizeof_op", "d3fk_init", "d3fk_last_error", "d3fk_device_error_flag", "d3fk_run",
-           "d3fk_run_profile", "d3fk_launch_count"] + sorted(set(SINGLE_ENTRY.values()))
+           "d3fk_run_nojoin", "d3fk_side_stream_join", "d3fk_run_profile", "d3fk_launch_count"] + sorted(set(SINGLE_ENTRY.values()))
+
+
+def _set_fields(struct, fields):
+    valid = {f[0] for f in struct._fields_}
+    for k, v in fields.items():
+        if k not in valid:
+            raise KeyError(f"{type(struct).__name__} has no field {k!r}")
+        if isinstance(v, dict):
+            _set_fields(getattr(struct, k), v)      # nested POD (d3fk_convbn_params.conv / .bn)
+        else:
+            setattr(struct, k, v)
 
 
 def make_op(kind, **fields):
-    """Build one d3fk_op record.  Pointer fields take ints (tensor.data_ptr()) or None."""
+    """Build one d3fk_op record.  Pointer fields take ints (tensor.data_ptr()) or None; nested structs take dicts."""
     op = Op()
     op.kind = kind
-    name = _UNION_FIELD[kind]
-    params = getattr(op.u, name)
-    valid = {f[0] for f in _PARAM_CLS[name]._fields_}
-    for k, v in fields.items():
-        if k not in valid:
-            raise KeyError(f"{name} params have no field {k!r}")
-        setattr(params, k, v)
+    _set_fields(getattr(op.u, _UNION_FIELD[kind]), fields)
     return op
 
 
@@ -161,6 +171,8 @@ def load():
     lib.d3fk_last_error.restype = C.c_char_p
     lib.d3fk_launch_count.restype = C.c_int64
     lib.d3fk_run.argtypes = [C.POINTER(Op), C.c_int, vp]
+    lib.d3fk_run_nojoin.argtypes = [C.POINTER(Op), C.c_int, vp]
+    lib.d3fk_side_stream_join.argtypes = [vp]
     lib.d3fk_init.argtypes = [C.c_int]
     lib.d3fk_run_profile.argtypes = [C.POINTER(Op), C.c_int, vp, C.POINTER(C.c_float)]
     for kind, name in SINGLE_ENTRY.items():
@@ -195,8 +207,12 @@ class OpList:
         self.n = len(ops)
         self.array = (Op * max(self.n, 1))(*ops)
 
-    def run(self, stream_ptr):
-        check(_lib.d3fk_run(self.array, self.n, stream_ptr))
+    def run(self, stream_ptr, join=True):
+        """join=False: weight-gradient ops stay on libd3fk's side stream; call side_stream_join() before reading them."""
+        if join:
+            check(_lib.d3fk_run(self.array, self.n, stream_ptr))
+        else:
+            check(_lib.d3fk_run_nojoin(self.array, self.n, stream_ptr))
 
     def profile(self, stream_ptr):
         """Per-op device milliseconds (CUDA events around every op; synchronises)."""
@@ -209,6 +225,11 @@ class OpList:
 
     def __iter__(self):
         return (self.array[i] for i in range(self.n))
+
+
+def side_stream_join(stream_ptr):
+    """Make `stream_ptr` wait for every weight-gradient kernel forked so far."""
+    check(load().d3fk_side_stream_join(stream_ptr))
 
 
 def run_single(op, stream_ptr):

@@ -34,6 +34,7 @@ int launch_conv_ffma(const d3fk_conv_params*, cudaStream_t);
 int launch_wgrad_ffma(const d3fk_wgrad_params*, cudaStream_t);
 int launch_conv_tc(const d3fk_conv_params*, cudaStream_t);
 int launch_wgrad_tc(const d3fk_wgrad_params*, cudaStream_t);
+int launch_conv_bn_tc(const d3fk_convbn_params*, cudaStream_t);
 int launch_pack(const d3fk_pack_params*, cudaStream_t);
 int launch_nchw_to_nhwc(const d3fk_layout_params*, cudaStream_t);
 int launch_bn_finalize(const d3fk_bn_params*, cudaStream_t);
@@ -71,8 +72,15 @@ static int wgrad_dispatch(const d3fk_wgrad_params* p, cudaStream_t s) {
   return set_error(D3FK_ERR_ARG, "wgrad: bad dtype %d", p->dtype);
 }
 
+static int convbn_dispatch(const d3fk_convbn_params* p, cudaStream_t s) {
+  if (p->conv.dtype == D3FK_BF16) return launch_conv_bn_tc(p, s);
+  int rc = conv_dispatch(&p->conv, s);      // fp32 parity mode: the two kernels
+  return rc ? rc : launch_bn_apply(&p->bn, s);
+}
+
 static int run_one(const d3fk_op* op, cudaStream_t s) {
   switch (op->kind) {
+    case D3FK_OP_CONV_BN: return convbn_dispatch(&op->u.convbn, s);
     case D3FK_OP_CONV: return conv_dispatch(&op->u.conv, s);
     case D3FK_OP_WGRAD: return wgrad_dispatch(&op->u.wgrad, s);
     case D3FK_OP_PACK: return launch_pack(&op->u.pack, s);
@@ -108,7 +116,7 @@ using namespace d3fk;
 
 extern "C" {
 
-int d3fk_version(void) { return 1; }
+int d3fk_version(void) { return 2; }
 int d3fk_sizeof_op(void) { return (int)sizeof(d3fk_op); }
 const char* d3fk_last_error(void) { return g_last_error; }
 int64_t d3fk_launch_count(void) { return g_launch_count; }
@@ -152,6 +160,8 @@ static cudaStream_t g_side_stream = nullptr;
 static cudaEvent_t g_fork_events[64];
 static cudaEvent_t g_join_event = nullptr;
 static int g_n_fork_events = 0;
+static unsigned g_fork_cursor = 0;
+static bool g_side_pending = false;
 static int g_skip_wgrad = 0;
 static int g_fork_wgrad = 1;   // D3FK_FORK_WGRAD=0: everything in stream order
 
@@ -167,17 +177,16 @@ static int ensure_side_stream() {
   return D3FK_OK;
 }
 
-int d3fk_run(const d3fk_op* ops, int n_ops, d3fk_stream stream) {
+static int run_list(const d3fk_op* ops, int n_ops, cudaStream_t s, bool join) {
   int rc = require_init();
   if (rc) return rc;
   rc = ensure_side_stream();
   if (rc) return rc;
-  cudaStream_t s = (cudaStream_t)stream;
   int forks = 0;
   for (int i = 0; i < n_ops; ++i) {
     if (ops[i].kind == D3FK_OP_WGRAD && g_skip_wgrad) continue;   // timing experiment only (D3FK_SKIP_WGRAD=1)
     if (ops[i].kind == D3FK_OP_WGRAD && g_fork_wgrad && n_ops > 1) {
-      cudaEvent_t ev = g_fork_events[forks % g_n_fork_events];
+      cudaEvent_t ev = g_fork_events[g_fork_cursor++ % g_n_fork_events];
       cudaError_t e = cudaEventRecord(ev, s);
       if (e == cudaSuccess) e = cudaStreamWaitEvent(g_side_stream, ev, 0);
       if (e != cudaSuccess) return set_error(D3FK_ERR_CUDA, "fork: %s", cudaGetErrorString(e));
@@ -193,11 +202,23 @@ int d3fk_run(const d3fk_op* ops, int n_ops, d3fk_stream stream) {
       return set_error(rc, "op %d (kind %d): %s", i, ops[i].kind, tmp);
     }
   }
-  if (forks) {
-    cudaError_t e = cudaEventRecord(g_join_event, g_side_stream);
-    if (e == cudaSuccess) e = cudaStreamWaitEvent(s, g_join_event, 0);
-    if (e != cudaSuccess) return set_error(D3FK_ERR_CUDA, "join: %s", cudaGetErrorString(e));
-  }
+  if (forks) g_side_pending = true;
+  if (join && g_side_pending) return d3fk_side_stream_join((d3fk_stream)s);
+  return D3FK_OK;
+}
+
+int d3fk_run(const d3fk_op* ops, int n_ops, d3fk_stream stream) { return run_list(ops, n_ops, (cudaStream_t)stream, true); }
+
+/* as d3fk_run, but weight-gradient ops forked onto the side stream are NOT joined: the caller joins once, with
+ * d3fk_side_stream_join, before anything consumes the weight gradients (optimizer step, gradient allreduce) */
+int d3fk_run_nojoin(const d3fk_op* ops, int n_ops, d3fk_stream stream) { return run_list(ops, n_ops, (cudaStream_t)stream, false); }
+
+int d3fk_side_stream_join(d3fk_stream stream) {
+  if (!g_side_stream) return D3FK_OK;
+  cudaError_t e = cudaEventRecord(g_join_event, g_side_stream);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent((cudaStream_t)stream, g_join_event, 0);
+  if (e != cudaSuccess) return set_error(D3FK_ERR_CUDA, "join: %s", cudaGetErrorString(e));
+  g_side_pending = false;
   return D3FK_OK;
 }
 
@@ -230,6 +251,7 @@ int d3fk_run_profile(const d3fk_op* ops, int n_ops, d3fk_stream stream, float* m
   }
 SINGLE(d3fk_conv, d3fk_conv_params, conv_dispatch)
 SINGLE(d3fk_wgrad, d3fk_wgrad_params, wgrad_dispatch)
+SINGLE(d3fk_conv_bn, d3fk_convbn_params, convbn_dispatch)
 SINGLE(d3fk_pack_weights, d3fk_pack_params, launch_pack)
 SINGLE(d3fk_nchw_to_nhwc, d3fk_layout_params, launch_nchw_to_nhwc)
 SINGLE(d3fk_bn_finalize, d3fk_bn_params, launch_bn_finalize)

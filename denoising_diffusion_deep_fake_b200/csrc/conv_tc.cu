@@ -330,6 +330,39 @@ __device__ __forceinline__ void epilogue_chunk(float (&f)[CW], const EpiTC& e, l
   }
 }
 
+// Fused train-mode BatchNorm (forward): when every output tile of the layer is resident at once (one tile per CTA, the
+// accumulator parked in TMEM — or, for split-K clusters, the reduced slice in shared memory), the conv kernel itself
+// finalises the batch statistics behind a grid-wide barrier and applies normalise + residual + ReLU from the fp32
+// accumulator: raw conv output (kept for the backward pass) and activation are both written by this one kernel and the
+// separate BN kernel (launch, prologue, a re-read of the raw tensor) disappears.
+struct FuseBN {
+  const float* gamma; const float* beta;
+  float* mean; float* invstd; float* running_mean; float* running_var; long long* nbt;
+  bf16* act; const bf16* res;
+  unsigned* barrier;         // zeroed by the forward's statistics memset
+  long long count;
+  int ldact, ldr, relu;
+  float eps, momentum;
+};
+
+// grid-wide barrier for a co-resident grid (called by ONE thread per CTA, after its CTA's global writes / atomics)
+__device__ __forceinline__ void grid_barrier_arrive_wait(unsigned* counter, unsigned expected, int* errflag) {
+  __threadfence();
+  atomicAdd(counter, 1u);
+  const long long t0 = clock64();
+  while (true) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+    if (v >= expected) break;
+    if (clock64() - t0 > 4000000000ll) {   // ~2 s: the grid was not co-resident
+      atomicExch(errflag, 2);
+      break;
+    }
+    __nanosleep(64);
+  }
+  __threadfence();
+}
+
 // PATH 0 (LINEAR): one source, no upsample, forward gather or stride-1 transposed gather — the tap
 //   offset is the same for every row, so a row costs two compares, one 64-bit add and the cp.async.
 // PATH 1 (GENERIC): nearest-2x upsample + channel concat (decoder conv1) and stride-2 transposed gather.
@@ -337,10 +370,10 @@ __device__ __forceinline__ void epilogue_chunk(float (&f)[CW], const EpiTC& e, l
 //   is the NHWC box {64 channels, bw, bh, bn} shifted by the tap offset, loaded by ONE cp.async.bulk.tensor.4d with
 //   hardware zero fill for the padding halo — no per-thread address arithmetic at all.
 // The weight tile is always a TMA 2-D box {64, BN} of the packed [Cout][K] matrix (OOB rows / K tail zero filled).
-template <int BN, int PATH>
+template <int BN, int PATH, int FUSE>
 __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(Gather g, FastDiv dWo, FastDiv dHo, const __grid_constant__ CUtensorMap tmA,
                                                              const __grid_constant__ CUtensorMap tmB, EpiTC e, TileSched ts,
-                                                             int* errflag) {
+                                                             FuseBN fb, int* errflag) {
   using Cfg = ConvCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int CW = BN >= 32 ? 32 : 16;
@@ -401,6 +434,62 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(Gather g, FastDiv d
     asm volatile("bar.sync 1, 128;" ::: "memory");
     for (int i = tid; i < 8 * BN; i += 128) s_stat[i] = 0.f;
     asm volatile("bar.sync 1, 128;" ::: "memory");
+  };
+
+  // FUSE: after this CTA's statistics are flushed — grid barrier, then scale / shift of the tile's BN channels into s_stat
+  // (free again after the flush): s_stat[c] = scale, s_stat[BN + c] = shift.  The CTA with m tile 0 (and k slice 0)
+  // publishes mean / invstd / running statistics of its n tile.
+  auto fuse_finalize = [&](int nt, bool publisher) {
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (tid == 0) grid_barrier_arrive_wait(fb.barrier, gridDim.x, errflag);
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    const int ch = nt * BN + tid;
+    if (tid < BN && ch < e.Cout) {
+      const double n = (double)fb.count;
+      const double mean = __ldcg(e.stats + ch) / n;
+      double var = __ldcg(e.stats + e.Cout + ch) / n - mean * mean;
+      if (var < 0) var = 0;
+      const double invstd = rsqrt(var + (double)fb.eps);
+      const double gm = (double)__ldg(fb.gamma + ch), bt = (double)__ldg(fb.beta + ch);
+      s_stat[tid] = (float)(gm * invstd);
+      s_stat[BN + tid] = (float)(bt - mean * gm * invstd);
+      if (publisher) {
+        fb.mean[ch] = (float)mean;
+        fb.invstd[ch] = (float)invstd;
+        if (fb.running_mean) {
+          const double unbiased = n > 1 ? var * n / (n - 1) : var;
+          fb.running_mean[ch] = (float)((1.0 - fb.momentum) * fb.running_mean[ch] + fb.momentum * mean);
+          fb.running_var[ch] = (float)((1.0 - fb.momentum) * fb.running_var[ch] + fb.momentum * unbiased);
+        }
+        if (ch == 0 && fb.nbt) *fb.nbt += 1;
+      }
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+  };
+  // FUSE: activation of CWF accumulator columns [ct, ct + CWF) (tile-relative) of output row m
+  auto fuse_apply = [&](float* f, int ncol, long long m, bool row_ok, int nt, int ct) {
+    if (!row_ok) return;
+    const int cbase = nt * BN + ct;
+    for (int q = 0; q < ncol / 8; ++q) {
+      float y[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) y[i] = fmaf(f[q * 8 + i], s_stat[ct + q * 8 + i], s_stat[BN + ct + q * 8 + i]);
+      if (fb.res) {
+        const uint4 rr = __ldg(reinterpret_cast<const uint4*>(fb.res + m * fb.ldr + cbase + q * 8));
+        const bf16* rb16 = reinterpret_cast<const bf16*>(&rr);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) y[i] += __bfloat162float(rb16[i]);
+      }
+      if (fb.relu) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) y[i] = fmaxf(y[i], 0.f);
+      }
+      uint4 o;
+      __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o2[i] = __floats2bfloat162_rn(y[2 * i], y[2 * i + 1]);
+      *reinterpret_cast<uint4*>(fb.act + m * fb.ldact + cbase + q * 8) = o;
+    }
   };
 
   int my_mt = 0, my_nt = 0, my_ks = 0;   // cluster mode: the single tile of this CTA
@@ -565,6 +654,23 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(Gather g, FastDiv d
         epilogue_chunk<CW>(f, e, (long long)m, row_ok, n0 + cc, on, oh, ow, do_stats, s_stat + warp * 2 * BN + cc,
                            s_stat + warp * 2 * BN + BN + cc, lane);
       }
+      if (FUSE == 1) {
+        // one tile per CTA (the launcher guarantees it): statistics -> grid barrier -> activation from the parked accumulator
+        flush_stats(nt);
+        cur_nt = -1;
+        fuse_finalize(nt, mt == 0);
+#pragma unroll 1
+        for (int cc = 0; cc < BN; cc += CW) {
+          uint32_t raw[CW];
+          const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + abuf * Cfg::ACC_COLS + (uint32_t)cc;
+          if (CW == 32) tmem_ld32(taddr, raw); else tmem_ld16(taddr, raw);
+          tmem_ld_wait();
+          float f[CW];
+#pragma unroll
+          for (int i = 0; i < CW; ++i) f[i] = __uint_as_float(raw[i]);
+          fuse_apply(f, CW, (long long)m, row_ok, nt, cc);
+        }
+      }
       tc_fence_before();   // this tile's TMEM reads are done: hand the accumulator buffer back to the MMA issuer
       mbar_arrive(acc_empty_bar(abuf));
     }
@@ -655,6 +761,23 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(Gather g, FastDiv d
                            s_stat + warp * 2 * BN + BN + ct, lane);
       }
       if (do_stats) flush_stats(my_nt);
+      if (FUSE == 1) {
+        fuse_finalize(my_nt, my_mt == 0 && rank == 0);
+#pragma unroll 1
+        for (int ch = 0; ch < SL; ch += 16) {
+          float f[16];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int r = 0; r < KS; ++r) {
+              const float4 v = ld_shared_f4(recv + (uint32_t)(((r * sl4 + (ch >> 2) + q) * 128 + row) * 16));
+              a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+            }
+            f[4 * q] = a.x; f[4 * q + 1] = a.y; f[4 * q + 2] = a.z; f[4 * q + 3] = a.w;
+          }
+          fuse_apply(f, 16, (long long)m, row_ok, my_nt, cslice + ch);
+        }
+      }
     }
   }
 
@@ -679,6 +802,12 @@ static int cluster_capacity(int cl, int ctas_per_sm) {
   const int per_sm = cl >= 8 ? 120 : cl >= 4 ? 138 : g_num_sms;   // usable SMs (of 148) for this cluster size
   return per_sm * ctas_per_sm;
 }
+
+// Fusion request of launch_conv_bn (below): set around a launch_conv_tc call; the launcher takes it when the layer
+// qualifies (BN == 128 tiles, one tile per co-resident CTA) and reports back through `taken`.
+struct FuseReq { const d3fk_bn_params* bn; unsigned* barrier; bool taken; };
+static thread_local FuseReq* t_fuse = nullptr;
+static int g_fuse_bn = 1;   // D3FK_FUSE_BN=0: always run BatchNorm as its own kernel
 
 template <int BN, int PATH>
 static int launch_conv_tc_bn(const Gather& g, const d3fk_conv_params* p, cudaStream_t s, const TileSched& box) {
@@ -726,15 +855,30 @@ static int launch_conv_tc_bn(const Gather& g, const d3fk_conv_params* p, cudaStr
     int rc = get_tensor_map(&tmA, p->src0, 4, dims, strides, bx, 128);
     if (rc) return rc;
   }
-  if (g_verbose) fprintf(stderr, "[d3fk] conv<%d,%d> mode=%d M=%d K=%d Cout=%d tiles=%d KS=%d kbps=%d grid=%d\n", BN, PATH, g.mode, g.M, g.K, p->Cout, tiles, ts.KS, ts.kb_per_split, grid);
-  if (ts.KS > 1) {
-    cudaError_t le = launch_k(conv_tc_kernel<BN, PATH>, dim3(grid), dim3(TC_THREADS), ConvCfg<BN>::SMEM, s, dim3(ts.KS, 1, 1), g,
-                                    make_fastdiv((uint32_t)g.Wo), make_fastdiv((uint32_t)g.Ho), tmA, tmB, e, ts, g_dev_error_flag);
-    if (le != cudaSuccess) return set_error(D3FK_ERR_CUDA, "conv_tc cluster launch: %s", cudaGetErrorString(le));
-  } else {
-    launch_k(conv_tc_kernel<BN, PATH>, dim3(grid), dim3(TC_THREADS), ConvCfg<BN>::SMEM, s, dim3(1, 1, 1), g, make_fastdiv((uint32_t)g.Wo), make_fastdiv((uint32_t)g.Ho),
-                                                                      tmA, tmB, e, ts, g_dev_error_flag);
+  // fused BatchNorm: every tile resident at once (grid == tiles * KS <= co-resident capacity), 128-wide tiles only
+  FuseBN fb;
+  memset(&fb, 0, sizeof(fb));
+  bool fuse = false;
+  if (BN == 128 && t_fuse && g_fuse_bn && p->stats && !p->scale && !p->shift && !p->res && !p->relu && !p->out_nchw && p->mode == 0 &&
+      p->Cout % BN == 0 && ts.total <= cluster_capacity(ts.KS, 2)) {
+    const d3fk_bn_params* b = t_fuse->bn;
+    fb.gamma = b->gamma; fb.beta = b->beta; fb.mean = b->mean; fb.invstd = b->invstd;
+    fb.running_mean = b->running_mean; fb.running_var = b->running_var; fb.nbt = (long long*)b->num_batches_tracked;
+    fb.act = (bf16*)b->y; fb.res = (const bf16*)b->res; fb.barrier = t_fuse->barrier; fb.count = b->count;
+    fb.ldact = b->ldy; fb.ldr = b->ldr; fb.relu = b->relu; fb.eps = b->eps; fb.momentum = b->momentum;
+    fuse = true;
+    grid = ts.total;
+    t_fuse->taken = true;
   }
+  if (g_verbose) fprintf(stderr, "[d3fk] conv<%d,%d> mode=%d M=%d K=%d Cout=%d tiles=%d KS=%d kbps=%d grid=%d fuse=%d\n", BN, PATH, g.mode, g.M, g.K, p->Cout, tiles, ts.KS, ts.kb_per_split, grid, (int)fuse);
+  cudaError_t le;
+  if (BN == 128 && fuse)
+    le = launch_k(conv_tc_kernel<BN, PATH, (BN == 128 ? 1 : 0)>, dim3(grid), dim3(TC_THREADS), ConvCfg<BN>::SMEM, s, dim3(ts.KS, 1, 1), g,
+                  make_fastdiv((uint32_t)g.Wo), make_fastdiv((uint32_t)g.Ho), tmA, tmB, e, ts, fb, g_dev_error_flag);
+  else
+    le = launch_k(conv_tc_kernel<BN, PATH, 0>, dim3(grid), dim3(TC_THREADS), ConvCfg<BN>::SMEM, s, dim3(ts.KS, 1, 1), g,
+                  make_fastdiv((uint32_t)g.Wo), make_fastdiv((uint32_t)g.Ho), tmA, tmB, e, ts, fb, g_dev_error_flag);
+  if (le != cudaSuccess) return set_error(D3FK_ERR_CUDA, "conv_tc launch: %s", cudaGetErrorString(le));
   count_launch();
   return check_launch("conv_tc");
 }
@@ -1139,6 +1283,18 @@ int launch_conv_tc(const d3fk_conv_params* p, cudaStream_t s) {
   if (tma_box(g, p, box)) return launch_conv_tc_path<2>(g, p, s, box);
   const bool linear = p->c1 == 0 && p->up0 == 0 && (p->mode == 0 || p->stride == 1);
   return linear ? launch_conv_tc_path<0>(g, p, s, box) : launch_conv_tc_path<1>(g, p, s, box);
+}
+
+// conv + train-mode BatchNorm (+residual) + ReLU as one op: fused into the conv kernel when the layer qualifies, otherwise
+// the two kernels back to back (same results up to the rounding of the raw tensor the unfused BN reads back).
+int launch_bn_apply(const d3fk_bn_params* p, cudaStream_t s);
+int launch_conv_bn_tc(const d3fk_convbn_params* p, cudaStream_t s) {
+  FuseReq req{&p->bn, (unsigned*)p->barrier, false};
+  t_fuse = p->barrier ? &req : nullptr;
+  int rc = launch_conv_tc(&p->conv, s);
+  t_fuse = nullptr;
+  if (rc || req.taken) return rc;
+  return launch_bn_apply(&p->bn, s);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1681,6 +1837,7 @@ int tc_init() {
   if (const char* v = getenv("D3FK_CLUSTER")) g_max_cluster = atoi(v);
   if (const char* v = getenv("D3FK_VERBOSE")) g_verbose = atoi(v);
   if (const char* v = getenv("D3FK_SLAB")) g_use_slab = atoi(v);
+  if (const char* v = getenv("D3FK_FUSE_BN")) g_fuse_bn = atoi(v);
   if (const char* v = getenv("D3FK_WG_SLAB")) g_use_wg_slab = atoi(v);
   if (const char* v = getenv("D3FK_WG_OCC")) g_wg_ctas_per_sm = atoi(v);
   if (const char* v = getenv("D3FK_WG_CAP")) g_wg_cap = atoi(v);
@@ -1688,18 +1845,21 @@ int tc_init() {
 #define SET_SMEM(k, bytes)                                                                          \
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);               \
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  SET_SMEM((conv_tc_kernel<16, 0>), ConvCfg<16>::SMEM)
-  SET_SMEM((conv_tc_kernel<32, 0>), ConvCfg<32>::SMEM)
-  SET_SMEM((conv_tc_kernel<64, 0>), ConvCfg<64>::SMEM)
-  SET_SMEM((conv_tc_kernel<128, 0>), ConvCfg<128>::SMEM)
-  SET_SMEM((conv_tc_kernel<16, 1>), ConvCfg<16>::SMEM)
-  SET_SMEM((conv_tc_kernel<32, 1>), ConvCfg<32>::SMEM)
-  SET_SMEM((conv_tc_kernel<64, 1>), ConvCfg<64>::SMEM)
-  SET_SMEM((conv_tc_kernel<128, 1>), ConvCfg<128>::SMEM)
-  SET_SMEM((conv_tc_kernel<16, 2>), ConvCfg<16>::SMEM)
-  SET_SMEM((conv_tc_kernel<32, 2>), ConvCfg<32>::SMEM)
-  SET_SMEM((conv_tc_kernel<64, 2>), ConvCfg<64>::SMEM)
-  SET_SMEM((conv_tc_kernel<128, 2>), ConvCfg<128>::SMEM)
+  SET_SMEM((conv_tc_kernel<16, 0, 0>), ConvCfg<16>::SMEM)
+  SET_SMEM((conv_tc_kernel<32, 0, 0>), ConvCfg<32>::SMEM)
+  SET_SMEM((conv_tc_kernel<64, 0, 0>), ConvCfg<64>::SMEM)
+  SET_SMEM((conv_tc_kernel<128, 0, 0>), ConvCfg<128>::SMEM)
+  SET_SMEM((conv_tc_kernel<16, 1, 0>), ConvCfg<16>::SMEM)
+  SET_SMEM((conv_tc_kernel<32, 1, 0>), ConvCfg<32>::SMEM)
+  SET_SMEM((conv_tc_kernel<64, 1, 0>), ConvCfg<64>::SMEM)
+  SET_SMEM((conv_tc_kernel<128, 1, 0>), ConvCfg<128>::SMEM)
+  SET_SMEM((conv_tc_kernel<16, 2, 0>), ConvCfg<16>::SMEM)
+  SET_SMEM((conv_tc_kernel<32, 2, 0>), ConvCfg<32>::SMEM)
+  SET_SMEM((conv_tc_kernel<64, 2, 0>), ConvCfg<64>::SMEM)
+  SET_SMEM((conv_tc_kernel<128, 2, 0>), ConvCfg<128>::SMEM)
+  SET_SMEM((conv_tc_kernel<128, 0, 1>), ConvCfg<128>::SMEM)
+  SET_SMEM((conv_tc_kernel<128, 1, 1>), ConvCfg<128>::SMEM)
+  SET_SMEM((conv_tc_kernel<128, 2, 1>), ConvCfg<128>::SMEM)
   SET_SMEM((conv_slab_kernel<16, 1>), SLAB_MAX_SMEM)
   SET_SMEM((conv_slab_kernel<16, 2>), SLAB_MAX_SMEM)
   SET_SMEM((conv_slab_kernel<16, 4>), SLAB_MAX_SMEM)

@@ -158,11 +158,13 @@ class UnetPlan:
         bns = [c for c in self.convs if c.bn]
         total = sum(c.cout for c in bns)
         self.bn_f32 = self._new((8, total), torch.float32)      # scale, shift, mean, invstd, coef[3], spare
-        self.stats = self._new((2, 2 * total), torch.float64)   # [fwd|bwd][per-BN (sum, sumsq)]
-        self.bn_off = {}
+        # [fwd|bwd][per-BN (sum, sumsq) ... | one 8-byte slot per BN: grid-barrier counter of the fused conv+BN kernel]
+        self.stats = self._new((2, 2 * total + len(bns)), torch.float64)
+        self.bn_off, self.bn_barrier = {}, {}
         off = 0
-        for c in bns:
+        for i, c in enumerate(bns):
             self.bn_off[c.bn] = off
+            self.bn_barrier[c.bn] = self.stats[0].data_ptr() + 8 * (2 * total + i)
             off += c.cout
 
     def _bnptr(self, bn, row, C):
@@ -229,8 +231,8 @@ class UnetPlan:
         return ops
 
     # ------------------------------------------------------------------ forward
-    def _conv_op(self, c, src0, src1=None, up0=0, out=None, relu=0, res=None, stats=False, out_nchw=None,
-                 affine=False):
+    def _conv_fields(self, c, src0, src1=None, up0=0, out=None, relu=0, res=None, stats=False, out_nchw=None,
+                     affine=False):
         Hi = src0.H * (2 if up0 else 1)
         Wi = src0.W * (2 if up0 else 1)
         Ho = (Hi + 2 * c.pad - c.k) // c.stride + 1
@@ -252,7 +254,12 @@ class UnetPlan:
             f.update(stats=self.stats[0].data_ptr() + 8 * 2 * self.bn_off[c.bn])
         if affine:
             f.update(scale=self._bnptr(c.bn, 0, c.cout), shift=self._bnptr(c.bn, 1, c.cout))
-        return make_op(_lib.OP_CONV, **f), Ho, Wo
+        return f
+
+    def _conv_op(self, c, src0, src1=None, up0=0, out=None, relu=0, res=None, stats=False, out_nchw=None,
+                 affine=False):
+        f = self._conv_fields(c, src0, src1, up0, out, relu, res, stats, out_nchw, affine)
+        return make_op(_lib.OP_CONV, **f), f["Ho"], f["Wo"]
 
     def _conv_bn_act(self, ops, c, src0, src1=None, up0=0, relu=1, res=None):
         """conv -> BN -> (+res) -> ReLU.  Train: raw conv output + batch statistics in the conv epilogue,
@@ -269,14 +276,14 @@ class UnetPlan:
             return act
         raw = T(self, self.B, Ho, Wo, c.cout)
         self.keep.append(raw.t)
-        op, _, _ = self._conv_op(c, src0, src1, up0, out=raw, stats=True)
-        ops.append(op)
+        conv_fields = self._conv_fields(c, src0, src1, up0, out=raw, stats=True)
         bn = self._bn_common(c)
         bn.update(count=raw.count, relu=relu, x=raw.ptr, ldx=raw.ld, y=act.ptr, ldy=act.ld)
         if res is not None:
             bn.update(res=res.ptr, ldr=res.ld)
         fwd_fields = {k: v for k, v in bn.items() if k not in ("bstats", "coef")}
-        ops.append(make_op(_lib.OP_BN_APPLY, **fwd_fields))   # finalises the batch statistics itself (stats set)
+        # ONE op: conv + BN finalize + normalise (+residual) + ReLU — fused into the conv kernel where the layer qualifies
+        ops.append(make_op(_lib.OP_CONV_BN, conv=conv_fields, bn=fwd_fields, barrier=self.bn_barrier[c.bn]))
         self.saved[c.name] = dict(src0=src0, src1=src1, up0=up0, raw=raw, act=act, relu=relu, bn=bn, res=res)
         return act
 
@@ -483,8 +490,12 @@ class UnetPlan:
         self.fwd_ops.run(stream)
 
     def run_backward(self, dy, stream, after_segment=None):
+        """Segments run back to back on `stream`; their weight-gradient kernels stay on libd3fk's side stream (no join
+        between segments, so the big decoder wgrads overlap the latency-bound encoder segments).  `after_segment(i)`
+        (data-parallel hook) must order its consumer behind BOTH streams; the final join orders `stream` itself."""
         op_params(self.bwd_segments[0].array[self.dy_op_index]).src = dy.data_ptr()
         for i, seg in enumerate(self.bwd_segments):
-            seg.run(stream)
+            seg.run(stream, join=False)
             if after_segment is not None:
                 after_segment(i)
+        _lib.side_stream_join(stream)

@@ -84,7 +84,8 @@ class GradAllReduce:
         cur = torch.cuda.current_stream()
         ev = torch.cuda.Event()
         ev.record(cur)
-        self.comm.wait_event(ev)
+        self.comm.wait_event(ev)                           # BN / bias gradients: main stream
+        _lib.side_stream_join(self.comm.cuda_stream)       # weight gradients: libd3fk's side stream
         s, e = self.buckets[i]
         with torch.cuda.stream(self.comm):
             allreduce_bucket_(self.model._grad_arena, s, e, self.group)

@@ -107,6 +107,17 @@ typedef struct d3fk_bn_params {
   float* coef;                          /* [3][C] scratch written by bn_bwd_finalize */
 } d3fk_bn_params;
 
+/* ---- convolution + train-mode BatchNorm (+residual) + ReLU as ONE op (the forward of every conv->BN->ReLU of the U-Net).
+ * Semantics = d3fk_conv(conv) followed by d3fk_bn_apply(bn) with bn.x == conv.out and bn.stats == conv.stats.  When every
+ * output tile of the layer is resident at once the library fuses the two: the conv kernel finalises the statistics behind a
+ * grid-wide barrier (`barrier`: a zeroed uint32 the caller clears with the statistics) and writes raw output and activation
+ * itself.  barrier == NULL forces the two-kernel form. */
+typedef struct d3fk_convbn_params {
+  d3fk_conv_params conv;
+  d3fk_bn_params bn;
+  uint32_t* barrier;
+} d3fk_convbn_params;
+
 /* ---- MaxPool2d(3,2,1) fwd/bwd, 2x2 sum pool (= backward of nearest 2x upsample), NCHW fp32 -> NHWC */
 typedef struct d3fk_pool_params {
   int32_t dtype, B, H, W, C, accumulate;  /* H,W: input extent of the forward op */
@@ -182,7 +193,8 @@ enum d3fk_op_kind {
   D3FK_OP_CHANSUM = 14, D3FK_OP_QSAMPLE = 15, D3FK_OP_POSTERIOR = 16,
   D3FK_OP_MEMSET = 17, D3FK_OP_INC = 18, D3FK_OP_ADAM = 19,
   D3FK_OP_PACK_ALL = 20, /* misc: p0 = device array of d3fk_pack_params, n = (blocks << 17) | (count << 1) | is_bf16 */
-  D3FK_OP_LOSS = 21
+  D3FK_OP_LOSS = 21,
+  D3FK_OP_CONV_BN = 22
 };
 
 typedef struct d3fk_op {
@@ -191,7 +203,7 @@ typedef struct d3fk_op {
     d3fk_conv_params conv; d3fk_wgrad_params wgrad; d3fk_pack_params pack; d3fk_bn_params bn;
     d3fk_pool_params pool; d3fk_layout_params layout; d3fk_chansum_params chansum;
     d3fk_qsample_params qsample; d3fk_posterior_params posterior; d3fk_misc_params misc;
-    d3fk_adam_params adam; d3fk_loss_params loss;
+    d3fk_adam_params adam; d3fk_loss_params loss; d3fk_convbn_params convbn;
   } u;
 } d3fk_op;
 
@@ -205,6 +217,13 @@ int d3fk_device_error_flag(void);         /* non-zero if a kernel hit its barrie
 /* run a recorded op list on `stream` (the hot path: one call per U-Net forward / backward) */
 int d3fk_run(const d3fk_op* ops, int n_ops, d3fk_stream stream);
 
+/* Weight-gradient ops (D3FK_OP_WGRAD) of a list are forked onto an internal side stream (they are off the backward
+ * critical path); d3fk_run joins that stream back into `stream` before it returns to the caller.  d3fk_run_nojoin leaves
+ * the side stream running — backward segments can then overlap the weight gradients of earlier segments — and the caller
+ * joins ONCE with d3fk_side_stream_join(stream) before anything reads the weight gradients (optimizer, allreduce). */
+int d3fk_run_nojoin(const d3fk_op* ops, int n_ops, d3fk_stream stream);
+int d3fk_side_stream_join(d3fk_stream stream);
+
 /* profiling aid: as d3fk_run, but brackets every op with CUDA events and returns per-op milliseconds
  * (synchronises the stream; allocates events — never used on the hot path) */
 int d3fk_run_profile(const d3fk_op* ops, int n_ops, d3fk_stream stream, float* ms_per_op);
@@ -212,6 +231,7 @@ int d3fk_run_profile(const d3fk_op* ops, int n_ops, d3fk_stream stream, float* m
 /* single-op entry points (same launchers; used by the per-op parity tests) */
 int d3fk_conv(const d3fk_conv_params* p, d3fk_stream stream);
 int d3fk_wgrad(const d3fk_wgrad_params* p, d3fk_stream stream);
+int d3fk_conv_bn(const d3fk_convbn_params* p, d3fk_stream stream);
 int d3fk_pack_weights(const d3fk_pack_params* p, d3fk_stream stream);
 int d3fk_nchw_to_nhwc(const d3fk_layout_params* p, d3fk_stream stream);
 int d3fk_bn_finalize(const d3fk_bn_params* p, d3fk_stream stream);

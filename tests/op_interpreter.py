@@ -242,6 +242,11 @@ def run_pack_all(p):
         run_pack(table[i])
 
 
+def run_conv_bn(p):
+    run_conv(p.conv)
+    run_bn_apply(p.bn)
+
+
 def run_memset(p):
     view(p.p0, (p.n,), torch.uint8).zero_()
 
@@ -252,7 +257,7 @@ _DISPATCH = {
     _lib.OP_BN_BWD_REDUCE: run_bn_bwd_reduce, _lib.OP_BN_BWD_FINALIZE: run_bn_bwd_finalize,
     _lib.OP_BN_BWD_APPLY: run_bn_bwd_apply, _lib.OP_MAXPOOL_FWD: run_maxpool_fwd, _lib.OP_MAXPOOL_BWD: run_maxpool_bwd,
     _lib.OP_SUMPOOL2: run_sumpool2, _lib.OP_CHANSUM: run_chansum, _lib.OP_MEMSET: run_memset,
-    _lib.OP_PACK_ALL: run_pack_all,
+    _lib.OP_PACK_ALL: run_pack_all, _lib.OP_CONV_BN: run_conv_bn,
 }
 
 

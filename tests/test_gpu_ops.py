@@ -241,3 +241,73 @@ def test_pools(dtype):
     t = {"x": torch.randn(B * H * W, 8, generator=g), "out": torch.zeros(3)}
     r4 = run_both(_lib.OP_CHANSUM, dtype, t, dict(C=3, ld=8, count=B * H * W), ["out"])
     assert rel_err(*r4["out"]) < 1e-4
+
+
+CONV_BN_CASES = [
+    # fused conv + BN: 128-wide tiles, one resident tile per CTA; PATH 2 (TMA), PATH 0 (stride 2, 1x1), PATH 1 (upsample + concat)
+    dict(B=16, Hi=8, Wi=8, c0=128, c1=0, up0=0, Cout=128, k=3, stride=1, pad=1, relu=1, res=True),
+    dict(B=40, Hi=8, Wi=8, c0=128, c1=0, up0=0, Cout=128, k=3, stride=1, pad=1, relu=1, res=False),
+    dict(B=16, Hi=4, Wi=4, c0=256, c1=0, up0=0, Cout=256, k=3, stride=1, pad=1, relu=1, res=True),      # split-K cluster
+    dict(B=32, Hi=2, Wi=2, c0=512, c1=0, up0=0, Cout=512, k=3, stride=1, pad=1, relu=0, res=False),     # split-K cluster
+    dict(B=8, Hi=16, Wi=16, c0=64, c1=0, up0=0, Cout=128, k=3, stride=2, pad=1, relu=1, res=False),
+    dict(B=8, Hi=16, Wi=16, c0=64, c1=0, up0=0, Cout=128, k=1, stride=2, pad=0, relu=0, res=False),
+    dict(B=4, Hi=8, Wi=8, c0=256, c1=128, up0=1, Cout=128, k=3, stride=1, pad=1, relu=1, res=False),
+    dict(B=2, Hi=16, Wi=16, c0=64, c1=0, up0=0, Cout=64, k=3, stride=1, pad=1, relu=1, res=False),       # not fusable: two kernels
+]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("case", CONV_BN_CASES)
+def test_conv_bn_op(dtype, case):
+    """D3FK_OP_CONV_BN (conv -> train-mode BN -> +res -> ReLU, fused behind a grid barrier when the layer qualifies) vs
+    conv then bn_apply on the CPU: raw output, activation, saved mean / invstd and running statistics."""
+    import op_interpreter as I
+    _lib.init(0)
+    c = dict(case)
+    B, Hi, Wi, c0, c1, up0, Cout, k, stride, pad = (c[x] for x in ("B", "Hi", "Wi", "c0", "c1", "up0", "Cout", "k", "stride", "pad"))
+    g = torch.Generator().manual_seed(7)
+    ctot = c0 + c1
+    Ho = (Hi + 2 * pad - k) // stride + 1
+    Wo = (Wi + 2 * pad - k) // stride + 1
+    tdt = torch.float32 if dtype == _lib.F32 else torch.bfloat16
+    host = {"src0": torch.randn(B, Hi >> up0, Wi >> up0, c0, generator=g),
+            "w": torch.randn(Cout, k * k * ctot, generator=g) / math.sqrt(k * k * ctot),
+            "raw": torch.zeros(B, Ho, Wo, Cout), "act": torch.zeros(B, Ho, Wo, Cout)}
+    if c1:
+        host["src1"] = torch.randn(B, Hi, Wi, c1, generator=g)
+    if c["res"]:
+        host["res"] = torch.randn(B, Ho, Wo, Cout, generator=g)
+    f32 = {"stats": torch.zeros(2, Cout, dtype=torch.float64), "gamma": torch.rand(Cout, generator=g) + 0.5,
+           "beta": torch.randn(Cout, generator=g), "running_mean": torch.zeros(Cout), "running_var": torch.ones(Cout),
+           "nbt": torch.zeros(1, dtype=torch.int64), "mean": torch.zeros(Cout), "invstd": torch.zeros(Cout),
+           "scale": torch.zeros(Cout), "shift": torch.zeros(Cout), "barrier": torch.zeros(2, dtype=torch.int32)}
+
+    def build(t, s, dt):
+        conv = dict(dtype=dt, mode=0, src0=t["src0"].data_ptr(), c0=c0, c1=c1, ld0=c0, ld1=c1, up0=up0, B=B, Hi=Hi, Wi=Wi, Ho=Ho,
+                    Wo=Wo, kh=k, kw=k, stride=stride, pad=pad, w=t["w"].data_ptr(), Cout=Cout, out=t["raw"].data_ptr(), ldo=Cout,
+                    stats=s["stats"].data_ptr())
+        if c1:
+            conv["src1"] = t["src1"].data_ptr()
+        bn = dict(dtype=dt, C=Cout, relu=c["relu"], count=B * Ho * Wo, x=t["raw"].data_ptr(), ldx=Cout, y=t["act"].data_ptr(),
+                  ldy=Cout, stats=s["stats"].data_ptr(), gamma=s["gamma"].data_ptr(), beta=s["beta"].data_ptr(),
+                  running_mean=s["running_mean"].data_ptr(), running_var=s["running_var"].data_ptr(),
+                  num_batches_tracked=s["nbt"].data_ptr(), eps=1e-5, momentum=0.1, scale=s["scale"].data_ptr(),
+                  shift=s["shift"].data_ptr(), mean=s["mean"].data_ptr(), invstd=s["invstd"].data_ptr())
+        if c["res"]:
+            bn.update(res=t["res"].data_ptr(), ldr=Cout)
+        return _lib.make_op(_lib.OP_CONV_BN, conv=conv, bn=bn, barrier=s["barrier"].data_ptr())
+
+    gt = {n: v.to("cuda:0").to(tdt) for n, v in host.items()}
+    gs = {n: v.to("cuda:0") for n, v in f32.items()}
+    ct = {n: gt[n].float().cpu().contiguous() for n in host}
+    cs = {n: v.clone() for n, v in f32.items()}
+    _lib.run_single(build(gt, gs, dtype), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert _lib.load().d3fk_device_error_flag() == 0, "kernel watchdog tripped"
+    I.run_ops([build(ct, cs, _lib.F32)])
+    tol = 1e-5 if dtype == _lib.F32 else 1e-2
+    assert rel_err(gt["raw"].float().cpu(), ct["raw"]) < tol
+    assert rel_err(gt["act"].float().cpu(), ct["act"]) < (1e-5 if dtype == _lib.F32 else 2e-2)
+    for n in ("mean", "invstd", "running_mean", "running_var"):
+        assert rel_err(gs[n].cpu(), cs[n]) < (1e-5 if dtype == _lib.F32 else 5e-3), n
+    assert int(gs["nbt"].item()) == 1

@@ -18,9 +18,11 @@ s = torch.cuda.current_stream().cuda_stream
 kind = _lib.OP_WGRAD if kind_name == "wgrad" else _lib.OP_CONV
 ops = list(plan.fwd_ops) + [op for seg in plan.bwd_segments for op in seg]
 for op in ops:
-    if op.kind != kind:
+    if op.kind != kind and not (kind == _lib.OP_CONV and op.kind == _lib.OP_CONV_BN):
         continue
     p = _lib.op_params(op)
+    if op.kind == _lib.OP_CONV_BN:
+        p = p.conv
     if (p.B * p.Ho * p.Wo, p.Cout, p.kh * p.kw * (p.c0 + p.c1)) != (M, N, K):
         continue
     if kind == _lib.OP_CONV and p.mode != mode:

@@ -11,6 +11,10 @@ KIND = {v: k for k, v in vars(_lib).items() if k.startswith("OP_")}
 
 def describe(op):
     p = _lib.op_params(op)
+    if op.kind == _lib.OP_CONV_BN:
+        p = p.conv
+        M = p.B * p.Ho * p.Wo; K = p.kh * p.kw * (p.c0 + p.c1)
+        return f"+BN mode{p.mode} M={M} N={p.Cout} K={K} k{p.kh}s{p.stride} up{p.up0}", 2.0 * M * p.Cout * K
     if op.kind == _lib.OP_CONV:
         M = p.B * p.Ho * p.Wo; K = p.kh * p.kw * (p.c0 + p.c1)
         return f"mode{p.mode} M={M} N={p.Cout} K={K} k{p.kh}s{p.stride} up{p.up0}", 2.0 * M * p.Cout * K

@@ -21,9 +21,11 @@ tot = 0.0
 seen = {}
 for seg in plan.bwd_segments:
     for op in seg:
-        if op.kind != kind:
+        if op.kind != kind and not (kind == _lib.OP_CONV and op.kind == _lib.OP_CONV_BN):
             continue
         p = _lib.op_params(op)
+        if op.kind == _lib.OP_CONV_BN:
+            p = p.conv
         key = (p.B * p.Ho * p.Wo, p.Cout, p.kh * p.kw * (p.c0 + p.c1), p.stride, p.up0)
         copies = []
         for _ in range(20):
