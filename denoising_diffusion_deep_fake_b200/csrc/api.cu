@@ -47,6 +47,7 @@ int launch_maxpool_fwd(const d3fk_pool_params*, cudaStream_t);
 int launch_maxpool_bwd(const d3fk_pool_params*, cudaStream_t);
 int launch_sumpool2(const d3fk_pool_params*, cudaStream_t);
 int launch_chansum(const d3fk_chansum_params*, cudaStream_t);
+int launch_upcat(const d3fk_upcat_params*, cudaStream_t);
 int launch_qsample(const d3fk_qsample_params*, cudaStream_t);
 int launch_posterior(const d3fk_posterior_params*, cudaStream_t);
 int launch_inc(const d3fk_misc_params*, cudaStream_t);
@@ -95,6 +96,7 @@ static int run_one(const d3fk_op* op, cudaStream_t s) {
     case D3FK_OP_MAXPOOL_BWD: return launch_maxpool_bwd(&op->u.pool, s);
     case D3FK_OP_SUMPOOL2: return launch_sumpool2(&op->u.pool, s);
     case D3FK_OP_CHANSUM: return launch_chansum(&op->u.chansum, s);
+    case D3FK_OP_UPCAT: return launch_upcat(&op->u.upcat, s);
     case D3FK_OP_QSAMPLE: return launch_qsample(&op->u.qsample, s);
     case D3FK_OP_POSTERIOR: return launch_posterior(&op->u.posterior, s);
     case D3FK_OP_MEMSET: {
@@ -264,6 +266,7 @@ SINGLE(d3fk_maxpool_fwd, d3fk_pool_params, launch_maxpool_fwd)
 SINGLE(d3fk_maxpool_bwd, d3fk_pool_params, launch_maxpool_bwd)
 SINGLE(d3fk_sumpool2, d3fk_pool_params, launch_sumpool2)
 SINGLE(d3fk_chansum, d3fk_chansum_params, launch_chansum)
+SINGLE(d3fk_upcat, d3fk_upcat_params, launch_upcat)
 SINGLE(d3fk_q_sample, d3fk_qsample_params, launch_qsample)
 SINGLE(d3fk_posterior_step, d3fk_posterior_params, launch_posterior)
 SINGLE(d3fk_adam, d3fk_adam_params, launch_adam)

@@ -934,7 +934,8 @@ struct SlabSched {
   int w_tile_bytes;       // BN * row_bytes: one tap's resident weight tile
   int total, tiles_per_img;
   int sgn;                // +1 forward taps, -1 transposed (dgrad)
-  int ksteps;             // Cin / 16
+  int ksteps;             // channels per chunk / 16
+  int chunks, ctot;       // 64-channel chunks per tap when Cin > 64 (each chunk is one pipeline stage); total Cin
   uint32_t layout;        // UMMA smem-descriptor layout type: 2 = SWIZZLE_128B, 4 = 64B, 6 = 32B
   int M;                  // B*H*W
 };
@@ -967,8 +968,8 @@ __global__ void __launch_bounds__(SlabCfg<BN>::THREADS) conv_slab_kernel(const _
   constexpr int NW = SlabCfg<BN>::NW;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t w_base = base;                                         // [9 taps][BN rows][row_bytes]
-  const uint32_t w_bytes = (uint32_t)((9 * ss.w_tile_bytes + 1023) & ~1023);
+  const uint32_t w_base = base;                                         // [9 taps][chunks][BN rows][row_bytes]
+  const uint32_t w_bytes = (uint32_t)((9 * ss.chunks * ss.w_tile_bytes + 1023) & ~1023);
   const uint32_t slab_base = base + w_bytes;                            // [stages][3][slab_bytes]
   const uint32_t stage_bytes = 3u * ss.slab_bytes;
   const uint32_t bar_base = slab_base + ss.stages * stage_bytes;        // full[4], empty[4], acc_full[2], acc_empty[2], wbar
@@ -1016,22 +1017,26 @@ __global__ void __launch_bounds__(SlabCfg<BN>::THREADS) conv_slab_kernel(const _
   if (warp == 4) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      // resident weights: 9 boxes {Cin, BN} of the packed [Cout][9*Cin] matrix (rows >= Cout zero filled)
-      mbar_arrive_expect_tx(wbar, 9u * ss.w_tile_bytes);
-      const int cin = ss.row_bytes >> 1;
-      for (int t = 0; t < 9; ++t) tma_load_2d(w_base + t * ss.w_tile_bytes, &tmB, t * cin, 0, wbar);
+      // resident weights: 9 * chunks boxes {chunk channels, BN} of the packed [Cout][9*Cin] matrix (rows >= Cout zero filled)
+      mbar_arrive_expect_tx(wbar, 9u * ss.chunks * ss.w_tile_bytes);
+      const int cch = ss.row_bytes >> 1;
+      for (int t = 0; t < 9; ++t)
+        for (int c = 0; c < ss.chunks; ++c)
+          tma_load_2d(w_base + (t * ss.chunks + c) * ss.w_tile_bytes, &tmB, t * ss.ctot + c * cch, 0, wbar);
       const int rows = S * ss.R;
-      uint32_t it = 0;
-      for (int t = blockIdx.x; t < ss.total; t += gridDim.x, ++it) {
+      uint32_t it = 0;                                  // pipeline stage counter: (super-tile, chunk) pairs
+      for (int t = blockIdx.x; t < ss.total; t += gridDim.x) {
         const int n = t / ss.tiles_per_img;
         const int rem = t - n * ss.tiles_per_img;
         const int hb = rem / ss.wtiles;
         const int h0 = hb * rows, w0 = (rem - hb * ss.wtiles) * ss.Wt;
-        const int st = it % ss.stages;
-        if (it >= (uint32_t)ss.stages) mbar_wait(empty_bar(st), ((it / ss.stages) - 1) & 1, errflag);
-        mbar_arrive_expect_tx(full_bar(st), 3u * ss.slab_tx);
-        for (int sx = 0; sx < 3; ++sx)
-          tma_load_4d(slab_base + st * stage_bytes + sx * ss.slab_bytes, &tmA, 0, w0 + sx - 1, h0 - 1, n, full_bar(st));
+        for (int c = 0; c < ss.chunks; ++c, ++it) {
+          const int st = it % ss.stages;
+          if (it >= (uint32_t)ss.stages) mbar_wait(empty_bar(st), ((it / ss.stages) - 1) & 1, errflag);
+          mbar_arrive_expect_tx(full_bar(st), 3u * ss.slab_tx);
+          for (int sx = 0; sx < 3; ++sx)
+            tma_load_4d(slab_base + st * stage_bytes + sx * ss.slab_bytes, &tmA, c * cch, w0 + sx - 1, h0 - 1, n, full_bar(st));
+        }
       }
     }
     __syncwarp();
@@ -1055,33 +1060,37 @@ __global__ void __launch_bounds__(SlabCfg<BN>::THREADS) conv_slab_kernel(const _
         const int sy = ss.sgn > 0 ? kh : 2 - kh;
         const int sx = ss.sgn > 0 ? kw : 2 - kw;
         a_off[tap] = ((uint32_t)(sx * ss.slab_bytes) >> 4) + (uint32_t)(sy + my_s * ss.R) * img_row16;
-        b_lo[tap] = dlo | ((w_base + (uint32_t)(tap * ss.w_tile_bytes)) >> 4);
+        b_lo[tap] = dlo | ((w_base + (uint32_t)(tap * ss.chunks * ss.w_tile_bytes)) >> 4);
       }
+      const uint32_t wchunk16 = (uint32_t)ss.w_tile_bytes >> 4;
       const bool active = my_p < P;                     // S * P == NW: always true; kept for clarity
       mbar_wait(wbar, 0, errflag);
-      uint32_t it = 0;
-      for (int t = blockIdx.x; t < ss.total; t += gridDim.x, ++it) {
-        const int st = it % ss.stages;
-        const uint32_t abuf = it & 1;
-        if (it >= 2) mbar_wait(acc_empty_bar(abuf), ((it >> 1) - 1) & 1, errflag);
-        mbar_wait(full_bar(st), (it / ss.stages) & 1, errflag);
-        tc_fence_after();
-        const uint32_t sub_lo = dlo | ((slab_base + st * stage_bytes) >> 4);
+      uint32_t it = 0, tile_it = 0;
+      for (int t = blockIdx.x; t < ss.total; t += gridDim.x, ++tile_it) {
+        const uint32_t abuf = tile_it & 1;
+        if (tile_it >= 2) mbar_wait(acc_empty_bar(abuf), ((tile_it >> 1) - 1) & 1, errflag);
         const uint32_t d_addr = tmem_d + abuf * (uint32_t)(NW * ACC) + (uint32_t)((my_s * P + my_p) * ACC);
         uint32_t first = 0u;
-        if (active) {
+        for (int c = 0; c < ss.chunks; ++c, ++it) {
+          const int st = it % ss.stages;
+          mbar_wait(full_bar(st), (it / ss.stages) & 1, errflag);
+          tc_fence_after();
+          const uint32_t sub_lo = dlo | ((slab_base + st * stage_bytes) >> 4);
+          const uint32_t bc = (uint32_t)c * wchunk16;
+          if (active) {
 #pragma unroll
-          for (int tap = 0; tap < 9; ++tap) {
-            if (tap % P == my_p) {                      // P in {1, 2, 4}
+            for (int tap = 0; tap < 9; ++tap) {
+              if (tap % P == my_p) {                    // P in {1, 2, 4}
 #pragma unroll
-              for (int kk = 0; kk < KSTEPS; ++kk) {
-                umma_f16_lohi_p(d_addr, sub_lo + a_off[tap] + 2u * kk, dhi, b_lo[tap] + 2u * kk, dhi, idesc, first, leader);
-                first = 1u;
+                for (int kk = 0; kk < KSTEPS; ++kk) {
+                  umma_f16_lohi_p(d_addr, sub_lo + a_off[tap] + 2u * kk, dhi, b_lo[tap] + bc + 2u * kk, dhi, idesc, first, leader);
+                  first = 1u;
+                }
               }
             }
           }
+          umma_commit_p(empty_bar(st), leader);
         }
-        umma_commit_p(empty_bar(st), leader);
         umma_commit_p(acc_full_bar(abuf), leader);
       }
     }
@@ -1181,7 +1190,7 @@ static bool slab_plan(const Gather& g, const d3fk_conv_params* p, int BN, SlabSc
   if (p->kh != 3 || p->kw != 3 || p->stride != 1 || p->pad != 1 || p->c1 != 0 || p->up0 != 0) return false;
   if (p->Ho != p->Hi || p->Wo != p->Wi) return false;
   const int C = g.ctot, W = p->Wi, H = p->Hi;
-  if (C != 16 && C != 32 && C != 64) return false;
+  if (C != 16 && C != 32 && C != 64 && C != 128) return false;   // 128 = two 64-channel chunks (one pipeline stage each)
   if (W != 16 && W != 32 && W != 64 && (W % 128)) return false;
   if (p->Cout > BN || (!p->out_nchw && p->Cout != BN)) return false;
   if (((uintptr_t)p->src0 & 15) || (g.ld0 % 8)) return false;
@@ -1189,13 +1198,16 @@ static bool slab_plan(const Gather& g, const d3fk_conv_params* p, int BN, SlabSc
   const int R = TC_BM / Wt;
   if (H % R) return false;
   ss.W = W; ss.H = H; ss.R = R; ss.Wt = Wt; ss.wtiles = W / Wt;
-  ss.row_bytes = C * 2;
-  ss.layout = C == 64 ? 2u : C == 32 ? 4u : 6u;
-  ss.ksteps = C / 16;
+  const int cch = C > 64 ? 64 : C;
+  ss.chunks = C / cch;
+  ss.ctot = C;
+  ss.row_bytes = cch * 2;
+  ss.layout = cch == 64 ? 2u : cch == 32 ? 4u : 6u;
+  ss.ksteps = cch / 16;
   ss.w_tile_bytes = BN * ss.row_bytes;
   ss.sgn = p->mode ? -1 : 1;
   ss.M = g.M;
-  const int w_bytes = (9 * ss.w_tile_bytes + 1023) & ~1023;
+  const int w_bytes = (9 * ss.chunks * ss.w_tile_bytes + 1023) & ~1023;
   // largest super-tile whose double-buffered accumulators fit TMEM and whose 2-stage slabs fit shared memory
   const int NW = BN >= 128 ? 2 : 4;                    // MMA warps (SlabCfg<BN>::NW): S must divide it
   for (int S = NW; S >= 1; S >>= 1) {
@@ -1225,14 +1237,14 @@ static int launch_conv_slab_bn(const Gather& g, const d3fk_conv_params* p, cudaS
   {
     uint64_t dims[2] = {(uint64_t)g.K, (uint64_t)p->Cout};
     uint64_t strides[1] = {(uint64_t)g.K * 2};
-    uint32_t bx[2] = {(uint32_t)C, (uint32_t)BN};
+    uint32_t bx[2] = {(uint32_t)(ss.row_bytes >> 1), (uint32_t)BN};
     int rc = get_tensor_map(&tmB, p->w, 2, dims, strides, bx, ss.row_bytes);
     if (rc) return rc;
   }
   {
     uint64_t dims[4] = {(uint64_t)C, (uint64_t)g.Wi, (uint64_t)g.Hi, (uint64_t)g.B};
     uint64_t strides[3] = {(uint64_t)g.ld0 * 2, (uint64_t)g.Wi * g.ld0 * 2, (uint64_t)g.Hi * g.Wi * g.ld0 * 2};
-    uint32_t bx[4] = {(uint32_t)C, (uint32_t)ss.Wt, (uint32_t)(ss.S * ss.R + 2), 1u};
+    uint32_t bx[4] = {(uint32_t)(ss.row_bytes >> 1), (uint32_t)ss.Wt, (uint32_t)(ss.S * ss.R + 2), 1u};
     int rc = get_tensor_map(&tmA, p->src0, 4, dims, strides, bx, ss.row_bytes);
     if (rc) return rc;
   }

@@ -450,6 +450,31 @@ __global__ void sumpool2_kernel(d3fk_pool_params p) {
   }
 }
 
+// nearest 2x upsample of src0 concatenated with src1 along channels (16-byte vectors; C's are multiples of 8 / 4)
+template <typename T>
+__global__ void upcat_kernel(d3fk_upcat_params p) {
+  pdl_enter();
+  constexpr int V = Vec<T>::N;
+  const int cv0 = p.c0 / V, cvs = (p.c0 + p.c1) / V;
+  const long long total = (long long)p.B * p.H * p.W * cvs;
+  const uint4* s0 = (const uint4*)p.src0;
+  const uint4* s1 = (const uint4*)p.src1;
+  uint4* out = (uint4*)p.out;
+  const int Hs = p.H >> 1, Ws = p.W >> 1;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long pix = e / cvs;
+    const int cv = (int)(e - pix * cvs);
+    const int w = (int)(pix % p.W);
+    const long long t = pix / p.W;
+    const int h = (int)(t % p.H);
+    const int n = (int)(t / p.H);
+    uint4 v;
+    if (cv < cv0) v = __ldg(s0 + (((long long)(n * Hs + (h >> 1)) * Ws + (w >> 1)) * p.ld0) / V + cv);
+    else v = __ldg(s1 + (pix * p.ld1) / V + (cv - cv0));
+    out[(pix * p.ldo) / V + cv] = v;
+  }
+}
+
 // out[c] += sum over pixels x[pix*ld + c], c < C <= 8
 template <typename T>
 __global__ void chansum_kernel(d3fk_chansum_params p) {
@@ -720,6 +745,16 @@ int launch_sumpool2(const d3fk_pool_params* p, cudaStream_t s) {
   DISPATCH_T(p->dtype, launch_k(sumpool2_kernel<T>, dim3(grid_for(total, 256)), dim3(256), 0, s, dim3(1, 1, 1), *p));
   count_launch();
   return check_launch("sumpool2");
+}
+int launch_upcat(const d3fk_upcat_params* p, cudaStream_t s) {
+  int V = p->dtype == D3FK_F32 ? 4 : 8;
+  D3FK_CHECK_ARG(p->c0 % V == 0 && p->c1 % V == 0 && p->ld0 % V == 0 && p->ldo % V == 0 && (p->c1 == 0 || p->ld1 % V == 0),
+                 "channel counts and pixel strides must be multiples of the 16-byte vector");
+  D3FK_CHECK_ARG(p->H % 2 == 0 && p->W % 2 == 0 && p->c0 > 0, "H, W even, c0 > 0");
+  long long total = (long long)p->B * p->H * p->W * ((p->c0 + p->c1) / V);
+  DISPATCH_T(p->dtype, launch_k(upcat_kernel<T>, dim3(grid_for(total, 256)), dim3(256), 0, s, dim3(1, 1, 1), *p));
+  count_launch();
+  return check_launch("upcat");
 }
 int launch_chansum(const d3fk_chansum_params* p, cudaStream_t s) {
   D3FK_CHECK_ARG(p->C <= 8 && p->ld % 8 == 0, "C<=8, ld%8");

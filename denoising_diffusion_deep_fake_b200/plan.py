@@ -326,9 +326,23 @@ class UnetPlan:
         x = feats[4]
         self.dec_io = []
         for d, skip in zip(self.dec, skips):
-            a1 = self._conv_bn_act(ops, d["conv1"], x, src1=skip, up0=1)
+            ctot = x.C + (skip.C if skip is not None else 0)
+            if 2 * x.W >= 16 and ctot in (16, 32, 64, 128):
+                # materialise upsample + concat once (one streaming pass) so conv1 — and its weight gradient — run on the
+                # slab path (each activation row read 3x by TMA) instead of a 9x per-thread gather through the upsample
+                cat = T(self, B, 2 * x.H, 2 * x.W, ctot)
+                self.keep.append(cat.t)
+                f = dict(dtype=self.dtype, B=B, H=cat.H, W=cat.W, c0=x.C, ld0=x.ld, ldo=cat.ld, src0=x.ptr, out=cat.ptr)
+                if skip is not None:
+                    f.update(c1=skip.C, ld1=skip.ld, src1=skip.ptr)
+                ops.append(make_op(_lib.OP_UPCAT, **f))
+                a1 = self._conv_bn_act(ops, d["conv1"], cat)
+                self.dec_io.append((d, x, skip, a1, None, cat))
+            else:
+                a1 = self._conv_bn_act(ops, d["conv1"], x, src1=skip, up0=1)
+                self.dec_io.append((d, x, skip, a1, None, None))
             out = self._conv_bn_act(ops, d["conv2"], a1)
-            self.dec_io.append((d, x, skip, a1, out))
+            self.dec_io[-1] = self.dec_io[-1][:4] + (out, self.dec_io[-1][5])
             x = out
         self.dec_out = x
         self.out_op_index = len(ops)
@@ -426,12 +440,15 @@ class UnetPlan:
                 ops.append(self._dgrad_op(conv, dy, gbuf, row0=row0, rows=rows))
 
         # ---- decoder, last block first
-        for d, x, skip, a1, out in reversed(self.dec_io):
+        for d, x, skip, a1, out, cat in reversed(self.dec_io):
             d_r2, _ = self._bn_bwd(ops, d["conv2"], grad[id(out)])
             ops.append(self._wgrad_op(d["conv2"], a1, None, 0, d_r2))
             add_grad(ops, d["conv2"], d_r2, a1)
             d_r1, _ = self._bn_bwd(ops, d["conv1"], grad[id(a1)])
-            ops.append(self._wgrad_op(d["conv1"], x, skip, 1, d_r1))
+            if cat is not None:
+                ops.append(self._wgrad_op(d["conv1"], cat, None, 0, d_r1))     # the materialised upsample + concat
+            else:
+                ops.append(self._wgrad_op(d["conv1"], x, skip, 1, d_r1))
             up_tmp = T(self, B, 2 * x.H, 2 * x.W, x.C)
             self.keep.append(up_tmp.t)
             add_grad(ops, d["conv1"], d_r1, None, row0=0, rows=x.C, tmp=up_tmp)

@@ -131,6 +131,14 @@ typedef struct d3fk_layout_params {
   const float* src; void* dst;            /* src fp32 NCHW [B,C,H,W] -> dst NHWC dtype [B,H,W,cpad] */
 } d3fk_layout_params;
 
+/* nearest 2x upsample of src0 + channel concat with src1, materialised (smp DecoderBlock: F.interpolate(scale_factor=2) +
+ * torch.cat): out[n,h,w, 0:c0] = src0[n, h/2, w/2, :], out[n,h,w, c0:c0+c1] = src1[n,h,w,:].  H, W = OUTPUT extent.  Used
+ * for the decoder convolutions that then run on the slab path (one HBM pass instead of a 9x gather). */
+typedef struct d3fk_upcat_params {
+  int32_t dtype, B, H, W, c0, c1, ld0, ld1, ldo, _pad0;
+  const void* src0; const void* src1; void* out;
+} d3fk_upcat_params;
+
 /* per-channel sum over (n,h,w) of an NHWC tensor into fp32 out[c] (head bias gradient) */
 typedef struct d3fk_chansum_params {
   int32_t dtype, C, ld, _pad0; int64_t count;
@@ -194,7 +202,8 @@ enum d3fk_op_kind {
   D3FK_OP_MEMSET = 17, D3FK_OP_INC = 18, D3FK_OP_ADAM = 19,
   D3FK_OP_PACK_ALL = 20, /* misc: p0 = device array of d3fk_pack_params, n = (blocks << 17) | (count << 1) | is_bf16 */
   D3FK_OP_LOSS = 21,
-  D3FK_OP_CONV_BN = 22
+  D3FK_OP_CONV_BN = 22,
+  D3FK_OP_UPCAT = 23
 };
 
 typedef struct d3fk_op {
@@ -203,7 +212,7 @@ typedef struct d3fk_op {
     d3fk_conv_params conv; d3fk_wgrad_params wgrad; d3fk_pack_params pack; d3fk_bn_params bn;
     d3fk_pool_params pool; d3fk_layout_params layout; d3fk_chansum_params chansum;
     d3fk_qsample_params qsample; d3fk_posterior_params posterior; d3fk_misc_params misc;
-    d3fk_adam_params adam; d3fk_loss_params loss; d3fk_convbn_params convbn;
+    d3fk_adam_params adam; d3fk_loss_params loss; d3fk_convbn_params convbn; d3fk_upcat_params upcat;
   } u;
 } d3fk_op;
 
@@ -244,6 +253,7 @@ int d3fk_maxpool_fwd(const d3fk_pool_params* p, d3fk_stream stream);
 int d3fk_maxpool_bwd(const d3fk_pool_params* p, d3fk_stream stream);
 int d3fk_sumpool2(const d3fk_pool_params* p, d3fk_stream stream);
 int d3fk_chansum(const d3fk_chansum_params* p, d3fk_stream stream);
+int d3fk_upcat(const d3fk_upcat_params* p, d3fk_stream stream);
 int d3fk_q_sample(const d3fk_qsample_params* p, d3fk_stream stream);
 int d3fk_posterior_step(const d3fk_posterior_params* p, d3fk_stream stream);
 int d3fk_adam(const d3fk_adam_params* p, d3fk_stream stream);

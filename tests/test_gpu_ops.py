@@ -93,6 +93,9 @@ CONV_CASES = [
     dict(B=1, Hi=12, Wi=256, c0=32, c1=0, up0=0, Cout=32, k=3, stride=1, pad=1, mode=1, res=True),             # two tiles across W
     dict(B=1, Hi=4, Wi=256, c0=16, c1=0, up0=0, Cout=3, k=3, stride=1, pad=1, mode=0, nchw=True),
     dict(B=2, Hi=32, Wi=32, c0=16, c1=0, up0=0, Cout=16, k=3, stride=1, pad=1, mode=1),                        # head dgrad (dy padded to 16)
+    dict(B=3, Hi=32, Wi=32, c0=128, c1=0, up0=0, Cout=32, k=3, stride=1, pad=1, mode=0, stats=True),            # two 64-channel chunks
+    dict(B=2, Hi=16, Wi=16, c0=128, c1=0, up0=0, Cout=64, k=3, stride=1, pad=1, mode=0, relu=1, affine=True),
+    dict(B=20, Hi=32, Wi=32, c0=128, c1=0, up0=0, Cout=32, k=3, stride=1, pad=1, mode=0, stats=True, seed=5),   # several tiles per CTA
 ]
 
 
@@ -311,3 +314,17 @@ def test_conv_bn_op(dtype, case):
     for n in ("mean", "invstd", "running_mean", "running_var"):
         assert rel_err(gs[n].cpu(), cs[n]) < (1e-5 if dtype == _lib.F32 else 5e-3), n
     assert int(gs["nbt"].item()) == 1
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("c0,c1", [(64, 64), (32, 0), (8, 24)])
+def test_upcat(dtype, c0, c1):
+    """Materialised nearest-2x upsample + channel concat (smp DecoderBlock) — exact copy semantics."""
+    g = torch.Generator().manual_seed(9)
+    B, H, W = 3, 16, 24
+    t = {"src0": torch.randn(B, H // 2, W // 2, c0, generator=g), "out": torch.zeros(B, H, W, c0 + c1)}
+    sc = dict(B=B, H=H, W=W, c0=c0, c1=c1, ld0=c0, ld1=c1, ldo=c0 + c1)
+    if c1:
+        t["src1"] = torch.randn(B, H, W, c1, generator=g)
+    r = run_both(_lib.OP_UPCAT, dtype, t, sc, ["out"])
+    assert torch.equal(r["out"][0], r["out"][1])

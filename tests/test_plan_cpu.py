@@ -102,7 +102,7 @@ def test_eval_plan_matches_oracle():
     x = torch.randn(2, 3, 64, 32)
     plan = cpu_plan(m, 2, 64, 32, False)
     assert sum(1 for op in plan.fwd_ops if op.kind in (_lib.OP_CONV, _lib.OP_CONV_BN)) == 47
-    assert len(plan.fwd_ops) == 49                                  # 47 convs (BN folded) + layout + maxpool
+    assert len(plan.fwd_ops) == 51                                  # 47 convs (BN folded) + layout + maxpool + 2 upsample-concat
     y = run_forward(plan, x)
     with torch.no_grad():
         assert rel(y, ref(x)) < 1e-5
