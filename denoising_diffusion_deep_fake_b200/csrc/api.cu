@@ -135,9 +135,10 @@ int d3fk_init(int device) {
   if (e != cudaSuccess) return set_error(D3FK_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
   if (prop.major != 10) return set_error(D3FK_ERR_ARCH, "device %d is sm_%d%d; libd3fk is sm_100a only", device, prop.major, prop.minor);
   if (!g_dev_error_flag) {
-    e = cudaMalloc(&g_dev_error_flag, sizeof(int));
+    const size_t dbg_bytes = 64 + 512 * 16 * sizeof(unsigned long long);   // error flag + (D3FK_TIMELINE builds) phase stamps
+    e = cudaMalloc(&g_dev_error_flag, dbg_bytes);
     if (e != cudaSuccess) return set_error(D3FK_ERR_CUDA, "cudaMalloc: %s", cudaGetErrorString(e));
-    cudaMemset(g_dev_error_flag, 0, sizeof(int));
+    cudaMemset(g_dev_error_flag, 0, dbg_bytes);
   }
   if (const char* v = getenv("D3FK_PDL")) g_use_pdl = atoi(v);
   int rc = tc_init();
@@ -145,6 +146,15 @@ int d3fk_init(int device) {
   rc = loss_init();
   if (rc) return rc;
   g_inited_device = device;
+  return D3FK_OK;
+}
+
+/* debug: copy the first n 64-bit timeline words (D3FK_TIMELINE builds only write them) and the launch counter */
+int d3fk_debug_timeline(unsigned long long* out, int n, unsigned* launches) {
+  if (!g_dev_error_flag) return D3FK_ERR_ARG;
+  cudaDeviceSynchronize();
+  cudaMemcpy(out, g_dev_error_flag + 16, (size_t)n * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  cudaMemcpy(launches, g_dev_error_flag + 4, sizeof(unsigned), cudaMemcpyDeviceToHost);
   return D3FK_OK;
 }
 

@@ -17,6 +17,21 @@ namespace d3fk {
 
 typedef __nv_bfloat16 bf16;
 
+// -DD3FK_TIMELINE (tools/build_timeline.sh; never shipped): CTA 0 of every conv_tc launch stamps %globaltimer at its
+// phase boundaries into the debug buffer behind the error flag — where do the ~10 us of a tiny tensor-core kernel go?
+#ifdef D3FK_TIMELINE
+#define TL_SLOTS 16
+#define TL_MAX 512
+__device__ __forceinline__ unsigned long long tl_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define TL_DECL unsigned long long* tl_buf = reinterpret_cast<unsigned long long*>(errflag + 16); __shared__ unsigned tl_idx;
+#define TL_BEGIN if (blockIdx.x == 0 && threadIdx.x == 0) { tl_idx = atomicAdd(reinterpret_cast<unsigned*>(errflag + 4), 1u) % TL_MAX; tl_buf[tl_idx * TL_SLOTS + 0] = tl_now(); }
+#define TL_STAMP(slot) if (blockIdx.x == 0) { tl_buf[tl_idx * TL_SLOTS + (slot)] = tl_now(); }
+#else
+#define TL_DECL
+#define TL_BEGIN
+#define TL_STAMP(slot)
+#endif
+
 // ------------------------------------------------------------------------------------------
 // PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -393,6 +408,8 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(Gather g, FastDiv d
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool clus = ts.KS > 1;
   const bool do_stats = e.stats != nullptr;
+  TL_DECL
+  TL_BEGIN
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -417,7 +434,9 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(Gather g, FastDiv d
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = *tmem_ptr_slot;
+  if (tid == 0) { TL_STAMP(1) }
   pdl_enter();   // prologue above overlaps the previous kernel; from here on its results are visible
+  if (tid == 0) { TL_STAMP(2) }
 
   // flush this CTA's accumulated statistics of n tile `nt` (epilogue warps only)
   auto flush_stats = [&](int nt) {
@@ -626,6 +645,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(Gather g, FastDiv d
       // ===================== epilogue: TMEM -> registers -> global =====================
       const uint32_t abuf = tile_iter & 1;
       mbar_wait(acc_full_bar(abuf), (tile_iter >> 1) & 1, errflag);
+      if (tid == 0) { TL_STAMP(5) }
       tc_fence_after();
       if (clus) break;   // split K: the accumulator is reduced across the cluster below
       if (do_stats && cur_nt != nt) {
@@ -653,7 +673,9 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(Gather g, FastDiv d
         for (int i = 0; i < CW; ++i) f[i] = __uint_as_float(raw[i]);
         epilogue_chunk<CW>(f, e, (long long)m, row_ok, n0 + cc, on, oh, ow, do_stats, s_stat + warp * 2 * BN + cc,
                            s_stat + warp * 2 * BN + BN + cc, lane);
+        if (tid == 0 && cc == 0) { TL_STAMP(8) }
       }
+      if (tid == 0) { TL_STAMP(9) }
       if (FUSE == 1) {
         // one tile per CTA (the launcher guarantees it): statistics -> grid barrier -> activation from the parked accumulator
         flush_stats(nt);
@@ -674,6 +696,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(Gather g, FastDiv d
       tc_fence_before();   // this tile's TMEM reads are done: hand the accumulator buffer back to the MMA issuer
       mbar_arrive(acc_empty_bar(abuf));
     }
+    if (tid == 0) { TL_STAMP(10) }
     if (!clus && do_stats && cur_nt >= 0) flush_stats(cur_nt);
   } else if (warp == 4) {
     // ===================== MMA issuer (one thread) =====================
@@ -694,6 +717,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(Gather g, FastDiv d
         for (int kb = kb0; kb < kb1; ++kb, ++kbg) {
           const int s = kbg % STAGES;
           mbar_wait(full_bar(s), (kbg / STAGES) & 1, errflag);
+          if (kbg == 0) { TL_STAMP(3) }
           tc_fence_after();
           const uint32_t a_addr = a_base + s * A_STAGE_BYTES;
           const uint32_t b_addr = b_base + s * Cfg::B_STAGE_BYTES;
@@ -706,6 +730,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(Gather g, FastDiv d
           umma_commit(empty_bar(s));
         }
         umma_commit(acc_full_bar(abuf));
+        TL_STAMP(4)
       }
     }
     __syncwarp();
@@ -781,9 +806,11 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(Gather g, FastDiv d
     }
   }
 
+  if (tid == 0) { TL_STAMP(6) }
   tc_fence_before();
   __syncthreads();
   if (warp == 4) tmem_dealloc(tmem_d, Cfg::TMEM_COLS);
+  if (tid == 128) { TL_STAMP(7) }
 }
 
 static int g_num_sms = 148;

@@ -222,6 +222,7 @@ int d3fk_sizeof_op(void);                 /* ABI check for the host-side struct 
 int d3fk_init(int device);                /* D3FK_ERR_ARCH unless the device is sm_100 */
 const char* d3fk_last_error(void);
 int d3fk_device_error_flag(void);         /* non-zero if a kernel hit its barrier watchdog (debug) */
+int d3fk_debug_timeline(unsigned long long* out, int n, unsigned* launches);   /* phase stamps of -DD3FK_TIMELINE builds */
 
 /* run a recorded op list on `stream` (the hot path: one call per U-Net forward / backward) */
 int d3fk_run(const d3fk_op* ops, int n_ops, d3fk_stream stream);
