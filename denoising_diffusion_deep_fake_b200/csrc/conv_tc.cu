@@ -246,7 +246,8 @@ static FastDiv make_fastdiv(uint32_t d) {
 }
 __device__ __forceinline__ uint32_t fdiv(uint32_t n, FastDiv f) { return (__umulhi(f.mul, n) + n) >> f.shr; }
 
-constexpr int TC_THREADS = 192;   // warps 0-3 gather/epilogue, warp 4 MMA issuer, warp 5 TMA producer
+constexpr int TC_THREADS = 320;   // warps 0-3 gather/epilogue, warp 4 MMA issuer, warp 5 TMA producer, warps 6-9 epilogue helpers
+constexpr int EPI_THREADS = 256;  // the 8 epilogue warps
 constexpr int WG_THREADS = 160;   // weight-gradient kernel: warps 0-3 gather/epilogue, warp 4 MMA issuer
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;                 // bf16 elements = 128 bytes = one swizzle row
@@ -406,6 +407,13 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(Gather g, FastDiv d
   auto acc_empty_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // Epilogue warps: 0-3 (also the gather producers of PATH 0/1) and the helpers 6-9.  A warp may touch TMEM lanes
+  // 32*(warp%4)..+32 only, so helper warp w shares the lane quarter of primary warp w%4 and takes every other column
+  // chunk: the epilogue is a dependent instruction chain per warp (~1 us per 32 columns with one warp per scheduler).
+  const bool is_epi = warp < 4 || warp >= 6;
+  const int q = warp & 3;                         // TMEM lane quarter / row group of this epilogue warp
+  const int half = warp >= 6 ? 1 : 0;             // helpers take the odd column chunks
+  const int etid = warp < 4 ? tid : 128 + (tid - 192);   // 0..255 over the 8 epilogue warps
   const bool clus = ts.KS > 1;
   const bool do_stats = e.stats != nullptr;
   TL_DECL
@@ -418,12 +426,12 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(Gather g, FastDiv d
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(acc_full_bar(b), 1);
-      mbar_init(acc_empty_bar(b), 128);
+      mbar_init(acc_empty_bar(b), EPI_THREADS);
     }
     fence_barrier_init();
   }
-  if (tid < 128) {
-    for (int i = tid; i < 8 * BN; i += 128) s_stat[i] = 0.f;
+  if (is_epi) {
+    for (int i = etid; i < 8 * BN; i += EPI_THREADS) s_stat[i] = 0.f;
   }
   if (warp == 5 && lane == 0) {
     tma_prefetch_desc(&tmB);
@@ -440,7 +448,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(Gather g, FastDiv d
 
   // flush this CTA's accumulated statistics of n tile `nt` (epilogue warps only)
   auto flush_stats = [&](int nt) {
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    asm volatile("bar.sync 1, 256;" ::: "memory");
     const int n0 = nt * BN;
     if (tid < BN && n0 + tid < e.Cout) {
       const float a = (s_stat[tid] + s_stat[2 * BN + tid]) + (s_stat[4 * BN + tid] + s_stat[6 * BN + tid]);
@@ -450,18 +458,18 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(Gather g, FastDiv d
         atomicAdd(&e.stats[e.Cout + n0 + tid], (double)b);
       }
     }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    for (int i = tid; i < 8 * BN; i += 128) s_stat[i] = 0.f;
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    for (int i = etid; i < 8 * BN; i += EPI_THREADS) s_stat[i] = 0.f;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
   };
 
   // FUSE: after this CTA's statistics are flushed — grid barrier, then scale / shift of the tile's BN channels into s_stat
   // (free again after the flush): s_stat[c] = scale, s_stat[BN + c] = shift.  The CTA with m tile 0 (and k slice 0)
   // publishes mean / invstd / running statistics of its n tile.
   auto fuse_finalize = [&](int nt, bool publisher) {
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    asm volatile("bar.sync 1, 256;" ::: "memory");
     if (tid == 0) grid_barrier_arrive_wait(fb.barrier, gridDim.x, errflag);
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    asm volatile("bar.sync 1, 256;" ::: "memory");
     const int ch = nt * BN + tid;
     if (tid < BN && ch < e.Cout) {
       const double n = (double)fb.count;
@@ -483,7 +491,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(Gather g, FastDiv d
         if (ch == 0 && fb.nbt) *fb.nbt += 1;
       }
     }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    asm volatile("bar.sync 1, 256;" ::: "memory");
   };
   // FUSE: activation of CWF accumulator columns [ct, ct + CWF) (tile-relative) of output row m
   auto fuse_apply = [&](float* f, int ncol, long long m, bool row_ok, int nt, int ct) {
@@ -555,7 +563,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(Gather g, FastDiv d
       }
     }
     __syncwarp();
-  } else if (warp < 4) {
+  } else if (is_epi) {
     const int j = tid & 7;    // 16-byte chunk (8 channels) within the 128-byte k-row
     const int rb = tid >> 3;  // rows rb + 16*i
     const uint32_t sw = (uint32_t)((j ^ (rb & 7)) << 4);
@@ -572,7 +580,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(Gather g, FastDiv d
       const int kb0 = ks * ts.kb_per_split;
       const int kb1 = min(ts.nkb, kb0 + ts.kb_per_split);
 
-      if (PATH != 2) {
+      if (PATH != 2 && warp < 4) {
         // ---- per-row state
         int rh[8], rw[8];
         int rn[8];                    // GENERIC: image index
@@ -652,7 +660,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(Gather g, FastDiv d
         if (cur_nt >= 0) flush_stats(cur_nt);
         cur_nt = nt;
       }
-      const int row = warp * 32 + lane;
+      const int row = q * 32 + lane;
       const int m = m0 + row;
       const bool row_ok = m < g.M;
       int on = 0, oh = 0, ow = 0;
@@ -663,16 +671,16 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(Gather g, FastDiv d
         oh = (int)q - on * e.Ho;
       }
 #pragma unroll 1
-      for (int cc = 0; cc < BN; cc += CW) {
+      for (int cc = half * CW; cc < BN; cc += 2 * CW) {
         uint32_t raw[CW];
-        const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + abuf * Cfg::ACC_COLS + (uint32_t)cc;
+        const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + abuf * Cfg::ACC_COLS + (uint32_t)cc;
         if (CW == 32) tmem_ld32(taddr, raw); else tmem_ld16(taddr, raw);
         tmem_ld_wait();
         float f[CW];
 #pragma unroll
         for (int i = 0; i < CW; ++i) f[i] = __uint_as_float(raw[i]);
-        epilogue_chunk<CW>(f, e, (long long)m, row_ok, n0 + cc, on, oh, ow, do_stats, s_stat + warp * 2 * BN + cc,
-                           s_stat + warp * 2 * BN + BN + cc, lane);
+        epilogue_chunk<CW>(f, e, (long long)m, row_ok, n0 + cc, on, oh, ow, do_stats, s_stat + q * 2 * BN + cc,
+                           s_stat + q * 2 * BN + BN + cc, lane);
         if (tid == 0 && cc == 0) { TL_STAMP(8) }
       }
       if (tid == 0) { TL_STAMP(9) }
@@ -682,9 +690,9 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(Gather g, FastDiv d
         cur_nt = -1;
         fuse_finalize(nt, mt == 0);
 #pragma unroll 1
-        for (int cc = 0; cc < BN; cc += CW) {
+        for (int cc = half * CW; cc < BN; cc += 2 * CW) {
           uint32_t raw[CW];
-          const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + abuf * Cfg::ACC_COLS + (uint32_t)cc;
+          const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + abuf * Cfg::ACC_COLS + (uint32_t)cc;
           if (CW == 32) tmem_ld32(taddr, raw); else tmem_ld16(taddr, raw);
           tmem_ld_wait();
           float f[CW];
@@ -744,15 +752,15 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(Gather g, FastDiv d
     const int KS = ts.KS, SL = BN / KS, sl4 = SL >> 2;
     const uint32_t rank = cluster_ctarank();
     const uint32_t recv = a_base;   // [KS][SL/4][128 rows] float4
-    const int row = warp * 32 + lane;
+    const int row = q * 32 + lane;
     tc_fence_before();
     cluster_sync_all();             // #1: all main loops done (every epilogue warp saw acc_full)
     tc_fence_after();
-    if (warp < 4) {
+    if (is_epi) {
 #pragma unroll 1
-      for (int cc = 0; cc < BN; cc += CW) {
+      for (int cc = half * CW; cc < BN; cc += 2 * CW) {
         uint32_t raw[CW];
-        const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)cc;
+        const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)cc;
         if (CW == 32) tmem_ld32(taddr, raw); else tmem_ld16(taddr, raw);
         tmem_ld_wait();
 #pragma unroll
@@ -765,12 +773,12 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(Gather g, FastDiv d
       }
     }
     cluster_sync_all();             // #2: all partials have landed
-    if (warp < 4) {
+    if (is_epi) {
       const int m = my_mt * TC_BM + row;
       const bool row_ok = m < g.M;
       const int cslice = (int)rank * SL;     // first column of my slice within the tile
 #pragma unroll 1
-      for (int ch = 0; ch < SL; ch += 16) {
+      for (int ch = half * 16; ch < SL; ch += 32) {
         float f[16];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -782,14 +790,14 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(Gather g, FastDiv d
           f[4 * q] = a.x; f[4 * q + 1] = a.y; f[4 * q + 2] = a.z; f[4 * q + 3] = a.w;
         }
         const int ct = cslice + ch;          // column within the tile
-        epilogue_chunk<16>(f, e, (long long)m, row_ok, my_nt * BN + ct, 0, 0, 0, do_stats, s_stat + warp * 2 * BN + ct,
-                           s_stat + warp * 2 * BN + BN + ct, lane);
+        epilogue_chunk<16>(f, e, (long long)m, row_ok, my_nt * BN + ct, 0, 0, 0, do_stats, s_stat + q * 2 * BN + ct,
+                           s_stat + q * 2 * BN + BN + ct, lane);
       }
       if (do_stats) flush_stats(my_nt);
       if (FUSE == 1) {
         fuse_finalize(my_nt, my_mt == 0 && rank == 0);
 #pragma unroll 1
-        for (int ch = 0; ch < SL; ch += 16) {
+        for (int ch = half * 16; ch < SL; ch += 32) {
           float f[16];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
