@@ -436,6 +436,12 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(Gather g, FastDiv d
   if (warp == 5 && lane == 0) {
     tma_prefetch_desc(&tmB);
     if (PATH == 2) tma_prefetch_desc(&tmA);
+    // The packed weights are not written by the preceding kernel (pack_all ran at the start of the step), so the first
+    // pipeline stages' weight tiles are pulled into L2 now, while the previous kernel is still draining (PDL prologue).
+    int mt0, nt0, ks0;
+    decode_tile(ts, blockIdx.x, mt0, nt0, ks0);
+    const int kbp = ks0 * ts.kb_per_split;
+    for (int i = 0; i < STAGES && kbp + i < ts.nkb; ++i) tma_prefetch_l2_2d(&tmB, (kbp + i) * TC_BK, nt0 * BN);
   }
   if (warp == 4) tmem_alloc(smem_u32((const void*)tmem_ptr_slot), Cfg::TMEM_COLS);
   tc_fence_before();
@@ -781,13 +787,13 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(Gather g, FastDiv d
       for (int ch = half * 16; ch < SL; ch += 32) {
         float f[16];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int c4 = 0; c4 < 4; ++c4) {
           float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
           for (int r = 0; r < KS; ++r) {
-            const float4 v = ld_shared_f4(recv + (uint32_t)(((r * sl4 + (ch >> 2) + q) * 128 + row) * 16));
+            const float4 v = ld_shared_f4(recv + (uint32_t)(((r * sl4 + (ch >> 2) + c4) * 128 + row) * 16));
             a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
           }
-          f[4 * q] = a.x; f[4 * q + 1] = a.y; f[4 * q + 2] = a.z; f[4 * q + 3] = a.w;
+          f[4 * c4] = a.x; f[4 * c4 + 1] = a.y; f[4 * c4 + 2] = a.z; f[4 * c4 + 3] = a.w;
         }
         const int ct = cslice + ch;          // column within the tile
         epilogue_chunk<16>(f, e, (long long)m, row_ok, my_nt * BN + ct, 0, 0, 0, do_stats, s_stat + q * 2 * BN + ct,
@@ -800,13 +806,13 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(Gather g, FastDiv d
         for (int ch = half * 16; ch < SL; ch += 32) {
           float f[16];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
+          for (int c4 = 0; c4 < 4; ++c4) {
             float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
             for (int r = 0; r < KS; ++r) {
-              const float4 v = ld_shared_f4(recv + (uint32_t)(((r * sl4 + (ch >> 2) + q) * 128 + row) * 16));
+              const float4 v = ld_shared_f4(recv + (uint32_t)(((r * sl4 + (ch >> 2) + c4) * 128 + row) * 16));
               a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
             }
-            f[4 * q] = a.x; f[4 * q + 1] = a.y; f[4 * q + 2] = a.z; f[4 * q + 3] = a.w;
+            f[4 * c4] = a.x; f[4 * c4 + 1] = a.y; f[4 * c4 + 2] = a.z; f[4 * c4 + 3] = a.w;
           }
           fuse_apply(f, 16, (long long)m, row_ok, my_nt, cslice + ch);
         }
@@ -1041,6 +1047,9 @@ __global__ void __launch_bounds__(SlabCfg<BN>::THREADS) conv_slab_kernel(const _
   if (warp == 4 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    const int cchp = ss.row_bytes >> 1;   // weights are not produced by the previous kernel: warm L2 during the PDL prologue
+    for (int t = 0; t < 9; ++t)
+      for (int c = 0; c < ss.chunks; ++c) tma_prefetch_l2_2d(&tmB, t * ss.ctot + c * cchp, 0);
   }
   if (warp == 5) tmem_alloc(smem_u32((const void*)tmem_ptr_slot), tmem_cols);
   tc_fence_before();

@@ -28,6 +28,12 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm,
       "l"(reinterpret_cast<uint64_t>(tm)), "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(bar)
       : "memory");
 }
+// L2 prefetch of a 2-D box (no shared-memory destination, no barrier): used before griddepcontrol.wait for operands the
+// previous kernel does not produce (packed weights), so the first real loads of the main loop hit L2
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* tm, int x0, int x1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(x0), "r"(x1)
+               : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
 }
