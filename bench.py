@@ -194,21 +194,53 @@ def run_d3fk(args):
     final_loss = float(loss)
 
     # ---------------- end to end through the public API with host buffers ("e2e")
+    # Every step copies its input batch from pinned host memory and reads its loss back to the host.  As a training
+    # loop does, the copy of step i+1 is issued on a copy stream while step i computes (two device buffers), and the
+    # loss of step i is read through a pinned buffer one step later (no host stall in the middle of the pipeline);
+    # all K copies and all K reads happen inside the timed region.
     host = torch.empty((B, 3, H, W), dtype=torch.float32).pin_memory()
     host.copy_(x)
-    xin = torch.empty_like(x)
-    for _ in range(2):
-        xin.copy_(host, non_blocking=True)
-        float(mod.training_step(xin))
+    xin = [torch.empty_like(x), torch.empty_like(x)]
+    loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+    copy_stream = torch.cuda.Stream(dev)
+    main_stream = torch.cuda.current_stream(dev)
+    copied = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+    loss_ready = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def issue_copy(i):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[i & 1])          # the step that last read this buffer is done with it
+            xin[i & 1].copy_(host, non_blocking=True)
+            copied[i & 1].record(copy_stream)
+
+    def run_e2e(n):
+        losses = []
+        for ev in consumed:
+            ev.record(main_stream)
+        issue_copy(0)
+        for i in range(n):
+            if i + 1 < n:
+                issue_copy(i + 1)
+            main_stream.wait_event(copied[i & 1])
+            l = mod.training_step(xin[i & 1])
+            consumed[i & 1].record(main_stream)
+            loss_host[i & 1:(i & 1) + 1].copy_(l.detach().reshape(1), non_blocking=True)
+            loss_ready[i & 1].record(main_stream)
+            if i >= 1:
+                loss_ready[(i - 1) & 1].synchronize()
+                losses.append(float(loss_host[(i - 1) & 1]))          # device->host read of step i-1's result
+        loss_ready[(n - 1) & 1].synchronize()
+        losses.append(float(loss_host[(n - 1) & 1]))
+        return losses
+
+    run_e2e(2)
     barrier()
-    t0 = time.perf_counter()
     e0.record()
-    for _ in range(args.steps):
-        xin.copy_(host, non_blocking=True)
-        l = mod.training_step(xin)
-        _ = float(l)                                # device->host read of the step's result
+    e2e_losses = run_e2e(args.steps)
     e1.record()
     barrier()
+    assert len(e2e_losses) == args.steps
     ms_e2e = e0.elapsed_time(e1)
     if world > 1:
         t = torch.tensor([ms_e2e], device=dev)

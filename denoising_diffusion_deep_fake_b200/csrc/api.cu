@@ -43,6 +43,9 @@ int launch_bn_apply(const d3fk_bn_params*, cudaStream_t);
 int launch_bn_bwd_reduce(const d3fk_bn_params*, cudaStream_t);
 int launch_bn_bwd_finalize(const d3fk_bn_params*, cudaStream_t);
 int launch_bn_bwd_apply(const d3fk_bn_params*, cudaStream_t);
+int launch_bn_bwd(const d3fk_bn_params*, cudaStream_t);
+extern int g_fuse_bn_bwd;
+extern long long g_fuse_bn_bwd_max;
 int launch_maxpool_fwd(const d3fk_pool_params*, cudaStream_t);
 int launch_maxpool_bwd(const d3fk_pool_params*, cudaStream_t);
 int launch_sumpool2(const d3fk_pool_params*, cudaStream_t);
@@ -92,6 +95,7 @@ static int run_one(const d3fk_op* op, cudaStream_t s) {
     case D3FK_OP_BN_BWD_REDUCE: return launch_bn_bwd_reduce(&op->u.bn, s);
     case D3FK_OP_BN_BWD_FINALIZE: return launch_bn_bwd_finalize(&op->u.bn, s);
     case D3FK_OP_BN_BWD_APPLY: return launch_bn_bwd_apply(&op->u.bn, s);
+    case D3FK_OP_BN_BWD: return launch_bn_bwd(&op->u.bn, s);
     case D3FK_OP_MAXPOOL_FWD: return launch_maxpool_fwd(&op->u.pool, s);
     case D3FK_OP_MAXPOOL_BWD: return launch_maxpool_bwd(&op->u.pool, s);
     case D3FK_OP_SUMPOOL2: return launch_sumpool2(&op->u.pool, s);
@@ -141,6 +145,8 @@ int d3fk_init(int device) {
     cudaMemset(g_dev_error_flag, 0, dbg_bytes);
   }
   if (const char* v = getenv("D3FK_PDL")) g_use_pdl = atoi(v);
+  if (const char* v = getenv("D3FK_FUSE_BN_BWD")) g_fuse_bn_bwd = atoi(v);
+  if (const char* v = getenv("D3FK_FUSE_BN_BWD_MAX")) g_fuse_bn_bwd_max = atoll(v);
   int rc = tc_init();
   if (rc) return rc;
   rc = loss_init();
@@ -272,6 +278,7 @@ SINGLE(d3fk_bn_fold, d3fk_bn_params, launch_bn_fold)
 SINGLE(d3fk_bn_bwd_reduce, d3fk_bn_params, launch_bn_bwd_reduce)
 SINGLE(d3fk_bn_bwd_finalize, d3fk_bn_params, launch_bn_bwd_finalize)
 SINGLE(d3fk_bn_bwd_apply, d3fk_bn_params, launch_bn_bwd_apply)
+SINGLE(d3fk_bn_bwd, d3fk_bn_params, launch_bn_bwd)
 SINGLE(d3fk_maxpool_fwd, d3fk_pool_params, launch_maxpool_fwd)
 SINGLE(d3fk_maxpool_bwd, d3fk_pool_params, launch_maxpool_bwd)
 SINGLE(d3fk_sumpool2, d3fk_pool_params, launch_sumpool2)

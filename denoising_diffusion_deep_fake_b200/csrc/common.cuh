@@ -59,6 +59,24 @@ static inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 blo
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 #ifdef __CUDACC__
+// grid-wide barrier for a co-resident grid (called by ONE thread per CTA, after its CTA's global writes / atomics)
+__device__ __forceinline__ void grid_barrier_arrive_wait(unsigned* counter, unsigned expected, int* errflag) {
+  __threadfence();
+  atomicAdd(counter, 1u);
+  const long long t0 = clock64();
+  while (true) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+    if (v >= expected) break;
+    if (clock64() - t0 > 4000000000ll) {   // ~2 s: the grid was not co-resident
+      atomicExch(errflag, 2);
+      break;
+    }
+    __nanosleep(64);
+  }
+  __threadfence();
+}
+
 __device__ __forceinline__ void pdl_enter() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");

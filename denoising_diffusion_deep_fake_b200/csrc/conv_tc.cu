@@ -361,24 +361,6 @@ struct FuseBN {
   float eps, momentum;
 };
 
-// grid-wide barrier for a co-resident grid (called by ONE thread per CTA, after its CTA's global writes / atomics)
-__device__ __forceinline__ void grid_barrier_arrive_wait(unsigned* counter, unsigned expected, int* errflag) {
-  __threadfence();
-  atomicAdd(counter, 1u);
-  const long long t0 = clock64();
-  while (true) {
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
-    if (v >= expected) break;
-    if (clock64() - t0 > 4000000000ll) {   // ~2 s: the grid was not co-resident
-      atomicExch(errflag, 2);
-      break;
-    }
-    __nanosleep(64);
-  }
-  __threadfence();
-}
-
 // PATH 0 (LINEAR): one source, no upsample, forward gather or stride-1 transposed gather — the tap
 //   offset is the same for every row, so a row costs two compares, one 64-bit add and the cp.async.
 // PATH 1 (GENERIC): nearest-2x upsample + channel concat (decoder conv1) and stride-2 transposed gather.

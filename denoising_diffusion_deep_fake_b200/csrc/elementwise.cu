@@ -8,6 +8,8 @@
 namespace d3fk {
 
 static constexpr int kSMs = 148;
+int g_fuse_bn_bwd = 0;   // D3FK_FUSE_BN_BWD=1: BN backward as one kernel behind a grid barrier (measured: no faster than two PDL launches)
+long long g_fuse_bn_bwd_max = 4ll << 20;   // D3FK_FUSE_BN_BWD_MAX: largest tensor (elements) that takes the one-launch form
 static inline int grid_for(long long work_items, int threads, int max_waves = 8) {
   long long blocks = (work_items + threads - 1) / threads;
   long long cap = (long long)kSMs * max_waves;
@@ -160,10 +162,8 @@ __global__ void __launch_bounds__(256, 2) bn_apply_kernel(d3fk_bn_params p) {
 // Lanes of a warp that own the same channel vector are folded with shuffles, warps with one shared-memory
 // slot each, the block with one double atomic per channel.
 template <typename T, typename Acc>
-__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(d3fk_bn_params p) {
-  pdl_enter();
+__device__ __forceinline__ void bn_bwd_reduce_body(const d3fk_bn_params& p, double* sred) {
   constexpr int V = Vec<T>::N;
-  extern __shared__ double sred[];  // [warps][2][C]
   const int C = p.C, cvs = C / V;
   const int nwarp = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rows_per_iter = blockDim.x / cvs;
@@ -245,6 +245,12 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(d3fk_bn_params p) {
     atomicAdd(&p.bstats[which * C + ch], a);
   }
 }
+template <typename T, typename Acc>
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(d3fk_bn_params p) {
+  pdl_enter();
+  extern __shared__ double sred_dyn[];  // [warps][2][C]
+  bn_bwd_reduce_body<T, Acc>(p, sred_dyn);
+}
 
 __global__ void bn_bwd_finalize_kernel(d3fk_bn_params p) {
   pdl_enter();
@@ -263,8 +269,7 @@ __global__ void bn_bwd_finalize_kernel(d3fk_bn_params p) {
 // The coefficients are derived in-kernel from the reduction sums; the first C/V threads of block 0 also write
 // dgamma / dbeta (no separate finalize launch).
 template <typename T>
-__global__ void bn_bwd_apply_kernel(d3fk_bn_params p) {
-  pdl_enter();
+__device__ __forceinline__ void bn_bwd_apply_body(const d3fk_bn_params& p, float* s_k) {
   constexpr int V = Vec<T>::N;
   const int cvs = p.C / V;
   const long long total = p.count * cvs;
@@ -276,10 +281,10 @@ __global__ void bn_bwd_apply_kernel(d3fk_bn_params p) {
   const long long e0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
   const int c = (int)(e0 % cvs) * V;
-  extern __shared__ float s_k[];     // [5][C]: k0, k1, k2, mean, invstd — derived once per block
+  // s_k: [5][C]: k0, k1, k2, mean, invstd — derived once per block (L2 loads: the sums were produced by atomics)
   for (int ch = threadIdx.x; ch < p.C; ch += blockDim.x) {
     const double n = (double)p.count;
-    const double s1 = p.bstats[ch], s2 = p.bstats[p.C + ch];
+    const double s1 = __ldcg(p.bstats + ch), s2 = __ldcg(p.bstats + p.C + ch);
     const float is = __ldg(p.invstd + ch);
     s_k[ch] = __ldg(p.gamma + ch) * is;
     s_k[p.C + ch] = (float)(s1 / n);
@@ -330,6 +335,26 @@ __global__ void bn_bwd_apply_kernel(d3fk_bn_params p) {
       }
     }
   }
+}
+
+template <typename T>
+__global__ void bn_bwd_apply_kernel(d3fk_bn_params p) {
+  pdl_enter();
+  extern __shared__ float s_k_dyn[];
+  bn_bwd_apply_body<T>(p, s_k_dyn);
+}
+
+// BN backward in ONE launch for a co-resident grid: reduction, grid barrier, apply (the tensors of the deep layers are a
+// few MB — the second read comes from L2 and a kernel boundary costs more than the barrier).
+template <typename T, typename Acc>
+__global__ void __launch_bounds__(256, 2) bn_bwd_kernel(d3fk_bn_params p, int* errflag) {
+  pdl_enter();
+  extern __shared__ double smem_bwd[];
+  bn_bwd_reduce_body<T, Acc>(p, smem_bwd);
+  __syncthreads();
+  if (threadIdx.x == 0) grid_barrier_arrive_wait(p.barrier, gridDim.x, errflag);
+  __syncthreads();
+  bn_bwd_apply_body<T>(p, reinterpret_cast<float*>(smem_bwd));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -721,6 +746,32 @@ int launch_bn_bwd_apply(const d3fk_bn_params* p, cudaStream_t s) {
   DISPATCH_T(p->dtype, launch_k(bn_bwd_apply_kernel<T>, dim3(grid_for(total, 256 * 4, 4)), dim3(256), 5 * p->C * sizeof(float), s, dim3(1, 1, 1), *p));
   count_launch();
   return check_launch("bn_bwd_apply");
+}
+int launch_bn_bwd(const d3fk_bn_params* p, cudaStream_t s) {
+  D3FK_CHECK_ARG(p->C % 8 == 0 && p->C <= 1024, "C must be a multiple of 8, <= 1024");
+  const int V = p->dtype == D3FK_F32 ? 4 : 8;
+  const int cvs = p->C / V;
+  const bool pow2 = (cvs & (cvs - 1)) == 0 && cvs <= 256;
+  // one launch only where latency dominates (tensor <= 4 M elements: L2-resident second pass); big layers stream twice
+  if (!p->barrier || !pow2 || !g_fuse_bn_bwd || p->count * (long long)p->C > g_fuse_bn_bwd_max) {
+    int rc = launch_bn_bwd_reduce(p, s);
+    return rc ? rc : launch_bn_bwd_apply(p, s);
+  }
+  const int threads = 256;
+  const int rows = threads / cvs;
+  // co-resident grid: at most 2 blocks per SM (launch bounds), sized like the reduce kernel
+  int grid = cdiv(p->count, (long long)rows * 8);
+  if (grid > kSMs * 2) grid = kSMs * 2;
+  if (grid < 1) grid = 1;
+  const int slotC = cvs < 32 ? p->C : 32 * V;
+  size_t smem = (size_t)(threads / 32) * 2 * slotC * sizeof(double);
+  const size_t smem_apply = 5 * (size_t)p->C * sizeof(float);
+  if (smem_apply > smem) smem = smem_apply;
+  if (p->dtype == D3FK_F32) launch_k(bn_bwd_kernel<float, double>, dim3(grid), dim3(threads), smem, s, dim3(1, 1, 1), *p, g_dev_error_flag);
+  else if (p->dtype == D3FK_BF16) launch_k(bn_bwd_kernel<__nv_bfloat16, float>, dim3(grid), dim3(threads), smem, s, dim3(1, 1, 1), *p, g_dev_error_flag);
+  else return set_error(D3FK_ERR_ARG, "bad dtype");
+  count_launch();
+  return check_launch("bn_bwd");
 }
 int launch_maxpool_fwd(const d3fk_pool_params* p, cudaStream_t s) {
   D3FK_CHECK_ARG(p->C % 8 == 0 && p->H % 2 == 0 && p->W % 2 == 0, "C%8, H%2, W%2");

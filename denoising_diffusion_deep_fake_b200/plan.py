@@ -396,8 +396,10 @@ class UnetPlan:
             bn.update(dres=g_masked.ptr, lddres=g_masked.ld)
         bn.pop("res", None)
         bn.pop("ldr", None)
-        ops.append(make_op(_lib.OP_BN_BWD_REDUCE, **bn))
-        ops.append(make_op(_lib.OP_BN_BWD_APPLY, **bn))       # derives its coefficients, writes dgamma/dbeta
+        # reduce + apply as ONE op (one kernel behind a grid barrier); the apply phase derives its coefficients and
+        # writes dgamma / dbeta.  The barrier counter is cleared by the backward's statistics memset.
+        bn["barrier"] = self.bn_barrier[c.bn] + self.stats.stride(0) * 8
+        ops.append(make_op(_lib.OP_BN_BWD, **bn))
         return d_raw, g_masked
 
     def _newT(self, like, C=None, H=None, W=None):

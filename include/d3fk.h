@@ -105,6 +105,7 @@ typedef struct d3fk_bn_params {
   double* bstats;                       /* [2][C] sum dy', sum dy'*xhat */
   float* dgamma; float* dbeta;
   float* coef;                          /* [3][C] scratch written by bn_bwd_finalize */
+  uint32_t* barrier;                    /* D3FK_OP_BN_BWD: zeroed grid-barrier counter (NULL: reduce and apply as two kernels) */
 } d3fk_bn_params;
 
 /* ---- convolution + train-mode BatchNorm (+residual) + ReLU as ONE op (the forward of every conv->BN->ReLU of the U-Net).
@@ -203,7 +204,8 @@ enum d3fk_op_kind {
   D3FK_OP_PACK_ALL = 20, /* misc: p0 = device array of d3fk_pack_params, n = (blocks << 17) | (count << 1) | is_bf16 */
   D3FK_OP_LOSS = 21,
   D3FK_OP_CONV_BN = 22,
-  D3FK_OP_UPCAT = 23
+  D3FK_OP_UPCAT = 23,
+  D3FK_OP_BN_BWD = 24    /* bn params: bn_bwd_reduce + bn_bwd_apply as one op (one kernel behind a grid barrier when `barrier` is set) */
 };
 
 typedef struct d3fk_op {
@@ -250,6 +252,7 @@ int d3fk_bn_fold(const d3fk_bn_params* p, d3fk_stream stream);
 int d3fk_bn_bwd_reduce(const d3fk_bn_params* p, d3fk_stream stream);
 int d3fk_bn_bwd_finalize(const d3fk_bn_params* p, d3fk_stream stream);
 int d3fk_bn_bwd_apply(const d3fk_bn_params* p, d3fk_stream stream);
+int d3fk_bn_bwd(const d3fk_bn_params* p, d3fk_stream stream);
 int d3fk_maxpool_fwd(const d3fk_pool_params* p, d3fk_stream stream);
 int d3fk_maxpool_bwd(const d3fk_pool_params* p, d3fk_stream stream);
 int d3fk_sumpool2(const d3fk_pool_params* p, d3fk_stream stream);

@@ -242,6 +242,11 @@ def run_pack_all(p):
         run_pack(table[i])
 
 
+def run_bn_bwd(p):
+    run_bn_bwd_reduce(p)
+    run_bn_bwd_apply(p)
+
+
 def run_upcat(p):
     a = nhwc(p.src0, p.B, p.H // 2, p.W // 2, p.ld0, p.c0)
     out = nhwc(p.out, p.B, p.H, p.W, p.ldo, p.c0 + p.c1)
@@ -265,7 +270,7 @@ _DISPATCH = {
     _lib.OP_BN_BWD_REDUCE: run_bn_bwd_reduce, _lib.OP_BN_BWD_FINALIZE: run_bn_bwd_finalize,
     _lib.OP_BN_BWD_APPLY: run_bn_bwd_apply, _lib.OP_MAXPOOL_FWD: run_maxpool_fwd, _lib.OP_MAXPOOL_BWD: run_maxpool_bwd,
     _lib.OP_SUMPOOL2: run_sumpool2, _lib.OP_CHANSUM: run_chansum, _lib.OP_MEMSET: run_memset,
-    _lib.OP_PACK_ALL: run_pack_all, _lib.OP_CONV_BN: run_conv_bn, _lib.OP_UPCAT: run_upcat,
+    _lib.OP_PACK_ALL: run_pack_all, _lib.OP_CONV_BN: run_conv_bn, _lib.OP_UPCAT: run_upcat, _lib.OP_BN_BWD: run_bn_bwd,
 }
 
 

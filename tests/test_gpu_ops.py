@@ -211,6 +211,14 @@ def test_bn_train_fwd_bwd(dtype, C, count, relu, res):
     r = run_both(_lib.OP_BN_BWD_APPLY, dtype, t, sc, ["dx", "dres", "dgamma", "dbeta"])
     for n, (a, b) in r.items():
         assert rel_err(a, b) < (1e-5 if dtype == _lib.F32 else 6e-3), n
+    # the fused form the plans run: reduce + grid barrier + apply in one launch (zeroed sums and barrier counter in)
+    t["bstats"] = torch.zeros(2, C, dtype=torch.float64)
+    t["barrier"] = torch.zeros(2, dtype=torch.int32)
+    t["dgamma"], t["dbeta"] = torch.zeros(C), torch.zeros(C)
+    t["dx"], t["dres"] = torch.zeros(count, C), torch.zeros(count, C)
+    r = run_both(_lib.OP_BN_BWD, dtype, t, sc, ["dx", "dres", "dgamma", "dbeta", "bstats"])
+    for n, (a, b) in r.items():
+        assert rel_err(a, b) < (1e-5 if dtype == _lib.F32 else 6e-3), n
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
