@@ -187,7 +187,10 @@ static int ensure_side_stream() {
   if (g_side_stream) return D3FK_OK;
   if (const char* v = getenv("D3FK_FORK_WGRAD")) g_fork_wgrad = atoi(v);
   if (const char* v = getenv("D3FK_SKIP_WGRAD")) g_skip_wgrad = atoi(v);
-  cudaError_t e = cudaStreamCreateWithFlags(&g_side_stream, cudaStreamNonBlocking);
+  // (a higher-priority main stream was measured: no gain — both chains are latency-bound, not slot-bound)
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  cudaError_t e = cudaStreamCreateWithPriority(&g_side_stream, cudaStreamNonBlocking, prio_lo);
   if (e != cudaSuccess) return set_error(D3FK_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
   for (int i = 0; i < 64 && e == cudaSuccess; ++i) { e = cudaEventCreateWithFlags(&g_fork_events[i], cudaEventDisableTiming); g_n_fork_events = i + 1; }
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g_join_event, cudaEventDisableTiming);
