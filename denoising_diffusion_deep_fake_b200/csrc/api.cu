@@ -174,9 +174,13 @@ int d3fk_device_error_flag(void) {
 // Weight gradients are off the backward critical path (dgrad_L -> BN-backward_{L-1} -> dgrad_{L-1} ...): d3fk_run forks
 // every OP_WGRAD onto a side stream behind an event recorded after its producer and joins the side stream at the end of
 // the op list, so the latency-bound deep-layer kernels of the two chains overlap.  Event record / wait are capture-safe.
-static cudaStream_t g_side_stream = nullptr;
+constexpr int MAX_SIDE = 8;
+static cudaStream_t g_side_streams[MAX_SIDE] = {nullptr};
+static cudaEvent_t g_join_events[MAX_SIDE];
+static int g_n_side = 3;       // D3FK_SIDE_STREAMS: weight gradients of different layers are independent of each other
+static unsigned g_side_cursor = 0;
+#define g_side_stream g_side_streams[0]
 static cudaEvent_t g_fork_events[64];
-static cudaEvent_t g_join_event = nullptr;
 static int g_n_fork_events = 0;
 static unsigned g_fork_cursor = 0;
 static bool g_side_pending = false;
@@ -190,10 +194,15 @@ static int ensure_side_stream() {
   // (a higher-priority main stream was measured: no gain — both chains are latency-bound, not slot-bound)
   int prio_lo = 0, prio_hi = 0;
   cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-  cudaError_t e = cudaStreamCreateWithPriority(&g_side_stream, cudaStreamNonBlocking, prio_lo);
-  if (e != cudaSuccess) return set_error(D3FK_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+  if (const char* v = getenv("D3FK_SIDE_STREAMS")) g_n_side = atoi(v);
+  if (g_n_side < 1) g_n_side = 1;
+  if (g_n_side > MAX_SIDE) g_n_side = MAX_SIDE;
+  cudaError_t e = cudaSuccess;
+  for (int i = 0; i < g_n_side && e == cudaSuccess; ++i) {
+    e = cudaStreamCreateWithPriority(&g_side_streams[i], cudaStreamNonBlocking, prio_lo);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g_join_events[i], cudaEventDisableTiming);
+  }
   for (int i = 0; i < 64 && e == cudaSuccess; ++i) { e = cudaEventCreateWithFlags(&g_fork_events[i], cudaEventDisableTiming); g_n_fork_events = i + 1; }
-  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g_join_event, cudaEventDisableTiming);
   if (e != cudaSuccess) return set_error(D3FK_ERR_CUDA, "cudaEventCreate: %s", cudaGetErrorString(e));
   return D3FK_OK;
 }
@@ -208,11 +217,12 @@ static int run_list(const d3fk_op* ops, int n_ops, cudaStream_t s, bool join) {
     if (ops[i].kind == D3FK_OP_WGRAD && g_skip_wgrad) continue;   // timing experiment only (D3FK_SKIP_WGRAD=1)
     if (ops[i].kind == D3FK_OP_WGRAD && g_fork_wgrad && n_ops > 1) {
       cudaEvent_t ev = g_fork_events[g_fork_cursor++ % g_n_fork_events];
+      cudaStream_t side = g_side_streams[g_side_cursor++ % g_n_side];   // round robin: no false wgrad -> wgrad ordering
       cudaError_t e = cudaEventRecord(ev, s);
-      if (e == cudaSuccess) e = cudaStreamWaitEvent(g_side_stream, ev, 0);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(side, ev, 0);
       if (e != cudaSuccess) return set_error(D3FK_ERR_CUDA, "fork: %s", cudaGetErrorString(e));
       ++forks;
-      rc = run_one(&ops[i], g_side_stream);
+      rc = run_one(&ops[i], side);
     } else {
       rc = run_one(&ops[i], s);
     }
@@ -235,10 +245,12 @@ int d3fk_run(const d3fk_op* ops, int n_ops, d3fk_stream stream) { return run_lis
 int d3fk_run_nojoin(const d3fk_op* ops, int n_ops, d3fk_stream stream) { return run_list(ops, n_ops, (cudaStream_t)stream, false); }
 
 int d3fk_side_stream_join(d3fk_stream stream) {
-  if (!g_side_stream) return D3FK_OK;
-  cudaError_t e = cudaEventRecord(g_join_event, g_side_stream);
-  if (e == cudaSuccess) e = cudaStreamWaitEvent((cudaStream_t)stream, g_join_event, 0);
-  if (e != cudaSuccess) return set_error(D3FK_ERR_CUDA, "join: %s", cudaGetErrorString(e));
+  if (!g_side_streams[0]) return D3FK_OK;
+  for (int i = 0; i < g_n_side; ++i) {
+    cudaError_t e = cudaEventRecord(g_join_events[i], g_side_streams[i]);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent((cudaStream_t)stream, g_join_events[i], 0);
+    if (e != cudaSuccess) return set_error(D3FK_ERR_CUDA, "join: %s", cudaGetErrorString(e));
+  }
   g_side_pending = false;
   return D3FK_OK;
 }
