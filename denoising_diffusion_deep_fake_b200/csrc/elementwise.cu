@@ -304,13 +304,16 @@ __device__ __forceinline__ void bn_bwd_apply_body(const d3fk_bn_params& p, float
     mean[i] = s_k[3 * p.C + c + i]; istd[i] = s_k[4 * p.C + c + i];
   }
   constexpr int U = 2;   // independent pixel vectors in flight per thread (3 loads each)
+  // Walk the tensor BACKWARDS: the reduction pass that ran just before streamed x, dy and act front to back, so their
+  // tails are what the 126 MB L2 still holds.
+  const long long last_pix = p.count - 1;
   for (long long e = e0; e < total; e += U * stride) {
     float xv[U][V], gv[U][V], av[U][V];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long eu = e + u * stride;
       if (eu < total) {
-        const long long pix = eu / cvs;
+        const long long pix = last_pix - eu / cvs;
         load_vec<T>(x + pix * p.ldx + c, xv[u]);
         load_vec<T>(dy + pix * p.lddy + c, gv[u]);
         if (p.relu) load_vec<T>(act + pix * p.ldact + c, av[u]);
@@ -320,7 +323,7 @@ __device__ __forceinline__ void bn_bwd_apply_body(const d3fk_bn_params& p, float
     for (int u = 0; u < U; ++u) {
       const long long eu = e + u * stride;
       if (eu < total) {
-        const long long pix = eu / cvs;
+        const long long pix = last_pix - eu / cvs;
         float o[V];
 #pragma unroll
         for (int i = 0; i < V; ++i) {
