@@ -18,7 +18,9 @@ class ConvParams(C.Structure):
                 ("kh", i32), ("kw", i32), ("stride", i32), ("pad", i32),
                 ("w", vp), ("Cout", i32), ("_pad0", i32),
                 ("out", vp), ("out_nchw", vp), ("scale", vp), ("shift", vp), ("res", vp), ("stats", vp),
-                ("ldo", i32), ("ldr", i32), ("relu", i32), ("_pad1", i32), ("ws", vp), ("ws_bytes", i64)]
+                ("ldo", i32), ("ldr", i32), ("relu", i32), ("_pad1", i32), ("ws", vp), ("ws_bytes", i64),
+                ("bw_x", vp), ("bw_act", vp), ("bw_mean", vp), ("bw_invstd", vp),
+                ("bw_ldx", i32), ("bw_ldact", i32), ("bw_relu", i32), ("_pad2", i32)]
 
 
 class WgradParams(C.Structure):

@@ -70,6 +70,8 @@ __device__ __forceinline__ void grid_barrier_arrive_wait(unsigned* counter, unsi
     if (v >= expected) break;
     if (clock64() - t0 > 4000000000ll) {   // ~2 s: the grid was not co-resident
       atomicExch(errflag, 2);
+      printf("[d3fk] grid barrier timeout: block %d of %d saw %u arrivals (expected %u), counter %p\n", (int)blockIdx.x, (int)gridDim.x, v,
+             expected, (void*)counter);
       break;
     }
     __nanosleep(64);

@@ -231,7 +231,43 @@ __device__ __forceinline__ float warp_colsum16(float* v, int lane) {
 struct EpiTC {
   bf16* out; float* out_nchw; const float* scale; const float* shift; const bf16* res; double* stats;
   int ldo, ldr, relu, Cout, Ho, Wo;
+  // BN-backward reduction fused into a dgrad epilogue (bw_x set): the stored output v is the gradient wrt the activation of
+  // the previous layer; the statistics become sum(g') and sum(g' * xhat) with g' = v masked by that layer's ReLU
+  // (bw_act > 0) and xhat = (bw_x - mean) * invstd — exactly what bn_bwd_reduce would compute in a second pass.
+  const bf16* bw_x; const bf16* bw_act; const float* bw_mean; const float* bw_invstd;
+  int bw_ldx, bw_ldact, bw_relu;
 };
+
+// in place: f -> g' ; sq -> g' * x (rows outside the tensor contribute zero).  The per-channel mean / invstd are applied
+// once per CTA when the partial sums are flushed: sum(g' * xhat) = invstd * (sum(g' * x) - mean * sum(g')).
+template <int CW>
+__device__ __forceinline__ void bw_stat_terms(float (&f)[CW], float (&sq)[CW], const EpiTC& e, long long m, bool row_ok, int cbase) {
+  if (!row_ok) {
+#pragma unroll
+    for (int i = 0; i < CW; ++i) { f[i] = 0.f; sq[i] = 0.f; }
+    return;
+  }
+#pragma unroll
+  for (int q8 = 0; q8 < CW / 8; ++q8) {
+    const uint4 xr = __ldg(reinterpret_cast<const uint4*>(e.bw_x + m * e.bw_ldx + cbase + q8 * 8));
+    const bf16* xb = reinterpret_cast<const bf16*>(&xr);
+    uint4 ar = make_uint4(0u, 0u, 0u, 0u);
+    if (e.bw_relu) ar = __ldg(reinterpret_cast<const uint4*>(e.bw_act + m * e.bw_ldact + cbase + q8 * 8));
+    const bf16* ab = reinterpret_cast<const bf16*>(&ar);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = q8 * 8 + i;
+      float gsel = f[c];
+      if (e.bw_relu && !(__bfloat162float(ab[i]) > 0.f)) gsel = 0.f;
+      f[c] = gsel;
+      sq[c] = gsel * __bfloat162float(xb[i]);
+    }
+  }
+}
+// per-CTA partial sums (a = sum g', b = sum g' * x) of channel ch -> the second BN-backward sum
+__device__ __forceinline__ double bw_second_sum(double a, double b, const EpiTC& e, int ch) {
+  return (double)__ldg(e.bw_invstd + ch) * (b - (double)__ldg(e.bw_mean + ch) * a);
+}
 
 struct FastDiv {
   uint32_t mul, shr;
@@ -286,7 +322,7 @@ __device__ __forceinline__ void decode_tile(const TileSched& ts, int t, int& mt,
 // ReLU, store (bf16 NHWC or fp32 NCHW) and per-channel batch statistics.  The statistics are folded over the 32 rows of
 // the warp with a transpose-reduce and ACCUMULATED into this warp's shared-memory slots (sstat_warp[col], [BN + col]);
 // the CTA flushes the slots to global memory with one double atomic per channel when its n tile changes / at the end.
-template <int CW>
+template <int CW, bool BW = true>
 __device__ __forceinline__ void epilogue_chunk(float (&f)[CW], const EpiTC& e, long long m, bool row_ok, int cbase, int on,
                                                int oh, int ow, bool do_stats, float* sstat_sum, float* sstat_sq, int lane) {
   if (e.scale) {
@@ -331,10 +367,14 @@ __device__ __forceinline__ void epilogue_chunk(float (&f)[CW], const EpiTC& e, l
   }
   if (do_stats) {
     float sq[CW];
+    if (BW && e.bw_x) {
+      bw_stat_terms<CW>(f, sq, e, m, row_ok, cbase);
+    } else {
 #pragma unroll
-    for (int i = 0; i < CW; ++i) {
-      if (!row_ok) f[i] = 0.f;
-      sq[i] = f[i] * f[i];
+      for (int i = 0; i < CW; ++i) {
+        if (!row_ok) f[i] = 0.f;
+        sq[i] = f[i] * f[i];
+      }
     }
     float cs, cq;
     if (CW == 32) { cs = warp_colsum32(f, lane); cq = warp_colsum32(sq, lane); }
@@ -369,7 +409,7 @@ struct FuseBN {
 //   hardware zero fill for the padding halo — no per-thread address arithmetic at all.
 // The weight tile is always a TMA 2-D box {64, BN} of the packed [Cout][K] matrix (OOB rows / K tail zero filled).
 template <int BN, int PATH, int FUSE>
-__global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(Gather g, FastDiv dWo, FastDiv dHo, const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(Gather g, FastDiv dWo, FastDiv dHo, const __grid_constant__ CUtensorMap tmA,
                                                              const __grid_constant__ CUtensorMap tmB, EpiTC e, TileSched ts,
                                                              FuseBN fb, int* errflag) {
   using Cfg = ConvCfg<BN>;
@@ -443,7 +483,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(Gather g, FastDiv d
       const float b = (s_stat[BN + tid] + s_stat[3 * BN + tid]) + (s_stat[5 * BN + tid] + s_stat[7 * BN + tid]);
       if (a != 0.f || b != 0.f) {
         atomicAdd(&e.stats[n0 + tid], (double)a);
-        atomicAdd(&e.stats[e.Cout + n0 + tid], (double)b);
+        atomicAdd(&e.stats[e.Cout + n0 + tid], (FUSE == 2 && e.bw_x) ? bw_second_sum((double)a, (double)b, e, n0 + tid) : (double)b);
       }
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -667,7 +707,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(Gather g, FastDiv d
         float f[CW];
 #pragma unroll
         for (int i = 0; i < CW; ++i) f[i] = __uint_as_float(raw[i]);
-        epilogue_chunk<CW>(f, e, (long long)m, row_ok, n0 + cc, on, oh, ow, do_stats, s_stat + q * 2 * BN + cc,
+        epilogue_chunk<CW, FUSE == 2>(f, e, (long long)m, row_ok, n0 + cc, on, oh, ow, do_stats, s_stat + q * 2 * BN + cc,
                            s_stat + q * 2 * BN + BN + cc, lane);
         if (tid == 0 && cc == 0) { TL_STAMP(8) }
       }
@@ -778,7 +818,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(Gather g, FastDiv d
           f[4 * c4] = a.x; f[4 * c4 + 1] = a.y; f[4 * c4 + 2] = a.z; f[4 * c4 + 3] = a.w;
         }
         const int ct = cslice + ch;          // column within the tile
-        epilogue_chunk<16>(f, e, (long long)m, row_ok, my_nt * BN + ct, 0, 0, 0, do_stats, s_stat + q * 2 * BN + ct,
+        epilogue_chunk<16, FUSE == 2>(f, e, (long long)m, row_ok, my_nt * BN + ct, 0, 0, 0, do_stats, s_stat + q * 2 * BN + ct,
                            s_stat + q * 2 * BN + BN + ct, lane);
       }
       if (do_stats) flush_stats(my_nt);
@@ -821,6 +861,12 @@ static int g_max_cluster = 8;   // D3FK_CLUSTER=n: cap the split-K cluster size 
 // Co-resident CTA capacity of a cluster launch, per CTAs-per-SM.  cudaOccupancyMaxActiveClusters reports one CTA per SM
 // for kernels that allocate tensor memory; tools/probes/cluster_residency.cu measured, on B200 at 2 CTAs/SM, 296 CTAs for
 // cluster sizes 1-2, 284 for 4 and 264 for 8 (GPC boundaries strand a few SMs) — the table below keeps a safety margin.
+// GUARANTEED co-resident CTAs of a cluster launch (what cudaOccupancyMaxActiveClusters reports for these kernels: one CTA
+// per SM, minus the SMs GPC boundaries strand) — the bound for anything that spins on a grid-wide barrier.  A 16 x 8-CTA
+// cluster grid of the 320-thread kernel was observed NOT to be co-resident (15 clusters were), although the probe kernel
+// reached 33: the optimistic table below is for wave sizing only.
+static int cluster_capacity_safe(int cl) { return cl >= 8 ? 120 : cl >= 4 ? 132 : g_num_sms; }
+
 static int cluster_capacity(int cl, int ctas_per_sm) {
   const int per_sm = cl >= 8 ? 120 : cl >= 4 ? 138 : g_num_sms;   // usable SMs (of 148) for this cluster size
   return per_sm * ctas_per_sm;
@@ -834,7 +880,8 @@ static int g_fuse_bn = 1;   // D3FK_FUSE_BN=0: always run BatchNorm as its own k
 
 template <int BN, int PATH>
 static int launch_conv_tc_bn(const Gather& g, const d3fk_conv_params* p, cudaStream_t s, const TileSched& box) {
-  EpiTC e{(bf16*)p->out, p->out_nchw, p->scale, p->shift, (const bf16*)p->res, p->stats, p->ldo, p->ldr, p->relu, p->Cout, p->Ho, p->Wo};
+  EpiTC e{(bf16*)p->out, p->out_nchw, p->scale, p->shift, (const bf16*)p->res, p->stats, p->ldo, p->ldr, p->relu, p->Cout, p->Ho, p->Wo,
+           (const bf16*)p->bw_x, (const bf16*)p->bw_act, p->bw_mean, p->bw_invstd, p->bw_ldx, p->bw_ldact, p->bw_relu};
   TileSched ts = box;
   ts.MT = cdiv(g.M, TC_BM);
   ts.NT = cdiv(p->Cout, BN);
@@ -883,7 +930,7 @@ static int launch_conv_tc_bn(const Gather& g, const d3fk_conv_params* p, cudaStr
   memset(&fb, 0, sizeof(fb));
   bool fuse = false;
   if (BN == 128 && t_fuse && g_fuse_bn && p->stats && !p->scale && !p->shift && !p->res && !p->relu && !p->out_nchw && p->mode == 0 &&
-      p->Cout % BN == 0 && ts.total <= cluster_capacity(ts.KS, 2)) {
+      p->Cout % BN == 0 && ts.total <= cluster_capacity_safe(ts.KS)) {
     const d3fk_bn_params* b = t_fuse->bn;
     fb.gamma = b->gamma; fb.beta = b->beta; fb.mean = b->mean; fb.invstd = b->invstd;
     fb.running_mean = b->running_mean; fb.running_var = b->running_var; fb.nbt = (long long*)b->num_batches_tracked;
@@ -895,7 +942,10 @@ static int launch_conv_tc_bn(const Gather& g, const d3fk_conv_params* p, cudaStr
   }
   if (g_verbose) fprintf(stderr, "[d3fk] conv<%d,%d> mode=%d M=%d K=%d Cout=%d tiles=%d KS=%d kbps=%d grid=%d fuse=%d\n", BN, PATH, g.mode, g.M, g.K, p->Cout, tiles, ts.KS, ts.kb_per_split, grid, (int)fuse);
   cudaError_t le;
-  if (BN == 128 && fuse)
+  if (p->bw_x)
+    le = launch_k(conv_tc_kernel<BN, PATH, 2>, dim3(grid), dim3(TC_THREADS), ConvCfg<BN>::SMEM, s, dim3(ts.KS, 1, 1), g,
+                  make_fastdiv((uint32_t)g.Wo), make_fastdiv((uint32_t)g.Ho), tmA, tmB, e, ts, fb, g_dev_error_flag);
+  else if (BN == 128 && fuse)
     le = launch_k(conv_tc_kernel<BN, PATH, (BN == 128 ? 1 : 0)>, dim3(grid), dim3(TC_THREADS), ConvCfg<BN>::SMEM, s, dim3(ts.KS, 1, 1), g,
                   make_fastdiv((uint32_t)g.Wo), make_fastdiv((uint32_t)g.Ho), tmA, tmB, e, ts, fb, g_dev_error_flag);
   else
@@ -1168,8 +1218,15 @@ __global__ void __launch_bounds__(SlabCfg<BN>::THREADS) conv_slab_kernel(const _
           epilogue_chunk<CW>(f, e, m, row_ok, cc, on, oh, ow, do_stats && !REG_STATS, s_stat + warp * 2 * BN + cc,
                              s_stat + warp * 2 * BN + BN + cc, lane);
           if (REG_STATS && do_stats) {
+            if (e.bw_x) {
+              float sq[CW];
+              bw_stat_terms<CW>(f, sq, e, m, row_ok, cc);
 #pragma unroll
-            for (int i = 0; i < CW; ++i) { rs[cc + i] += f[i]; rq[cc + i] = fmaf(f[i], f[i], rq[cc + i]); }
+              for (int i = 0; i < CW; ++i) { rs[cc + i] += f[i]; rq[cc + i] += sq[i]; }
+            } else {
+#pragma unroll
+              for (int i = 0; i < CW; ++i) { rs[cc + i] += f[i]; rq[cc + i] = fmaf(f[i], f[i], rq[cc + i]); }
+            }
           }
         }
       }
@@ -1197,7 +1254,7 @@ __global__ void __launch_bounds__(SlabCfg<BN>::THREADS) conv_slab_kernel(const _
         const float a = (s_stat[tid] + s_stat[2 * BN + tid]) + (s_stat[4 * BN + tid] + s_stat[6 * BN + tid]);
         const float b = (s_stat[BN + tid] + s_stat[3 * BN + tid]) + (s_stat[5 * BN + tid] + s_stat[7 * BN + tid]);
         atomicAdd(&e.stats[tid], (double)a);
-        atomicAdd(&e.stats[e.Cout + tid], (double)b);
+        atomicAdd(&e.stats[e.Cout + tid], e.bw_x ? bw_second_sum((double)a, (double)b, e, tid) : (double)b);
       }
     }
   }
@@ -1257,7 +1314,8 @@ static bool slab_plan(const Gather& g, const d3fk_conv_params* p, int BN, SlabSc
 
 template <int BN, int KSTEPS>
 static int launch_conv_slab_bn(const Gather& g, const d3fk_conv_params* p, cudaStream_t s, const SlabSched& ss, int smem) {
-  EpiTC e{(bf16*)p->out, p->out_nchw, p->scale, p->shift, (const bf16*)p->res, p->stats, p->ldo, p->ldr, p->relu, p->Cout, p->Ho, p->Wo};
+  EpiTC e{(bf16*)p->out, p->out_nchw, p->scale, p->shift, (const bf16*)p->res, p->stats, p->ldo, p->ldr, p->relu, p->Cout, p->Ho, p->Wo,
+           (const bf16*)p->bw_x, (const bf16*)p->bw_act, p->bw_mean, p->bw_invstd, p->bw_ldx, p->bw_ldact, p->bw_relu};
   alignas(64) CUtensorMap tmA, tmB;
   const int C = g.ctot;
   {
@@ -1895,6 +1953,18 @@ int tc_init() {
   SET_SMEM((conv_tc_kernel<32, 2, 0>), ConvCfg<32>::SMEM)
   SET_SMEM((conv_tc_kernel<64, 2, 0>), ConvCfg<64>::SMEM)
   SET_SMEM((conv_tc_kernel<128, 2, 0>), ConvCfg<128>::SMEM)
+  SET_SMEM((conv_tc_kernel<16, 0, 2>), ConvCfg<16>::SMEM)
+  SET_SMEM((conv_tc_kernel<16, 1, 2>), ConvCfg<16>::SMEM)
+  SET_SMEM((conv_tc_kernel<16, 2, 2>), ConvCfg<16>::SMEM)
+  SET_SMEM((conv_tc_kernel<32, 0, 2>), ConvCfg<32>::SMEM)
+  SET_SMEM((conv_tc_kernel<32, 1, 2>), ConvCfg<32>::SMEM)
+  SET_SMEM((conv_tc_kernel<32, 2, 2>), ConvCfg<32>::SMEM)
+  SET_SMEM((conv_tc_kernel<64, 0, 2>), ConvCfg<64>::SMEM)
+  SET_SMEM((conv_tc_kernel<64, 1, 2>), ConvCfg<64>::SMEM)
+  SET_SMEM((conv_tc_kernel<64, 2, 2>), ConvCfg<64>::SMEM)
+  SET_SMEM((conv_tc_kernel<128, 0, 2>), ConvCfg<128>::SMEM)
+  SET_SMEM((conv_tc_kernel<128, 1, 2>), ConvCfg<128>::SMEM)
+  SET_SMEM((conv_tc_kernel<128, 2, 2>), ConvCfg<128>::SMEM)
   SET_SMEM((conv_tc_kernel<128, 0, 1>), ConvCfg<128>::SMEM)
   SET_SMEM((conv_tc_kernel<128, 1, 1>), ConvCfg<128>::SMEM)
   SET_SMEM((conv_tc_kernel<128, 2, 1>), ConvCfg<128>::SMEM)

@@ -58,7 +58,13 @@ typedef struct d3fk_conv_params {
   const void* res;
   double* stats;
   int32_t ldo, ldr, relu, _pad1;
-  void* ws; int64_t ws_bytes;   /* optional fp32 scratch for split-K (layers whose tiles cannot fill the chip) */
+  void* ws; int64_t ws_bytes;   /* unused since split K reduces inside a thread-block cluster (kept for ABI stability) */
+  /* BN-backward reduction fused into a dgrad epilogue (bw_x != NULL; bf16 engine): the output is the gradient g wrt the
+   * activation of a conv -> BN -> ReLU layer whose raw conv output is bw_x (pixel stride bw_ldx), activation bw_act and saved
+   * statistics bw_mean / bw_invstd; `stats` then receives sum(g') and sum(g' * xhat), g' = g where bw_act > 0 (if bw_relu)
+   * else 0, xhat = (bw_x - mean) * invstd — the two sums of d3fk_bn_bwd_reduce, without its pass over g, x and act. */
+  const void* bw_x; const void* bw_act; const float* bw_mean; const float* bw_invstd;
+  int32_t bw_ldx, bw_ldact, bw_relu, _pad2;
 } d3fk_conv_params;
 
 /* ---- weight gradient (replaces cuDNN wgrad): dw[co][ci][kh][kw] += sum_{n,ho,wo} dy[n,ho,wo,co] * A[...]

@@ -6,7 +6,7 @@ import torch
 from denoising_diffusion_deep_fake_b200 import _lib
 import op_interpreter as I
 
-T_FIELDS = {"src0", "src1", "w", "out", "res", "dy", "x", "y", "act", "dx", "dres", "dst", "w_fwd", "w_dgrad"}
+T_FIELDS = {"src0", "src1", "w", "out", "res", "dy", "x", "y", "act", "dx", "dres", "dst", "w_fwd", "w_dgrad", "bw_x", "bw_act"}
 # fields that are dtype-typed only for some ops
 _NOT_T = {(_lib.OP_PACK, "w"), (_lib.OP_NCHW2NHWC, "src"), (_lib.OP_CHANSUM, "out")}
 

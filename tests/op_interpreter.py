@@ -64,7 +64,18 @@ def run_conv(p):
         v = v + nhwc(p.res, p.B, p.Ho, p.Wo, p.ldr, p.Cout).permute(0, 3, 1, 2)
     if p.relu:
         v = v.clamp_min(0)
-    if p.stats:
+    if p.stats and p.bw_x:
+        # fused BN-backward reduction: sums of g' and g' * xhat (see d3fk_conv_params.bw_*)
+        st = view(p.stats, (2, p.Cout), torch.float64)
+        x = nhwc(p.bw_x, p.B, p.Ho, p.Wo, p.bw_ldx, p.Cout).permute(0, 3, 1, 2)
+        g = v
+        if p.bw_relu:
+            act = nhwc(p.bw_act, p.B, p.Ho, p.Wo, p.bw_ldact, p.Cout).permute(0, 3, 1, 2)
+            g = torch.where(act > 0, v, torch.zeros_like(v))
+        xh = (x - view(p.bw_mean, (p.Cout,)).view(1, -1, 1, 1)) * view(p.bw_invstd, (p.Cout,)).view(1, -1, 1, 1)
+        st[0] += g.double().sum(dim=(0, 2, 3))
+        st[1] += (g.double() * xh.double()).sum(dim=(0, 2, 3))
+    elif p.stats:
         st = view(p.stats, (2, p.Cout), torch.float64)
         st[0] += v.double().sum(dim=(0, 2, 3))
         st[1] += (v.double() ** 2).sum(dim=(0, 2, 3))

@@ -15,7 +15,7 @@ DTYPES = [_lib.F32, _lib.BF16]
 
 
 def _conv_case(dtype, B, Hi, Wi, c0, c1, up0, Cout, k, stride, pad, mode, relu=0, res=False, affine=False,
-               stats=False, nchw=False, seed=0, splitk=False):
+               stats=False, nchw=False, seed=0, splitk=False, bw=None):
     g = torch.Generator().manual_seed(seed)
     ctot = c0 + c1
     if mode == 0:
@@ -49,6 +49,14 @@ def _conv_case(dtype, B, Hi, Wi, c0, c1, up0, Cout, k, stride, pad, mode, relu=0
     if splitk:
         t["ws"] = torch.zeros(4 << 20)
         sc["ws_bytes"] = 16 << 20
+    if bw is not None:     # fused BN-backward reduction (dgrad epilogue): bw = relu flag of the layer whose gradient this is
+        t["bw_x"] = torch.randn(B, Ho, Wo, Cout, generator=g) * 1.5 + 0.3
+        t["bw_act"] = torch.randn(B, Ho, Wo, Cout, generator=g).clamp_min(0)
+        t["bw_mean"] = torch.randn(Cout, generator=g) * 0.3
+        t["bw_invstd"] = torch.rand(Cout, generator=g) + 0.5
+        t["stats"] = torch.zeros(2, Cout, dtype=torch.float64)
+        sc.update(bw_ldx=Cout, bw_ldact=Cout, bw_relu=bw)
+        outs.append("stats")
     return run_both(_lib.OP_CONV, dtype, t, sc, outs)
 
 
@@ -336,3 +344,25 @@ def test_upcat(dtype, c0, c1):
         t["src1"] = torch.randn(B, H, W, c1, generator=g)
     r = run_both(_lib.OP_UPCAT, dtype, t, sc, ["out"])
     assert torch.equal(r["out"][0], r["out"][1])
+
+
+BW_CASES = [
+    # BN-backward reduction fused into the dgrad epilogue: generic tiles, split-K cluster, stride 2, slab (N = 64 / 32 / 16)
+    dict(B=16, Hi=8, Wi=8, c0=128, c1=0, up0=0, Cout=128, k=3, stride=1, pad=1, mode=1, res=True, bw=1),
+    dict(B=16, Hi=4, Wi=4, c0=256, c1=0, up0=0, Cout=256, k=3, stride=1, pad=1, mode=1, bw=1),
+    dict(B=16, Hi=4, Wi=4, c0=256, c1=0, up0=0, Cout=256, k=3, stride=1, pad=1, mode=1, res=True, bw=0),
+    dict(B=4, Hi=8, Wi=8, c0=128, c1=0, up0=0, Cout=64, k=3, stride=2, pad=1, mode=1, bw=1),
+    dict(B=6, Hi=16, Wi=16, c0=64, c1=0, up0=0, Cout=64, k=3, stride=1, pad=1, mode=1, res=True, bw=1),
+    dict(B=3, Hi=32, Wi=32, c0=32, c1=0, up0=0, Cout=32, k=3, stride=1, pad=1, mode=1, bw=1),
+    dict(B=2, Hi=64, Wi=64, c0=16, c1=0, up0=0, Cout=16, k=3, stride=1, pad=1, mode=1, bw=1),
+    dict(B=2, Hi=64, Wi=64, c0=16, c1=0, up0=0, Cout=32, k=3, stride=1, pad=1, mode=1, bw=0),
+]
+
+
+@pytest.mark.parametrize("case", BW_CASES)
+def test_dgrad_with_fused_bn_backward_reduction(case):
+    """d3fk_conv_params.bw_*: the dgrad epilogue also produces sum(g') and sum(g' * xhat) of the BatchNorm it feeds (bf16 engine)."""
+    r = _conv_case(_lib.BF16, **case)
+    assert rel_err(*r["out"]) < 1e-2
+    g, c = r["stats"]
+    assert rel_err(g, c) < 2e-2, rel_err(g, c)

@@ -29,9 +29,14 @@ for op in ops:
         continue
     c = _lib.Op(); ctypes.memmove(ctypes.byref(c), ctypes.byref(op), ctypes.sizeof(_lib.Op))
     ol = _lib.OpList([c] * 1)
-    for _ in range(5):
+    for _ in range(3):
         ol.run(s)
     torch.cuda.synchronize()
+    torch.cuda.profiler.start()       # ncu --profile-from-start off: capture from here
+    for _ in range(2):
+        ol.run(s)
+    torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
     print("ran", kind_name, M, N, K)
     break
 else:
