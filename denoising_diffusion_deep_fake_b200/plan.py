@@ -135,13 +135,14 @@ class UnetPlan:
         self._alloc_bn()
         # fp32 scratch for split-K convolutions (deep layers whose output tiles cannot fill 148 SMs)
         self.ws = self._new((SPLITK_WS_BYTES // 4,), torch.float32) if dtype == _lib.BF16 else None
+        self.grad_arena, self.grad_offsets = (grad_arena, grad_offsets) if training else (None, None)
         self.pack_ops = _lib.OpList(self._build_pack())
+        self.prepacked_version = None   # Unet._weights_version() the packed operands were last produced for (train.StepOverlap)
         self.saved = {}
         fwd = self._build_forward()
         self.fwd_ops = _lib.OpList(fwd)
         self.bwd_segments = None
         if training:
-            self.grad_arena, self.grad_offsets = grad_arena, grad_offsets
             self.bwd_segments = [_lib.OpList(seg) for seg in self._build_backward()]
         self._record_param_ptrs()
 
@@ -207,28 +208,53 @@ class UnetPlan:
 
     # ------------------------------------------------------------------ weight packing / BN folding
     def _build_pack(self):
-        ops = []
-        packs = []
-        blocks = 0
-        for c in self.convs:
-            cin_pad = CIN_PAD if c.cin == 3 else c.cin
-            cout_pad = DY_PAD if c.cout == 3 else c.cout
-            wd = self.w_dgrad.get(c.name)
-            assert c.k * c.k * min(c.cin, 32) <= 288, "pack_all tile: taps * min(Cin, 32) must be <= 288"
-            packs.append(make_op(_lib.OP_PACK, dtype=self.dtype, Cout=c.cout, Cin=c.cin, kh=c.k, kw=c.k,
-                                 cin_pad=cin_pad, cout_pad=cout_pad, blk0=blocks,
-                                 w=self.params[c.name + ".weight"].data_ptr(),
-                                 w_fwd=self.w_fwd[c.name].data_ptr(),
-                                 w_dgrad=wd.data_ptr() if wd is not None else None))
-            blocks += -(-c.cout // 32) * -(-c.cin // 32)
-        # one launch for all 47 layers: the descriptors live in a device table
+        """Pack ops, grouped by gradient bucket (= backward segment): `pack_bucket_ops[i]` re-packs exactly the layers whose
+        master weights bucket i of the flat arena holds, so a trainer can re-pack a bucket as soon as its Adam update has
+        run, while the rest of backward is still executing (train.StepOverlap)."""
+        import bisect
         import ctypes
+        ops = []
+        if self.grad_offsets is not None:
+            stage_first = ["segmentation_head.0.weight", "encoder.layer4.2.conv2.weight", "encoder.layer3.5.conv2.weight",
+                           "encoder.layer2.3.conv2.weight", "encoder.layer1.2.conv2.weight"]
+            starts = [self.grad_offsets[n] for n in stage_first]
+            bucket_of = lambda c: bisect.bisect_right(starts, self.grad_offsets[c.name + ".weight"]) - 1
+            n_buckets = len(starts)
+        else:
+            bucket_of = lambda c: 0
+            n_buckets = 1
+        groups = [[] for _ in range(n_buckets)]
+        for c in self.convs:
+            groups[bucket_of(c)].append(c)
+        packs, spans = [], []
+        for group in groups:
+            blocks, first = 0, len(packs)
+            for c in group:
+                cin_pad = CIN_PAD if c.cin == 3 else c.cin
+                cout_pad = DY_PAD if c.cout == 3 else c.cout
+                wd = self.w_dgrad.get(c.name)
+                assert c.k * c.k * min(c.cin, 32) <= 288, "pack_all tile: taps * min(Cin, 32) must be <= 288"
+                packs.append(make_op(_lib.OP_PACK, dtype=self.dtype, Cout=c.cout, Cin=c.cin, kh=c.k, kw=c.k,
+                                     cin_pad=cin_pad, cout_pad=cout_pad, blk0=blocks,
+                                     w=self.params[c.name + ".weight"].data_ptr(),
+                                     w_fwd=self.w_fwd[c.name].data_ptr(),
+                                     w_dgrad=wd.data_ptr() if wd is not None else None))
+                blocks += -(-c.cout // 32) * -(-c.cin // 32)
+            spans.append((first, len(packs) - first, blocks))
+        # one launch per bucket: the descriptors live in a device table (blk0 restarts at each bucket)
         table = (_lib.PackParams * len(packs))(*[op_params(o) for o in packs])
         raw = torch.frombuffer(bytearray(bytes(table)), dtype=torch.uint8).clone()
         self.pack_table = raw.to(self.device)
         self.keep.append(self.pack_table)
-        ops.append(make_op(_lib.OP_PACK_ALL, p0=self.pack_table.data_ptr(),
-                           n=(blocks << 17) | (len(packs) << 1) | (1 if self.dtype == _lib.BF16 else 0)))
+        self.pack_bucket_ops = []
+        for first, count, blocks in spans:
+            if count == 0:
+                self.pack_bucket_ops.append(None)
+                continue
+            op = make_op(_lib.OP_PACK_ALL, p0=self.pack_table.data_ptr() + first * ctypes.sizeof(_lib.PackParams),
+                         n=(blocks << 17) | (count << 1) | (1 if self.dtype == _lib.BF16 else 0))
+            ops.append(op)
+            self.pack_bucket_ops.append(_lib.OpList([op]))
         if not self.training:
             for c in self.convs:
                 if c.bn:
@@ -527,6 +553,10 @@ class UnetPlan:
     # ------------------------------------------------------------------ execution
     def run_pack(self, stream):
         self.pack_ops.run(stream)
+
+    def run_pack_bucket(self, i, stream):
+        if self.pack_bucket_ops[i] is not None:
+            self.pack_bucket_ops[i].run(stream)
 
     def run_forward(self, x, y, stream):
         op_params(self.fwd_ops.array[self.in_op_index]).src = x.data_ptr()

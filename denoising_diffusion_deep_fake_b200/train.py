@@ -8,6 +8,7 @@ statistics, mean-reduced gradients — one NCCL allreduce per backward segment, 
 stream as soon as that segment's gradients are final so it overlaps the rest of backward."""
 import copy
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -55,6 +56,21 @@ class FlatAdam:
             break
         self.model.__dict__["_stat_updates"] = self.model.__dict__.get("_stat_updates", 0) + 1
 
+    # ---- bucket-wise form of step() (StepOverlap): begin_step, step_range per bucket, end_step
+    def begin_step(self):
+        self.check_aliasing()
+        self.step_count += 1
+
+    def step_range(self, start, end):
+        adam_step_(self.flat_p[start:end], self.model._grad_arena[start:end], self.m[start:end], self.v[start:end],
+                   self.lr, self.betas[0], self.betas[1], self.eps, self.step_count)
+
+    def end_step(self, plan=None):
+        m = self.model
+        m.__dict__["_stat_updates"] = m.__dict__.get("_stat_updates", 0) + 1
+        if plan is not None:        # the plan's packed operands already hold the updated weights
+            plan.prepacked_version = m._weights_version()
+
     def state_dict(self):
         return {"m": self.m, "v": self.v, "step": self.step_count, "lr": self.lr}
 
@@ -68,30 +84,66 @@ def cosine_lr(base_lr, epoch, t_max):
     return base_lr * (1 + math.cos(math.pi * epoch / t_max)) / 2
 
 
-class GradAllReduce:
-    """Bucketed gradient mean over the data-parallel group, overlapped with backward."""
+class StepOverlap:
+    """Everything that FOLLOWS a backward segment, taken off the critical path.  When backward segment i has been
+    enqueued, the update stream (ordered behind the main stream and behind libd3fk's weight-gradient streams) runs, for
+    gradient bucket i only:  [NCCL mean-allreduce]  ->  [fused Adam]  ->  [re-pack of the bucket's bf16 operands]
+    while the main stream goes on with segment i+1 — the deep segments are latency-bound, so these bandwidth-bound
+    passes ride along for free.  `finish()` orders the main stream behind the update stream.
 
-    def __init__(self, model, group=None):
-        import torch.distributed as dist
-        self.dist, self.group, self.model = dist, group, model
+    allreduce: a process group is given (data parallel).  adam: a FlatAdam is given (otherwise the caller steps its own
+    optimiser after finish())."""
+
+    def __init__(self, model, optimizer=None, group=None, distributed=False):
+        self.model, self.optimizer, self.group, self.distributed = model, optimizer, group, distributed
+        if distributed:
+            import torch.distributed as dist
+            self.world = dist.get_world_size(group)
         dev = next(model.parameters()).device
         self.comm = torch.cuda.Stream(dev)
         self.buckets = model.grad_buckets()
+        self.armed = False          # the optimiser part runs only inside a training step that asked for it
+        self.stepped = False
+        self._plan = None
         model.__dict__["_dp_hook"] = self.after_segment
-        self.world = dist.get_world_size(group)
 
-    def after_segment(self, i):
+    def after_segment(self, i, plan=None):
+        do_adam = self.armed and self.optimizer is not None
+        if not (self.distributed or do_adam):
+            return
         cur = torch.cuda.current_stream()
         ev = torch.cuda.Event()
         ev.record(cur)
-        self.comm.wait_event(ev)                           # BN / bias gradients: main stream
-        _lib.side_stream_join(self.comm.cuda_stream)       # weight gradients: libd3fk's side stream
+        self.comm.wait_event(ev)                           # BN / bias gradients, dgrad reads of the packed weights: main stream
+        _lib.side_stream_join(self.comm.cuda_stream)       # weight gradients: libd3fk's side streams
         s, e = self.buckets[i]
         with torch.cuda.stream(self.comm):
-            allreduce_bucket_(self.model._grad_arena, s, e, self.group)
+            if self.distributed:
+                allreduce_bucket_(self.model._grad_arena, s, e, self.group)
+            if do_adam:
+                if i == 0:
+                    self.optimizer.begin_step()
+                self.optimizer.step_range(s, e)
+                if plan is not None:
+                    plan.run_pack_bucket(i, self.comm.cuda_stream)
+                    self._plan = plan
+                if i == len(self.buckets) - 1:
+                    self.stepped = True
 
     def wait(self):
         torch.cuda.current_stream().wait_stream(self.comm)
+
+    def finish(self):
+        """Main stream waits for the update stream; returns True when the optimiser step (and the re-pack) already ran."""
+        self.wait()
+        stepped, self.stepped = self.stepped, False
+        if stepped:
+            self.optimizer.end_step(self._plan)
+        self._plan = None
+        return stepped
+
+
+GradAllReduce = StepOverlap    # the allreduce-only use (optimizer=None) keeps its old name
 
 
 class DenoiserModule(nn.Module):
@@ -113,16 +165,21 @@ class DenoiserModule(nn.Module):
     def forward(self, image):
         return self.model(image)
 
-    def configure_optimizers(self, fused=True):
+    def configure_optimizers(self, fused=True, overlap=True):
+        """fused: one-kernel Adam over the flat arenas; overlap (fused only): the Adam update and the bf16 re-pack of each
+        gradient bucket run on a second stream underneath the rest of backward (StepOverlap)."""
         p = self.hparams
         if fused:
             self.optimizer = FlatAdam(self.model, lr=p["learning_rate"])
+            if overlap and os.environ.get("D3FK_OVERLAP_STEP", "1") != "0":
+                self.allreduce = StepOverlap(self.model, self.optimizer)
         else:
             self.optimizer = torch.optim.Adam(self.model.parameters(), lr=p["learning_rate"])
         return self.optimizer
 
     def enable_data_parallel(self, group=None):
-        self.allreduce = GradAllReduce(self.model, group)
+        overlap_adam = self.allreduce is not None and self.allreduce.optimizer is not None
+        self.allreduce = StepOverlap(self.model, self.optimizer if overlap_adam else None, group, distributed=True)
 
     def blend_random_amount_of_noise_with_each_sample(self, batch, noise=None, y=None):
         p = self.hparams
@@ -137,10 +194,18 @@ class DenoiserModule(nn.Module):
         loss = self.training_criterion(image_prediction, image)
         if not isinstance(self.optimizer, FlatAdam):
             self.optimizer.zero_grad(set_to_none=True)
-        loss.backward()
+        stepped = False
         if self.allreduce is not None:
-            self.allreduce.wait()
-        self.optimizer.step()
+            self.allreduce.armed = True
+            try:
+                loss.backward()
+            finally:
+                self.allreduce.armed = False
+            stepped = self.allreduce.finish()
+        else:
+            loss.backward()
+        if not stepped:
+            self.optimizer.step()
         self.global_step += 1
         return loss
 

@@ -140,6 +140,7 @@ class Unet(nn.Module):
         self.__dict__["_param_names"] = None
         self.__dict__["_packed_version"] = {}
         self.__dict__["_dp_hook"] = None
+        self.__dict__["_version_tensors"] = None
 
     def __deepcopy__(self, memo):
         new = Unet(precision=self.precision)
@@ -155,7 +156,7 @@ class Unet(nn.Module):
     def __getstate__(self):
         state = self.__dict__.copy()
         for k in ("_plans", "_grad_arena", "_grad_offsets", "_param_dict", "_param_names", "_packed_version",
-                  "_dp_hook"):
+                  "_dp_hook", "_version_tensors"):
             state.pop(k, None)
         return state
 
@@ -255,14 +256,20 @@ class Unet(nn.Module):
         return plan
 
     def _weights_version(self):
-        return (sum(p._version for p in self.parameters()) + sum(b._version for b in self.buffers())
-                + self.__dict__.get("_stat_updates", 0))
+        ts = self.__dict__.get("_version_tensors")
+        if ts is None:      # cached flat list (reset with the other runtime state): this runs twice per training step
+            ts = self.__dict__["_version_tensors"] = list(self.parameters()) + list(self.buffers())
+        return sum(t._version for t in ts) + self.__dict__.get("_stat_updates", 0)
 
     def _run_forward(self, plan, x):
         x = x.contiguous()
         stream = torch.cuda.current_stream(x.device).cuda_stream
         if plan.training:
-            plan.run_pack(stream)          # master weights change every optimiser step
+            # master weights change every optimiser step; a trainer that re-packed bucket by bucket right after its Adam
+            # update (train.StepOverlap) recorded the version it packed
+            if plan.prepacked_version is None or plan.prepacked_version != self._weights_version():
+                plan.run_pack(stream)
+            plan.prepacked_version = None
             # the kernels update the BN running statistics in place, invisible to tensor._version
             self.__dict__["_stat_updates"] = self.__dict__.get("_stat_updates", 0) + 1
         else:
@@ -278,7 +285,8 @@ class Unet(nn.Module):
     def _run_backward(self, plan, dy):
         dy = dy.contiguous()
         stream = torch.cuda.current_stream(dy.device).cuda_stream
-        plan.run_backward(dy, stream, after_segment=self._dp_hook)
+        hook = self._dp_hook
+        plan.run_backward(dy, stream, after_segment=(lambda i: hook(i, plan)) if hook is not None else None)
 
     # -------------------------------------------------------------- nn.Module API
     def forward(self, x):

@@ -226,3 +226,51 @@ def test_sampler_trajectory_psnr():
     real = x_start.clamp(-1, 1)
     with torch.no_grad():
         assert rel_err(swap_face(m, real.to(DEV)).cpu(), ref(real)) < 1e-5
+
+
+def test_overlapped_optimizer_step():
+    """train.StepOverlap (per-bucket Adam + re-pack on a second stream underneath backward) against the plain order
+    backward -> one Adam over the whole arena -> full re-pack in the next forward.  Deterministic parts are held bit
+    exact: the bucket-wise Adam equals the one-launch Adam on the same gradients, and the packed operands left behind
+    equal a fresh full pack of the updated masters.  An external weight change must still trigger a re-pack."""
+    from denoising_diffusion_deep_fake_b200.train import DenoiserModule
+    from denoising_diffusion_deep_fake_b200.functional import adam_step_
+    hp = dict(encoder_name="resnet34", learning_rate=0.02, noise_exponential_sampling_lambda=5,
+              cosine_scheduler_max_epoch=100, precision="bf16", seed=3)
+    torch.manual_seed(0)
+    a = DenoiserModule(**hp).to(DEV).train()
+    b = DenoiserModule(**hp).to(DEV).train()
+    b.load_state_dict(a.state_dict())
+    a.configure_optimizers(fused=True, overlap=True)
+    b.configure_optimizers(fused=True, overlap=False)
+    assert a.allreduce is not None and b.allreduce is None
+    g = torch.Generator(device=DEV).manual_seed(1)
+    x = torch.randn(16, 3, 64, 64, generator=g, device=DEV).clamp(-1, 1)
+    opt = a.optimizer
+    for step in range(3):
+        p0, m0, v0 = opt.flat_p.clone(), opt.m.clone(), opt.v.clone()
+        la, lb = a.training_step(x), b.training_step(x)
+        torch.cuda.synchronize()
+        assert abs(float(la) - float(lb)) <= 2e-2 * abs(float(lb)), (step, float(la), float(lb))
+        # (1) bucket-wise Adam == one-launch Adam on the gradients this step produced (still in the arena)
+        adam_step_(p0, a.model._grad_arena, m0, v0, opt.lr, opt.betas[0], opt.betas[1], opt.eps, step + 1)
+        assert opt.step_count == step + 1 == b.optimizer.step_count
+        assert torch.equal(p0, opt.flat_p) and torch.equal(m0, opt.m) and torch.equal(v0, opt.v)
+        # (2) the operands packed underneath backward == a full pack of the updated master weights
+        plan = next(p for plans in a.model._plans.values() for p in plans if p.training)
+        assert plan.prepacked_version == a.model._weights_version()
+        before = {n: t.clone() for n, t in list(plan.w_fwd.items()) + [("d:" + n, t) for n, t in plan.w_dgrad.items()]}
+        plan.run_pack(torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        for n, t in list(plan.w_fwd.items()) + [("d:" + n, t) for n, t in plan.w_dgrad.items()]:
+            assert torch.equal(before[n], t), n
+    # an external weight change must not be missed by the skipped pack
+    with torch.no_grad():
+        for p in a.model.parameters():
+            p.mul_(0.5)
+    assert plan.prepacked_version != a.model._weights_version()
+    a.training_step(x)
+    torch.cuda.synchronize()
+    first = next(iter(plan.w_fwd))
+    w = dict(a.model.named_parameters())[first + ".weight"]
+    assert plan.prepacked_version == a.model._weights_version() and torch.isfinite(w).all()

@@ -66,7 +66,9 @@ def test_train_plan_matches_oracle(B, H, W):
     x = torch.randn(B, 3, H, W)
     dy = torch.randn(B, 3, H, W)
     plan = cpu_plan(m, B, H, W, True)
-    assert len(plan.pack_ops) == 1 and len(plan.bwd_segments) == 5
+    # weight packing: one launch per gradient bucket (= backward segment), 47 layers in total
+    assert len(plan.pack_ops) == 5 and len(plan.pack_bucket_ops) == 5 and len(plan.bwd_segments) == 5
+    assert sum((_lib.op_params(o).n >> 1) & 0xFFFF for o in plan.pack_ops) == 47
     y = run_forward(plan, x)
     ref.train()
     y_ref = ref(x)
@@ -124,3 +126,33 @@ def test_module_contract_on_cpu():
     w = fresh.encoder.layer1[0].conv1.weight
     assert abs(w.std().item() - (2.0 / (64 * 9)) ** 0.5) < 5e-3       # kaiming_normal_(fan_out)
     assert float(fresh.segmentation_head[0].bias.abs().max()) == 0.0
+
+
+def test_pack_buckets_follow_backward_segments():
+    """train.StepOverlap re-packs bucket i (and updates its master weights) while backward segments > i still run:
+    no op of a later segment may read a packed operand of bucket i, nor write a gradient outside buckets >= its own."""
+    _, m = make_pair()
+    plan = cpu_plan(m, 2, 64, 64, True)
+    buckets = m.grad_buckets()
+    packed_of_bucket = []
+    for ol in plan.pack_bucket_ops:
+        p = _lib.op_params(ol.array[0])
+        n = (p.n >> 1) & 0xFFFF
+        table = (_lib.PackParams * n).from_address(p.p0)
+        packed_of_bucket.append({t.w_fwd for t in table} | {t.w_dgrad for t in table if t.w_dgrad})
+    assert sum(len(s) for s in packed_of_bucket) >= 47
+    base = m._grad_arena.data_ptr()
+    for j, seg in enumerate(plan.bwd_segments):
+        for op in seg:
+            p = _lib.op_params(op)
+            if op.kind == _lib.OP_CONV:
+                for i in range(j):
+                    assert p.w not in packed_of_bucket[i], f"segment {j} reads a packed weight of bucket {i}"
+            written = []
+            if op.kind == _lib.OP_WGRAD:
+                written.append(p.dw)
+            if op.kind in (_lib.OP_BN_BWD, _lib.OP_BN_BWD_APPLY, _lib.OP_BN_BWD_FINALIZE):
+                written += [q for q in (p.dgamma, p.dbeta) if q]
+            for q in written:
+                off = (q - base) // 4
+                assert buckets[j][0] <= off < buckets[j][1], f"segment {j} writes a gradient of another bucket ({off})"

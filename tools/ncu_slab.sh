@@ -1,12 +1,17 @@
 #!/bin/bash
-# ncu --set full captures of the narrow decoder-tail kernels (one launch each); outputs under gpurun_out/
-set -x
+# ncu --set full captures of single ops (one launch each).  The .ncu-rep files (17 MB each with the source import) are
+# exported to text on the box and removed: gpurun brings back at most 64 MiB.
 cap() {  # name kind M N K mode
+  local rep=gpurun_out/$1.ncu-rep
   timeout 300 ncu --set full --clock-control none --import-source on --profile-from-start off -c 1 -f -o gpurun_out/$1 \
     python tools/one_op.py $2 $3 $4 $5 $6 > gpurun_out/$1.log 2>&1
-  tail -2 gpurun_out/$1.log
+  tail -1 gpurun_out/$1.log
+  [ -f $rep ] || return
+  ncu -i $rep --page details > gpurun_out/$1_details.txt 2>&1
+  ncu -i $rep --page raw --csv > gpurun_out/$1_raw.csv 2>&1
+  ncu -i $rep --page source --csv 2>/dev/null | gzip -9 > gpurun_out/$1_source.csv.gz
+  rm -f $rep
 }
-cap r01d_slab16_k288 conv 1048576 16 288 0
-cap r01d_head_n3 conv 1048576 3 144 0
-cap r01d_slab32_k1152 conv 262144 32 1152 0
-cap r01d_stem conv 262144 64 392 0
+for spec in "$@"; do
+  cap $spec
+done
