@@ -120,7 +120,7 @@ def conv_only_oplist(plan):
     contribute their convolution only: d3fk_convbn_params starts with the d3fk_conv_params)."""
     from denoising_diffusion_deep_fake_b200 import _lib
     import ctypes
-    kinds = (_lib.OP_CONV, _lib.OP_WGRAD, _lib.OP_CONV_BN)
+    kinds = (_lib.OP_CONV, _lib.OP_WGRAD, _lib.OP_CONV_BN, _lib.OP_WGRAD_GROUP)
     ops = [op for op in plan.fwd_ops if op.kind in kinds]
     for seg in plan.bwd_segments or []:
         ops += [op for op in seg if op.kind in kinds]
@@ -149,6 +149,10 @@ def run_d3fk(args):
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    if args.main_priority:
+        # the training step's main chain on a high-priority stream: its small latency-bound kernels get the next free CTA
+        # slot ahead of the weight-gradient / optimiser kernels running on libd3fk's (lowest-priority) side streams
+        torch.cuda.set_stream(torch.cuda.Stream(dev, priority=-args.main_priority))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -339,6 +343,7 @@ def main():
     ap.add_argument("--sample-steps", type=int, default=50)
     ap.add_argument("--no-sample", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--main-priority", type=int, default=int(os.environ.get("D3FK_MAIN_PRIORITY", "0")))
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

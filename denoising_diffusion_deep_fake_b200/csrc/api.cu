@@ -34,6 +34,7 @@ int launch_conv_ffma(const d3fk_conv_params*, cudaStream_t);
 int launch_wgrad_ffma(const d3fk_wgrad_params*, cudaStream_t);
 int launch_conv_tc(const d3fk_conv_params*, cudaStream_t);
 int launch_wgrad_tc(const d3fk_wgrad_params*, cudaStream_t);
+int launch_wgrad_group_tc(const d3fk_wgrad_group_params*, cudaStream_t);
 int launch_conv_bn_tc(const d3fk_convbn_params*, cudaStream_t);
 int launch_pack(const d3fk_pack_params*, cudaStream_t);
 int launch_nchw_to_nhwc(const d3fk_layout_params*, cudaStream_t);
@@ -76,6 +77,18 @@ static int wgrad_dispatch(const d3fk_wgrad_params* p, cudaStream_t s) {
   return set_error(D3FK_ERR_ARG, "wgrad: bad dtype %d", p->dtype);
 }
 
+static int wgrad_group_dispatch(const d3fk_wgrad_group_params* p, cudaStream_t s) {
+  if (p->base.dtype == D3FK_BF16) return launch_wgrad_group_tc(p, s);
+  if (p->count < 1 || p->count > D3FK_WGRAD_GROUP_MAX) return set_error(D3FK_ERR_ARG, "wgrad group: count %d", p->count);
+  for (int i = 0; i < p->count; ++i) {        // fp32 parity mode: one launch per problem
+    d3fk_wgrad_params one = p->base;
+    one.src0 = p->src0[i]; one.dy = p->dy[i]; one.dw = p->dw[i];
+    int rc = wgrad_dispatch(&one, s);
+    if (rc) return rc;
+  }
+  return D3FK_OK;
+}
+
 static int convbn_dispatch(const d3fk_convbn_params* p, cudaStream_t s) {
   if (p->conv.dtype == D3FK_BF16) return launch_conv_bn_tc(p, s);
   int rc = conv_dispatch(&p->conv, s);      // fp32 parity mode: the two kernels
@@ -87,6 +100,7 @@ static int run_one(const d3fk_op* op, cudaStream_t s) {
     case D3FK_OP_CONV_BN: return convbn_dispatch(&op->u.convbn, s);
     case D3FK_OP_CONV: return conv_dispatch(&op->u.conv, s);
     case D3FK_OP_WGRAD: return wgrad_dispatch(&op->u.wgrad, s);
+    case D3FK_OP_WGRAD_GROUP: return wgrad_group_dispatch(&op->u.wgrad_group, s);
     case D3FK_OP_PACK: return launch_pack(&op->u.pack, s);
     case D3FK_OP_NCHW2NHWC: return launch_nchw_to_nhwc(&op->u.layout, s);
     case D3FK_OP_BN_FINALIZE: return launch_bn_finalize(&op->u.bn, s);
@@ -214,8 +228,9 @@ static int run_list(const d3fk_op* ops, int n_ops, cudaStream_t s, bool join) {
   if (rc) return rc;
   int forks = 0;
   for (int i = 0; i < n_ops; ++i) {
-    if (ops[i].kind == D3FK_OP_WGRAD && g_skip_wgrad) continue;   // timing experiment only (D3FK_SKIP_WGRAD=1)
-    if (ops[i].kind == D3FK_OP_WGRAD && g_fork_wgrad && n_ops > 1) {
+    const bool is_wgrad = ops[i].kind == D3FK_OP_WGRAD || ops[i].kind == D3FK_OP_WGRAD_GROUP;
+    if (is_wgrad && g_skip_wgrad) continue;   // timing experiment only (D3FK_SKIP_WGRAD=1)
+    if (is_wgrad && g_fork_wgrad && n_ops > 1) {
       cudaEvent_t ev = g_fork_events[g_fork_cursor++ % g_n_fork_events];
       cudaStream_t side = g_side_streams[g_side_cursor++ % g_n_side];   // round robin: no false wgrad -> wgrad ordering
       cudaError_t e = cudaEventRecord(ev, s);
@@ -284,6 +299,7 @@ int d3fk_run_profile(const d3fk_op* ops, int n_ops, d3fk_stream stream, float* m
   }
 SINGLE(d3fk_conv, d3fk_conv_params, conv_dispatch)
 SINGLE(d3fk_wgrad, d3fk_wgrad_params, wgrad_dispatch)
+SINGLE(d3fk_wgrad_group, d3fk_wgrad_group_params, wgrad_group_dispatch)
 SINGLE(d3fk_conv_bn, d3fk_convbn_params, convbn_dispatch)
 SINGLE(d3fk_pack_weights, d3fk_pack_params, launch_pack)
 SINGLE(d3fk_nchw_to_nhwc, d3fk_layout_params, launch_nchw_to_nhwc)

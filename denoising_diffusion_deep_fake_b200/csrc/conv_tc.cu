@@ -269,6 +269,8 @@ __device__ __forceinline__ double bw_second_sum(double a, double b, const EpiTC&
   return (double)__ldg(e.bw_invstd + ch) * (b - (double)__ldg(e.bw_mean + ch) * a);
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 struct FastDiv {
   uint32_t mul, shr;
 };
@@ -464,6 +466,20 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(Gather g, FastDi
     decode_tile(ts, blockIdx.x, mt0, nt0, ks0);
     const int kbp = ks0 * ts.kb_per_split;
     for (int i = 0; i < STAGES && kbp + i < ts.nkb; ++i) tma_prefetch_l2_2d(&tmB, (kbp + i) * TC_BK, nt0 * BN);
+  }
+  if (FUSE == 2 && is_epi && e.bw_x) {
+    // Fused BN-backward reduction: the epilogue reads one row segment of the forward's raw output / activation per lane.
+    // They were written a whole forward ago (HBM, not L2) and not by the preceding kernel: pull the first tile's segments
+    // into L2 now, so the loads on the epilogue's dependent chain are L2 hits.
+    int mt0, nt0, ks0;
+    decode_tile(ts, blockIdx.x, mt0, nt0, ks0);
+    const long long mp = (long long)mt0 * TC_BM + q * 32 + lane;
+    if (mp < g.M) {
+      for (int b = half * 128; b < BN * 2; b += 256) {
+        prefetch_l2(reinterpret_cast<const char*>(e.bw_x + mp * e.bw_ldx + nt0 * BN) + b);
+        if (e.bw_relu) prefetch_l2(reinterpret_cast<const char*>(e.bw_act + mp * e.bw_ldact + nt0 * BN) + b);
+      }
+    }
   }
   if (warp == 4) tmem_alloc(smem_u32((const void*)tmem_ptr_slot), Cfg::TMEM_COLS);
   tc_fence_before();
@@ -1401,6 +1417,7 @@ int launch_conv_bn_tc(const d3fk_convbn_params* p, cudaStream_t s) {
 // partial tiles are reduce-scattered through distributed shared memory, so a tile costs (splits / CL) atomic passes
 // (none when splits == CL) instead of `splits`.
 constexpr int WG_PIX = 64;
+constexpr int WG_ONE_PER_SM_SMEM = 120 * 1024;   // more than half of the 227 KB an SM offers: one CTA per SM
 constexpr int WG_A_STAGE = 2 * WG_PIX * 128;
 template <int BN> struct WgradCfg {
   static constexpr int STAGES = BN >= 128 ? 3 : 4;
@@ -1410,11 +1427,20 @@ template <int BN> struct WgradCfg {
   static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
 };
 
+// A group of identically shaped problems shares one launch: blockIdx.z = problem * splits + pixel split (splits is a
+// multiple of the cluster size, so a cluster never straddles two problems).
+struct WgGroup {
+  int count, splits;
+  const void* src0[D3FK_WGRAD_GROUP_MAX];
+  const bf16* dy[D3FK_WGRAD_GROUP_MAX];
+  float* dw[D3FK_WGRAD_GROUP_MAX];
+};
+
 template <int BN>
-__global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(Gather g, FastDiv dWo, FastDiv dHo, const bf16* __restrict__ dy,
-                                                              int ldy, int Cout, float* __restrict__ dw, int cin_real,
+__global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(Gather g, FastDiv dWo, FastDiv dHo, const bf16* __restrict__ dy_one,
+                                                              int ldy, int Cout, float* __restrict__ dw_one, int cin_real,
                                                               int cout_real, int blocks_per_split, int lbo_a, int lbo_b,
-                                                              int CL, int* errflag) {
+                                                              int CL, int* errflag, const __grid_constant__ WgGroup grp) {
   using Cfg = WgradCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int CW = 32;
@@ -1432,10 +1458,15 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(Gather g, FastDiv 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int k0 = blockIdx.x * 128, co0 = blockIdx.y * BN;
   const int nblk_total = (g.M + WG_PIX - 1) / WG_PIX;
-  const int blk_beg = blockIdx.z * blocks_per_split;
+  const int prob = grp.count > 0 ? (int)blockIdx.z / grp.splits : 0;
+  const int zsplit = (int)blockIdx.z - prob * grp.splits;
+  const bf16* __restrict__ dy = grp.count > 0 ? grp.dy[prob] : dy_one;
+  float* __restrict__ dw = grp.count > 0 ? grp.dw[prob] : dw_one;
+  const void* src0 = grp.count > 0 ? grp.src0[prob] : g.src0;
+  const int blk_beg = zsplit * blocks_per_split;
   const int blk_end = min(nblk_total, blk_beg + blocks_per_split);
   const int nblk = max(0, blk_end - blk_beg);
-  const bool use_atomic = (int)gridDim.z > CL;
+  const bool use_atomic = grp.splits > CL;
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -1487,7 +1518,7 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(Gather g, FastDiv 
       kkh[cb] = tap / g.kw;
       kkw[cb] = tap - kkh[cb] * g.kw;
       const bool second = kc >= g.c0;
-      sb[cb] = second ? (const bf16*)g.src1 + (kc - g.c0) : (const bf16*)g.src0 + kc;
+      sb[cb] = second ? (const bf16*)g.src1 + (kc - g.c0) : (const bf16*)src0 + kc;
       sld[cb] = second ? g.ld1 : g.ld0;
       sup[cb] = second ? 0 : g.up0;
       shs[cb] = g.Hi >> sup[cb];
@@ -1516,7 +1547,7 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(Gather g, FastDiv 
           const int hi = h0 + kkh[cb], wi = w0 + kkw[cb];
           const bool ok = kok[cb] && (unsigned)hi < (unsigned)g.Hi && (unsigned)wi < (unsigned)g.Wi;
           const long long pix = (long long)((n * shs[cb] + (hi >> sup[cb])) * sws[cb] + (wi >> sup[cb]));
-          const void* src = ok ? (const void*)(sb[cb] + pix * sld[cb]) : g.src0;
+          const void* src = ok ? (const void*)(sb[cb] + pix * sld[cb]) : src0;
           cp_async_16(a_base + s * WG_A_STAGE + cb * (WG_PIX * 128) + prow * 128 + sw, src, ok ? 16u : 0u);
         }
 #pragma unroll
@@ -1621,24 +1652,32 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(Gather g, FastDiv 
 static int g_wg_ctas_per_sm = 2;
 static int g_wg_cap = 0;     // D3FK_WG_CAP=n: override the co-resident CTA capacity used to size the pixel splits
 static int g_wg_plain = 1;   // D3FK_WG_PLAIN=0: launch cluster-size-1 grids through cudaLaunchKernelEx too
+// Grouped launches run for 50-90 us on a side stream while the latency-bound main chain needs a free CTA slot every few
+// microseconds: D3FK_WG_GROUP_OCC=1 pads their shared-memory request so that only ONE of them fits an SM and the other slot
+// stays available to the main chain.
+static int g_wg_group_occ = 2;
 
 template <int BN>
-static int launch_wgrad_tc_bn(const Gather& g, const d3fk_wgrad_params* p, cudaStream_t s) {
+static int launch_wgrad_tc_bn(const Gather& g, const d3fk_wgrad_params* p, cudaStream_t s, const d3fk_wgrad_group_params* group = nullptr) {
   const int gx = cdiv(g.K, 128), gy = cdiv(p->Cout, BN);
   const int nblk = cdiv(g.M, WG_PIX);
-  const int tiles = gx * gy;
+  const int G = group ? group->count : 1;
+  const int tiles = gx * gy * G;
   // Pixel splits and cluster size: one wave of co-resident CTAs.  Cost model (us): pipeline stages per CTA, plus the atomic
   // passes over the K x Cout outputs when a tile's splits span several clusters, plus the cluster reduction itself.
-  const double elems = (double)g.K * p->cout_real;
+  const double elems = (double)g.K * p->cout_real * G;
   const int max_cl = g_max_cluster < 8 ? (g_max_cluster < 1 ? 1 : g_max_cluster) : 8;
   int cl = 1, splits = 1;
   double best = 1e30;
   for (int c = 1; c <= max_cl; c *= 2) {
-    int cap = g_wg_cap > 0 ? g_wg_cap : cluster_capacity(c, g_wg_ctas_per_sm);
+    int cap = g_wg_cap > 0 ? g_wg_cap : cluster_capacity(c, (group && g_wg_group_occ == 1) ? 1 : g_wg_ctas_per_sm);
     int smax = cap / tiles;
     if (smax > nblk) smax = nblk;
     smax = (smax / c) * c;
-    if (smax < c) continue;
+    if (smax < c) {
+      if (c == 1) { best = (double)nblk * 0.4 * cdiv(tiles, cap); cl = 1; splits = 1; }   // more tiles than one wave: no split
+      continue;
+    }
     const int cand[2] = {smax, c};
     for (int i = 0; i < 2; ++i) {
       const int sp = cand[i];
@@ -1646,18 +1685,25 @@ static int launch_wgrad_tc_bn(const Gather& g, const d3fk_wgrad_params* p, cudaS
       if (est < best) { best = est; cl = c; splits = sp; }
     }
   }
-  const int want = splits, cap = 0;
   const int bps = cdiv(nblk, splits);
-  dim3 grid(gx, gy, splits);
-  if (g_verbose) fprintf(stderr, "[d3fk] wgrad<%d> M=%d K=%d Cout=%d tiles=%d want=%d cl=%d cap=%d splits=%d bps=%d\n", BN, g.M, g.K, p->Cout, tiles, want, cl, cap, splits, bps);
+  WgGroup grp;
+  memset(&grp, 0, sizeof(grp));
+  grp.splits = splits;
+  if (group) {
+    grp.count = G;
+    for (int i = 0; i < G; ++i) { grp.src0[i] = group->src0[i]; grp.dy[i] = (const bf16*)group->dy[i]; grp.dw[i] = group->dw[i]; }
+  }
+  dim3 grid(gx, gy, splits * G);
+  const size_t smem = (group && g_wg_group_occ == 1) ? (size_t)WG_ONE_PER_SM_SMEM : (size_t)WgradCfg<BN>::SMEM;
+  if (g_verbose) fprintf(stderr, "[d3fk] wgrad<%d> M=%d K=%d Cout=%d group=%d tiles=%d cl=%d splits=%d bps=%d\n", BN, g.M, g.K, p->Cout, G, tiles, cl, splits, bps);
   if (cl == 1 && g_wg_plain) {
-    launch_k(wgrad_tc_kernel<BN>, dim3(grid), dim3(WG_THREADS), WgradCfg<BN>::SMEM, s, dim3(1, 1, 1), g, make_fastdiv((uint32_t)g.Wo), make_fastdiv((uint32_t)g.Ho),
+    launch_k(wgrad_tc_kernel<BN>, dim3(grid), dim3(WG_THREADS), smem, s, dim3(1, 1, 1), g, make_fastdiv((uint32_t)g.Wo), make_fastdiv((uint32_t)g.Ho),
                                                                   (const bf16*)p->dy, p->ldy, p->Cout, p->dw, p->cin_real, p->cout_real,
-                                                                  bps, WG_PIX * 128, WG_PIX * 128, cl, g_dev_error_flag);
+                                                                  bps, WG_PIX * 128, WG_PIX * 128, cl, g_dev_error_flag, grp);
   } else {
-    cudaError_t le = launch_k(wgrad_tc_kernel<BN>, grid, dim3(WG_THREADS), WgradCfg<BN>::SMEM, s, dim3(1, 1, cl), g,
+    cudaError_t le = launch_k(wgrad_tc_kernel<BN>, grid, dim3(WG_THREADS), smem, s, dim3(1, 1, cl), g,
                                     make_fastdiv((uint32_t)g.Wo), make_fastdiv((uint32_t)g.Ho), (const bf16*)p->dy, p->ldy, p->Cout,
-                                    p->dw, p->cin_real, p->cout_real, bps, WG_PIX * 128, WG_PIX * 128, cl, g_dev_error_flag);
+                                    p->dw, p->cin_real, p->cout_real, bps, WG_PIX * 128, WG_PIX * 128, cl, g_dev_error_flag, grp);
     if (le != cudaSuccess) return set_error(D3FK_ERR_CUDA, "wgrad_tc launch: %s", cudaGetErrorString(le));
   }
   count_launch();
@@ -1919,6 +1965,23 @@ int launch_wgrad_tc(const d3fk_wgrad_params* p, cudaStream_t s) {
   return launch_wgrad_tc_bn<64>(g, p, s);
 }
 
+int launch_wgrad_group_tc(const d3fk_wgrad_group_params* gp, cudaStream_t s) {
+  const d3fk_wgrad_params* p = &gp->base;
+  D3FK_CHECK_ARG(gp->count >= 1 && gp->count <= D3FK_WGRAD_GROUP_MAX, "wgrad group: count out of range");
+  D3FK_CHECK_ARG(p->c1 == 0 && p->src1 == nullptr, "wgrad group: single-source layers only");
+  for (int i = 0; i < gp->count; ++i) {
+    D3FK_CHECK_ARG(gp->src0[i] && gp->dy[i] && gp->dw[i], "wgrad group: null pointer in a problem");
+    D3FK_CHECK_ARG((((uintptr_t)gp->src0[i] | (uintptr_t)gp->dy[i]) & 15) == 0, "wgrad group: operands must be 16-byte aligned");
+  }
+  Gather g;
+  int rc = make_gather(g, gp->src0[0], nullptr, p->c0, 0, p->ld0, p->ld1, p->up0, p->B, p->Hi, p->Wi, p->Ho, p->Wo, p->kh,
+                       p->kw, p->stride, p->pad, 0);
+  if (rc) return rc;
+  D3FK_CHECK_ARG(p->Cout % 8 == 0 && p->ldy % 8 == 0, "Cout and ldy must be multiples of 8");
+  if (p->Cout > 64) return launch_wgrad_tc_bn<128>(g, p, s, gp);
+  return launch_wgrad_tc_bn<64>(g, p, s, gp);
+}
+
 int tc_init() {
   cudaError_t e = cudaSuccess;
   int dev = 0, sms = 0;
@@ -1938,6 +2001,7 @@ int tc_init() {
   if (const char* v = getenv("D3FK_WG_OCC")) g_wg_ctas_per_sm = atoi(v);
   if (const char* v = getenv("D3FK_WG_CAP")) g_wg_cap = atoi(v);
   if (const char* v = getenv("D3FK_WG_PLAIN")) g_wg_plain = atoi(v);
+  if (const char* v = getenv("D3FK_WG_GROUP_OCC")) g_wg_group_occ = atoi(v);
 #define SET_SMEM(k, bytes)                                                                          \
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);               \
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -1982,8 +2046,8 @@ int tc_init() {
   SET_SMEM((conv_slab_kernel<128, 4>), SLAB_MAX_SMEM)
   SET_SMEM(wgrad_slab_kernel<16>, SLAB_MAX_SMEM)
   SET_SMEM(wgrad_slab_kernel<32>, SLAB_MAX_SMEM)
-  SET_SMEM(wgrad_tc_kernel<64>, WgradCfg<64>::SMEM)
-  SET_SMEM(wgrad_tc_kernel<128>, WgradCfg<128>::SMEM)
+  SET_SMEM(wgrad_tc_kernel<64>, WG_ONE_PER_SM_SMEM)
+  SET_SMEM(wgrad_tc_kernel<128>, WG_ONE_PER_SM_SMEM)
 #undef SET_SMEM
   if (e != cudaSuccess) return set_error(D3FK_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   return D3FK_OK;

@@ -15,10 +15,16 @@ import torch
 from . import _lib
 from ._lib import make_op, op_params
 
-# D3FK_FUSE_BNBW=1: fold BN-backward's reduction into the epilogue of the dgrad that produces the gradient (23 fewer launches
-# per step).  Opt-in: measured on B200 the per-lane x / act loads lengthen the dgrad epilogues by as much as the removed
-# reduction passes cost (step 4.53 ms fused vs 4.42 ms unfused).
-FUSE_BN_BWD_REDUCE = os.environ.get("D3FK_FUSE_BNBW", "0") == "1"
+# D3FK_FUSE_BNBW=<elements>: fold BN-backward's reduction into the epilogue of the dgrad that produces the gradient, for
+# layers whose BN tensor has at most that many elements (1 = every layer, 0 = never).  On the big decoder-tail / stem tensors
+# the per-lane x / act loads lengthen the dgrad epilogue by more than the removed (HBM-bound) reduction pass costs; on the
+# deep, latency-bound layers the removed kernel boundary wins.
+_f = int(os.environ.get("D3FK_FUSE_BNBW", "0"))
+FUSE_BN_BWD_MAX_ELEMS = (1 << 62) if _f == 1 else _f
+# D3FK_WGRAD_GROUP=1: one weight-gradient launch per group of identically shaped encoder layers (D3FK_OP_WGRAD_GROUP) instead
+# of one per convolution.  Measured: -0.33 ms of GPU work per step, but no change of the step time (the weight gradients are
+# hidden behind the latency-bound main chain either way, and the last group lengthens the tail) - opt-in.
+GROUP_WGRAD = os.environ.get("D3FK_WGRAD_GROUP", "0") == "1"
 
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
@@ -398,6 +404,33 @@ class UnetPlan:
             f.update(src1=src1.ptr, c1=src1.C, ld1=src1.ld)
         return make_op(_lib.OP_WGRAD, **f)
 
+    def _wgrad_encoder(self, ops, pending, c, src, dy):
+        """Weight gradient of an encoder convolution.  The 3x3 / stride-1 / Cin == Cout convolutions of a ResNet stage are
+        identically shaped: they are collected and emitted as ONE grouped launch at the end of the stage's segment
+        (D3FK_OP_WGRAD_GROUP) — every dY of the stage is alive until then, the plan never recycles gradient buffers."""
+        if GROUP_WGRAD and c.k == 3 and c.stride == 1 and c.cin == c.cout and len(pending) < _lib.WGRAD_GROUP_MAX:
+            pending.append((c, src, dy))
+        else:
+            ops.append(self._wgrad_op(c, src, None, 0, dy))
+
+    def _flush_wgrad_group(self, ops, pending):
+        if not pending:
+            return
+        if len(pending) == 1:
+            c, src, dy = pending[0]
+            ops.append(self._wgrad_op(c, src, None, 0, dy))
+        else:
+            c, src, dy = pending[0]
+            for c2, s2, d2 in pending[1:]:
+                assert (c2.k, c2.stride, c2.pad, c2.cin, c2.cout, s2.H, s2.W, s2.C, s2.ld, d2.H, d2.W, d2.C, d2.ld) == \
+                       (c.k, c.stride, c.pad, c.cin, c.cout, src.H, src.W, src.C, src.ld, dy.H, dy.W, dy.C, dy.ld)
+            base = dict(dtype=self.dtype, c0=src.C, ld0=src.ld, up0=0, B=self.B, Hi=src.H, Wi=src.W, Ho=dy.H, Wo=dy.W,
+                        kh=c.k, kw=c.k, stride=c.stride, pad=c.pad, ldy=dy.ld, Cout=dy.C, cin_real=c.cin, cout_real=c.cout)
+            ops.append(make_op(_lib.OP_WGRAD_GROUP, base=base, count=len(pending),
+                               src0=[s2.ptr for _, s2, _ in pending], dy=[d2.ptr for _, _, d2 in pending],
+                               dw=[self._gptr(c2.name + ".weight") for c2, _, _ in pending]))
+        pending.clear()
+
     def _dgrad_op(self, c, dy, out, res=None, row0=0, rows=None):
         """dX (= out, channels [row0, row0+rows) of the conv input) from dY through conv c."""
         cout_pad = dy.C
@@ -429,7 +462,8 @@ class UnetPlan:
             bn.update(dres=g_masked.ptr, lddres=g_masked.ld)
         bn.pop("res", None)
         bn.pop("ldr", None)
-        prod = self._grad_producer.get(id(g_act)) if (self.dtype == _lib.BF16 and FUSE_BN_BWD_REDUCE) else None
+        fuse = self.dtype == _lib.BF16 and raw.B * raw.H * raw.W * raw.C <= FUSE_BN_BWD_MAX_ELEMS
+        prod = self._grad_producer.get(id(g_act)) if fuse else None
         if prod is not None:
             # The gradient arriving here was written (last) by a dgrad convolution: that kernel's epilogue also produces
             # sum(g') and sum(g' * xhat) (d3fk_conv_params.bw_*), so only the apply pass is left of BN backward.
@@ -518,13 +552,14 @@ class UnetPlan:
         for n in nblocks_per_stage:
             acc += n
             boundaries.add(acc)
+        pending = []      # identically shaped weight gradients of the current stage (see _wgrad_encoder)
         for bi in range(len(self.block_io) - 1, -1, -1):
             b, x, a1, idn, out = self.block_io[bi]
             d_r2, g_masked = self._bn_bwd(ops, b["conv2"], grad[id(out)], want_dres=True)
-            ops.append(self._wgrad_op(b["conv2"], a1, None, 0, d_r2))
+            self._wgrad_encoder(ops, pending, b["conv2"], a1, d_r2)
             add_grad(ops, b["conv2"], d_r2, a1)
             d_r1, _ = self._bn_bwd(ops, b["conv1"], grad[id(a1)])
-            ops.append(self._wgrad_op(b["conv1"], x, None, 0, d_r1))
+            self._wgrad_encoder(ops, pending, b["conv1"], x, d_r1)
             if b["down"] is not None:
                 d_rd, _ = self._bn_bwd(ops, b["down"], g_masked)
                 ops.append(self._wgrad_op(b["down"], x, None, 0, d_rd))
@@ -536,6 +571,8 @@ class UnetPlan:
                 grad[id(x)] = gx
                 ops.append(self._dgrad_op(b["conv1"], d_r1, gx, res=g_masked))
                 self._grad_producer[id(gx)] = ops[-1]
+            if bi in boundaries or bi == 0:
+                self._flush_wgrad_group(ops, pending)      # layer1's group overlaps the max-pool / stem backward below
             if bi in boundaries and bi != len(self.block_io):
                 segs.append(ops)
                 ops = []

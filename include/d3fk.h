@@ -80,6 +80,20 @@ typedef struct d3fk_wgrad_params {
   int32_t ldy, Cout, cin_real, cout_real;
 } d3fk_wgrad_params;
 
+/* ---- grouped weight gradient: `count` problems of IDENTICAL geometry (the 3x3 / stride-1 convolutions of one ResNet stage)
+ * in ONE launch.  `base` describes the geometry (its src0 / dy / dw are ignored); problem i reads src0[i], dy[i] and writes
+ * dw[i].  Single-source layers only (base.c1 == 0).  The deep stages' weight gradients are tiny GEMMs (4096 or 1024 pixels
+ * of reduction): launched one by one each needs a pixel split over a cluster, a reduction and ~20 us of fixed cost; grouped,
+ * the output tiles of the whole stage fill the chip and each CTA reduces over all (or most) pixels. */
+#define D3FK_WGRAD_GROUP_MAX 12
+typedef struct d3fk_wgrad_group_params {
+  d3fk_wgrad_params base;
+  int32_t count, _pad0;
+  const void* src0[D3FK_WGRAD_GROUP_MAX];
+  const void* dy[D3FK_WGRAD_GROUP_MAX];
+  float* dw[D3FK_WGRAD_GROUP_MAX];
+} d3fk_wgrad_group_params;
+
 /* ---- weight packing: fp32 OIHW master -> [Cout][kh][kw][cin_pad] (forward) and/or
  * [Cin][kh][kw][cout_pad] (dgrad) in dtype, zero padded. */
 typedef struct d3fk_pack_params {
@@ -211,6 +225,7 @@ enum d3fk_op_kind {
   D3FK_OP_LOSS = 21,
   D3FK_OP_CONV_BN = 22,
   D3FK_OP_UPCAT = 23,
+  D3FK_OP_WGRAD_GROUP = 25,   /* wgrad_group params; forked onto the side streams like D3FK_OP_WGRAD */
   D3FK_OP_BN_BWD = 24    /* bn params: bn_bwd_reduce + bn_bwd_apply as one op (one kernel behind a grid barrier when `barrier` is set) */
 };
 
@@ -221,6 +236,7 @@ typedef struct d3fk_op {
     d3fk_pool_params pool; d3fk_layout_params layout; d3fk_chansum_params chansum;
     d3fk_qsample_params qsample; d3fk_posterior_params posterior; d3fk_misc_params misc;
     d3fk_adam_params adam; d3fk_loss_params loss; d3fk_convbn_params convbn; d3fk_upcat_params upcat;
+    d3fk_wgrad_group_params wgrad_group;
   } u;
 } d3fk_op;
 
@@ -249,6 +265,7 @@ int d3fk_run_profile(const d3fk_op* ops, int n_ops, d3fk_stream stream, float* m
 /* single-op entry points (same launchers; used by the per-op parity tests) */
 int d3fk_conv(const d3fk_conv_params* p, d3fk_stream stream);
 int d3fk_wgrad(const d3fk_wgrad_params* p, d3fk_stream stream);
+int d3fk_wgrad_group(const d3fk_wgrad_group_params* p, d3fk_stream stream);
 int d3fk_conv_bn(const d3fk_convbn_params* p, d3fk_stream stream);
 int d3fk_pack_weights(const d3fk_pack_params* p, d3fk_stream stream);
 int d3fk_nchw_to_nhwc(const d3fk_layout_params* p, d3fk_stream stream);

@@ -253,6 +253,13 @@ def run_pack_all(p):
         run_pack(table[i])
 
 
+def run_wgrad_group(p):
+    for i in range(p.count):
+        one = _lib.WgradParams.from_buffer_copy(bytes(p.base))
+        one.src0, one.dy, one.dw = p.src0[i], p.dy[i], p.dw[i]
+        run_wgrad(one)
+
+
 def run_bn_bwd(p):
     run_bn_bwd_reduce(p)
     run_bn_bwd_apply(p)
@@ -282,6 +289,7 @@ _DISPATCH = {
     _lib.OP_BN_BWD_APPLY: run_bn_bwd_apply, _lib.OP_MAXPOOL_FWD: run_maxpool_fwd, _lib.OP_MAXPOOL_BWD: run_maxpool_bwd,
     _lib.OP_SUMPOOL2: run_sumpool2, _lib.OP_CHANSUM: run_chansum, _lib.OP_MEMSET: run_memset,
     _lib.OP_PACK_ALL: run_pack_all, _lib.OP_CONV_BN: run_conv_bn, _lib.OP_UPCAT: run_upcat, _lib.OP_BN_BWD: run_bn_bwd,
+    _lib.OP_WGRAD_GROUP: run_wgrad_group,
 }
 
 

@@ -8,6 +8,7 @@ import torch
 
 from denoising_diffusion_deep_fake_b200 import _lib
 from gpu_harness import run_both, rel_err
+import op_interpreter as I
 
 pytestmark = pytest.mark.gpu
 TOL = {_lib.F32: 1e-5, _lib.BF16: 1e-2}
@@ -366,3 +367,43 @@ def test_dgrad_with_fused_bn_backward_reduction(case):
     assert rel_err(*r["out"]) < 1e-2
     g, c = r["stats"]
     assert rel_err(g, c) < 2e-2, rel_err(g, c)
+
+
+WGRAD_GROUP_CASES = [
+    # (count, B, H, C): the encoder stages' shapes at reduced batch, plus regimes that exercise every split / cluster choice:
+    # many tiles (no split), few tiles (cluster split over the pixels), a single problem, the maximum group size
+    (6, 4, 16, 64), (7, 8, 8, 128), (11, 16, 4, 256), (5, 32, 2, 512), (1, 16, 4, 256), (12, 2, 8, 64), (2, 64, 4, 128),
+]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("count,B,H,C", WGRAD_GROUP_CASES)
+def test_wgrad_group(dtype, count, B, H, C):
+    """d3fk_wgrad_group: `count` identically shaped 3x3 / stride-1 weight gradients in one launch, against the CPU interpreter
+    (per problem) and against the single-problem entry point d3fk_wgrad on the same operands."""
+    _lib.init(0)
+    dev = "cuda:0"
+    tdt = torch.float32 if dtype == _lib.F32 else torch.bfloat16
+    g = torch.Generator().manual_seed(5)
+    xs = [torch.randn(B, H, H, C, generator=g).to(dev).to(tdt) for _ in range(count)]
+    dys = [torch.randn(B, H, H, C, generator=g).to(dev).to(tdt) for _ in range(count)]
+    dws = [torch.zeros(C, C, 3, 3, device=dev) for _ in range(count)]
+    base = dict(dtype=dtype, c0=C, c1=0, ld0=C, ld1=0, up0=0, B=B, Hi=H, Wi=H, Ho=H, Wo=H, kh=3, kw=3, stride=1, pad=1,
+                ldy=C, Cout=C, cin_real=C, cout_real=C)
+    op = _lib.make_op(_lib.OP_WGRAD_GROUP, base=base, count=count, src0=[t.data_ptr() for t in xs],
+                      dy=[t.data_ptr() for t in dys], dw=[t.data_ptr() for t in dws])
+    stream = torch.cuda.current_stream().cuda_stream
+    _lib.run_single(op, stream)
+    torch.cuda.synchronize()
+    assert _lib.load().d3fk_device_error_flag() == 0, "kernel watchdog tripped"
+    tol = 2e-5 if dtype == _lib.F32 else 1e-2
+    for i in range(count):
+        x_c, dy_c = xs[i].float().cpu().contiguous(), dys[i].float().cpu().contiguous()
+        dw_c = torch.zeros(C, C, 3, 3)
+        cpu_base = dict(base, dtype=_lib.F32)
+        I.run_ops([_lib.make_op(_lib.OP_WGRAD, src0=x_c.data_ptr(), dy=dy_c.data_ptr(), dw=dw_c.data_ptr(), **cpu_base)])
+        assert rel_err(dws[i].cpu(), dw_c) < tol, (i, rel_err(dws[i].cpu(), dw_c))
+        one = torch.zeros(C, C, 3, 3, device=dev)
+        _lib.run_single(_lib.make_op(_lib.OP_WGRAD, src0=xs[i].data_ptr(), dy=dys[i].data_ptr(), dw=one.data_ptr(), **base), stream)
+        torch.cuda.synchronize()
+        assert rel_err(dws[i].cpu(), one.cpu()) < (1e-6 if dtype == _lib.F32 else 1e-5)

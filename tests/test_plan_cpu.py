@@ -151,6 +151,8 @@ def test_pack_buckets_follow_backward_segments():
             written = []
             if op.kind == _lib.OP_WGRAD:
                 written.append(p.dw)
+            if op.kind == _lib.OP_WGRAD_GROUP:
+                written += [p.dw[i] for i in range(p.count)]
             if op.kind in (_lib.OP_BN_BWD, _lib.OP_BN_BWD_APPLY, _lib.OP_BN_BWD_FINALIZE):
                 written += [q for q in (p.dgamma, p.dbeta) if q]
             for q in written:

@@ -21,6 +21,10 @@ def describe(op):
     if op.kind == _lib.OP_WGRAD:
         M = p.B * p.Ho * p.Wo; K = p.kh * p.kw * (p.c0 + p.c1)
         return f"M={M} N={p.Cout} K={K} k{p.kh}s{p.stride} up{p.up0}", 2.0 * M * p.Cout * K
+    if op.kind == _lib.OP_WGRAD_GROUP:
+        b = p.base
+        M = b.B * b.Ho * b.Wo; K = b.kh * b.kw * b.c0
+        return f"x{p.count} M={M} N={b.Cout} K={K} k{b.kh}s{b.stride}", 2.0 * M * b.Cout * K * p.count
     if op.kind in (_lib.OP_BN_APPLY, _lib.OP_BN_BWD_REDUCE, _lib.OP_BN_BWD_APPLY):
         return f"count={p.count} C={p.C}", 0.0
     return "", 0.0
