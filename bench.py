@@ -288,7 +288,8 @@ def run_d3fk(args):
     if not args.no_sample:
         sb, ss, n_steps = args.sample_batch, args.sample_size, args.sample_steps
         mod.model.eval()
-        smp = Sampler(mod.model, sb, ss, ss, n_steps, r_start=1.0, eta=1.0, seed=7 + rank, use_graph=True)
+        smp = Sampler(mod.model, sb, ss, ss, n_steps, r_start=1.0, eta=1.0, seed=7 + rank, use_graph=True,
+                      chains=args.sample_chains)
         smp.run()
         barrier()
         e0.record()
@@ -301,7 +302,8 @@ def run_d3fk(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             sms = t.item()
         sample = {"metric": "sample_img_steps_per_s", "value": world * sb * n_steps / (sms / 1e3), "unit": "img-steps/s",
-                  "config": {"workload": f"{n_steps}-step DDPM sampling @{ss}x{ss}, batch {sb}/GPU, CUDA-graph replay"},
+                  "config": {"workload": f"{n_steps}-step DDPM sampling @{ss}x{ss}, batch {sb}/GPU, CUDA-graph replay",
+                             "chains": smp.chains},
                   "ms_per_step": sms / n_steps, "kernels_per_step": smp.kernels_per_step}
         mod.model.train()
 
@@ -341,6 +343,7 @@ def main():
     ap.add_argument("--sample-batch", type=int, default=64)
     ap.add_argument("--sample-size", type=int, default=128)
     ap.add_argument("--sample-steps", type=int, default=50)
+    ap.add_argument("--sample-chains", type=int, default=None, help="sub-batches sampled as parallel graph branches")
     ap.add_argument("--no-sample", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--main-priority", type=int, default=int(os.environ.get("D3FK_MAIN_PRIORITY", "0")))

@@ -255,6 +255,17 @@ class Unet(nn.Module):
         plans.append(plan)
         return plan
 
+    def _new_plan(self, x, training=False):
+        """A private plan instance (not cached per shape): the sampler owns one per chain."""
+        dev = x.device
+        _lib.init(dev.index if dev.index is not None else torch.cuda.current_device())
+        B, _, H, W = x.shape
+        if training:
+            self._ensure_grad_arena(dev)
+        return UnetPlan(dict(self.named_parameters()), dict(self.named_buffers()), B, H, W, self.dtype_code, dev, training,
+                        grad_arena=self._grad_arena if training else None,
+                        grad_offsets=self._grad_offsets if training else None)
+
     def _weights_version(self):
         ts = self.__dict__.get("_version_tensors")
         if ts is None:      # cached flat list (reset with the other runtime state): this runs twice per training step
