@@ -688,6 +688,63 @@ __global__ void __launch_bounds__(256) adam_kernel(d3fk_adam_params p) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Video-frame pre / post-processing (d3f/train_deep_fake/lit_module.py:272-300).  HBM-bound byte shuffles: 3 B read + 12 B
+// written per pixel one way, 12 B + 3 B the other.  A thread owns 4 consecutive pixels of one image: 12 contiguous frame
+// bytes (three 32-bit words) on the HWC side, one float4 per colour plane on the NCHW side; H*W % 4 == 0 is required (the
+// network needs H, W % 32 == 0 anyway).  BGR <-> RGB is the index 2 - c.
+__global__ void __launch_bounds__(256) frames_to_tensor_kernel(d3fk_frames_params p) {
+  pdl_enter();
+  const long long hw = (long long)p.H * p.W, q_per_img = hw >> 2, total = q_per_img * p.N;
+  float m255[3], s255[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) { m255[c] = __fmul_rn(p.mean[c], 255.f); s255[c] = __fmul_rn(p.std[c], 255.f); }
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / q_per_img, q = i - n * q_per_img;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(p.frames + (n * hw + 4 * q) * 3);
+    uint32_t w[3] = {__ldcs(src), __ldcs(src + 1), __ldcs(src + 2)};
+    const uint8_t* b = reinterpret_cast<const uint8_t*>(w);          // b[3*pix + {0:B, 1:G, 2:R}]
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {                                    // c: RGB plane
+      float4 o;
+      o.x = __fdiv_rn(__fsub_rn((float)b[0 + 2 - c], m255[c]), s255[c]);
+      o.y = __fdiv_rn(__fsub_rn((float)b[3 + 2 - c], m255[c]), s255[c]);
+      o.z = __fdiv_rn(__fsub_rn((float)b[6 + 2 - c], m255[c]), s255[c]);
+      o.w = __fdiv_rn(__fsub_rn((float)b[9 + 2 - c], m255[c]), s255[c]);
+      reinterpret_cast<float4*>(p.tensor + (n * 3 + c) * hw)[q] = o;
+    }
+  }
+}
+
+__device__ __forceinline__ uint32_t denorm_u8(float t, float s255, float m255) {
+  const float v = __fadd_rn(__fmul_rn(t, s255), m255);              // tensor *= std*255; tensor += mean*255 (two roundings)
+  int iv = (v != v) ? 0 : (v >= 2147483648.f ? 2147483647 : (v <= -2147483648.f ? (-2147483647 - 1) : (int)v));   // .int(): toward zero
+  iv = min(max(iv, 0), 255);
+  return (uint32_t)iv;
+}
+__global__ void __launch_bounds__(256) tensor_to_frames_kernel(d3fk_frames_params p) {
+  pdl_enter();
+  const long long hw = (long long)p.H * p.W, q_per_img = hw >> 2, total = q_per_img * p.N;
+  float m255[3], s255[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) { m255[c] = __fmul_rn(p.mean[c], 255.f); s255[c] = __fmul_rn(p.std[c], 255.f); }
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / q_per_img, q = i - n * q_per_img;
+    uint32_t w[3] = {0u, 0u, 0u};
+    uint8_t* b = reinterpret_cast<uint8_t*>(w);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float4 t = __ldcs(reinterpret_cast<const float4*>(p.tensor + (n * 3 + c) * hw) + q);
+      b[0 + 2 - c] = (uint8_t)denorm_u8(t.x, s255[c], m255[c]);
+      b[3 + 2 - c] = (uint8_t)denorm_u8(t.y, s255[c], m255[c]);
+      b[6 + 2 - c] = (uint8_t)denorm_u8(t.z, s255[c], m255[c]);
+      b[9 + 2 - c] = (uint8_t)denorm_u8(t.w, s255[c], m255[c]);
+    }
+    uint32_t* dst = reinterpret_cast<uint32_t*>(p.frames + (n * hw + 4 * q) * 3);
+    dst[0] = w[0]; dst[1] = w[1]; dst[2] = w[2];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // launchers
 #define DISPATCH_T(dtype, ...)                                   \
   if ((dtype) == D3FK_F32) { using T = float; __VA_ARGS__; }     \
@@ -844,6 +901,27 @@ int launch_pack_all(const d3fk_misc_params* p, cudaStream_t s) {
   else launch_k(pack_all_kernel<float>, dim3((unsigned)blocks), dim3(256), 0, s, dim3(1, 1, 1), (const d3fk_pack_params*)p->p0, count);
   count_launch();
   return check_launch("pack_all");
+}
+static int check_frames(const d3fk_frames_params* p) {
+  D3FK_CHECK_ARG(p->N > 0 && p->H > 0 && p->W > 0 && p->frames && p->tensor, "empty batch or null buffer");
+  D3FK_CHECK_ARG(((long long)p->H * p->W) % 4 == 0, "H*W must be a multiple of 4");
+  D3FK_CHECK_ARG((((uintptr_t)p->frames) & 3) == 0 && (((uintptr_t)p->tensor) & 15) == 0, "frames must be 4-byte and tensor 16-byte aligned");
+  D3FK_CHECK_ARG(p->std[0] != 0.f && p->std[1] != 0.f && p->std[2] != 0.f, "std must be non-zero");
+  return D3FK_OK;
+}
+int launch_frames_to_tensor(const d3fk_frames_params* p, cudaStream_t s) {
+  int rc = check_frames(p);
+  if (rc) return rc;
+  launch_k(frames_to_tensor_kernel, dim3(grid_for((long long)p->N * p->H * p->W / 4, 256)), dim3(256), 0, s, dim3(1, 1, 1), *p);
+  count_launch();
+  return check_launch("frames_to_tensor");
+}
+int launch_tensor_to_frames(const d3fk_frames_params* p, cudaStream_t s) {
+  int rc = check_frames(p);
+  if (rc) return rc;
+  launch_k(tensor_to_frames_kernel, dim3(grid_for((long long)p->N * p->H * p->W / 4, 256)), dim3(256), 0, s, dim3(1, 1, 1), *p);
+  count_launch();
+  return check_launch("tensor_to_frames");
 }
 int launch_adam(const d3fk_adam_params* p, cudaStream_t s) {
   D3FK_CHECK_ARG((((uintptr_t)p->p | (uintptr_t)p->g | (uintptr_t)p->m | (uintptr_t)p->v | (uintptr_t)p->ema) & 15) == 0, "arenas must be 16-byte aligned");

@@ -89,3 +89,41 @@ def adam_step_(p, g, m, v, lr, beta1, beta2, eps, step, ema=None, ema_decay=0.0,
                  eps=float(eps), bias1=1.0 - beta1 ** step, bias2=1.0 - beta2 ** step, ema_decay=float(ema_decay),
                  grad_scale=float(grad_scale))
     _lib.run_single(op, _stream(p))
+
+
+def _frames_op(kind, frames, tensor, mean, std):
+    N, H, W, _ = frames.shape
+    op = make_op(kind, N=N, H=H, W=W, frames=frames.data_ptr(), tensor=tensor.data_ptr(),
+                 mean=[float(v) for v in mean], std=[float(v) for v in std])
+    _lib.run_single(op, _stream(tensor))
+
+
+def frames_to_tensor(frames_bgr, mean, std):
+    """LitModule.cv2_to_tensor_normalised (d3f/train_deep_fake/lit_module.py:272-283), batched and on the device:
+    uint8 BGR frames [N,H,W,3] (or one [H,W,3]) -> normalised fp32 RGB [N,3,H,W] = (v - mean*255) / (std*255)."""
+    if frames_bgr.dim() == 3:
+        frames_bgr = frames_bgr.unsqueeze(0)
+    if not frames_bgr.is_cuda:
+        raise _lib.D3fkError("frames must be on a B200 (sm_100a) CUDA device; there is no CPU path")
+    if frames_bgr.dtype != torch.uint8 or frames_bgr.dim() != 4 or frames_bgr.shape[-1] != 3:
+        raise RuntimeError(f"expected uint8 BGR frames [N,H,W,3], got {frames_bgr.dtype} {tuple(frames_bgr.shape)}")
+    frames_bgr = frames_bgr.contiguous()
+    N, H, W, _ = frames_bgr.shape
+    _lib.init(frames_bgr.device.index if frames_bgr.device.index is not None else torch.cuda.current_device())
+    out = torch.empty((N, 3, H, W), dtype=torch.float32, device=frames_bgr.device)
+    _frames_op(_lib.OP_FRAMES_TO_TENSOR, frames_bgr, out, mean, std)
+    return out
+
+
+def tensor_to_frames(tensor, mean, std):
+    """LitModule.tensor_cv2_to_denormalised (d3f/train_deep_fake/lit_module.py:285-300), batched and on the device:
+    fp32 RGB [N,3,H,W] -> uint8 BGR frames [N,H,W,3] = clamp(int(t*std*255 + mean*255), 0, 255).  The input is left
+    untouched (the reference scales it in place)."""
+    _require_cuda_f32(tensor, "tensor")
+    if tensor.dim() != 4 or tensor.shape[1] != 3:
+        raise RuntimeError(f"expected fp32 RGB [N,3,H,W], got {tuple(tensor.shape)}")
+    tensor = tensor.contiguous()
+    N, _, H, W = tensor.shape
+    out = torch.empty((N, H, W, 3), dtype=torch.uint8, device=tensor.device)
+    _frames_op(_lib.OP_TENSOR_TO_FRAMES, out, tensor, mean, std)
+    return out

@@ -359,10 +359,30 @@ class DeepFakeModule(nn.Module):
 
     @torch.no_grad()
     def predict_fake(self, real, model_a_or_b):
-        """Batched tensor-level predict_fake (lit_module.py:251-270): normalised [B,3,H,W] in, same out."""
+        """predict_fake (lit_module.py:251-270).  Two input forms:
+        * the reference's: one uint8 BGR frame [H,W,3] (numpy, as cv2 delivers it) or a batch [N,H,W,3] (numpy or a uint8
+          CUDA tensor) -> the fake frame(s), same type and layout.  Normalisation, the network and the conversion back
+          all run on the device (d3fk_frames_to_tensor / d3fk_tensor_to_frames); model "a" uses mean_b / std_b and
+          model "b" mean_a / std_a, as the reference does (:253-257).
+        * a normalised fp32 tensor [B,3,H,W] -> the network output (tensor-level use inside training code)."""
+        import numpy as np
+        from .functional import frames_to_tensor, tensor_to_frames
         model = self.model_a if model_a_or_b == "a" else self.model_b
+        is_numpy = isinstance(real, np.ndarray)
+        frames = torch.from_numpy(np.ascontiguousarray(real)) if is_numpy else real
         was = model.training
         model.eval()
-        out = model(real)
-        model.train(was)
-        return out
+        try:
+            if frames.dtype != torch.uint8:
+                return model(frames)
+            p = self.hparams
+            other = "b" if model_a_or_b == "a" else "a"
+            mean, std = p.get(f"mean_{other}", [0.5] * 3), p.get(f"std_{other}", [0.5] * 3)
+            single = frames.dim() == 3
+            dev = next(model.parameters()).device
+            x = frames_to_tensor(frames.to(dev, non_blocking=True), mean, std)
+            fake = tensor_to_frames(model(x), mean, std)
+            fake = fake[0] if single else fake
+            return fake.cpu().numpy() if is_numpy else fake
+        finally:
+            model.train(was)

@@ -160,6 +160,20 @@ typedef struct d3fk_upcat_params {
   const void* src0; const void* src1; void* out;
 } d3fk_upcat_params;
 
+/* ---- video-frame pre / post-processing, batched.
+ * frames_to_tensor replaces LitModule.cv2_to_tensor_normalised (d3f/train_deep_fake/lit_module.py:272-283):
+ *   uint8 BGR HWC [N,H,W,3] -> fp32 RGB NCHW [N,3,H,W],  t = (float(v) - mean_c*255) / (std_c*255)   (two fp32 roundings)
+ * tensor_to_frames replaces LitModule.tensor_cv2_to_denormalised (:285-300):
+ *   fp32 RGB NCHW -> uint8 BGR HWC,  v = clamp(int(t*(std_c*255) + mean_c*255), 0, 255)  (product and sum rounded
+ *   separately, conversion truncates toward zero as tensor.int() does and saturates beyond int32 as it does on a CUDA
+ *   device).  mean / std are in RGB order (the configs' order).
+ * `frames` is read by to_tensor and written by to_frames; `tensor` the other way round. */
+typedef struct d3fk_frames_params {
+  int32_t N, H, W, _pad0;
+  uint8_t* frames; float* tensor;
+  float mean[3], std[3];
+} d3fk_frames_params;
+
 /* per-channel sum over (n,h,w) of an NHWC tensor into fp32 out[c] (head bias gradient) */
 typedef struct d3fk_chansum_params {
   int32_t dtype, C, ld, _pad0; int64_t count;
@@ -225,6 +239,7 @@ enum d3fk_op_kind {
   D3FK_OP_LOSS = 21,
   D3FK_OP_CONV_BN = 22,
   D3FK_OP_UPCAT = 23,
+  D3FK_OP_FRAMES_TO_TENSOR = 26, D3FK_OP_TENSOR_TO_FRAMES = 27,   /* frames params */
   D3FK_OP_WGRAD_GROUP = 25,   /* wgrad_group params; forked onto the side streams like D3FK_OP_WGRAD */
   D3FK_OP_BN_BWD = 24    /* bn params: bn_bwd_reduce + bn_bwd_apply as one op (one kernel behind a grid barrier when `barrier` is set) */
 };
@@ -236,7 +251,7 @@ typedef struct d3fk_op {
     d3fk_pool_params pool; d3fk_layout_params layout; d3fk_chansum_params chansum;
     d3fk_qsample_params qsample; d3fk_posterior_params posterior; d3fk_misc_params misc;
     d3fk_adam_params adam; d3fk_loss_params loss; d3fk_convbn_params convbn; d3fk_upcat_params upcat;
-    d3fk_wgrad_group_params wgrad_group;
+    d3fk_wgrad_group_params wgrad_group; d3fk_frames_params frames;
   } u;
 } d3fk_op;
 
@@ -266,6 +281,8 @@ int d3fk_run_profile(const d3fk_op* ops, int n_ops, d3fk_stream stream, float* m
 int d3fk_conv(const d3fk_conv_params* p, d3fk_stream stream);
 int d3fk_wgrad(const d3fk_wgrad_params* p, d3fk_stream stream);
 int d3fk_wgrad_group(const d3fk_wgrad_group_params* p, d3fk_stream stream);
+int d3fk_frames_to_tensor(const d3fk_frames_params* p, d3fk_stream stream);
+int d3fk_tensor_to_frames(const d3fk_frames_params* p, d3fk_stream stream);
 int d3fk_conv_bn(const d3fk_convbn_params* p, d3fk_stream stream);
 int d3fk_pack_weights(const d3fk_pack_params* p, d3fk_stream stream);
 int d3fk_nchw_to_nhwc(const d3fk_layout_params* p, d3fk_stream stream);

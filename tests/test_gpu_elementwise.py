@@ -103,3 +103,97 @@ def test_fused_adam_matches_torch_optim(n, betas, with_ema):
     assert rel_err(p.cpu(), ref.detach()) < 1e-6
     if with_ema:
         assert rel_err(ema.cpu(), ema_ref) < 1e-6
+
+
+FRAME_NORMS = [([0.5, 0.5, 0.5], [0.5, 0.5, 0.5]), ([0.485, 0.456, 0.406], [0.229, 0.224, 0.225])]
+
+
+@pytest.mark.parametrize("mean,std", FRAME_NORMS)
+@pytest.mark.parametrize("shape", [(3, 32, 64), (1, 128, 128), (2, 6, 10), (5, 448, 448)])
+def test_frames_to_tensor_bit_exact(mean, std, shape):
+    """d3fk_frames_to_tensor vs the reference arithmetic (d3f/train_deep_fake/lit_module.py:272-283): bit-exact."""
+    import numpy as np
+    from denoising_diffusion_deep_fake_b200.functional import frames_to_tensor
+    N, H, W = shape
+    rng = np.random.default_rng(0)
+    frames = rng.integers(0, 256, size=(N, H, W, 3), dtype=np.uint8)
+    frames[0, 0, :4] = [[0, 0, 0], [255, 255, 255], [0, 128, 255], [1, 2, 3]]
+    ref = oracle.cv2_to_tensor_normalised(frames, mean, std)
+    out = frames_to_tensor(torch.from_numpy(frames).to(DEV), mean, std)
+    assert out.shape == ref.shape and out.dtype == torch.float32
+    assert torch.equal(out.cpu(), ref)
+    one = frames_to_tensor(torch.from_numpy(frames[0]).to(DEV), mean, std)        # a single [H,W,3] frame
+    assert torch.equal(one.cpu(), ref[:1])
+
+
+@pytest.mark.parametrize("mean,std", FRAME_NORMS)
+@pytest.mark.parametrize("shape", [(3, 32, 64), (1, 128, 128), (2, 6, 10), (5, 448, 448)])
+def test_tensor_to_frames_bit_exact(mean, std, shape):
+    """d3fk_tensor_to_frames vs the reference arithmetic (:285-300): bit-exact bytes, including truncation toward zero,
+    the clamp, values far out of range and exact level boundaries; the input tensor is not modified.  (Beyond +-2^31 the
+    reference's `tensor.int()` is device-dependent — x86 yields INT_MIN, CUDA saturates; d3fk saturates like the CUDA
+    device the reference runs this on — so the test stays inside the int32 range.)"""
+    import numpy as np
+    from denoising_diffusion_deep_fake_b200.functional import tensor_to_frames
+    N, H, W = shape
+    g = torch.Generator().manual_seed(1)
+    t = torch.randn(N, 3, H, W, generator=g) * 1.2
+    flat = t.view(-1)
+    flat[:8] = torch.tensor([-1.0, 1.0, 0.0, 1e6, -1e6, 16000000.0, -0.0039215689, 1.0000001])
+    levels = torch.arange(256, dtype=torch.float32)
+    flat[8:8 + 256] = (levels - 127.5) / 127.5                   # exact level boundaries of the 0.5 / 0.5 normalisation
+    ref = oracle.tensor_cv2_to_denormalised(t, mean, std)
+    t_dev = t.to(DEV)
+    keep = t_dev.clone()
+    out = tensor_to_frames(t_dev, mean, std)
+    assert out.dtype == torch.uint8 and tuple(out.shape) == (N, H, W, 3)
+    assert np.array_equal(out.cpu().numpy(), ref)
+    assert torch.equal(t_dev, keep)
+
+
+def test_frame_round_trip_and_errors():
+    """frames -> tensor -> frames equals the reference's own round trip (which loses one level on some values), at a full
+    video-frame size; malformed inputs fail loudly."""
+    import numpy as np
+    from denoising_diffusion_deep_fake_b200.functional import frames_to_tensor, tensor_to_frames
+    rng = np.random.default_rng(3)
+    frames = rng.integers(0, 256, size=(4, 448, 448, 3), dtype=np.uint8)
+    mean, std = [0.5] * 3, [0.5] * 3
+    ref = oracle.tensor_cv2_to_denormalised(oracle.cv2_to_tensor_normalised(frames, mean, std), mean, std)
+    out = tensor_to_frames(frames_to_tensor(torch.from_numpy(frames).to(DEV), mean, std), mean, std)
+    assert np.array_equal(out.cpu().numpy(), ref)
+    assert int(np.abs(out.cpu().numpy().astype(int) - frames.astype(int)).max()) <= 1
+    with pytest.raises(d3._lib.D3fkError):
+        frames_to_tensor(torch.from_numpy(frames), mean, std)                     # CPU tensor: no CPU path
+    with pytest.raises(RuntimeError):
+        frames_to_tensor(torch.zeros(1, 8, 8, 3, device=DEV), mean, std)          # not uint8
+    with pytest.raises(d3._lib.D3fkError):
+        frames_to_tensor(torch.zeros(1, 3, 3, 3, dtype=torch.uint8, device=DEV), mean, std)   # H*W % 4 != 0
+    with pytest.raises(d3._lib.D3fkError):
+        tensor_to_frames(torch.zeros(1, 3, 8, 8, device=DEV), mean, [0.5, 0.0, 0.5])          # std == 0
+
+
+def test_predict_fake_on_frames():
+    """DeepFakeModule.predict_fake with the reference's signature (one uint8 BGR frame in, one out,
+    d3f/train_deep_fake/lit_module.py:251-270) against the oracle chain normalise -> U-Net (eval) -> denormalise."""
+    import numpy as np
+    from denoising_diffusion_deep_fake_b200.train import DeepFakeModule
+    torch.manual_seed(0)
+    mod = DeepFakeModule(encoder_name="resnet34", learning_rate=1e-3, noise_exponential_sampling_lambda=3, mode="denoise",
+                         mean_a=[0.5, 0.5, 0.5], std_a=[0.5, 0.5, 0.5], mean_b=[0.45, 0.5, 0.55], std_b=[0.4, 0.5, 0.6],
+                         precision="fp32").to(DEV)
+    ref = oracle.Unet()
+    ref.load_state_dict(mod.model_a.state_dict())
+    ref.eval()
+    rng = np.random.default_rng(5)
+    frame = rng.integers(0, 256, size=(64, 64, 3), dtype=np.uint8)
+    fake = mod.predict_fake(frame, "a")
+    assert isinstance(fake, np.ndarray) and fake.dtype == np.uint8 and fake.shape == frame.shape
+    with torch.no_grad():
+        x = oracle.cv2_to_tensor_normalised(frame[None], [0.45, 0.5, 0.55], [0.4, 0.5, 0.6])     # model a uses mean_b / std_b
+        want = oracle.tensor_cv2_to_denormalised(ref(x), [0.45, 0.5, 0.55], [0.4, 0.5, 0.6])[0]
+    diff = np.abs(fake.astype(int) - want.astype(int))
+    assert diff.max() <= 1 and (diff != 0).mean() < 1e-2      # fp32 network within 1e-5: at most a level flips at a boundary
+    batch = torch.from_numpy(np.stack([frame, frame[::-1].copy()])).to(DEV)
+    out = mod.predict_fake(batch, "a")
+    assert out.is_cuda and out.dtype == torch.uint8 and np.array_equal(out[0].cpu().numpy(), fake)

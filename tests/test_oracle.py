@@ -146,3 +146,29 @@ def test_golden_vectors():
     with torch.no_grad():
         assert torch.allclose(model(gold["noisy"]), gold["pred_eval"], atol=2e-5, rtol=1e-4)
     assert abs(oracle.ssim(gold["x"].clamp(0, 1), gold["noisy"].clamp(0, 1)).item() - gold["ssim_xn"].item()) < 1e-6
+
+
+def test_frame_conversion_known_answers():
+    """oracle.frames restates d3f/train_deep_fake/lit_module.py:272-300: BGR uint8 HWC <-> normalised RGB fp32 CHW."""
+    import numpy as np
+    frame = np.zeros((1, 2, 2, 3), dtype=np.uint8)
+    frame[0, 0, 0] = (10, 20, 30)            # B, G, R
+    frame[0, 1, 1] = (255, 0, 128)
+    t = oracle.cv2_to_tensor_normalised(frame, [0.5, 0.5, 0.5], [0.5, 0.5, 0.5])
+    assert t.shape == (1, 3, 2, 2) and t.dtype == torch.float32
+    f32 = np.float32
+    assert t[0, 0, 0, 0].item() == (f32(30) - f32(127.5)) / f32(127.5)       # R plane first
+    assert t[0, 2, 0, 0].item() == (f32(10) - f32(127.5)) / f32(127.5)
+    assert t[0, 0, 1, 1].item() == (f32(128) - f32(127.5)) / f32(127.5)
+    assert t[0, 1, 0, 1].item() == -1.0 and t[0, 2, 1, 1].item() == 1.0
+    # back: truncation toward zero, clamp, channel reversal
+    x = torch.tensor([[-1.5, -1.0, 0.0, 0.999], [1.0, 1.7, 0.2, -0.004]]).reshape(1, 1, 2, 4).repeat(1, 3, 1, 1)
+    x[0, 2] += 0.01
+    out = oracle.tensor_cv2_to_denormalised(x, [0.5, 0.5, 0.5], [0.5, 0.5, 0.5])
+    assert out.shape == (1, 2, 4, 3) and out.dtype == np.uint8
+    assert out[0, 0, :, 2].tolist() == [0, 0, 127, 254] and out[0, 1, :, 2].tolist() == [255, 255, 153, 126]   # R from plane 0
+    assert out[0, 0, 2, 0] == 128                                             # B from plane 2 (0.01 * 127.5 + 127.5 = 128.775)
+    # the reference's own round trip is NOT the identity for every level (fp32 rounding + truncation): pin the count
+    levels = np.arange(256, dtype=np.uint8).reshape(1, 16, 16, 1).repeat(3, axis=3)
+    back = oracle.tensor_cv2_to_denormalised(oracle.cv2_to_tensor_normalised(levels, [0.5] * 3, [0.5] * 3), [0.5] * 3, [0.5] * 3)
+    assert int((back != levels).sum()) == int((back.astype(int) - levels.astype(int) == -1).sum())   # only ever one level low
