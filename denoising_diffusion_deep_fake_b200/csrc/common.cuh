@@ -111,6 +111,14 @@ template <typename T> __device__ __forceinline__ void load_vec(const T* p, float
 #pragma unroll
   for (int i = 0; i < N; ++i) out[i] = to_f<T>(e[i]);
 }
+// the same in two steps, for loops that keep several vectors in flight: hold the packed 16 bytes (4 registers), widen at use
+template <typename T> __device__ __forceinline__ uint4 load_raw(const T* p) { return *reinterpret_cast<const uint4*>(p); }
+template <typename T> __device__ __forceinline__ void unpack_vec(const uint4& raw, float* out) {
+  constexpr int N = Vec<T>::N;
+  const T* e = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+  for (int i = 0; i < N; ++i) out[i] = to_f<T>(e[i]);
+}
 template <typename T> __device__ __forceinline__ void store_vec(T* p, const float* in) {
   constexpr int N = Vec<T>::N;
   uint4 raw;

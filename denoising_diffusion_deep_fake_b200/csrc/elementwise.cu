@@ -18,6 +18,13 @@ static inline int grid_for(long long work_items, int threads, int max_waves = 8)
   return (int)blocks;
 }
 
+// Occupancy of the BatchNorm kernels (bf16 engine): at the 110-126 registers ptxas picks on its own only two blocks fit
+// an SM and the backward kernels reached 33-37 % of the HBM peak (ncu, r01e); capping the registers buys the third / fourth block.
+#ifndef D3FK_BN_BWD_BLOCKS
+#define D3FK_BN_BWD_BLOCKS 3
+#endif
+#define BN_BWD_OCC(T) (sizeof(T) == 2 ? D3FK_BN_BWD_BLOCKS : 1)
+
 // ---------------------------------------------------------------------------------------------
 // NCHW fp32 -> NHWC T, channels zero-padded to cpad (a multiple of 8)
 template <typename T>
@@ -79,7 +86,7 @@ __global__ void bn_fold_kernel(d3fk_bn_params p) {
 // every thread derives scale/shift of its own 8 (4) channels from the conv-epilogue sums, and the first C/V
 // threads of block 0 publish mean / invstd / running statistics — no separate finalize launch.
 template <typename T>
-__global__ void __launch_bounds__(256, 2) bn_apply_kernel(d3fk_bn_params p) {
+__global__ void __launch_bounds__(256, BN_BWD_OCC(T)) bn_apply_kernel(d3fk_bn_params p) {
   pdl_enter();
   constexpr int V = Vec<T>::N;
   constexpr int U = 4;               // independent 16-byte loads in flight per thread
@@ -91,15 +98,15 @@ __global__ void __launch_bounds__(256, 2) bn_apply_kernel(d3fk_bn_params p) {
   const long long e0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;   // multiple of cvs: the channel vector is loop invariant
   const int c = (int)(e0 % cvs) * V;
-  float v[U][V], r[U][V];
+  uint4 vr[U], rr[U];                // held packed (4 registers per vector) until used: 3 blocks per SM instead of 2
   auto load_batch = [&](long long e) {
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long eu = e + u * stride;
       if (eu < total) {
         const long long pix = eu / cvs;
-        load_vec<T>(x + pix * p.ldx + c, v[u]);
-        if (res) load_vec<T>(res + pix * p.ldr + c, r[u]);
+        vr[u] = load_raw<T>(x + pix * p.ldx + c);
+        if (res) rr[u] = load_raw<T>(res + pix * p.ldr + c);
       }
     }
   };
@@ -143,14 +150,17 @@ __global__ void __launch_bounds__(256, 2) bn_apply_kernel(d3fk_bn_params p) {
       const long long eu = e + u * stride;
       if (eu < total) {
         const long long pix = eu / cvs;
+        float v[V], r[V];
+        unpack_vec<T>(vr[u], v);
+        if (res) unpack_vec<T>(rr[u], r);
 #pragma unroll
         for (int i = 0; i < V; ++i) {
-          float t = fmaf(v[u][i], scf[i], shf[i]);
-          if (res) t += r[u][i];
+          float t = fmaf(v[i], scf[i], shf[i]);
+          if (res) t += r[i];
           if (p.relu) t = fmaxf(t, 0.f);
-          v[u][i] = t;
+          v[i] = t;
         }
-        store_vec<T>(y + pix * p.ldy + c, v[u]);
+        store_vec<T>(y + pix * p.ldy + c, v);
       }
     }
     e += U * stride;
@@ -179,27 +189,31 @@ __device__ __forceinline__ void bn_bwd_reduce_body(const d3fk_bn_params& p, doub
     const T* x = (const T*)p.x;
     const T* dy = (const T*)p.dy;
     const T* act = (const T*)p.act;
-    constexpr int U = 2;   // independent pixel rows in flight per thread
+    constexpr int U = 2;   // independent pixel rows in flight per thread, held PACKED (4 registers per 16-byte vector)
     const long long pstride = (long long)gridDim.x * rows_per_iter;
     for (long long pix0 = (long long)blockIdx.x * rows_per_iter + prow; pix0 < p.count; pix0 += U * pstride) {
-      float xv[U][V], gv[U][V], av[U][V];
+      uint4 xr[U], gr[U], ar[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const long long pix = pix0 + u * pstride;
         if (pix < p.count) {
-          load_vec<T>(x + pix * p.ldx + c, xv[u]);
-          load_vec<T>(dy + pix * p.lddy + c, gv[u]);
-          if (p.relu) load_vec<T>(act + pix * p.ldact + c, av[u]);
+          xr[u] = load_raw<T>(x + pix * p.ldx + c);
+          gr[u] = load_raw<T>(dy + pix * p.lddy + c);
+          if (p.relu) ar[u] = load_raw<T>(act + pix * p.ldact + c);
         }
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         if (pix0 + u * pstride < p.count) {
+          float xv[V], gv[V], av[V];
+          unpack_vec<T>(xr[u], xv);
+          unpack_vec<T>(gr[u], gv);
+          if (p.relu) unpack_vec<T>(ar[u], av);
 #pragma unroll
           for (int i = 0; i < V; ++i) {
-            float g = gv[u][i];
-            if (p.relu && !(av[u][i] > 0.f)) g = 0.f;
-            float xh = (xv[u][i] - mean[i]) * istd[i];
+            float g = gv[i];
+            if (p.relu && !(av[i] > 0.f)) g = 0.f;
+            float xh = (xv[i] - mean[i]) * istd[i];
             s1[i] += (Acc)g;
             s2[i] += (Acc)(g * xh);
           }
@@ -246,7 +260,7 @@ __device__ __forceinline__ void bn_bwd_reduce_body(const d3fk_bn_params& p, doub
   }
 }
 template <typename T, typename Acc>
-__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(d3fk_bn_params p) {
+__global__ void __launch_bounds__(256, BN_BWD_OCC(T)) bn_bwd_reduce_kernel(d3fk_bn_params p) {
   pdl_enter();
   extern __shared__ double sred_dyn[];  // [warps][2][C]
   bn_bwd_reduce_body<T, Acc>(p, sred_dyn);
@@ -265,6 +279,10 @@ __global__ void bn_bwd_finalize_kernel(d3fk_bn_params p) {
   p.coef[2 * p.C + c] = (float)(s2 / n);
 }
 
+__device__ __forceinline__ void lds_volatile_f4(uint32_t addr, float (&v)[4]) {
+  asm volatile("ld.volatile.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(addr));
+}
+
 // dx = c0*(dy' - c1 - xhat*c2), c0 = gamma*invstd, c1 = sum(dy')/n, c2 = sum(dy'*xhat)/n; optionally dres = dy'.
 // The coefficients are derived in-kernel from the reduction sums; the first C/V threads of block 0 also write
 // dgamma / dbeta (no separate finalize launch).
@@ -281,42 +299,41 @@ __device__ __forceinline__ void bn_bwd_apply_body(const d3fk_bn_params& p, float
   const long long e0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
   const int c = (int)(e0 % cvs) * V;
-  // s_k: [5][C]: k0, k1, k2, mean, invstd — derived once per block (L2 loads: the sums were produced by atomics)
+  // s_k: [4][C]: A = gamma*invstd, Bm = -A*invstd*sum(dy'*xhat)/n, C1 = -A*sum(dy')/n, mean — derived once per block (L2
+  // loads: the sums were produced by atomics), so that dx = A*dy' + Bm*(x - mean) + C1.  The coefficients stay in shared
+  // memory and are re-read (volatile 16-byte loads, warp-broadcast) at every use: as 5 x V registers per thread they cost a
+  // third of the register file and one of the three resident blocks.
   for (int ch = threadIdx.x; ch < p.C; ch += blockDim.x) {
     const double n = (double)p.count;
     const double s1 = __ldcg(p.bstats + ch), s2 = __ldcg(p.bstats + p.C + ch);
     const float is = __ldg(p.invstd + ch);
-    s_k[ch] = __ldg(p.gamma + ch) * is;
-    s_k[p.C + ch] = (float)(s1 / n);
-    s_k[2 * p.C + ch] = (float)(s2 / n);
+    const float A = __ldg(p.gamma + ch) * is;
+    s_k[ch] = A;
+    s_k[p.C + ch] = -A * is * (float)(s2 / n);
+    s_k[2 * p.C + ch] = -A * (float)(s1 / n);
     s_k[3 * p.C + ch] = __ldg(p.mean + ch);
-    s_k[4 * p.C + ch] = is;
     if (blockIdx.x == 0) {
       if (p.dbeta) p.dbeta[ch] = (float)s1;
       if (p.dgamma) p.dgamma[ch] = (float)s2;
     }
   }
   __syncthreads();
-  float k0[V], k1[V], k2[V], mean[V], istd[V];
-#pragma unroll
-  for (int i = 0; i < V; ++i) {
-    k0[i] = s_k[c + i]; k1[i] = s_k[p.C + c + i]; k2[i] = s_k[2 * p.C + c + i];
-    mean[i] = s_k[3 * p.C + c + i]; istd[i] = s_k[4 * p.C + c + i];
-  }
-  constexpr int U = 2;   // independent pixel vectors in flight per thread (3 loads each)
+  const uint32_t sk_addr = (uint32_t)__cvta_generic_to_shared(s_k + c);
+  const uint32_t sk_pitch = (uint32_t)p.C * 4u;
+  constexpr int U = 2;   // independent pixel vectors in flight per thread (3 loads each), held packed until used
   // Walk the tensor BACKWARDS: the reduction pass that ran just before streamed x, dy and act front to back, so their
   // tails are what the 126 MB L2 still holds.
   const long long last_pix = p.count - 1;
   for (long long e = e0; e < total; e += U * stride) {
-    float xv[U][V], gv[U][V], av[U][V];
+    uint4 xr[U], gr[U], ar[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long eu = e + u * stride;
       if (eu < total) {
         const long long pix = last_pix - eu / cvs;
-        load_vec<T>(x + pix * p.ldx + c, xv[u]);
-        load_vec<T>(dy + pix * p.lddy + c, gv[u]);
-        if (p.relu) load_vec<T>(act + pix * p.ldact + c, av[u]);
+        xr[u] = load_raw<T>(x + pix * p.ldx + c);
+        gr[u] = load_raw<T>(dy + pix * p.lddy + c);
+        if (p.relu) ar[u] = load_raw<T>(act + pix * p.ldact + c);
       }
     }
 #pragma unroll
@@ -324,24 +341,35 @@ __device__ __forceinline__ void bn_bwd_apply_body(const d3fk_bn_params& p, float
       const long long eu = e + u * stride;
       if (eu < total) {
         const long long pix = last_pix - eu / cvs;
-        float o[V];
+        float xv[V], gv[V], av[V], o[V];
+        unpack_vec<T>(xr[u], xv);
+        unpack_vec<T>(gr[u], gv);
+        if (p.relu) unpack_vec<T>(ar[u], av);
 #pragma unroll
-        for (int i = 0; i < V; ++i) {
-          float g = gv[u][i];
-          if (p.relu && !(av[u][i] > 0.f)) g = 0.f;
-          gv[u][i] = g;
-          const float xh = (xv[u][i] - mean[i]) * istd[i];
-          o[i] = k0[i] * (g - k1[i] - xh * k2[i]);
+        for (int i4 = 0; i4 < V; i4 += 4) {
+          float kA[4], kB[4], kC[4], kM[4];
+          lds_volatile_f4(sk_addr + 4u * i4, kA);
+          lds_volatile_f4(sk_addr + sk_pitch + 4u * i4, kB);
+          lds_volatile_f4(sk_addr + 2u * sk_pitch + 4u * i4, kC);
+          lds_volatile_f4(sk_addr + 3u * sk_pitch + 4u * i4, kM);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int i = i4 + j;
+            float g = gv[i];
+            if (p.relu && !(av[i] > 0.f)) g = 0.f;
+            gv[i] = g;
+            o[i] = fmaf(kA[j], g, fmaf(kB[j], xv[i] - kM[j], kC[j]));
+          }
         }
         store_vec<T>(dx + pix * p.lddx + c, o);
-        if (dres) store_vec<T>(dres + pix * p.lddres + c, gv[u]);
+        if (dres) store_vec<T>(dres + pix * p.lddres + c, gv);
       }
     }
   }
 }
 
 template <typename T>
-__global__ void bn_bwd_apply_kernel(d3fk_bn_params p) {
+__global__ void __launch_bounds__(256, BN_BWD_OCC(T)) bn_bwd_apply_kernel(d3fk_bn_params p) {
   pdl_enter();
   extern __shared__ float s_k_dyn[];
   bn_bwd_apply_body<T>(p, s_k_dyn);
@@ -532,17 +560,19 @@ __global__ void chansum_kernel(d3fk_chansum_params p) {
 
 // ---------------------------------------------------------------------------------------------
 // q_sample: out = sqrt(1-r_b) x + sqrt(r_b) eps   (d3f/train_denoiser/lit_module.py:128-153)
-__global__ void qsample_kernel(d3fk_qsample_params p) {
+// blockIdx.y = sample: the noise ratio r_b (one Philox draw, one log, two square roots) is formed once per block, not once
+// per 4 elements; the Philox counter of the element noise is still the global vector index, so results are unchanged.
+__global__ void __launch_bounds__(256) qsample_kernel(d3fk_qsample_params p) {
   pdl_enter();
-  const long long nvec = (long long)p.B * p.chw / 4;
   const int vec_per_sample = p.chw / 4;
-  const float cexp = __expf(-p.lam);
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
-    int b = (int)(i / vec_per_sample);
+  const int b = blockIdx.y;
+  __shared__ float s_coef[2];
+  if (threadIdx.x == 0) {
     float r;
     if (p.fixed_r >= 0.f) {
       r = p.fixed_r;
     } else {
+      const float cexp = __expf(-p.lam);
       float y;
       if (p.y) y = __ldg(p.y + b);
       else {
@@ -552,7 +582,15 @@ __global__ void qsample_kernel(d3fk_qsample_params p) {
       }
       r = (1.0f / p.lam) * logf(1.0f / (y * (1.0f - cexp) + cexp));
     }
-    float a = sqrtf(1.0f - r), s = sqrtf(r);
+    s_coef[0] = sqrtf(1.0f - r);
+    s_coef[1] = sqrtf(r);
+    if (p.r_out && blockIdx.x == 0) p.r_out[b] = r;
+  }
+  __syncthreads();
+  const float a = s_coef[0], s = s_coef[1];
+  const long long base = (long long)b * vec_per_sample;
+  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < vec_per_sample; v += gridDim.x * blockDim.x) {
+    const long long i = base + v;
     float4 x = __ldg(reinterpret_cast<const float4*>(p.x) + i);
     float4 n;
     if (p.noise) n = __ldg(reinterpret_cast<const float4*>(p.noise) + i);
@@ -560,7 +598,6 @@ __global__ void qsample_kernel(d3fk_qsample_params p) {
     float4 o = make_float4(a * x.x + s * n.x, a * x.y + s * n.y, a * x.z + s * n.z, a * x.w + s * n.w);
     reinterpret_cast<float4*>(p.out)[i] = o;
     if (p.noise_out) reinterpret_cast<float4*>(p.noise_out)[i] = n;
-    if (p.r_out && i == (long long)b * vec_per_sample) p.r_out[b] = r;
   }
 }
 
@@ -772,7 +809,7 @@ int launch_bn_apply(const d3fk_bn_params* p, cudaStream_t s) {
   D3FK_CHECK_ARG(p->C % 8 == 0, "C must be a multiple of 8");
   int V = p->dtype == D3FK_F32 ? 4 : 8;
   long long total = p->count * (p->C / V);
-  DISPATCH_T(p->dtype, launch_k(bn_apply_kernel<T>, dim3(grid_for(total, 256 * 4, 2)), dim3(256), 2 * p->C * sizeof(float), s, dim3(1, 1, 1), *p));
+  DISPATCH_T(p->dtype, launch_k(bn_apply_kernel<T>, dim3(grid_for(total, 256 * 4, D3FK_BN_BWD_BLOCKS)), dim3(256), 2 * p->C * sizeof(float), s, dim3(1, 1, 1), *p));
   count_launch();
   return check_launch("bn_apply");
 }
@@ -803,7 +840,7 @@ int launch_bn_bwd_apply(const d3fk_bn_params* p, cudaStream_t s) {
   D3FK_CHECK_ARG(p->C % 8 == 0, "C must be a multiple of 8");
   int V = p->dtype == D3FK_F32 ? 4 : 8;
   long long total = p->count * (p->C / V);
-  DISPATCH_T(p->dtype, launch_k(bn_bwd_apply_kernel<T>, dim3(grid_for(total, 256 * 4, 4)), dim3(256), 5 * p->C * sizeof(float), s, dim3(1, 1, 1), *p));
+  DISPATCH_T(p->dtype, launch_k(bn_bwd_apply_kernel<T>, dim3(grid_for(total, 256 * 4, D3FK_BN_BWD_BLOCKS)), dim3(256), 5 * p->C * sizeof(float), s, dim3(1, 1, 1), *p));
   count_launch();
   return check_launch("bn_bwd_apply");
 }
@@ -875,8 +912,13 @@ int launch_chansum(const d3fk_chansum_params* p, cudaStream_t s) {
 }
 int launch_qsample(const d3fk_qsample_params* p, cudaStream_t s) {
   D3FK_CHECK_ARG(p->chw % 4 == 0, "C*H*W must be a multiple of 4");
-  long long nvec = (long long)p->B * p->chw / 4;
-  launch_k(qsample_kernel, dim3(grid_for(nvec, 256)), dim3(256), 0, s, dim3(1, 1, 1), *p);
+  D3FK_CHECK_ARG(p->B >= 1 && p->B <= 65535, "batch must be 1..65535");
+  const int vps = p->chw / 4;
+  int gx = cdiv(vps, 256 * 4);                    // ~4 vectors per thread; enough blocks per sample to fill the chip at small B
+  const int want = cdiv(148 * 8, p->B);
+  if (gx < want) gx = want < cdiv(vps, 256) ? want : cdiv(vps, 256);
+  if (gx < 1) gx = 1;
+  launch_k(qsample_kernel, dim3(gx, p->B), dim3(256), 0, s, dim3(1, 1, 1), *p);
   count_launch();
   return check_launch("q_sample");
 }

@@ -3,7 +3,7 @@
 # exported to text on the box and removed: gpurun brings back at most 64 MiB.
 cap() {  # name kind M N K mode
   local rep=gpurun_out/$1.ncu-rep
-  timeout 300 ncu --set full --clock-control none --import-source on --profile-from-start off -c 1 -f -o gpurun_out/$1 \
+  timeout 300 ncu --set full --clock-control none --import-source on --profile-from-start off -c ${NCU_COUNT:-1} -f -o gpurun_out/$1 \
     python tools/one_op.py $2 $3 $4 $5 $6 > gpurun_out/$1.log 2>&1
   tail -1 gpurun_out/$1.log
   [ -f $rep ] || return

@@ -17,6 +17,25 @@ plan = next(p for plans in mod.model._plans.values() for p in plans if p.trainin
 s = torch.cuda.current_stream().cuda_stream
 kind = _lib.OP_WGRAD if kind_name == "wgrad" else _lib.OP_CONV
 ops = list(plan.fwd_ops) + [op for seg in plan.bwd_segments for op in seg]
+if kind_name in ("bn_bwd", "bn_apply"):          # python tools/one_op.py bn_bwd <count> <C> 0 [launch index to capture]
+    want = (_lib.OP_BN_BWD, _lib.OP_BN_BWD_REDUCE) if kind_name == "bn_bwd" else (_lib.OP_BN_APPLY,)
+    for op in ops:
+        p = _lib.op_params(op)
+        if op.kind in want and (p.count, p.C) == (M, N):
+            c = _lib.Op(); ctypes.memmove(ctypes.byref(c), ctypes.byref(op), ctypes.sizeof(_lib.Op))
+            ol = _lib.OpList([c])
+            for _ in range(3):
+                ol.run(s)
+            torch.cuda.synchronize()
+            torch.cuda.profiler.start()
+            ol.run(s)
+            torch.cuda.synchronize()
+            torch.cuda.profiler.stop()
+            print("ran", kind_name, M, N)
+            break
+    else:
+        print("op not found")
+    sys.exit(0)
 for op in ops:
     if op.kind != kind and not (kind == _lib.OP_CONV and op.kind == _lib.OP_CONV_BN):
         continue
