@@ -427,9 +427,11 @@ __global__ void maxpool_fwd_kernel(d3fk_pool_params p) {
     }
     store_vec<T>(y + pix * p.ldy + c, best);
     if (p.idx) {
-      unsigned char* ip = p.idx + pix * p.C + c;
+      unsigned long long pk = 0ull;          // one 8-byte (V = 8) / 4-byte (V = 4) store instead of V byte stores
 #pragma unroll
-      for (int i = 0; i < V; ++i) ip[i] = bi[i];
+      for (int i = 0; i < V; ++i) pk |= (unsigned long long)bi[i] << (8 * i);
+      if (V == 8) *reinterpret_cast<unsigned long long*>(p.idx + pix * p.C + c) = pk;
+      else *reinterpret_cast<unsigned int*>(p.idx + pix * p.C + c) = (unsigned int)pk;
     }
   }
 }
@@ -463,10 +465,13 @@ __global__ void maxpool_bwd_kernel(d3fk_pool_params p) {
         long long op = (long long)(n * Ho + ho) * Wo + wo;
         float d[V];
         load_vec<T>(dy + op * p.lddy + c, d);
-        const unsigned char* ip = p.idx + op * p.C + c;
+        // the V tap indices of this channel vector in ONE load (V = 8: 8 bytes, V = 4: 4 bytes) instead of V byte loads
+        unsigned long long ipk;
+        if (V == 8) ipk = __ldg(reinterpret_cast<const unsigned long long*>(p.idx + op * p.C + c));
+        else ipk = (unsigned long long)__ldg(reinterpret_cast<const unsigned int*>(p.idx + op * p.C + c));
 #pragma unroll
         for (int i = 0; i < V; ++i)
-          if (ip[i] == tap) g[i] += d[i];
+          if ((int)((ipk >> (8 * i)) & 0xFFull) == tap) g[i] += d[i];
       }
     }
     store_vec<T>(dx + pix * p.lddx + c, g);
