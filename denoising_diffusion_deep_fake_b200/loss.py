@@ -28,21 +28,27 @@ def _workspace(device):
     return ws
 
 
+def _launch(prediction, target, lo, hi, need_grad):
+    """ONE launch: the scalar loss and (optionally) dL/dprediction."""
+    _lib.init(prediction.device.index)
+    pred = prediction.contiguous()
+    tgt = target.contiguous()
+    B, C, H, W = pred.shape
+    grad = torch.empty_like(pred) if need_grad else None
+    loss = torch.empty((), dtype=torch.float32, device=pred.device)
+    win = (_lib.f32 * 12)(*(_window() + [0.0]))
+    op = _lib.make_op(_lib.OP_LOSS, B=B, C=C, H=H, W=W, pred=pred.data_ptr(), target=tgt.data_ptr(),
+                      grad=None if grad is None else grad.data_ptr(), acc=_workspace(pred.device).data_ptr(),
+                      lo=float(lo), hi=float(hi), grad_scale=1.0, win=win, loss_out=loss.data_ptr())
+    _lib.run_single(op, torch.cuda.current_stream(pred.device).cuda_stream)
+    return loss, grad
+
+
 class _FusedMseSsim(torch.autograd.Function):
     @staticmethod
     def forward(ctx, prediction, target, lo, hi):
-        _lib.init(prediction.device.index)
-        pred = prediction.contiguous()
-        tgt = target.contiguous()
-        B, C, H, W = pred.shape
         need_grad = prediction.requires_grad
-        grad = torch.empty_like(pred) if need_grad else None
-        loss = torch.empty((), dtype=torch.float32, device=pred.device)
-        win = (_lib.f32 * 12)(*(_window() + [0.0]))
-        op = _lib.make_op(_lib.OP_LOSS, B=B, C=C, H=H, W=W, pred=pred.data_ptr(), target=tgt.data_ptr(),
-                          grad=None if grad is None else grad.data_ptr(), acc=_workspace(pred.device).data_ptr(),
-                          lo=float(lo), hi=float(hi), grad_scale=1.0, win=win, loss_out=loss.data_ptr())
-        _lib.run_single(op, torch.cuda.current_stream(pred.device).cuda_stream)   # ONE launch: value and gradient
+        loss, grad = _launch(prediction, target, lo, hi, need_grad)
         ctx.save_for_backward(grad) if need_grad else None
         ctx.has_grad = need_grad
         return loss
@@ -91,7 +97,17 @@ class MseStructuralSimilarityLoss(nn.Module):
         x = (x - self.input_min_value) / (self.input_max_value - self.input_min_value)
         return x.clip(0.0, 1.0)
 
+    def value_and_grad(self, prediction, target):
+        """(loss, dL/dprediction) without an autograd node: a trainer that owns the step calls
+        `prediction.backward(grad)` itself and saves the `grad * grad_output` pass autograd would add (train.DenoiserModule)."""
+        self._check(prediction, target)
+        return _launch(prediction.detach(), target, self.input_min_value, self.input_max_value, True)
+
     def forward(self, prediction, target):
+        self._check(prediction, target)
+        return _FusedMseSsim.apply(prediction, target, self.input_min_value, self.input_max_value)
+
+    def _check(self, prediction, target):
         if not (prediction.is_cuda and target.is_cuda):
             raise _lib.D3fkError("d3fk.MseStructuralSimilarityLoss runs only on a B200 (sm_100a) CUDA device; "
                                  "there is no CPU path")
@@ -101,4 +117,3 @@ class MseStructuralSimilarityLoss(nn.Module):
                              f"(the U-Net's own constraint), got {tuple(prediction.shape)} {prediction.dtype}")
         if target.requires_grad:
             raise NotImplementedError("the criterion does not back-propagate into the target (the reference never does)")
-        return _FusedMseSsim.apply(prediction, target, self.input_min_value, self.input_max_value)

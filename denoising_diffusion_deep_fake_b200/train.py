@@ -191,19 +191,21 @@ class DenoiserModule(nn.Module):
         Lightning would take).  Returns the loss tensor (no host sync)."""
         image_noisy = self.blend_random_amount_of_noise_with_each_sample(image, noise, y)
         image_prediction = self.model(image_noisy)
-        loss = self.training_criterion(image_prediction, image)
+        # value and dL/dprediction from the one fused launch; the U-Net backward is seeded directly (no autograd node for
+        # the criterion, no grad * grad_output pass)
+        loss, grad = self.training_criterion.value_and_grad(image_prediction, image)
         if not isinstance(self.optimizer, FlatAdam):
             self.optimizer.zero_grad(set_to_none=True)
         stepped = False
         if self.allreduce is not None:
             self.allreduce.armed = True
             try:
-                loss.backward()
+                image_prediction.backward(grad)
             finally:
                 self.allreduce.armed = False
             stepped = self.allreduce.finish()
         else:
-            loss.backward()
+            image_prediction.backward(grad)
         if not stepped:
             self.optimizer.step()
         self.global_step += 1
