@@ -1116,18 +1116,22 @@ __global__ void __launch_bounds__(SlabCfg<BN>::THREADS) conv_slab_kernel(const _
         for (int c = 0; c < ss.chunks; ++c)
           tma_load_2d(w_base + (t * ss.chunks + c) * ss.w_tile_bytes, &tmB, t * ss.ctot + c * cch, 0, wbar);
       const int rows = S * ss.R;
-      uint32_t it = 0;                                  // pipeline stage counter: (super-tile, chunk) pairs
+      // pipeline position over (super-tile, chunk) pairs as running counters: stage index, parity of the round, and whether
+      // the ring has wrapped (a run-time `it % stages` / `it / stages` is a ~20-instruction sequence in every role's loop)
+      int st = 0;
+      uint32_t round_par = 0;
+      bool wrapped = false;
       for (int t = blockIdx.x; t < ss.total; t += gridDim.x) {
         const int n = t / ss.tiles_per_img;
         const int rem = t - n * ss.tiles_per_img;
         const int hb = rem / ss.wtiles;
         const int h0 = hb * rows, w0 = (rem - hb * ss.wtiles) * ss.Wt;
-        for (int c = 0; c < ss.chunks; ++c, ++it) {
-          const int st = it % ss.stages;
-          if (it >= (uint32_t)ss.stages) mbar_wait(empty_bar(st), ((it / ss.stages) - 1) & 1, errflag);
+        for (int c = 0; c < ss.chunks; ++c) {
+          if (wrapped) mbar_wait(empty_bar(st), round_par ^ 1u, errflag);
           mbar_arrive_expect_tx(full_bar(st), 3u * ss.slab_tx);
           for (int sx = 0; sx < 3; ++sx)
             tma_load_4d(slab_base + st * stage_bytes + sx * ss.slab_bytes, &tmA, c * cch, w0 + sx - 1, h0 - 1, n, full_bar(st));
+          if (++st == ss.stages) { st = 0; round_par ^= 1u; wrapped = true; }
         }
       }
     }
@@ -1157,22 +1161,24 @@ __global__ void __launch_bounds__(SlabCfg<BN>::THREADS) conv_slab_kernel(const _
       const uint32_t wchunk16 = (uint32_t)ss.w_tile_bytes >> 4;
       const bool active = my_p < P;                     // S * P == NW: always true; kept for clarity
       mbar_wait(wbar, 0, errflag);
-      uint32_t it = 0, tile_it = 0;
+      uint32_t tile_it = 0;
+      int st = 0;
+      uint32_t round_par = 0;
+      const int pmask = P - 1;                          // P is 1, 2 or 4: tap % P == tap & (P - 1)
       for (int t = blockIdx.x; t < ss.total; t += gridDim.x, ++tile_it) {
         const uint32_t abuf = tile_it & 1;
         if (tile_it >= 2) mbar_wait(acc_empty_bar(abuf), ((tile_it >> 1) - 1) & 1, errflag);
         const uint32_t d_addr = tmem_d + abuf * (uint32_t)(NW * ACC) + (uint32_t)((my_s * P + my_p) * ACC);
         uint32_t first = 0u;
-        for (int c = 0; c < ss.chunks; ++c, ++it) {
-          const int st = it % ss.stages;
-          mbar_wait(full_bar(st), (it / ss.stages) & 1, errflag);
+        for (int c = 0; c < ss.chunks; ++c) {
+          mbar_wait(full_bar(st), round_par, errflag);
           tc_fence_after();
           const uint32_t sub_lo = dlo | ((slab_base + st * stage_bytes) >> 4);
           const uint32_t bc = (uint32_t)c * wchunk16;
           if (active) {
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
-              if (tap % P == my_p) {                    // P in {1, 2, 4}
+              if ((tap & pmask) == my_p) {              // P in {1, 2, 4}
 #pragma unroll
                 for (int kk = 0; kk < KSTEPS; ++kk) {
                   umma_f16_lohi_p(d_addr, sub_lo + a_off[tap] + 2u * kk, dhi, b_lo[tap] + bc + 2u * kk, dhi, idesc, first, leader);
@@ -1182,6 +1188,7 @@ __global__ void __launch_bounds__(SlabCfg<BN>::THREADS) conv_slab_kernel(const _
             }
           }
           umma_commit_p(empty_bar(st), leader);
+          if (++st == ss.stages) { st = 0; round_par ^= 1u; }
         }
         umma_commit_p(acc_full_bar(abuf), leader);
       }
