@@ -54,6 +54,7 @@ int launch_chansum(const d3fk_chansum_params*, cudaStream_t);
 int launch_upcat(const d3fk_upcat_params*, cudaStream_t);
 int launch_frames_to_tensor(const d3fk_frames_params*, cudaStream_t);
 int launch_tensor_to_frames(const d3fk_frames_params*, cudaStream_t);
+int launch_affine_qsample(const d3fk_affine_qsample_params*, cudaStream_t);
 int launch_qsample(const d3fk_qsample_params*, cudaStream_t);
 int launch_posterior(const d3fk_posterior_params*, cudaStream_t);
 int launch_inc(const d3fk_misc_params*, cudaStream_t);
@@ -119,6 +120,7 @@ static int run_one(const d3fk_op* op, cudaStream_t s) {
     case D3FK_OP_UPCAT: return launch_upcat(&op->u.upcat, s);
     case D3FK_OP_FRAMES_TO_TENSOR: return launch_frames_to_tensor(&op->u.frames, s);
     case D3FK_OP_TENSOR_TO_FRAMES: return launch_tensor_to_frames(&op->u.frames, s);
+    case D3FK_OP_AFFINE_QSAMPLE: return launch_affine_qsample(&op->u.affine_qsample, s);
     case D3FK_OP_QSAMPLE: return launch_qsample(&op->u.qsample, s);
     case D3FK_OP_POSTERIOR: return launch_posterior(&op->u.posterior, s);
     case D3FK_OP_MEMSET: {
@@ -321,6 +323,7 @@ SINGLE(d3fk_chansum, d3fk_chansum_params, launch_chansum)
 SINGLE(d3fk_upcat, d3fk_upcat_params, launch_upcat)
 SINGLE(d3fk_frames_to_tensor, d3fk_frames_params, launch_frames_to_tensor)
 SINGLE(d3fk_tensor_to_frames, d3fk_frames_params, launch_tensor_to_frames)
+SINGLE(d3fk_affine_q_sample, d3fk_affine_qsample_params, launch_affine_qsample)
 SINGLE(d3fk_q_sample, d3fk_qsample_params, launch_qsample)
 SINGLE(d3fk_posterior_step, d3fk_posterior_params, launch_posterior)
 SINGLE(d3fk_adam, d3fk_adam_params, launch_adam)

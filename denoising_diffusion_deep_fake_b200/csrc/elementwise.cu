@@ -565,6 +565,10 @@ __global__ void chansum_kernel(d3fk_chansum_params p) {
 
 // ---------------------------------------------------------------------------------------------
 // q_sample: out = sqrt(1-r_b) x + sqrt(r_b) eps   (d3f/train_denoiser/lit_module.py:128-153)
+// sqrt(1-r) x + sqrt(r) n with a FIXED rounding order (one product rounded, then one fused multiply-add): q_sample and the
+// fused affine + q_sample kernel must agree bit for bit, whatever contraction the compiler would pick in each.
+__device__ __forceinline__ float blend1(float a, float x, float s, float n) { return __fmaf_rn(a, x, __fmul_rn(s, n)); }
+
 // blockIdx.y = sample: the noise ratio r_b (one Philox draw, one log, two square roots) is formed once per block, not once
 // per 4 elements; the Philox counter of the element noise is still the global vector index, so results are unchanged.
 __global__ void __launch_bounds__(256) qsample_kernel(d3fk_qsample_params p) {
@@ -600,9 +604,77 @@ __global__ void __launch_bounds__(256) qsample_kernel(d3fk_qsample_params p) {
     float4 n;
     if (p.noise) n = __ldg(reinterpret_cast<const float4*>(p.noise) + i);
     else n = philox_normal4(p.seed, (uint64_t)i, p.offset);
-    float4 o = make_float4(a * x.x + s * n.x, a * x.y + s * n.y, a * x.z + s * n.z, a * x.w + s * n.w);
+    float4 o = make_float4(blend1(a, x.x, s, n.x), blend1(a, x.y, s, n.y), blend1(a, x.z, s, n.z), blend1(a, x.w, s, n.w));
     reinterpret_cast<float4*>(p.out)[i] = o;
     if (p.noise_out) reinterpret_cast<float4*>(p.noise_out)[i] = n;
+  }
+}
+
+// Random affine warp (bilinear, zero padding) fused with q_sample.  blockIdx.y = sample; a thread owns 4 consecutive
+// elements of the NCHW sample (W % 4 == 0: the same image row and channel), i.e. exactly the vector qsample_kernel owns,
+// so the Philox counters — and therefore the noise — are those of q_sample applied to the augmented image.
+__global__ void __launch_bounds__(256) affine_qsample_kernel(d3fk_affine_qsample_params p) {
+  pdl_enter();
+  const int hw = p.H * p.W;
+  const int vec_per_sample = p.C * hw / 4;
+  const int b = blockIdx.y;
+  __shared__ float s_coef[2];
+  __shared__ float s_m[6];
+  if (threadIdx.x < 6) s_m[threadIdx.x] = __ldg(p.minv + 6 * b + threadIdx.x);
+  if (threadIdx.x == 32) {
+    float r;
+    if (p.fixed_r >= 0.f) {
+      r = p.fixed_r;
+    } else {
+      const float cexp = __expf(-p.lam);
+      float y;
+      if (p.y) y = __ldg(p.y + b);
+      else {
+        uint4 u = philox4x32_10(make_uint4((uint32_t)b, 0u, (uint32_t)p.offset, 0x9E3779B9u),
+                                make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
+        y = (float)(u.x >> 8) * (1.0f / 16777216.0f);
+      }
+      r = (1.0f / p.lam) * logf(1.0f / (y * (1.0f - cexp) + cexp));
+    }
+    s_coef[0] = sqrtf(1.0f - r);
+    s_coef[1] = sqrtf(r);
+    if (p.r_out && blockIdx.x == 0) p.r_out[b] = r;
+  }
+  __syncthreads();
+  const float a = s_coef[0], s = s_coef[1];
+  const float m0 = s_m[0], m1 = s_m[1], m2 = s_m[2], m3 = s_m[3], m4 = s_m[4], m5 = s_m[5];
+  const long long base = (long long)b * vec_per_sample;
+  const float* xs = p.x + (long long)b * p.C * hw;
+  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < vec_per_sample; v += gridDim.x * blockDim.x) {
+    const int e = 4 * v;                  // element within the sample: (c, oy, ox .. ox+3)
+    const int c = e / hw;
+    const int pix = e - c * hw;
+    const int oy = pix / p.W, ox = pix - oy * p.W;
+    const float* plane = xs + (long long)c * hw;
+    float g[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float fx = (float)(ox + j), fy = (float)oy;
+      const float sx = fmaf(m0, fx, fmaf(m1, fy, m2));
+      const float sy = fmaf(m3, fx, fmaf(m4, fy, m5));
+      const float x0f = floorf(sx), y0f = floorf(sy);
+      const float wx1 = sx - x0f, wy1 = sy - y0f, wx0 = 1.f - wx1, wy0 = 1.f - wy1;
+      const int x0 = (int)x0f, y0 = (int)y0f;
+      const bool in_x0 = (unsigned)x0 < (unsigned)p.W, in_x1 = (unsigned)(x0 + 1) < (unsigned)p.W;
+      const bool in_y0 = (unsigned)y0 < (unsigned)p.H, in_y1 = (unsigned)(y0 + 1) < (unsigned)p.H;
+      const float v00 = (in_x0 && in_y0) ? __ldg(plane + y0 * p.W + x0) : 0.f;
+      const float v01 = (in_x1 && in_y0) ? __ldg(plane + y0 * p.W + x0 + 1) : 0.f;
+      const float v10 = (in_x0 && in_y1) ? __ldg(plane + (y0 + 1) * p.W + x0) : 0.f;
+      const float v11 = (in_x1 && in_y1) ? __ldg(plane + (y0 + 1) * p.W + x0 + 1) : 0.f;
+      g[j] = wy0 * (wx0 * v00 + wx1 * v01) + wy1 * (wx0 * v10 + wx1 * v11);
+    }
+    const long long i = base + v;
+    float4 n;
+    if (p.noise) n = __ldg(reinterpret_cast<const float4*>(p.noise) + i);
+    else n = philox_normal4(p.seed, (uint64_t)i, p.offset);
+    if (p.out_aug) reinterpret_cast<float4*>(p.out_aug)[i] = make_float4(g[0], g[1], g[2], g[3]);
+    reinterpret_cast<float4*>(p.out_noisy)[i] =
+        make_float4(blend1(a, g[0], s, n.x), blend1(a, g[1], s, n.y), blend1(a, g[2], s, n.z), blend1(a, g[3], s, n.w));
   }
 }
 
@@ -926,6 +998,20 @@ int launch_qsample(const d3fk_qsample_params* p, cudaStream_t s) {
   launch_k(qsample_kernel, dim3(gx, p->B), dim3(256), 0, s, dim3(1, 1, 1), *p);
   count_launch();
   return check_launch("q_sample");
+}
+int launch_affine_qsample(const d3fk_affine_qsample_params* p, cudaStream_t s) {
+  D3FK_CHECK_ARG(p->B >= 1 && p->B <= 65535 && p->C >= 1 && p->H >= 1, "batch must be 1..65535, C and H positive");
+  D3FK_CHECK_ARG(p->W >= 4 && p->W % 4 == 0, "W must be a multiple of 4");
+  D3FK_CHECK_ARG(p->x && p->minv && p->out_noisy, "x, minv and out_noisy are required");
+  D3FK_CHECK_ARG((long long)p->C * p->H * p->W < (1ll << 31), "one sample must have fewer than 2^31 elements");
+  const int vps = p->C * p->H * p->W / 4;
+  int gx = cdiv(vps, 256 * 2);
+  const int want = cdiv(148 * 8, p->B);
+  if (gx < want) gx = want < cdiv(vps, 256) ? want : cdiv(vps, 256);
+  if (gx < 1) gx = 1;
+  launch_k(affine_qsample_kernel, dim3(gx, p->B), dim3(256), 0, s, dim3(1, 1, 1), *p);
+  count_launch();
+  return check_launch("affine_q_sample");
 }
 int launch_posterior(const d3fk_posterior_params* p, cudaStream_t s) {
   D3FK_CHECK_ARG(p->n % 4 == 0, "n must be a multiple of 4");

@@ -127,3 +127,50 @@ def tensor_to_frames(tensor, mean, std):
     out = torch.empty((N, H, W, 3), dtype=torch.uint8, device=tensor.device)
     _frames_op(_lib.OP_TENSOR_TO_FRAMES, out, tensor, mean, std)
     return out
+
+
+def random_affine_inverse_maps(B, H, W, degrees=15.0, translate=(0.2, 0.2), scale=(0.8, 1.2), generator=None, device=None):
+    """Per-sample inverse affine maps [B,6] (output pixel -> source pixel) with the parameter distribution of the reference's
+    `K.RandomAffine(degrees=15, translate=[0.2, 0.2], scale=[0.8, 1.2], shear=0, p=1.0)`
+    (d3f/train_denoiser/lit_module.py:55-65): angle ~ U(-degrees, degrees), translation ~ U(-t*W, t*W) x U(-t*H, t*H), one
+    isotropic scale ~ U(lo, hi); rotation + scale about the image centre ((W-1)/2, (H-1)/2), then the translation.  Host
+    arithmetic on B x 4 numbers (float64, closed-form inverse); the warp itself is d3fk_affine_q_sample."""
+    u = torch.rand(B, 4, generator=generator, dtype=torch.float64)
+    th = (2 * u[:, 0] - 1) * degrees * math.pi / 180.0
+    tx = (2 * u[:, 1] - 1) * translate[0] * W
+    ty = (2 * u[:, 2] - 1) * translate[1] * H
+    sc = scale[0] + u[:, 3] * (scale[1] - scale[0])
+    cx, cy = (W - 1) / 2.0, (H - 1) / 2.0
+    # forward: p_out = s R (p_src - c) + c + t, R = [[cos, sin], [-sin, cos]]  =>  p_src = R^T (p_out - c - t) / s + c
+    ca, sa = torch.cos(th) / sc, torch.sin(th) / sc
+    m = torch.stack([ca, -sa, cx - ca * (cx + tx) + sa * (cy + ty),
+                     sa, ca, cy - sa * (cx + tx) - ca * (cy + ty)], dim=1)
+    return m.to(torch.float32).to(device) if device is not None else m.to(torch.float32)
+
+
+def affine_q_sample(batch, inverse_maps, lam, noise=None, y=None, seed=0, offset=0, fixed_r=None, return_aux=False):
+    """The reference's `image = augment(image); image_noisy = blend_noise(image)` (d3f/train_denoiser/lit_module.py:113-115) in
+    ONE kernel: per-sample affine warp (bilinear, zero padding; `inverse_maps` [B,6] or [B,2,3], output pixel -> source pixel)
+    and the noising of the warped image.  Returns (image_augmented, image_noisy) — the loss target and the network input —
+    and with return_aux also the per-sample noise ratio.  Noise is that of `q_sample(image_augmented, ...)` with the same
+    seed / offset, bit for bit."""
+    _require_cuda_f32(batch, "batch")
+    if batch.dim() != 4 or batch.shape[-1] % 4:
+        raise RuntimeError(f"expected [B,C,H,W] with W a multiple of 4, got {tuple(batch.shape)}")
+    batch = batch.contiguous()
+    B, C, H, W = batch.shape
+    m = inverse_maps.reshape(B, 6).to(device=batch.device, dtype=torch.float32).contiguous()
+    aug, noisy = torch.empty_like(batch), torch.empty_like(batch)
+    r_out = torch.empty(B, dtype=torch.float32, device=batch.device) if return_aux else None
+    if noise is not None:
+        noise = noise.contiguous()
+    if y is not None:
+        y = y.reshape(B).contiguous()
+    op = make_op(_lib.OP_AFFINE_QSAMPLE, B=B, C=C, H=H, W=W, lam=float(lam), fixed_r=-1.0 if fixed_r is None else float(fixed_r),
+                 x=batch.data_ptr(), minv=m.data_ptr(), noise=None if noise is None else noise.data_ptr(),
+                 y=None if y is None else y.data_ptr(), out_aug=aug.data_ptr(), out_noisy=noisy.data_ptr(),
+                 r_out=None if r_out is None else r_out.data_ptr(), seed=int(seed), offset=int(offset))
+    _lib.run_single(op, _stream(batch))
+    if return_aux:
+        return aug, noisy, r_out.view(B, 1, 1, 1)
+    return aug, noisy

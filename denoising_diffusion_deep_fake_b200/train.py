@@ -14,7 +14,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .functional import adam_step_, q_sample
+from .functional import adam_step_, affine_q_sample, q_sample, random_affine_inverse_maps
 from .parallel import allreduce_bucket_
 from .loss import MseStructuralSimilarityLoss
 from .unet import Unet
@@ -161,6 +161,7 @@ class DenoiserModule(nn.Module):
         self.current_epoch = 0
         self.optimizer = None
         self.allreduce = None
+        self._aug_generator = None
 
     def forward(self, image):
         return self.model(image)
@@ -186,10 +187,25 @@ class DenoiserModule(nn.Module):
         return q_sample(batch, p["noise_exponential_sampling_lambda"], noise=noise, y=y,
                         seed=p.get("seed", 0), offset=self.global_step)
 
+    def augment_and_blend(self, batch, noise=None, y=None):
+        """`image = self.shared_augmentation_sequence(image)` + the noising (lit_module.py:55-65, :113-115) as one kernel:
+        returns (augmented image = the loss target, noisy augmented image = the network input)."""
+        p = self.hparams
+        B, _, H, W = batch.shape
+        if self._aug_generator is None:
+            self._aug_generator = torch.Generator().manual_seed(int(p.get("seed", 0)) + 0x5EED)
+        maps = random_affine_inverse_maps(B, H, W, generator=self._aug_generator)
+        return affine_q_sample(batch, maps, p["noise_exponential_sampling_lambda"], noise=noise, y=y,
+                               seed=p.get("seed", 0), offset=self.global_step)
+
     def training_step(self, image, noise=None, y=None):
-        """noising -> U-Net -> MSE+SSIM loss -> backward -> Adam (lit_module.py:107-126 + the optimiser step
-        Lightning would take).  Returns the loss tensor (no host sync)."""
-        image_noisy = self.blend_random_amount_of_noise_with_each_sample(image, noise, y)
+        """[affine augmentation ->] noising -> U-Net -> MSE+SSIM loss -> backward -> Adam (lit_module.py:107-126 + the
+        optimiser step Lightning would take).  Returns the loss tensor (no host sync).  hparam `augment` (default False:
+        the benchmark feeds pre-augmented tensors) switches the reference's kornia RandomAffine on."""
+        if self.hparams.get("augment", False):
+            image, image_noisy = self.augment_and_blend(image, noise, y)
+        else:
+            image_noisy = self.blend_random_amount_of_noise_with_each_sample(image, noise, y)
         image_prediction = self.model(image_noisy)
         # value and dL/dprediction from the one fused launch; the U-Net backward is seeded directly (no autograd node for
         # the criterion, no grad * grad_output pass)

@@ -191,6 +191,21 @@ typedef struct d3fk_qsample_params {
   uint64_t seed, offset;
 } d3fk_qsample_params;
 
+/* ---- random affine augmentation fused with the noising.  Replaces
+ * `image = self.shared_augmentation_sequence(image)` (kornia RandomAffine, d3f/train_denoiser/lit_module.py:55-65, :113)
+ * followed by blend_random_amount_of_noise_with_each_sample (:115): one pass reads x and writes BOTH the augmented clean
+ * image (the loss target) and its noised version.
+ * minv: B x 6 floats, the INVERSE map of each sample, output pixel (ox, oy) -> source pixel
+ *   sx = m0*ox + m1*oy + m2,  sy = m3*ox + m4*oy + m5     (pixel centres at integer coordinates)
+ * sampled bilinearly with zero padding outside the image.  Noise / ratio exactly as d3fk_q_sample applied to the augmented
+ * image (same Philox counters), so affine_q_sample(x) == q_sample(affine(x)) bit for bit. */
+typedef struct d3fk_affine_qsample_params {
+  int32_t B, C, H, W; float lam, fixed_r;
+  const float* x; const float* minv; const float* noise; const float* y;
+  float* out_aug; float* out_noisy; float* r_out;
+  uint64_t seed, offset;
+} d3fk_affine_qsample_params;
+
 /* ---- posterior update x_{i-1} = k_xi*x_i + k_x0*x0_hat + sigma*z ------------
  * Coefficients come from coef_table[*step][0..2] when coef_table is set (CUDA-graph replay: the
  * graph is step-independent), else from the immediates. z supplied or Philox(seed, offset+*step). */
@@ -240,6 +255,7 @@ enum d3fk_op_kind {
   D3FK_OP_CONV_BN = 22,
   D3FK_OP_UPCAT = 23,
   D3FK_OP_FRAMES_TO_TENSOR = 26, D3FK_OP_TENSOR_TO_FRAMES = 27,   /* frames params */
+  D3FK_OP_AFFINE_QSAMPLE = 28,
   D3FK_OP_WGRAD_GROUP = 25,   /* wgrad_group params; forked onto the side streams like D3FK_OP_WGRAD */
   D3FK_OP_BN_BWD = 24    /* bn params: bn_bwd_reduce + bn_bwd_apply as one op (one kernel behind a grid barrier when `barrier` is set) */
 };
@@ -251,7 +267,7 @@ typedef struct d3fk_op {
     d3fk_pool_params pool; d3fk_layout_params layout; d3fk_chansum_params chansum;
     d3fk_qsample_params qsample; d3fk_posterior_params posterior; d3fk_misc_params misc;
     d3fk_adam_params adam; d3fk_loss_params loss; d3fk_convbn_params convbn; d3fk_upcat_params upcat;
-    d3fk_wgrad_group_params wgrad_group; d3fk_frames_params frames;
+    d3fk_wgrad_group_params wgrad_group; d3fk_frames_params frames; d3fk_affine_qsample_params affine_qsample;
   } u;
 } d3fk_op;
 
@@ -283,6 +299,7 @@ int d3fk_wgrad(const d3fk_wgrad_params* p, d3fk_stream stream);
 int d3fk_wgrad_group(const d3fk_wgrad_group_params* p, d3fk_stream stream);
 int d3fk_frames_to_tensor(const d3fk_frames_params* p, d3fk_stream stream);
 int d3fk_tensor_to_frames(const d3fk_frames_params* p, d3fk_stream stream);
+int d3fk_affine_q_sample(const d3fk_affine_qsample_params* p, d3fk_stream stream);
 int d3fk_conv_bn(const d3fk_convbn_params* p, d3fk_stream stream);
 int d3fk_pack_weights(const d3fk_pack_params* p, d3fk_stream stream);
 int d3fk_nchw_to_nhwc(const d3fk_layout_params* p, d3fk_stream stream);

@@ -197,3 +197,51 @@ def test_predict_fake_on_frames():
     batch = torch.from_numpy(np.stack([frame, frame[::-1].copy()])).to(DEV)
     out = mod.predict_fake(batch, "a")
     assert out.is_cuda and out.dtype == torch.uint8 and np.array_equal(out[0].cpu().numpy(), fake)
+
+
+@pytest.mark.parametrize("shape", [(8, 3, 64, 64), (3, 3, 32, 96), (2, 3, 128, 128)])
+def test_affine_q_sample(shape):
+    """d3fk_affine_q_sample (d3f/train_denoiser/lit_module.py:113-115): the warp against the oracle's bilinear /
+    zero-padding restatement on the same inverse maps, and the noising bit-identical to q_sample of the warped image."""
+    from denoising_diffusion_deep_fake_b200.functional import affine_q_sample, random_affine_inverse_maps
+    B, C, H, W = shape
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(shape, generator=g).clamp(-1, 1)
+    m = random_affine_inverse_maps(B, H, W, generator=g)
+    noise = torch.randn(shape, generator=g)
+    y = torch.rand(B, 1, 1, 1, generator=g)
+    aug_ref = oracle.warp_affine_bilinear(x, m.view(B, 2, 3))
+    r_ref = oracle.sample_noise_ratio(y, 5.0)
+    aug, noisy, r = affine_q_sample(x.to(DEV), m, 5.0, noise=noise.to(DEV), y=y.to(DEV), return_aux=True)
+    # tolerance: the source coordinate is rounded differently (fma in the kernel): 1 ulp at ~100 px = 8e-6 px times an image
+    # slope of up to 2 per pixel
+    assert (aug.cpu() - aug_ref).abs().max() < 1e-4, (aug.cpu() - aug_ref).abs().max()
+    assert rel_err(r.cpu(), r_ref) < 1e-6
+    assert rel_err(noisy.cpu(), oracle.blend_noise(aug_ref, noise, r_ref)) < 2e-5
+    # fused == two kernels, bit for bit, on both RNG paths
+    assert torch.equal(noisy, d3.q_sample(aug, 5.0, noise=noise.to(DEV), y=y.to(DEV)))
+    aug2, noisy2 = affine_q_sample(x.to(DEV), m, 5.0, seed=11, offset=4)
+    assert torch.equal(aug2, aug) and torch.equal(noisy2, d3.q_sample(aug2, 5.0, seed=11, offset=4))
+    # identity map: the image itself; a map that leaves the image: zeros
+    ident = torch.tensor([1.0, 0, 0, 0, 1, 0]).repeat(B, 1)
+    a_id, _ = affine_q_sample(x.to(DEV), ident, 5.0, seed=1)
+    assert torch.equal(a_id.cpu(), x)
+    far = torch.tensor([1.0, 0, 10.0 * W, 0, 1, 0]).repeat(B, 1)
+    a_far, n_far, r_far = affine_q_sample(x.to(DEV), far, 5.0, noise=noise.to(DEV), y=y.to(DEV), return_aux=True)
+    assert float(a_far.abs().max()) == 0.0 and rel_err(n_far.cpu(), torch.sqrt(r_ref) * noise) < 1e-6
+
+
+def test_training_step_with_augmentation():
+    """DenoiserModule(augment=True): the training step warps and noises in one kernel and regresses onto the WARPED image
+    (the reference's order: augment, noise, predict, loss against the augmented image — lit_module.py:113-119)."""
+    from denoising_diffusion_deep_fake_b200.train import DenoiserModule
+    torch.manual_seed(0)
+    mod = DenoiserModule(encoder_name="resnet34", learning_rate=1e-3, noise_exponential_sampling_lambda=5,
+                         cosine_scheduler_max_epoch=10, precision="bf16", seed=5, augment=True).to(DEV).train()
+    mod.configure_optimizers(fused=True)
+    g = torch.Generator(device=DEV).manual_seed(1)
+    x = torch.randn(8, 3, 64, 64, generator=g, device=DEV).clamp(-1, 1)
+    losses = [float(mod.training_step(x)) for _ in range(12)]
+    assert all(l == l and l < 10 for l in losses) and min(losses[-4:]) < losses[0]
+    aug, noisy = mod.augment_and_blend(x)
+    assert aug.shape == x.shape and not torch.equal(aug, x) and torch.isfinite(noisy).all()

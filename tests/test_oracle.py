@@ -172,3 +172,32 @@ def test_frame_conversion_known_answers():
     levels = np.arange(256, dtype=np.uint8).reshape(1, 16, 16, 1).repeat(3, axis=3)
     back = oracle.tensor_cv2_to_denormalised(oracle.cv2_to_tensor_normalised(levels, [0.5] * 3, [0.5] * 3), [0.5] * 3, [0.5] * 3)
     assert int((back != levels).sum()) == int((back.astype(int) - levels.astype(int) == -1).sum())   # only ever one level low
+
+
+def test_affine_augmentation_restatement():
+    """oracle.augment (kornia RandomAffine restated, d3f/train_denoiser/lit_module.py:55-65): parameter ranges, the
+    centre-anchored map, and the bilinear / zero-padding warp pinned to torch's own grid_sample on the same inverse maps."""
+    B, H, W = 6, 32, 48
+    g = torch.Generator().manual_seed(3)
+    angle, tx, ty, sc = oracle.sample_affine_params(B, H, W, generator=g)
+    assert (angle.abs() <= 15).all() and (tx.abs() <= 0.2 * W).all() and (ty.abs() <= 0.2 * H).all()
+    assert (sc >= 0.8).all() and (sc <= 1.2).all()
+    M, Minv = oracle.affine_matrices(angle, tx, ty, sc, H, W)
+    centre = torch.tensor([(W - 1) / 2, (H - 1) / 2, 1.0], dtype=torch.float64)
+    moved = M @ centre                                       # the centre moves by exactly the translation
+    assert torch.allclose(moved[:, 0] - centre[0], tx) and torch.allclose(moved[:, 1] - centre[1], ty)
+    assert torch.allclose(torch.linalg.det(M[:, :2, :2]), sc ** 2)
+    x = torch.randn(B, 3, H, W)
+    out = oracle.warp_affine_bilinear(x, Minv[:, :2])
+    oy, ox = torch.meshgrid(torch.arange(H, dtype=torch.float64), torch.arange(W, dtype=torch.float64), indexing="ij")
+    sx = Minv[:, 0, 0, None, None] * ox + Minv[:, 0, 1, None, None] * oy + Minv[:, 0, 2, None, None]
+    sy = Minv[:, 1, 0, None, None] * ox + Minv[:, 1, 1, None, None] * oy + Minv[:, 1, 2, None, None]
+    grid = torch.stack([2 * sx / (W - 1) - 1, 2 * sy / (H - 1) - 1], dim=-1).float()
+    ref = torch.nn.functional.grid_sample(x, grid, mode="bilinear", padding_mode="zeros", align_corners=True)
+    assert (out - ref).abs().max() < 1e-4
+    ident = torch.eye(3, dtype=torch.float64).repeat(B, 1, 1)
+    assert torch.equal(oracle.warp_affine_bilinear(x, ident[:, :2]), x)
+    # the product's closed-form inverse maps (host arithmetic, no device needed) are the oracle's matrix inverses
+    from denoising_diffusion_deep_fake_b200.functional import random_affine_inverse_maps
+    m = random_affine_inverse_maps(B, H, W, generator=torch.Generator().manual_seed(3))
+    assert (m.view(B, 2, 3).double() - Minv[:, :2]).abs().max() < 1e-5

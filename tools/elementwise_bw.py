@@ -6,7 +6,7 @@ import torch
 import denoising_diffusion_deep_fake_b200 as d3
 from denoising_diffusion_deep_fake_b200 import _lib
 from denoising_diffusion_deep_fake_b200.functional import (q_sample, posterior_step_, adam_step_, frames_to_tensor,
-                                                            tensor_to_frames)
+                                                            tensor_to_frames, affine_q_sample, random_affine_inverse_maps)
 dev = torch.device("cuda:0")
 _lib.init(0)
 peak = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"]
@@ -35,6 +35,8 @@ y = torch.rand(B, 1, 1, 1, device=dev)
 n = x.numel()
 timed("q_sample, Philox noise in-kernel (read x, write out)", lambda: q_sample(x, 5.0, seed=1), 8 * n)
 timed("q_sample, noise given (read x, noise, write out)", lambda: q_sample(x, 5.0, noise=noise, y=y), 12 * n)
+maps = random_affine_inverse_maps(B, H, H).to(dev)
+timed("affine_q_sample, Philox (read x, write augmented + noisy)", lambda: affine_q_sample(x, maps, 5.0, seed=1), 12 * n)
 h = torch.randn_like(x)
 timed("posterior_step eta=0 (read x, x0_hat, write x)", lambda: posterior_step_(x, h, 0.5, 0.4, eta=0.0), 12 * n)
 timed("posterior_step eta=1, Philox z", lambda: posterior_step_(x, h, 0.5, 0.4, eta=1.0, seed=3), 12 * n)
