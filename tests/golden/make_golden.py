@@ -42,5 +42,31 @@ def main():
     print("wrote", path, {k: tuple(v.shape) for k, v in out.items()})
 
 
+def main_rows_f3_f4():
+    """Second fixture: frame conversion bytes and the affine warp.  Kept in its own file so that adding it
+    did not rewrite the first one."""
+    rng = np.random.default_rng(7)
+    frames = rng.integers(0, 256, size=(2, 8, 12, 3), dtype=np.uint8)
+    mean, std = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
+    tens = oracle.cv2_to_tensor_normalised(frames, mean, std)
+    g = torch.Generator().manual_seed(11)
+    net_out = tens + 0.3 * torch.randn(tens.shape, generator=g)          # stands in for a network output
+    back = oracle.tensor_cv2_to_denormalised(net_out, mean, std)
+    x = torch.randn(3, 3, 16, 24, generator=g).clamp(-1, 1)
+    angle, tx, ty, sc = oracle.sample_affine_params(3, 16, 24, generator=g)
+    _, minv = oracle.affine_matrices(angle, tx, ty, sc, 16, 24)
+    warped = oracle.warp_affine_bilinear(x, minv[:, :2])
+    out = dict(frames=frames, mean=np.array(mean, np.float32), std=np.array(std, np.float32), tensor=tens.numpy(),
+               net_out=net_out.numpy(), frames_back=back, aff_x=x.numpy(), aff_angle=angle.numpy(), aff_tx=tx.numpy(),
+               aff_ty=ty.numpy(), aff_scale=sc.numpy(), aff_minv=minv[:, :2].numpy(), aff_warped=warped.numpy())
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "d3f_golden_f3_f4.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, {k: tuple(np.shape(v)) for k, v in out.items()})
+
+
 if __name__ == "__main__":
-    main()
+    if "--rows-f3-f4" in sys.argv:
+        main_rows_f3_f4()
+    else:
+        main()
+        main_rows_f3_f4()

@@ -245,3 +245,19 @@ def test_training_step_with_augmentation():
     assert all(l == l and l < 10 for l in losses) and min(losses[-4:]) < losses[0]
     aug, noisy = mod.augment_and_blend(x)
     assert aug.shape == x.shape and not torch.equal(aug, x) and torch.isfinite(noisy).all()
+
+
+def test_rows_f3_f4_against_committed_golden_vectors():
+    """The CUDA kernels against tests/golden/d3f_golden_f3_f4.npz: frame bytes exactly, warp within coordinate rounding."""
+    import os
+    import numpy as np
+    from denoising_diffusion_deep_fake_b200.functional import affine_q_sample, frames_to_tensor, tensor_to_frames
+    gold = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "d3f_golden_f3_f4.npz")))
+    mean, std = gold["mean"].tolist(), gold["std"].tolist()
+    t = frames_to_tensor(torch.from_numpy(gold["frames"]).to(DEV), mean, std)
+    assert torch.equal(t.cpu(), torch.from_numpy(gold["tensor"]))
+    back = tensor_to_frames(torch.from_numpy(gold["net_out"]).to(DEV), mean, std)
+    assert np.array_equal(back.cpu().numpy(), gold["frames_back"])
+    x = torch.from_numpy(gold["aff_x"]).to(DEV)
+    aug, _ = affine_q_sample(x, torch.from_numpy(gold["aff_minv"]).float(), 5.0, seed=1)
+    assert (aug.cpu() - torch.from_numpy(gold["aff_warped"])).abs().max() < 1e-4

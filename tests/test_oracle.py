@@ -201,3 +201,18 @@ def test_affine_augmentation_restatement():
     from denoising_diffusion_deep_fake_b200.functional import random_affine_inverse_maps
     m = random_affine_inverse_maps(B, H, W, generator=torch.Generator().manual_seed(3))
     assert (m.view(B, 2, 3).double() - Minv[:, :2]).abs().max() < 1e-5
+
+
+GOLD_F34 = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "d3f_golden_f3_f4.npz")
+
+
+def test_golden_vectors_rows_f3_f4():
+    """The oracle reproduces the committed frame-conversion / affine-warp fixture (tests/golden/make_golden.py --rows-f3-f4)."""
+    gold = dict(np.load(GOLD_F34))
+    mean, std = gold["mean"].tolist(), gold["std"].tolist()
+    assert torch.equal(oracle.cv2_to_tensor_normalised(gold["frames"], mean, std), torch.from_numpy(gold["tensor"]))
+    assert np.array_equal(oracle.tensor_cv2_to_denormalised(torch.from_numpy(gold["net_out"]), mean, std), gold["frames_back"])
+    _, minv = oracle.affine_matrices(*(torch.from_numpy(gold[k]) for k in ("aff_angle", "aff_tx", "aff_ty", "aff_scale")), 16, 24)
+    assert np.allclose(minv[:, :2].numpy(), gold["aff_minv"], atol=1e-12)
+    warped = oracle.warp_affine_bilinear(torch.from_numpy(gold["aff_x"]), torch.from_numpy(gold["aff_minv"]))
+    assert torch.allclose(warped, torch.from_numpy(gold["aff_warped"]), atol=1e-6)
