@@ -16,15 +16,18 @@ constexpr int LW = 11;            // window
 constexpr int LH = LW - 1;        // halo
 constexpr int LI = LT + 2 * LH;   // 52: staged input edge
 constexpr int LM = LT + LH;       // 42: windows (map pixels) touching the tile
-constexpr int LOSS_SMEM = (2 * LI * LI + 5 * LI * LM + 3 * LM * LM) * 4;
+// the a / b / c maps reuse the staged-input region (dead after the horizontal pass; 3*42*42 <= 2*52*52): 65 KB per block,
+// three blocks per SM instead of two
+constexpr int LOSS_SMEM = (2 * LI * LI + 5 * LI * LM) * 4;
+static_assert(3 * LM * LM <= 2 * LI * LI, "the derivative maps must fit the staged-input region");
 
-__global__ void __launch_bounds__(256) mse_ssim_loss_kernel(d3fk_loss_params p) {
+__global__ void __launch_bounds__(256, 3) mse_ssim_loss_kernel(d3fk_loss_params p) {
   pdl_enter();
   extern __shared__ float sm[];
   float* xs = sm;                       // [LI][LI] normalised clipped prediction (0 outside the image)
   float* ys = xs + LI * LI;             // [LI][LI] target
   float* hs = ys + LI * LI;             // [5][LI][LM] horizontal pass; later [3][LM][LT] transposed horizontal pass
-  float* ms = hs + 5 * LI * LM;         // [3][LM][LM] a, b, c maps
+  float* ms = xs;                       // [3][LM][LM] a, b, c maps — over xs / ys, which are dead once step 2 is done
   __shared__ float g[LW];
   __shared__ double red[2][8];
   const int tid = threadIdx.x;
@@ -124,12 +127,13 @@ __global__ void __launch_bounds__(256) mse_ssim_loss_kernel(d3fk_loss_params p) 
         const float mxx = mx * mx, myy = my * my, mxy = mx * my;
         const float sxx = exx - mxx, syy = eyy - myy, sxy = exy - mxy;
         const float A1 = 2.f * mxy + C1, A2 = 2.f * sxy + C2, B1 = mxx + myy + C1, B2 = sxx + syy + C2;
-        const float S1 = A1 / B1, S2 = A2 / B2;
+        const float rB1 = 1.f / B1, rB2 = 1.f / B2;          // two divisions per window instead of six
+        const float S1 = A1 * rB1, S2 = A2 * rB2;
         // windows whose origin lies inside the tile are owned (counted) by this block
         if (jr >= LH && jc >= LH) ss_sum += (double)(S1 * S2);
-        a = S2 * 2.f * (my - S1 * mx) / B1 + S1 * 2.f * (S2 * mx - my) / B2;
-        bb = -S1 * S2 / B2;
-        cc = 2.f * S1 / B2;
+        a = S2 * 2.f * (my - S1 * mx) * rB1 + S1 * 2.f * (S2 * mx - my) * rB2;
+        bb = -S1 * S2 * rB2;
+        cc = 2.f * S1 * rB2;
       }
       const int idx = jr * LM + jc;
       ms[idx] = a; ms[LM * LM + idx] = bb; ms[2 * LM * LM + idx] = cc;
@@ -192,8 +196,8 @@ __global__ void __launch_bounds__(256) mse_ssim_loss_kernel(d3fk_loss_params p) 
       const float d = pr - tg;
       mse_sum += (double)d * d;
       if (p.grad) {
-        const float x = xs[(ir + LH) * LI + ic + LH], y = ys[(ir + LH) * LI + ic + LH];
         const float xn = (pr - p.lo) * inv_range;
+        const float x = fminf(fmaxf(xn, 0.f), 1.f), y = fminf(fmaxf((tg - p.lo) * inv_range, 0.f), 1.f);   // as staged in step 1
         const float inside = (xn > 0.f && xn < 1.f) ? 1.f : 0.f;   // clip() passes no gradient outside [lo, hi]
         const float dss = A[o] + 2.f * x * Bm[o] + y * Cm[o];
         p.grad[oidx] = k_mse * d - k_ssim * inside * dss;
@@ -212,12 +216,12 @@ __global__ void __launch_bounds__(256) mse_ssim_loss_kernel(d3fk_loss_params p) 
     double a = 0;
     for (int w = 0; w < 8; ++w) a += red[tid][w];
     atomicAdd(&p.acc[tid], a);
+    if (p.loss_out) __threadfence();      // only the two publishing threads fence (a block-wide fence was 3 % of the kernel)
   }
   if (p.loss_out) {
     // The last block to finish forms the scalar loss and resets the accumulators (acc[2] doubles as the ticket), so the
     // criterion is ONE launch: no memset before, no scalar arithmetic kernels after.
     __shared__ unsigned s_ticket;
-    __threadfence();
     __syncthreads();
     unsigned* ticket = reinterpret_cast<unsigned*>(p.acc + 2);
     if (tid == 0) s_ticket = atomicAdd(ticket, 1u);
