@@ -300,7 +300,7 @@ def run_d3fk(args):
         sb, ss, n_steps = args.sample_batch, args.sample_size, args.sample_steps
         mod.model.eval()
         smp = Sampler(mod.model, sb, ss, ss, n_steps, r_start=1.0, eta=1.0, seed=7 + rank, use_graph=True,
-                      chains=args.sample_chains)
+                      chains=args.sample_chains, steps_per_graph=args.sample_steps_per_graph)
         smp.run()
         barrier()
         e0.record()
@@ -314,7 +314,7 @@ def run_d3fk(args):
             sms = t.item()
         sample = {"metric": "sample_img_steps_per_s", "value": world * sb * n_steps / (sms / 1e3), "unit": "img-steps/s",
                   "config": {"workload": f"{n_steps}-step DDPM sampling @{ss}x{ss}, batch {sb}/GPU, CUDA-graph replay",
-                             "chains": smp.chains},
+                             "chains": smp.chains, "steps_per_graph": smp.steps_per_graph},
                   "ms_per_step": sms / n_steps, "kernels_per_step": smp.kernels_per_step}
         mod.model.train()
 
@@ -355,6 +355,7 @@ def main():
     ap.add_argument("--sample-size", type=int, default=128)
     ap.add_argument("--sample-steps", type=int, default=50)
     ap.add_argument("--sample-chains", type=int, default=None, help="sub-batches sampled as parallel graph branches")
+    ap.add_argument("--sample-steps-per-graph", type=int, default=int(os.environ.get("D3FK_STEPS_PER_GRAPH", "1")))
     ap.add_argument("--no-sample", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--main-priority", type=int, default=int(os.environ.get("D3FK_MAIN_PRIORITY", "0")))
