@@ -1386,6 +1386,7 @@ static int try_launch_conv_slab(const Gather& g, const d3fk_conv_params* p, cuda
   return rc ? rc : 1;
 }
 
+int try_launch_head_conv(const d3fk_conv_params* p, cudaStream_t s);
 int launch_conv_tc(const d3fk_conv_params* p, cudaStream_t s) {
   Gather g;
   int rc = make_gather(g, p->src0, p->src1, p->c0, p->c1, p->ld0, p->ld1, p->up0, p->B, p->Hi, p->Wi, p->Ho, p->Wo, p->kh,
@@ -1395,6 +1396,8 @@ int launch_conv_tc(const d3fk_conv_params* p, cudaStream_t s) {
   D3FK_CHECK_ARG(p->out_nchw || (p->ldo % 8 == 0), "ldo must be a multiple of 8");
   D3FK_CHECK_ARG(!p->scale || p->shift, "scale requires shift");
   D3FK_CHECK_ARG(((uintptr_t)p->w & 15) == 0, "weights must be 16-byte aligned");
+  const int head = try_launch_head_conv(p, s);          // 16 -> 3 channels, fp32 NCHW out: CUDA cores (head_conv.cu)
+  if (head) return head < 0 ? head : D3FK_OK;
   const int slab = try_launch_conv_slab(g, p, s);
   if (slab) return slab < 0 ? slab : D3FK_OK;
   TileSched box;

@@ -16,7 +16,7 @@ DTYPES = [_lib.F32, _lib.BF16]
 
 
 def _conv_case(dtype, B, Hi, Wi, c0, c1, up0, Cout, k, stride, pad, mode, relu=0, res=False, affine=False,
-               stats=False, nchw=False, seed=0, splitk=False, bw=None):
+               stats=False, nchw=False, seed=0, splitk=False, bw=None, bias=False):
     g = torch.Generator().manual_seed(seed)
     ctot = c0 + c1
     if mode == 0:
@@ -43,6 +43,8 @@ def _conv_case(dtype, B, Hi, Wi, c0, c1, up0, Cout, k, stride, pad, mode, relu=0
         sc["ldr"] = Cout
     if affine:
         t["scale"] = torch.rand(Cout, generator=g) + 0.5
+        t["shift"] = torch.randn(Cout, generator=g)
+    if bias:               # shift without scale: the segmentation head's bias
         t["shift"] = torch.randn(Cout, generator=g)
     if stats:
         t["stats"] = torch.zeros(2, Cout, dtype=torch.float64)
@@ -407,3 +409,21 @@ def test_wgrad_group(dtype, count, B, H, C):
         _lib.run_single(_lib.make_op(_lib.OP_WGRAD, src0=xs[i].data_ptr(), dy=dys[i].data_ptr(), dw=one.data_ptr(), **base), stream)
         torch.cuda.synchronize()
         assert rel_err(dws[i].cpu(), one.cpu()) < (1e-6 if dtype == _lib.F32 else 1e-5)
+
+
+HEAD_CASES = [
+    # the segmentation head (16 -> 3, bias, fp32 NCHW out): CUDA-core kernel head_conv.cu for every tile width (W % 128 / 64 /
+    # 32), one output channel, a single image, and shapes that must fall back to the tensor-core path (H % 32 != 0)
+    dict(B=2, Hi=64, Wi=64, Cout=3), dict(B=1, Hi=128, Wi=128, Cout=3), dict(B=3, Hi=32, Wi=96, Cout=3),
+    dict(B=2, Hi=32, Wi=32, Cout=1), dict(B=1, Hi=64, Wi=256, Cout=2), dict(B=2, Hi=16, Wi=64, Cout=3),
+]
+
+
+@pytest.mark.parametrize("case", HEAD_CASES)
+@pytest.mark.parametrize("bias", [False, True])
+def test_head_conv(case, bias):
+    r = _conv_case(_lib.BF16, c0=16, c1=0, up0=0, k=3, stride=1, pad=1, mode=0, nchw=True, bias=bias, seed=3, **case)
+    g, c = r["out_nchw"]
+    assert rel_err(g, c) < 2e-3, rel_err(g, c)        # bf16 inputs / weights, fp32 accumulation on both sides
+    # edges (zero padding) specifically
+    assert rel_err(g[..., 0, :], c[..., 0, :]) < 2e-3 and rel_err(g[..., :, -1], c[..., :, -1]) < 2e-3
