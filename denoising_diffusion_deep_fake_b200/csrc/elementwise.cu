@@ -99,18 +99,20 @@ __global__ void __launch_bounds__(256, BN_BWD_OCC(T)) bn_apply_kernel(d3fk_bn_pa
   const long long stride = (long long)gridDim.x * blockDim.x;   // multiple of cvs: the channel vector is loop invariant
   const int c = (int)(e0 % cvs) * V;
   uint4 vr[U], rr[U];                // held packed (4 registers per vector) until used: 3 blocks per SM instead of 2
-  auto load_batch = [&](long long e) {
+  // the pixel of element e0 + k * stride is pix0 + k * pstep (stride is a multiple of cvs): no division per vector
+  const long long pix0 = e0 / cvs, pstep = stride / cvs;
+  auto load_batch = [&](long long e, long long pixb) {
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long eu = e + u * stride;
       if (eu < total) {
-        const long long pix = eu / cvs;
+        const long long pix = pixb + u * pstep;
         vr[u] = load_raw<T>(x + pix * p.ldx + c);
         if (res) rr[u] = load_raw<T>(res + pix * p.ldr + c);
       }
     }
   };
-  load_batch(e0);                    // first loads are in flight while the block derives scale / shift
+  load_batch(e0, pix0);              // first loads are in flight while the block derives scale / shift
   extern __shared__ float s_aff[];   // [2][C] scale, shift — derived once per block
   for (int ch = threadIdx.x; ch < p.C; ch += blockDim.x) {
     float sc, sh;
@@ -144,12 +146,13 @@ __global__ void __launch_bounds__(256, BN_BWD_OCC(T)) bn_apply_kernel(d3fk_bn_pa
   float scf[V], shf[V];
 #pragma unroll
   for (int i = 0; i < V; ++i) { scf[i] = s_aff[c + i]; shf[i] = s_aff[p.C + c + i]; }
+  long long pixb = pix0;
   for (long long e = e0; e < total;) {
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long eu = e + u * stride;
       if (eu < total) {
-        const long long pix = eu / cvs;
+        const long long pix = pixb + u * pstep;
         float v[V], r[V];
         unpack_vec<T>(vr[u], v);
         if (res) unpack_vec<T>(rr[u], r);
@@ -164,7 +167,8 @@ __global__ void __launch_bounds__(256, BN_BWD_OCC(T)) bn_apply_kernel(d3fk_bn_pa
       }
     }
     e += U * stride;
-    if (e < total) load_batch(e);
+    pixb += U * pstep;
+    if (e < total) load_batch(e, pixb);
   }
 }
 
@@ -324,13 +328,15 @@ __device__ __forceinline__ void bn_bwd_apply_body(const d3fk_bn_params& p, float
   // Walk the tensor BACKWARDS: the reduction pass that ran just before streamed x, dy and act front to back, so their
   // tails are what the 126 MB L2 still holds.
   const long long last_pix = p.count - 1;
-  for (long long e = e0; e < total; e += U * stride) {
+  const long long pstep = stride / cvs;          // stride is a multiple of cvs: element e0 + k * stride is pixel e0 / cvs + k * pstep
+  long long pixb = last_pix - e0 / cvs;
+  for (long long e = e0; e < total; e += U * stride, pixb -= U * pstep) {
     uint4 xr[U], gr[U], ar[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long eu = e + u * stride;
       if (eu < total) {
-        const long long pix = last_pix - eu / cvs;
+        const long long pix = pixb - u * pstep;
         xr[u] = load_raw<T>(x + pix * p.ldx + c);
         gr[u] = load_raw<T>(dy + pix * p.lddy + c);
         if (p.relu) ar[u] = load_raw<T>(act + pix * p.ldact + c);
@@ -340,7 +346,7 @@ __device__ __forceinline__ void bn_bwd_apply_body(const d3fk_bn_params& p, float
     for (int u = 0; u < U; ++u) {
       const long long eu = e + u * stride;
       if (eu < total) {
-        const long long pix = last_pix - eu / cvs;
+        const long long pix = pixb - u * pstep;
         float xv[V], gv[V], av[V], o[V];
         unpack_vec<T>(xr[u], xv);
         unpack_vec<T>(gr[u], gv);
@@ -388,6 +394,28 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_kernel(d3fk_bn_params p, int* e
   bn_bwd_apply_body<T>(p, reinterpret_cast<float*>(smem_bwd));
 }
 
+// element index -> (pixel, channel vector, w, h, n) of a [n][h][w][cvs] walk.  32-bit arithmetic whenever the index fits
+// (always, at the sizes this path sees): five 64-bit divisions per 16-byte vector made the pool kernels issue-bound.
+__device__ __forceinline__ void split_index(long long e, int cvs, int W, int H, long long& pix, int& cv, int& w, int& h, int& n) {
+  if (e < 0x7fffffffLL) {
+    const unsigned ue = (unsigned)e, up = ue / (unsigned)cvs;
+    cv = (int)(ue - up * (unsigned)cvs);
+    const unsigned t = up / (unsigned)W;
+    w = (int)(up - t * (unsigned)W);
+    const unsigned un = t / (unsigned)H;
+    h = (int)(t - un * (unsigned)H);
+    n = (int)un;
+    pix = (long long)up;
+  } else {
+    pix = e / cvs;
+    cv = (int)(e - pix * cvs);
+    w = (int)(pix % W);
+    const long long t = pix / W;
+    h = (int)(t % H);
+    n = (int)(t / H);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // MaxPool2d(kernel 3, stride 2, pad 1): first-max tie-break in window scan order (ATen semantics)
 template <typename T>
@@ -399,12 +427,10 @@ __global__ void maxpool_fwd_kernel(d3fk_pool_params p) {
   const T* x = (const T*)p.x;
   T* y = (T*)p.y;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    long long pix = e / cvs;
-    int c = (int)(e - pix * cvs) * V;
-    int wo = (int)(pix % Wo);
-    long long t = pix / Wo;
-    int ho = (int)(t % Ho);
-    int n = (int)(t / Ho);
+    long long pix;
+    int c, wo, ho, n;
+    split_index(e, cvs, Wo, Ho, pix, c, wo, ho, n);
+    c *= V;
     float best[V];
     unsigned char bi[V];
 #pragma unroll
@@ -445,12 +471,10 @@ __global__ void maxpool_bwd_kernel(d3fk_pool_params p) {
   const T* dy = (const T*)p.dy;
   T* dx = (T*)p.dx;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    long long pix = e / cvs;
-    int c = (int)(e - pix * cvs) * V;
-    int w = (int)(pix % p.W);
-    long long t = pix / p.W;
-    int h = (int)(t % p.H);
-    int n = (int)(t / p.H);
+    long long pix;
+    int c, w, h, n;
+    split_index(e, cvs, p.W, p.H, pix, c, w, h, n);
+    c *= V;
     float g[V];
 #pragma unroll
     for (int i = 0; i < V; ++i) g[i] = 0.f;
@@ -488,12 +512,10 @@ __global__ void sumpool2_kernel(d3fk_pool_params p) {
   const T* dy = (const T*)p.dy;
   T* dx = (T*)p.dx;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    long long pix = e / cvs;
-    int c = (int)(e - pix * cvs) * V;
-    int w = (int)(pix % p.W);
-    long long t = pix / p.W;
-    int h = (int)(t % p.H);
-    int n = (int)(t / p.H);
+    long long pix;
+    int c, w, h, n;
+    split_index(e, cvs, p.W, p.H, pix, c, w, h, n);
+    c *= V;
     float g[V];
 #pragma unroll
     for (int i = 0; i < V; ++i) g[i] = 0.f;
@@ -891,6 +913,7 @@ int launch_bn_apply(const d3fk_bn_params* p, cudaStream_t s) {
   D3FK_CHECK_ARG(p->C % 8 == 0, "C must be a multiple of 8");
   int V = p->dtype == D3FK_F32 ? 4 : 8;
   long long total = p->count * (p->C / V);
+  D3FK_CHECK_ARG(256 % (p->C / V) == 0, "C / vector width must divide 256 (the kernel's channel vector is loop invariant)");
   DISPATCH_T(p->dtype, launch_k(bn_apply_kernel<T>, dim3(grid_for(total, 256 * 4, D3FK_BN_BWD_BLOCKS)), dim3(256), 2 * p->C * sizeof(float), s, dim3(1, 1, 1), *p));
   count_launch();
   return check_launch("bn_apply");
@@ -922,6 +945,7 @@ int launch_bn_bwd_apply(const d3fk_bn_params* p, cudaStream_t s) {
   D3FK_CHECK_ARG(p->C % 8 == 0, "C must be a multiple of 8");
   int V = p->dtype == D3FK_F32 ? 4 : 8;
   long long total = p->count * (p->C / V);
+  D3FK_CHECK_ARG(256 % (p->C / V) == 0, "C / vector width must divide 256 (the kernel's channel vector is loop invariant)");
   DISPATCH_T(p->dtype, launch_k(bn_bwd_apply_kernel<T>, dim3(grid_for(total, 256 * 4, D3FK_BN_BWD_BLOCKS)), dim3(256), 5 * p->C * sizeof(float), s, dim3(1, 1, 1), *p));
   count_launch();
   return check_launch("bn_bwd_apply");
