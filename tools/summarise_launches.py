@@ -27,7 +27,7 @@ def short(n):
 starts = [i for i, L in enumerate(ls) if 'qsample_kernel' in L["name"]]
 steps = max(1, len(starts) - 1)
 span = ls[starts[0]:starts[-1]] if len(starts) > 1 else ls
-is_conv = lambda n: any(k in n for k in ("conv_tc_kernel", "conv_slab_kernel", "wgrad_tc_kernel", "wgrad_slab_kernel"))
+is_conv = lambda n: any(k in n for k in ("conv_tc_kernel", "conv_slab_kernel", "wgrad_tc_kernel", "wgrad_slab_kernel", "head_conv_kernel"))
 conv = [L for L in span if is_conv(L["name"])]
 info = {"source": path, "steps": steps, "launches_per_step": len(span) / steps,
         "kernel_us_per_step": sum(L["t"] for L in span) / steps,
