@@ -89,6 +89,9 @@ def denoise(config, input_list, synthetic, size, precision, checkpoint_dir):
     hp = read_yaml_file_into_dict(config)
     hp["input_image_list_path"] = input_list
     hp.setdefault("precision", precision)
+    # the reference's training step always runs its kornia RandomAffine on the batch (lit_module.py:55-65, :113); here it is
+    # fused with the noising (d3fk_affine_q_sample).  `augment: false` in the YAML turns it off.
+    hp.setdefault("augment", True)
     dev = torch.device("cuda", torch.cuda.current_device())
     module = DenoiserModule(**hp).to(dev).train()
     print_hparams(module.hparams)
