@@ -164,9 +164,11 @@ int d3fk_init(int device) {
     if (e != cudaSuccess) return set_error(D3FK_ERR_CUDA, "cudaMalloc: %s", cudaGetErrorString(e));
     cudaMemset(g_dev_error_flag, 0, dbg_bytes);
   }
-  if (const char* v = getenv("D3FK_PDL")) g_use_pdl = atoi(v);
+  if (const char* v = getenv("D3FK_PDL")) g_use_pdl = atoi(v);     // launch attribute only: same kernels, same results
+#ifdef D3FK_DEBUG
   if (const char* v = getenv("D3FK_FUSE_BN_BWD")) g_fuse_bn_bwd = atoi(v);
   if (const char* v = getenv("D3FK_FUSE_BN_BWD_MAX")) g_fuse_bn_bwd_max = atoll(v);
+#endif
   int rc = tc_init();
   if (rc) return rc;
   rc = loss_init();
@@ -204,13 +206,17 @@ static cudaEvent_t g_fork_events[64];
 static int g_n_fork_events = 0;
 static unsigned g_fork_cursor = 0;
 static bool g_side_pending = false;
+#ifdef D3FK_DEBUG
 static int g_skip_wgrad = 0;
+#endif
 static int g_fork_wgrad = 1;   // D3FK_FORK_WGRAD=0: everything in stream order
 
 static int ensure_side_stream() {
   if (g_side_stream) return D3FK_OK;
-  if (const char* v = getenv("D3FK_FORK_WGRAD")) g_fork_wgrad = atoi(v);
-  if (const char* v = getenv("D3FK_SKIP_WGRAD")) g_skip_wgrad = atoi(v);
+  if (const char* v = getenv("D3FK_FORK_WGRAD")) g_fork_wgrad = atoi(v);   // stream placement only
+#ifdef D3FK_DEBUG
+  if (const char* v = getenv("D3FK_SKIP_WGRAD")) g_skip_wgrad = atoi(v);   // timing experiment: DROPS work — debug builds only
+#endif
   // (a higher-priority main stream was measured: no gain — both chains are latency-bound, not slot-bound)
   int prio_lo = 0, prio_hi = 0;
   cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
@@ -235,7 +241,9 @@ static int run_list(const d3fk_op* ops, int n_ops, cudaStream_t s, bool join) {
   int forks = 0;
   for (int i = 0; i < n_ops; ++i) {
     const bool is_wgrad = ops[i].kind == D3FK_OP_WGRAD || ops[i].kind == D3FK_OP_WGRAD_GROUP;
+#ifdef D3FK_DEBUG
     if (is_wgrad && g_skip_wgrad) continue;   // timing experiment only (D3FK_SKIP_WGRAD=1)
+#endif
     if (is_wgrad && g_fork_wgrad && n_ops > 1) {
       cudaEvent_t ev = g_fork_events[g_fork_cursor++ % g_n_fork_events];
       cudaStream_t side = g_side_streams[g_side_cursor++ % g_n_side];   // round robin: no false wgrad -> wgrad ordering

@@ -68,11 +68,11 @@ __device__ __forceinline__ void grid_barrier_arrive_wait(unsigned* counter, unsi
     unsigned v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
     if (v >= expected) break;
-    if (clock64() - t0 > 4000000000ll) {   // ~2 s: the grid was not co-resident
+    if (clock64() - t0 > 4000000000ll) {   // ~2 s: the grid was not co-resident — fatal (sticky CUDA error), never continue
       atomicExch(errflag, 2);
       printf("[d3fk] grid barrier timeout: block %d of %d saw %u arrivals (expected %u), counter %p\n", (int)blockIdx.x, (int)gridDim.x, v,
              expected, (void*)counter);
-      break;
+      __trap();
     }
     __nanosleep(64);
   }

@@ -1,0 +1,409 @@
+// conv_slab.cu — the slab convolution (3x3 / stride 1, Cin <= 128, W >= 16): see the comment above conv_slab_kernel.
+#include "tc_common.cuh"
+
+namespace d3fk {
+
+// ------------------------------------------------------------------------------------------
+// Slab convolution: 3x3 / stride 1 / pad 1, one source, Cin in {16, 32, 64}, W in {16, 32, 64} (forward and dgrad).
+// The implicit-GEMM kernels above re-read every activation pixel once per tap (9x) from L2.  Here a persistent CTA owns
+// super-tiles of S*R full image rows (S sub-tiles of R*W = 128 pixels).  For each super-tile ONE TMA box per horizontal
+// tap offset (3 boxes: columns shifted by -1/0/+1, S*R+2 rows, hardware zero fill for the halo) lands in shared memory;
+// all 9 taps of all S sub-tiles are then UMMA operands that differ only by a row offset into those slabs, and the 9 weight
+// tiles stay resident in shared memory for the whole kernel.  L2 -> SM traffic per pixel drops from 9x to 3*(S*R+2)/(S*R)
+// and no thread computes an address: warp 5 issues 3 TMA loads per super-tile, warp 4 issues the MMAs, warps 0-3 only run
+// the epilogue (double-buffered TMEM accumulators), so load, MMA and epilogue of consecutive super-tiles overlap.
+struct SlabSched {
+  int W, H, R, S;         // image extent; rows per 128-pixel sub-tile; sub-tiles per super-tile
+  int Wt, wtiles;         // tile width min(W, 128) and tiles across the image width
+  int row_bytes;          // Cin * 2 = bytes of one pixel row of the K-major operand = TMA / UMMA swizzle span (32/64/128)
+  int slab_bytes;         // (S*R + 2) * W * row_bytes rounded up to 1 KB
+  int slab_tx;            // bytes one slab load delivers
+  int stages;             // slab pipeline depth
+  int w_tile_bytes;       // BN * row_bytes: one tap's resident weight tile
+  int total, tiles_per_img;
+  int sgn;                // +1 forward taps, -1 transposed (dgrad)
+  int ksteps;             // channels per chunk / 16
+  int chunks, ctot;       // 64-channel chunks per tap when Cin > 64 (each chunk is one pipeline stage); total Cin
+  uint32_t layout;        // UMMA smem-descriptor layout type: 2 = SWIZZLE_128B, 4 = 64B, 6 = 32B
+  int M;                  // B*H*W
+};
+
+__device__ __forceinline__ uint64_t make_smem_desc_sw(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;                              // leading byte offset (unused for swizzled K-major): 16 B
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;   // stride between 8-row groups
+  d |= (uint64_t)1 << 46;                              // descriptor version (Blackwell)
+  d |= (uint64_t)layout << 61;
+  return d;
+}
+
+// Warps: 0-3 epilogue, 4 TMA producer, 5..5+NW-1 MMA issuers.  A single thread sustains only one of these small MMAs
+// per ~90 cycles (descriptor moves into uniform registers + the issue itself are a dependent chain), so the 9*KSTEPS*S
+// MMAs of a super-tile are spread over NW warps: warp w owns sub-tile w % S and every P-th tap (P = NW / S) in a private
+// accumulator; the epilogue adds the P partial accumulators of a sub-tile.
+template <int BN> struct SlabCfg {
+  static constexpr int NW = BN >= 128 ? 2 : 4;
+  static constexpr int THREADS = (5 + NW) * 32;
+  static constexpr int ACC = BN < 32 ? 32 : BN;
+  static constexpr int TMEM_COLS = 2 * NW * ACC;       // double buffered
+};
+template <int BN, int KSTEPS>
+__global__ void __launch_bounds__(SlabCfg<BN>::THREADS) conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                                                               EpiTC e, SlabSched ss, FastDiv dWo, FastDiv dHo, int* errflag) {
+  constexpr int CW = BN >= 32 ? 32 : 16;
+  constexpr int ACC = SlabCfg<BN>::ACC;
+  constexpr int NW = SlabCfg<BN>::NW;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t w_base = base;                                         // [9 taps][chunks][BN rows][row_bytes]
+  const uint32_t w_bytes = (uint32_t)((9 * ss.chunks * ss.w_tile_bytes + 1023) & ~1023);
+  const uint32_t slab_base = base + w_bytes;                            // [stages][3][slab_bytes]
+  const uint32_t stage_bytes = 3u * ss.slab_bytes;
+  const uint32_t bar_base = slab_base + ss.stages * stage_bytes;        // full[4], empty[4], acc_full[2], acc_empty[2], wbar
+  uint8_t* gen_bar = smem_raw + (bar_base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_ptr_slot = reinterpret_cast<volatile uint32_t*>(gen_bar + 8 * 13);
+  float* s_stat = reinterpret_cast<float*>(gen_bar + 128);              // [4 warps][2][BN]
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (4 + s); };
+  auto acc_full_bar = [&](int b) { return bar_base + 8u * (8 + b); };
+  auto acc_empty_bar = [&](int b) { return bar_base + 8u * (10 + b); };
+  const uint32_t wbar = bar_base + 8u * 12;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool do_stats = e.stats != nullptr;
+  const int S = ss.S;
+  const int P = NW / S;                                 // partial accumulators (tap subsets) per sub-tile
+  constexpr uint32_t tmem_cols = (uint32_t)SlabCfg<BN>::TMEM_COLS;
+
+  if (tid == 0) {
+    for (int s = 0; s < 4; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), NW);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(acc_full_bar(b), NW);
+      mbar_init(acc_empty_bar(b), 128);
+    }
+    mbar_init(wbar, 1);
+    fence_barrier_init();
+  }
+  if (tid < 128) {
+    for (int i = tid; i < 8 * BN; i += 128) s_stat[i] = 0.f;
+  }
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    const int cchp = ss.row_bytes >> 1;   // weights are not produced by the previous kernel: warm L2 during the PDL prologue
+    for (int t = 0; t < 9; ++t)
+      for (int c = 0; c < ss.chunks; ++c) tma_prefetch_l2_2d(&tmB, t * ss.ctot + c * cchp, 0);
+  }
+  if (warp == 5) tmem_alloc(smem_u32((const void*)tmem_ptr_slot), tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_ptr_slot;
+  pdl_enter();
+
+  if (warp == 4) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      // resident weights: 9 * chunks boxes {chunk channels, BN} of the packed [Cout][9*Cin] matrix (rows >= Cout zero filled)
+      mbar_arrive_expect_tx(wbar, 9u * ss.chunks * ss.w_tile_bytes);
+      const int cch = ss.row_bytes >> 1;
+      for (int t = 0; t < 9; ++t)
+        for (int c = 0; c < ss.chunks; ++c)
+          tma_load_2d(w_base + (t * ss.chunks + c) * ss.w_tile_bytes, &tmB, t * ss.ctot + c * cch, 0, wbar);
+      const int rows = S * ss.R;
+      // pipeline position over (super-tile, chunk) pairs as running counters: stage index, parity of the round, and whether
+      // the ring has wrapped (a run-time `it % stages` / `it / stages` is a ~20-instruction sequence in every role's loop)
+      int st = 0;
+      uint32_t round_par = 0;
+      bool wrapped = false;
+      for (int t = blockIdx.x; t < ss.total; t += gridDim.x) {
+        const int n = t / ss.tiles_per_img;
+        const int rem = t - n * ss.tiles_per_img;
+        const int hb = rem / ss.wtiles;
+        const int h0 = hb * rows, w0 = (rem - hb * ss.wtiles) * ss.Wt;
+        for (int c = 0; c < ss.chunks; ++c) {
+          if (wrapped) mbar_wait(empty_bar(st), round_par ^ 1u, errflag);
+          mbar_arrive_expect_tx(full_bar(st), 3u * ss.slab_tx);
+          for (int sx = 0; sx < 3; ++sx)
+            tma_load_4d(slab_base + st * stage_bytes + sx * ss.slab_bytes, &tmA, c * cch, w0 + sx - 1, h0 - 1, n, full_bar(st));
+          if (++st == ss.stages) { st = 0; round_par ^= 1u; wrapped = true; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 5) {
+    // ===================== MMA issuers =====================
+    // The loop is kept to two adds per MMA: every descriptor is (constant high word, low word = constant | address >> 4)
+    // and this warp's tap offsets live in registers.  Warp-uniform loop, leader-predicated issue.
+    {
+      const int w = warp - 5;
+      const int my_s = w % S, my_p = w / S;            // sub-tile and tap subset of this warp
+      const uint32_t leader = lane == 0 ? 1u : 0u;
+      constexpr uint32_t idesc = make_idesc(TC_BM, BN, 0, 0);
+      const uint32_t sbo = 8u * ss.row_bytes;
+      const uint64_t dtempl = make_smem_desc_sw(0, sbo, ss.layout);
+      const uint32_t dhi = (uint32_t)(dtempl >> 32), dlo = (uint32_t)dtempl;
+      const uint32_t img_row16 = (uint32_t)(ss.Wt * ss.row_bytes) >> 4;  // one image row of the slab, in 16-byte units
+      uint32_t a_off[9], b_lo[9];
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const int kh = tap / 3, kw = tap - kh * 3;
+        const int sy = ss.sgn > 0 ? kh : 2 - kh;
+        const int sx = ss.sgn > 0 ? kw : 2 - kw;
+        a_off[tap] = ((uint32_t)(sx * ss.slab_bytes) >> 4) + (uint32_t)(sy + my_s * ss.R) * img_row16;
+        b_lo[tap] = dlo | ((w_base + (uint32_t)(tap * ss.chunks * ss.w_tile_bytes)) >> 4);
+      }
+      const uint32_t wchunk16 = (uint32_t)ss.w_tile_bytes >> 4;
+      const bool active = my_p < P;                     // S * P == NW: always true; kept for clarity
+      mbar_wait(wbar, 0, errflag);
+      uint32_t tile_it = 0;
+      int st = 0;
+      uint32_t round_par = 0;
+      const int pmask = P - 1;                          // P is 1, 2 or 4: tap % P == tap & (P - 1)
+      for (int t = blockIdx.x; t < ss.total; t += gridDim.x, ++tile_it) {
+        const uint32_t abuf = tile_it & 1;
+        if (tile_it >= 2) mbar_wait(acc_empty_bar(abuf), ((tile_it >> 1) - 1) & 1, errflag);
+        const uint32_t d_addr = tmem_d + abuf * (uint32_t)(NW * ACC) + (uint32_t)((my_s * P + my_p) * ACC);
+        uint32_t first = 0u;
+        for (int c = 0; c < ss.chunks; ++c) {
+          mbar_wait(full_bar(st), round_par, errflag);
+          tc_fence_after();
+          const uint32_t sub_lo = dlo | ((slab_base + st * stage_bytes) >> 4);
+          const uint32_t bc = (uint32_t)c * wchunk16;
+          if (active) {
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+              if ((tap & pmask) == my_p) {              // P in {1, 2, 4}
+#pragma unroll
+                for (int kk = 0; kk < KSTEPS; ++kk) {
+                  umma_f16_lohi_p(d_addr, sub_lo + a_off[tap] + 2u * kk, dhi, b_lo[tap] + bc + 2u * kk, dhi, idesc, first, leader);
+                  first = 1u;
+                }
+              }
+            }
+          }
+          umma_commit_p(empty_bar(st), leader);
+          if (++st == ss.stages) { st = 0; round_par ^= 1u; }
+        }
+        umma_commit_p(acc_full_bar(abuf), leader);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue warps =====================
+    // Narrow layers (BN <= 32) keep their batch statistics in registers: a thread owns row (warp*32+lane) of every
+    // sub-tile, so it accumulates its own per-column sums over the whole kernel and the 128 rows are folded ONCE at
+    // the end (instead of a shuffle transpose-reduce per tile).
+    constexpr bool REG_STATS = BN <= 32;
+    float rs[REG_STATS ? BN : 1], rq[REG_STATS ? BN : 1];
+#pragma unroll
+    for (int i = 0; i < (REG_STATS ? BN : 1); ++i) { rs[i] = 0.f; rq[i] = 0.f; }
+    uint32_t it = 0;
+    const int row = warp * 32 + lane;
+    for (int t = blockIdx.x; t < ss.total; t += gridDim.x, ++it) {
+      const uint32_t abuf = it & 1;
+      const int n = t / ss.tiles_per_img;
+      const int rem = t - n * ss.tiles_per_img;
+      const int hb = rem / ss.wtiles;
+      const int h0 = hb * S * ss.R, w0 = (rem - hb * ss.wtiles) * ss.Wt;
+      mbar_wait(acc_full_bar(abuf), (it >> 1) & 1, errflag);
+      tc_fence_after();
+      for (int s = 0; s < S; ++s) {
+        const long long m = ((long long)n * ss.H + h0 + s * ss.R) * ss.W + w0 + row;   // 128 consecutive pixels
+        const bool row_ok = m < ss.M;
+        int on = 0, oh = 0, ow = 0;
+        if (e.out_nchw && row_ok) {
+          const uint32_t q = fdiv((uint32_t)m, dWo);
+          ow = (int)m - (int)q * e.Wo;
+          on = (int)fdiv(q, dHo);
+          oh = (int)q - on * e.Ho;
+        }
+#pragma unroll
+        for (int cc = 0; cc < BN; cc += CW) {
+          uint32_t raw[CW];
+          const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + abuf * (uint32_t)(NW * ACC) + (uint32_t)(s * P * ACC + cc);
+          if (CW == 32) tmem_ld32(taddr, raw); else tmem_ld16(taddr, raw);
+          tmem_ld_wait();
+          float f[CW];
+#pragma unroll
+          for (int i = 0; i < CW; ++i) f[i] = __uint_as_float(raw[i]);
+          for (int pp = 1; pp < P; ++pp) {              // add the other tap subsets' partial accumulators
+            if (CW == 32) tmem_ld32(taddr + (uint32_t)(pp * ACC), raw); else tmem_ld16(taddr + (uint32_t)(pp * ACC), raw);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < CW; ++i) f[i] += __uint_as_float(raw[i]);
+          }
+          epilogue_chunk<CW>(f, e, m, row_ok, cc, on, oh, ow, do_stats && !REG_STATS, s_stat + warp * 2 * BN + cc,
+                             s_stat + warp * 2 * BN + BN + cc, lane);
+          if (REG_STATS && do_stats) {
+            if (e.bw_x) {
+              float sq[CW];
+              bw_stat_terms<CW>(f, sq, e, m, row_ok, cc);
+#pragma unroll
+              for (int i = 0; i < CW; ++i) { rs[cc + i] += f[i]; rq[cc + i] += sq[i]; }
+            } else {
+#pragma unroll
+              for (int i = 0; i < CW; ++i) { rs[cc + i] += f[i]; rq[cc + i] = fmaf(f[i], f[i], rq[cc + i]); }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(acc_empty_bar(abuf));
+    }
+    if (do_stats) {
+      if (REG_STATS) {
+#pragma unroll
+        for (int cc = 0; cc < BN; cc += CW) {
+          float a[CW], b[CW];
+#pragma unroll
+          for (int i = 0; i < CW; ++i) { a[i] = rs[cc + i]; b[i] = rq[cc + i]; }
+          float cs, cq;
+          if (CW == 32) { cs = warp_colsum32(a, lane); cq = warp_colsum32(b, lane); }
+          else { cs = warp_colsum16(a, lane); cq = warp_colsum16(b, lane); }
+          if (lane < CW) {
+            s_stat[warp * 2 * BN + cc + lane] = cs;
+            s_stat[warp * 2 * BN + BN + cc + lane] = cq;
+          }
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (tid < BN && tid < e.Cout) {
+        const float a = (s_stat[tid] + s_stat[2 * BN + tid]) + (s_stat[4 * BN + tid] + s_stat[6 * BN + tid]);
+        const float b = (s_stat[BN + tid] + s_stat[3 * BN + tid]) + (s_stat[5 * BN + tid] + s_stat[7 * BN + tid]);
+        atomicAdd(&e.stats[tid], (double)a);
+        atomicAdd(&e.stats[e.Cout + tid], e.bw_x ? bw_second_sum((double)a, (double)b, e, tid) : (double)b);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tmem_d, tmem_cols);
+}
+
+static int g_use_slab = 1;   // D3FK_SLAB=0: never take the slab path
+
+// Slab-path eligibility and geometry.  Returns false when the generic kernels must be used.
+static bool slab_plan(const Gather& g, const d3fk_conv_params* p, int BN, SlabSched& ss, int& smem) {
+  if (!g_use_slab) return false;
+  if (p->kh != 3 || p->kw != 3 || p->stride != 1 || p->pad != 1 || p->c1 != 0 || p->up0 != 0) return false;
+  if (p->Ho != p->Hi || p->Wo != p->Wi) return false;
+  const int C = g.ctot, W = p->Wi, H = p->Hi;
+  if (C != 16 && C != 32 && C != 64 && C != 128) return false;   // 128 = two 64-channel chunks (one pipeline stage each)
+  if (W != 16 && W != 32 && W != 64 && (W % 128)) return false;
+  if (p->Cout > BN || (!p->out_nchw && p->Cout != BN)) return false;
+  if (((uintptr_t)p->src0 & 15) || (g.ld0 % 8)) return false;
+  const int Wt = W < TC_BM ? W : TC_BM;
+  const int R = TC_BM / Wt;
+  if (H % R) return false;
+  ss.W = W; ss.H = H; ss.R = R; ss.Wt = Wt; ss.wtiles = W / Wt;
+  const int cch = C > 64 ? 64 : C;
+  ss.chunks = C / cch;
+  ss.ctot = C;
+  ss.row_bytes = cch * 2;
+  ss.layout = cch == 64 ? 2u : cch == 32 ? 4u : 6u;
+  ss.ksteps = cch / 16;
+  ss.w_tile_bytes = BN * ss.row_bytes;
+  ss.sgn = p->mode ? -1 : 1;
+  ss.M = g.M;
+  const int w_bytes = (9 * ss.chunks * ss.w_tile_bytes + 1023) & ~1023;
+  // largest super-tile whose double-buffered accumulators fit TMEM and whose 2-stage slabs fit shared memory
+  const int NW = BN >= 128 ? 2 : 4;                    // MMA warps (SlabCfg<BN>::NW): S must divide it
+  for (int S = NW; S >= 1; S >>= 1) {
+    if (H % (S * R)) continue;
+    const int slab = ((S * R + 2) * Wt * ss.row_bytes + 1023) & ~1023;
+    for (int stages = 3; stages >= 2; --stages) {
+      const int need = 1024 + w_bytes + stages * 3 * slab + 128 + 8 * BN * 4;
+      if (need > SLAB_MAX_SMEM) continue;
+      ss.S = S;
+      ss.slab_bytes = slab;
+      ss.slab_tx = (S * R + 2) * Wt * ss.row_bytes;
+      ss.stages = stages;
+      ss.tiles_per_img = (H / (S * R)) * ss.wtiles;
+      ss.total = p->B * ss.tiles_per_img;
+      smem = need;
+      return true;
+    }
+  }
+  return false;
+}
+
+template <int BN, int KSTEPS>
+static int launch_conv_slab_bn(const Gather& g, const d3fk_conv_params* p, cudaStream_t s, const SlabSched& ss, int smem) {
+  EpiTC e{(bf16*)p->out, p->out_nchw, p->scale, p->shift, (const bf16*)p->res, p->stats, p->ldo, p->ldr, p->relu, p->Cout, p->Ho, p->Wo,
+           (const bf16*)p->bw_x, (const bf16*)p->bw_act, p->bw_mean, p->bw_invstd, p->bw_ldx, p->bw_ldact, p->bw_relu};
+  alignas(64) CUtensorMap tmA, tmB;
+  const int C = g.ctot;
+  {
+    uint64_t dims[2] = {(uint64_t)g.K, (uint64_t)p->Cout};
+    uint64_t strides[1] = {(uint64_t)g.K * 2};
+    uint32_t bx[2] = {(uint32_t)(ss.row_bytes >> 1), (uint32_t)BN};
+    int rc = get_tensor_map(&tmB, p->w, 2, dims, strides, bx, ss.row_bytes);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[4] = {(uint64_t)C, (uint64_t)g.Wi, (uint64_t)g.Hi, (uint64_t)g.B};
+    uint64_t strides[3] = {(uint64_t)g.ld0 * 2, (uint64_t)g.Wi * g.ld0 * 2, (uint64_t)g.Hi * g.Wi * g.ld0 * 2};
+    uint32_t bx[4] = {(uint32_t)(ss.row_bytes >> 1), (uint32_t)ss.Wt, (uint32_t)(ss.S * ss.R + 2), 1u};
+    int rc = get_tensor_map(&tmA, p->src0, 4, dims, strides, bx, ss.row_bytes);
+    if (rc) return rc;
+  }
+  int occ = (227 * 1024) / (smem + 1024);
+  const int tmem_cols = SlabCfg<BN>::TMEM_COLS;
+  if (occ * tmem_cols > 512) occ = 512 / tmem_cols;
+  if (occ < 1) occ = 1;
+  int grid = ss.total < g_num_sms * occ ? ss.total : g_num_sms * occ;
+  if (g_verbose) fprintf(stderr, "[d3fk] slab<%d> mode=%d M=%d C=%d Cout=%d W=%d S=%d stages=%d smem=%d grid=%d total=%d\n", BN, g.mode, g.M, C, p->Cout, ss.W, ss.S, ss.stages, smem, grid, ss.total);
+  launch_k(conv_slab_kernel<BN, KSTEPS>, dim3(grid), dim3(SlabCfg<BN>::THREADS), (size_t)smem, s, dim3(1, 1, 1), tmA, tmB, e, ss,
+           make_fastdiv((uint32_t)g.Wo), make_fastdiv((uint32_t)g.Ho), g_dev_error_flag);
+  count_launch();
+  return check_launch("conv_slab");
+}
+
+// returns 1 when the slab path took the op, 0 when it is not eligible, < 0 on error
+int try_launch_conv_slab(const Gather& g, const d3fk_conv_params* p, cudaStream_t s) {
+  const int C = p->Cout;
+  const int BN = C <= 16 ? 16 : C <= 32 ? 32 : C <= 64 ? 64 : C <= 128 ? 128 : 0;
+  if (!BN) return 0;
+  if (p->out_nchw && BN != 16) return 0;
+  SlabSched ss;
+  memset(&ss, 0, sizeof(ss));
+  int smem = 0;
+  if (!slab_plan(g, p, BN, ss, smem)) return 0;
+  int rc;
+#define SLAB_CASE(bn, ks) if (BN == bn && ss.ksteps == ks) rc = launch_conv_slab_bn<bn, ks>(g, p, s, ss, smem); else
+  SLAB_CASE(16, 1) SLAB_CASE(16, 2) SLAB_CASE(16, 4) SLAB_CASE(32, 1) SLAB_CASE(32, 2) SLAB_CASE(32, 4)
+  SLAB_CASE(64, 1) SLAB_CASE(64, 2) SLAB_CASE(64, 4) SLAB_CASE(128, 1) SLAB_CASE(128, 2) SLAB_CASE(128, 4)
+  rc = set_error(D3FK_ERR_UNSUPPORTED, "slab: BN=%d ksteps=%d", BN, ss.ksteps);
+#undef SLAB_CASE
+  return rc ? rc : 1;
+}
+
+
+int slab_init() {
+  cudaError_t e = cudaSuccess;
+#ifdef D3FK_DEBUG
+  if (const char* v = getenv("D3FK_SLAB")) g_use_slab = atoi(v);
+#endif
+  D3FK_SET_SMEM((conv_slab_kernel<16, 1>), SLAB_MAX_SMEM)
+  D3FK_SET_SMEM((conv_slab_kernel<16, 2>), SLAB_MAX_SMEM)
+  D3FK_SET_SMEM((conv_slab_kernel<16, 4>), SLAB_MAX_SMEM)
+  D3FK_SET_SMEM((conv_slab_kernel<32, 1>), SLAB_MAX_SMEM)
+  D3FK_SET_SMEM((conv_slab_kernel<32, 2>), SLAB_MAX_SMEM)
+  D3FK_SET_SMEM((conv_slab_kernel<32, 4>), SLAB_MAX_SMEM)
+  D3FK_SET_SMEM((conv_slab_kernel<64, 1>), SLAB_MAX_SMEM)
+  D3FK_SET_SMEM((conv_slab_kernel<64, 2>), SLAB_MAX_SMEM)
+  D3FK_SET_SMEM((conv_slab_kernel<64, 4>), SLAB_MAX_SMEM)
+  D3FK_SET_SMEM((conv_slab_kernel<128, 1>), SLAB_MAX_SMEM)
+  D3FK_SET_SMEM((conv_slab_kernel<128, 2>), SLAB_MAX_SMEM)
+  D3FK_SET_SMEM((conv_slab_kernel<128, 4>), SLAB_MAX_SMEM)
+  if (e != cudaSuccess) return set_error(D3FK_ERR_CUDA, "cudaFuncSetAttribute (slab): %s", cudaGetErrorString(e));
+  return D3FK_OK;
+}
+
+}  // namespace d3fk

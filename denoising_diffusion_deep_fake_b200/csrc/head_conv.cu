@@ -117,9 +117,11 @@ static int launch_head_tw(const d3fk_conv_params* p, cudaStream_t s) {
 
 // 1 = launched, 0 = not this kernel's shape (the caller falls through to the tensor-core paths), < 0 = error
 int try_launch_head_conv(const d3fk_conv_params* p, cudaStream_t s) {
+#ifdef D3FK_DEBUG
   static int enabled = -1;
   if (enabled < 0) { const char* v = getenv("D3FK_HEAD_CONV"); enabled = v ? atoi(v) : 1; }
   if (!enabled) return 0;
+#endif
   if (p->dtype != D3FK_BF16 || p->mode != 0 || p->kh != 3 || p->kw != 3 || p->stride != 1 || p->pad != 1) return 0;
   if (p->c0 != HC_C || p->c1 != 0 || p->up0 != 0 || p->src1 || p->Cout < 1 || p->Cout > 3) return 0;
   if (!p->out_nchw || p->out || p->res || p->stats || p->relu || p->scale || p->bw_x) return 0;

@@ -1,0 +1,397 @@
+// tc_common.cuh — what the tcgen05 translation units share (conv_tc.cu, conv_slab.cu, wgrad_tc.cu): PTX wrappers
+// (mbarrier, cp.async, tcgen05 alloc / mma / commit / ld, cluster + DSMEM), UMMA descriptors, the fused epilogue and the
+// launch-geometry globals.  Split out of conv_tc.cu so that the three kernel families compile in parallel.
+#pragma once
+#include <stdlib.h>
+#include <string.h>
+#include "common.cuh"
+#include "tma.cuh"
+
+namespace d3fk {
+
+typedef __nv_bfloat16 bf16;
+
+// -DD3FK_TIMELINE (tools/build_timeline.sh; never shipped): CTA 0 of every conv_tc launch stamps %globaltimer at its
+// phase boundaries into the debug buffer behind the error flag — where do the ~10 us of a tiny tensor-core kernel go?
+#ifdef D3FK_TIMELINE
+#define TL_SLOTS 16
+#define TL_MAX 512
+__device__ __forceinline__ unsigned long long tl_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define TL_DECL unsigned long long* tl_buf = reinterpret_cast<unsigned long long*>(errflag + 16); __shared__ unsigned tl_idx;
+#define TL_BEGIN if (blockIdx.x == 0 && threadIdx.x == 0) { tl_idx = atomicAdd(reinterpret_cast<unsigned*>(errflag + 4), 1u) % TL_MAX; tl_buf[tl_idx * TL_SLOTS + 0] = tl_now(); }
+#define TL_STAMP(slot) if (blockIdx.x == 0) { tl_buf[tl_idx * TL_SLOTS + (slot)] = tl_now(); }
+#else
+#define TL_DECL
+#define TL_BEGIN
+#define TL_STAMP(slot)
+#endif
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// arrive-on triggered when all prior cp.async of this thread have landed (pending count +1 now, -1 then)
+__device__ __forceinline__ void cp_async_mbar_arrive(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+// NOTE on proxies: the cp.async (LDGSTS) gather writes shared memory and tcgen05.mma reads it through the async proxy.
+// There is deliberately no fence.proxy.async between the full-barrier wait and the MMA: completion of the copies is
+// tracked by the mbarrier itself (cp.async.mbarrier.arrive -> ARRIVES.LDGSTSBAR), exactly the protocol of CUTLASS's
+// sm100 cp.async main loop (cutlass/gemm/collective/sm100_mma_cpasync_warpspecialized.hpp:499-566: producer_commit with
+// cpasync_barrier_arrive, consumer_wait, then cute::gemm -> tcgen05.mma, no proxy fence in between).  The fence lowers to
+// MEMBAR.ALL.CTA, which drains every in-flight LDGSTS of the CTA and serialises the whole pipeline.  Every byte of a
+// stage is written by cp.async (padding uses the zero-fill form), never by st.shared; tests/test_gpu_ops.py::
+// test_cp_async_path_is_race_free re-runs ragged shapes 1000 times and demands bit-identical results.
+//
+// Bounded wait: a barrier that does not complete within ~2 s is a protocol bug or a lost TMA transaction.  The kernel
+// sets the device error flag and TRAPS: the launch fails with a sticky CUDA error that the next libd3fk call (and the
+// next CUDA call of the host framework) reports — garbage is never produced at full speed.
+static __device__ __noinline__ void mbar_timeout(int* errflag, uint32_t bar, uint32_t parity) {
+  atomicExch(errflag, 1);
+  printf("[d3fk] mbarrier watchdog: block %d thread %d waited > 2 s on barrier 0x%x parity %u\n", (int)blockIdx.x,
+         (int)threadIdx.x, bar, parity);
+  __trap();
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* errflag) {
+  if (mbar_try_wait(bar, parity)) return;
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (uint32_t it = 1;; ++it) {
+    if (mbar_try_wait(bar, parity)) return;
+    if ((it & 1023u) == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      if (t - t0 > 2000000000ull) mbar_timeout(errflag, bar, parity);
+    }
+  }
+}
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint32_t bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+}
+// L1-allocating variant: the 3x3 taps of a tile re-read the same input lines, so the activation gather can hit L1
+__device__ __forceinline__ void cp_async_16_ca(uint32_t dst, const void* src, uint32_t bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// same, descriptors given as (lo, hi) words: the issue loop only adds to the 14-bit address field of the low word
+__device__ __forceinline__ void umma_f16_lohi(uint32_t d_tmem, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(d_tmem), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Warp-uniform issue: the whole MMA warp runs the loop and only the leader lane's instruction takes effect (inside an
+// `if (lane == 0)` region ptxas wraps every tcgen05.mma in an ELECT / R2UR serialisation loop).
+__device__ __forceinline__ void umma_f16_lohi_p(uint32_t d_tmem, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t idesc,
+                                                uint32_t accumulate, uint32_t leader) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "setp.ne.b32 q, %7, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(d_tmem), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate), "r"(leader)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_p(uint32_t bar, uint32_t leader) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar), "r"(leader)
+      : "memory");
+}
+// mbarrier arrive once all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---- thread-block cluster / distributed shared memory helpers (split-K reduction across the CTAs of a cluster)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// all threads of all CTAs of the cluster; release/acquire orders the DSMEM traffic around it
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_f4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout), SWIZZLE_128B, version 1.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+  return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): bf16 x bf16 -> f32, M x N, majors selectable.
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// transpose-reduce: on return lane l holds the sum over the 32 lanes of v[l]
+__device__ __forceinline__ float warp_colsum32(float* v, int lane) {
+#pragma unroll
+  for (int ofs = 16, n = 32; ofs >= 1; ofs >>= 1, n >>= 1) {
+    const bool up = (lane & ofs) != 0;
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) {
+      float send = up ? v[i] : v[i + n / 2];
+      float keep = up ? v[i + n / 2] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, ofs);
+    }
+  }
+  return v[0];
+}
+// 16 columns: lanes l and l+16 both end with the sum of column (l & 15)
+__device__ __forceinline__ float warp_colsum16(float* v, int lane) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], 16);
+#pragma unroll
+  for (int ofs = 8, n = 16; ofs >= 1; ofs >>= 1, n >>= 1) {
+    const bool up = (lane & ofs) != 0;
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) {
+      float send = up ? v[i] : v[i + n / 2];
+      float keep = up ? v[i + n / 2] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, ofs);
+    }
+  }
+  return v[0];
+}
+
+struct EpiTC {
+  bf16* out; float* out_nchw; const float* scale; const float* shift; const bf16* res; double* stats;
+  int ldo, ldr, relu, Cout, Ho, Wo;
+  // BN-backward reduction fused into a dgrad epilogue (bw_x set): the stored output v is the gradient wrt the activation of
+  // the previous layer; the statistics become sum(g') and sum(g' * xhat) with g' = v masked by that layer's ReLU
+  // (bw_act > 0) and xhat = (bw_x - mean) * invstd — exactly what bn_bwd_reduce would compute in a second pass.
+  const bf16* bw_x; const bf16* bw_act; const float* bw_mean; const float* bw_invstd;
+  int bw_ldx, bw_ldact, bw_relu;
+};
+
+// in place: f -> g' ; sq -> g' * x (rows outside the tensor contribute zero).  The per-channel mean / invstd are applied
+// once per CTA when the partial sums are flushed: sum(g' * xhat) = invstd * (sum(g' * x) - mean * sum(g')).
+template <int CW>
+__device__ __forceinline__ void bw_stat_terms(float (&f)[CW], float (&sq)[CW], const EpiTC& e, long long m, bool row_ok, int cbase) {
+  if (!row_ok) {
+#pragma unroll
+    for (int i = 0; i < CW; ++i) { f[i] = 0.f; sq[i] = 0.f; }
+    return;
+  }
+#pragma unroll
+  for (int q8 = 0; q8 < CW / 8; ++q8) {
+    const uint4 xr = __ldg(reinterpret_cast<const uint4*>(e.bw_x + m * e.bw_ldx + cbase + q8 * 8));
+    const bf16* xb = reinterpret_cast<const bf16*>(&xr);
+    uint4 ar = make_uint4(0u, 0u, 0u, 0u);
+    if (e.bw_relu) ar = __ldg(reinterpret_cast<const uint4*>(e.bw_act + m * e.bw_ldact + cbase + q8 * 8));
+    const bf16* ab = reinterpret_cast<const bf16*>(&ar);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = q8 * 8 + i;
+      float gsel = f[c];
+      if (e.bw_relu && !(__bfloat162float(ab[i]) > 0.f)) gsel = 0.f;
+      f[c] = gsel;
+      sq[c] = gsel * __bfloat162float(xb[i]);
+    }
+  }
+}
+// per-CTA partial sums (a = sum g', b = sum g' * x) of channel ch -> the second BN-backward sum
+__device__ __forceinline__ double bw_second_sum(double a, double b, const EpiTC& e, int ch) {
+  return (double)__ldg(e.bw_invstd + ch) * (b - (double)__ldg(e.bw_mean + ch) * a);
+}
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+struct FastDiv {
+  uint32_t mul, shr;
+};
+static FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f;
+  uint32_t l = 0;
+  while ((1ull << l) < d) ++l;
+  f.shr = l;
+  f.mul = (uint32_t)(((1ull << 32) * ((1ull << l) - d)) / d + 1);
+  return f;
+}
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, FastDiv f) { return (__umulhi(f.mul, n) + n) >> f.shr; }
+
+constexpr int TC_THREADS = 320;   // warps 0-3 gather/epilogue, warp 4 MMA issuer, warp 5 TMA producer, warps 6-9 epilogue helpers
+constexpr int EPI_THREADS = 256;  // the 8 epilogue warps
+constexpr int WG_THREADS = 160;   // weight-gradient kernel: warps 0-3 gather/epilogue, warp 4 MMA issuer
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;                 // bf16 elements = 128 bytes = one swizzle row
+constexpr int A_STAGE_BYTES = TC_BM * 128;
+
+// Epilogue of CW accumulator columns [cbase, cbase+CW) of output row m held in f[]: folded-BN affine / bias, residual,
+// ReLU, store (bf16 NHWC or fp32 NCHW) and per-channel batch statistics.  The statistics are folded over the 32 rows of
+// the warp with a transpose-reduce and ACCUMULATED into this warp's shared-memory slots (sstat_warp[col], [BN + col]);
+// the CTA flushes the slots to global memory with one double atomic per channel when its n tile changes / at the end.
+template <int CW, bool BW = true>
+__device__ __forceinline__ void epilogue_chunk(float (&f)[CW], const EpiTC& e, long long m, bool row_ok, int cbase, int on,
+                                               int oh, int ow, bool do_stats, float* sstat_sum, float* sstat_sq, int lane) {
+  if (e.scale) {
+#pragma unroll
+    for (int i = 0; i < CW; ++i)
+      if (cbase + i < e.Cout) f[i] = fmaf(f[i], __ldg(e.scale + cbase + i), __ldg(e.shift + cbase + i));
+  } else if (e.shift) {
+#pragma unroll
+    for (int i = 0; i < CW; ++i)
+      if (cbase + i < e.Cout) f[i] += __ldg(e.shift + cbase + i);
+  }
+  if (e.res && row_ok) {
+    const uint4* rp4 = reinterpret_cast<const uint4*>(e.res + m * e.ldr + cbase);
+#pragma unroll
+    for (int q = 0; q < CW / 8; ++q) {
+      uint4 rr = __ldg(rp4 + q);
+      const bf16* rb16 = reinterpret_cast<const bf16*>(&rr);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[q * 8 + i] += __bfloat162float(rb16[i]);
+    }
+  }
+  if (e.relu) {
+#pragma unroll
+    for (int i = 0; i < CW; ++i) f[i] = fmaxf(f[i], 0.f);
+  }
+  if (row_ok) {
+    if (e.out_nchw) {
+#pragma unroll
+      for (int i = 0; i < CW; ++i)
+        if (cbase + i < e.Cout) e.out_nchw[(((long long)on * e.Cout + cbase + i) * e.Ho + oh) * e.Wo + ow] = f[i];
+    } else {
+      uint4* op = reinterpret_cast<uint4*>(e.out + m * e.ldo + cbase);
+#pragma unroll
+      for (int q = 0; q < CW / 8; ++q) {
+        uint4 o;
+        __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o2[i] = __floats2bfloat162_rn(f[q * 8 + 2 * i], f[q * 8 + 2 * i + 1]);
+        op[q] = o;
+      }
+    }
+  }
+  if (do_stats) {
+    float sq[CW];
+    if (BW && e.bw_x) {
+      bw_stat_terms<CW>(f, sq, e, m, row_ok, cbase);
+    } else {
+#pragma unroll
+      for (int i = 0; i < CW; ++i) {
+        if (!row_ok) f[i] = 0.f;
+        sq[i] = f[i] * f[i];
+      }
+    }
+    float cs, cq;
+    if (CW == 32) { cs = warp_colsum32(f, lane); cq = warp_colsum32(sq, lane); }
+    else { cs = warp_colsum16(f, lane); cq = warp_colsum16(sq, lane); }
+    if (lane < CW) {           // one writer per (warp, column) slot: no shared-memory atomics, deterministic
+      sstat_sum[lane] += cs;
+      sstat_sq[lane] += cq;
+    }
+  }
+}
+
+// ---- launch-geometry state shared by the tensor-core translation units (defined in conv_tc.cu)
+extern int g_num_sms;
+extern int g_verbose;       // D3FK_VERBOSE=1: print launch geometry
+extern int g_max_cluster;   // cap of the split-K / split-pixel cluster size (debug builds: D3FK_CLUSTER)
+constexpr int SLAB_MAX_SMEM = 225 * 1024;
+
+// Co-resident CTA capacity of a cluster launch, per CTAs-per-SM.  cudaOccupancyMaxActiveClusters reports one CTA per SM
+// for kernels that allocate tensor memory; tools/probes/cluster_residency.cu measured, on B200 at 2 CTAs/SM, 296 CTAs for
+// cluster sizes 1-2, 284 for 4 and 264 for 8 (GPC boundaries strand a few SMs) — the table below keeps a safety margin.
+// GUARANTEED co-resident CTAs of a cluster launch (what cudaOccupancyMaxActiveClusters reports for these kernels: one CTA
+// per SM, minus the SMs GPC boundaries strand) — the bound for anything that spins on a grid-wide barrier.  A 16 x 8-CTA
+// cluster grid of the 320-thread kernel was observed NOT to be co-resident (15 clusters were), although the probe kernel
+// reached 33: the optimistic table below is for wave sizing only.
+static inline int cluster_capacity_safe(int cl) { return cl >= 8 ? 120 : cl >= 4 ? 132 : g_num_sms; }
+static inline int cluster_capacity(int cl, int ctas_per_sm) {
+  const int per_sm = cl >= 8 ? 120 : cl >= 4 ? 138 : g_num_sms;   // usable SMs (of 148) for this cluster size
+  return per_sm * ctas_per_sm;
+}
+
+#define D3FK_SET_SMEM(k, bytes)                                                                     \
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);               \
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+
+}  // namespace d3fk
