@@ -608,7 +608,7 @@ __global__ void __launch_bounds__(256) qsample_kernel(d3fk_qsample_params p) {
     if (p.fixed_r >= 0.f) {
       r = p.fixed_r;
     } else {
-      const float cexp = __expf(-p.lam);
+      const float cexp = expf(-p.lam);     // once per block: the accurate form
       float y;
       if (p.y) y = __ldg(p.y + b);
       else {
@@ -617,6 +617,7 @@ __global__ void __launch_bounds__(256) qsample_kernel(d3fk_qsample_params p) {
         y = (float)(u.x >> 8) * (1.0f / 16777216.0f);  // U[0,1) like torch.rand
       }
       r = (1.0f / p.lam) * logf(1.0f / (y * (1.0f - cexp) + cexp));
+      r = fminf(fmaxf(r, 0.f), 1.f);   // y == 0 can round to 1 + ulp: sqrtf(1 - r) would be NaN for the whole sample
     }
     s_coef[0] = sqrtf(1.0f - r);
     s_coef[1] = sqrtf(r);
@@ -653,7 +654,7 @@ __global__ void __launch_bounds__(256) affine_qsample_kernel(d3fk_affine_qsample
     if (p.fixed_r >= 0.f) {
       r = p.fixed_r;
     } else {
-      const float cexp = __expf(-p.lam);
+      const float cexp = expf(-p.lam);     // once per block: the accurate form
       float y;
       if (p.y) y = __ldg(p.y + b);
       else {
@@ -662,6 +663,7 @@ __global__ void __launch_bounds__(256) affine_qsample_kernel(d3fk_affine_qsample
         y = (float)(u.x >> 8) * (1.0f / 16777216.0f);
       }
       r = (1.0f / p.lam) * logf(1.0f / (y * (1.0f - cexp) + cexp));
+      r = fminf(fmaxf(r, 0.f), 1.f);   // y == 0 can round to 1 + ulp: sqrtf(1 - r) would be NaN for the whole sample
     }
     s_coef[0] = sqrtf(1.0f - r);
     s_coef[1] = sqrtf(r);

@@ -129,13 +129,17 @@ def tensor_to_frames(tensor, mean, std):
     return out
 
 
-def random_affine_inverse_maps(B, H, W, degrees=15.0, translate=(0.2, 0.2), scale=(0.8, 1.2), generator=None, device=None):
+def random_affine_inverse_maps(B, H, W, degrees=15.0, translate=(0.2, 0.2), scale=(0.8, 1.2), generator=None, device=None,
+                               p=1.0):
     """Per-sample inverse affine maps [B,6] (output pixel -> source pixel) with the parameter distribution of the reference's
     `K.RandomAffine(degrees=15, translate=[0.2, 0.2], scale=[0.8, 1.2], shear=0, p=1.0)`
     (d3f/train_denoiser/lit_module.py:55-65): angle ~ U(-degrees, degrees), translation ~ U(-t*W, t*W) x U(-t*H, t*H), one
     isotropic scale ~ U(lo, hi); rotation + scale about the image centre ((W-1)/2, (H-1)/2), then the translation.  Host
-    arithmetic on B x 4 numbers (float64, closed-form inverse); the warp itself is d3fk_affine_q_sample."""
+    arithmetic on B x 4 numbers (float64, closed-form inverse); the warp itself is d3fk_affine_q_sample.
+    p < 1: each sample is augmented with probability p and gets the identity map otherwise (albumentations'
+    ShiftScaleRotate(p=0.7) of d3f/train_deep_fake/lit_module.py:99-111; one extra uniform draw per sample)."""
     u = torch.rand(B, 4, generator=generator, dtype=torch.float64)
+    keep = torch.rand(B, generator=generator, dtype=torch.float64) < p if p < 1.0 else None
     th = (2 * u[:, 0] - 1) * degrees * math.pi / 180.0
     tx = (2 * u[:, 1] - 1) * translate[0] * W
     ty = (2 * u[:, 2] - 1) * translate[1] * H
@@ -145,6 +149,9 @@ def random_affine_inverse_maps(B, H, W, degrees=15.0, translate=(0.2, 0.2), scal
     ca, sa = torch.cos(th) / sc, torch.sin(th) / sc
     m = torch.stack([ca, -sa, cx - ca * (cx + tx) + sa * (cy + ty),
                      sa, ca, cy - sa * (cx + tx) - ca * (cy + ty)], dim=1)
+    if keep is not None:
+        ident = torch.tensor([1.0, 0.0, 0.0, 0.0, 1.0, 0.0], dtype=torch.float64).expand(B, 6)
+        m = torch.where(keep.view(B, 1), m, ident)
     return m.to(torch.float32).to(device) if device is not None else m.to(torch.float32)
 
 

@@ -11,7 +11,7 @@ import click
 import torch
 import yaml
 
-from .train import DeepFakeModule, DenoiserModule, cosine_lr
+from .train import DeepFakeModule, DenoiserModule, FlatAdam, cosine_lr, set_lr
 
 
 def read_yaml_file_into_dict(yaml_file_path):
@@ -43,7 +43,7 @@ def list_file_batches(list_path, batch_size, mean, std, device):
     perm = torch.randperm(len(names)).tolist()
     mean_t = torch.tensor(mean, dtype=torch.float32).view(1, 3, 1, 1)
     std_t = torch.tensor(std, dtype=torch.float32).view(1, 3, 1, 1)
-    for i in range(0, len(perm) - batch_size + 1, batch_size):
+    for i in range(0, len(perm), batch_size):           # the last, smaller batch is kept (DataLoader drop_last=False)
         imgs = []
         for j in perm[i:i + batch_size]:
             img = cv2.cvtColor(cv2.imread(os.path.join(root, names[j])), cv2.COLOR_BGR2RGB)
@@ -51,11 +51,19 @@ def list_file_batches(list_path, batch_size, mean, std, device):
         yield ((torch.stack(imgs) - mean_t) / std_t).to(device, non_blocking=True)
 
 
+def _optimizers_of(module):
+    opts = [getattr(module, n, None) for n in ("optimizer", "optimizer_a", "optimizer_b")]
+    return [o for o in opts if o is not None]
+
+
 def save_checkpoint(path, module, epoch, extra=None):
-    """Lightning-shaped checkpoint: {'state_dict', 'hyper_parameters', 'epoch', ...} with the reference's key
-    prefixes (model. / model_a. / model_b. / ema_model_*.ema_model.)."""
+    """Lightning-shaped checkpoint: {'state_dict', 'hyper_parameters', 'epoch', 'global_step', 'optimizer_states'} with the
+    reference's key prefixes (model. / model_a. / model_b. / ema_model_*.ema_model.).  optimizer_states holds the Adam
+    moments, step count and current LR of every optimiser (Lightning's `ckpt_path` resume restores them,
+    d3f/train_deep_fake/start_training.py:19-23, :50-53)."""
     ckpt = {"state_dict": module.state_dict(), "hyper_parameters": dict(module.hparams), "epoch": epoch,
-            "global_step": module.global_step}
+            "global_step": module.global_step,
+            "optimizer_states": [o.state_dict() for o in _optimizers_of(module)]}
     ckpt.update(extra or {})
     os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
     torch.save(ckpt, path)
@@ -72,6 +80,24 @@ def load_checkpoint(path, cls, strict=True, **overrides):
     return module, ckpt
 
 
+def restore_optimizers(module, ckpt):
+    """After configure_optimizers(): Adam moments / step counts from the checkpoint (when the optimiser form matches) and the
+    cosine LR of the epoch being resumed — a resumed run continues at cosine_lr(current_epoch), not at the base LR."""
+    states = ckpt.get("optimizer_states") or []
+    opts = _optimizers_of(module)
+    if len(states) == len(opts):
+        for o, sd in zip(opts, states):
+            if isinstance(o, FlatAdam) == ("m" in sd and "v" in sd):
+                if isinstance(o, FlatAdam):
+                    o.load_state_dict({k: (v.to(o.m.device) if torch.is_tensor(v) else v) for k, v in sd.items()})
+                else:
+                    o.load_state_dict(sd)
+    p = module.hparams
+    lr = cosine_lr(p["learning_rate"], module.current_epoch, p["cosine_scheduler_max_epoch"])
+    for o in opts:
+        set_lr(o, lr)
+
+
 @click.group()
 def cli():
     pass
@@ -86,6 +112,8 @@ def cli():
 @click.option("--checkpoint_dir", default="d3fk_checkpoints")
 def denoise(config, input_list, synthetic, size, precision, checkpoint_dir):
     """Train the denoiser (reference: `d3f denoise`)."""
+    if not input_list and not synthetic:
+        raise click.UsageError("give --input_list (the reference's image list) or --synthetic N (seeded synthetic batches)")
     hp = read_yaml_file_into_dict(config)
     hp["input_image_list_path"] = input_list
     hp.setdefault("precision", precision)
@@ -108,26 +136,26 @@ def denoise(config, input_list, synthetic, size, precision, checkpoint_dir):
         save_checkpoint(os.path.join(checkpoint_dir, "last.ckpt"), module, epoch + 1)
 
 
-def _fit_deep_fake(module, size, synthetic, checkpoint_dir):
+def _fit_deep_fake(module, size, synthetic, checkpoint_dir, ckpt=None):
     p = module.hparams
     dev = torch.device("cuda", torch.cuda.current_device())
     module.to(dev).train()
+    if not synthetic:
+        p.setdefault("augment", True)      # list-file data: the reference's ShiftScaleRotate (lit_module.py:99-111)
     print_hparams(p)
-    opts = module.configure_optimizers()
+    module.configure_optimizers()
+    if ckpt is not None:
+        restore_optimizers(module, ckpt)
     for epoch in range(module.current_epoch, p["max_epochs"]):
         if synthetic:
             it = zip(synthetic_batches(p["batch_size"], size, synthetic, dev, seed=2 * epoch),
                      synthetic_batches(p["batch_size"], size, synthetic, dev, seed=2 * epoch + 1))
         else:
-            it = zip(list_file_batches(p["data_path_a"], p["batch_size"], p["mean_a"], p["mean_a"], dev),
-                     list_file_batches(p["data_path_b"], p["batch_size"], p["mean_b"], p["mean_b"], dev))
+            it = zip(list_file_batches(p["data_path_a"], p["batch_size"], p["mean_a"], p["std_a"], dev),
+                     list_file_batches(p["data_path_b"], p["batch_size"], p["mean_b"], p["std_b"], dev))
         for batch_a, batch_b in it:
-            out = module.training_step(batch_a, batch_b)
-        module.current_epoch = epoch + 1
-        lr = cosine_lr(p["learning_rate"], module.current_epoch, p["cosine_scheduler_max_epoch"])
-        for o in opts:
-            for g in o.param_groups:
-                g["lr"] = lr
+            module.training_step(batch_a, batch_b)
+        module.on_epoch_end()
         print(f"epoch {epoch} " + " ".join(f"{k}={float(v):.5f}" for k, v in module.logged.items()))
         save_checkpoint(os.path.join(checkpoint_dir, "last.ckpt"), module, epoch + 1)
 
@@ -161,8 +189,8 @@ def new(config_path, synthetic, size, checkpoint_dir):
 @click.option("--checkpoint_path", required=True, help="Path to model checkpoint.")
 @_add(_common)
 def resume(checkpoint_path, synthetic, size, checkpoint_dir):
-    module, _ = load_checkpoint(checkpoint_path, DeepFakeModule)
-    _fit_deep_fake(module, size, synthetic, checkpoint_dir)
+    module, ckpt = load_checkpoint(checkpoint_path, DeepFakeModule)
+    _fit_deep_fake(module, size, synthetic, checkpoint_dir, ckpt)
 
 
 @train.command()

@@ -160,5 +160,7 @@ def swap_face(model, real, n_steps=1, r_start=0.0, eta=0.0, seed=0):
         out = model(real)
         model.train(was)
         return out
-    x_start = q_sample(real, 1.0, seed=seed, fixed_r=r_start)
+    # the start noise comes from a Philox key of its own (as Sampler.run's does): with the sampler's key the first ancestral
+    # z (eta > 0; posterior step 0 draws philox(seed, element, offset 0)) would be the very noise the source was noised with
+    x_start = q_sample(real, 1.0, seed=seed ^ 0x5EED, fixed_r=r_start)
     return sample(model, x_start, n_steps, r_start=r_start, eta=eta, seed=seed)

@@ -48,26 +48,30 @@ class FlatAdam:
             raise RuntimeError("model parameters were re-allocated (.to()/.cuda()) after FlatAdam was built")
 
     def step(self, ema_flat=None, ema_decay=0.0, grad_scale=1.0):
+        """One fused launch over the whole arena.  ema_flat (same layout as flat_p): the kernel's EMA arm also performs
+        ema += (1 - ema_decay) * (p_new - ema) in the same pass (ema_pytorch's lerp on the parameters)."""
         self.check_aliasing()
         self.step_count += 1
         adam_step_(self.flat_p, self.model._grad_arena, self.m, self.v, self.lr, self.betas[0], self.betas[1],
                    self.eps, self.step_count, ema=ema_flat, ema_decay=ema_decay, grad_scale=grad_scale)
-        for p in self.model.parameters():       # in-place update invisible to autograd's version counters
-            break
         self.model.__dict__["_stat_updates"] = self.model.__dict__.get("_stat_updates", 0) + 1
 
     # ---- bucket-wise form of step() (StepOverlap): begin_step, step_range per bucket, end_step
-    def begin_step(self):
+    def begin_step(self, ema_flat=None, ema_decay=0.0):
         self.check_aliasing()
         self.step_count += 1
+        self._ema_flat, self._ema_decay = ema_flat, ema_decay
 
     def step_range(self, start, end):
+        ema = getattr(self, "_ema_flat", None)
         adam_step_(self.flat_p[start:end], self.model._grad_arena[start:end], self.m[start:end], self.v[start:end],
-                   self.lr, self.betas[0], self.betas[1], self.eps, self.step_count)
+                   self.lr, self.betas[0], self.betas[1], self.eps, self.step_count,
+                   ema=None if ema is None else ema[start:end], ema_decay=getattr(self, "_ema_decay", 0.0))
 
     def end_step(self, plan=None):
         m = self.model
         m.__dict__["_stat_updates"] = m.__dict__.get("_stat_updates", 0) + 1
+        self._ema_flat = None
         if plan is not None:        # the plan's packed operands already hold the updated weights
             plan.prepacked_version = m._weights_version()
 
@@ -77,6 +81,15 @@ class FlatAdam:
     def load_state_dict(self, sd):
         self.m.copy_(sd["m"]), self.v.copy_(sd["v"])
         self.step_count, self.lr = sd["step"], sd["lr"]
+
+
+def set_lr(optimizer, lr):
+    """Per-epoch cosine LR for either optimiser form (FlatAdam or torch.optim.Adam)."""
+    if isinstance(optimizer, FlatAdam):
+        optimizer.lr = lr
+    else:
+        for g in optimizer.param_groups:
+            g["lr"] = lr
 
 
 def cosine_lr(base_lr, epoch, t_max):
@@ -103,6 +116,7 @@ class StepOverlap:
         self.comm = torch.cuda.Stream(dev)
         self.buckets = model.grad_buckets()
         self.armed = False          # the optimiser part runs only inside a training step that asked for it
+        self.ema_target = (None, 0.0)   # (flat EMA arena, decay) the Adam launches of THIS step also lerp (swap mode)
         self.stepped = False
         self._plan = None
         model.__dict__["_dp_hook"] = self.after_segment
@@ -122,7 +136,7 @@ class StepOverlap:
                 allreduce_bucket_(self.model._grad_arena, s, e, self.group)
             if do_adam:
                 if i == 0:
-                    self.optimizer.begin_step()
+                    self.optimizer.begin_step(*self.ema_target)
                 self.optimizer.step_range(s, e)
                 if plan is not None:
                     plan.run_pack_bucket(i, self.comm.cuda_stream)
@@ -230,17 +244,20 @@ class DenoiserModule(nn.Module):
     def on_epoch_end(self):
         self.current_epoch += 1
         lr = cosine_lr(self.hparams["learning_rate"], self.current_epoch, self.hparams["cosine_scheduler_max_epoch"])
-        if isinstance(self.optimizer, FlatAdam):
-            self.optimizer.lr = lr
-        else:
-            for g in self.optimizer.param_groups:
-                g["lr"] = lr
+        set_lr(self.optimizer, lr)
 
 
 class EMA(nn.Module):
     """ema_pytorch.EMA(model, beta, update_every, include_online_model=False) semantics:
     copy for the first `update_after_step` updates, then lerp with decay
-    clamp(1-(1+(step-101)/inv_gamma)^-power, 0, beta) over float params and buffers."""
+    clamp(1-(1+(step-101)/inv_gamma)^-power, 0, beta) over float params and buffers.
+
+    Fast path (`bind_flat`): the EMA parameters become views of ONE flat fp32 arena laid out like the online model's
+    FlatAdam arena, and the parameter lerp of the next `update()` is performed by the EMA arm of the fused Adam kernel
+    (d3fk_adam) in the same pass that updates the online weights — `planned_lerp()` tells the trainer whether the next
+    update() will lerp and with which decay; `update()` then only advances the counters and lerps the (tiny) BN buffers.
+    The schedule is driven from host mirrors of the `step` / `initted` buffers (no device sync per step); a
+    load_state_dict re-synchronises them (resume)."""
 
     def __init__(self, model, beta=0.9999, update_after_step=100, update_every=10, inv_gamma=1.0, power=2 / 3,
                  min_value=0.0, include_online_model=True):
@@ -257,6 +274,16 @@ class EMA(nn.Module):
         self.register_buffer("step", torch.tensor(0))
         self._step_host = 0
         self._initted_host = False
+        self._flat = None            # flat arena of the EMA parameters (bind_flat)
+        self._online_flat = None     # the online model's FlatAdam arena
+        self._preapplied = False     # the parameter lerp of the NEXT update() already ran inside the Adam kernel
+        self.register_load_state_dict_post_hook(EMA._resync_host_mirrors)
+
+    @staticmethod
+    def _resync_host_mirrors(module, incompatible_keys):
+        module._step_host = int(module.step)
+        module._initted_host = bool(module.initted)
+        module._preapplied = False
 
     @property
     def model(self):
@@ -270,9 +297,57 @@ class EMA(nn.Module):
         return min(max(value, self.min_value), self.beta)
 
     @torch.no_grad()
+    def bind_flat(self, optimizer):
+        """Re-home the EMA parameters in one flat arena with the layout of `optimizer.flat_p` (a FlatAdam over the online
+        model).  Call after the module sits on its device."""
+        model, ema = self.model, self.ema_model
+        model._ensure_param_tables()
+        flat = torch.zeros_like(optimizer.flat_p)
+        ema_params = dict(ema.named_parameters())
+        for name, off in model._grad_offsets.items():
+            p = ema_params[name]
+            flat[off:off + p.numel()].copy_(p.data.reshape(-1))
+            p.data = flat[off:off + p.numel()].view(p.shape)
+        self._flat, self._online_flat = flat, optimizer.flat_p
+
+    def _flat_ok(self):
+        """The flat views survive only as long as nobody re-allocated the parameters (.to() / .cuda())."""
+        if self._flat is None:
+            return False
+        name = self.model._param_names[0]
+        off = self.model._grad_offsets[name]
+        ok = (dict(self.ema_model.named_parameters())[name].data_ptr() == self._flat.data_ptr() + 4 * off
+              and self.model._param_dict[name].data_ptr() == self._online_flat.data_ptr() + 4 * off)
+        if not ok:
+            self._flat = self._online_flat = None
+        return ok
+
+    def planned_lerp(self):
+        """(flat EMA arena, decay) if the next update() call will lerp the parameters, else None."""
+        step = self._step_host
+        if step % self.update_every != 0 or step <= self.update_after_step or not self._initted_host:
+            return None
+        if self._preapplied or not self._flat_ok():
+            return None
+        return self._flat, self.get_current_decay(step + 1)
+
+    def mark_preapplied(self):
+        self._preapplied = True
+        self._bump_version()
+
+    def _bump_version(self):
+        d = self.ema_model.__dict__
+        if "_stat_updates" in d or hasattr(self.ema_model, "_weights_version"):
+            d["_stat_updates"] = d.get("_stat_updates", 0) + 1     # in-place writes invisible to tensor._version
+
+    @torch.no_grad()
     def _copy(self):
-        for e, m in zip(self.ema_model.parameters(), self.model.parameters()):
-            e.copy_(m)
+        if self._flat_ok():
+            self._flat.copy_(self._online_flat)
+            self._bump_version()
+        else:
+            for e, m in zip(self.ema_model.parameters(), self.model.parameters()):
+                e.copy_(m)
         for e, m in zip(self.ema_model.buffers(), self.model.buffers()):
             e.copy_(m)
 
@@ -291,11 +366,19 @@ class EMA(nn.Module):
             self._initted_host = True
             self.initted.fill_(True)
         decay = self.get_current_decay(self._step_host)
-        ep = [e for e in self.ema_model.parameters() if e.is_floating_point()]
-        mp = [m for e, m in zip(self.ema_model.parameters(), self.model.parameters()) if e.is_floating_point()]
+        if self._preapplied:
+            self._preapplied = False          # parameters: done by the EMA arm of the online model's last Adam launch
+        elif self._flat_ok():
+            self._flat.lerp_(self._online_flat, 1 - decay)
+            self._bump_version()
+        else:
+            ep = [e for e in self.ema_model.parameters() if e.is_floating_point()]
+            mp = [m for e, m in zip(self.ema_model.parameters(), self.model.parameters()) if e.is_floating_point()]
+            torch._foreach_lerp_(ep, mp, 1 - decay)
         eb = [e for e in self.ema_model.buffers() if e.is_floating_point()]
         mb = [m for e, m in zip(self.ema_model.buffers(), self.model.buffers()) if e.is_floating_point()]
-        torch._foreach_lerp_(ep + eb, mp + mb, 1 - decay)
+        if eb:
+            torch._foreach_lerp_(eb, mb, 1 - decay)
 
     def forward(self, *a, **k):
         return self.ema_model(*a, **k)
@@ -317,6 +400,9 @@ class DeepFakeModule(nn.Module):
         self.global_step = 0
         self.current_epoch = 0
         self.logged = {}
+        self._aug_generator = None
+        self.optimizer_a = self.optimizer_b = None
+        self.overlap_a = self.overlap_b = None
 
     def create_ema_model(self, model):
         p = self.hparams
@@ -324,31 +410,110 @@ class DeepFakeModule(nn.Module):
             return EMA(model, beta=p["ema_beta"], update_every=p["ema_update_every"], include_online_model=False)
         return None
 
-    def configure_optimizers(self):
+    def configure_optimizers(self, fused=None, overlap=True):
+        """Two Adams with betas from the config (lit_module.py:113-125).  fused (default: whenever the models sit on a CUDA
+        device): one-kernel FlatAdam per model over its flat arenas, the EMA copies re-homed in flat arenas so the Adam
+        launch also performs their parameter lerp, and — `overlap` — the per-bucket Adam / re-pack running underneath
+        backward (StepOverlap), as in DenoiserModule.  fused=False keeps torch.optim.Adam over .parameters()."""
         p = self.hparams
         betas = (p["adam_b1"], p["adam_b2"])
-        self.optimizer_a = torch.optim.Adam(self.model_a.parameters(), lr=p["learning_rate"], betas=betas)
-        self.optimizer_b = torch.optim.Adam(self.model_b.parameters(), lr=p["learning_rate"], betas=betas)
+        if fused is None:
+            fused = next(self.model_a.parameters()).is_cuda
+        if fused:
+            self.optimizer_a = FlatAdam(self.model_a, lr=p["learning_rate"], betas=betas)
+            self.optimizer_b = FlatAdam(self.model_b, lr=p["learning_rate"], betas=betas)
+            if overlap and os.environ.get("D3FK_OVERLAP_STEP", "1") != "0":
+                self.overlap_a = StepOverlap(self.model_a, self.optimizer_a)
+                self.overlap_b = StepOverlap(self.model_b, self.optimizer_b)
+            if self.ema_model_a is not None:
+                self.ema_model_a.bind_flat(self.optimizer_a)
+                self.ema_model_b.bind_flat(self.optimizer_b)
+        else:
+            self.optimizer_a = torch.optim.Adam(self.model_a.parameters(), lr=p["learning_rate"], betas=betas)
+            self.optimizer_b = torch.optim.Adam(self.model_b.parameters(), lr=p["learning_rate"], betas=betas)
         return [self.optimizer_a, self.optimizer_b]
 
-    def blend_random_amount_of_noise_with_each_sample(self, batch):
+    def blend_random_amount_of_noise_with_each_sample(self, batch, noise=None, y=None):
         p = self.hparams
         self._noise_calls = getattr(self, "_noise_calls", 0) + 1
-        return q_sample(batch, p["noise_exponential_sampling_lambda"], seed=p.get("seed", 0), offset=self._noise_calls)
+        return q_sample(batch, p["noise_exponential_sampling_lambda"], noise=noise, y=y, seed=p.get("seed", 0),
+                        offset=self._noise_calls)
 
-    def training_step(self, batch_a, batch_b):
-        """Both optimiser passes of one Lightning batch (lit_module.py:142-156)."""
+    def augment(self, batch):
+        """The reference augments in its DataLoader workers: A.ShiftScaleRotate(shift 0.2, scale 0.1, rotate 15, border 0,
+        p=0.7) (lit_module.py:99-111).  Here: the same parameter distribution, applied on the device by the affine kernel
+        (bilinear, zero border); samples that draw "no augmentation" get the identity map.  hparam `augment` (default off:
+        tensor-level callers and the benchmark feed ready batches) switches it on; the CLI does for list-file data."""
+        B, _, H, W = batch.shape
+        if self._aug_generator is None:
+            self._aug_generator = torch.Generator().manual_seed(int(self.hparams.get("seed", 0)) + 0xA06)
+        maps = random_affine_inverse_maps(B, H, W, degrees=15.0, translate=(0.2, 0.2), scale=(0.9, 1.1), p=0.7,
+                                          generator=self._aug_generator)
+        aug, _ = affine_q_sample(batch, maps, 1.0, fixed_r=0.0)
+        return aug
+
+    def training_step(self, batch_a, batch_b, noise=None, y=None):
+        """Both optimiser passes of one Lightning batch (lit_module.py:142-156).  noise / y: optional dicts {"a": ..., "b": ...}
+        of supplied noising draws (parity runs)."""
         out = {}
-        for name, real, real_model, fake_model, opt in (
-                ("a", batch_a, self.model_a, self.ema_model_b, self.optimizer_a),
-                ("b", batch_b, self.model_b, self.ema_model_a, self.optimizer_b)):
-            opt.zero_grad(set_to_none=True)
-            loss = self.training_step_for_one_model(name, real, real_model, fake_model)
-            loss.backward()
-            opt.step()
-            out[name] = loss
+        if self.optimizer_a is None:
+            self.configure_optimizers()
+        if self.hparams.get("augment", False):
+            batch_a, batch_b = self.augment(batch_a), self.augment(batch_b)
+        for name, real, real_model, fake_model, own_ema, opt, ov in (
+                ("a", batch_a, self.model_a, self.ema_model_b, self.ema_model_a, self.optimizer_a, self.overlap_a),
+                ("b", batch_b, self.model_b, self.ema_model_a, self.ema_model_b, self.optimizer_b, self.overlap_b)):
+            self._draws = (None if noise is None else noise[name], None if y is None else y[name])
+            if isinstance(opt, FlatAdam):
+                out[name] = self._fused_step_for_one_model(name, real, real_model, fake_model, own_ema, opt, ov)
+            else:
+                opt.zero_grad(set_to_none=True)
+                loss = self.training_step_for_one_model(name, real, real_model, fake_model)
+                loss.backward()
+                opt.step()
+                out[name] = loss
+        self._draws = (None, None)
         self.global_step += 1
         return out
+
+    def _fused_step_for_one_model(self, name, real, real_model, fake_model, own_ema, opt, ov):
+        """One optimiser pass on the fast path: loss value and dL/dprediction from the one criterion launch, the U-Net
+        backward seeded directly, gradients in the flat arena, ONE Adam launch (per bucket, underneath backward, with
+        StepOverlap) whose EMA arm also lerps this model's EMA copy when its next update() is a lerp."""
+        real_prediction = self._prediction_for_one_model(name, real, real_model, fake_model)
+        loss, grad = self.criterion.value_and_grad(real_prediction, real)
+        self.logged[f"loss_{self.hparams['mode']}/train_{name}"] = loss
+        planned = own_ema.planned_lerp() if own_ema is not None else None
+        ema_flat, decay = planned if planned is not None else (None, 0.0)
+        stepped = False
+        if ov is not None:
+            ov.armed, ov.ema_target = True, (ema_flat, decay)
+            try:
+                real_prediction.backward(grad)
+            finally:
+                ov.armed = False
+            stepped = ov.finish()
+        else:
+            real_prediction.backward(grad)
+        if not stepped:
+            opt.step(ema_flat=ema_flat, ema_decay=decay)
+        if planned is not None:
+            own_ema.mark_preapplied()
+        return loss
+
+    def _prediction_for_one_model(self, name, real, real_model, fake_model):
+        """The data flow of training_{denoise,swap}_step_for_one_model up to the prediction (lit_module.py:168-197)."""
+        noise, y = getattr(self, "_draws", (None, None))
+        if self.hparams["mode"] == "denoise":
+            with torch.no_grad():
+                noisy_real = self.blend_random_amount_of_noise_with_each_sample(real, noise, y)
+            return real_model(noisy_real)
+        fake_model.update()
+        with torch.no_grad():
+            fake = fake_model(real)                        # one pass, BN in train mode as in the reference
+            self.logged[f"swap_difference/{name}"] = nn.functional.mse_loss(real, fake)
+            noisy_fake = self.blend_random_amount_of_noise_with_each_sample(fake, noise, y)
+        return real_model(noisy_fake)
 
     def training_step_for_one_model(self, name, real, real_model, fake_model):
         if self.hparams["mode"] == "denoise":
@@ -356,24 +521,22 @@ class DeepFakeModule(nn.Module):
         return self.training_swap_step_for_one_model(name, real, real_model, fake_model)
 
     def training_denoise_step_for_one_model(self, name, real, real_model):
-        with torch.no_grad():
-            noisy_real = self.blend_random_amount_of_noise_with_each_sample(real)
-        real_prediction = real_model(noisy_real)
+        real_prediction = self._prediction_for_one_model(name, real, real_model, None)
         loss = self.criterion(real_prediction, real)
         self.logged[f"loss_denoise/train_{name}"] = loss.detach()
         return loss
 
     def training_swap_step_for_one_model(self, name, real, real_model, fake_model):
-        fake_model.update()
-        with torch.no_grad():
-            fake = fake_model(real)                        # one pass, BN in train mode as in the reference
-            swap_diff = nn.functional.mse_loss(real, fake)
-            noisy_fake = self.blend_random_amount_of_noise_with_each_sample(fake)
-        real_prediction = real_model(noisy_fake)
+        real_prediction = self._prediction_for_one_model(name, real, real_model, fake_model)
         loss = self.criterion(real_prediction, real)
-        self.logged[f"swap_difference/{name}"] = swap_diff
         self.logged[f"loss_swap/train_{name}"] = loss.detach()
         return loss
+
+    def on_epoch_end(self):
+        self.current_epoch += 1
+        lr = cosine_lr(self.hparams["learning_rate"], self.current_epoch, self.hparams["cosine_scheduler_max_epoch"])
+        for o in (self.optimizer_a, self.optimizer_b):
+            set_lr(o, lr)
 
     @torch.no_grad()
     def predict_fake(self, real, model_a_or_b):

@@ -126,3 +126,84 @@ def test_bench_reference_arm_contract():
     out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
                           "--warmup", "0"], capture_output=True, text=True, timeout=120, env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
     assert out.returncode == 0 and not [l for l in out.stdout.splitlines() if l.startswith("{")]
+
+
+def test_ema_resume_keeps_schedule():
+    """A checkpoint taken mid-run restores the host-side schedule mirrors: after load_state_dict the next update() must
+    continue the decay warm-up where it stopped (not re-copy the online weights over the loaded EMA)."""
+    torch.manual_seed(0)
+    a, b = torch.nn.Linear(6, 6), torch.nn.Linear(6, 6)
+    b.load_state_dict(a.state_dict())
+    ea = oracle.EMA(a, beta=0.999, update_every=5, include_online_model=False)
+    eb = EMA(b, beta=0.999, update_every=5, include_online_model=False)
+
+    def drift():
+        with torch.no_grad():
+            d = torch.randn(6, 6) * 0.1
+            a.weight.add_(d), b.weight.add_(d)
+
+    for _ in range(137):
+        drift(), ea.update(), eb.update()
+    sd = {k: v.clone() for k, v in eb.state_dict().items()}
+    resumed = EMA(b, beta=0.999, update_every=5, include_online_model=False)      # fresh object: mirrors at 0 / False
+    resumed.load_state_dict(sd)
+    assert resumed._step_host == 137 and resumed._initted_host is True
+    for _ in range(40):
+        drift(), ea.update(), resumed.update()
+        assert torch.allclose(ea.ema_model.weight, resumed.ema_model.weight, atol=1e-6)
+    assert int(resumed.step) == int(ea.step) == 177
+    # as a submodule of a checkpointed parent (the way DeepFakeModule holds it)
+    holder = torch.nn.Module()
+    holder.ema_model_a = EMA(b, beta=0.999, update_every=5, include_online_model=False)
+    holder.load_state_dict({"ema_model_a." + k: v for k, v in sd.items()})
+    assert holder.ema_model_a._step_host == 137 and holder.ema_model_a._initted_host is True
+
+
+def test_checkpoint_restores_optimizer_state_and_cosine_lr(tmp_path):
+    """`train resume`: Adam moments / step counts come back from the checkpoint and the resumed epoch runs at
+    cosine_lr(current_epoch), not at the base LR (Lightning's ckpt_path semantics)."""
+    from denoising_diffusion_deep_fake_b200.main import load_checkpoint, restore_optimizers, save_checkpoint
+    from denoising_diffusion_deep_fake_b200.train import DeepFakeModule
+    hp = dict(encoder_name="resnet34", learning_rate=0.02, noise_exponential_sampling_lambda=3, max_epochs=50,
+              cosine_scheduler_max_epoch=50, mode="denoise", adam_b1=0.5, adam_b2=0.999, batch_size=2, precision="fp32")
+    m = DeepFakeModule(**hp)
+    opts = m.configure_optimizers(fused=False)
+    for o in opts:                                  # a fake step so that the state is non-trivial
+        for p in o.param_groups[0]["params"][:3]:
+            p.grad = torch.ones_like(p)
+        o.step()
+    m.current_epoch = 7
+    path = str(tmp_path / "last.ckpt")
+    save_checkpoint(path, m, epoch=7)
+    m2, ckpt = load_checkpoint(path, DeepFakeModule)
+    assert m2.current_epoch == 7 and len(ckpt["optimizer_states"]) == 2
+    opts2 = m2.configure_optimizers(fused=False)
+    restore_optimizers(m2, ckpt)
+    for o, o2 in zip(opts, opts2):
+        s, s2 = o.state_dict()["state"], o2.state_dict()["state"]
+        assert set(s) == set(s2) and len(s) == 3
+        for k in s:
+            assert torch.equal(s[k]["exp_avg"], s2[k]["exp_avg"]) and float(s[k]["step"]) == float(s2[k]["step"]) == 1.0
+        assert o2.param_groups[0]["lr"] == pytest.approx(cosine_lr(0.02, 7, 50))
+        assert o2.param_groups[0]["betas"] == (0.5, 0.999)
+
+
+def test_denoise_cli_needs_a_data_source(tmp_path):
+    from click.testing import CliRunner
+    from denoising_diffusion_deep_fake_b200.main import cli
+    cfg = tmp_path / "c.yml"
+    cfg.write_text("batch_size: 2\nlearning_rate: 0.02\nmax_epochs: 1\ncosine_scheduler_max_epoch: 1\nencoder_name: resnet34\n"
+                   "noise_exponential_sampling_lambda: 5\n")
+    res = CliRunner().invoke(cli, ["denoise", "--config", str(cfg)])
+    assert res.exit_code != 0 and "--input_list" in res.output
+
+
+def test_random_affine_maps_with_probability():
+    from denoising_diffusion_deep_fake_b200.functional import random_affine_inverse_maps
+    g = torch.Generator().manual_seed(0)
+    m = random_affine_inverse_maps(4000, 32, 32, scale=(0.9, 1.1), p=0.7, generator=g)
+    ident = torch.tensor([1.0, 0.0, 0.0, 0.0, 1.0, 0.0])
+    frac = (m == ident).all(dim=1).float().mean().item()
+    assert abs(frac - 0.3) < 0.03
+    det = m[:, 0] * m[:, 4] - m[:, 1] * m[:, 3]                 # inverse map: 1 / scale^2
+    assert (det > 1 / 1.1 ** 2 - 1e-4).all() and (det < 1 / 0.9 ** 2 + 1e-4).all()
