@@ -99,7 +99,11 @@ class MiscParams(C.Structure):
 class AdamParams(C.Structure):
     _fields_ = [("n", i64), ("p", vp), ("g", vp), ("m", vp), ("v", vp), ("ema", vp),
                 ("lr", f32), ("beta1", f32), ("beta2", f32), ("eps", f32), ("bias1", f32), ("bias2", f32),
-                ("ema_decay", f32), ("grad_scale", f32)]
+                ("ema_decay", f32), ("grad_scale", f32), ("dyn", vp)]
+
+
+class ScalarsParams(C.Structure):
+    _fields_ = [("dst", vp), ("v", f32 * 4)]
 
 
 class LossParams(C.Structure):
@@ -122,7 +126,7 @@ class _OpUnion(C.Union):
                 ("qsample", QsampleParams), ("posterior", PosteriorParams), ("misc", MiscParams),
                 ("adam", AdamParams), ("loss", LossParams), ("convbn", ConvBnParams), ("upcat", UpcatParams),
                 ("wgrad_group", WgradGroupParams), ("frames", FramesParams),
-                ("affine_qsample", AffineQsampleParams)]
+                ("affine_qsample", AffineQsampleParams), ("scalars", ScalarsParams)]
 
 
 class Op(C.Structure):
@@ -133,7 +137,7 @@ class Op(C.Structure):
 (OP_CONV, OP_WGRAD, OP_PACK, OP_NCHW2NHWC, OP_BN_FINALIZE, OP_BN_APPLY, OP_BN_FOLD, OP_BN_BWD_REDUCE,
  OP_BN_BWD_FINALIZE, OP_BN_BWD_APPLY, OP_MAXPOOL_FWD, OP_MAXPOOL_BWD, OP_SUMPOOL2, OP_CHANSUM, OP_QSAMPLE,
  OP_POSTERIOR, OP_MEMSET, OP_INC, OP_ADAM, OP_PACK_ALL, OP_LOSS, OP_CONV_BN, OP_UPCAT, OP_BN_BWD, OP_WGRAD_GROUP, OP_FRAMES_TO_TENSOR, OP_TENSOR_TO_FRAMES,
- OP_AFFINE_QSAMPLE) = range(1, 29)
+ OP_AFFINE_QSAMPLE, OP_SET_SCALARS) = range(1, 30)
 
 _UNION_FIELD = {OP_CONV: "conv", OP_WGRAD: "wgrad", OP_PACK: "pack", OP_NCHW2NHWC: "layout",
                 OP_BN_FINALIZE: "bn", OP_BN_APPLY: "bn", OP_BN_FOLD: "bn", OP_BN_BWD_REDUCE: "bn",
@@ -142,12 +146,12 @@ _UNION_FIELD = {OP_CONV: "conv", OP_WGRAD: "wgrad", OP_PACK: "pack", OP_NCHW2NHW
                 OP_MEMSET: "misc", OP_INC: "misc", OP_ADAM: "adam", OP_PACK_ALL: "misc",
                 OP_LOSS: "loss", OP_CONV_BN: "convbn", OP_UPCAT: "upcat", OP_BN_BWD: "bn",
                 OP_WGRAD_GROUP: "wgrad_group", OP_FRAMES_TO_TENSOR: "frames", OP_TENSOR_TO_FRAMES: "frames",
-                OP_AFFINE_QSAMPLE: "affine_qsample"}
+                OP_AFFINE_QSAMPLE: "affine_qsample", OP_SET_SCALARS: "scalars"}
 _PARAM_CLS = {"conv": ConvParams, "wgrad": WgradParams, "pack": PackParams, "bn": BnParams, "pool": PoolParams,
               "layout": LayoutParams, "chansum": ChansumParams, "qsample": QsampleParams,
               "posterior": PosteriorParams, "misc": MiscParams, "adam": AdamParams, "loss": LossParams,
               "convbn": ConvBnParams, "upcat": UpcatParams, "wgrad_group": WgradGroupParams,
-              "frames": FramesParams, "affine_qsample": AffineQsampleParams}
+              "frames": FramesParams, "affine_qsample": AffineQsampleParams, "scalars": ScalarsParams}
 
 SINGLE_ENTRY = {OP_CONV: "d3fk_conv", OP_WGRAD: "d3fk_wgrad", OP_PACK: "d3fk_pack_weights",
                 OP_NCHW2NHWC: "d3fk_nchw_to_nhwc", OP_BN_FINALIZE: "d3fk_bn_finalize", OP_BN_APPLY: "d3fk_bn_apply",
@@ -157,7 +161,8 @@ SINGLE_ENTRY = {OP_CONV: "d3fk_conv", OP_WGRAD: "d3fk_wgrad", OP_PACK: "d3fk_pac
                 OP_CHANSUM: "d3fk_chansum", OP_QSAMPLE: "d3fk_q_sample", OP_POSTERIOR: "d3fk_posterior_step",
                 OP_ADAM: "d3fk_adam", OP_LOSS: "d3fk_mse_ssim_loss", OP_CONV_BN: "d3fk_conv_bn", OP_UPCAT: "d3fk_upcat", OP_BN_BWD: "d3fk_bn_bwd",
                 OP_WGRAD_GROUP: "d3fk_wgrad_group", OP_FRAMES_TO_TENSOR: "d3fk_frames_to_tensor",
-                OP_TENSOR_TO_FRAMES: "d3fk_tensor_to_frames", OP_AFFINE_QSAMPLE: "d3fk_affine_q_sample"}
+                OP_TENSOR_TO_FRAMES: "d3fk_tensor_to_frames", OP_AFFINE_QSAMPLE: "d3fk_affine_q_sample",
+                OP_SET_SCALARS: "d3fk_set_scalars"}
 EXPORTS = ["d3fk_version", "d3fk_sizeof_op", "d3fk_init", "d3fk_last_error", "d3fk_device_error_flag", "d3fk_run",
            "d3fk_run_nojoin", "d3fk_side_stream_join", "d3fk_run_profile", "d3fk_launch_count", "d3fk_debug_timeline"] + sorted(set(SINGLE_ENTRY.values()))
 

@@ -59,6 +59,7 @@ int launch_qsample(const d3fk_qsample_params*, cudaStream_t);
 int launch_posterior(const d3fk_posterior_params*, cudaStream_t);
 int launch_inc(const d3fk_misc_params*, cudaStream_t);
 int launch_adam(const d3fk_adam_params*, cudaStream_t);
+int launch_set_scalars(const d3fk_scalars_params*, cudaStream_t);
 int launch_pack_all(const d3fk_misc_params*, cudaStream_t);
 int launch_loss(const d3fk_loss_params*, cudaStream_t);
 int loss_init();
@@ -130,6 +131,7 @@ static int run_one(const d3fk_op* op, cudaStream_t s) {
     }
     case D3FK_OP_INC: return launch_inc(&op->u.misc, s);
     case D3FK_OP_ADAM: return launch_adam(&op->u.adam, s);
+    case D3FK_OP_SET_SCALARS: return launch_set_scalars(&op->u.scalars, s);
     case D3FK_OP_PACK_ALL: return launch_pack_all(&op->u.misc, s);
     case D3FK_OP_LOSS: return launch_loss(&op->u.loss, s);
     default: return set_error(D3FK_ERR_ARG, "unknown op kind %d", op->kind);
@@ -335,6 +337,7 @@ SINGLE(d3fk_affine_q_sample, d3fk_affine_qsample_params, launch_affine_qsample)
 SINGLE(d3fk_q_sample, d3fk_qsample_params, launch_qsample)
 SINGLE(d3fk_posterior_step, d3fk_posterior_params, launch_posterior)
 SINGLE(d3fk_adam, d3fk_adam_params, launch_adam)
+SINGLE(d3fk_set_scalars, d3fk_scalars_params, launch_set_scalars)
 SINGLE(d3fk_mse_ssim_loss, d3fk_loss_params, launch_loss)
 
 }  // extern "C"

@@ -798,6 +798,9 @@ __device__ __forceinline__ void adam_one(float& w, float g, float& m, float& v, 
 }
 __global__ void __launch_bounds__(256) adam_kernel(d3fk_adam_params p) {
   pdl_enter();
+  if (p.dyn) {      // per-step scalars from device memory (graph replay); written by the host before the replay
+    p.lr = __ldg(p.dyn); p.bias1 = __ldg(p.dyn + 1); p.bias2 = __ldg(p.dyn + 2); p.ema_decay = __ldg(p.dyn + 3);
+  }
   const float step = p.lr / p.bias1;
   const float rsb2 = rsqrtf(p.bias2);
   const long long nvec = p.n >> 2;
@@ -1088,6 +1091,17 @@ int launch_tensor_to_frames(const d3fk_frames_params* p, cudaStream_t s) {
   count_launch();
   return check_launch("tensor_to_frames");
 }
+__global__ void set_scalars_kernel(d3fk_scalars_params p) {
+  pdl_enter();
+  if (threadIdx.x < 4) p.dst[threadIdx.x] = p.v[threadIdx.x];
+}
+int launch_set_scalars(const d3fk_scalars_params* p, cudaStream_t s) {
+  D3FK_CHECK_ARG(p->dst != nullptr, "dst is null");
+  launch_k(set_scalars_kernel, dim3(1), dim3(32), 0, s, dim3(1, 1, 1), *p);
+  count_launch();
+  return check_launch("set_scalars");
+}
+
 int launch_adam(const d3fk_adam_params* p, cudaStream_t s) {
   D3FK_CHECK_ARG((((uintptr_t)p->p | (uintptr_t)p->g | (uintptr_t)p->m | (uintptr_t)p->v | (uintptr_t)p->ema) & 15) == 0, "arenas must be 16-byte aligned");
   launch_k(adam_kernel, dim3(grid_for(p->n / 4 + 1, 256)), dim3(256), 0, s, dim3(1, 1, 1), *p);

@@ -24,14 +24,17 @@ def _require_cuda_f32(t, name):
     _lib.init(t.device.index)
 
 
-def q_sample(batch, lam, noise=None, y=None, seed=0, offset=0, fixed_r=None, return_aux=False):
+def q_sample(batch, lam, noise=None, y=None, seed=0, offset=0, fixed_r=None, return_aux=False, out=None):
     """noisy = sqrt(1-r)*batch + sqrt(r)*noise with per-sample r = 1/lam*log(1/(y(1-c)+c)), c = e^-lam.
     noise / y: optional tensors (parity with the reference's torch.randn_like / torch.rand draws);
     otherwise drawn in-kernel from Philox4x32-10(seed, offset)."""
     _require_cuda_f32(batch, "batch")
     batch = batch.contiguous()
     B = batch.shape[0]
-    out = torch.empty_like(batch)
+    if out is None:
+        out = torch.empty_like(batch)
+    elif out.shape != batch.shape or out.dtype != torch.float32 or not out.is_contiguous() or out.device != batch.device:
+        raise ValueError("q_sample: `out` must be a contiguous float32 tensor of the batch's shape on its device")
     r_out = torch.empty(B, dtype=torch.float32, device=batch.device) if return_aux else None
     n_out = torch.empty_like(batch) if (return_aux and noise is None) else None
     if noise is not None:
@@ -81,13 +84,19 @@ def posterior_step_(x_i, x0_hat, r_i, r_prev, z=None, eta=0.0, seed=0, offset=0)
     return x_i
 
 
-def adam_step_(p, g, m, v, lr, beta1, beta2, eps, step, ema=None, ema_decay=0.0, grad_scale=1.0):
-    """Fused torch.optim.Adam update (+optional EMA lerp) over flat fp32 arenas."""
+def adam_scalars(lr, beta1, beta2, step, ema_decay=0.0):
+    """The per-step scalars of d3fk_adam: (lr, bias1, bias2, ema_decay)."""
+    return float(lr), 1.0 - beta1 ** step, 1.0 - beta2 ** step, float(ema_decay)
+
+
+def adam_step_(p, g, m, v, lr, beta1, beta2, eps, step, ema=None, ema_decay=0.0, grad_scale=1.0, dyn=None):
+    """Fused torch.optim.Adam update (+optional EMA lerp) over flat fp32 arenas.  dyn: device float tensor holding
+    adam_scalars(...) — the launch then reads its per-step scalars from there (CUDA-graph replay)."""
     _require_cuda_f32(p, "p")
     op = make_op(_lib.OP_ADAM, n=p.numel(), p=p.data_ptr(), g=g.data_ptr(), m=m.data_ptr(), v=v.data_ptr(),
                  ema=None if ema is None else ema.data_ptr(), lr=float(lr), beta1=float(beta1), beta2=float(beta2),
                  eps=float(eps), bias1=1.0 - beta1 ** step, bias2=1.0 - beta2 ** step, ema_decay=float(ema_decay),
-                 grad_scale=float(grad_scale))
+                 grad_scale=float(grad_scale), dyn=None if dyn is None else dyn.data_ptr())
     _lib.run_single(op, _stream(p))
 
 
@@ -155,7 +164,8 @@ def random_affine_inverse_maps(B, H, W, degrees=15.0, translate=(0.2, 0.2), scal
     return m.to(torch.float32).to(device) if device is not None else m.to(torch.float32)
 
 
-def affine_q_sample(batch, inverse_maps, lam, noise=None, y=None, seed=0, offset=0, fixed_r=None, return_aux=False):
+def affine_q_sample(batch, inverse_maps, lam, noise=None, y=None, seed=0, offset=0, fixed_r=None, return_aux=False,
+                    out=None):
     """The reference's `image = augment(image); image_noisy = blend_noise(image)` (d3f/train_denoiser/lit_module.py:113-115) in
     ONE kernel: per-sample affine warp (bilinear, zero padding; `inverse_maps` [B,6] or [B,2,3], output pixel -> source pixel)
     and the noising of the warped image.  Returns (image_augmented, image_noisy) — the loss target and the network input —
@@ -167,7 +177,10 @@ def affine_q_sample(batch, inverse_maps, lam, noise=None, y=None, seed=0, offset
     batch = batch.contiguous()
     B, C, H, W = batch.shape
     m = inverse_maps.reshape(B, 6).to(device=batch.device, dtype=torch.float32).contiguous()
-    aug, noisy = torch.empty_like(batch), torch.empty_like(batch)
+    aug, noisy = out if out is not None else (torch.empty_like(batch), torch.empty_like(batch))
+    for t in (aug, noisy):
+        if t.shape != batch.shape or t.dtype != torch.float32 or not t.is_contiguous() or t.device != batch.device:
+            raise ValueError("affine_q_sample: `out` must be two contiguous float32 tensors of the batch's shape on its device")
     r_out = torch.empty(B, dtype=torch.float32, device=batch.device) if return_aux else None
     if noise is not None:
         noise = noise.contiguous()

@@ -14,7 +14,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .functional import adam_step_, affine_q_sample, q_sample, random_affine_inverse_maps
+from .functional import adam_scalars, adam_step_, affine_q_sample, q_sample, random_affine_inverse_maps
 from .parallel import allreduce_bucket_
 from .loss import MseStructuralSimilarityLoss
 from .unet import Unet
@@ -40,6 +40,22 @@ class FlatAdam:
         model.bind_flat_grads()
         self.m = torch.zeros_like(self.flat_p)
         self.v = torch.zeros_like(self.flat_p)
+        # per-step scalars (lr, bias corrections, EMA decay) in device memory, so that the Adam launches can be recorded
+        # once in a CUDA graph: dyn_host (pinned) is filled by push_scalars() and copied on the stream before the step
+        self.dyn = None
+
+    def enable_device_scalars(self):
+        if self.dyn is None:
+            self.dyn = torch.zeros(4, dtype=torch.float32, device=self.flat_p.device)
+        return self.dyn
+
+    def push_scalars(self, step, ema_decay=0.0):
+        """Write the scalars of optimiser step `step` to the device: one tiny launch on the current stream that carries
+        the four floats BY VALUE (a host staging buffer could be overwritten before a queued copy has read it — the host
+        runs many replayed steps ahead of the device)."""
+        vals = adam_scalars(self.lr, self.betas[0], self.betas[1], step, ema_decay)
+        op = _lib.make_op(_lib.OP_SET_SCALARS, dst=self.dyn.data_ptr(), v=list(vals))
+        _lib.run_single(op, torch.cuda.current_stream(self.dyn.device).cuda_stream)
 
     def check_aliasing(self):
         name = self.model._param_names[0]
@@ -52,8 +68,10 @@ class FlatAdam:
         ema += (1 - ema_decay) * (p_new - ema) in the same pass (ema_pytorch's lerp on the parameters)."""
         self.check_aliasing()
         self.step_count += 1
+        if self.dyn is not None:
+            self.push_scalars(self.step_count, ema_decay)
         adam_step_(self.flat_p, self.model._grad_arena, self.m, self.v, self.lr, self.betas[0], self.betas[1],
-                   self.eps, self.step_count, ema=ema_flat, ema_decay=ema_decay, grad_scale=grad_scale)
+                   self.eps, self.step_count, ema=ema_flat, ema_decay=ema_decay, grad_scale=grad_scale, dyn=self.dyn)
         self.model.__dict__["_stat_updates"] = self.model.__dict__.get("_stat_updates", 0) + 1
 
     # ---- bucket-wise form of step() (StepOverlap): begin_step, step_range per bucket, end_step
@@ -61,12 +79,14 @@ class FlatAdam:
         self.check_aliasing()
         self.step_count += 1
         self._ema_flat, self._ema_decay = ema_flat, ema_decay
+        if self.dyn is not None and not torch.cuda.is_current_stream_capturing():
+            self.push_scalars(self.step_count, ema_decay)     # (a graph replay pushes them itself, before the replay)
 
     def step_range(self, start, end):
         ema = getattr(self, "_ema_flat", None)
         adam_step_(self.flat_p[start:end], self.model._grad_arena[start:end], self.m[start:end], self.v[start:end],
                    self.lr, self.betas[0], self.betas[1], self.eps, self.step_count,
-                   ema=None if ema is None else ema[start:end], ema_decay=getattr(self, "_ema_decay", 0.0))
+                   ema=None if ema is None else ema[start:end], ema_decay=getattr(self, "_ema_decay", 0.0), dyn=self.dyn)
 
     def end_step(self, plan=None):
         m = self.model
@@ -160,6 +180,91 @@ class StepOverlap:
 GradAllReduce = StepOverlap    # the allreduce-only use (optimizer=None) keeps its old name
 
 
+class GraphedStep:
+    """The training step behind the noising — U-Net forward, criterion, backward with its weight-gradient side streams,
+    per-bucket [allreduce ->] Adam -> re-pack on the update stream — recorded ONCE as a CUDA graph and replayed per step
+    (SURVEY §7 step 7).  The step is static: every buffer belongs to the plan or to the graph's private pool, the kernels'
+    programmatic-dependent-launch edges are kept by the capture, and what changes from step to step lives in device memory
+    (Adam's lr / bias corrections: FlatAdam.dyn; BN's num_batches_tracked; the Philox offset stays outside: the noising
+    launch is issued eagerly in front of the replay and writes into the graph's static input).
+
+    One graph per input buffer address (a caller that reuses its device buffers — bench.py, a double-buffered loader —
+    replays directly; any other batch is copied into a module-owned static buffer first).  A graph is dropped whenever the
+    weights were changed from outside (load_state_dict, manual edits), which the version counter reveals."""
+
+    MAX_POINTER_GRAPHS = 2
+
+    def __init__(self, module):
+        self.module = module
+        self.entries = {}       # key -> dict(graph, x, noisy, loss, version)
+        self.seen = {}          # data_ptr -> times seen (pointer graphs are built for repeat customers only)
+        self.static_x = {}      # shape -> module-owned input buffer
+        self.eager_steps = 0    # eager steps since the last invalidation: capture needs warmed plans and a valid pre-pack
+        self.replays = 0
+
+    def invalidate(self):
+        self.entries.clear()
+        self.eager_steps = 0
+
+    def _capture(self, x):
+        mod = self.module
+        model, opt = mod.model, mod.optimizer
+        noisy = torch.empty_like(x)
+        plan = model._acquire_plan(noisy, training=True)
+        if plan.prepacked_version is None or plan.prepacked_version != model._weights_version():
+            return None                      # the forward would start with a full pack: not the steady state yet
+        host = (opt.step_count, model.__dict__.get("_stat_updates", 0), plan.generation, plan.prepacked_version)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            loss = mod._step_body(x, noisy)
+        # nothing ran during the capture: take back the host-side bookkeeping it advanced
+        opt.step_count, model.__dict__["_stat_updates"], plan.generation, plan.prepacked_version = host
+        plan.pending_backward = False
+        return dict(graph=g, x=x, noisy=noisy, loss=loss, plan=plan)
+
+    def step(self, image, noise=None, y=None):
+        """Returns the loss tensor, or None when the step has to run eagerly (warm-up, stale graph)."""
+        mod = self.module
+        model, opt = mod.model, mod.optimizer
+        if self.eager_steps < 2:
+            self.eager_steps += 1
+            return None
+        ptr = image.data_ptr()
+        key = (ptr, tuple(image.shape))
+        ent = self.entries.get(key)
+        if ent is None:
+            self.seen[ptr] = self.seen.get(ptr, 0) + 1
+            n_ptr = sum(1 for k in self.entries if k[0] != "static")
+            if self.seen[ptr] >= 2 and n_ptr < self.MAX_POINTER_GRAPHS and image.is_contiguous():
+                ent = self._capture(image)
+                if ent is None:
+                    return None
+                self.entries[key] = ent
+            else:
+                key = ("static", tuple(image.shape))
+                ent = self.entries.get(key)
+                if ent is None:
+                    ent = self._capture(torch.empty_like(image, memory_format=torch.contiguous_format))
+                    if ent is None:
+                        return None
+                    self.entries[key] = ent
+        if ent["plan"].prepacked_version != model._weights_version() or ent["plan"].params_moved():
+            self.invalidate()                # weights were touched from outside: eager steps re-establish the steady state
+            return None
+        if ent["x"].data_ptr() != ptr:
+            ent["x"].copy_(image)
+        mod._noise_into(ent["x"], ent["noisy"], noise, y)
+        opt.push_scalars(opt.step_count + 1)
+        ent["graph"].replay()
+        # the host-side bookkeeping of the step the replay just enqueued
+        opt.step_count += 1
+        model.__dict__["_stat_updates"] = model.__dict__.get("_stat_updates", 0) + 2      # BN running stats + Adam
+        ent["plan"].generation += 1
+        ent["plan"].prepacked_version = model._weights_version()
+        self.replays += 1
+        return ent["loss"]
+
+
 class DenoiserModule(nn.Module):
     """train_denoiser LitModule, minus Lightning.  hparams: encoder_name, learning_rate,
     noise_exponential_sampling_lambda, cosine_scheduler_max_epoch (+ precision, seed: new)."""
@@ -176,6 +281,7 @@ class DenoiserModule(nn.Module):
         self.optimizer = None
         self.allreduce = None
         self._aug_generator = None
+        self._graphed = None       # GraphedStep once the fused trainer is in its steady state (False: disabled)
 
     def forward(self, image):
         return self.model(image)
@@ -212,10 +318,54 @@ class DenoiserModule(nn.Module):
         return affine_q_sample(batch, maps, p["noise_exponential_sampling_lambda"], noise=noise, y=y,
                                seed=p.get("seed", 0), offset=self.global_step)
 
+    def _noise_into(self, image, noisy, noise=None, y=None):
+        """The noising launch in front of a graph replay: image -> noisy (both static buffers of the graph)."""
+        p = self.hparams
+        q_sample(image, p["noise_exponential_sampling_lambda"], noise=noise, y=y, seed=p.get("seed", 0),
+                 offset=self.global_step, out=noisy)
+
+    def _step_body(self, image, image_noisy):
+        """Forward, criterion, backward and the overlapped per-bucket optimiser work, without autograd objects (the body a
+        GraphedStep records)."""
+        model, ov = self.model, self.allreduce
+        plan = model._acquire_plan(image_noisy, training=True)
+        image_prediction = model._run_forward(plan, image_noisy)
+        loss, grad = self.training_criterion.value_and_grad(image_prediction, image)
+        ov.armed = True
+        try:
+            model._run_backward(plan, grad)
+        finally:
+            ov.armed = False
+        if not ov.finish():
+            raise RuntimeError("the overlapped optimiser step did not run")
+        return loss
+
+    def _graph_eligible(self):
+        if self._graphed is False:
+            return False
+        ok = (isinstance(self.optimizer, FlatAdam) and self.allreduce is not None and self.allreduce.optimizer is not None
+              and self.model.training and not self.hparams.get("augment", False)
+              and self.hparams.get("cuda_graph", os.environ.get("D3FK_TRAIN_GRAPH", "1") != "0")
+              and all(p.requires_grad for p in self.model.parameters()))
+        if ok and self.allreduce.distributed:
+            ok = os.environ.get("D3FK_TRAIN_GRAPH_DP", "0") == "1"      # NCCL inside the capture: opt-in
+        return ok
+
     def training_step(self, image, noise=None, y=None):
         """[affine augmentation ->] noising -> U-Net -> MSE+SSIM loss -> backward -> Adam (lit_module.py:107-126 + the
         optimiser step Lightning would take).  Returns the loss tensor (no host sync).  hparam `augment` (default False:
-        the benchmark feeds pre-augmented tensors) switches the reference's kornia RandomAffine on."""
+        the benchmark feeds pre-augmented tensors) switches the reference's kornia RandomAffine on.
+        With the fused optimiser the step is replayed from a CUDA graph after two eager warm-up steps (GraphedStep;
+        hparam `cuda_graph: false` or D3FK_TRAIN_GRAPH=0 keeps it eager)."""
+        if self._graph_eligible():
+            if self._graphed is None:
+                self.optimizer.enable_device_scalars()
+                self._graphed = GraphedStep(self)
+            loss = self._graphed.step(image, noise, y)
+            if loss is not None:
+                self.global_step += 1
+                self._check_device_flag()
+                return loss
         if self.hparams.get("augment", False):
             image, image_noisy = self.augment_and_blend(image, noise, y)
         else:
@@ -239,7 +389,14 @@ class DenoiserModule(nn.Module):
         if not stepped:
             self.optimizer.step()
         self.global_step += 1
+        self._check_device_flag()
         return loss
+
+    def _check_device_flag(self, every=512):
+        """A kernel watchdog traps (sticky CUDA error) — this additionally polls the device error flag every `every` steps
+        (a 4-byte read; it synchronises, hence not every step)."""
+        if self.global_step % every == 0 and _lib.load().d3fk_device_error_flag():
+            raise _lib.D3fkError("a d3fk kernel reported a barrier watchdog timeout; the results of this run are void")
 
     def on_epoch_end(self):
         self.current_epoch += 1

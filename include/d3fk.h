@@ -222,12 +222,21 @@ typedef struct d3fk_misc_params {          /* MEMSET: p0[0..n) bytes = 0; INC: *
 } d3fk_misc_params;
 
 /* ---- fused Adam (+EMA lerp) over a flat fp32 arena (torch.optim.Adam semantics: eps outside sqrt,
- * no weight decay, no amsgrad; d3f/train_denoiser/lit_module.py:95, train_deep_fake/lit_module.py:116-120) */
+ * no weight decay, no amsgrad; d3f/train_denoiser/lit_module.py:95, train_deep_fake/lit_module.py:116-120).
+ * bias1 = 1 - beta1^step, bias2 = 1 - beta2^step (the caller's step count). */
 typedef struct d3fk_adam_params {
   int64_t n;
   float* p; const float* g; float* m; float* v; float* ema;
   float lr, beta1, beta2, eps, bias1, bias2, ema_decay, grad_scale;
+  const float* dyn;   /* nullable: device floats {lr, bias1, bias2, ema_decay} that override the immediates — the per-step
+                         scalars of a launch recorded once in a CUDA graph and replayed every training step */
 } d3fk_adam_params;
+
+/* ---- four floats written to device memory by value (no host buffer to race with): the per-step scalars `dyn` of the
+ * Adam launches inside a replayed CUDA graph are refreshed with this launch in front of every replay. */
+typedef struct d3fk_scalars_params {
+  float* dst; float v[4];
+} d3fk_scalars_params;
 
 /* ---- fused MSE + (1 - SSIM) criterion, forward and gradient
  * (d3f/loss_functions/structural_similarity_loss.py:14-26 + piqa.SSIM defaults).
@@ -256,6 +265,7 @@ enum d3fk_op_kind {
   D3FK_OP_UPCAT = 23,
   D3FK_OP_FRAMES_TO_TENSOR = 26, D3FK_OP_TENSOR_TO_FRAMES = 27,   /* frames params */
   D3FK_OP_AFFINE_QSAMPLE = 28,
+  D3FK_OP_SET_SCALARS = 29,   /* scalars params */
   D3FK_OP_WGRAD_GROUP = 25,   /* wgrad_group params; forked onto the side streams like D3FK_OP_WGRAD */
   D3FK_OP_BN_BWD = 24    /* bn params: bn_bwd_reduce + bn_bwd_apply as one op (one kernel behind a grid barrier when `barrier` is set) */
 };
@@ -268,6 +278,7 @@ typedef struct d3fk_op {
     d3fk_qsample_params qsample; d3fk_posterior_params posterior; d3fk_misc_params misc;
     d3fk_adam_params adam; d3fk_loss_params loss; d3fk_convbn_params convbn; d3fk_upcat_params upcat;
     d3fk_wgrad_group_params wgrad_group; d3fk_frames_params frames; d3fk_affine_qsample_params affine_qsample;
+    d3fk_scalars_params scalars;
   } u;
 } d3fk_op;
 
@@ -318,6 +329,7 @@ int d3fk_upcat(const d3fk_upcat_params* p, d3fk_stream stream);
 int d3fk_q_sample(const d3fk_qsample_params* p, d3fk_stream stream);
 int d3fk_posterior_step(const d3fk_posterior_params* p, d3fk_stream stream);
 int d3fk_adam(const d3fk_adam_params* p, d3fk_stream stream);
+int d3fk_set_scalars(const d3fk_scalars_params* p, d3fk_stream stream);
 int d3fk_mse_ssim_loss(const d3fk_loss_params* p, d3fk_stream stream);
 
 /* number of kernels launched by this library since load (bench.py's gpu_launches) */

@@ -427,3 +427,69 @@ def test_head_conv(case, bias):
     assert rel_err(g, c) < 2e-3, rel_err(g, c)        # bf16 inputs / weights, fp32 accumulation on both sides
     # edges (zero padding) specifically
     assert rel_err(g[..., 0, :], c[..., 0, :]) < 2e-3 and rel_err(g[..., :, -1], c[..., :, -1]) < 2e-3
+
+
+# ---- the cp.async (LDGSTS) operand path has no fence.proxy.async between the full-barrier wait and tcgen05.mma
+# (csrc/tc_common.cuh, "NOTE on proxies"; the protocol of CUTLASS's sm100 cp.async main loop).  A generic->async proxy
+# race would show up as run-to-run differences: ragged shapes through every gather path, 1000 launches in total, each
+# compared bit for bit with the first.
+CP_ASYNC_STRESS = [
+    # conv PATH 0 (linear gather): strided forward, 1x1/2, the 7x7 stem, a ragged M tail
+    ("conv", dict(B=3, Hi=16, Wi=16, c0=64, c1=0, up0=0, Cout=128, k=3, stride=2, pad=1, mode=0)),
+    ("conv", dict(B=5, Hi=8, Wi=8, c0=128, c1=0, up0=0, Cout=256, k=1, stride=2, pad=0, mode=0)),
+    ("conv", dict(B=1, Hi=32, Wi=96, c0=8, c1=0, up0=0, Cout=64, k=7, stride=2, pad=3, mode=0)),
+    ("conv", dict(B=7, Hi=6, Wi=10, c0=64, c1=0, up0=0, Cout=64, k=3, stride=1, pad=1, mode=0)),
+    # conv PATH 1 (generic gather): upsample + concat, stride-2 transposed gather
+    ("conv", dict(B=3, Hi=8, Wi=8, c0=256, c1=128, up0=1, Cout=128, k=3, stride=1, pad=1, mode=0)),
+    ("conv", dict(B=2, Hi=6, Wi=10, c0=128, c1=0, up0=0, Cout=64, k=3, stride=2, pad=1, mode=1)),
+    # generic weight gradient (per-thread cp.async gather of both operands)
+    ("wgrad", dict(B=3, Hi=16, Wi=16, c0=64, c1=0, up0=0, Cout=128, k=3, stride=2, pad=1)),
+    ("wgrad", dict(B=2, Hi=8, Wi=8, c0=256, c1=128, up0=1, Cout=128, k=3, stride=1, pad=1)),
+    ("wgrad", dict(B=5, Hi=6, Wi=10, c0=64, c1=0, up0=0, Cout=64, k=3, stride=1, pad=1)),
+    ("wgrad", dict(B=9, Hi=2, Wi=2, c0=512, c1=0, up0=0, Cout=512, k=3, stride=1, pad=1)),
+]
+
+
+def test_cp_async_path_is_race_free():
+    _lib.init(0)
+    dev = "cuda:0"
+    stream = torch.cuda.current_stream().cuda_stream
+    iters = 1000 // len(CP_ASYNC_STRESS)
+    for kind, c in CP_ASYNC_STRESS:
+        g = torch.Generator().manual_seed(7)
+        B, Hi, Wi, c0, c1, up0, Cout, k, stride, pad = (c[x] for x in ("B", "Hi", "Wi", "c0", "c1", "up0", "Cout", "k", "stride", "pad"))
+        ctot = c0 + c1
+        src0 = torch.randn(B, Hi >> up0, Wi >> up0, c0, generator=g).to(dev).bfloat16()
+        src1 = torch.randn(B, Hi, Wi, max(c1, 8), generator=g).to(dev).bfloat16()
+        if kind == "conv":
+            mode = c["mode"]
+            Ho, Wo = ((Hi + 2 * pad - k) // stride + 1, (Wi + 2 * pad - k) // stride + 1) if mode == 0 else (Hi * stride, Wi * stride)
+            w = (torch.randn(Cout, k * k * ctot, generator=g) / math.sqrt(k * k * ctot)).to(dev).bfloat16()
+            out = torch.zeros(B, Ho, Wo, Cout, device=dev, dtype=torch.bfloat16)
+            op = _lib.make_op(_lib.OP_CONV, dtype=_lib.BF16, mode=mode, src0=src0.data_ptr(), src1=src1.data_ptr() if c1 else None,
+                              c0=c0, c1=c1, ld0=c0, ld1=c1, up0=up0, B=B, Hi=Hi, Wi=Wi, Ho=Ho, Wo=Wo, kh=k, kw=k, stride=stride,
+                              pad=pad, w=w.data_ptr(), Cout=Cout, out=out.data_ptr(), ldo=Cout)
+            exact = True
+        else:
+            Ho, Wo = (Hi + 2 * pad - k) // stride + 1, (Wi + 2 * pad - k) // stride + 1
+            dy = torch.randn(B, Ho, Wo, Cout, generator=g).to(dev).bfloat16()
+            out = torch.zeros(Cout, ctot, k, k, device=dev)
+            op = _lib.make_op(_lib.OP_WGRAD, dtype=_lib.BF16, src0=src0.data_ptr(), src1=src1.data_ptr() if c1 else None, c0=c0, c1=c1,
+                              ld0=c0, ld1=c1, up0=up0, B=B, Hi=Hi, Wi=Wi, Ho=Ho, Wo=Wo, kh=k, kw=k, stride=stride, pad=pad,
+                              dy=dy.data_ptr(), dw=out.data_ptr(), ldy=Cout, Cout=Cout, cin_real=ctot, cout_real=Cout)
+            exact = False       # pixel splits beyond one cluster are summed with atomics: order-dependent last bits
+        first = None
+        bad = torch.zeros((), device=dev)
+        for _ in range(iters):
+            if kind == "wgrad":
+                out.zero_()
+            _lib.run_single(op, stream)
+            if first is None:
+                first = out.clone()
+                assert torch.isfinite(first.float()).all() and first.float().abs().max() > 0
+            elif exact:
+                bad += (out != first).any()
+            else:
+                bad += ((out - first).norm() > 1e-5 * first.norm())
+        assert bad.item() == 0, (kind, c, bad.item())
+    assert _lib.load().d3fk_device_error_flag() == 0

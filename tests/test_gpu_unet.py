@@ -73,8 +73,8 @@ def test_train_forward_parity_bf16(B, H, W):
     assert e < 1.25 * e_ac + 5e-3 and e < 0.15, (e, e_ac)
 
 
-@pytest.mark.parametrize("precision,tol", [("fp32", 2e-5), ("bf16", 3e-2)])
-def test_backward_in_situ(precision, tol):
+@pytest.mark.parametrize("precision,tol,B", [("fp32", 2e-5, 4), ("bf16", 3e-2, 4), ("bf16", 3e-2, 256)])
+def test_backward_in_situ(precision, tol, B):
     """Whole-network backward, flip-free: ReLU masks are discontinuous, so two implementations whose forward
     activations differ by 1e-5 produce gradients that differ by ~sqrt(1e-5) per layer (measured: 1e-2 between
     the fp32 oracle and ANY other fp32 implementation).  To hold every backward kernel to a tight tolerance at
@@ -86,8 +86,8 @@ def test_backward_in_situ(precision, tol):
     from denoising_diffusion_deep_fake_b200.plan import UnetPlan
     import op_interpreter as I
     ref, m = _models(precision, seed=4)
-    B, H, W = 4, 64, 64
-    x = torch.randn(B, 3, H, W)
+    H, W = 64, 64                # B = 256: BASELINE configs[1], the tile schedules / split-K clusters / fused conv+BN
+    x = torch.randn(B, 3, H, W)  # grid-barrier paths bench.py actually runs
     dy = torch.randn(B, 3, H, W)
     m.train()
     y = m(x.to(DEV))
@@ -118,10 +118,13 @@ def test_backward_in_situ(precision, tol):
     assert worst < tol, (worst_name, worst)
 
 
-@pytest.mark.parametrize("precision,tol_head,tol_all", [("fp32", 1e-5, 5e-2), ("bf16", 2e-1, 2.0)])
-def test_train_step_gradients_vs_oracle(precision, tol_head, tol_all):
-    """End-to-end gradients against the oracle's autograd.  The head (no ReLU between it and the loss) is held
-    to 1e-5 in fp32; deeper tensors carry the ReLU-mask flip noise described above and are bounded loosely."""
+@pytest.mark.parametrize("precision,tol_head,tol_all,min_cos", [("fp32", 1e-5, 5e-2, 0.9999), ("bf16", 2e-1, None, 0.6)])
+def test_train_step_gradients_vs_oracle(precision, tol_head, tol_all, min_cos):
+    """End-to-end gradients against the oracle's autograd on RANDOM-INIT weights — the chaotic regime (see
+    tests/test_ref_pin.py::test_oracle_fp32_gradients_against_fp64: the oracle's own fp32 and fp64 gradients differ by
+    4e-3 here; torch's bf16 autocast of the oracle reaches a whole-arena cosine of only 0.82).  The head (no ReLU between
+    it and the loss) is held tightly; the whole arena must still POINT the right way (cosine), which garbage would not.
+    The tolerance-grade comparison runs on trained weights in tests/test_gpu_parity_configs.py."""
     ref, m = _models(precision)
     B, H, W = 8, 64, 64
     x = torch.randn(B, 3, H, W)
@@ -133,7 +136,13 @@ def test_train_step_gradients_vs_oracle(precision, tol_head, tol_all):
     errs = {n: rel_err(pm[n].grad.cpu(), p.grad) for n, p in ref.named_parameters()}
     assert errs["segmentation_head.0.bias"] < (1e-5 if precision == "fp32" else 5e-3)    # bf16: dy itself is rounded
     assert errs["segmentation_head.0.weight"] < tol_head
-    assert max(errs.values()) < tol_all, max(errs, key=errs.get)
+    if tol_all is not None:
+        assert max(errs.values()) < tol_all, max(errs, key=errs.get)
+    names = [n for n, _ in ref.named_parameters()]
+    a = torch.cat([pm[n].grad.cpu().flatten().double() for n in names])
+    b = torch.cat([dict(ref.named_parameters())[n].grad.flatten().double() for n in names])
+    c = (a @ b / (a.norm() * b.norm())).item()
+    assert c > min_cos, c
     assert d3._lib.load().d3fk_device_error_flag() == 0
 
 
