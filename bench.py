@@ -245,7 +245,7 @@ def conv_only_oplist(plan):
     contribute their convolution only: d3fk_convbn_params starts with the d3fk_conv_params)."""
     from denoising_diffusion_deep_fake_b200 import _lib
     import ctypes
-    kinds = (_lib.OP_CONV, _lib.OP_WGRAD, _lib.OP_CONV_BN, _lib.OP_WGRAD_GROUP)
+    kinds = (_lib.OP_CONV, _lib.OP_WGRAD, _lib.OP_CONV_BN, _lib.OP_WGRAD_GROUP, _lib.OP_JOIN)   # JOIN: branch-lane bookkeeping
     ops = [op for op in plan.fwd_ops if op.kind in kinds]
     for seg in plan.bwd_segments or []:
         ops += [op for op in seg if op.kind in kinds]
@@ -256,7 +256,7 @@ def conv_only_oplist(plan):
         if c.kind == _lib.OP_CONV_BN:
             c.kind = _lib.OP_CONV
         copies.append(c)
-    return _lib.OpList(copies), len(copies)
+    return _lib.OpList(copies), sum(1 for c in copies if c.kind != _lib.OP_JOIN)
 
 
 def run_d3fk(args):

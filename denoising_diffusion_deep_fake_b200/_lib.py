@@ -130,14 +130,15 @@ class _OpUnion(C.Union):
 
 
 class Op(C.Structure):
-    _fields_ = [("kind", i32), ("_pad", i32), ("u", _OpUnion)]
+    _fields_ = [("kind", i32), ("lane", i32), ("u", _OpUnion)]
 
 
 # op kinds (enum d3fk_op_kind)
 (OP_CONV, OP_WGRAD, OP_PACK, OP_NCHW2NHWC, OP_BN_FINALIZE, OP_BN_APPLY, OP_BN_FOLD, OP_BN_BWD_REDUCE,
  OP_BN_BWD_FINALIZE, OP_BN_BWD_APPLY, OP_MAXPOOL_FWD, OP_MAXPOOL_BWD, OP_SUMPOOL2, OP_CHANSUM, OP_QSAMPLE,
  OP_POSTERIOR, OP_MEMSET, OP_INC, OP_ADAM, OP_PACK_ALL, OP_LOSS, OP_CONV_BN, OP_UPCAT, OP_BN_BWD, OP_WGRAD_GROUP, OP_FRAMES_TO_TENSOR, OP_TENSOR_TO_FRAMES,
- OP_AFFINE_QSAMPLE, OP_SET_SCALARS) = range(1, 30)
+ OP_AFFINE_QSAMPLE, OP_SET_SCALARS, OP_JOIN) = range(1, 31)
+MAX_LANES = 2
 
 _UNION_FIELD = {OP_CONV: "conv", OP_WGRAD: "wgrad", OP_PACK: "pack", OP_NCHW2NHWC: "layout",
                 OP_BN_FINALIZE: "bn", OP_BN_APPLY: "bn", OP_BN_FOLD: "bn", OP_BN_BWD_REDUCE: "bn",
@@ -146,7 +147,7 @@ _UNION_FIELD = {OP_CONV: "conv", OP_WGRAD: "wgrad", OP_PACK: "pack", OP_NCHW2NHW
                 OP_MEMSET: "misc", OP_INC: "misc", OP_ADAM: "adam", OP_PACK_ALL: "misc",
                 OP_LOSS: "loss", OP_CONV_BN: "convbn", OP_UPCAT: "upcat", OP_BN_BWD: "bn",
                 OP_WGRAD_GROUP: "wgrad_group", OP_FRAMES_TO_TENSOR: "frames", OP_TENSOR_TO_FRAMES: "frames",
-                OP_AFFINE_QSAMPLE: "affine_qsample", OP_SET_SCALARS: "scalars"}
+                OP_AFFINE_QSAMPLE: "affine_qsample", OP_SET_SCALARS: "scalars", OP_JOIN: "misc"}
 _PARAM_CLS = {"conv": ConvParams, "wgrad": WgradParams, "pack": PackParams, "bn": BnParams, "pool": PoolParams,
               "layout": LayoutParams, "chansum": ChansumParams, "qsample": QsampleParams,
               "posterior": PosteriorParams, "misc": MiscParams, "adam": AdamParams, "loss": LossParams,
@@ -182,10 +183,12 @@ def _set_fields(struct, fields):
             setattr(struct, k, v)
 
 
-def make_op(kind, **fields):
-    """Build one d3fk_op record.  Pointer fields take ints (tensor.data_ptr()) or None; nested structs take dicts."""
+def make_op(kind, lane=0, **fields):
+    """Build one d3fk_op record.  Pointer fields take ints (tensor.data_ptr()) or None; nested structs take dicts.
+    lane: 0 = the caller's stream, 1..MAX_LANES = a branch stream of d3fk_run (d3fk_op.lane)."""
     op = Op()
     op.kind = kind
+    op.lane = lane
     _set_fields(getattr(op.u, _UNION_FIELD[kind]), fields)
     return op
 

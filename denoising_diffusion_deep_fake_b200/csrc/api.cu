@@ -132,6 +132,7 @@ static int run_one(const d3fk_op* op, cudaStream_t s) {
     case D3FK_OP_INC: return launch_inc(&op->u.misc, s);
     case D3FK_OP_ADAM: return launch_adam(&op->u.adam, s);
     case D3FK_OP_SET_SCALARS: return launch_set_scalars(&op->u.scalars, s);
+    case D3FK_OP_JOIN: return D3FK_OK;      // stream bookkeeping of run_list; nothing to launch
     case D3FK_OP_PACK_ALL: return launch_pack_all(&op->u.misc, s);
     case D3FK_OP_LOSS: return launch_loss(&op->u.loss, s);
     default: return set_error(D3FK_ERR_ARG, "unknown op kind %d", op->kind);
@@ -212,6 +213,10 @@ static bool g_side_pending = false;
 static int g_skip_wgrad = 0;
 #endif
 static int g_fork_wgrad = 1;   // D3FK_FORK_WGRAD=0: everything in stream order
+#define g_fork_lanes g_fork_wgrad
+
+static cudaStream_t g_lane_streams[D3FK_MAX_LANES] = {nullptr};
+static cudaEvent_t g_lane_events[D3FK_MAX_LANES];
 
 static int ensure_side_stream() {
   if (g_side_stream) return D3FK_OK;
@@ -231,17 +236,55 @@ static int ensure_side_stream() {
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g_join_events[i], cudaEventDisableTiming);
   }
   for (int i = 0; i < 64 && e == cudaSuccess; ++i) { e = cudaEventCreateWithFlags(&g_fork_events[i], cudaEventDisableTiming); g_n_fork_events = i + 1; }
+  for (int i = 0; i < D3FK_MAX_LANES && e == cudaSuccess; ++i) {   // branch lanes: default priority, like the caller's stream
+    e = cudaStreamCreateWithPriority(&g_lane_streams[i], cudaStreamNonBlocking, 0);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g_lane_events[i], cudaEventDisableTiming);
+  }
   if (e != cudaSuccess) return set_error(D3FK_ERR_CUDA, "cudaEventCreate: %s", cudaGetErrorString(e));
   return D3FK_OK;
 }
 
-static int run_list(const d3fk_op* ops, int n_ops, cudaStream_t s, bool join) {
+
+static int lane_join(int lane, cudaStream_t main, bool* open) {
+  if (lane < 1 || lane > D3FK_MAX_LANES) return set_error(D3FK_ERR_ARG, "join: lane %d out of range", lane);
+  if (!open[lane - 1]) return D3FK_OK;
+  cudaError_t e = cudaEventRecord(g_lane_events[lane - 1], g_lane_streams[lane - 1]);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(main, g_lane_events[lane - 1], 0);
+  if (e != cudaSuccess) return set_error(D3FK_ERR_CUDA, "lane join: %s", cudaGetErrorString(e));
+  open[lane - 1] = false;
+  return D3FK_OK;
+}
+
+static int run_list(const d3fk_op* ops, int n_ops, cudaStream_t main_stream, bool join) {
   int rc = require_init();
   if (rc) return rc;
   rc = ensure_side_stream();
   if (rc) return rc;
   int forks = 0;
+  bool lane_open[D3FK_MAX_LANES] = {false};
   for (int i = 0; i < n_ops; ++i) {
+    if (ops[i].kind == D3FK_OP_JOIN) {
+      rc = lane_join((int)ops[i].u.misc.n, main_stream, lane_open);
+      if (rc) return rc;
+      continue;
+    }
+    cudaStream_t s = main_stream;
+    const int lane = ops[i].lane;
+    if (lane != 0) {
+      if (lane < 1 || lane > D3FK_MAX_LANES) return set_error(D3FK_ERR_ARG, "op %d: lane %d out of range", i, lane);
+      if (!g_fork_lanes) {
+        // D3FK_FORK_WGRAD=0 (everything in stream order) also keeps the branches on the main stream
+      } else {
+        s = g_lane_streams[lane - 1];
+        if (!lane_open[lane - 1]) {            // fork: the branch starts behind what the main stream holds now
+          cudaEvent_t ev = g_fork_events[g_fork_cursor++ % g_n_fork_events];
+          cudaError_t e = cudaEventRecord(ev, main_stream);
+          if (e == cudaSuccess) e = cudaStreamWaitEvent(s, ev, 0);
+          if (e != cudaSuccess) return set_error(D3FK_ERR_CUDA, "lane fork: %s", cudaGetErrorString(e));
+          lane_open[lane - 1] = true;
+        }
+      }
+    }
     const bool is_wgrad = ops[i].kind == D3FK_OP_WGRAD || ops[i].kind == D3FK_OP_WGRAD_GROUP;
 #ifdef D3FK_DEBUG
     if (is_wgrad && g_skip_wgrad) continue;   // timing experiment only (D3FK_SKIP_WGRAD=1)
@@ -264,8 +307,12 @@ static int run_list(const d3fk_op* ops, int n_ops, cudaStream_t s, bool join) {
       return set_error(rc, "op %d (kind %d): %s", i, ops[i].kind, tmp);
     }
   }
+  for (int l = 1; l <= D3FK_MAX_LANES; ++l) {      // a branch the list left open ends with the list
+    rc = lane_join(l, main_stream, lane_open);
+    if (rc) return rc;
+  }
   if (forks) g_side_pending = true;
-  if (join && g_side_pending) return d3fk_side_stream_join((d3fk_stream)s);
+  if (join && g_side_pending) return d3fk_side_stream_join((d3fk_stream)main_stream);
   return D3FK_OK;
 }
 

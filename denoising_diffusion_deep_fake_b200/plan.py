@@ -26,6 +26,9 @@ FUSE_BN_BWD_MAX_ELEMS = (1 << 62) if _f == 1 else _f
 # hidden behind the latency-bound main chain either way, and the last group lengthens the tail) - opt-in.
 GROUP_WGRAD = os.environ.get("D3FK_WGRAD_GROUP", "0") == "1"
 
+# The downsample branch of a stage's first block on a branch stream of d3fk_run (0: everything on the main chain).
+BRANCH_LANE = int(os.environ.get("D3FK_BRANCH_LANE", "1"))
+
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
 SPLITK_WS_BYTES = 64 << 20
@@ -296,13 +299,15 @@ class UnetPlan:
         return f
 
     def _conv_op(self, c, src0, src1=None, up0=0, out=None, relu=0, res=None, stats=False, out_nchw=None,
-                 affine=False):
+                 affine=False, lane=0):
         f = self._conv_fields(c, src0, src1, up0, out, relu, res, stats, out_nchw, affine)
-        return make_op(_lib.OP_CONV, **f), f["Ho"], f["Wo"]
+        return make_op(_lib.OP_CONV, lane=lane, **f), f["Ho"], f["Wo"]
 
-    def _conv_bn_act(self, ops, c, src0, src1=None, up0=0, relu=1, res=None):
+    def _conv_bn_act(self, ops, c, src0, src1=None, up0=0, relu=1, res=None, lane=0):
         """conv -> BN -> (+res) -> ReLU.  Train: raw conv output + batch statistics in the conv epilogue,
-        finalize, one fused apply pass.  Eval: BN folded into the conv epilogue.  Returns the activation."""
+        finalize, one fused apply pass.  Eval: BN folded into the conv epilogue.  Returns the activation.
+        lane != 0: the op runs on a branch stream of d3fk_run (always in its two-kernel form: a branch never waits on a
+        grid-wide barrier)."""
         Hi = src0.H * (2 if up0 else 1)
         Ho = (Hi + 2 * c.pad - c.k) // c.stride + 1
         Wi = src0.W * (2 if up0 else 1)
@@ -310,7 +315,7 @@ class UnetPlan:
         act = T(self, self.B, Ho, Wo, c.cout)
         self.keep.append(act.t)
         if not self.training:
-            op, _, _ = self._conv_op(c, src0, src1, up0, out=act, relu=relu, res=res, affine=True)
+            op, _, _ = self._conv_op(c, src0, src1, up0, out=act, relu=relu, res=res, affine=True, lane=lane)
             ops.append(op)
             return act
         raw = T(self, self.B, Ho, Wo, c.cout)
@@ -322,7 +327,8 @@ class UnetPlan:
             bn.update(res=res.ptr, ldr=res.ld)
         fwd_fields = {k: v for k, v in bn.items() if k not in ("bstats", "coef")}
         # ONE op: conv + BN finalize + normalise (+residual) + ReLU — fused into the conv kernel where the layer qualifies
-        ops.append(make_op(_lib.OP_CONV_BN, conv=conv_fields, bn=fwd_fields, barrier=self.bn_barrier[c.bn]))
+        ops.append(make_op(_lib.OP_CONV_BN, lane=lane, conv=conv_fields, bn=fwd_fields,
+                           barrier=None if lane else self.bn_barrier[c.bn]))
         self.saved[c.name] = dict(src0=src0, src1=src1, up0=up0, raw=raw, act=act, relu=relu, bn=bn, res=res)
         return act
 
@@ -348,14 +354,15 @@ class UnetPlan:
         self.block_io = []
         for blocks in self.stages:
             for b in blocks:
-                a1 = self._conv_bn_act(ops, b["conv1"], x)
                 idn = x
                 if b["down"] is not None:
-                    idn = self._conv_bn_act(ops, b["down"], x, relu=0)
-                if self.training:
-                    out = self._conv_bn_act(ops, b["conv2"], a1, relu=1, res=idn)
-                else:
-                    out = self._conv_bn_act(ops, b["conv2"], a1, relu=1, res=idn)
+                    # the 1x1 / stride-2 downsample branch is independent of conv1 -> BN -> ReLU until the residual add
+                    # (torchvision BasicBlock.forward, resnet.py:89-105): it runs on branch lane 1, next to conv1
+                    idn = self._conv_bn_act(ops, b["down"], x, relu=0, lane=BRANCH_LANE)
+                a1 = self._conv_bn_act(ops, b["conv1"], x)
+                if b["down"] is not None and BRANCH_LANE:
+                    ops.append(make_op(_lib.OP_JOIN, n=BRANCH_LANE))
+                out = self._conv_bn_act(ops, b["conv2"], a1, relu=1, res=idn)
                 self.block_io.append((b, x, a1, idn, out))
                 x = out
             feats.append(x)
@@ -394,7 +401,7 @@ class UnetPlan:
     def _gptr(self, name):
         return self.grad_arena.data_ptr() + 4 * self.grad_offsets[name]
 
-    def _wgrad_op(self, c, src0, src1, up0, dy, cout_buf=None):
+    def _wgrad_op(self, c, src0, src1, up0, dy, cout_buf=None, lane=0):
         Hi = src0.H * (2 if up0 else 1)
         Wi = src0.W * (2 if up0 else 1)
         f = dict(dtype=self.dtype, src0=src0.ptr, c0=src0.C, ld0=src0.ld, up0=up0, B=self.B, Hi=Hi, Wi=Wi,
@@ -402,7 +409,7 @@ class UnetPlan:
                  Cout=dy.C, cin_real=c.cin, cout_real=c.cout, dw=self._gptr(c.name + ".weight"))
         if src1 is not None:
             f.update(src1=src1.ptr, c1=src1.C, ld1=src1.ld)
-        return make_op(_lib.OP_WGRAD, **f)
+        return make_op(_lib.OP_WGRAD, lane=lane, **f)
 
     def _wgrad_encoder(self, ops, pending, c, src, dy):
         """Weight gradient of an encoder convolution.  The 3x3 / stride-1 / Cin == Cout convolutions of a ResNet stage are
@@ -431,7 +438,7 @@ class UnetPlan:
                                dw=[self._gptr(c2.name + ".weight") for c2, _, _ in pending]))
         pending.clear()
 
-    def _dgrad_op(self, c, dy, out, res=None, row0=0, rows=None):
+    def _dgrad_op(self, c, dy, out, res=None, row0=0, rows=None, lane=0):
         """dX (= out, channels [row0, row0+rows) of the conv input) from dY through conv c."""
         cout_pad = dy.C
         rows = out.C if rows is None else rows
@@ -444,9 +451,9 @@ class UnetPlan:
             f.update(ws=self.ws.data_ptr(), ws_bytes=SPLITK_WS_BYTES)
         if res is not None:
             f.update(res=res.ptr, ldr=res.ld)
-        return make_op(_lib.OP_CONV, **f)
+        return make_op(_lib.OP_CONV, lane=lane, **f)
 
-    def _bn_bwd(self, ops, c, g_act, want_dres=False):
+    def _bn_bwd(self, ops, c, g_act, want_dres=False, lane=0):
         """Backward through BN(+ReLU) of conv c given grad wrt its activation.  Returns (d_raw, g_masked)."""
         sv = self.saved[c.name]
         raw, act = sv["raw"], sv["act"]
@@ -473,12 +480,12 @@ class UnetPlan:
             pp.bw_act, pp.bw_ldact = act.ptr, act.ld
             pp.bw_mean, pp.bw_invstd = bn["mean"], bn["invstd"]
             pp.bw_relu = bn["relu"]
-            ops.append(make_op(_lib.OP_BN_BWD_APPLY, **bn))
+            ops.append(make_op(_lib.OP_BN_BWD_APPLY, lane=lane, **bn))
         else:
             # reduce + apply as ONE op; the apply phase derives its coefficients and writes dgamma / dbeta.  The barrier
-            # counter (one-kernel form, opt-in) is cleared by the backward's statistics memset.
-            bn["barrier"] = self.bn_barrier[c.bn] + self.stats.stride(0) * 8
-            ops.append(make_op(_lib.OP_BN_BWD, **bn))
+            # counter (one-kernel form, opt-in) is cleared by the backward's statistics memset.  Branch lanes: two kernels.
+            bn["barrier"] = None if lane else self.bn_barrier[c.bn] + self.stats.stride(0) * 8
+            ops.append(make_op(_lib.OP_BN_BWD, lane=lane, **bn))
         return d_raw, g_masked
 
     def _newT(self, like, C=None, H=None, W=None):
@@ -509,18 +516,18 @@ class UnetPlan:
         self._grad_producer[id(g)] = ops[-1]
         grad = {id(self.dec_out): g}   # activation buffer -> its (so far accumulated) gradient buffer
 
-        def add_grad(ops, conv, dy, target, row0=0, rows=None, tmp=None):
+        def add_grad(ops, conv, dy, target, row0=0, rows=None, tmp=None, lane=0):
             """dgrad of `conv` into the gradient of `target` (accumulating if one exists)."""
             if tmp is not None:
-                ops.append(self._dgrad_op(conv, dy, tmp, row0=row0, rows=rows))
+                ops.append(self._dgrad_op(conv, dy, tmp, row0=row0, rows=rows, lane=lane))
                 return
             if id(target) in grad:
                 gbuf = grad[id(target)]
-                ops.append(self._dgrad_op(conv, dy, gbuf, res=gbuf, row0=row0, rows=rows))
+                ops.append(self._dgrad_op(conv, dy, gbuf, res=gbuf, row0=row0, rows=rows, lane=lane))
             else:
                 gbuf = self._newT(target)
                 grad[id(target)] = gbuf
-                ops.append(self._dgrad_op(conv, dy, gbuf, row0=row0, rows=rows))
+                ops.append(self._dgrad_op(conv, dy, gbuf, row0=row0, rows=rows, lane=lane))
             self._grad_producer[id(gbuf)] = ops[-1]
 
         # ---- decoder, last block first
@@ -556,14 +563,19 @@ class UnetPlan:
         for bi in range(len(self.block_io) - 1, -1, -1):
             b, x, a1, idn, out = self.block_io[bi]
             d_r2, g_masked = self._bn_bwd(ops, b["conv2"], grad[id(out)], want_dres=True)
+            if b["down"] is not None:
+                # the downsample branch (BN backward, weight gradient, dgrad into a fresh grad[x]) on branch lane 1, next
+                # to the conv2 -> conv1 chain; the chain's last dgrad accumulates onto it behind the join
+                d_rd, _ = self._bn_bwd(ops, b["down"], g_masked, lane=BRANCH_LANE)
+                ops.append(self._wgrad_op(b["down"], x, None, 0, d_rd, lane=BRANCH_LANE))
+                add_grad(ops, b["down"], d_rd, x, lane=BRANCH_LANE)
             self._wgrad_encoder(ops, pending, b["conv2"], a1, d_r2)
             add_grad(ops, b["conv2"], d_r2, a1)
             d_r1, _ = self._bn_bwd(ops, b["conv1"], grad[id(a1)])
             self._wgrad_encoder(ops, pending, b["conv1"], x, d_r1)
             if b["down"] is not None:
-                d_rd, _ = self._bn_bwd(ops, b["down"], g_masked)
-                ops.append(self._wgrad_op(b["down"], x, None, 0, d_rd))
-                add_grad(ops, b["down"], d_rd, x)
+                if BRANCH_LANE:
+                    ops.append(make_op(_lib.OP_JOIN, n=BRANCH_LANE))
                 add_grad(ops, b["conv1"], d_r1, x)
             else:
                 assert id(x) not in grad

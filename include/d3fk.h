@@ -266,12 +266,20 @@ enum d3fk_op_kind {
   D3FK_OP_FRAMES_TO_TENSOR = 26, D3FK_OP_TENSOR_TO_FRAMES = 27,   /* frames params */
   D3FK_OP_AFFINE_QSAMPLE = 28,
   D3FK_OP_SET_SCALARS = 29,   /* scalars params */
+  D3FK_OP_JOIN = 30,          /* misc params: n = lane to join back into the main stream */
   D3FK_OP_WGRAD_GROUP = 25,   /* wgrad_group params; forked onto the side streams like D3FK_OP_WGRAD */
   D3FK_OP_BN_BWD = 24    /* bn params: bn_bwd_reduce + bn_bwd_apply as one op (one kernel behind a grid barrier when `barrier` is set) */
 };
 
+/* `lane`: 0 = the caller's stream (the main chain).  lane 1..D3FK_MAX_LANES = an internal branch stream: the op runs there,
+ * ordered behind everything the main stream held when the branch's first op was reached (fork), and the main stream picks
+ * the branch up again at D3FK_OP_JOIN (misc.n = lane; any lane still open at the end of the list is joined there).  Used
+ * for the 1x1 / stride-2 downsample branch of a ResNet stage's first block, which is independent of the block's conv1 ->
+ * BN -> ReLU chain until the residual add (torchvision BasicBlock.forward, resnet.py:89-105).  Branch ops never wait on a
+ * grid-wide barrier (the plans emit their two-kernel forms), so two co-scheduled kernels cannot deadlock on residency. */
+#define D3FK_MAX_LANES 2
 typedef struct d3fk_op {
-  int32_t kind, _pad;
+  int32_t kind, lane;
   union {
     d3fk_conv_params conv; d3fk_wgrad_params wgrad; d3fk_pack_params pack; d3fk_bn_params bn;
     d3fk_pool_params pool; d3fk_layout_params layout; d3fk_chansum_params chansum;

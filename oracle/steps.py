@@ -44,7 +44,7 @@ def training_swap_step_for_one_model(real, real_model, fake_model, criterion, la
                       real_prediction=real_prediction)
 
 
-def short_training_run(ref, sd0, steps, batch=16, device="cpu", lam=5.0, lr=0.02):
+def short_training_run(ref, sd0, steps, batch=16, device="cpu", lam=5.0, lr=0.02, size=64, seed0=100):
     """State dict after `steps` reference training steps on synthetic faces (Adam lr 0.02, lambda 5:
     d3f/train_denoiser/denoiser_config.yml:3,8), starting from state `sd0` of oracle network `ref` (not modified).
     The parity tests use it to leave the chaotic random-init regime: BatchNorm over freshly initialised weights amplifies
@@ -59,8 +59,8 @@ def short_training_run(ref, sd0, steps, batch=16, device="cpu", lam=5.0, lr=0.02
     opt = torch.optim.Adam(m.parameters(), lr=lr)
     gen = torch.Generator(device=device).manual_seed(1)
     for i in range(steps):
-        g = torch.Generator(device=device).manual_seed(100 + i)
-        x = F.avg_pool2d(0.5 * torch.randn(batch, 3, 64, 64, generator=g, device=device), 5, 1, 2).mul(2.5).clamp(-1, 1)
+        g = torch.Generator(device=device).manual_seed(seed0 + i)
+        x = F.avg_pool2d(0.5 * torch.randn(batch, 3, size, size, generator=g, device=device), 5, 1, 2).mul(2.5).clamp(-1, 1)
         loss, _ = denoiser_training_step(m, crit, x, lam, generator=gen)
         opt.zero_grad()
         loss.backward()

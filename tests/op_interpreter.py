@@ -295,4 +295,6 @@ _DISPATCH = {
 
 def run_ops(oplist):
     for op in oplist:
+        if op.kind == _lib.OP_JOIN:          # stream bookkeeping only: the interpreter runs every lane in list order
+            continue
         _DISPATCH[op.kind](_lib.op_params(op))
