@@ -26,6 +26,16 @@ struct SlabSched {
   int chunks, ctot;       // 64-channel chunks per tap when Cin > 64 (each chunk is one pipeline stage); total Cin
   uint32_t layout;        // UMMA smem-descriptor layout type: 2 = SWIZZLE_128B, 4 = 64B, 6 = 32B
   int M;                  // B*H*W
+  // FLAT variant (flat != 0): ONE slab per stage instead of three column-shifted ones.  The slab is the (RT + 2) x Wp
+  // pixel box (Wp = Wt + 2: one halo column on each side, zero filled by TMA at the image border) kept as a flat list of
+  // pixel rows; an M tile is 128 CONSECUTIVE slab positions q = r * Wp + w, so that tap (kh, kw) of every row of the tile
+  // is the same flat offset kh * Wp + kw — a start-address shift of the UMMA descriptor by whole pixel rows (not a
+  // multiple of the 8-row swizzle atom: the descriptor's base-offset field carries the phase).  The two halo positions
+  // per image row compute junk that the epilogue drops; activations are read 1.3x instead of 3.75x.
+  int flat, Wp, RT;       // RT: image rows per super-tile
+  uint32_t bo_mode;       // 1: descriptor base offset = (start address >> 7) & 7; 0: leave it zero
+  uint32_t ablate;        // -DD3FK_DEBUG builds only (D3FK_SLAB_ABLATE): 1 = no epilogue work, 2 = no MMAs, 4 = no TMA data
+  FastDiv dWp;
 };
 
 __device__ __forceinline__ uint64_t make_smem_desc_sw(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout) {
@@ -59,11 +69,12 @@ __global__ void __launch_bounds__(SlabCfg<BN>::THREADS) conv_slab_kernel(const _
   const uint32_t w_base = base;                                         // [9 taps][chunks][BN rows][row_bytes]
   const uint32_t w_bytes = (uint32_t)((9 * ss.chunks * ss.w_tile_bytes + 1023) & ~1023);
   const uint32_t slab_base = base + w_bytes;                            // [stages][3][slab_bytes]
-  const uint32_t stage_bytes = 3u * ss.slab_bytes;
+  const uint32_t stage_bytes = (ss.flat ? 1u : 3u) * ss.slab_bytes;
   const uint32_t bar_base = slab_base + ss.stages * stage_bytes;        // full[4], empty[4], acc_full[2], acc_empty[2], wbar
   uint8_t* gen_bar = smem_raw + (bar_base - smem_u32(smem_raw));
   volatile uint32_t* tmem_ptr_slot = reinterpret_cast<volatile uint32_t*>(gen_bar + 8 * 13);
   float* s_stat = reinterpret_cast<float*>(gen_bar + 128);              // [4 warps][2][BN]
+  float* s_aff = s_stat + 8 * BN;                                       // [2][BN] staged scale / shift (eval: folded BN; head: bias)
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (4 + s); };
   auto acc_full_bar = [&](int b) { return bar_base + 8u * (8 + b); };
@@ -114,7 +125,7 @@ __global__ void __launch_bounds__(SlabCfg<BN>::THREADS) conv_slab_kernel(const _
       for (int t = 0; t < 9; ++t)
         for (int c = 0; c < ss.chunks; ++c)
           tma_load_2d(w_base + (t * ss.chunks + c) * ss.w_tile_bytes, &tmB, t * ss.ctot + c * cch, 0, wbar);
-      const int rows = S * ss.R;
+      const int rows = ss.flat ? ss.RT : S * ss.R;
       // pipeline position over (super-tile, chunk) pairs as running counters: stage index, parity of the round, and whether
       // the ring has wrapped (a run-time `it % stages` / `it / stages` is a ~20-instruction sequence in every role's loop)
       int st = 0;
@@ -127,9 +138,19 @@ __global__ void __launch_bounds__(SlabCfg<BN>::THREADS) conv_slab_kernel(const _
         const int h0 = hb * rows, w0 = (rem - hb * ss.wtiles) * ss.Wt;
         for (int c = 0; c < ss.chunks; ++c) {
           if (wrapped) mbar_wait(empty_bar(st), round_par ^ 1u, errflag);
-          mbar_arrive_expect_tx(full_bar(st), 3u * ss.slab_tx);
-          for (int sx = 0; sx < 3; ++sx)
-            tma_load_4d(slab_base + st * stage_bytes + sx * ss.slab_bytes, &tmA, c * cch, w0 + sx - 1, h0 - 1, n, full_bar(st));
+#ifdef D3FK_DEBUG
+          if (ss.ablate & 4u) {
+            mbar_arrive_expect_tx(full_bar(st), 0u);
+          } else
+#endif
+          if (ss.flat) {
+            mbar_arrive_expect_tx(full_bar(st), (uint32_t)ss.slab_tx);
+            tma_load_4d(slab_base + st * stage_bytes, &tmA, c * cch, w0 - 1, h0 - 1, n, full_bar(st));
+          } else {
+            mbar_arrive_expect_tx(full_bar(st), 3u * ss.slab_tx);
+            for (int sx = 0; sx < 3; ++sx)
+              tma_load_4d(slab_base + st * stage_bytes + sx * ss.slab_bytes, &tmA, c * cch, w0 + sx - 1, h0 - 1, n, full_bar(st));
+          }
           if (++st == ss.stages) { st = 0; round_par ^= 1u; wrapped = true; }
         }
       }
@@ -154,10 +175,12 @@ __global__ void __launch_bounds__(SlabCfg<BN>::THREADS) conv_slab_kernel(const _
         const int kh = tap / 3, kw = tap - kh * 3;
         const int sy = ss.sgn > 0 ? kh : 2 - kh;
         const int sx = ss.sgn > 0 ? kw : 2 - kw;
-        a_off[tap] = ((uint32_t)(sx * ss.slab_bytes) >> 4) + (uint32_t)(sy + my_s * ss.R) * img_row16;
+        a_off[tap] = ss.flat ? ((uint32_t)((my_s * TC_BM + sy * ss.Wp + sx) * ss.row_bytes) >> 4)
+                             : ((uint32_t)(sx * ss.slab_bytes) >> 4) + (uint32_t)(sy + my_s * ss.R) * img_row16;
         b_lo[tap] = dlo | ((w_base + (uint32_t)(tap * ss.chunks * ss.w_tile_bytes)) >> 4);
       }
       const uint32_t wchunk16 = (uint32_t)ss.w_tile_bytes >> 4;
+      const uint32_t bo_shift = ss.row_bytes == 128 ? 3u : ss.row_bytes == 64 ? 2u : 1u;   // bo_mode 2 (experiment): row index
       const bool active = my_p < P;                     // S * P == NW: always true; kept for clarity
       mbar_wait(wbar, 0, errflag);
       uint32_t tile_it = 0;
@@ -174,13 +197,21 @@ __global__ void __launch_bounds__(SlabCfg<BN>::THREADS) conv_slab_kernel(const _
           tc_fence_after();
           const uint32_t sub_lo = dlo | ((slab_base + st * stage_bytes) >> 4);
           const uint32_t bc = (uint32_t)c * wchunk16;
+#ifdef D3FK_DEBUG
+          if (active && !(ss.ablate & 2u)) {
+#else
           if (active) {
+#endif
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
               if ((tap & pmask) == my_p) {              // P in {1, 2, 4}
 #pragma unroll
                 for (int kk = 0; kk < KSTEPS; ++kk) {
-                  umma_f16_lohi_p(d_addr, sub_lo + a_off[tap] + 2u * kk, dhi, b_lo[tap] + bc + 2u * kk, dhi, idesc, first, leader);
+                  const uint32_t a_lo = sub_lo + a_off[tap] + 2u * kk;
+                  // base offset (descriptor bits 49-51): the phase of the start address within the 8-row swizzle pattern
+                  const uint32_t a_hi = ss.bo_mode == 1 ? (dhi | (((a_lo >> 3) & 7u) << 17))
+                                      : ss.bo_mode == 2 ? (dhi | (((a_lo >> bo_shift) & 7u) << 17)) : dhi;
+                  umma_f16_lohi_p(d_addr, a_lo, a_hi, b_lo[tap] + bc + 2u * kk, dhi, idesc, first, leader);
                   first = 1u;
                 }
               }
@@ -199,6 +230,14 @@ __global__ void __launch_bounds__(SlabCfg<BN>::THREADS) conv_slab_kernel(const _
     // sub-tile, so it accumulates its own per-column sums over the whole kernel and the 128 rows are folded ONCE at
     // the end (instead of a shuffle transpose-reduce per tile).
     constexpr bool REG_STATS = BN <= 32;
+    const bool affine = e.scale != nullptr || e.shift != nullptr;
+    if (affine) {                    // after griddepcontrol.wait: whatever produced scale / shift has completed
+      if (tid < BN) {
+        s_aff[tid] = e.scale ? (tid < e.Cout ? __ldg(e.scale + tid) : 0.f) : 1.f;
+        s_aff[BN + tid] = tid < e.Cout ? __ldg(e.shift + tid) : 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
     float rs[REG_STATS ? BN : 1], rq[REG_STATS ? BN : 1];
 #pragma unroll
     for (int i = 0; i < (REG_STATS ? BN : 1); ++i) { rs[i] = 0.f; rq[i] = 0.f; }
@@ -209,19 +248,41 @@ __global__ void __launch_bounds__(SlabCfg<BN>::THREADS) conv_slab_kernel(const _
       const int n = t / ss.tiles_per_img;
       const int rem = t - n * ss.tiles_per_img;
       const int hb = rem / ss.wtiles;
-      const int h0 = hb * S * ss.R, w0 = (rem - hb * ss.wtiles) * ss.Wt;
+      const int h0 = hb * (ss.flat ? ss.RT : S * ss.R), w0 = (rem - hb * ss.wtiles) * ss.Wt;
       mbar_wait(acc_full_bar(abuf), (it >> 1) & 1, errflag);
       tc_fence_after();
+#ifdef D3FK_DEBUG
+      if (ss.ablate & 1u) {
+        tc_fence_before();
+        mbar_arrive(acc_empty_bar(abuf));
+        continue;
+      }
+#endif
       for (int s = 0; s < S; ++s) {
-        const long long m = ((long long)n * ss.H + h0 + s * ss.R) * ss.W + w0 + row;   // 128 consecutive pixels
-        const bool row_ok = m < ss.M;
+        long long m;
+        bool row_ok;
         int on = 0, oh = 0, ow = 0;
-        if (e.out_nchw && row_ok) {
-          const uint32_t q = fdiv((uint32_t)m, dWo);
-          ow = (int)m - (int)q * e.Wo;
-          on = (int)fdiv(q, dHo);
-          oh = (int)q - on * e.Ho;
+        if (ss.flat) {
+          // slab position q = r * Wp + w of this accumulator row; the columns w >= Wt are the halo positions (junk)
+          const uint32_t q = (uint32_t)(s * TC_BM + row);
+          const int r = (int)fdiv(q, ss.dWp);
+          const int w = (int)q - r * ss.Wp;
+          row_ok = w < ss.Wt && r < ss.RT && h0 + r < ss.H && w0 + w < ss.W;
+          m = ((long long)n * ss.H + h0 + r) * ss.W + w0 + w;
+          on = n; oh = h0 + r; ow = w0 + w;
+        } else {
+          m = ((long long)n * ss.H + h0 + s * ss.R) * ss.W + w0 + row;   // 128 consecutive pixels
+          row_ok = m < ss.M;
+          if (e.out_nchw && row_ok) {
+            const uint32_t q = fdiv((uint32_t)m, dWo);
+            ow = (int)m - (int)q * e.Wo;
+            on = (int)fdiv(q, dHo);
+            oh = (int)q - on * e.Ho;
+          }
         }
+        // (Tried and dropped: software-pipelining the TMEM reads — the next chunk's tcgen05.ld in flight while this one is
+        // stored — with 16-column chunks to make room for the second register buffer: 5-100 % SLOWER on every layer, the
+        // extra chunk iterations and register pressure cost more than the exposed load latency.)
 #pragma unroll
         for (int cc = 0; cc < BN; cc += CW) {
           uint32_t raw[CW];
@@ -238,14 +299,14 @@ __global__ void __launch_bounds__(SlabCfg<BN>::THREADS) conv_slab_kernel(const _
             for (int i = 0; i < CW; ++i) f[i] += __uint_as_float(raw[i]);
           }
           epilogue_chunk<CW>(f, e, m, row_ok, cc, on, oh, ow, do_stats && !REG_STATS, s_stat + warp * 2 * BN + cc,
-                             s_stat + warp * 2 * BN + BN + cc, lane);
+                             s_stat + warp * 2 * BN + BN + cc, lane, affine ? s_aff + cc : nullptr, BN);
           if (REG_STATS && do_stats) {
             if (e.bw_x) {
               float sq[CW];
               bw_stat_terms<CW>(f, sq, e, m, row_ok, cc);
 #pragma unroll
               for (int i = 0; i < CW; ++i) { rs[cc + i] += f[i]; rq[cc + i] += sq[i]; }
-            } else {
+            } else if (row_ok) {
 #pragma unroll
               for (int i = 0; i < CW; ++i) { rs[cc + i] += f[i]; rq[cc + i] = fmaf(f[i], f[i], rq[cc + i]); }
             }
@@ -287,6 +348,14 @@ __global__ void __launch_bounds__(SlabCfg<BN>::THREADS) conv_slab_kernel(const _
 }
 
 static int g_use_slab = 1;   // D3FK_SLAB=0: never take the slab path
+static int g_slab_flat = 0;        // flat (single-slab) variant — 1: whenever W >= min_w; 0: only for sizes the three-slab layout
+                                   // cannot take (ragged W / H); -1: never.  Correct for every swizzle width, but measured NOT
+                                   // faster than the three-slab layout on B200 (these kernels are not load-bound)
+static int g_slab_flat_min_w = 32; // narrower images: the halo positions would waste too many accumulator rows
+static int g_slab_bo = 0;          // descriptor base-offset field of the flat variant: measured on B200 — the swizzle is a
+                                   // function of the absolute shared-memory address, a start address shifted by whole pixel
+                                   // rows needs NO base offset (mode 0 exact for SWIZZLE_32B/64B/128B; modes 1, 2 wrong)
+static int g_slab_ablate = 0;      // D3FK_SLAB_ABLATE (debug builds): SlabSched::ablate
 
 // Slab-path eligibility and geometry.  Returns false when the generic kernels must be used.
 static bool slab_plan(const Gather& g, const d3fk_conv_params* p, int BN, SlabSched& ss, int& smem) {
@@ -295,13 +364,8 @@ static bool slab_plan(const Gather& g, const d3fk_conv_params* p, int BN, SlabSc
   if (p->Ho != p->Hi || p->Wo != p->Wi) return false;
   const int C = g.ctot, W = p->Wi, H = p->Hi;
   if (C != 16 && C != 32 && C != 64 && C != 128) return false;   // 128 = two 64-channel chunks (one pipeline stage each)
-  if (W != 16 && W != 32 && W != 64 && (W % 128)) return false;
   if (p->Cout > BN || (!p->out_nchw && p->Cout != BN)) return false;
   if (((uintptr_t)p->src0 & 15) || (g.ld0 % 8)) return false;
-  const int Wt = W < TC_BM ? W : TC_BM;
-  const int R = TC_BM / Wt;
-  if (H % R) return false;
-  ss.W = W; ss.H = H; ss.R = R; ss.Wt = Wt; ss.wtiles = W / Wt;
   const int cch = C > 64 ? 64 : C;
   ss.chunks = C / cch;
   ss.ctot = C;
@@ -311,14 +375,52 @@ static bool slab_plan(const Gather& g, const d3fk_conv_params* p, int BN, SlabSc
   ss.w_tile_bytes = BN * ss.row_bytes;
   ss.sgn = p->mode ? -1 : 1;
   ss.M = g.M;
+  ss.ablate = (uint32_t)g_slab_ablate;
   const int w_bytes = (9 * ss.chunks * ss.w_tile_bytes + 1023) & ~1023;
-  // largest super-tile whose double-buffered accumulators fit TMEM and whose 2-stage slabs fit shared memory
   const int NW = BN >= 128 ? 2 : 4;                    // MMA warps (SlabCfg<BN>::NW): S must divide it
+  const int Wt_l = W < TC_BM ? W : TC_BM;
+  const bool legacy_ok = (W == 16 || W == 32 || W == 64 || W % 128 == 0) && H % (TC_BM / Wt_l) == 0;
+  if ((g_slab_flat > 0 || (g_slab_flat == 0 && !legacy_ok)) && W >= g_slab_flat_min_w) {
+    // FLAT variant: one (RT + 2) x (Wt + 2) slab per stage, M tiles over consecutive slab positions (see SlabSched).  Any
+    // H and W: ragged tiles are masked in the epilogue, out-of-image rows / columns are TMA zero fill.
+    const int Wt = W < TC_BM ? W : TC_BM, Wp = Wt + 2;
+    ss.W = W; ss.H = H; ss.Wt = Wt; ss.Wp = Wp; ss.wtiles = cdiv(W, Wt); ss.R = 1;
+    ss.flat = 1; ss.bo_mode = (uint32_t)g_slab_bo; ss.dWp = make_fastdiv((uint32_t)Wp);
+    for (int S = NW; S >= 1; S >>= 1) {
+      const int rt_max = (S * TC_BM - Wt) / Wp + 1;   // last valid position (RT - 1) * Wp + Wt - 1 < S * 128
+      if (S * TC_BM < Wt || rt_max < 1) continue;
+      const int T = cdiv(H, rt_max), RT = cdiv(H, T);     // balanced row split of the image
+      const int used = cdiv((RT - 1) * Wp + Wt, TC_BM);    // sub-tiles that hold valid positions
+      if (S > 1 && used <= S / 2) continue;                // a smaller super-tile does the same work
+      const int rows_loaded = (RT + 2) * Wp;
+      const int rows_read = S * TC_BM + 2 * Wp + 2;        // the furthest (junk) row a tap of the last sub-tile touches
+      const int slab = ((rows_loaded > rows_read ? rows_loaded : rows_read) * ss.row_bytes + 1023) & ~1023;
+      for (int stages = 4; stages >= 2; --stages) {
+        const int need = 1024 + w_bytes + stages * slab + 128 + 10 * BN * 4;
+        if (need > SLAB_MAX_SMEM) continue;
+        ss.S = S; ss.RT = RT;
+        ss.slab_bytes = slab;
+        ss.slab_tx = rows_loaded * ss.row_bytes;
+        ss.stages = stages;
+        ss.tiles_per_img = T * ss.wtiles;
+        ss.total = p->B * ss.tiles_per_img;
+        smem = need;
+        return true;
+      }
+    }
+    ss.flat = 0;
+  }
+  if (W != 16 && W != 32 && W != 64 && (W % 128)) return false;
+  const int Wt = W < TC_BM ? W : TC_BM;
+  const int R = TC_BM / Wt;
+  if (H % R) return false;
+  ss.W = W; ss.H = H; ss.R = R; ss.Wt = Wt; ss.wtiles = W / Wt;
+  // largest super-tile whose double-buffered accumulators fit TMEM and whose 2-stage slabs fit shared memory
   for (int S = NW; S >= 1; S >>= 1) {
     if (H % (S * R)) continue;
     const int slab = ((S * R + 2) * Wt * ss.row_bytes + 1023) & ~1023;
     for (int stages = 3; stages >= 2; --stages) {
-      const int need = 1024 + w_bytes + stages * 3 * slab + 128 + 8 * BN * 4;
+      const int need = 1024 + w_bytes + stages * 3 * slab + 128 + 10 * BN * 4;
       if (need > SLAB_MAX_SMEM) continue;
       ss.S = S;
       ss.slab_bytes = slab;
@@ -350,6 +452,7 @@ static int launch_conv_slab_bn(const Gather& g, const d3fk_conv_params* p, cudaS
     uint64_t dims[4] = {(uint64_t)C, (uint64_t)g.Wi, (uint64_t)g.Hi, (uint64_t)g.B};
     uint64_t strides[3] = {(uint64_t)g.ld0 * 2, (uint64_t)g.Wi * g.ld0 * 2, (uint64_t)g.Hi * g.Wi * g.ld0 * 2};
     uint32_t bx[4] = {(uint32_t)(ss.row_bytes >> 1), (uint32_t)ss.Wt, (uint32_t)(ss.S * ss.R + 2), 1u};
+    if (ss.flat) { bx[1] = (uint32_t)ss.Wp; bx[2] = (uint32_t)(ss.RT + 2); }
     int rc = get_tensor_map(&tmA, p->src0, 4, dims, strides, bx, ss.row_bytes);
     if (rc) return rc;
   }
@@ -358,7 +461,7 @@ static int launch_conv_slab_bn(const Gather& g, const d3fk_conv_params* p, cudaS
   if (occ * tmem_cols > 512) occ = 512 / tmem_cols;
   if (occ < 1) occ = 1;
   int grid = ss.total < g_num_sms * occ ? ss.total : g_num_sms * occ;
-  if (g_verbose) fprintf(stderr, "[d3fk] slab<%d> mode=%d M=%d C=%d Cout=%d W=%d S=%d stages=%d smem=%d grid=%d total=%d\n", BN, g.mode, g.M, C, p->Cout, ss.W, ss.S, ss.stages, smem, grid, ss.total);
+  if (g_verbose) fprintf(stderr, "[d3fk] slab<%d> mode=%d M=%d C=%d Cout=%d W=%d S=%d stages=%d smem=%d grid=%d total=%d flat=%d RT=%d\n", BN, g.mode, g.M, C, p->Cout, ss.W, ss.S, ss.stages, smem, grid, ss.total, ss.flat, ss.RT);
   launch_k(conv_slab_kernel<BN, KSTEPS>, dim3(grid), dim3(SlabCfg<BN>::THREADS), (size_t)smem, s, dim3(1, 1, 1), tmA, tmB, e, ss,
            make_fastdiv((uint32_t)g.Wo), make_fastdiv((uint32_t)g.Ho), g_dev_error_flag);
   count_launch();
@@ -389,6 +492,10 @@ int slab_init() {
   cudaError_t e = cudaSuccess;
 #ifdef D3FK_DEBUG
   if (const char* v = getenv("D3FK_SLAB")) g_use_slab = atoi(v);
+  if (const char* v = getenv("D3FK_SLAB_FLAT")) g_slab_flat = atoi(v);
+  if (const char* v = getenv("D3FK_SLAB_FLAT_MIN_W")) g_slab_flat_min_w = atoi(v);
+  if (const char* v = getenv("D3FK_SLAB_BO")) g_slab_bo = atoi(v);
+  if (const char* v = getenv("D3FK_SLAB_ABLATE")) g_slab_ablate = atoi(v);
 #endif
   D3FK_SET_SMEM((conv_slab_kernel<16, 1>), SLAB_MAX_SMEM)
   D3FK_SET_SMEM((conv_slab_kernel<16, 2>), SLAB_MAX_SMEM)

@@ -15,7 +15,7 @@ namespace d3fk {
 template <int BN> struct ConvCfg {
   static constexpr int STAGES = BN >= 128 ? 3 : 4;
   static constexpr int B_STAGE_BYTES = BN * 128;
-  static constexpr int SMEM = 1024 + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256 + 8 * BN * 4;
+  static constexpr int SMEM = 1024 + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256 + 10 * BN * 4;
   static constexpr int ACC_COLS = BN < 32 ? 32 : BN;   // one accumulator buffer
   static constexpr int TMEM_COLS = 2 * ACC_COLS;        // double buffered: epilogue of tile i overlaps MMAs of tile i+1
 };
@@ -78,6 +78,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(Gather g, FastDi
   uint8_t* gen_bar = smem_raw + (base - smem_u32(smem_raw)) + STAGES * (A_STAGE_BYTES + Cfg::B_STAGE_BYTES);
   volatile uint32_t* tmem_ptr_slot = reinterpret_cast<volatile uint32_t*>(gen_bar + 8 * (2 * STAGES + 4));
   float* s_stat = reinterpret_cast<float*>(gen_bar + 256);  // [4 warps][2][BN]
+  float* s_aff = s_stat + 8 * BN;                           // [2][BN] scale / shift of the current n tile (see epilogue_chunk)
+  const bool affine = e.scale != nullptr || e.shift != nullptr;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto acc_full_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + b); };
@@ -91,6 +93,16 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(Gather g, FastDi
   const int q = warp & 3;                         // TMEM lane quarter / row group of this epilogue warp
   const int half = warp >= 6 ? 1 : 0;             // helpers take the odd column chunks
   const int etid = warp < 4 ? tid : 128 + (tid - 192);   // 0..255 over the 8 epilogue warps
+  // (re)stage the affine coefficients of n tile `nt`: all 8 epilogue warps call it at the same point of their tile loops
+  auto stage_affine = [&](int nt) {
+    asm volatile("bar.sync 1, 256;" ::: "memory");     // nobody still reads the previous tile's coefficients
+    const int ch = nt * BN + etid;
+    if (etid < BN) {
+      s_aff[etid] = e.scale ? (ch < e.Cout ? __ldg(e.scale + ch) : 0.f) : 1.f;
+      s_aff[BN + etid] = ch < e.Cout ? __ldg(e.shift + ch) : 0.f;
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+  };
   const bool clus = ts.KS > 1;
   const bool do_stats = e.stats != nullptr;
   TL_DECL
@@ -269,7 +281,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(Gather g, FastDi
     const int sshift = g.mode ? g.sshift : 0;                        // of the stride (forward folds it into h0/w0)
     uint32_t kbg = 0;  // k-blocks issued by this CTA so far (pipeline stage / phase bookkeeping)
     uint32_t tile_iter = 0;
-    int cur_nt = -1;
+    int cur_nt = -1, cur_aff_nt = -1;
     for (int t = blockIdx.x; t < ts.total; t += gridDim.x, ++tile_iter) {
       int mt, nt, ks;
       decode_tile(ts, t, mt, nt, ks);
@@ -353,6 +365,10 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(Gather g, FastDi
       if (tid == 0) { TL_STAMP(5) }
       tc_fence_after();
       if (clus) break;   // split K: the accumulator is reduced across the cluster below
+      if (affine && cur_aff_nt != nt) {
+        stage_affine(nt);
+        cur_aff_nt = nt;
+      }
       if (do_stats && cur_nt != nt) {
         if (cur_nt >= 0) flush_stats(cur_nt);
         cur_nt = nt;
@@ -377,7 +393,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(Gather g, FastDi
 #pragma unroll
         for (int i = 0; i < CW; ++i) f[i] = __uint_as_float(raw[i]);
         epilogue_chunk<CW, FUSE == 2>(f, e, (long long)m, row_ok, n0 + cc, on, oh, ow, do_stats, s_stat + q * 2 * BN + cc,
-                           s_stat + q * 2 * BN + BN + cc, lane);
+                           s_stat + q * 2 * BN + BN + cc, lane, affine ? s_aff + cc : nullptr, BN);
         if (tid == 0 && cc == 0) { TL_STAMP(8) }
       }
       if (tid == 0) { TL_STAMP(9) }
@@ -471,6 +487,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(Gather g, FastDi
     }
     cluster_sync_all();             // #2: all partials have landed
     if (is_epi) {
+      if (affine) stage_affine(my_nt);
       const int m = my_mt * TC_BM + row;
       const bool row_ok = m < g.M;
       const int cslice = (int)rank * SL;     // first column of my slice within the tile
@@ -488,7 +505,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(Gather g, FastDi
         }
         const int ct = cslice + ch;          // column within the tile
         epilogue_chunk<16, FUSE == 2>(f, e, (long long)m, row_ok, my_nt * BN + ct, 0, 0, 0, do_stats, s_stat + q * 2 * BN + ct,
-                           s_stat + q * 2 * BN + BN + ct, lane);
+                           s_stat + q * 2 * BN + BN + ct, lane, affine ? s_aff + ct : nullptr, BN);
       }
       if (do_stats) flush_stats(my_nt);
       if (FUSE == 1) {

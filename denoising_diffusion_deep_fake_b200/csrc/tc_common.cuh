@@ -307,10 +307,22 @@ constexpr int A_STAGE_BYTES = TC_BM * 128;
 // ReLU, store (bf16 NHWC or fp32 NCHW) and per-channel batch statistics.  The statistics are folded over the 32 rows of
 // the warp with a transpose-reduce and ACCUMULATED into this warp's shared-memory slots (sstat_warp[col], [BN + col]);
 // the CTA flushes the slots to global memory with one double atomic per channel when its n tile changes / at the end.
+// s_aff (nullable): the chunk's affine coefficients staged in shared memory by the CTA — s_aff[0..CW) = scale (1 for a plain
+// bias), s_aff[aff_stride + 0..CW) = shift (0 beyond Cout) — read with broadcast 16-byte loads instead of 2 * CW global loads
+// per thread and tile (the eval forward, where every convolution carries a folded BatchNorm, is epilogue-bound on them).
 template <int CW, bool BW = true>
 __device__ __forceinline__ void epilogue_chunk(float (&f)[CW], const EpiTC& e, long long m, bool row_ok, int cbase, int on,
-                                               int oh, int ow, bool do_stats, float* sstat_sum, float* sstat_sq, int lane) {
-  if (e.scale) {
+                                               int oh, int ow, bool do_stats, float* sstat_sum, float* sstat_sq, int lane,
+                                               const float* s_aff = nullptr, int aff_stride = 0) {
+  if (s_aff) {
+#pragma unroll
+    for (int q = 0; q < CW / 4; ++q) {
+      const float4 a = *reinterpret_cast<const float4*>(s_aff + 4 * q);
+      const float4 b = *reinterpret_cast<const float4*>(s_aff + aff_stride + 4 * q);
+      f[4 * q] = fmaf(f[4 * q], a.x, b.x); f[4 * q + 1] = fmaf(f[4 * q + 1], a.y, b.y);
+      f[4 * q + 2] = fmaf(f[4 * q + 2], a.z, b.z); f[4 * q + 3] = fmaf(f[4 * q + 3], a.w, b.w);
+    }
+  } else if (e.scale) {
 #pragma unroll
     for (int i = 0; i < CW; ++i)
       if (cbase + i < e.Cout) f[i] = fmaf(f[i], __ldg(e.scale + cbase + i), __ldg(e.shift + cbase + i));

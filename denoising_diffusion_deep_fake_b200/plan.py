@@ -411,6 +411,24 @@ class UnetPlan:
             f.update(src1=src1.ptr, c1=src1.C, ld1=src1.ld)
         return make_op(_lib.OP_WGRAD, lane=lane, **f)
 
+    def _wgrad_ops(self, c, src0, src1, up0, dy, lane=0):
+        """Weight-gradient op(s) of one convolution.  A 3x3 / stride-1 layer with 128 input channels and a narrow output
+        (decoder block 3 conv1: 128 -> 32 on 262 144 pixels, the largest single kernel of the step through the generic
+        kernel's 64-wide tiles) is split into two 64-channel halves of the input — pixel stride unchanged, channel
+        offset 64, dW offset 64 * 9 — each of which the slab weight-gradient kernel takes (activations by TMA, read
+        3.75x from L2 instead of 9x, no per-thread gather)."""
+        if (self.dtype == _lib.BF16 and src1 is None and not up0 and c.k == 3 and c.stride == 1 and c.cin == 128
+                and c.cout in (16, 32) and src0.W in (16, 32, 64) and src0.count >= 128 * 148 * 4):
+            esz = 2
+            ops = []
+            for half in range(2):
+                f = dict(dtype=self.dtype, src0=src0.ptr + half * 64 * esz, c0=64, ld0=src0.ld, up0=0, B=self.B, Hi=src0.H,
+                         Wi=src0.W, Ho=dy.H, Wo=dy.W, kh=3, kw=3, stride=1, pad=1, dy=dy.ptr, ldy=dy.ld, Cout=dy.C,
+                         cin_real=c.cin, cout_real=c.cout, dw=self._gptr(c.name + ".weight") + half * 64 * 9 * 4)
+                ops.append(make_op(_lib.OP_WGRAD, lane=lane, **f))
+            return ops
+        return [self._wgrad_op(c, src0, src1, up0, dy, lane=lane)]
+
     def _wgrad_encoder(self, ops, pending, c, src, dy):
         """Weight gradient of an encoder convolution.  The 3x3 / stride-1 / Cin == Cout convolutions of a ResNet stage are
         identically shaped: they are collected and emitted as ONE grouped launch at the end of the stage's segment
@@ -537,7 +555,7 @@ class UnetPlan:
             add_grad(ops, d["conv2"], d_r2, a1)
             d_r1, _ = self._bn_bwd(ops, d["conv1"], grad[id(a1)])
             if cat is not None:
-                ops.append(self._wgrad_op(d["conv1"], cat, None, 0, d_r1))     # the materialised upsample + concat
+                ops += self._wgrad_ops(d["conv1"], cat, None, 0, d_r1)         # the materialised upsample + concat
             else:
                 ops.append(self._wgrad_op(d["conv1"], x, skip, 1, d_r1))
             up_tmp = T(self, B, 2 * x.H, 2 * x.W, x.C)

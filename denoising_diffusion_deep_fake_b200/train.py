@@ -192,7 +192,7 @@ class GraphedStep:
     replays directly; any other batch is copied into a module-owned static buffer first).  A graph is dropped whenever the
     weights were changed from outside (load_state_dict, manual edits), which the version counter reveals."""
 
-    MAX_POINTER_GRAPHS = 2
+    MAX_POINTER_GRAPHS = 4
 
     def __init__(self, module):
         self.module = module
@@ -201,6 +201,8 @@ class GraphedStep:
         self.static_x = {}      # shape -> module-owned input buffer
         self.eager_steps = 0    # eager steps since the last invalidation: capture needs warmed plans and a valid pre-pack
         self.replays = 0
+        self.kernels_replayed = 0   # libd3fk kernel nodes executed through replays (the library's own counter sees only
+                                    # the launches of the capture)
 
     def invalidate(self):
         self.entries.clear()
@@ -215,12 +217,14 @@ class GraphedStep:
             return None                      # the forward would start with a full pack: not the steady state yet
         host = (opt.step_count, model.__dict__.get("_stat_updates", 0), plan.generation, plan.prepacked_version)
         g = torch.cuda.CUDAGraph()
+        k0 = _lib.launch_count()
         with torch.cuda.graph(g):
             loss = mod._step_body(x, noisy)
+        kernels = _lib.launch_count() - k0
         # nothing ran during the capture: take back the host-side bookkeeping it advanced
         opt.step_count, model.__dict__["_stat_updates"], plan.generation, plan.prepacked_version = host
         plan.pending_backward = False
-        return dict(graph=g, x=x, noisy=noisy, loss=loss, plan=plan)
+        return dict(graph=g, x=x, noisy=noisy, loss=loss, plan=plan, kernels=kernels)
 
     def step(self, image, noise=None, y=None):
         """Returns the loss tensor, or None when the step has to run eagerly (warm-up, stale graph)."""
@@ -262,6 +266,7 @@ class GraphedStep:
         ent["plan"].generation += 1
         ent["plan"].prepacked_version = model._weights_version()
         self.replays += 1
+        self.kernels_replayed += ent["kernels"]
         return ent["loss"]
 
 

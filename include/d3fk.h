@@ -69,7 +69,9 @@ typedef struct d3fk_conv_params {
 
 /* ---- weight gradient (replaces cuDNN wgrad): dw[co][ci][kh][kw] += sum_{n,ho,wo} dy[n,ho,wo,co] * A[...]
  * with the same mode-0 gather as the forward conv.  dw is the fp32 OIHW master-gradient tensor
- * (cin_real input channels); contributions are added with atomics, the caller zeroes it first. */
+ * (cin_real input channels); contributions are added with atomics, the caller zeroes it first.  cin_real is the extent
+ * (= stride) of dw's input-channel dimension: a launch over a channel sub-range of the input (c0 + c1 < cin_real, src0 and
+ * dw offset to the first channel of the range) accumulates that slice of dw. */
 typedef struct d3fk_wgrad_params {
   int32_t dtype, _pad0;
   const void* src0; const void* src1;
