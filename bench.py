@@ -527,7 +527,18 @@ def run_d3fk(args):
                         train={"value": value, "ms_per_step": ms / args.steps}, e2e=None)
         print(json.dumps(line), flush=True)
     if world > 1:
+        # Teardown: the replayed step graphs hold NCCL work; release them before the communicator goes away, and never let a
+        # stuck teardown keep the launcher waiting — the measurement is finished and printed at this point.
+        import gc
+        threading.Timer(45.0, lambda: os._exit(0)).start()
+        g = getattr(mod, "_graphed", None)
+        if g:
+            g.entries.clear()
+        gc.collect()
+        torch.cuda.synchronize()
+        dist.barrier()
         dist.destroy_process_group()
+        os._exit(0)
 
 
 def main():

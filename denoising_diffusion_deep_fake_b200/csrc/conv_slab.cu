@@ -58,7 +58,9 @@ template <int BN> struct SlabCfg {
   static constexpr int ACC = BN < 32 ? 32 : BN;
   static constexpr int TMEM_COLS = 2 * NW * ACC;       // double buffered
 };
-template <int BN, int KSTEPS>
+// AFF: the epilogue applies scale / shift (eval: folded BatchNorm; head: bias) staged in shared memory.  A template
+// parameter, not a run-time branch: the staging code costs the training-mode kernels 20 registers and 5-12 % of their time.
+template <int BN, int KSTEPS, bool AFF>
 __global__ void __launch_bounds__(SlabCfg<BN>::THREADS) conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                                EpiTC e, SlabSched ss, FastDiv dWo, FastDiv dHo, int* errflag) {
   constexpr int CW = BN >= 32 ? 32 : 16;
@@ -230,7 +232,7 @@ __global__ void __launch_bounds__(SlabCfg<BN>::THREADS) conv_slab_kernel(const _
     // sub-tile, so it accumulates its own per-column sums over the whole kernel and the 128 rows are folded ONCE at
     // the end (instead of a shuffle transpose-reduce per tile).
     constexpr bool REG_STATS = BN <= 32;
-    const bool affine = e.scale != nullptr || e.shift != nullptr;
+    constexpr bool affine = AFF;
     if (affine) {                    // after griddepcontrol.wait: whatever produced scale / shift has completed
       if (tid < BN) {
         s_aff[tid] = e.scale ? (tid < e.Cout ? __ldg(e.scale + tid) : 0.f) : 1.f;
@@ -435,7 +437,7 @@ static bool slab_plan(const Gather& g, const d3fk_conv_params* p, int BN, SlabSc
   return false;
 }
 
-template <int BN, int KSTEPS>
+template <int BN, int KSTEPS, bool AFF>
 static int launch_conv_slab_bn(const Gather& g, const d3fk_conv_params* p, cudaStream_t s, const SlabSched& ss, int smem) {
   EpiTC e{(bf16*)p->out, p->out_nchw, p->scale, p->shift, (const bf16*)p->res, p->stats, p->ldo, p->ldr, p->relu, p->Cout, p->Ho, p->Wo,
            (const bf16*)p->bw_x, (const bf16*)p->bw_act, p->bw_mean, p->bw_invstd, p->bw_ldx, p->bw_ldact, p->bw_relu};
@@ -462,7 +464,7 @@ static int launch_conv_slab_bn(const Gather& g, const d3fk_conv_params* p, cudaS
   if (occ < 1) occ = 1;
   int grid = ss.total < g_num_sms * occ ? ss.total : g_num_sms * occ;
   if (g_verbose) fprintf(stderr, "[d3fk] slab<%d> mode=%d M=%d C=%d Cout=%d W=%d S=%d stages=%d smem=%d grid=%d total=%d flat=%d RT=%d\n", BN, g.mode, g.M, C, p->Cout, ss.W, ss.S, ss.stages, smem, grid, ss.total, ss.flat, ss.RT);
-  launch_k(conv_slab_kernel<BN, KSTEPS>, dim3(grid), dim3(SlabCfg<BN>::THREADS), (size_t)smem, s, dim3(1, 1, 1), tmA, tmB, e, ss,
+  launch_k(conv_slab_kernel<BN, KSTEPS, AFF>, dim3(grid), dim3(SlabCfg<BN>::THREADS), (size_t)smem, s, dim3(1, 1, 1), tmA, tmB, e, ss,
            make_fastdiv((uint32_t)g.Wo), make_fastdiv((uint32_t)g.Ho), g_dev_error_flag);
   count_launch();
   return check_launch("conv_slab");
@@ -479,7 +481,10 @@ int try_launch_conv_slab(const Gather& g, const d3fk_conv_params* p, cudaStream_
   int smem = 0;
   if (!slab_plan(g, p, BN, ss, smem)) return 0;
   int rc;
-#define SLAB_CASE(bn, ks) if (BN == bn && ss.ksteps == ks) rc = launch_conv_slab_bn<bn, ks>(g, p, s, ss, smem); else
+  const bool aff = p->scale != nullptr || p->shift != nullptr;
+#define SLAB_CASE(bn, ks)                                                                                     \
+  if (BN == bn && ss.ksteps == ks) rc = aff ? launch_conv_slab_bn<bn, ks, true>(g, p, s, ss, smem)            \
+                                            : launch_conv_slab_bn<bn, ks, false>(g, p, s, ss, smem); else
   SLAB_CASE(16, 1) SLAB_CASE(16, 2) SLAB_CASE(16, 4) SLAB_CASE(32, 1) SLAB_CASE(32, 2) SLAB_CASE(32, 4)
   SLAB_CASE(64, 1) SLAB_CASE(64, 2) SLAB_CASE(64, 4) SLAB_CASE(128, 1) SLAB_CASE(128, 2) SLAB_CASE(128, 4)
   rc = set_error(D3FK_ERR_UNSUPPORTED, "slab: BN=%d ksteps=%d", BN, ss.ksteps);
@@ -497,18 +502,30 @@ int slab_init() {
   if (const char* v = getenv("D3FK_SLAB_BO")) g_slab_bo = atoi(v);
   if (const char* v = getenv("D3FK_SLAB_ABLATE")) g_slab_ablate = atoi(v);
 #endif
-  D3FK_SET_SMEM((conv_slab_kernel<16, 1>), SLAB_MAX_SMEM)
-  D3FK_SET_SMEM((conv_slab_kernel<16, 2>), SLAB_MAX_SMEM)
-  D3FK_SET_SMEM((conv_slab_kernel<16, 4>), SLAB_MAX_SMEM)
-  D3FK_SET_SMEM((conv_slab_kernel<32, 1>), SLAB_MAX_SMEM)
-  D3FK_SET_SMEM((conv_slab_kernel<32, 2>), SLAB_MAX_SMEM)
-  D3FK_SET_SMEM((conv_slab_kernel<32, 4>), SLAB_MAX_SMEM)
-  D3FK_SET_SMEM((conv_slab_kernel<64, 1>), SLAB_MAX_SMEM)
-  D3FK_SET_SMEM((conv_slab_kernel<64, 2>), SLAB_MAX_SMEM)
-  D3FK_SET_SMEM((conv_slab_kernel<64, 4>), SLAB_MAX_SMEM)
-  D3FK_SET_SMEM((conv_slab_kernel<128, 1>), SLAB_MAX_SMEM)
-  D3FK_SET_SMEM((conv_slab_kernel<128, 2>), SLAB_MAX_SMEM)
-  D3FK_SET_SMEM((conv_slab_kernel<128, 4>), SLAB_MAX_SMEM)
+  D3FK_SET_SMEM((conv_slab_kernel<16, 1, false>), SLAB_MAX_SMEM)
+  D3FK_SET_SMEM((conv_slab_kernel<16, 1, true>), SLAB_MAX_SMEM)
+  D3FK_SET_SMEM((conv_slab_kernel<16, 2, false>), SLAB_MAX_SMEM)
+  D3FK_SET_SMEM((conv_slab_kernel<16, 2, true>), SLAB_MAX_SMEM)
+  D3FK_SET_SMEM((conv_slab_kernel<16, 4, false>), SLAB_MAX_SMEM)
+  D3FK_SET_SMEM((conv_slab_kernel<16, 4, true>), SLAB_MAX_SMEM)
+  D3FK_SET_SMEM((conv_slab_kernel<32, 1, false>), SLAB_MAX_SMEM)
+  D3FK_SET_SMEM((conv_slab_kernel<32, 1, true>), SLAB_MAX_SMEM)
+  D3FK_SET_SMEM((conv_slab_kernel<32, 2, false>), SLAB_MAX_SMEM)
+  D3FK_SET_SMEM((conv_slab_kernel<32, 2, true>), SLAB_MAX_SMEM)
+  D3FK_SET_SMEM((conv_slab_kernel<32, 4, false>), SLAB_MAX_SMEM)
+  D3FK_SET_SMEM((conv_slab_kernel<32, 4, true>), SLAB_MAX_SMEM)
+  D3FK_SET_SMEM((conv_slab_kernel<64, 1, false>), SLAB_MAX_SMEM)
+  D3FK_SET_SMEM((conv_slab_kernel<64, 1, true>), SLAB_MAX_SMEM)
+  D3FK_SET_SMEM((conv_slab_kernel<64, 2, false>), SLAB_MAX_SMEM)
+  D3FK_SET_SMEM((conv_slab_kernel<64, 2, true>), SLAB_MAX_SMEM)
+  D3FK_SET_SMEM((conv_slab_kernel<64, 4, false>), SLAB_MAX_SMEM)
+  D3FK_SET_SMEM((conv_slab_kernel<64, 4, true>), SLAB_MAX_SMEM)
+  D3FK_SET_SMEM((conv_slab_kernel<128, 1, false>), SLAB_MAX_SMEM)
+  D3FK_SET_SMEM((conv_slab_kernel<128, 1, true>), SLAB_MAX_SMEM)
+  D3FK_SET_SMEM((conv_slab_kernel<128, 2, false>), SLAB_MAX_SMEM)
+  D3FK_SET_SMEM((conv_slab_kernel<128, 2, true>), SLAB_MAX_SMEM)
+  D3FK_SET_SMEM((conv_slab_kernel<128, 4, false>), SLAB_MAX_SMEM)
+  D3FK_SET_SMEM((conv_slab_kernel<128, 4, true>), SLAB_MAX_SMEM)
   if (e != cudaSuccess) return set_error(D3FK_ERR_CUDA, "cudaFuncSetAttribute (slab): %s", cudaGetErrorString(e));
   return D3FK_OK;
 }

@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(Gather g, FastDi
   volatile uint32_t* tmem_ptr_slot = reinterpret_cast<volatile uint32_t*>(gen_bar + 8 * (2 * STAGES + 4));
   float* s_stat = reinterpret_cast<float*>(gen_bar + 256);  // [4 warps][2][BN]
   float* s_aff = s_stat + 8 * BN;                           // [2][BN] scale / shift of the current n tile (see epilogue_chunk)
-  const bool affine = e.scale != nullptr || e.shift != nullptr;
+  constexpr bool affine = FUSE == 3;        // FUSE 3: plain convolution whose epilogue applies staged scale / shift (eval)
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto acc_full_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + b); };
@@ -620,6 +620,9 @@ static int launch_conv_tc_bn(const Gather& g, const d3fk_conv_params* p, cudaStr
   else if (BN == 128 && fuse)
     le = launch_k(conv_tc_kernel<BN, PATH, (BN == 128 ? 1 : 0)>, dim3(grid), dim3(TC_THREADS), ConvCfg<BN>::SMEM, s, dim3(ts.KS, 1, 1), g,
                   make_fastdiv((uint32_t)g.Wo), make_fastdiv((uint32_t)g.Ho), tmA, tmB, e, ts, fb, g_dev_error_flag);
+  else if (p->scale || p->shift)
+    le = launch_k(conv_tc_kernel<BN, PATH, 3>, dim3(grid), dim3(TC_THREADS), ConvCfg<BN>::SMEM, s, dim3(ts.KS, 1, 1), g,
+                  make_fastdiv((uint32_t)g.Wo), make_fastdiv((uint32_t)g.Ho), tmA, tmB, e, ts, fb, g_dev_error_flag);
   else
     le = launch_k(conv_tc_kernel<BN, PATH, 0>, dim3(grid), dim3(TC_THREADS), ConvCfg<BN>::SMEM, s, dim3(ts.KS, 1, 1), g,
                   make_fastdiv((uint32_t)g.Wo), make_fastdiv((uint32_t)g.Ho), tmA, tmB, e, ts, fb, g_dev_error_flag);
@@ -742,6 +745,18 @@ int tc_init() {
   D3FK_SET_SMEM((conv_tc_kernel<128, 0, 1>), ConvCfg<128>::SMEM)
   D3FK_SET_SMEM((conv_tc_kernel<128, 1, 1>), ConvCfg<128>::SMEM)
   D3FK_SET_SMEM((conv_tc_kernel<128, 2, 1>), ConvCfg<128>::SMEM)
+  D3FK_SET_SMEM((conv_tc_kernel<16, 0, 3>), ConvCfg<16>::SMEM)
+  D3FK_SET_SMEM((conv_tc_kernel<16, 1, 3>), ConvCfg<16>::SMEM)
+  D3FK_SET_SMEM((conv_tc_kernel<16, 2, 3>), ConvCfg<16>::SMEM)
+  D3FK_SET_SMEM((conv_tc_kernel<32, 0, 3>), ConvCfg<32>::SMEM)
+  D3FK_SET_SMEM((conv_tc_kernel<32, 1, 3>), ConvCfg<32>::SMEM)
+  D3FK_SET_SMEM((conv_tc_kernel<32, 2, 3>), ConvCfg<32>::SMEM)
+  D3FK_SET_SMEM((conv_tc_kernel<64, 0, 3>), ConvCfg<64>::SMEM)
+  D3FK_SET_SMEM((conv_tc_kernel<64, 1, 3>), ConvCfg<64>::SMEM)
+  D3FK_SET_SMEM((conv_tc_kernel<64, 2, 3>), ConvCfg<64>::SMEM)
+  D3FK_SET_SMEM((conv_tc_kernel<128, 0, 3>), ConvCfg<128>::SMEM)
+  D3FK_SET_SMEM((conv_tc_kernel<128, 1, 3>), ConvCfg<128>::SMEM)
+  D3FK_SET_SMEM((conv_tc_kernel<128, 2, 3>), ConvCfg<128>::SMEM)
   if (e != cudaSuccess) return set_error(D3FK_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   int rc = slab_init();
   if (rc) return rc;

@@ -353,7 +353,9 @@ class DenoiserModule(nn.Module):
               and self.hparams.get("cuda_graph", os.environ.get("D3FK_TRAIN_GRAPH", "1") != "0")
               and all(p.requires_grad for p in self.model.parameters()))
         if ok and self.allreduce.distributed:
-            ok = os.environ.get("D3FK_TRAIN_GRAPH_DP", "0") == "1"      # NCCL inside the capture: opt-in
+            # the NCCL allreduces of the gradient buckets are captured with the step (every rank captures on the same
+            # step); measured at 2 GPUs: 4.33 -> 4.22 ms per step.  D3FK_TRAIN_GRAPH_DP=0 keeps data parallel eager.
+            ok = os.environ.get("D3FK_TRAIN_GRAPH_DP", "1") != "0"
         return ok
 
     def training_step(self, image, noise=None, y=None):

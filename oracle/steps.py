@@ -44,25 +44,38 @@ def training_swap_step_for_one_model(real, real_model, fake_model, criterion, la
                       real_prediction=real_prediction)
 
 
-def short_training_run(ref, sd0, steps, batch=16, device="cpu", lam=5.0, lr=0.02, size=64, seed0=100):
+def short_training_run(ref, sd0, steps, batch=16, device="cpu", lam=5.0, lr=0.02, size=64, seed0=100, dtype=torch.float32,
+                       calibrate=0):
     """State dict after `steps` reference training steps on synthetic faces (Adam lr 0.02, lambda 5:
     d3f/train_denoiser/denoiser_config.yml:3,8), starting from state `sd0` of oracle network `ref` (not modified).
     The parity tests use it to leave the chaotic random-init regime: BatchNorm over freshly initialised weights amplifies
     1e-6-class forward differences into 1e-3-class gradient differences between ANY two implementations
-    (tests/test_ref_pin.py::test_oracle_fp32_gradients_against_fp64)."""
+    (tests/test_ref_pin.py::test_oracle_fp32_gradients_against_fp64).
+    dtype float64 makes a GPU run reproducible (atomics-order noise of 1e-16 does not grow to anything visible in 150 steps;
+    in float32 two runs of the same script end in visibly different states).  calibrate: that many extra train-mode
+    forward passes with frozen weights, so that the BatchNorm running statistics the eval-mode forward folds in belong to
+    the final weights (at lr 0.02 they lag several steps behind).  Returned tensors are float32 (integers unchanged)."""
     import copy
     from .loss import MseStructuralSimilarityLoss
     m = copy.deepcopy(ref)
     m.load_state_dict(sd0)
-    m = m.to(device).train()
+    m = m.to(device).to(dtype).train()
     crit = MseStructuralSimilarityLoss(-1.0, 1.0)
     opt = torch.optim.Adam(m.parameters(), lr=lr)
     gen = torch.Generator(device=device).manual_seed(1)
-    for i in range(steps):
+
+    def batch_of(i):
         g = torch.Generator(device=device).manual_seed(seed0 + i)
         x = F.avg_pool2d(0.5 * torch.randn(batch, 3, size, size, generator=g, device=device), 5, 1, 2).mul(2.5).clamp(-1, 1)
-        loss, _ = denoiser_training_step(m, crit, x, lam, generator=gen)
+        return x.to(dtype)
+
+    for i in range(steps):
+        loss, _ = denoiser_training_step(m, crit, batch_of(i), lam, generator=gen)
         opt.zero_grad()
         loss.backward()
         opt.step()
-    return {k: v.detach().clone() for k, v in m.state_dict().items()}
+    with torch.no_grad():
+        for i in range(calibrate):
+            noisy, _, _ = blend_random_amount_of_noise_with_each_sample(batch_of(steps + i), lam, gen)
+            m(noisy)
+    return {k: (v.detach().float() if v.is_floating_point() else v.detach().clone()) for k, v in m.state_dict().items()}
