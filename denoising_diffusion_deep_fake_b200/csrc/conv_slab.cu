@@ -30,10 +30,10 @@ struct SlabSched {
   // pixel box (Wp = Wt + 2: one halo column on each side, zero filled by TMA at the image border) kept as a flat list of
   // pixel rows; an M tile is 128 CONSECUTIVE slab positions q = r * Wp + w, so that tap (kh, kw) of every row of the tile
   // is the same flat offset kh * Wp + kw — a start-address shift of the UMMA descriptor by whole pixel rows (not a
-  // multiple of the 8-row swizzle atom: the descriptor's base-offset field carries the phase).  The two halo positions
+  // multiple of the 8-row swizzle atom; measured: no descriptor base offset is needed, the swizzle follows the absolute
+  // shared-memory address).  The two halo positions
   // per image row compute junk that the epilogue drops; activations are read 1.3x instead of 3.75x.
   int flat, Wp, RT;       // RT: image rows per super-tile
-  uint32_t bo_mode;       // 1: descriptor base offset = (start address >> 7) & 7; 0: leave it zero
   uint32_t ablate;        // -DD3FK_DEBUG builds only (D3FK_SLAB_ABLATE): 1 = no epilogue work, 2 = no MMAs, 4 = no TMA data
   FastDiv dWp;
 };
@@ -48,10 +48,11 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw(uint32_t saddr, uint32_t s
   return d;
 }
 
-// Warps: 0-3 epilogue, 4 TMA producer, 5..5+NW-1 MMA issuers.  A single thread sustains only one of these small MMAs
-// per ~90 cycles (descriptor moves into uniform registers + the issue itself are a dependent chain), so the 9*KSTEPS*S
-// MMAs of a super-tile are spread over NW warps: warp w owns sub-tile w % S and every P-th tap (P = NW / S) in a private
-// accumulator; the epilogue adds the P partial accumulators of a sub-tile.
+// Warps: 0-3 epilogue, 4 TMA producer, 5..5+NW-1 MMA issuers: MMA warp w (w < S) issues the 9*KSTEPS*chunks MMAs of
+// sub-tile w of every super-tile from ONE elected thread (elect.sync: descriptor words live in uniform registers, ~2 SASS
+// instructions per MMA).  (Until round 2 the issue loop ran behind a lane compare and cost ~31 instructions per MMA — one
+// MMA per ~90 cycles — which is why the taps of a sub-tile used to be split over several warps with partial accumulators
+// that the epilogue had to add up.)
 template <int BN> struct SlabCfg {
   static constexpr int NW = BN >= 128 ? 2 : 4;
   static constexpr int THREADS = (5 + NW) * 32;
@@ -83,19 +84,18 @@ __global__ void __launch_bounds__(SlabCfg<BN>::THREADS) conv_slab_kernel(const _
   auto acc_empty_bar = [&](int b) { return bar_base + 8u * (10 + b); };
   const uint32_t wbar = bar_base + 8u * 12;
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = warp_index_uniform(), lane = tid & 31;
   const bool do_stats = e.stats != nullptr;
   const int S = ss.S;
-  const int P = NW / S;                                 // partial accumulators (tap subsets) per sub-tile
   constexpr uint32_t tmem_cols = (uint32_t)SlabCfg<BN>::TMEM_COLS;
 
   if (tid == 0) {
     for (int s = 0; s < 4; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), NW);
+      mbar_init(empty_bar(s), S);
     }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(acc_full_bar(b), NW);
+      mbar_init(acc_full_bar(b), S);
       mbar_init(acc_empty_bar(b), 128);
     }
     mbar_init(wbar, 1);
@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(SlabCfg<BN>::THREADS) conv_slab_kernel(const _
   if (tid < 128) {
     for (int i = tid; i < 8 * BN; i += 128) s_stat[i] = 0.f;
   }
-  if (warp == 4 && lane == 0) {
+  if (warp == 4 && elect_one_sync()) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     const int cchp = ss.row_bytes >> 1;   // weights are not produced by the previous kernel: warm L2 during the PDL prologue
@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(SlabCfg<BN>::THREADS) conv_slab_kernel(const _
 
   if (warp == 4) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (elect_one_sync()) {
       // resident weights: 9 * chunks boxes {chunk channels, BN} of the packed [Cout][9*Cin] matrix (rows >= Cout zero filled)
       mbar_arrive_expect_tx(wbar, 9u * ss.chunks * ss.w_tile_bytes);
       const int cch = ss.row_bytes >> 1;
@@ -160,12 +160,9 @@ __global__ void __launch_bounds__(SlabCfg<BN>::THREADS) conv_slab_kernel(const _
     __syncwarp();
   } else if (warp >= 5) {
     // ===================== MMA issuers =====================
-    // The loop is kept to two adds per MMA: every descriptor is (constant high word, low word = constant | address >> 4)
-    // and this warp's tap offsets live in registers.  Warp-uniform loop, leader-predicated issue.
-    {
-      const int w = warp - 5;
-      const int my_s = w % S, my_p = w / S;            // sub-tile and tap subset of this warp
-      const uint32_t leader = lane == 0 ? 1u : 0u;
+    // One elected thread per sub-tile.  Every descriptor is (constant high word, low word = constant | address >> 4).
+    const int w = warp - 5;                             // this warp's sub-tile
+    if (w < S && elect_one_sync()) {
       constexpr uint32_t idesc = make_idesc(TC_BM, BN, 0, 0);
       const uint32_t sbo = 8u * ss.row_bytes;
       const uint64_t dtempl = make_smem_desc_sw(0, sbo, ss.layout);
@@ -177,22 +174,22 @@ __global__ void __launch_bounds__(SlabCfg<BN>::THREADS) conv_slab_kernel(const _
         const int kh = tap / 3, kw = tap - kh * 3;
         const int sy = ss.sgn > 0 ? kh : 2 - kh;
         const int sx = ss.sgn > 0 ? kw : 2 - kw;
-        a_off[tap] = ss.flat ? ((uint32_t)((my_s * TC_BM + sy * ss.Wp + sx) * ss.row_bytes) >> 4)
-                             : ((uint32_t)(sx * ss.slab_bytes) >> 4) + (uint32_t)(sy + my_s * ss.R) * img_row16;
+        // flat variant: the swizzle is a function of the absolute shared-memory address, so a start address shifted by whole
+        // pixel rows needs no descriptor base offset (measured on B200 for SWIZZLE_32B / 64B / 128B)
+        a_off[tap] = ss.flat ? ((uint32_t)((w * TC_BM + sy * ss.Wp + sx) * ss.row_bytes) >> 4)
+                             : ((uint32_t)(sx * ss.slab_bytes) >> 4) + (uint32_t)(sy + w * ss.R) * img_row16;
         b_lo[tap] = dlo | ((w_base + (uint32_t)(tap * ss.chunks * ss.w_tile_bytes)) >> 4);
       }
       const uint32_t wchunk16 = (uint32_t)ss.w_tile_bytes >> 4;
-      const uint32_t bo_shift = ss.row_bytes == 128 ? 3u : ss.row_bytes == 64 ? 2u : 1u;   // bo_mode 2 (experiment): row index
-      const bool active = my_p < P;                     // S * P == NW: always true; kept for clarity
       mbar_wait(wbar, 0, errflag);
       uint32_t tile_it = 0;
       int st = 0;
       uint32_t round_par = 0;
-      const int pmask = P - 1;                          // P is 1, 2 or 4: tap % P == tap & (P - 1)
       for (int t = blockIdx.x; t < ss.total; t += gridDim.x, ++tile_it) {
         const uint32_t abuf = tile_it & 1;
         if (tile_it >= 2) mbar_wait(acc_empty_bar(abuf), ((tile_it >> 1) - 1) & 1, errflag);
-        const uint32_t d_addr = tmem_d + abuf * (uint32_t)(NW * ACC) + (uint32_t)((my_s * P + my_p) * ACC);
+        tc_fence_after();
+        const uint32_t d_addr = tmem_d + abuf * (uint32_t)(NW * ACC) + (uint32_t)(w * ACC);
         uint32_t first = 0u;
         for (int c = 0; c < ss.chunks; ++c) {
           mbar_wait(full_bar(st), round_par, errflag);
@@ -200,29 +197,22 @@ __global__ void __launch_bounds__(SlabCfg<BN>::THREADS) conv_slab_kernel(const _
           const uint32_t sub_lo = dlo | ((slab_base + st * stage_bytes) >> 4);
           const uint32_t bc = (uint32_t)c * wchunk16;
 #ifdef D3FK_DEBUG
-          if (active && !(ss.ablate & 2u)) {
-#else
-          if (active) {
+          if (!(ss.ablate & 2u))
 #endif
+          {
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
-              if ((tap & pmask) == my_p) {              // P in {1, 2, 4}
 #pragma unroll
-                for (int kk = 0; kk < KSTEPS; ++kk) {
-                  const uint32_t a_lo = sub_lo + a_off[tap] + 2u * kk;
-                  // base offset (descriptor bits 49-51): the phase of the start address within the 8-row swizzle pattern
-                  const uint32_t a_hi = ss.bo_mode == 1 ? (dhi | (((a_lo >> 3) & 7u) << 17))
-                                      : ss.bo_mode == 2 ? (dhi | (((a_lo >> bo_shift) & 7u) << 17)) : dhi;
-                  umma_f16_lohi_p(d_addr, a_lo, a_hi, b_lo[tap] + bc + 2u * kk, dhi, idesc, first, leader);
-                  first = 1u;
-                }
+              for (int kk = 0; kk < KSTEPS; ++kk) {
+                umma_f16_lohi(d_addr, sub_lo + a_off[tap] + 2u * kk, dhi, b_lo[tap] + bc + 2u * kk, dhi, idesc, first);
+                first = 1u;
               }
             }
           }
-          umma_commit_p(empty_bar(st), leader);
+          umma_commit(empty_bar(st));
           if (++st == ss.stages) { st = 0; round_par ^= 1u; }
         }
-        umma_commit_p(acc_full_bar(abuf), leader);
+        umma_commit(acc_full_bar(abuf));
       }
     }
     __syncwarp();
@@ -288,18 +278,12 @@ __global__ void __launch_bounds__(SlabCfg<BN>::THREADS) conv_slab_kernel(const _
 #pragma unroll
         for (int cc = 0; cc < BN; cc += CW) {
           uint32_t raw[CW];
-          const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + abuf * (uint32_t)(NW * ACC) + (uint32_t)(s * P * ACC + cc);
+          const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + abuf * (uint32_t)(NW * ACC) + (uint32_t)(s * ACC + cc);
           if (CW == 32) tmem_ld32(taddr, raw); else tmem_ld16(taddr, raw);
           tmem_ld_wait();
           float f[CW];
 #pragma unroll
           for (int i = 0; i < CW; ++i) f[i] = __uint_as_float(raw[i]);
-          for (int pp = 1; pp < P; ++pp) {              // add the other tap subsets' partial accumulators
-            if (CW == 32) tmem_ld32(taddr + (uint32_t)(pp * ACC), raw); else tmem_ld16(taddr + (uint32_t)(pp * ACC), raw);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < CW; ++i) f[i] += __uint_as_float(raw[i]);
-          }
           epilogue_chunk<CW>(f, e, m, row_ok, cc, on, oh, ow, do_stats && !REG_STATS, s_stat + warp * 2 * BN + cc,
                              s_stat + warp * 2 * BN + BN + cc, lane, affine ? s_aff + cc : nullptr, BN);
           if (REG_STATS && do_stats) {
@@ -354,9 +338,6 @@ static int g_slab_flat = 0;        // flat (single-slab) variant — 1: whenever
                                    // cannot take (ragged W / H); -1: never.  Correct for every swizzle width, but measured NOT
                                    // faster than the three-slab layout on B200 (these kernels are not load-bound)
 static int g_slab_flat_min_w = 32; // narrower images: the halo positions would waste too many accumulator rows
-static int g_slab_bo = 0;          // descriptor base-offset field of the flat variant: measured on B200 — the swizzle is a
-                                   // function of the absolute shared-memory address, a start address shifted by whole pixel
-                                   // rows needs NO base offset (mode 0 exact for SWIZZLE_32B/64B/128B; modes 1, 2 wrong)
 static int g_slab_ablate = 0;      // D3FK_SLAB_ABLATE (debug builds): SlabSched::ablate
 
 // Slab-path eligibility and geometry.  Returns false when the generic kernels must be used.
@@ -387,7 +368,7 @@ static bool slab_plan(const Gather& g, const d3fk_conv_params* p, int BN, SlabSc
     // H and W: ragged tiles are masked in the epilogue, out-of-image rows / columns are TMA zero fill.
     const int Wt = W < TC_BM ? W : TC_BM, Wp = Wt + 2;
     ss.W = W; ss.H = H; ss.Wt = Wt; ss.Wp = Wp; ss.wtiles = cdiv(W, Wt); ss.R = 1;
-    ss.flat = 1; ss.bo_mode = (uint32_t)g_slab_bo; ss.dWp = make_fastdiv((uint32_t)Wp);
+    ss.flat = 1; ss.dWp = make_fastdiv((uint32_t)Wp);
     for (int S = NW; S >= 1; S >>= 1) {
       const int rt_max = (S * TC_BM - Wt) / Wp + 1;   // last valid position (RT - 1) * Wp + Wt - 1 < S * 128
       if (S * TC_BM < Wt || rt_max < 1) continue;
@@ -499,7 +480,6 @@ int slab_init() {
   if (const char* v = getenv("D3FK_SLAB")) g_use_slab = atoi(v);
   if (const char* v = getenv("D3FK_SLAB_FLAT")) g_slab_flat = atoi(v);
   if (const char* v = getenv("D3FK_SLAB_FLAT_MIN_W")) g_slab_flat_min_w = atoi(v);
-  if (const char* v = getenv("D3FK_SLAB_BO")) g_slab_bo = atoi(v);
   if (const char* v = getenv("D3FK_SLAB_ABLATE")) g_slab_ablate = atoi(v);
 #endif
   D3FK_SET_SMEM((conv_slab_kernel<16, 1, false>), SLAB_MAX_SMEM)

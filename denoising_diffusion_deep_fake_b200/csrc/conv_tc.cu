@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(Gather g, FastDi
   auto acc_full_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + b); };
   auto acc_empty_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = warp_index_uniform(), lane = tid & 31;
   // Epilogue warps: 0-3 (also the gather producers of PATH 0/1) and the helpers 6-9.  A warp may touch TMEM lanes
   // 32*(warp%4)..+32 only, so helper warp w shares the lane quarter of primary warp w%4 and takes every other column
   // chunk: the epilogue is a dependent instruction chain per warp (~1 us per 32 columns with one warp per scheduler).
@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(Gather g, FastDi
   if (is_epi) {
     for (int i = etid; i < 8 * BN; i += EPI_THREADS) s_stat[i] = 0.f;
   }
-  if (warp == 5 && lane == 0) {
+  if (warp == 5 && elect_one_sync()) {
     tma_prefetch_desc(&tmB);
     if (PATH == 2) tma_prefetch_desc(&tmA);
     // The packed weights are not written by the preceding kernel (pack_all ran at the start of the step), so the first
@@ -232,8 +232,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(Gather g, FastDi
   if (clus) decode_tile(ts, blockIdx.x, my_mt, my_nt, my_ks);
 
   if (warp == 5) {
-    // ===================== TMA producer (one thread) =====================
-    if (lane == 0) {
+    // ===================== TMA producer (one elected thread) =====================
+    if (elect_one_sync()) {
       uint32_t kbg = 0;
       const int sgn = g.mode ? -1 : 1;
       const int off = g.mode ? g.pad : -g.pad;
@@ -420,8 +420,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(Gather g, FastDi
     if (tid == 0) { TL_STAMP(10) }
     if (!clus && do_stats && cur_nt >= 0) flush_stats(cur_nt);
   } else if (warp == 4) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (one elected thread) =====================
+    if (elect_one_sync()) {
       constexpr uint32_t idesc = make_idesc(TC_BM, BN, 0, 0);
       uint32_t kbg = 0, tile_iter = 0;
       for (int t = blockIdx.x; t < ts.total; t += gridDim.x, ++tile_iter) {

@@ -30,6 +30,19 @@ __device__ __forceinline__ unsigned long long tl_now() { unsigned long long t; a
 // PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of a fully converged warp (elect.sync).  Every single-thread issue region (tcgen05.mma / commit, TMA loads)
+// is entered through this and NOT through `lane == 0`: inside an elect region ptxas knows that one thread is active and
+// moves descriptor / coordinate words into uniform registers with a plain R2UR (or computes them on the uniform datapath
+// outright); behind a lane compare it wraps EVERY UTCHMMA / UTMALDG in an ELECT + R2UR.BROADCAST + BRA.U.ANY waterfall
+// loop — ~31 SASS instructions per MMA instead of ~2 (ncu source page of conv_slab_kernel, profiles/r02_issue_loop.txt).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+// warp index as a value the compiler can prove warp-uniform
+__device__ __forceinline__ int warp_index_uniform() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }

@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(Gather g, FastDiv 
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   const uint32_t accum_bar = bar_base + 8u * (2 * STAGES);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = warp_index_uniform(), lane = tid & 31;
   const int k0 = blockIdx.x * 128, co0 = blockIdx.y * BN;
   const int nblk_total = (g.M + WG_PIX - 1) / WG_PIX;
   const int prob = grp.count > 0 ? (int)blockIdx.z / grp.splits : 0;
@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(Gather g, FastDiv 
       }
     }
   } else if (warp == 4) {
-    if (lane == 0 && nblk > 0) {
+    if (nblk > 0 && elect_one_sync()) {
       constexpr uint32_t idesc = make_idesc(128, BN, 1, 1);
       for (int it = 0; it < nblk; ++it) {
         const int s = it % STAGES;
@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(WGS_THREADS) wgrad_slab_kernel(const __grid_co
   auto empty_bar = [&](int s) { return bar_base + 8u * (4 + s); };
   const uint32_t acc_full = bar_base + 8u * 8;
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = warp_index_uniform(), lane = tid & 31;
   const int nacc = 3 * ss.MB;                       // accumulators per K-step parity set
   uint32_t tmem_cols = 32;
   while ((int)tmem_cols < 2 * nacc * ACC) tmem_cols <<= 1;
@@ -365,7 +365,7 @@ __global__ void __launch_bounds__(WGS_THREADS) wgrad_slab_kernel(const __grid_co
     mbar_init(acc_full, WGS_NW);
     fence_barrier_init();
   }
-  if (warp == 4 && lane == 0) {
+  if (warp == 4 && elect_one_sync()) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmD);
   }
@@ -377,7 +377,7 @@ __global__ void __launch_bounds__(WGS_THREADS) wgrad_slab_kernel(const __grid_co
   pdl_enter();
 
   if (warp == 4) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       const int rows = ss.S * ss.R;
       uint32_t it = 0;
       for (int t = blockIdx.x; t < ss.total; t += gridDim.x, ++it) {
@@ -396,11 +396,10 @@ __global__ void __launch_bounds__(WGS_THREADS) wgrad_slab_kernel(const __grid_co
     __syncwarp();
   } else if (warp >= 5) {
     // MMA issuers: warp w owns kw = w % 3 and the K steps (16-pixel groups) of parity w / 3, in its own accumulators —
-    // six independent issue streams (one thread sustains only ~1 small MMA per 90 cycles).
-    if (has_work) {
+    // six independent issue streams, each ONE elected thread (elect.sync: descriptors in uniform registers).
+    if (has_work && elect_one_sync()) {
       const int w = warp - 5;
       const int sx = w % 3, par = w / 3;
-      const uint32_t leader = lane == 0 ? 1u : 0u;
       constexpr uint32_t idesc = make_idesc(128, BN, 1, 1);
       const uint32_t img_row = (uint32_t)(ss.Wt * ss.a_row_bytes);       // M-atom stride of the A operand = one tap row (kh)
       const uint64_t a_t = make_smem_desc_mn(0, img_row, 8u * ss.a_row_bytes, ss.a_layout);
@@ -422,17 +421,17 @@ __global__ void __launch_bounds__(WGS_THREADS) wgrad_slab_kernel(const __grid_co
         for (int mb = 0; mb < ss.MB; ++mb) {
           const uint32_t d_addr = d_base + (uint32_t)(mb * ACC);
           uint32_t a_cur = a_lo + (uint32_t)mb * mb_off, b_cur = b_lo;
-          umma_f16_lohi_p(d_addr, a_cur, ahi, b_cur, bhi, idesc, it ? 1u : 0u, leader);
+          umma_f16_lohi(d_addr, a_cur, ahi, b_cur, bhi, idesc, it ? 1u : 0u);
 #pragma unroll 4
           for (int j = 1; j < ksteps2; ++j) {
             a_cur += a_step2;
             b_cur += b_step2;
-            umma_f16_lohi_p(d_addr, a_cur, ahi, b_cur, bhi, idesc, 1u, leader);
+            umma_f16_lohi(d_addr, a_cur, ahi, b_cur, bhi, idesc, 1u);
           }
         }
-        umma_commit_p(empty_bar(st), leader);
+        umma_commit(empty_bar(st));
       }
-      umma_commit_p(acc_full, leader);
+      umma_commit(acc_full);
     }
     __syncwarp();
   } else if (has_work) {

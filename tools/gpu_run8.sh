@@ -1,0 +1,7 @@
+#!/bin/bash
+mkdir -p gpurun_out
+export PYTHONUNBUFFERED=1
+echo "== pytest ops+unet"; timeout 1200 python -m pytest tests/test_gpu_ops.py tests/test_gpu_unet.py -q -m gpu -p no:cacheprovider -x > gpurun_out/r8_pytest.txt 2>&1; tail -5 gpurun_out/r8_pytest.txt
+echo "== split conv / bn"; timeout 600 python tools/split_convbn.py > gpurun_out/r8_split.txt 2>&1; tail -48 gpurun_out/r8_split.txt
+echo "== bench"; timeout 900 python bench.py --steps 20 --warmup 5 --no-cpu --no-cudnn --no-swap --sample-steps 200 > gpurun_out/r8_bench.txt 2>&1; tail -c 2600 gpurun_out/r8_bench.txt
+echo "== per-op"; timeout 600 python tools/profile_ops.py --repeat 20 --top 400 > gpurun_out/r8_per_op.txt 2>&1; grep "====" gpurun_out/r8_per_op.txt
