@@ -48,14 +48,20 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw(uint32_t saddr, uint32_t s
   return d;
 }
 
-// Warps: 0-3 epilogue, 4 TMA producer, 5..5+NW-1 MMA issuers: MMA warp w (w < S) issues the 9*KSTEPS*chunks MMAs of
+// Warps: 0-7 epilogue, 8 TMA producer, 9..9+NW-1 MMA issuers: MMA warp w (w < S) issues the 9*KSTEPS*chunks MMAs of
 // sub-tile w of every super-tile from ONE elected thread (elect.sync: descriptor words live in uniform registers, ~2 SASS
 // instructions per MMA).  (Until round 2 the issue loop ran behind a lane compare and cost ~31 instructions per MMA — one
 // MMA per ~90 cycles — which is why the taps of a sub-tile used to be split over several warps with partial accumulators
 // that the epilogue had to add up.)
+// Eight epilogue warps: the epilogue is a dependent chain per warp (tcgen05.ld -> convert -> store -> statistics) and with
+// four warps it alone took 85 % of a narrow layer's time (ablation: D3FK_SLAB_ABLATE=6).  A warp may read TMEM lanes
+// 32*(warp%4)..+32 only, so warps e and e+4 share a row quarter and split the work: the two column halves of a tile
+// (BN >= 32: also halves the per-thread statistics registers) or alternate sub-tiles (BN = 16: a thread keeps a whole
+// 32-byte output row).
 template <int BN> struct SlabCfg {
   static constexpr int NW = BN >= 128 ? 2 : 4;
-  static constexpr int THREADS = (5 + NW) * 32;
+  static constexpr int EPI_WARPS = 8;
+  static constexpr int THREADS = (EPI_WARPS + 1 + NW) * 32;
   static constexpr int ACC = BN < 32 ? 32 : BN;
   static constexpr int TMEM_COLS = 2 * NW * ACC;       // double buffered
 };
@@ -64,7 +70,6 @@ template <int BN> struct SlabCfg {
 template <int BN, int KSTEPS, bool AFF>
 __global__ void __launch_bounds__(SlabCfg<BN>::THREADS) conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                                EpiTC e, SlabSched ss, FastDiv dWo, FastDiv dHo, int* errflag) {
-  constexpr int CW = BN >= 32 ? 32 : 16;
   constexpr int ACC = SlabCfg<BN>::ACC;
   constexpr int NW = SlabCfg<BN>::NW;
   extern __shared__ uint8_t smem_raw[];
@@ -76,8 +81,8 @@ __global__ void __launch_bounds__(SlabCfg<BN>::THREADS) conv_slab_kernel(const _
   const uint32_t bar_base = slab_base + ss.stages * stage_bytes;        // full[4], empty[4], acc_full[2], acc_empty[2], wbar
   uint8_t* gen_bar = smem_raw + (bar_base - smem_u32(smem_raw));
   volatile uint32_t* tmem_ptr_slot = reinterpret_cast<volatile uint32_t*>(gen_bar + 8 * 13);
-  float* s_stat = reinterpret_cast<float*>(gen_bar + 128);              // [4 warps][2][BN]
-  float* s_aff = s_stat + 8 * BN;                                       // [2][BN] staged scale / shift (eval: folded BN; head: bias)
+  float* s_stat = reinterpret_cast<float*>(gen_bar + 128);              // [8 warps][2][BN]
+  float* s_aff = s_stat + 16 * BN;                                       // [2][BN] staged scale / shift (eval: folded BN; head: bias)
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (4 + s); };
   auto acc_full_bar = [&](int b) { return bar_base + 8u * (8 + b); };
@@ -96,29 +101,29 @@ __global__ void __launch_bounds__(SlabCfg<BN>::THREADS) conv_slab_kernel(const _
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(acc_full_bar(b), S);
-      mbar_init(acc_empty_bar(b), 128);
+      mbar_init(acc_empty_bar(b), 256);
     }
     mbar_init(wbar, 1);
     fence_barrier_init();
   }
-  if (tid < 128) {
-    for (int i = tid; i < 8 * BN; i += 128) s_stat[i] = 0.f;
+  if (tid < 256) {
+    for (int i = tid; i < 16 * BN; i += 256) s_stat[i] = 0.f;
   }
-  if (warp == 4 && elect_one_sync()) {
+  if (warp == 8 && elect_one_sync()) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     const int cchp = ss.row_bytes >> 1;   // weights are not produced by the previous kernel: warm L2 during the PDL prologue
     for (int t = 0; t < 9; ++t)
       for (int c = 0; c < ss.chunks; ++c) tma_prefetch_l2_2d(&tmB, t * ss.ctot + c * cchp, 0);
   }
-  if (warp == 5) tmem_alloc(smem_u32((const void*)tmem_ptr_slot), tmem_cols);
+  if (warp == 9) tmem_alloc(smem_u32((const void*)tmem_ptr_slot), tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = *tmem_ptr_slot;
   pdl_enter();
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ===================== TMA producer =====================
     if (elect_one_sync()) {
       // resident weights: 9 * chunks boxes {chunk channels, BN} of the packed [Cout][9*Cin] matrix (rows >= Cout zero filled)
@@ -158,10 +163,10 @@ __global__ void __launch_bounds__(SlabCfg<BN>::THREADS) conv_slab_kernel(const _
       }
     }
     __syncwarp();
-  } else if (warp >= 5) {
+  } else if (warp >= 9) {
     // ===================== MMA issuers =====================
     // One elected thread per sub-tile.  Every descriptor is (constant high word, low word = constant | address >> 4).
-    const int w = warp - 5;                             // this warp's sub-tile
+    const int w = warp - 9;                             // this warp's sub-tile
     if (w < S && elect_one_sync()) {
       constexpr uint32_t idesc = make_idesc(TC_BM, BN, 0, 0);
       const uint32_t sbo = 8u * ss.row_bytes;
@@ -217,24 +222,31 @@ __global__ void __launch_bounds__(SlabCfg<BN>::THREADS) conv_slab_kernel(const _
     }
     __syncwarp();
   } else {
-    // ===================== epilogue warps =====================
-    // Narrow layers (BN <= 32) keep their batch statistics in registers: a thread owns row (warp*32+lane) of every
-    // sub-tile, so it accumulates its own per-column sums over the whole kernel and the 128 rows are folded ONCE at
-    // the end (instead of a shuffle transpose-reduce per tile).
-    constexpr bool REG_STATS = BN <= 32;
+    // ===================== epilogue warps (0-7) =====================
+    const int q = warp & 3, h = warp >> 2;              // TMEM lane quarter (= row group) and work half of this warp
+    constexpr bool SPLIT_COLS = BN >= 32;               // halves = column halves; BN = 16: halves = alternate sub-tiles
+    constexpr int NC = SPLIT_COLS ? BN / 2 : BN;        // accumulator columns of a sub-tile this warp handles
+    constexpr int CW = NC >= 32 ? 32 : 16;              // columns per tcgen05.ld
+    const int c_lo = SPLIT_COLS ? h * NC : 0;
+    const int s_first = SPLIT_COLS ? 0 : h, s_step = SPLIT_COLS ? 1 : 2;
+    // Narrow slices (16 columns per warp) keep their batch statistics in registers: a thread owns one row of every sub-tile
+    // it handles, so it accumulates its own per-column sums over the whole kernel and the rows are folded ONCE at the end
+    // (instead of a shuffle transpose-reduce per tile).
+    constexpr bool REG_STATS = NC <= 16;
     constexpr bool affine = AFF;
     if (affine) {                    // after griddepcontrol.wait: whatever produced scale / shift has completed
       if (tid < BN) {
         s_aff[tid] = e.scale ? (tid < e.Cout ? __ldg(e.scale + tid) : 0.f) : 1.f;
         s_aff[BN + tid] = tid < e.Cout ? __ldg(e.shift + tid) : 0.f;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
     }
-    float rs[REG_STATS ? BN : 1], rq[REG_STATS ? BN : 1];
+    float rs[REG_STATS ? NC : 1], rq[REG_STATS ? NC : 1];
 #pragma unroll
-    for (int i = 0; i < (REG_STATS ? BN : 1); ++i) { rs[i] = 0.f; rq[i] = 0.f; }
+    for (int i = 0; i < (REG_STATS ? NC : 1); ++i) { rs[i] = 0.f; rq[i] = 0.f; }
     uint32_t it = 0;
-    const int row = warp * 32 + lane;
+    const int row = q * 32 + lane;
+    float* my_stat = s_stat + warp * 2 * BN;
     for (int t = blockIdx.x; t < ss.total; t += gridDim.x, ++it) {
       const uint32_t abuf = it & 1;
       const int n = t / ss.tiles_per_img;
@@ -250,15 +262,15 @@ __global__ void __launch_bounds__(SlabCfg<BN>::THREADS) conv_slab_kernel(const _
         continue;
       }
 #endif
-      for (int s = 0; s < S; ++s) {
+      for (int s = s_first; s < S; s += s_step) {
         long long m;
         bool row_ok;
         int on = 0, oh = 0, ow = 0;
         if (ss.flat) {
-          // slab position q = r * Wp + w of this accumulator row; the columns w >= Wt are the halo positions (junk)
-          const uint32_t q = (uint32_t)(s * TC_BM + row);
-          const int r = (int)fdiv(q, ss.dWp);
-          const int w = (int)q - r * ss.Wp;
+          // slab position p = r * Wp + w of this accumulator row; the columns w >= Wt are the halo positions (junk)
+          const uint32_t pos = (uint32_t)(s * TC_BM + row);
+          const int r = (int)fdiv(pos, ss.dWp);
+          const int w = (int)pos - r * ss.Wp;
           row_ok = w < ss.Wt && r < ss.RT && h0 + r < ss.H && w0 + w < ss.W;
           m = ((long long)n * ss.H + h0 + r) * ss.W + w0 + w;
           on = n; oh = h0 + r; ow = w0 + w;
@@ -266,35 +278,35 @@ __global__ void __launch_bounds__(SlabCfg<BN>::THREADS) conv_slab_kernel(const _
           m = ((long long)n * ss.H + h0 + s * ss.R) * ss.W + w0 + row;   // 128 consecutive pixels
           row_ok = m < ss.M;
           if (e.out_nchw && row_ok) {
-            const uint32_t q = fdiv((uint32_t)m, dWo);
-            ow = (int)m - (int)q * e.Wo;
-            on = (int)fdiv(q, dHo);
-            oh = (int)q - on * e.Ho;
+            const uint32_t pq = fdiv((uint32_t)m, dWo);
+            ow = (int)m - (int)pq * e.Wo;
+            on = (int)fdiv(pq, dHo);
+            oh = (int)pq - on * e.Ho;
           }
         }
         // (Tried and dropped: software-pipelining the TMEM reads — the next chunk's tcgen05.ld in flight while this one is
-        // stored — with 16-column chunks to make room for the second register buffer: 5-100 % SLOWER on every layer, the
-        // extra chunk iterations and register pressure cost more than the exposed load latency.)
+        // stored: the extra chunk iterations and register pressure cost more than the exposed load latency.)
 #pragma unroll
-        for (int cc = 0; cc < BN; cc += CW) {
+        for (int cl = 0; cl < NC; cl += CW) {
+          const int cc = c_lo + cl;                     // first accumulator column of this chunk
           uint32_t raw[CW];
-          const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + abuf * (uint32_t)(NW * ACC) + (uint32_t)(s * ACC + cc);
+          const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + abuf * (uint32_t)(NW * ACC) + (uint32_t)(s * ACC + cc);
           if (CW == 32) tmem_ld32(taddr, raw); else tmem_ld16(taddr, raw);
           tmem_ld_wait();
           float f[CW];
 #pragma unroll
           for (int i = 0; i < CW; ++i) f[i] = __uint_as_float(raw[i]);
-          epilogue_chunk<CW>(f, e, m, row_ok, cc, on, oh, ow, do_stats && !REG_STATS, s_stat + warp * 2 * BN + cc,
-                             s_stat + warp * 2 * BN + BN + cc, lane, affine ? s_aff + cc : nullptr, BN);
+          epilogue_chunk<CW>(f, e, m, row_ok, cc, on, oh, ow, do_stats && !REG_STATS, my_stat + cc, my_stat + BN + cc, lane,
+                             affine ? s_aff + cc : nullptr, BN);
           if (REG_STATS && do_stats) {
             if (e.bw_x) {
               float sq[CW];
               bw_stat_terms<CW>(f, sq, e, m, row_ok, cc);
 #pragma unroll
-              for (int i = 0; i < CW; ++i) { rs[cc + i] += f[i]; rq[cc + i] += sq[i]; }
+              for (int i = 0; i < CW; ++i) { rs[cl + i] += f[i]; rq[cl + i] += sq[i]; }
             } else if (row_ok) {
 #pragma unroll
-              for (int i = 0; i < CW; ++i) { rs[cc + i] += f[i]; rq[cc + i] = fmaf(f[i], f[i], rq[cc + i]); }
+              for (int i = 0; i < CW; ++i) { rs[cl + i] += f[i]; rq[cl + i] = fmaf(f[i], f[i], rq[cl + i]); }
             }
           }
         }
@@ -303,25 +315,21 @@ __global__ void __launch_bounds__(SlabCfg<BN>::THREADS) conv_slab_kernel(const _
       mbar_arrive(acc_empty_bar(abuf));
     }
     if (do_stats) {
-      if (REG_STATS) {
+      if (REG_STATS) {                                  // NC == CW == 16
+        float a[CW], b[CW];
 #pragma unroll
-        for (int cc = 0; cc < BN; cc += CW) {
-          float a[CW], b[CW];
-#pragma unroll
-          for (int i = 0; i < CW; ++i) { a[i] = rs[cc + i]; b[i] = rq[cc + i]; }
-          float cs, cq;
-          if (CW == 32) { cs = warp_colsum32(a, lane); cq = warp_colsum32(b, lane); }
-          else { cs = warp_colsum16(a, lane); cq = warp_colsum16(b, lane); }
-          if (lane < CW) {
-            s_stat[warp * 2 * BN + cc + lane] = cs;
-            s_stat[warp * 2 * BN + BN + cc + lane] = cq;
-          }
+        for (int i = 0; i < CW; ++i) { a[i] = rs[i]; b[i] = rq[i]; }
+        const float cs = warp_colsum16(a, lane), cq = warp_colsum16(b, lane);
+        if (lane < CW) {
+          my_stat[c_lo + lane] = cs;
+          my_stat[BN + c_lo + lane] = cq;
         }
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       if (tid < BN && tid < e.Cout) {
-        const float a = (s_stat[tid] + s_stat[2 * BN + tid]) + (s_stat[4 * BN + tid] + s_stat[6 * BN + tid]);
-        const float b = (s_stat[BN + tid] + s_stat[3 * BN + tid]) + (s_stat[5 * BN + tid] + s_stat[7 * BN + tid]);
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int wq = 0; wq < 8; ++wq) { a += s_stat[wq * 2 * BN + tid]; b += s_stat[wq * 2 * BN + BN + tid]; }
         atomicAdd(&e.stats[tid], (double)a);
         atomicAdd(&e.stats[e.Cout + tid], e.bw_x ? bw_second_sum((double)a, (double)b, e, tid) : (double)b);
       }
@@ -330,7 +338,7 @@ __global__ void __launch_bounds__(SlabCfg<BN>::THREADS) conv_slab_kernel(const _
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc(tmem_d, tmem_cols);
+  if (warp == 9) tmem_dealloc(tmem_d, tmem_cols);
 }
 
 static int g_use_slab = 1;   // D3FK_SLAB=0: never take the slab path
@@ -379,7 +387,7 @@ static bool slab_plan(const Gather& g, const d3fk_conv_params* p, int BN, SlabSc
       const int rows_read = S * TC_BM + 2 * Wp + 2;        // the furthest (junk) row a tap of the last sub-tile touches
       const int slab = ((rows_loaded > rows_read ? rows_loaded : rows_read) * ss.row_bytes + 1023) & ~1023;
       for (int stages = 4; stages >= 2; --stages) {
-        const int need = 1024 + w_bytes + stages * slab + 128 + 10 * BN * 4;
+        const int need = 1024 + w_bytes + stages * slab + 128 + 18 * BN * 4;
         if (need > SLAB_MAX_SMEM) continue;
         ss.S = S; ss.RT = RT;
         ss.slab_bytes = slab;
@@ -403,7 +411,7 @@ static bool slab_plan(const Gather& g, const d3fk_conv_params* p, int BN, SlabSc
     if (H % (S * R)) continue;
     const int slab = ((S * R + 2) * Wt * ss.row_bytes + 1023) & ~1023;
     for (int stages = 3; stages >= 2; --stages) {
-      const int need = 1024 + w_bytes + stages * 3 * slab + 128 + 10 * BN * 4;
+      const int need = 1024 + w_bytes + stages * 3 * slab + 128 + 18 * BN * 4;
       if (need > SLAB_MAX_SMEM) continue;
       ss.S = S;
       ss.slab_bytes = slab;
