@@ -291,12 +291,20 @@ __global__ void __launch_bounds__(SlabCfg<BN>::THREADS) conv_slab_kernel(const _
           const int cc = c_lo + cl;                     // first accumulator column of this chunk
           uint32_t raw[CW];
           const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + abuf * (uint32_t)(NW * ACC) + (uint32_t)(s * ACC + cc);
+          // wide layers: plain batch statistics from tensor memory in the 16x256b arrangement (tmem_col_stats); the flat
+          // variant (junk halo positions inside a row quarter) and the dgrad-fused BN-backward sums keep the row-wise path
+          const bool tstats = !REG_STATS && do_stats && !e.bw_x && !ss.flat;
+          if (tstats) {
+            const long long mq = ((long long)n * ss.H + h0 + s * ss.R) * ss.W + w0 + q * 32;   // first row of this quarter
+            const long long lim = (long long)ss.M - mq;
+            tmem_col_stats<CW>(taddr, lim > 32 ? 32 : (int)lim, my_stat + cc, my_stat + BN + cc, lane);
+          }
           if (CW == 32) tmem_ld32(taddr, raw); else tmem_ld16(taddr, raw);
           tmem_ld_wait();
           float f[CW];
 #pragma unroll
           for (int i = 0; i < CW; ++i) f[i] = __uint_as_float(raw[i]);
-          epilogue_chunk<CW>(f, e, m, row_ok, cc, on, oh, ow, do_stats && !REG_STATS, my_stat + cc, my_stat + BN + cc, lane,
+          epilogue_chunk<CW>(f, e, m, row_ok, cc, on, oh, ow, do_stats && !REG_STATS && !tstats, my_stat + cc, my_stat + BN + cc, lane,
                              affine ? s_aff + cc : nullptr, BN);
           if (REG_STATS && do_stats) {
             if (e.bw_x) {

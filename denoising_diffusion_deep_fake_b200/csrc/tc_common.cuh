@@ -192,6 +192,17 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// The same barrier without memory ordering on the arrive side (no MEMBAR.ALL.GPU + ERRBAR in front of UCGABAR_ARV): for
+// phases that only order control flow ("every CTA of the cluster is past its main loop").
+__device__ __forceinline__ void cluster_sync_relaxed() {
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
+}
+// Asynchronous 16-byte store into the shared memory of a CTA of the cluster; its completion is counted (complete_tx, 16
+// bytes) on an mbarrier of the DESTINATION CTA — the receiver waits on its own barrier, no cluster-wide barrier or fence.
+__device__ __forceinline__ void st_async_f4(uint32_t remote_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t remote_mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+               ::"r"(remote_addr), "r"(a), "r"(b), "r"(c), "r"(d), "r"(remote_mbar) : "memory");
+}
 __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
   uint32_t r;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
@@ -251,6 +262,89 @@ __device__ __forceinline__ float warp_colsum16(float* v, int lane) {
     }
   }
   return v[0];
+}
+
+// ---- per-channel batch statistics straight from tensor memory
+// tcgen05.ld.16x256b hands a warp its 32 accumulator rows in the mma C-fragment arrangement (measured with
+// tools/probes/tmem_layout_probe.cu): of one load at lane base L, thread t holds rows L + t/4 and L + t/4 + 8 and, per
+// 8-column block j, the columns 8j + 2(t%4) + {0, 1} (registers 4j + {0,1} | {2,3}).  A thread therefore sums FOUR rows of
+// its column pair in registers and the remaining reduction runs over the 8 lanes that share t % 4: 8 + 4 + 2 shuffles for
+// the sums AND the sums of squares of 32 columns, against 2 x 31 for the transpose-reduce of the row-per-thread (32x32b)
+// arrangement — which, queued behind the epilogue's scattered 16-byte stores in the same memory-instruction pipe, took
+// 0.7 us per 32-column chunk and was the largest single piece of every training-forward epilogue.
+template <int NREP> __device__ __forceinline__ void tmem_ld_16x256b(uint32_t taddr, uint32_t* v);
+template <> __device__ __forceinline__ void tmem_ld_16x256b<4>(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+template <> __device__ __forceinline__ void tmem_ld_16x256b<2>(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
+// 16 fp32 columns of this thread's accumulator row back into tensor memory (the split-K owner parks its reduced slice so
+// that the statistics can be taken in the 16x256b arrangement)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* f) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "f"(f[0]), "f"(f[1]), "f"(f[2]), "f"(f[3]), "f"(f[4]), "f"(f[5]), "f"(f[6]), "f"(f[7]), "f"(f[8]), "f"(f[9]),
+        "f"(f[10]), "f"(f[11]), "f"(f[12]), "f"(f[13]), "f"(f[14]), "f"(f[15])
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+// Sums and sums of squares of CW (32 or 16) accumulator columns starting at taddr's column, over the 32 rows of this warp's
+// lane quarter (taddr carries the quarter's lane base), ACCUMULATED into sstat_sum[0..CW) / sstat_sq[0..CW) (one owner
+// lane per slot).  row_limit: rows (relative to the quarter's first row) >= row_limit are excluded.
+template <int CW>
+__device__ __forceinline__ void tmem_col_stats(uint32_t taddr, int row_limit, float* sstat_sum, float* sstat_sq, int lane) {
+  constexpr int J = CW / 8;                 // 8-column blocks
+  uint32_t a[4 * J], b[4 * J];
+  tmem_ld_16x256b<J>(taddr, a);
+  tmem_ld_16x256b<J>(taddr + (16u << 16), b);
+  tmem_ld_wait();
+  const int r0 = lane >> 2;
+  const bool v0 = r0 < row_limit, v1 = r0 + 8 < row_limit, v2 = r0 + 16 < row_limit, v3 = r0 + 24 < row_limit;
+  float s[4 * J];                           // [0, 2J): sums, [2J, 4J): sums of squares; index j * 2 + e
+#pragma unroll
+  for (int j = 0; j < J; ++j)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const float x0 = v0 ? __uint_as_float(a[4 * j + e]) : 0.f, x1 = v1 ? __uint_as_float(a[4 * j + 2 + e]) : 0.f;
+      const float x2 = v2 ? __uint_as_float(b[4 * j + e]) : 0.f, x3 = v3 ? __uint_as_float(b[4 * j + 2 + e]) : 0.f;
+      s[j * 2 + e] = (x0 + x1) + (x2 + x3);
+      s[2 * J + j * 2 + e] = fmaf(x0, x0, x1 * x1) + fmaf(x2, x2, x3 * x3);
+    }
+  // transpose-reduce over the lanes that share lane % 4 (lane bits 4, 3, 2): the surviving index bits are those lane bits
+#define D3FK_TR_LEVEL(ofs, n)                                                 \
+  {                                                                           \
+    const bool up = (lane & (ofs)) != 0;                                      \
+    _Pragma("unroll") for (int i = 0; i < (n) / 2; ++i) {                     \
+      const float send = up ? s[i] : s[i + (n) / 2];                          \
+      const float keep = up ? s[i + (n) / 2] : s[i];                          \
+      s[i] = keep + __shfl_xor_sync(0xffffffffu, send, (ofs));                \
+    }                                                                         \
+  }
+  D3FK_TR_LEVEL(16, 4 * J)
+  D3FK_TR_LEVEL(8, 2 * J)
+  D3FK_TR_LEVEL(4, J)
+#undef D3FK_TR_LEVEL
+  const int which = (lane >> 4) & 1;
+  float* dst = which ? sstat_sq : sstat_sum;
+  if (CW == 32) {                           // idx = which:1 | j:2 | e:1 ; two survivors (e = 0, 1)
+    const int j = ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+    const int col = 8 * j + 2 * (lane & 3);
+    dst[col] += s[0];
+    dst[col + 1] += s[1];
+  } else {                                  // idx = which:1 | j:1 | e:1 ; one survivor
+    const int col = 8 * ((lane >> 3) & 1) + 2 * (lane & 3) + ((lane >> 2) & 1);
+    dst[col] += s[0];
+  }
 }
 
 struct EpiTC {

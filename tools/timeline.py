@@ -29,6 +29,8 @@ for op in ops:
     c = _lib.Op(); ctypes.memmove(ctypes.byref(c), ctypes.byref(op), ctypes.sizeof(_lib.Op))
     if c.kind == _lib.OP_CONV_BN:
         c.kind = _lib.OP_CONV
+    if os.environ.get('NOSTATS') == '1':
+        c.u.conv.stats = None      # timing experiment: epilogue without the batch-statistics reduction
     reps = 12
     ol = _lib.OpList([c] * reps)
     ol.run(s); torch.cuda.synchronize()
@@ -37,11 +39,11 @@ for op in ops:
     ol.run(s); torch.cuda.synchronize()
     n1 = ctypes.c_uint()
     lib.d3fk_debug_timeline(buf, 512 * 16, ctypes.byref(n1))
-    names = ["entry", "prologue", "pdl_wait", "first_data", "mma_issued", "acc_full", "epi_done", "exit", "chunk0", "chunks", "tiles_done"]
+    names = ["entry", "prologue", "pdl_wait", "first_data", "mma_issued", "acc_full", "epi_done", "exit", "chunk0", "chunks", "tiles_done", "csync1", "scattered", "csync2", "reduced", "flushed"]
     prev_exit = None
     print("launch: " + " ".join(f"{n:>10s}" for n in names) + "   (ns since this launch's entry; gap = entry - previous exit)")
     for i in range(n0.value, n1.value):
-        row = [buf[(i % 512) * 16 + k] for k in range(11)]
+        row = [buf[(i % 512) * 16 + k] for k in range(16)]
         gap = (row[0] - prev_exit) if prev_exit else 0
         print(f"{i:6d}: " + " ".join(f"{(v - row[0]) if v else -1:10d}" for v in row) + f"   gap {gap}")
         prev_exit = row[7]
