@@ -49,6 +49,7 @@ __device__ __forceinline__ void decode_tile(const TileSched& ts, int t, int& mt,
 struct FuseBN {
   const float* gamma; const float* beta;
   float* mean; float* invstd; float* running_mean; float* running_var; long long* nbt;
+  float* scale; float* shift;   // published for the backward pass (d3fk_bn_params.mask_from_x)
   bf16* act; const bf16* res;
   unsigned* barrier;         // zeroed by the forward's statistics memset
   long long count;
@@ -194,6 +195,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(Gather g, FastDi
       if (publisher) {
         fb.mean[ch] = (float)mean;
         fb.invstd[ch] = (float)invstd;
+        if (fb.scale) { fb.scale[ch] = s_stat[tid]; fb.shift[ch] = s_stat[BN + tid]; }
         if (fb.running_mean) {
           const double unbiased = n > 1 ? var * n / (n - 1) : var;
           fb.running_mean[ch] = (float)((1.0 - fb.momentum) * fb.running_mean[ch] + fb.momentum * mean);
@@ -211,7 +213,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(Gather g, FastDi
     for (int q = 0; q < ncol / 8; ++q) {
       float y[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) y[i] = fmaf(f[q * 8 + i], s_stat[ct + q * 8 + i], s_stat[BN + ct + q * 8 + i]);
+      for (int i = 0; i < 8; ++i)      // from the bf16-ROUNDED raw value: bit-identical to the two-kernel form (and to the backward's mask)
+        y[i] = fmaf(__bfloat162float(__float2bfloat16_rn(f[q * 8 + i])), s_stat[ct + q * 8 + i], s_stat[BN + ct + q * 8 + i]);
       if (fb.res) {
         const uint4 rr = __ldg(reinterpret_cast<const uint4*>(fb.res + m * fb.ldr + cbase + q * 8));
         const bf16* rb16 = reinterpret_cast<const bf16*>(&rr);
@@ -654,7 +657,7 @@ static int launch_conv_tc_bn(const Gather& g, const d3fk_conv_params* p, cudaStr
   if (BN == 128 && t_fuse && g_fuse_bn && p->stats && !p->scale && !p->shift && !p->res && !p->relu && !p->out_nchw && p->mode == 0 &&
       p->Cout % BN == 0 && ts.total <= cluster_capacity_safe(ts.KS)) {
     const d3fk_bn_params* b = t_fuse->bn;
-    fb.gamma = b->gamma; fb.beta = b->beta; fb.mean = b->mean; fb.invstd = b->invstd;
+    fb.gamma = b->gamma; fb.beta = b->beta; fb.mean = b->mean; fb.invstd = b->invstd; fb.scale = b->scale; fb.shift = b->shift;
     fb.running_mean = b->running_mean; fb.running_var = b->running_var; fb.nbt = (long long*)b->num_batches_tracked;
     fb.act = (bf16*)b->y; fb.res = (const bf16*)b->res; fb.barrier = t_fuse->barrier; fb.count = b->count;
     fb.ldact = b->ldy; fb.ldr = b->ldr; fb.relu = b->relu; fb.eps = b->eps; fb.momentum = b->momentum;

@@ -128,6 +128,7 @@ __global__ void __launch_bounds__(256, BN_BWD_OCC(T)) bn_apply_kernel(d3fk_bn_pa
       if (blockIdx.x == 0) {
         p.mean[ch] = (float)mean;
         p.invstd[ch] = (float)invstd;
+        if (p.scale) { p.scale[ch] = sc; p.shift[ch] = sh; }   // backward re-derives the ReLU mask from them (mask_from_x)
         if (p.running_mean) {
           const double unbiased = n > 1 ? var * n / (n - 1) : var;
           p.running_mean[ch] = (float)((1.0 - p.momentum) * p.running_mean[ch] + p.momentum * mean);
@@ -172,10 +173,14 @@ __global__ void __launch_bounds__(256, BN_BWD_OCC(T)) bn_apply_kernel(d3fk_bn_pa
   }
 }
 
+__device__ __forceinline__ void lds_volatile_f4(uint32_t addr, float (&v)[4]) {
+  asm volatile("ld.volatile.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(addr));
+}
+
 // per-channel sums of dy' and dy'*xhat ; dy' = relu ? (act>0 ? dy : 0) : dy.
 // Lanes of a warp that own the same channel vector are folded with shuffles, warps with one shared-memory
 // slot each, the block with one double atomic per channel.
-template <typename T, typename Acc>
+template <typename T, typename Acc, bool XMASK>
 __device__ __forceinline__ void bn_bwd_reduce_body(const d3fk_bn_params& p, double* sred) {
   constexpr int V = Vec<T>::N;
   const int C = p.C, cvs = C / V;
@@ -186,10 +191,20 @@ __device__ __forceinline__ void bn_bwd_reduce_body(const d3fk_bn_params& p, doub
   Acc s1[V], s2[V];
 #pragma unroll
   for (int i = 0; i < V; ++i) { s1[i] = 0; s2[i] = 0; }
+  constexpr bool xmask = XMASK;                      // p.relu && p.mask_from_x, resolved at launch (register budget)
+  float* s_ms = reinterpret_cast<float*>(sred);      // [2][C] scale, shift — aliases the reduction slots, dead until the loop ends
+  if (xmask) {
+    for (int ch = threadIdx.x; ch < C; ch += blockDim.x) { s_ms[ch] = p.scale[ch]; s_ms[C + ch] = p.shift[ch]; }
+    __syncthreads();
+  }
+  const uint32_t ms_addr = (uint32_t)__cvta_generic_to_shared(s_ms + c);
   if (prow < rows_per_iter) {
     float mean[V], istd[V];
 #pragma unroll
     for (int i = 0; i < V; ++i) { mean[i] = p.mean[c + i]; istd[i] = p.invstd[c + i]; }
+    // mask_from_x: act = relu(x * scale + shift) was computed from exactly these x, scale, shift — its sign is recomputed
+    // instead of streaming `act` a second and third time (2 of the 6 + 8 bytes per element of BN backward)
+    // (scale / shift are re-read from shared memory at every use: as 2 x V registers they spill the streaming loop)
     const T* x = (const T*)p.x;
     const T* dy = (const T*)p.dy;
     const T* act = (const T*)p.act;
@@ -203,28 +218,48 @@ __device__ __forceinline__ void bn_bwd_reduce_body(const d3fk_bn_params& p, doub
         if (pix < p.count) {
           xr[u] = load_raw<T>(x + pix * p.ldx + c);
           gr[u] = load_raw<T>(dy + pix * p.lddy + c);
-          if (p.relu) ar[u] = load_raw<T>(act + pix * p.ldact + c);
+          if (p.relu && !xmask) ar[u] = load_raw<T>(act + pix * p.ldact + c);
         }
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         if (pix0 + u * pstride < p.count) {
-          float xv[V], gv[V], av[V];
+          float xv[V], gv[V];
           unpack_vec<T>(xr[u], xv);
           unpack_vec<T>(gr[u], gv);
-          if (p.relu) unpack_vec<T>(ar[u], av);
+          if (xmask) {
 #pragma unroll
-          for (int i = 0; i < V; ++i) {
-            float g = gv[i];
-            if (p.relu && !(av[i] > 0.f)) g = 0.f;
-            float xh = (xv[i] - mean[i]) * istd[i];
-            s1[i] += (Acc)g;
-            s2[i] += (Acc)(g * xh);
+            for (int i4 = 0; i4 < V; i4 += 4) {
+              float kS[4], kT[4];
+              lds_volatile_f4(ms_addr + 4u * i4, kS);
+              lds_volatile_f4(ms_addr + 4u * (uint32_t)C + 4u * i4, kT);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int i = i4 + j;
+                float g = gv[i];
+                if (!(fmaf(xv[i], kS[j], kT[j]) > 0.f)) g = 0.f;
+                float xh = (xv[i] - mean[i]) * istd[i];
+                s1[i] += (Acc)g;
+                s2[i] += (Acc)(g * xh);
+              }
+            }
+          } else {
+            float av[V];
+            if (p.relu) unpack_vec<T>(ar[u], av);
+#pragma unroll
+            for (int i = 0; i < V; ++i) {
+              float g = gv[i];
+              if (p.relu && !(av[i] > 0.f)) g = 0.f;
+              float xh = (xv[i] - mean[i]) * istd[i];
+              s1[i] += (Acc)g;
+              s2[i] += (Acc)(g * xh);
+            }
           }
         }
       }
     }
   }
+  if (xmask) __syncthreads();     // the staged scale / shift are dead: the slots below overwrite them
   // fold lanes that share cv (lane stride cvs) when a warp holds several pixel rows
   if (cvs < 32) {
 #pragma unroll
@@ -263,11 +298,11 @@ __device__ __forceinline__ void bn_bwd_reduce_body(const d3fk_bn_params& p, doub
     atomicAdd(&p.bstats[which * C + ch], a);
   }
 }
-template <typename T, typename Acc>
+template <typename T, typename Acc, bool XMASK>
 __global__ void __launch_bounds__(256, BN_BWD_OCC(T)) bn_bwd_reduce_kernel(d3fk_bn_params p) {
   pdl_enter();
   extern __shared__ double sred_dyn[];  // [warps][2][C]
-  bn_bwd_reduce_body<T, Acc>(p, sred_dyn);
+  bn_bwd_reduce_body<T, Acc, XMASK>(p, sred_dyn);
 }
 
 __global__ void bn_bwd_finalize_kernel(d3fk_bn_params p) {
@@ -283,14 +318,11 @@ __global__ void bn_bwd_finalize_kernel(d3fk_bn_params p) {
   p.coef[2 * p.C + c] = (float)(s2 / n);
 }
 
-__device__ __forceinline__ void lds_volatile_f4(uint32_t addr, float (&v)[4]) {
-  asm volatile("ld.volatile.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(addr));
-}
 
 // dx = c0*(dy' - c1 - xhat*c2), c0 = gamma*invstd, c1 = sum(dy')/n, c2 = sum(dy'*xhat)/n; optionally dres = dy'.
 // The coefficients are derived in-kernel from the reduction sums; the first C/V threads of block 0 also write
 // dgamma / dbeta (no separate finalize launch).
-template <typename T>
+template <typename T, bool XMASK>
 __device__ __forceinline__ void bn_bwd_apply_body(const d3fk_bn_params& p, float* s_k) {
   constexpr int V = Vec<T>::N;
   const int cvs = p.C / V;
@@ -316,6 +348,10 @@ __device__ __forceinline__ void bn_bwd_apply_body(const d3fk_bn_params& p, float
     s_k[p.C + ch] = -A * is * (float)(s2 / n);
     s_k[2 * p.C + ch] = -A * (float)(s1 / n);
     s_k[3 * p.C + ch] = __ldg(p.mean + ch);
+    if (XMASK) {
+      s_k[4 * p.C + ch] = p.scale[ch];
+      s_k[5 * p.C + ch] = p.shift[ch];
+    }
     if (blockIdx.x == 0) {
       if (p.dbeta) p.dbeta[ch] = (float)s1;
       if (p.dgamma) p.dgamma[ch] = (float)s2;
@@ -325,6 +361,7 @@ __device__ __forceinline__ void bn_bwd_apply_body(const d3fk_bn_params& p, float
   const uint32_t sk_addr = (uint32_t)__cvta_generic_to_shared(s_k + c);
   const uint32_t sk_pitch = (uint32_t)p.C * 4u;
   constexpr int U = 2;   // independent pixel vectors in flight per thread (3 loads each), held packed until used
+  constexpr bool xmask = XMASK;
   // Walk the tensor BACKWARDS: the reduction pass that ran just before streamed x, dy and act front to back, so their
   // tails are what the 126 MB L2 still holds.
   const long long last_pix = p.count - 1;
@@ -339,7 +376,7 @@ __device__ __forceinline__ void bn_bwd_apply_body(const d3fk_bn_params& p, float
         const long long pix = pixb - u * pstep;
         xr[u] = load_raw<T>(x + pix * p.ldx + c);
         gr[u] = load_raw<T>(dy + pix * p.lddy + c);
-        if (p.relu) ar[u] = load_raw<T>(act + pix * p.ldact + c);
+        if (p.relu && !xmask) ar[u] = load_raw<T>(act + pix * p.ldact + c);
       }
     }
 #pragma unroll
@@ -350,7 +387,7 @@ __device__ __forceinline__ void bn_bwd_apply_body(const d3fk_bn_params& p, float
         float xv[V], gv[V], av[V], o[V];
         unpack_vec<T>(xr[u], xv);
         unpack_vec<T>(gr[u], gv);
-        if (p.relu) unpack_vec<T>(ar[u], av);
+        if (p.relu && !xmask) unpack_vec<T>(ar[u], av);
 #pragma unroll
         for (int i4 = 0; i4 < V; i4 += 4) {
           float kA[4], kB[4], kC[4], kM[4];
@@ -358,6 +395,13 @@ __device__ __forceinline__ void bn_bwd_apply_body(const d3fk_bn_params& p, float
           lds_volatile_f4(sk_addr + sk_pitch + 4u * i4, kB);
           lds_volatile_f4(sk_addr + 2u * sk_pitch + 4u * i4, kC);
           lds_volatile_f4(sk_addr + 3u * sk_pitch + 4u * i4, kM);
+          if (xmask) {
+            float kS[4], kT[4];
+            lds_volatile_f4(sk_addr + 4u * sk_pitch + 4u * i4, kS);
+            lds_volatile_f4(sk_addr + 5u * sk_pitch + 4u * i4, kT);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) av[i4 + j] = fmaf(xv[i4 + j], kS[j], kT[j]);
+          }
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int i = i4 + j;
@@ -374,24 +418,24 @@ __device__ __forceinline__ void bn_bwd_apply_body(const d3fk_bn_params& p, float
   }
 }
 
-template <typename T>
+template <typename T, bool XMASK>
 __global__ void __launch_bounds__(256, BN_BWD_OCC(T)) bn_bwd_apply_kernel(d3fk_bn_params p) {
   pdl_enter();
   extern __shared__ float s_k_dyn[];
-  bn_bwd_apply_body<T>(p, s_k_dyn);
+  bn_bwd_apply_body<T, XMASK>(p, s_k_dyn);
 }
 
 // BN backward in ONE launch for a co-resident grid: reduction, grid barrier, apply (the tensors of the deep layers are a
 // few MB — the second read comes from L2 and a kernel boundary costs more than the barrier).
-template <typename T, typename Acc>
+template <typename T, typename Acc, bool XMASK>
 __global__ void __launch_bounds__(256, 2) bn_bwd_kernel(d3fk_bn_params p, int* errflag) {
   pdl_enter();
   extern __shared__ double smem_bwd[];
-  bn_bwd_reduce_body<T, Acc>(p, smem_bwd);
+  bn_bwd_reduce_body<T, Acc, XMASK>(p, smem_bwd);
   __syncthreads();
   if (threadIdx.x == 0) grid_barrier_arrive_wait(p.barrier, gridDim.x, errflag);
   __syncthreads();
-  bn_bwd_apply_body<T>(p, reinterpret_cast<float*>(smem_bwd));
+  bn_bwd_apply_body<T, XMASK>(p, reinterpret_cast<float*>(smem_bwd));
 }
 
 // element index -> (pixel, channel vector, w, h, n) of a [n][h][w][cvs] walk.  32-bit arithmetic whenever the index fits
@@ -935,9 +979,15 @@ int launch_bn_bwd_reduce(const d3fk_bn_params* p, cudaStream_t s) {
   if (grid < 1) grid = 1;
   const int slotC = cvs < 32 ? p->C : 32 * V;
   size_t smem = (size_t)(threads / 32) * 2 * slotC * sizeof(double);
-  if (p->dtype == D3FK_F32) launch_k(bn_bwd_reduce_kernel<float, double>, dim3(grid), dim3(threads), smem, s, dim3(1, 1, 1), *p);
-  else if (p->dtype == D3FK_BF16) launch_k(bn_bwd_reduce_kernel<__nv_bfloat16, float>, dim3(grid), dim3(threads), smem, s, dim3(1, 1, 1), *p);
-  else return set_error(D3FK_ERR_ARG, "bad dtype");
+  const bool xm = p->relu && p->mask_from_x;
+  D3FK_CHECK_ARG(!xm || (p->scale && p->shift), "mask_from_x needs scale / shift");
+  if (p->dtype == D3FK_F32) {
+    if (xm) launch_k(bn_bwd_reduce_kernel<float, double, true>, dim3(grid), dim3(threads), smem, s, dim3(1, 1, 1), *p);
+    else launch_k(bn_bwd_reduce_kernel<float, double, false>, dim3(grid), dim3(threads), smem, s, dim3(1, 1, 1), *p);
+  } else if (p->dtype == D3FK_BF16) {
+    if (xm) launch_k(bn_bwd_reduce_kernel<__nv_bfloat16, float, true>, dim3(grid), dim3(threads), smem, s, dim3(1, 1, 1), *p);
+    else launch_k(bn_bwd_reduce_kernel<__nv_bfloat16, float, false>, dim3(grid), dim3(threads), smem, s, dim3(1, 1, 1), *p);
+  } else return set_error(D3FK_ERR_ARG, "bad dtype");
   count_launch();
   return check_launch("bn_bwd_reduce");
 }
@@ -951,7 +1001,10 @@ int launch_bn_bwd_apply(const d3fk_bn_params* p, cudaStream_t s) {
   int V = p->dtype == D3FK_F32 ? 4 : 8;
   long long total = p->count * (p->C / V);
   D3FK_CHECK_ARG(256 % (p->C / V) == 0, "C / vector width must divide 256 (the kernel's channel vector is loop invariant)");
-  DISPATCH_T(p->dtype, launch_k(bn_bwd_apply_kernel<T>, dim3(grid_for(total, 256 * 4, D3FK_BN_BWD_BLOCKS)), dim3(256), 5 * p->C * sizeof(float), s, dim3(1, 1, 1), *p));
+  const bool xm = p->relu && p->mask_from_x;
+  D3FK_CHECK_ARG(!xm || (p->scale && p->shift), "mask_from_x needs scale / shift");
+  if (xm) { DISPATCH_T(p->dtype, launch_k(bn_bwd_apply_kernel<T, true>, dim3(grid_for(total, 256 * 4, D3FK_BN_BWD_BLOCKS)), dim3(256), 6 * p->C * sizeof(float), s, dim3(1, 1, 1), *p)); }
+  else { DISPATCH_T(p->dtype, launch_k(bn_bwd_apply_kernel<T, false>, dim3(grid_for(total, 256 * 4, D3FK_BN_BWD_BLOCKS)), dim3(256), 6 * p->C * sizeof(float), s, dim3(1, 1, 1), *p)); }
   count_launch();
   return check_launch("bn_bwd_apply");
 }
@@ -973,11 +1026,17 @@ int launch_bn_bwd(const d3fk_bn_params* p, cudaStream_t s) {
   if (grid < 1) grid = 1;
   const int slotC = cvs < 32 ? p->C : 32 * V;
   size_t smem = (size_t)(threads / 32) * 2 * slotC * sizeof(double);
-  const size_t smem_apply = 5 * (size_t)p->C * sizeof(float);
+  const size_t smem_apply = 6 * (size_t)p->C * sizeof(float);
   if (smem_apply > smem) smem = smem_apply;
-  if (p->dtype == D3FK_F32) launch_k(bn_bwd_kernel<float, double>, dim3(grid), dim3(threads), smem, s, dim3(1, 1, 1), *p, g_dev_error_flag);
-  else if (p->dtype == D3FK_BF16) launch_k(bn_bwd_kernel<__nv_bfloat16, float>, dim3(grid), dim3(threads), smem, s, dim3(1, 1, 1), *p, g_dev_error_flag);
-  else return set_error(D3FK_ERR_ARG, "bad dtype");
+  const bool xm = p->relu && p->mask_from_x;
+  D3FK_CHECK_ARG(!xm || (p->scale && p->shift), "mask_from_x needs scale / shift");
+  if (p->dtype == D3FK_F32) {
+    if (xm) launch_k(bn_bwd_kernel<float, double, true>, dim3(grid), dim3(threads), smem, s, dim3(1, 1, 1), *p, g_dev_error_flag);
+    else launch_k(bn_bwd_kernel<float, double, false>, dim3(grid), dim3(threads), smem, s, dim3(1, 1, 1), *p, g_dev_error_flag);
+  } else if (p->dtype == D3FK_BF16) {
+    if (xm) launch_k(bn_bwd_kernel<__nv_bfloat16, float, true>, dim3(grid), dim3(threads), smem, s, dim3(1, 1, 1), *p, g_dev_error_flag);
+    else launch_k(bn_bwd_kernel<__nv_bfloat16, float, false>, dim3(grid), dim3(threads), smem, s, dim3(1, 1, 1), *p, g_dev_error_flag);
+  } else return set_error(D3FK_ERR_ARG, "bad dtype");
   count_launch();
   return check_launch("bn_bwd");
 }

@@ -485,6 +485,9 @@ class UnetPlan:
             g_masked = T(self, raw.B, raw.H, raw.W, raw.C)
             self.keep.append(g_masked.t)
             bn.update(dres=g_masked.ptr, lddres=g_masked.ld)
+        # no residual in the forward: act = relu(raw * scale + shift) exactly, so backward re-derives the ReLU mask from
+        # raw (which it streams anyway) and the scale / shift the forward published instead of reading act
+        bn["mask_from_x"] = 1 if (sv["res"] is None and sv["relu"]) else 0
         bn.pop("res", None)
         bn.pop("ldr", None)
         fuse = self.dtype == _lib.BF16 and raw.B * raw.H * raw.W * raw.C <= FUSE_BN_BWD_MAX_ELEMS

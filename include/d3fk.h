@@ -110,7 +110,9 @@ typedef struct d3fk_pack_params {
  * coefficients from bstats/mean/invstd/gamma and writes dgamma/dbeta; bn_finalize / bn_bwd_finalize remain as
  * stand-alone entry points. */
 typedef struct d3fk_bn_params {
-  int32_t dtype, C, relu, _pad0;
+  int32_t dtype, C, relu;
+  int32_t mask_from_x;                  /* backward: ReLU mask = (x*scale + shift > 0) instead of reading `act` — valid when the
+                                           forward had no residual (train forward publishes scale / shift for this) */
   int64_t count;                        /* B*H*W */
   const void* x; void* y; const void* res;
   int32_t ldx, ldy, ldr, _pad1;

@@ -94,7 +94,7 @@ s = torch.cuda.current_stream().cuda_stream
 report("pack", plan.pack_ops, s, top=5)
 report("train forward", plan.fwd_ops, s, a.top)
 for i, seg in enumerate(plan.bwd_segments):
-    report(f"backward segment {i}", seg, s, a.top if i == 0 else 12)
+    report(f"backward segment {i}", seg, s, a.top if (i == 0 or a.top > 100) else 12)
 # whole-step pieces outside the plan
 import time
 def timed(fn, n=5):
