@@ -303,7 +303,7 @@ def run_d3fk(args):
     # W untimed warm-up steps (at least 3) — and, because W steps of a 4 ms step are over before the GPU has settled at its
     # boost clocks, 64 more untimed steps (≈0.3 s; a fixed count, identical on every rank: each step is a collective).
     # Reported as "warmup_actual"; the timed region is untouched.
-    n_warm = max(args.warmup, 3) + 64
+    n_warm = max(args.warmup, 3) + int(os.environ.get("D3FK_BENCH_EXTRA_WARMUP", "64"))   # (0 for ncu launch lists)
     for _ in range(n_warm):
         loss = mod.training_step(x)
     barrier()
