@@ -12,8 +12,13 @@
 
 namespace d3fk {
 
-template <int BN> struct ConvCfg {
-  static constexpr int STAGES = BN >= 128 ? 3 : 4;
+// Pipeline depth.  In the eval forward (FUSE 3: the sampler) 128-wide tiles fed by TMA (PATH 2) run ONE CTA per SM with six
+// stages (198 KB): a single CTA needs ~200 KB in flight to cover latency x bandwidth of the L2 -> SM operand stream
+// (layer3-size tile: 14.3 -> 12.6 us, sampling step 0.896 -> 0.863 ms).  Training keeps three stages / two CTAs per SM:
+// measured 3.77 -> 3.83 ms per step with six — a 198 KB CTA leaves no room for a weight-gradient CTA of the side stream
+// next to it, and that overlap is worth more than the faster main loop.
+template <int BN, int PATH, int FUSE> struct ConvCfg {
+  static constexpr int STAGES = BN >= 128 ? ((PATH == 2 && FUSE == 3) ? 6 : 3) : 4;
   static constexpr int B_STAGE_BYTES = BN * 128;
   static constexpr int SMEM = 1024 + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256 + 10 * BN * 4;
   static constexpr int ACC_COLS = BN < 32 ? 32 : BN;   // one accumulator buffer
@@ -68,7 +73,7 @@ template <int BN, int PATH, int FUSE>
 __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(Gather g, FastDiv dWo, FastDiv dHo, const __grid_constant__ CUtensorMap tmA,
                                                              const __grid_constant__ CUtensorMap tmB, EpiTC e, TileSched ts,
                                                              FuseBN fb, int* errflag) {
-  using Cfg = ConvCfg<BN>;
+  using Cfg = ConvCfg<BN, PATH, FUSE>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int CW = BN >= 32 ? 32 : 16;
   extern __shared__ uint8_t smem_raw[];
@@ -627,8 +632,10 @@ static int launch_conv_tc_bn(const Gather& g, const d3fk_conv_params* p, cudaStr
     ts.kb_per_split = ts.nkb;
   }
   ts.total = tiles * ts.KS;
-  int occ = (227 * 1024) / (ConvCfg<BN>::SMEM + 1024);
-  if (occ * ConvCfg<BN>::TMEM_COLS > 512) occ = 512 / ConvCfg<BN>::TMEM_COLS;
+  const bool eval_affine = !p->bw_x && (p->scale || p->shift);      // launches the FUSE 3 variant below
+  const int smem_bytes = eval_affine ? ConvCfg<BN, PATH, 3>::SMEM : ConvCfg<BN, PATH, 0>::SMEM;
+  int occ = (227 * 1024) / (smem_bytes + 1024);
+  if (occ * ConvCfg<BN, PATH, 0>::TMEM_COLS > 512) occ = 512 / ConvCfg<BN, PATH, 0>::TMEM_COLS;
   if (g_occ_cap > 0 && occ > g_occ_cap) occ = g_occ_cap;
   int grid = ts.total < g_num_sms * occ ? ts.total : g_num_sms * occ;
   if (!g_tile_loop || ts.KS > 1) grid = ts.total;
@@ -668,16 +675,16 @@ static int launch_conv_tc_bn(const Gather& g, const d3fk_conv_params* p, cudaStr
   if (g_verbose) fprintf(stderr, "[d3fk] conv<%d,%d> mode=%d M=%d K=%d Cout=%d tiles=%d KS=%d kbps=%d grid=%d fuse=%d\n", BN, PATH, g.mode, g.M, g.K, p->Cout, tiles, ts.KS, ts.kb_per_split, grid, (int)fuse);
   cudaError_t le;
   if (p->bw_x)
-    le = launch_k(conv_tc_kernel<BN, PATH, 2>, dim3(grid), dim3(TC_THREADS), ConvCfg<BN>::SMEM, s, dim3(ts.KS, 1, 1), g,
+    le = launch_k(conv_tc_kernel<BN, PATH, 2>, dim3(grid), dim3(TC_THREADS), ConvCfg<BN, PATH, 2>::SMEM, s, dim3(ts.KS, 1, 1), g,
                   make_fastdiv((uint32_t)g.Wo), make_fastdiv((uint32_t)g.Ho), tmA, tmB, e, ts, fb, g_dev_error_flag);
   else if (BN == 128 && fuse)
-    le = launch_k(conv_tc_kernel<BN, PATH, (BN == 128 ? 1 : 0)>, dim3(grid), dim3(TC_THREADS), ConvCfg<BN>::SMEM, s, dim3(ts.KS, 1, 1), g,
+    le = launch_k(conv_tc_kernel<BN, PATH, (BN == 128 ? 1 : 0)>, dim3(grid), dim3(TC_THREADS), ConvCfg<BN, PATH, 1>::SMEM, s, dim3(ts.KS, 1, 1), g,
                   make_fastdiv((uint32_t)g.Wo), make_fastdiv((uint32_t)g.Ho), tmA, tmB, e, ts, fb, g_dev_error_flag);
   else if (p->scale || p->shift)
-    le = launch_k(conv_tc_kernel<BN, PATH, 3>, dim3(grid), dim3(TC_THREADS), ConvCfg<BN>::SMEM, s, dim3(ts.KS, 1, 1), g,
+    le = launch_k(conv_tc_kernel<BN, PATH, 3>, dim3(grid), dim3(TC_THREADS), ConvCfg<BN, PATH, 3>::SMEM, s, dim3(ts.KS, 1, 1), g,
                   make_fastdiv((uint32_t)g.Wo), make_fastdiv((uint32_t)g.Ho), tmA, tmB, e, ts, fb, g_dev_error_flag);
   else
-    le = launch_k(conv_tc_kernel<BN, PATH, 0>, dim3(grid), dim3(TC_THREADS), ConvCfg<BN>::SMEM, s, dim3(ts.KS, 1, 1), g,
+    le = launch_k(conv_tc_kernel<BN, PATH, 0>, dim3(grid), dim3(TC_THREADS), ConvCfg<BN, PATH, 0>::SMEM, s, dim3(ts.KS, 1, 1), g,
                   make_fastdiv((uint32_t)g.Wo), make_fastdiv((uint32_t)g.Ho), tmA, tmB, e, ts, fb, g_dev_error_flag);
   if (le != cudaSuccess) return set_error(D3FK_ERR_CUDA, "conv_tc launch: %s", cudaGetErrorString(le));
   count_launch();
@@ -772,45 +779,45 @@ int tc_init() {
   if (const char* v = getenv("D3FK_CLUSTER")) g_max_cluster = atoi(v);
   if (const char* v = getenv("D3FK_FUSE_BN")) g_fuse_bn = atoi(v);
 #endif
-  D3FK_SET_SMEM((conv_tc_kernel<16, 0, 0>), ConvCfg<16>::SMEM)
-  D3FK_SET_SMEM((conv_tc_kernel<32, 0, 0>), ConvCfg<32>::SMEM)
-  D3FK_SET_SMEM((conv_tc_kernel<64, 0, 0>), ConvCfg<64>::SMEM)
-  D3FK_SET_SMEM((conv_tc_kernel<128, 0, 0>), ConvCfg<128>::SMEM)
-  D3FK_SET_SMEM((conv_tc_kernel<16, 1, 0>), ConvCfg<16>::SMEM)
-  D3FK_SET_SMEM((conv_tc_kernel<32, 1, 0>), ConvCfg<32>::SMEM)
-  D3FK_SET_SMEM((conv_tc_kernel<64, 1, 0>), ConvCfg<64>::SMEM)
-  D3FK_SET_SMEM((conv_tc_kernel<128, 1, 0>), ConvCfg<128>::SMEM)
-  D3FK_SET_SMEM((conv_tc_kernel<16, 2, 0>), ConvCfg<16>::SMEM)
-  D3FK_SET_SMEM((conv_tc_kernel<32, 2, 0>), ConvCfg<32>::SMEM)
-  D3FK_SET_SMEM((conv_tc_kernel<64, 2, 0>), ConvCfg<64>::SMEM)
-  D3FK_SET_SMEM((conv_tc_kernel<128, 2, 0>), ConvCfg<128>::SMEM)
-  D3FK_SET_SMEM((conv_tc_kernel<16, 0, 2>), ConvCfg<16>::SMEM)
-  D3FK_SET_SMEM((conv_tc_kernel<16, 1, 2>), ConvCfg<16>::SMEM)
-  D3FK_SET_SMEM((conv_tc_kernel<16, 2, 2>), ConvCfg<16>::SMEM)
-  D3FK_SET_SMEM((conv_tc_kernel<32, 0, 2>), ConvCfg<32>::SMEM)
-  D3FK_SET_SMEM((conv_tc_kernel<32, 1, 2>), ConvCfg<32>::SMEM)
-  D3FK_SET_SMEM((conv_tc_kernel<32, 2, 2>), ConvCfg<32>::SMEM)
-  D3FK_SET_SMEM((conv_tc_kernel<64, 0, 2>), ConvCfg<64>::SMEM)
-  D3FK_SET_SMEM((conv_tc_kernel<64, 1, 2>), ConvCfg<64>::SMEM)
-  D3FK_SET_SMEM((conv_tc_kernel<64, 2, 2>), ConvCfg<64>::SMEM)
-  D3FK_SET_SMEM((conv_tc_kernel<128, 0, 2>), ConvCfg<128>::SMEM)
-  D3FK_SET_SMEM((conv_tc_kernel<128, 1, 2>), ConvCfg<128>::SMEM)
-  D3FK_SET_SMEM((conv_tc_kernel<128, 2, 2>), ConvCfg<128>::SMEM)
-  D3FK_SET_SMEM((conv_tc_kernel<128, 0, 1>), ConvCfg<128>::SMEM)
-  D3FK_SET_SMEM((conv_tc_kernel<128, 1, 1>), ConvCfg<128>::SMEM)
-  D3FK_SET_SMEM((conv_tc_kernel<128, 2, 1>), ConvCfg<128>::SMEM)
-  D3FK_SET_SMEM((conv_tc_kernel<16, 0, 3>), ConvCfg<16>::SMEM)
-  D3FK_SET_SMEM((conv_tc_kernel<16, 1, 3>), ConvCfg<16>::SMEM)
-  D3FK_SET_SMEM((conv_tc_kernel<16, 2, 3>), ConvCfg<16>::SMEM)
-  D3FK_SET_SMEM((conv_tc_kernel<32, 0, 3>), ConvCfg<32>::SMEM)
-  D3FK_SET_SMEM((conv_tc_kernel<32, 1, 3>), ConvCfg<32>::SMEM)
-  D3FK_SET_SMEM((conv_tc_kernel<32, 2, 3>), ConvCfg<32>::SMEM)
-  D3FK_SET_SMEM((conv_tc_kernel<64, 0, 3>), ConvCfg<64>::SMEM)
-  D3FK_SET_SMEM((conv_tc_kernel<64, 1, 3>), ConvCfg<64>::SMEM)
-  D3FK_SET_SMEM((conv_tc_kernel<64, 2, 3>), ConvCfg<64>::SMEM)
-  D3FK_SET_SMEM((conv_tc_kernel<128, 0, 3>), ConvCfg<128>::SMEM)
-  D3FK_SET_SMEM((conv_tc_kernel<128, 1, 3>), ConvCfg<128>::SMEM)
-  D3FK_SET_SMEM((conv_tc_kernel<128, 2, 3>), ConvCfg<128>::SMEM)
+  D3FK_SET_SMEM((conv_tc_kernel<16, 0, 0>), (ConvCfg<16, 0, 0>::SMEM))
+  D3FK_SET_SMEM((conv_tc_kernel<32, 0, 0>), (ConvCfg<32, 0, 0>::SMEM))
+  D3FK_SET_SMEM((conv_tc_kernel<64, 0, 0>), (ConvCfg<64, 0, 0>::SMEM))
+  D3FK_SET_SMEM((conv_tc_kernel<128, 0, 0>), (ConvCfg<128, 0, 0>::SMEM))
+  D3FK_SET_SMEM((conv_tc_kernel<16, 1, 0>), (ConvCfg<16, 1, 0>::SMEM))
+  D3FK_SET_SMEM((conv_tc_kernel<32, 1, 0>), (ConvCfg<32, 1, 0>::SMEM))
+  D3FK_SET_SMEM((conv_tc_kernel<64, 1, 0>), (ConvCfg<64, 1, 0>::SMEM))
+  D3FK_SET_SMEM((conv_tc_kernel<128, 1, 0>), (ConvCfg<128, 1, 0>::SMEM))
+  D3FK_SET_SMEM((conv_tc_kernel<16, 2, 0>), (ConvCfg<16, 2, 0>::SMEM))
+  D3FK_SET_SMEM((conv_tc_kernel<32, 2, 0>), (ConvCfg<32, 2, 0>::SMEM))
+  D3FK_SET_SMEM((conv_tc_kernel<64, 2, 0>), (ConvCfg<64, 2, 0>::SMEM))
+  D3FK_SET_SMEM((conv_tc_kernel<128, 2, 0>), (ConvCfg<128, 2, 0>::SMEM))
+  D3FK_SET_SMEM((conv_tc_kernel<16, 0, 2>), (ConvCfg<16, 0, 2>::SMEM))
+  D3FK_SET_SMEM((conv_tc_kernel<16, 1, 2>), (ConvCfg<16, 1, 2>::SMEM))
+  D3FK_SET_SMEM((conv_tc_kernel<16, 2, 2>), (ConvCfg<16, 2, 2>::SMEM))
+  D3FK_SET_SMEM((conv_tc_kernel<32, 0, 2>), (ConvCfg<32, 0, 2>::SMEM))
+  D3FK_SET_SMEM((conv_tc_kernel<32, 1, 2>), (ConvCfg<32, 1, 2>::SMEM))
+  D3FK_SET_SMEM((conv_tc_kernel<32, 2, 2>), (ConvCfg<32, 2, 2>::SMEM))
+  D3FK_SET_SMEM((conv_tc_kernel<64, 0, 2>), (ConvCfg<64, 0, 2>::SMEM))
+  D3FK_SET_SMEM((conv_tc_kernel<64, 1, 2>), (ConvCfg<64, 1, 2>::SMEM))
+  D3FK_SET_SMEM((conv_tc_kernel<64, 2, 2>), (ConvCfg<64, 2, 2>::SMEM))
+  D3FK_SET_SMEM((conv_tc_kernel<128, 0, 2>), (ConvCfg<128, 0, 2>::SMEM))
+  D3FK_SET_SMEM((conv_tc_kernel<128, 1, 2>), (ConvCfg<128, 1, 2>::SMEM))
+  D3FK_SET_SMEM((conv_tc_kernel<128, 2, 2>), (ConvCfg<128, 2, 2>::SMEM))
+  D3FK_SET_SMEM((conv_tc_kernel<128, 0, 1>), (ConvCfg<128, 0, 1>::SMEM))
+  D3FK_SET_SMEM((conv_tc_kernel<128, 1, 1>), (ConvCfg<128, 1, 1>::SMEM))
+  D3FK_SET_SMEM((conv_tc_kernel<128, 2, 1>), (ConvCfg<128, 2, 1>::SMEM))
+  D3FK_SET_SMEM((conv_tc_kernel<16, 0, 3>), (ConvCfg<16, 0, 3>::SMEM))
+  D3FK_SET_SMEM((conv_tc_kernel<16, 1, 3>), (ConvCfg<16, 1, 3>::SMEM))
+  D3FK_SET_SMEM((conv_tc_kernel<16, 2, 3>), (ConvCfg<16, 2, 3>::SMEM))
+  D3FK_SET_SMEM((conv_tc_kernel<32, 0, 3>), (ConvCfg<32, 0, 3>::SMEM))
+  D3FK_SET_SMEM((conv_tc_kernel<32, 1, 3>), (ConvCfg<32, 1, 3>::SMEM))
+  D3FK_SET_SMEM((conv_tc_kernel<32, 2, 3>), (ConvCfg<32, 2, 3>::SMEM))
+  D3FK_SET_SMEM((conv_tc_kernel<64, 0, 3>), (ConvCfg<64, 0, 3>::SMEM))
+  D3FK_SET_SMEM((conv_tc_kernel<64, 1, 3>), (ConvCfg<64, 1, 3>::SMEM))
+  D3FK_SET_SMEM((conv_tc_kernel<64, 2, 3>), (ConvCfg<64, 2, 3>::SMEM))
+  D3FK_SET_SMEM((conv_tc_kernel<128, 0, 3>), (ConvCfg<128, 0, 3>::SMEM))
+  D3FK_SET_SMEM((conv_tc_kernel<128, 1, 3>), (ConvCfg<128, 1, 3>::SMEM))
+  D3FK_SET_SMEM((conv_tc_kernel<128, 2, 3>), (ConvCfg<128, 2, 3>::SMEM))
   if (e != cudaSuccess) return set_error(D3FK_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   int rc = slab_init();
   if (rc) return rc;
