@@ -31,11 +31,19 @@ struct WgGroup {
   float* dw[D3FK_WGRAD_GROUP_MAX];
 };
 
-template <int BN>
+// TMA variant (3x3-style "same" convolutions at stride 1 with Cin % 64 == 0 and power-of-two extents — the 33 encoder /
+// decoder-conv2 weight gradients of the step): a 64-pixel block is an axis-aligned (w, h, n) box, so one column block of the
+// A stage (64 channels of one tap for 64 pixels) is ONE cp.async.bulk.tensor.4d — shifted by the tap, hardware zero fill for
+// the halo — and the dY tile is a 2-D box per 64 output channels.  One elected thread of warp 0 is the producer; nobody
+// computes an address (the gather variant issues 16 cp.async and ~150 instructions per thread and stage).
+struct WgBox { int bw, bh, bn, wt, ht; };
+template <int BN, bool TMA>
 __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(Gather g, FastDiv dWo, FastDiv dHo, const bf16* __restrict__ dy_one,
                                                               int ldy, int Cout, float* __restrict__ dw_one, int cin_real,
                                                               int cout_real, int blocks_per_split, int lbo_a, int lbo_b,
-                                                              int CL, int* errflag, const __grid_constant__ WgGroup grp) {
+                                                              int CL, int* errflag, const __grid_constant__ WgGroup grp,
+                                                              const __grid_constant__ CUtensorMap tmA,
+                                                              const __grid_constant__ CUtensorMap tmD, WgBox box) {
   using Cfg = WgradCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int CW = 32;
@@ -65,11 +73,15 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(Gather g, FastDiv 
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar(s), 128);
+      mbar_init(full_bar(s), TMA ? 1 : 128);
       mbar_init(empty_bar(s), 1);
     }
     mbar_init(accum_bar, 1);
     fence_barrier_init();
+  }
+  if (TMA && warp == 0 && elect_one_sync()) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmD);
   }
   if (warp == 4) tmem_alloc(smem_u32((const void*)tmem_ptr_slot), Cfg::TMEM_COLS);
   tc_fence_before();
@@ -97,6 +109,39 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(Gather g, FastDiv 
   };
 
   if (warp < 4) {
+    if (TMA) {
+      // ===================== TMA producer (one elected thread of warp 0) =====================
+      if (warp == 0 && elect_one_sync()) {
+        int kc[2], dh[2], dwv[2];
+        bool kok[2];
+#pragma unroll
+        for (int cb = 0; cb < 2; ++cb) {
+          const int k = k0 + cb * 64;
+          kok[cb] = k < g.K;
+          const int tap = kok[cb] ? k / g.ctot : 0;
+          kc[cb] = kok[cb] ? k - tap * g.ctot : 0;
+          const int khi = tap / g.kw;
+          dh[cb] = khi - g.pad;
+          dwv[cb] = tap - khi * g.kw - g.pad;
+        }
+        const uint32_t tx = (uint32_t)(((kok[0] ? 1 : 0) + (kok[1] ? 1 : 0) + Cfg::NCB) * (WG_PIX * 128));
+        for (int it = 0; it < nblk; ++it) {
+          const int s = it % STAGES;
+          if (it >= STAGES) mbar_wait(empty_bar(s), ((it / STAGES) - 1) & 1, errflag);
+          const int blk = blk_beg + it;
+          const int tw = blk % box.wt, r2 = blk / box.wt;
+          const int w0 = tw * box.bw, h0 = (r2 % box.ht) * box.bh, n0 = (r2 / box.ht) * box.bn;
+          mbar_arrive_expect_tx(full_bar(s), tx);
+#pragma unroll
+          for (int cb = 0; cb < 2; ++cb)      // (a column block beyond K is not loaded: its accumulator rows are never stored)
+            if (kok[cb]) tma_load_4d(a_base + s * WG_A_STAGE + cb * (WG_PIX * 128), &tmA, kc[cb], w0 + dwv[cb], h0 + dh[cb], n0, full_bar(s));
+#pragma unroll
+          for (int cb = 0; cb < Cfg::NCB; ++cb)
+            tma_load_2d(b_base + s * Cfg::B_STAGE + cb * (WG_PIX * 128), &tmD, co0 + cb * 64, blk * WG_PIX, full_bar(s));
+        }
+      }
+      __syncwarp();
+    }
     const int j = tid & 7;
     const int rb = tid >> 3;  // pixel rows rb + 16*i, i < 4
     const uint32_t sw = (uint32_t)((j ^ (rb & 7)) << 4);
@@ -119,7 +164,7 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(Gather g, FastDiv 
       shs[cb] = g.Hi >> sup[cb];
       sws[cb] = g.Wi >> sup[cb];
     }
-    for (int it = 0; it < nblk; ++it) {
+    for (int it = 0; it < (TMA ? 0 : nblk); ++it) {
       const int s = it % STAGES;
       if (it >= STAGES) mbar_wait(empty_bar(s), ((it / STAGES) - 1) & 1, errflag);
       const int mbase = (blk_beg + it) * WG_PIX;
@@ -252,9 +297,51 @@ static int g_wg_plain = 1;   // D3FK_WG_PLAIN=0: launch cluster-size-1 grids thr
 // stays available to the main chain.
 static int g_wg_group_occ = 2;
 
+static int g_wg_tma = 1;     // D3FK_WG_TMA=0 (debug builds): always gather
+
+// TMA eligibility of the generic weight gradient: single source, no upsample, stride 1, "same" geometry, Cin % 64 == 0, and
+// the 64-pixel block an axis-aligned (w, h, n) box in linear pixel order (as tma_box() of the convolution, with 64 pixels).
+static bool wg_tma_box(const Gather& g, const d3fk_wgrad_params* p, WgBox& b) {
+  if (!g_wg_tma) return false;
+  if (p->c1 != 0 || p->src1 || p->up0 != 0 || p->stride != 1 || g.ctot % 64 != 0) return false;
+  if (p->Ho != p->Hi || p->Wo != p->Wi || 2 * p->pad != p->kh - 1 || p->kh != p->kw) return false;
+  if (((uintptr_t)p->src0 & 15) || ((uintptr_t)p->dy & 15) || (g.ld0 % 8) || (p->ldy % 8)) return false;
+  const int W = p->Wi, H = p->Hi;
+  int bw = W < WG_PIX ? W : WG_PIX;
+  if (WG_PIX % bw || W % bw) return false;
+  int bh = WG_PIX / bw;
+  if (bh > H) bh = H;
+  if ((WG_PIX / bw) % bh || H % bh) return false;
+  const int bn = WG_PIX / (bw * bh);
+  if (bw < W && bh != 1) return false;
+  if (bh < H && bn != 1) return false;
+  if (bn > 256) return false;
+  b.bw = bw; b.bh = bh; b.bn = bn; b.wt = W / bw; b.ht = H / bh;
+  return true;
+}
+
 template <int BN>
 static int launch_wgrad_tc_bn(const Gather& g, const d3fk_wgrad_params* p, cudaStream_t s, const d3fk_wgrad_group_params* group = nullptr) {
   const int gx = cdiv(g.K, 128), gy = cdiv(p->Cout, BN);
+  WgBox box;
+  memset(&box, 0, sizeof(box));
+  const bool tma = !group && wg_tma_box(g, p, box);
+  alignas(64) CUtensorMap tmA, tmD;
+  memset(&tmA, 0, sizeof(tmA));
+  memset(&tmD, 0, sizeof(tmD));
+  if (tma) {
+    uint64_t dims[4] = {(uint64_t)g.c0, (uint64_t)g.Wi, (uint64_t)g.Hi, (uint64_t)g.B};
+    uint64_t strides[3] = {(uint64_t)g.ld0 * 2, (uint64_t)g.Wi * g.ld0 * 2, (uint64_t)g.Hi * g.Wi * g.ld0 * 2};
+    uint32_t bx[4] = {64u, (uint32_t)box.bw, (uint32_t)box.bh, (uint32_t)box.bn};
+    int rc = get_tensor_map(&tmA, p->src0, 4, dims, strides, bx, 128);
+    if (rc) return rc;
+    uint64_t ddims[2] = {(uint64_t)p->Cout, (uint64_t)g.M};
+    uint64_t dstrides[1] = {(uint64_t)p->ldy * 2};
+    uint32_t dbx[2] = {64u, (uint32_t)WG_PIX};
+    rc = get_tensor_map(&tmD, p->dy, 2, ddims, dstrides, dbx, 128);
+    if (rc) return rc;
+  }
+  const double stage_us = tma ? 0.2 : 0.4;      // measured main-loop time per 64-pixel stage
   const int nblk = cdiv(g.M, WG_PIX);
   const int G = group ? group->count : 1;
   const int tiles = gx * gy * G;
@@ -270,13 +357,15 @@ static int launch_wgrad_tc_bn(const Gather& g, const d3fk_wgrad_params* p, cudaS
     if (smax > nblk) smax = nblk;
     smax = (smax / c) * c;
     if (smax < c) {
-      if (c == 1) { best = (double)nblk * 0.4 * cdiv(tiles, cap); cl = 1; splits = 1; }   // more tiles than one wave: no split
+      if (c == 1) { best = (double)nblk * stage_us * cdiv(tiles, cap); cl = 1; splits = 1; }   // more tiles than one wave: no split
       continue;
     }
     const int cand[2] = {smax, c};
     for (int i = 0; i < 2; ++i) {
       const int sp = cand[i];
-      const double est = (double)cdiv(nblk, sp) * 0.4 + (sp > c ? (sp / c) * elems / 216e3 : 0.0) + (c > 1 ? 1.0 : 0.0);
+      // cluster reduction: (c - 1) / c of each CTA's 128 x BN fp32 tile crosses the SM-to-SM network (~19 B / cycle / SM, two CTAs per SM)
+      const double dsmem_us = c > 1 ? 0.5 + (double)(c - 1) / c * (128.0 * BN * 4 * g_wg_ctas_per_sm) / (19.0 * 1965.0) : 0.0;
+      const double est = (double)cdiv(nblk, sp) * stage_us + (sp > c ? (sp / c) * elems / 216e3 : 0.0) + dsmem_us;
       if (est < best) { best = est; cl = c; splits = sp; }
     }
   }
@@ -290,17 +379,18 @@ static int launch_wgrad_tc_bn(const Gather& g, const d3fk_wgrad_params* p, cudaS
   }
   dim3 grid(gx, gy, splits * G);
   const size_t smem = (group && g_wg_group_occ == 1) ? (size_t)WG_ONE_PER_SM_SMEM : (size_t)WgradCfg<BN>::SMEM;
-  if (g_verbose) fprintf(stderr, "[d3fk] wgrad<%d> M=%d K=%d Cout=%d group=%d tiles=%d cl=%d splits=%d bps=%d\n", BN, g.M, g.K, p->Cout, G, tiles, cl, splits, bps);
-  if (cl == 1 && g_wg_plain) {
-    launch_k(wgrad_tc_kernel<BN>, dim3(grid), dim3(WG_THREADS), smem, s, dim3(1, 1, 1), g, make_fastdiv((uint32_t)g.Wo), make_fastdiv((uint32_t)g.Ho),
-                                                                  (const bf16*)p->dy, p->ldy, p->Cout, p->dw, p->cin_real, p->cout_real,
-                                                                  bps, WG_PIX * 128, WG_PIX * 128, cl, g_dev_error_flag, grp);
-  } else {
-    cudaError_t le = launch_k(wgrad_tc_kernel<BN>, grid, dim3(WG_THREADS), smem, s, dim3(1, 1, cl), g,
-                                    make_fastdiv((uint32_t)g.Wo), make_fastdiv((uint32_t)g.Ho), (const bf16*)p->dy, p->ldy, p->Cout,
-                                    p->dw, p->cin_real, p->cout_real, bps, WG_PIX * 128, WG_PIX * 128, cl, g_dev_error_flag, grp);
-    if (le != cudaSuccess) return set_error(D3FK_ERR_CUDA, "wgrad_tc launch: %s", cudaGetErrorString(le));
-  }
+  if (g_verbose) fprintf(stderr, "[d3fk] wgrad<%d> M=%d K=%d Cout=%d group=%d tiles=%d cl=%d splits=%d bps=%d tma=%d\n", BN, g.M, g.K, p->Cout, G, tiles, cl, splits, bps, (int)tma);
+  const dim3 cluster = (cl == 1 && g_wg_plain) ? dim3(1, 1, 1) : dim3(1, 1, cl);
+  cudaError_t le;
+  if (tma)
+    le = launch_k(wgrad_tc_kernel<BN, true>, grid, dim3(WG_THREADS), smem, s, cluster, g, make_fastdiv((uint32_t)g.Wo),
+                  make_fastdiv((uint32_t)g.Ho), (const bf16*)p->dy, p->ldy, p->Cout, p->dw, p->cin_real, p->cout_real, bps,
+                  WG_PIX * 128, WG_PIX * 128, cl, g_dev_error_flag, grp, tmA, tmD, box);
+  else
+    le = launch_k(wgrad_tc_kernel<BN, false>, grid, dim3(WG_THREADS), smem, s, cluster, g, make_fastdiv((uint32_t)g.Wo),
+                  make_fastdiv((uint32_t)g.Ho), (const bf16*)p->dy, p->ldy, p->Cout, p->dw, p->cin_real, p->cout_real, bps,
+                  WG_PIX * 128, WG_PIX * 128, cl, g_dev_error_flag, grp, tmA, tmD, box);
+  if (le != cudaSuccess) return set_error(D3FK_ERR_CUDA, "wgrad_tc launch: %s", cudaGetErrorString(le));
   count_launch();
   return check_launch("wgrad_tc");
 }
@@ -582,14 +672,17 @@ int wgrad_init() {
 #ifdef D3FK_DEBUG
   if (const char* v = getenv("D3FK_WG_SLAB")) g_use_wg_slab = atoi(v);
   if (const char* v = getenv("D3FK_WG_OCC")) g_wg_ctas_per_sm = atoi(v);
+  if (const char* v = getenv("D3FK_WG_TMA")) g_wg_tma = atoi(v);
   if (const char* v = getenv("D3FK_WG_CAP")) g_wg_cap = atoi(v);
   if (const char* v = getenv("D3FK_WG_PLAIN")) g_wg_plain = atoi(v);
   if (const char* v = getenv("D3FK_WG_GROUP_OCC")) g_wg_group_occ = atoi(v);
 #endif
   D3FK_SET_SMEM(wgrad_slab_kernel<16>, SLAB_MAX_SMEM)
   D3FK_SET_SMEM(wgrad_slab_kernel<32>, SLAB_MAX_SMEM)
-  D3FK_SET_SMEM(wgrad_tc_kernel<64>, WG_ONE_PER_SM_SMEM)
-  D3FK_SET_SMEM(wgrad_tc_kernel<128>, WG_ONE_PER_SM_SMEM)
+  D3FK_SET_SMEM((wgrad_tc_kernel<64, false>), WG_ONE_PER_SM_SMEM)
+  D3FK_SET_SMEM((wgrad_tc_kernel<128, false>), WG_ONE_PER_SM_SMEM)
+  D3FK_SET_SMEM((wgrad_tc_kernel<64, true>), WG_ONE_PER_SM_SMEM)
+  D3FK_SET_SMEM((wgrad_tc_kernel<128, true>), WG_ONE_PER_SM_SMEM)
   if (e != cudaSuccess) return set_error(D3FK_ERR_CUDA, "cudaFuncSetAttribute (wgrad): %s", cudaGetErrorString(e));
   return D3FK_OK;
 }

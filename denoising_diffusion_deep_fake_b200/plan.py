@@ -25,6 +25,9 @@ FUSE_BN_BWD_MAX_ELEMS = (1 << 62) if _f == 1 else _f
 # of one per convolution.  Measured: -0.33 ms of GPU work per step, but no change of the step time (the weight gradients are
 # hidden behind the latency-bound main chain either way, and the last group lengthens the tail) - opt-in.
 GROUP_WGRAD = os.environ.get("D3FK_WGRAD_GROUP", "0") == "1"
+# D3FK_WGRAD_GROUP_SIZE=n (with D3FK_WGRAD_GROUP=1): flush a group as soon as it holds n problems instead of at the end of the
+# stage (0: whole stage) - the grouped launch then starts earlier, behind the n-th BatchNorm backward.
+GROUP_WGRAD_SIZE = int(os.environ.get("D3FK_WGRAD_GROUP_SIZE", "0"))
 
 # The downsample branch of a stage's first block on a branch stream of d3fk_run (0: everything on the main chain).
 BRANCH_LANE = int(os.environ.get("D3FK_BRANCH_LANE", "1"))
@@ -435,6 +438,8 @@ class UnetPlan:
         (D3FK_OP_WGRAD_GROUP) — every dY of the stage is alive until then, the plan never recycles gradient buffers."""
         if GROUP_WGRAD and c.k == 3 and c.stride == 1 and c.cin == c.cout and len(pending) < _lib.WGRAD_GROUP_MAX:
             pending.append((c, src, dy))
+            if GROUP_WGRAD_SIZE and len(pending) >= GROUP_WGRAD_SIZE:
+                self._flush_wgrad_group(ops, pending)
         else:
             ops.append(self._wgrad_op(c, src, None, 0, dy))
 
