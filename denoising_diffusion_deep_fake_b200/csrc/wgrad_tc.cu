@@ -57,6 +57,7 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(Gather g, FastDiv 
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   const uint32_t accum_bar = bar_base + 8u * (2 * STAGES);
+  const uint32_t recv_bar = bar_base + 8u * (2 * STAGES + 2);   // cluster reduction: the partial tiles of my column slice have landed
 
   const int tid = threadIdx.x, warp = warp_index_uniform(), lane = tid & 31;
   const int k0 = blockIdx.x * 128, co0 = blockIdx.y * BN;
@@ -77,6 +78,7 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(Gather g, FastDiv 
       mbar_init(empty_bar(s), 1);
     }
     mbar_init(accum_bar, 1);
+    mbar_init(recv_bar, 1);
     fence_barrier_init();
   }
   if (TMA && warp == 0 && elect_one_sync()) {
@@ -243,13 +245,16 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(Gather g, FastDiv 
   }
 
   if (CL > 1) {
-    // reduce-scatter the CL partial tiles through distributed shared memory (see conv_tc_kernel)
+    // reduce-scatter the CL partial tiles through distributed shared memory, as conv_tc_kernel does: one relaxed cluster
+    // barrier ("every CTA is past its main loop": the stages are dead), then st.async stores that count their bytes on the
+    // OWNER's mbarrier — no release / acquire cluster barrier (MEMBAR.ALL.GPU), an owner starts as soon as ITS slice is in.
     const int SL = BN / CL, sl4 = SL >> 2;
     const uint32_t rank = cluster_ctarank();
     const uint32_t recv = a_base;   // [CL][SL/4][128 rows] float4 over the dead pipeline stages
     const int row = (warp & 3) * 32 + lane;
+    if (tid == 0) mbar_arrive_expect_tx(recv_bar, (uint32_t)(128 * BN * 4));
     tc_fence_before();
-    cluster_sync_all();
+    cluster_sync_relaxed();
     tc_fence_after();
     if (warp < 4) {
 #pragma unroll 1
@@ -267,19 +272,20 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(Gather g, FastDiv 
           const int col = cc + 4 * q;
           const int owner = col / SL, within = col - owner * SL;
           const uint32_t la = recv + (uint32_t)((((int)rank * sl4 + (within >> 2)) * 128 + row) * 16);
-          st_cluster_f4(mapa_shared(la, (uint32_t)owner), raw[4 * q], raw[4 * q + 1], raw[4 * q + 2], raw[4 * q + 3]);
+          st_async_f4(mapa_shared(la, (uint32_t)owner), raw[4 * q], raw[4 * q + 1], raw[4 * q + 2], raw[4 * q + 3],
+                      mapa_shared(recv_bar, (uint32_t)owner));
         }
       }
-    }
-    cluster_sync_all();
-    if (warp < 4 && row_ok) {
-      for (int c4 = 0; c4 < sl4; ++c4) {
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int r = 0; r < CL; ++r) {
-          const float4 v = ld_shared_f4(recv + (uint32_t)(((r * sl4 + c4) * 128 + row) * 16));
-          a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+      mbar_wait(recv_bar, 0, errflag);
+      if (row_ok) {
+        for (int c4 = 0; c4 < sl4; ++c4) {
+          float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int r = 0; r < CL; ++r) {
+            const float4 v = ld_shared_f4(recv + (uint32_t)(((r * sl4 + c4) * 128 + row) * 16));
+            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+          }
+          emit4(co0 + (int)rank * SL + 4 * c4, a.x, a.y, a.z, a.w);
         }
-        emit4(co0 + (int)rank * SL + 4 * c4, a.x, a.y, a.z, a.w);
       }
     }
   }
