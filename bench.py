@@ -413,18 +413,18 @@ def run_d3fk(args):
     except Exception:
         pass
     peak = peaks.get("bf16_tflops_sustained", 1400.0)
-    # DRAM bytes of the family per step from the committed ncu launch list (profiles/conv_traffic_r01.json, written by
+    # DRAM bytes of the family per step from the committed ncu launch list (profiles/conv_traffic_r02.json, written by
     # tools/summarise_launches.py --json from `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` over the same
     # command; cold-cache per launch).  Only quoted for the workload it was captured on.
     traffic = None
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "conv_traffic_r01.json")))
+        tj = json.load(open(os.path.join(ROOT, "profiles", "conv_traffic_r02.json")))
         if (B, H, W, args.precision) == (256, 64, 64, "bf16") and abs(tj["conv_family"]["launches_per_step"] - n_conv) < 0.5:
             traffic = tj["conv_family"]["dram_read_bytes_per_step"] + tj["conv_family"]["dram_write_bytes_per_step"]
     except Exception:
         pass
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": traffic, "traffic_unit": "bytes of DRAM traffic per step over the family's launches (ncu, profiles/conv_traffic_r01.json)",
+                "traffic": traffic, "traffic_unit": "bytes of DRAM traffic per step over the family's launches (ncu, profiles/conv_traffic_r02.json)",
                 "kernel": "conv_tc_kernel + conv_slab_kernel + wgrad_tc_kernel + wgrad_slab_kernel (tcgen05 implicit GEMM)",
                 "launches_per_step": n_conv, "ms_per_step": conv_ms,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback",

@@ -138,6 +138,7 @@ class Op(C.Structure):
  OP_BN_BWD_FINALIZE, OP_BN_BWD_APPLY, OP_MAXPOOL_FWD, OP_MAXPOOL_BWD, OP_SUMPOOL2, OP_CHANSUM, OP_QSAMPLE,
  OP_POSTERIOR, OP_MEMSET, OP_INC, OP_ADAM, OP_PACK_ALL, OP_LOSS, OP_CONV_BN, OP_UPCAT, OP_BN_BWD, OP_WGRAD_GROUP, OP_FRAMES_TO_TENSOR, OP_TENSOR_TO_FRAMES,
  OP_AFFINE_QSAMPLE, OP_SET_SCALARS, OP_JOIN) = range(1, 31)
+OP_NCHW2S2D, OP_PACK_STEM = 31, 32
 MAX_LANES = 2
 
 _UNION_FIELD = {OP_CONV: "conv", OP_WGRAD: "wgrad", OP_PACK: "pack", OP_NCHW2NHWC: "layout",
@@ -147,7 +148,8 @@ _UNION_FIELD = {OP_CONV: "conv", OP_WGRAD: "wgrad", OP_PACK: "pack", OP_NCHW2NHW
                 OP_MEMSET: "misc", OP_INC: "misc", OP_ADAM: "adam", OP_PACK_ALL: "misc",
                 OP_LOSS: "loss", OP_CONV_BN: "convbn", OP_UPCAT: "upcat", OP_BN_BWD: "bn",
                 OP_WGRAD_GROUP: "wgrad_group", OP_FRAMES_TO_TENSOR: "frames", OP_TENSOR_TO_FRAMES: "frames",
-                OP_AFFINE_QSAMPLE: "affine_qsample", OP_SET_SCALARS: "scalars", OP_JOIN: "misc"}
+                OP_AFFINE_QSAMPLE: "affine_qsample", OP_SET_SCALARS: "scalars", OP_JOIN: "misc",
+                OP_NCHW2S2D: "layout", OP_PACK_STEM: "pack"}
 _PARAM_CLS = {"conv": ConvParams, "wgrad": WgradParams, "pack": PackParams, "bn": BnParams, "pool": PoolParams,
               "layout": LayoutParams, "chansum": ChansumParams, "qsample": QsampleParams,
               "posterior": PosteriorParams, "misc": MiscParams, "adam": AdamParams, "loss": LossParams,

@@ -38,6 +38,8 @@ int launch_wgrad_group_tc(const d3fk_wgrad_group_params*, cudaStream_t);
 int launch_conv_bn_tc(const d3fk_convbn_params*, cudaStream_t);
 int launch_pack(const d3fk_pack_params*, cudaStream_t);
 int launch_nchw_to_nhwc(const d3fk_layout_params*, cudaStream_t);
+int launch_nchw_to_s2d(const d3fk_layout_params*, cudaStream_t);
+int launch_pack_stem(const d3fk_pack_params*, cudaStream_t);
 int launch_bn_finalize(const d3fk_bn_params*, cudaStream_t);
 int launch_bn_fold(const d3fk_bn_params*, cudaStream_t);
 int launch_bn_apply(const d3fk_bn_params*, cudaStream_t);
@@ -71,7 +73,10 @@ static int require_init() {
 }
 
 static int conv_dispatch(const d3fk_conv_params* p, cudaStream_t s) {
-  if (p->dtype == D3FK_F32) return launch_conv_ffma(p, s);
+  if (p->dtype == D3FK_F32) {
+    if (p->mode == 2) return set_error(D3FK_ERR_UNSUPPORTED, "conv mode 2 (windowed rows) is a bf16-engine path");
+    return launch_conv_ffma(p, s);
+  }
   if (p->dtype == D3FK_BF16) return launch_conv_tc(p, s);
   return set_error(D3FK_ERR_ARG, "conv: bad dtype %d", p->dtype);
 }
@@ -107,6 +112,8 @@ static int run_one(const d3fk_op* op, cudaStream_t s) {
     case D3FK_OP_WGRAD_GROUP: return wgrad_group_dispatch(&op->u.wgrad_group, s);
     case D3FK_OP_PACK: return launch_pack(&op->u.pack, s);
     case D3FK_OP_NCHW2NHWC: return launch_nchw_to_nhwc(&op->u.layout, s);
+    case D3FK_OP_NCHW2S2D: return launch_nchw_to_s2d(&op->u.layout, s);
+    case D3FK_OP_PACK_STEM: return launch_pack_stem(&op->u.pack, s);
     case D3FK_OP_BN_FINALIZE: return launch_bn_finalize(&op->u.bn, s);
     case D3FK_OP_BN_APPLY: return launch_bn_apply(&op->u.bn, s);
     case D3FK_OP_BN_FOLD: return launch_bn_fold(&op->u.bn, s);

@@ -31,6 +31,8 @@ template <int BN, int PATH, int FUSE> struct ConvCfg {
 struct TileSched {
   int MT, NT, KS, kb_per_split, nkb, total, a_ca;
   int bw, bh, bn, wt, ht;   // PATH 2: the 128-pixel M tile as a (w, h, n) box and the tile grid along w / h
+  int off_w, off_h;         // PATH 2: box origin offsets (-pad forward, +pad transposed; windowed rows: 0 / -pad)
+  int a_pitch;              // PATH 2: pixels per image row of the A tensor in memory (0: Wi; windowed rows: Wi + 3)
 };
 
 __device__ __forceinline__ void decode_tile(const TileSched& ts, int t, int& mt, int& nt, int& ks) {
@@ -245,7 +247,6 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(Gather g, FastDi
     if (elect_one_sync()) {
       uint32_t kbg = 0;
       const int sgn = g.mode ? -1 : 1;
-      const int off = g.mode ? g.pad : -g.pad;
       for (int t = blockIdx.x; t < ts.total; t += gridDim.x) {
         int mt, nt, ks;
         decode_tile(ts, t, mt, nt, ks);
@@ -255,8 +256,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(Gather g, FastDi
         if (PATH == 2) {
           const int tw = mt % ts.wt;
           const int r2 = mt / ts.wt;
-          w0 = tw * ts.bw + off;
-          h0 = (r2 % ts.ht) * ts.bh + off;
+          w0 = tw * ts.bw + ts.off_w;
+          h0 = (r2 % ts.ht) * ts.bh + ts.off_h;
           i0 = (r2 / ts.ht) * ts.bn;
           const int k = kb0 * TC_BK;
           tap = k / g.ctot;
@@ -652,7 +653,8 @@ static int launch_conv_tc_bn(const Gather& g, const d3fk_conv_params* p, cudaStr
   }
   if (PATH == 2) {
     uint64_t dims[4] = {(uint64_t)g.c0, (uint64_t)g.Wi, (uint64_t)g.Hi, (uint64_t)g.B};
-    uint64_t strides[3] = {(uint64_t)g.ld0 * 2, (uint64_t)g.Wi * g.ld0 * 2, (uint64_t)g.Hi * g.Wi * g.ld0 * 2};
+    const uint64_t pitch = (uint64_t)(ts.a_pitch ? ts.a_pitch : g.Wi);
+    uint64_t strides[3] = {(uint64_t)g.ld0 * 2, pitch * g.ld0 * 2, (uint64_t)g.Hi * pitch * g.ld0 * 2};
     uint32_t bx[4] = {TC_BK, (uint32_t)ts.bw, (uint32_t)ts.bh, (uint32_t)ts.bn};
     int rc = get_tensor_map(&tmA, p->src0, 4, dims, strides, bx, 128);
     if (rc) return rc;
@@ -720,7 +722,32 @@ static bool tma_box(const Gather& g, const d3fk_conv_params* p, TileSched& ts) {
   if (bh < H && bn != 1) return false;
   if (bn > 256) return false;
   ts.bw = bw; ts.bh = bh; ts.bn = bn; ts.wt = W / bw; ts.ht = H / bh;
+  ts.off_w = ts.off_h = p->mode ? p->pad : -p->pad;
+  ts.a_pitch = 0;
   return true;
+}
+
+// conv mode 2 ("windowed rows", include/d3fk.h): the space-to-depth stem.  Every (pixel, kh) is one contiguous 128-byte row of
+// the padded space-to-depth image, so the A operand is a 4-D TMA box over a tensor map whose pixel stride (32 B) is smaller
+// than its innermost extent (128 B) — overlapping windows; the kernel is the ordinary PATH 2 kernel.
+static int launch_conv_windowed(const d3fk_conv_params* p, cudaStream_t s) {
+  D3FK_CHECK_ARG(p->c0 == 64 && p->c1 == 0 && p->ld0 == 16 && p->kh == 4 && p->kw == 1 && p->stride == 1 && p->up0 == 0,
+                 "conv mode 2: c0 = 64, ld0 = 16, 4 x 1 taps, stride 1");
+  D3FK_CHECK_ARG(p->Ho == p->Hi && p->Wo == p->Wi && p->Cout == 64 && !p->out_nchw && !p->bw_x, "conv mode 2: Ho = Hi, Wo = Wi, Cout = 64");
+  d3fk_conv_params q = *p;
+  q.mode = 0;      // forward tap order; the window geometry lives in the tile schedule
+  Gather g;
+  int rc = make_gather(g, q.src0, nullptr, q.c0, 0, q.ld0, 0, 0, q.B, q.Hi, q.Wi, q.Ho, q.Wo, q.kh, q.kw, 1, q.pad, 0);
+  if (rc) return rc;
+  TileSched box;
+  memset(&box, 0, sizeof(box));
+  q.pad = 0; q.kh = q.kw = 1;          // tma_box() checks a "same" geometry: true for the window view (the taps are handled below)
+  if (!tma_box(g, &q, box)) return set_error(D3FK_ERR_UNSUPPORTED, "conv mode 2: the 128-pixel tile is not a (w, h, n) box for %d x %d", p->Ho, p->Wo);
+  q.pad = p->pad; q.kh = p->kh; q.kw = p->kw;
+  box.off_w = 0;
+  box.off_h = -p->pad;
+  box.a_pitch = p->Wi + 3;
+  return launch_conv_tc_bn<64, 2>(g, &q, s, box);
 }
 
 int try_launch_conv_slab(const Gather& g, const d3fk_conv_params* p, cudaStream_t s);   // conv_slab.cu
@@ -734,6 +761,7 @@ int launch_conv_tc(const d3fk_conv_params* p, cudaStream_t s) {
   D3FK_CHECK_ARG(p->out_nchw || (p->ldo % 8 == 0), "ldo must be a multiple of 8");
   D3FK_CHECK_ARG(!p->scale || p->shift, "scale requires shift");
   D3FK_CHECK_ARG(((uintptr_t)p->w & 15) == 0, "weights must be 16-byte aligned");
+  if (p->mode == 2) return launch_conv_windowed(p, s);
   const int head = try_launch_head_conv(p, s);          // 16 -> 3 channels, fp32 NCHW out: CUDA cores (head_conv.cu)
   if (head) return head < 0 ? head : D3FK_OK;
   const int slab = try_launch_conv_slab(g, p, s);

@@ -46,6 +46,43 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, T* __restrict
   }
 }
 
+// fp32 NCHW (3 channels) -> the padded space-to-depth image the stem convolution (conv mode 2) reads: one thread per
+// space-to-depth pixel (2x2 image pixels x 4 channels = 32 bytes).  Pad pixels and the 4th channel stay as allocated (zero).
+__global__ void __launch_bounds__(256) nchw_to_s2d_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int B, int H, int W) {
+  pdl_enter();
+  const int Hs = H >> 1, Ws = W >> 1;
+  const long long total = (long long)B * Hs * Ws;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ws = (int)(i % Ws);
+    const long long t = i / Ws;
+    const int hs = (int)(t % Hs), b = (int)(t / Hs);
+    float v[16];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float* p = src + (((long long)b * 3 + c) * H + 2 * hs) * W + 2 * ws;
+      const float2 r0 = *reinterpret_cast<const float2*>(p), r1 = *reinterpret_cast<const float2*>(p + W);
+      v[0 * 4 + c] = r0.x; v[1 * 4 + c] = r0.y; v[2 * 4 + c] = r1.x; v[3 * 4 + c] = r1.y;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) v[q * 4 + 3] = 0.f;
+    __nv_bfloat16* d = dst + (((long long)b * Hs + hs) * (Ws + 3) + ws + 2) * 16;
+    store_vec<__nv_bfloat16>(d, v);
+    store_vec<__nv_bfloat16>(d + 8, v + 8);
+  }
+}
+// 7x7 / stride-2 stem weights -> the [Cout][4 (th)][4 (tw)][2x2 (dy, dx)][4 (ci)] operand of conv mode 2
+__global__ void pack_stem_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cout) {
+  pdl_enter();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Cout * 256) return;
+  const int co = i >> 8, k = i & 255;
+  const int th = k >> 6, tw = (k >> 4) & 3, dy = (k >> 3) & 1, dx = (k >> 2) & 1, ci = k & 3;
+  const int kh = 2 * th + dy - 1, kw = 2 * tw + dx - 1;
+  float v = 0.f;
+  if (ci < 3 && kh >= 0 && kh < 7 && kw >= 0 && kw < 7) v = w[((co * 3 + ci) * 7 + kh) * 7 + kw];
+  out[i] = __float2bfloat16_rn(v);
+}
+
 // ---------------------------------------------------------------------------------------------
 // BN statistics -> scale/shift, saved mean/invstd, running-stat update (momentum, unbiased var)
 __global__ void bn_finalize_kernel(d3fk_bn_params p) {
@@ -947,6 +984,20 @@ int launch_nchw_to_nhwc(const d3fk_layout_params* p, cudaStream_t s) {
   DISPATCH_T(p->dtype, launch_k(nchw_to_nhwc_kernel<T>, dim3(grid_for(total, 256)), dim3(256), 0, s, dim3(1, 1, 1), p->src, (T*)p->dst, p->B, p->C, p->H * p->W, p->cpad));
   count_launch();
   return check_launch("nchw_to_nhwc");
+}
+int launch_nchw_to_s2d(const d3fk_layout_params* p, cudaStream_t s) {
+  D3FK_CHECK_ARG(p->dtype == D3FK_BF16 && p->C == 3 && p->cpad == 4 && p->H % 2 == 0 && p->W % 2 == 0, "s2d: bf16, C = 3, cpad = 4, even H and W");
+  D3FK_CHECK_ARG((((uintptr_t)p->src) & 7) == 0 && (((uintptr_t)p->dst) & 15) == 0, "s2d: alignment");
+  const long long total = (long long)p->B * (p->H / 2) * (p->W / 2);
+  launch_k(nchw_to_s2d_kernel, dim3(grid_for(total, 256)), dim3(256), 0, s, dim3(1, 1, 1), p->src, (__nv_bfloat16*)p->dst, p->B, p->H, p->W);
+  count_launch();
+  return check_launch("nchw_to_s2d");
+}
+int launch_pack_stem(const d3fk_pack_params* p, cudaStream_t s) {
+  D3FK_CHECK_ARG(p->dtype == D3FK_BF16 && p->Cin == 3 && p->kh == 7 && p->kw == 7 && p->w && p->w_fwd, "pack_stem: bf16 7x7 stem weights");
+  launch_k(pack_stem_kernel, dim3(cdiv(p->Cout * 256, 256)), dim3(256), 0, s, dim3(1, 1, 1), p->w, (__nv_bfloat16*)p->w_fwd, p->Cout);
+  count_launch();
+  return check_launch("pack_stem");
 }
 int launch_bn_finalize(const d3fk_bn_params* p, cudaStream_t s) {
   launch_k(bn_finalize_kernel, dim3(cdiv(p->C, 128)), dim3(128), 0, s, dim3(1, 1, 1), *p);

@@ -173,6 +173,22 @@ class UnetPlan:
             self.w_fwd[c.name] = self._new((c.cout, taps * cin_pad), self.tdtype)
             if self.training and c is not self.stem:
                 self.w_dgrad[c.name] = self._new((c.cin, taps * cout_pad), self.tdtype)
+        # bf16 engine: the 7x7 / stride-2 stem runs as a space-to-depth convolution (conv mode 2, include/d3fk.h) whenever
+        # its 128-pixel output tile is a (w, h, n) box — K = 256 by TMA instead of K = 392 by per-thread gather (65 -> 25 us)
+        self.stem_s2d = self.dtype == _lib.BF16 and self._stem_box_ok(self.H // 2, self.W // 2)
+        self.w_stem_s2d = self._new((self.stem.cout, 256), self.tdtype) if self.stem_s2d else None
+
+    @staticmethod
+    def _stem_box_ok(Ho, Wo):
+        """tma_box() of csrc/conv_tc.cu for the stem's output: 128 consecutive pixels form an axis-aligned (w, h, n) box."""
+        bw = min(Wo, 128)
+        if 128 % bw or Wo % bw:
+            return False
+        bh = min(128 // bw, Ho)
+        if (128 // bw) % bh or Ho % bh:
+            return False
+        bn = 128 // (bw * bh)
+        return not (bw < Wo and bh != 1) and not (bh < Ho and bn != 1) and bn <= 256
 
     def _alloc_bn(self):
         bns = [c for c in self.convs if c.bn]
@@ -266,7 +282,14 @@ class UnetPlan:
             op = make_op(_lib.OP_PACK_ALL, p0=self.pack_table.data_ptr() + first * ctypes.sizeof(_lib.PackParams),
                          n=(blocks << 17) | (count << 1) | (1 if self.dtype == _lib.BF16 else 0))
             ops.append(op)
-            self.pack_bucket_ops.append(_lib.OpList([op]))
+            bucket_ops = [op]
+            if self.stem_s2d and len(self.pack_bucket_ops) == bucket_of(self.stem):
+                stem_op = make_op(_lib.OP_PACK_STEM, dtype=self.dtype, Cout=self.stem.cout, Cin=3, kh=7, kw=7, cin_pad=4,
+                                  cout_pad=self.stem.cout, w=self.params[self.stem.name + ".weight"].data_ptr(),
+                                  w_fwd=self.w_stem_s2d.data_ptr())
+                ops.append(stem_op)
+                bucket_ops.append(stem_op)
+            self.pack_bucket_ops.append(_lib.OpList(bucket_ops))
         if not self.training:
             for c in self.convs:
                 if c.bn:
@@ -277,7 +300,7 @@ class UnetPlan:
 
     # ------------------------------------------------------------------ forward
     def _conv_fields(self, c, src0, src1=None, up0=0, out=None, relu=0, res=None, stats=False, out_nchw=None,
-                     affine=False):
+                     affine=False, override=None):
         Hi = src0.H * (2 if up0 else 1)
         Wi = src0.W * (2 if up0 else 1)
         Ho = (Hi + 2 * c.pad - c.k) // c.stride + 1
@@ -299,14 +322,16 @@ class UnetPlan:
             f.update(stats=self.stats[0].data_ptr() + 8 * 2 * self.bn_off[c.bn])
         if affine:
             f.update(scale=self._bnptr(c.bn, 0, c.cout), shift=self._bnptr(c.bn, 1, c.cout))
+        if override:
+            f.update(override)
         return f
 
     def _conv_op(self, c, src0, src1=None, up0=0, out=None, relu=0, res=None, stats=False, out_nchw=None,
-                 affine=False, lane=0):
-        f = self._conv_fields(c, src0, src1, up0, out, relu, res, stats, out_nchw, affine)
+                 affine=False, lane=0, override=None):
+        f = self._conv_fields(c, src0, src1, up0, out, relu, res, stats, out_nchw, affine, override)
         return make_op(_lib.OP_CONV, lane=lane, **f), f["Ho"], f["Wo"]
 
-    def _conv_bn_act(self, ops, c, src0, src1=None, up0=0, relu=1, res=None, lane=0):
+    def _conv_bn_act(self, ops, c, src0, src1=None, up0=0, relu=1, res=None, lane=0, override=None):
         """conv -> BN -> (+res) -> ReLU.  Train: raw conv output + batch statistics in the conv epilogue,
         finalize, one fused apply pass.  Eval: BN folded into the conv epilogue.  Returns the activation.
         lane != 0: the op runs on a branch stream of d3fk_run (always in its two-kernel form: a branch never waits on a
@@ -318,12 +343,12 @@ class UnetPlan:
         act = T(self, self.B, Ho, Wo, c.cout)
         self.keep.append(act.t)
         if not self.training:
-            op, _, _ = self._conv_op(c, src0, src1, up0, out=act, relu=relu, res=res, affine=True, lane=lane)
+            op, _, _ = self._conv_op(c, src0, src1, up0, out=act, relu=relu, res=res, affine=True, lane=lane, override=override)
             ops.append(op)
             return act
         raw = T(self, self.B, Ho, Wo, c.cout)
         self.keep.append(raw.t)
-        conv_fields = self._conv_fields(c, src0, src1, up0, out=raw, stats=True)
+        conv_fields = self._conv_fields(c, src0, src1, up0, out=raw, stats=True, override=override)
         bn = self._bn_common(c)
         bn.update(count=raw.count, relu=relu, x=raw.ptr, ldx=raw.ld, y=act.ptr, ldy=act.ld)
         if res is not None:
@@ -342,10 +367,21 @@ class UnetPlan:
             ops.append(make_op(_lib.OP_MEMSET, p0=self.stats[0].data_ptr(), n=self.stats[0].numel() * 8))
         self.x8 = T(self, B, H, W, CIN_PAD)
         self.keep.append(self.x8.t)
-        self.in_op_index = len(ops)
-        ops.append(make_op(_lib.OP_NCHW2NHWC, dtype=self.dtype, B=B, C=3, H=H, W=W, cpad=CIN_PAD, src=None,
-                           dst=self.x8.ptr))
-        f1 = self._conv_bn_act(ops, self.stem, self.x8)
+        self.in_op_indices = []           # every op that reads the caller's NCHW input (run_forward patches their .src)
+        stem_override = None
+        if self.stem_s2d:
+            # padded space-to-depth image [B][H/2][W/2 + 3][16] (zero-initialised: the pad pixels / 4th channel are never written)
+            self.xs2d = self._new((B, H // 2, W // 2 + 3, 16), self.tdtype)
+            self.in_op_indices.append(len(ops))
+            ops.append(make_op(_lib.OP_NCHW2S2D, dtype=self.dtype, B=B, C=3, H=H, W=W, cpad=4, src=None, dst=self.xs2d.data_ptr()))
+            stem_override = dict(mode=2, src0=self.xs2d.data_ptr(), c0=64, c1=0, ld0=16, up0=0, Hi=H // 2, Wi=W // 2, kh=4, kw=1,
+                                 stride=1, pad=2, w=self.w_stem_s2d.data_ptr())
+        if self.training or not self.stem_s2d:      # the 8-channel NHWC image: the gather-form stem and the stem's weight gradient
+            self.in_op_indices.append(len(ops))
+            ops.append(make_op(_lib.OP_NCHW2NHWC, dtype=self.dtype, B=B, C=3, H=H, W=W, cpad=CIN_PAD, src=None,
+                               dst=self.x8.ptr))
+        self.in_op_index = self.in_op_indices[0]
+        f1 = self._conv_bn_act(ops, self.stem, self.x8, override=stem_override)
         p1 = T(self, B, f1.H // 2, f1.W // 2, 64)
         self.keep.append(p1.t)
         self.pool_idx = self._new((B, p1.H, p1.W, 64), torch.uint8) if self.training else None
@@ -634,7 +670,8 @@ class UnetPlan:
             self.pack_bucket_ops[i].run(stream)
 
     def run_forward(self, x, y, stream):
-        op_params(self.fwd_ops.array[self.in_op_index]).src = x.data_ptr()
+        for i in self.in_op_indices:
+            op_params(self.fwd_ops.array[i]).src = x.data_ptr()
         op_params(self.fwd_ops.array[self.out_op_index]).out_nchw = y.data_ptr()
         self.fwd_ops.run(stream)
 

@@ -41,6 +41,14 @@ typedef void* d3fk_stream; /* cudaStream_t */
  * mode 1 (transposed gather = dgrad of a conv with the same kh/kw/stride/pad):
  *         out[n,h,w,ci] = sum_{kh,kw,co} A[n,(h+pad-kh)/stride,(w+pad-kw)/stride,co] * w[ci][kh][kw][co]
  *         (terms whose coordinate is not divisible by stride or out of range are zero).
+ * mode 2 (bf16 engine only; the 7x7 / stride-2 stem as a space-to-depth convolution): "windowed rows".  src0 is the
+ *         space-to-depth image written by D3FK_OP_NCHW2S2D — [B][Hi][Wi + 3][ld0 = 16] with 2 zero pixels on the left and 1 on
+ *         the right of every row — and the c0 = 64 "channels" of position (n, h, w) are the 64 CONTIGUOUS elements that start
+ *         at padded pixel w, i.e. the 4-pixel window w-2 .. w+1 of the unpadded row: windows overlap, the pixel stride ld0 is
+ *         smaller than c0.  out[n,ho,wo,co] = sum_{kh < 4, c < 64} src0[n, ho - pad + kh, window wo][c] * w[co][kh][c]
+ *         (kw = 1, stride 1, pad = 2 in h only, Ho = Hi, Wo = Wi; weights from D3FK_OP_PACK_STEM).  Each (pixel, kh) is one
+ *         128-byte operand row, so the whole A tile is a TMA box: K = 256 (4 k-blocks, none of them padding) instead of the
+ *         392 of the 7x7 gather, and no per-thread gather.
  * A is the channel concatenation of src0 (c0 channels, optionally read through a nearest 2x upsample:
  * F.interpolate(scale_factor=2) + torch.cat of smp's DecoderBlock) and src1 (c1 channels).
  * Epilogue: v = acc; v = v*scale[c]+shift[c] (if scale); v += res (if res); v = max(v,0) (if relu);
@@ -272,7 +280,11 @@ enum d3fk_op_kind {
   D3FK_OP_SET_SCALARS = 29,   /* scalars params */
   D3FK_OP_JOIN = 30,          /* misc params: n = lane to join back into the main stream */
   D3FK_OP_WGRAD_GROUP = 25,   /* wgrad_group params; forked onto the side streams like D3FK_OP_WGRAD */
-  D3FK_OP_BN_BWD = 24    /* bn params: bn_bwd_reduce + bn_bwd_apply as one op (one kernel behind a grid barrier when `barrier` is set) */
+  D3FK_OP_BN_BWD = 24,   /* bn params: bn_bwd_reduce + bn_bwd_apply as one op (one kernel behind a grid barrier when `barrier` is set) */
+  D3FK_OP_NCHW2S2D = 31,   /* layout params (C = 3, cpad = 4, H and W even): fp32 NCHW -> the padded space-to-depth image of conv mode 2:
+                              dst[b][h/2][w/2 + 2][((h%2)*2 + (w%2))*4 + c]; the pad pixels / channel are left untouched (zero them once) */
+  D3FK_OP_PACK_STEM = 32   /* pack params (Cout, Cin = 3, kh = kw = 7): w_fwd[co][th*64 + tw*16 + (dy*2+dx)*4 + ci] =
+                              w[co][ci][2*th+dy-1][2*tw+dx-1] (0 outside the 7x7 window and for ci = 3): the conv mode 2 weights */
 };
 
 /* `lane`: 0 = the caller's stream (the main chain).  lane 1..D3FK_MAX_LANES = an internal branch stream: the op runs there,

@@ -493,3 +493,37 @@ def test_cp_async_path_is_race_free():
                 bad += ((out - first).norm() > 1e-5 * first.norm())
         assert bad.item() == 0, (kind, c, bad.item())
     assert _lib.load().d3fk_device_error_flag() == 0
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 64, 64), (3, 32, 32), (1, 128, 128), (1, 256, 256), (5, 64, 32)])
+def test_stem_space_to_depth(B, H, W):
+    """The 7x7 / stride-2 stem as a space-to-depth convolution (D3FK_OP_NCHW2S2D + D3FK_OP_PACK_STEM + conv mode 2: every
+    (pixel, kh) one 128-byte window of the padded space-to-depth image, A operand by TMA over a tensor map with overlapping
+    rows) against torch's conv2d on the same bf16-rounded operands, with the batch statistics of its epilogue."""
+    import math
+    import torch.nn.functional as F
+    dev = "cuda:0"
+    _lib.init(0)
+    stream = torch.cuda.current_stream().cuda_stream
+    g = torch.Generator().manual_seed(B * 7 + H)
+    x = torch.randn(B, 3, H, W, generator=g).to(dev)
+    w = (torch.randn(64, 3, 7, 7, generator=g) / math.sqrt(147)).to(dev)
+    Hs, Ws = H // 2, W // 2
+    xs = torch.zeros(B, Hs, Ws + 3, 16, device=dev, dtype=torch.bfloat16)
+    wp = torch.zeros(64, 256, device=dev, dtype=torch.bfloat16)
+    out = torch.zeros(B, Hs, Ws, 64, device=dev, dtype=torch.bfloat16)
+    st = torch.zeros(2, 64, dtype=torch.float64, device=dev)
+    ops = [_lib.make_op(_lib.OP_NCHW2S2D, dtype=_lib.BF16, B=B, C=3, H=H, W=W, cpad=4, src=x.data_ptr(), dst=xs.data_ptr()),
+           _lib.make_op(_lib.OP_PACK_STEM, dtype=_lib.BF16, Cout=64, Cin=3, kh=7, kw=7, cin_pad=4, cout_pad=64, w=w.data_ptr(),
+                        w_fwd=wp.data_ptr()),
+           _lib.make_op(_lib.OP_CONV, dtype=_lib.BF16, mode=2, src0=xs.data_ptr(), c0=64, c1=0, ld0=16, ld1=0, up0=0, B=B, Hi=Hs,
+                        Wi=Ws, Ho=Hs, Wo=Ws, kh=4, kw=1, stride=1, pad=2, w=wp.data_ptr(), Cout=64, out=out.data_ptr(), ldo=64,
+                        stats=st.data_ptr())]
+    _lib.OpList(ops).run(stream)
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.bfloat16().double(), w.bfloat16().double(), stride=2, padding=3).permute(0, 2, 3, 1)
+    assert rel_err(out.float().cpu(), ref.float().cpu()) < 4e-3          # bf16 rounding of the stored output
+    assert rel_err(st[0].cpu(), ref.sum((0, 1, 2)).cpu()) < 1e-5
+    assert rel_err(st[1].cpu(), (ref * ref).sum((0, 1, 2)).cpu()) < 1e-5
+    assert xs[:, :, :2].abs().max() == 0 and xs[:, :, -1].abs().max() == 0      # the pad pixels stay zero
+    assert _lib.load().d3fk_device_error_flag() == 0

@@ -100,7 +100,9 @@ def test_backward_in_situ(precision, tol, B):
     mc._ensure_grad_arena(torch.device("cpu"))
     twin = UnetPlan(dict(mc.named_parameters()), dict(mc.named_buffers()), B, H, W, _lib.F32, "cpu", True,
                     grad_arena=mc._grad_arena, grad_offsets=mc._grad_offsets)
-    gpu_keep = [t for t in plan.keep if t is not plan.ws]      # the bf16 plan also owns a split-K scratch buffer
+    # the bf16 plan also owns a split-K scratch buffer and the space-to-depth stem's operands (input image, packed weights)
+    only_gpu = [plan.ws, getattr(plan, "w_stem_s2d", None), getattr(plan, "xs2d", None)]
+    gpu_keep = [t for t in plan.keep if not any(t is o for o in only_gpu)]
     assert len(twin.keep) == len(gpu_keep)
     for tc, tg in zip(twin.keep, gpu_keep):
         if tc.shape == tg.shape:
