@@ -852,19 +852,46 @@ __global__ void __launch_bounds__(256) pack_all_kernel(const d3fk_pack_params* _
     for (int c = lane; c < ncol; c += 32) tile[r][c] = __ldg(src + c);
   }
   __syncthreads();
-  // one (row, tap) pair per warp iteration, lanes along the contiguous output channel: no per-element index division
+  // bf16, full 8-channel groups (every layer but the 3-channel stem / head edges): one 16-byte store per (row, tap, 8 channels)
+  // — the 2-byte-per-lane form below issued four times as many store instructions and ran at 1.1 TB/s.
+  const bool vec8 = sizeof(T) == 2 && (nci & 7) == 0 && (nco & 7) == 0;
   if (p.w_fwd) {
     T* dst = (T*)p.w_fwd;
-    for (int q = warp; q < nco * taps; q += nwarp) {
-      const int r = q / taps, t = q - r * taps;
-      if (lane < nci) dst[((long long)(co0 + r) * taps + t) * p.cin_pad + ci0 + lane] = from_f<T>(tile[r][lane * taps + t]);
+    if (vec8) {
+      const int nv = nci >> 3;
+      for (int it = threadIdx.x; it < nco * taps * nv; it += blockDim.x) {
+        const int v = it % nv, q = it / nv;
+        const int r = q / taps, t = q - r * taps;
+        float x[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = tile[r][(v * 8 + i) * taps + t];
+        store_vec<T>(dst + ((long long)(co0 + r) * taps + t) * p.cin_pad + ci0 + v * 8, x);
+      }
+    } else {
+      // one (row, tap) pair per warp iteration, lanes along the contiguous output channel: no per-element index division
+      for (int q = warp; q < nco * taps; q += nwarp) {
+        const int r = q / taps, t = q - r * taps;
+        if (lane < nci) dst[((long long)(co0 + r) * taps + t) * p.cin_pad + ci0 + lane] = from_f<T>(tile[r][lane * taps + t]);
+      }
     }
   }
   if (p.w_dgrad) {
     T* dst = (T*)p.w_dgrad;
-    for (int q = warp; q < nci * taps; q += nwarp) {
-      const int c = q / taps, t = q - c * taps;
-      if (lane < nco) dst[((long long)(ci0 + c) * taps + t) * p.cout_pad + co0 + lane] = from_f<T>(tile[lane][c * taps + t]);
+    if (vec8) {
+      const int nv = nco >> 3;
+      for (int it = threadIdx.x; it < nci * taps * nv; it += blockDim.x) {
+        const int v = it % nv, q = it / nv;
+        const int c = q / taps, t = q - c * taps;
+        float x[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = tile[v * 8 + i][c * taps + t];
+        store_vec<T>(dst + ((long long)(ci0 + c) * taps + t) * p.cout_pad + co0 + v * 8, x);
+      }
+    } else {
+      for (int q = warp; q < nci * taps; q += nwarp) {
+        const int c = q / taps, t = q - c * taps;
+        if (lane < nco) dst[((long long)(ci0 + c) * taps + t) * p.cout_pad + co0 + lane] = from_f<T>(tile[lane][c * taps + t]);
+      }
     }
   }
 }
