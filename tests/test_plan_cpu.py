@@ -105,7 +105,9 @@ def test_eval_plan_matches_oracle():
     plan = cpu_plan(m, 2, 64, 32, False)
     assert sum(1 for op in plan.fwd_ops if op.kind in (_lib.OP_CONV, _lib.OP_CONV_BN)) == 47
     n_join = sum(1 for op in plan.fwd_ops if op.kind == _lib.OP_JOIN)   # branch-lane joins of the 3 downsample blocks
-    assert len(plan.fwd_ops) - n_join == 51                         # 47 convs (BN folded) + layout + maxpool + 2 upsample-concat
+    n_upcat = sum(1 for op in plan.fwd_ops if op.kind == _lib.OP_UPCAT)   # blocks 3-4 (slab path) + blocks 0-2 (TMA-fed generic path)
+    assert n_upcat in (2, 5)
+    assert len(plan.fwd_ops) - n_join - n_upcat == 49               # 47 convs (BN folded) + layout + maxpool
     assert n_join in (0, 3)
     y = run_forward(plan, x)
     with torch.no_grad():
