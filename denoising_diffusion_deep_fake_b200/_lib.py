@@ -24,7 +24,7 @@ class ConvParams(C.Structure):
 
 
 class WgradParams(C.Structure):
-    _fields_ = [("dtype", i32), ("_pad0", i32), ("src0", vp), ("src1", vp),
+    _fields_ = [("dtype", i32), ("mode", i32), ("src0", vp), ("src1", vp),
                 ("c0", i32), ("c1", i32), ("ld0", i32), ("ld1", i32), ("up0", i32),
                 ("B", i32), ("Hi", i32), ("Wi", i32), ("Ho", i32), ("Wo", i32),
                 ("kh", i32), ("kw", i32), ("stride", i32), ("pad", i32),

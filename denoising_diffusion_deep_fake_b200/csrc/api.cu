@@ -81,7 +81,10 @@ static int conv_dispatch(const d3fk_conv_params* p, cudaStream_t s) {
   return set_error(D3FK_ERR_ARG, "conv: bad dtype %d", p->dtype);
 }
 static int wgrad_dispatch(const d3fk_wgrad_params* p, cudaStream_t s) {
-  if (p->dtype == D3FK_F32) return launch_wgrad_ffma(p, s);
+  if (p->dtype == D3FK_F32) {
+    if (p->mode == 2) return set_error(D3FK_ERR_UNSUPPORTED, "wgrad mode 2 (space-to-depth stem) is a bf16-engine path");
+    return launch_wgrad_ffma(p, s);
+  }
   if (p->dtype == D3FK_BF16) return launch_wgrad_tc(p, s);
   return set_error(D3FK_ERR_ARG, "wgrad: bad dtype %d", p->dtype);
 }

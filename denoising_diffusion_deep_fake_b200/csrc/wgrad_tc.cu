@@ -36,7 +36,7 @@ struct WgGroup {
 // A stage (64 channels of one tap for 64 pixels) is ONE cp.async.bulk.tensor.4d — shifted by the tap, hardware zero fill for
 // the halo — and the dY tile is a 2-D box per 64 output channels.  One elected thread of warp 0 is the producer; nobody
 // computes an address (the gather variant issues 16 cp.async and ~150 instructions per thread and stage).
-struct WgBox { int bw, bh, bn, wt, ht; };
+struct WgBox { int bw, bh, bn, wt, ht; int win; };   // win: windowed rows of the space-to-depth stem (d3fk_wgrad_params.mode 2)
 template <int BN, bool TMA>
 __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(Gather g, FastDiv dWo, FastDiv dHo, const bf16* __restrict__ dy_one,
                                                               int ldy, int Cout, float* __restrict__ dw_one, int cin_real,
@@ -96,8 +96,16 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(Gather g, FastDiv 
   const int krow = k0 + (warp & 3) * 32 + lane;
   int tap_o = 0, ci_o = 0;
   if (krow < g.K) { tap_o = krow / g.ctot; ci_o = krow - tap_o * g.ctot; }
-  const bool row_ok = krow < g.K && ci_o < cin_real;
-  const int taps = g.kh * g.kw;
+  bool row_ok = krow < g.K && ci_o < cin_real;
+  int taps = g.kh * g.kw;
+  if (TMA && box.win) {
+    // windowed rows: k = th*64 + tw*16 + (dy*2+dx)*4 + ci  ->  tap (2th+dy-1, 2tw+dx-1) of the 7x7 master gradient, channel ci
+    const int kh7 = 2 * (krow >> 6) + ((krow >> 3) & 1) - 1, kw7 = 2 * ((krow >> 4) & 3) + ((krow >> 2) & 1) - 1;
+    ci_o = krow & 3;
+    tap_o = kh7 * 7 + kw7;
+    taps = 49;
+    row_ok = krow < g.K && ci_o < cin_real && kh7 >= 0 && kh7 < 7 && kw7 >= 0 && kw7 < 7;
+  }
   auto emit4 = [&](int co, float a, float b, float c, float d) {   // columns co..co+3 of this thread's row
     float v[4] = {a, b, c, d};
 #pragma unroll
@@ -124,7 +132,7 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(Gather g, FastDiv 
           kc[cb] = kok[cb] ? k - tap * g.ctot : 0;
           const int khi = tap / g.kw;
           dh[cb] = khi - g.pad;
-          dwv[cb] = tap - khi * g.kw - g.pad;
+          dwv[cb] = box.win ? 0 : tap - khi * g.kw - g.pad;      // windowed rows: the kw taps are inside the 128-byte window
         }
         const uint32_t tx = (uint32_t)(((kok[0] ? 1 : 0) + (kok[1] ? 1 : 0) + Cfg::NCB) * (WG_PIX * 128));
         for (int it = 0; it < nblk; ++it) {
@@ -331,13 +339,26 @@ static int launch_wgrad_tc_bn(const Gather& g, const d3fk_wgrad_params* p, cudaS
   const int gx = cdiv(g.K, 128), gy = cdiv(p->Cout, BN);
   WgBox box;
   memset(&box, 0, sizeof(box));
-  const bool tma = !group && wg_tma_box(g, p, box);
+  const bool win = p->mode == 2;
+  bool tma;
+  if (win) {
+    D3FK_CHECK_ARG(!group && p->c0 == 64 && p->c1 == 0 && p->ld0 == 16 && p->kh == 4 && p->kw == 1 && p->stride == 1 && p->up0 == 0 &&
+                   p->Ho == p->Hi && p->Wo == p->Wi && p->cin_real == 3, "wgrad mode 2: the space-to-depth stem geometry");
+    d3fk_wgrad_params q = *p;
+    q.pad = 0; q.kh = q.kw = 1;          // the window view is a "same" 1x1 geometry for the box test
+    tma = wg_tma_box(g, &q, box);
+    if (!tma) return set_error(D3FK_ERR_UNSUPPORTED, "wgrad mode 2: the 64-pixel block is not a (w, h, n) box for %d x %d", p->Ho, p->Wo);
+    box.win = 1;
+  } else {
+    tma = !group && wg_tma_box(g, p, box);
+  }
   alignas(64) CUtensorMap tmA, tmD;
   memset(&tmA, 0, sizeof(tmA));
   memset(&tmD, 0, sizeof(tmD));
   if (tma) {
+    const uint64_t pitch = (uint64_t)(win ? g.Wi + 3 : g.Wi);      // pixels per image row in memory
     uint64_t dims[4] = {(uint64_t)g.c0, (uint64_t)g.Wi, (uint64_t)g.Hi, (uint64_t)g.B};
-    uint64_t strides[3] = {(uint64_t)g.ld0 * 2, (uint64_t)g.Wi * g.ld0 * 2, (uint64_t)g.Hi * g.Wi * g.ld0 * 2};
+    uint64_t strides[3] = {(uint64_t)g.ld0 * 2, pitch * g.ld0 * 2, (uint64_t)g.Hi * pitch * g.ld0 * 2};
     uint32_t bx[4] = {64u, (uint32_t)box.bw, (uint32_t)box.bh, (uint32_t)box.bn};
     int rc = get_tensor_map(&tmA, p->src0, 4, dims, strides, bx, 128);
     if (rc) return rc;
@@ -649,8 +670,10 @@ int launch_wgrad_tc(const d3fk_wgrad_params* p, cudaStream_t s) {
                        p->kw, p->stride, p->pad, 0);
   if (rc) return rc;
   D3FK_CHECK_ARG(p->Cout % 8 == 0 && p->ldy % 8 == 0, "Cout and ldy must be multiples of 8");
-  const int slab = try_launch_wgrad_slab(g, p, s);
-  if (slab) return slab < 0 ? slab : D3FK_OK;
+  if (p->mode != 2) {
+    const int slab = try_launch_wgrad_slab(g, p, s);
+    if (slab) return slab < 0 ? slab : D3FK_OK;
+  }
   if (p->Cout > 64) return launch_wgrad_tc_bn<128>(g, p, s);
   return launch_wgrad_tc_bn<64>(g, p, s);
 }

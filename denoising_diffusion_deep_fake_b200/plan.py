@@ -382,7 +382,7 @@ class UnetPlan:
             ops.append(make_op(_lib.OP_NCHW2S2D, dtype=self.dtype, B=B, C=3, H=H, W=W, cpad=4, src=None, dst=self.xs2d.data_ptr()))
             stem_override = dict(mode=2, src0=self.xs2d.data_ptr(), c0=64, c1=0, ld0=16, up0=0, Hi=H // 2, Wi=W // 2, kh=4, kw=1,
                                  stride=1, pad=2, w=self.w_stem_s2d.data_ptr())
-        if self.training or not self.stem_s2d:      # the 8-channel NHWC image: the gather-form stem and the stem's weight gradient
+        if not self.stem_s2d:                       # the 8-channel NHWC image of the gather-form stem (and its weight gradient)
             self.in_op_indices.append(len(ops))
             ops.append(make_op(_lib.OP_NCHW2NHWC, dtype=self.dtype, B=B, C=3, H=H, W=W, cpad=CIN_PAD, src=None,
                                dst=self.x8.ptr))
@@ -664,7 +664,14 @@ class UnetPlan:
                            dy=grad[id(self.p1)].ptr, lddy=grad[id(self.p1)].ld, idx=self.pool_idx.data_ptr(),
                            dx=g_f1.ptr, lddx=g_f1.ld, accumulate=1))
         d_r, _ = self._bn_bwd(ops, self.stem, g_f1)
-        ops.append(self._wgrad_op(self.stem, self.x8, None, 0, d_r))
+        if self.stem_s2d:
+            # the stem's weight gradient from the same windowed rows as its forward (d3fk_wgrad_params.mode 2): TMA-fed, K = 256
+            ops.append(make_op(_lib.OP_WGRAD, dtype=self.dtype, mode=2, src0=self.xs2d.data_ptr(), c0=64, c1=0, ld0=16, up0=0,
+                               B=self.B, Hi=self.H // 2, Wi=self.W // 2, Ho=d_r.H, Wo=d_r.W, kh=4, kw=1, stride=1, pad=2,
+                               dy=d_r.ptr, ldy=d_r.ld, Cout=d_r.C, cin_real=3, cout_real=self.stem.cout,
+                               dw=self._gptr(self.stem.name + ".weight")))
+        else:
+            ops.append(self._wgrad_op(self.stem, self.x8, None, 0, d_r))
         segs.append(ops)
         return segs
 

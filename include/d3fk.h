@@ -81,7 +81,10 @@ typedef struct d3fk_conv_params {
  * (= stride) of dw's input-channel dimension: a launch over a channel sub-range of the input (c0 + c1 < cin_real, src0 and
  * dw offset to the first channel of the range) accumulates that slice of dw. */
 typedef struct d3fk_wgrad_params {
-  int32_t dtype, _pad0;
+  int32_t dtype;
+  int32_t mode;   /* 0: the gather above.  2 (bf16 engine): the space-to-depth stem, operands as conv mode 2 (src0 = the padded
+                     space-to-depth image, c0 = 64 window channels, ld0 = 16, kh = 4, kw = 1, pad = 2); dw is still the 7x7 OIHW
+                     master gradient (cin_real = 3): row k = th*64 + tw*16 + (dy*2+dx)*4 + ci lands on tap (2th+dy-1, 2tw+dx-1) */
   const void* src0; const void* src1;
   int32_t c0, c1, ld0, ld1, up0;
   int32_t B, Hi, Wi, Ho, Wo;

@@ -526,4 +526,14 @@ def test_stem_space_to_depth(B, H, W):
     assert rel_err(st[0].cpu(), ref.sum((0, 1, 2)).cpu()) < 1e-5
     assert rel_err(st[1].cpu(), (ref * ref).sum((0, 1, 2)).cpu()) < 1e-5
     assert xs[:, :, :2].abs().max() == 0 and xs[:, :, -1].abs().max() == 0      # the pad pixels stay zero
+    # weight gradient from the same windowed rows (d3fk_wgrad_params.mode 2) into the 7x7 OIHW master gradient
+    dy = torch.randn(B, Hs, Ws, 64, generator=g).to(dev).bfloat16()
+    dw = torch.zeros(64, 3, 7, 7, device=dev)
+    _lib.run_single(_lib.make_op(_lib.OP_WGRAD, dtype=_lib.BF16, mode=2, src0=xs.data_ptr(), c0=64, c1=0, ld0=16, up0=0, B=B, Hi=Hs,
+                                 Wi=Ws, Ho=Hs, Wo=Ws, kh=4, kw=1, stride=1, pad=2, dy=dy.data_ptr(), ldy=64, Cout=64, cin_real=3,
+                                 cout_real=64, dw=dw.data_ptr()), stream)
+    torch.cuda.synchronize()
+    xd = x.bfloat16().double().cpu()
+    dw_ref = torch.nn.grad.conv2d_weight(xd, (64, 3, 7, 7), dy.double().cpu().permute(0, 3, 1, 2), stride=2, padding=3)
+    assert rel_err(dw.cpu(), dw_ref.float()) < 1e-4, rel_err(dw.cpu(), dw_ref.float())
     assert _lib.load().d3fk_device_error_flag() == 0
