@@ -587,6 +587,8 @@ __global__ void __launch_bounds__(WGS_THREADS) wgrad_slab_kernel(const __grid_co
 }
 
 static int g_use_wg_slab = 1;   // D3FK_WG_SLAB=0: never take the slab weight-gradient path
+static int g_wgs_smax = 4;      // D3FK_WGS_SMAX (debug builds): largest super-tile (sub-tiles of 128 pixels) of the slab weight gradient
+static int g_wgs_stages = 3;    // D3FK_WGS_STAGES (debug builds): deepest pipeline tried (<= 4)
 
 template <int BN>
 static int launch_wgrad_slab_bn(const Gather& g, const d3fk_wgrad_params* p, cudaStream_t s, WgSlabSched& ss) {
@@ -602,7 +604,7 @@ static int launch_wgrad_slab_bn(const Gather& g, const d3fk_wgrad_params* p, cud
   if (2 * 3 * ss.MB * ACC > 512) return 0;
   int smem = 0;
   bool found = false;
-  for (int S = 4; S >= 1 && !found; S >>= 1) {
+  for (int S = g_wgs_smax; S >= 1 && !found; S >>= 1) {
     if (H % (S * R)) continue;
     const int slab = ((S * R + 2) * Wt * ss.a_row_bytes + 1023) & ~1023;
     const int dyb = (S * 128 * ss.b_row_bytes + 1023) & ~1023;
@@ -610,7 +612,7 @@ static int launch_wgrad_slab_bn(const Gather& g, const d3fk_wgrad_params* p, cud
     // inside the stage (the dY tile that follows the slabs absorbs them)
     const int overrun = (128 / C > 3 ? 128 / C - 3 : (C == 64 ? 1 : 0)) * Wt * ss.a_row_bytes;
     if (overrun > dyb) continue;
-    for (int stages = 3; stages >= 2; --stages) {
+    for (int stages = g_wgs_stages; stages >= 2; --stages) {
       const int need = 1024 + stages * (3 * slab + dyb) + 128;
       if (need > SLAB_MAX_SMEM) continue;
       ss.S = S; ss.slab_bytes = slab; ss.slab_tx = (S * R + 2) * Wt * ss.a_row_bytes; ss.dy_bytes = S * 128 * ss.b_row_bytes;
@@ -700,6 +702,8 @@ int wgrad_init() {
   cudaError_t e = cudaSuccess;
 #ifdef D3FK_DEBUG
   if (const char* v = getenv("D3FK_WG_SLAB")) g_use_wg_slab = atoi(v);
+  if (const char* v = getenv("D3FK_WGS_SMAX")) g_wgs_smax = atoi(v);
+  if (const char* v = getenv("D3FK_WGS_STAGES")) { g_wgs_stages = atoi(v); if (g_wgs_stages > 4) g_wgs_stages = 4; if (g_wgs_stages < 2) g_wgs_stages = 2; }
   if (const char* v = getenv("D3FK_WG_OCC")) g_wg_ctas_per_sm = atoi(v);
   if (const char* v = getenv("D3FK_WG_TMA")) g_wg_tma = atoi(v);
   if (const char* v = getenv("D3FK_WG_CAP")) g_wg_cap = atoi(v);
