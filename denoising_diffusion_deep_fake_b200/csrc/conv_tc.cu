@@ -1,13 +1,14 @@
-// conv_tc.cu — bf16 implicit-GEMM convolution, dgrad and wgrad on the Blackwell 5th-gen tensor
-// cores: tcgen05.mma issued by one elected thread, accumulators in TMEM, operands staged in
-// 128B-swizzled shared memory by an asynchronous gather (cp.async completing on mbarriers),
-// tcgen05.ld epilogue fused with BN-statistics / folded-BN affine / residual / ReLU.
+// conv_tc.cu — bf16 implicit-GEMM convolution and dgrad on the Blackwell 5th-gen tensor cores (the weight gradients live
+// in wgrad_tc.cu, the narrow 3x3 layers in conv_slab.cu): tcgen05.mma issued by one ELECTED thread (elect.sync),
+// accumulators double-buffered in TMEM, operands in 128B-swizzled shared memory — by TMA boxes (PATH 2: stride-1 "same"
+// convolutions; also the space-to-depth stem, conv mode 2) or by an asynchronous per-thread gather (PATH 0 / 1: cp.async
+// completing on mbarriers) —, tcgen05.ld epilogue fused with BN statistics / folded-BN affine / residual / ReLU, split K
+// over a thread-block cluster with an st.async reduce-scatter, train-mode BatchNorm fused behind a grid barrier.
 //
-// Forward / dgrad:  D[M = B*Ho*Wo pixels, N = Cout] = A[M, K = taps*Cin] x W[N, K]^T     (both K-major)
-// Weight gradient:  D[M = 128 k-rows, N = Cout]     = A[pixels, k]^T x dY[pixels, Cout]  (both MN-major)
+// D[M = B*Ho*Wo pixels, N = Cout] = A[M, K = taps*Cin] x W[N, K]^T     (both K-major)
 //
-// Warp roles (160 threads): warps 0-3 = gather producers, then epilogue (TMEM lane quarter = warp);
-// warp 4 = TMEM allocator + single-thread MMA issuer.
+// Warp roles (320 threads): warps 0-3 = gather producers (PATH 0 / 1), then epilogue (TMEM lane quarter = warp % 4);
+// warp 4 = TMEM allocator + MMA issuer; warp 5 = TMA producer; warps 6-9 = epilogue helpers (odd column chunks).
 #include "tc_common.cuh"
 
 namespace d3fk {

@@ -135,26 +135,6 @@ __device__ __forceinline__ void umma_f16_lohi(uint32_t d_tmem, uint32_t alo, uin
       ::"r"(d_tmem), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// Warp-uniform issue: the whole MMA warp runs the loop and only the leader lane's instruction takes effect (inside an
-// `if (lane == 0)` region ptxas wraps every tcgen05.mma in an ELECT / R2UR serialisation loop).
-__device__ __forceinline__ void umma_f16_lohi_p(uint32_t d_tmem, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t idesc,
-                                                uint32_t accumulate, uint32_t leader) {
-  asm volatile(
-      "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
-      "mov.b64 da, {%1, %2};\n\t"
-      "mov.b64 db, {%3, %4};\n\t"
-      "setp.ne.b32 p, %6, 0;\n\t"
-      "setp.ne.b32 q, %7, 0;\n\t"
-      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
-      ::"r"(d_tmem), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate), "r"(leader)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit_p(uint32_t bar, uint32_t leader) {
-  asm volatile(
-      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
-      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar), "r"(leader)
-      : "memory");
-}
 // mbarrier arrive once all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
