@@ -59,3 +59,22 @@ def test_product_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+def test_op_kinds_match_the_header_enum():
+    """Every D3FK_OP_* value of include/d3fk.h equals the OP_* constant of the Python mirror (and vice versa)."""
+    text = open(os.path.join(ROOT, "include", "d3fk.h")).read()
+    body = text[text.index("enum d3fk_op_kind"):]
+    body = re.sub(r"/\*.*?\*/", "", body[:body.index("};")], flags=re.S)
+    header = {m.group(1): int(m.group(2)) for m in re.finditer(r"D3FK_OP_([A-Z0-9_]+)\s*=\s*(\d+)", body)}
+    mirror = {k[3:]: v for k, v in vars(_lib).items() if k.startswith("OP_") and isinstance(v, int)}
+    assert header == mirror, (sorted(set(header.items()) ^ set(mirror.items())))
+    assert len(set(header.values())) == len(header)          # no two kinds share a value
+
+
+def test_space_to_depth_stem_is_chosen_where_its_tile_is_a_box():
+    """plan.UnetPlan._stem_box_ok mirrors tma_box() of csrc/conv_tc.cu for the stem's output grid."""
+    from denoising_diffusion_deep_fake_b200.plan import UnetPlan
+    ok = UnetPlan._stem_box_ok
+    assert ok(32, 32) and ok(64, 64) and ok(128, 128) and ok(16, 16) and ok(32, 16) and ok(16, 256)
+    assert not ok(48, 48) and not ok(80, 80)                 # 96 x 96 / 160 x 160 inputs keep the gather-form stem

@@ -174,8 +174,9 @@ def test_eval_forward_parity(precision, tol):
         ref(torch.randn(4, 3, 64, 64))
     m.load_state_dict(ref.state_dict())
     ref.eval(), m.eval()
-    # B = 1 (video inference), the smallest legal image (1x1 bottleneck), a non-square one, BASELINE configs[4]'s 256x256
-    for B, H, W in ((1, 64, 64), (4, 64, 64), (2, 128, 64), (3, 32, 32), (1, 256, 256)):
+    # B = 1 (video inference), the smallest legal image (1x1 bottleneck), a non-square one, BASELINE configs[4]'s 256x256, and a
+    # size whose stem tile is not a (w, h, n) box (96 x 96: the gather-form stem instead of the space-to-depth one)
+    for B, H, W in ((1, 64, 64), (4, 64, 64), (2, 128, 64), (3, 32, 32), (1, 256, 256), (2, 96, 96)):
         x = torch.randn(B, 3, H, W)
         with torch.no_grad():
             y_ref = ref(x)
