@@ -75,7 +75,8 @@ class PoolParams(C.Structure):
 
 
 class LayoutParams(C.Structure):
-    _fields_ = [("dtype", i32), ("B", i32), ("C", i32), ("H", i32), ("W", i32), ("cpad", i32), ("src", vp), ("dst", vp)]
+    _fields_ = [("dtype", i32), ("B", i32), ("C", i32), ("H", i32), ("W", i32), ("cpad", i32), ("src", vp), ("dst", vp),
+                ("chansum", vp)]
 
 
 class ChansumParams(C.Structure):

@@ -27,10 +27,15 @@ static inline int grid_for(long long work_items, int threads, int max_waves = 8)
 
 // ---------------------------------------------------------------------------------------------
 // NCHW fp32 -> NHWC T, channels zero-padded to cpad (a multiple of 8)
+// chansum (nullable, C <= 8): per-channel sums of the rounded values written, accumulated with one atomic per warp and channel
+// (the head's bias gradient: saves the separate pass over dst).
 template <typename T>
-__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, T* __restrict__ dst, int B, int C, int HW, int cpad) {
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, T* __restrict__ dst, int B, int C, int HW, int cpad, float* chansum) {
   pdl_enter();
   long long total = (long long)B * HW;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
   for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < total; p += (long long)gridDim.x * blockDim.x) {
     long long n = p / HW;
     long long hw = p - n * HW;
@@ -42,6 +47,20 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, T* __restrict
 #pragma unroll
       for (int i = 0; i < V; ++i) v[i] = (c0 + i < C) ? __ldg(s + (long long)(c0 + i) * HW) : 0.f;
       store_vec<T>(d + c0, v);
+      if (chansum && c0 < 8) {
+#pragma unroll
+        for (int i = 0; i < V; ++i)
+          if (c0 + i < 8) acc[c0 + i] += to_f<T>(from_f<T>(v[i]));
+      }
+    }
+  }
+  if (chansum) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float a = acc[i];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      if ((threadIdx.x & 31) == 0 && i < C) atomicAdd(chansum + i, a);
     }
   }
 }
@@ -1025,8 +1044,9 @@ __global__ void __launch_bounds__(256) tensor_to_frames_kernel(d3fk_frames_param
 
 int launch_nchw_to_nhwc(const d3fk_layout_params* p, cudaStream_t s) {
   D3FK_CHECK_ARG(p->cpad % 8 == 0 && p->C <= p->cpad, "cpad must be a multiple of 8 and >= C");
+  D3FK_CHECK_ARG(!p->chansum || p->C <= 8, "chansum: C <= 8");
   long long total = (long long)p->B * p->H * p->W;
-  DISPATCH_T(p->dtype, launch_k(nchw_to_nhwc_kernel<T>, dim3(grid_for(total, 256)), dim3(256), 0, s, dim3(1, 1, 1), p->src, (T*)p->dst, p->B, p->C, p->H * p->W, p->cpad));
+  DISPATCH_T(p->dtype, launch_k(nchw_to_nhwc_kernel<T>, dim3(grid_for(total, 256)), dim3(256), 0, s, dim3(1, 1, 1), p->src, (T*)p->dst, p->B, p->C, p->H * p->W, p->cpad, p->chansum));
   count_launch();
   return check_launch("nchw_to_nhwc");
 }

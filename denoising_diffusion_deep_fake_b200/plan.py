@@ -575,10 +575,9 @@ class UnetPlan:
         self.dy8 = T(self, B, self.H, self.W, DY_PAD)
         self.keep.append(self.dy8.t)
         self.dy_op_index = len(ops)
+        # ... and the head's bias gradient (per-channel sums of dY) in the same pass
         ops.append(make_op(_lib.OP_NCHW2NHWC, dtype=self.dtype, B=B, C=3, H=self.H, W=self.W, cpad=DY_PAD, src=None,
-                           dst=self.dy8.ptr))
-        ops.append(make_op(_lib.OP_CHANSUM, dtype=self.dtype, C=3, ld=DY_PAD, count=self.dy8.count, x=self.dy8.ptr,
-                           out=self._gptr(self.head.name + ".bias")))
+                           dst=self.dy8.ptr, chansum=self._gptr(self.head.name + ".bias")))
         ops.append(self._wgrad_op(self.head, self.dec_out, None, 0, self.dy8))
         g = self._newT(self.dec_out)
         ops.append(self._dgrad_op(self.head, self.dy8, g))

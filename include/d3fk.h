@@ -165,6 +165,8 @@ typedef struct d3fk_pool_params {
 typedef struct d3fk_layout_params {
   int32_t dtype, B, C, H, W, cpad;
   const float* src; void* dst;            /* src fp32 NCHW [B,C,H,W] -> dst NHWC dtype [B,H,W,cpad] */
+  float* chansum;                         /* D3FK_OP_NCHW2NHWC, nullable, C <= 8: chansum[c] += sum over pixels of the (dtype-rounded) values
+                                             written — the bias gradient of the head, without a second pass over dst */
 } d3fk_layout_params;
 
 /* nearest 2x upsample of src0 + channel concat with src1, materialised (smp DecoderBlock: F.interpolate(scale_factor=2) +

@@ -111,6 +111,8 @@ def run_layout(p):
     dst = view(p.dst, (p.B, p.H, p.W, p.cpad))
     dst.zero_()
     dst[..., :p.C] = src.permute(0, 2, 3, 1)
+    if p.chansum:
+        view(p.chansum, (p.C,)).add_(dst[..., :p.C].reshape(-1, p.C).sum(0))
 
 
 def run_bn_finalize(p):
