@@ -162,3 +162,36 @@ def test_pack_buckets_follow_backward_segments():
             for q in written:
                 off = (q - base) // 4
                 assert buckets[j][0] <= off < buckets[j][1], f"segment {j} writes a gradient of another bucket ({off})"
+
+
+def test_bf16_plan_structure_space_to_depth_stem_and_materialised_concats():
+    """Host logic only (no kernel runs): the bf16 plans route the stem through the space-to-depth operands (forward AND weight
+    gradient, conv / wgrad mode 2), pack its weights in the stem's own gradient bucket, read the caller's input through ONE
+    layout op, and materialise upsample + concat for all five decoder blocks; a size whose stem tile is not a box keeps the
+    gather-form stem."""
+    m = d3.Unet(precision="bf16")
+    m._ensure_grad_arena(torch.device("cpu"))
+    plan = UnetPlan(dict(m.named_parameters()), dict(m.named_buffers()), 2, 64, 64, _lib.BF16, "cpu", True,
+                    grad_arena=m._grad_arena, grad_offsets=m._grad_offsets)
+    assert plan.stem_s2d and len(plan.in_op_indices) == 1
+    kinds = [op.kind for op in plan.fwd_ops]
+    assert kinds.count(_lib.OP_NCHW2S2D) == 1 and kinds.count(_lib.OP_NCHW2NHWC) == 0 and kinds.count(_lib.OP_UPCAT) == 5
+    stem = next(op for op in plan.fwd_ops if op.kind == _lib.OP_CONV_BN)
+    cv = _lib.op_params(stem).conv
+    assert (cv.mode, cv.c0, cv.ld0, cv.kh, cv.kw, cv.stride, cv.pad, cv.Hi, cv.Wi, cv.Ho, cv.Wo, cv.Cout) == (2, 64, 16, 4, 1, 1, 2, 32, 32, 32, 32, 64)
+    assert cv.src0 == plan.xs2d.data_ptr() and cv.w == plan.w_stem_s2d.data_ptr() and tuple(plan.xs2d.shape) == (2, 32, 35, 16)
+    wg = [op for seg in plan.bwd_segments for op in seg if op.kind == _lib.OP_WGRAD]
+    stem_wg = [op for op in wg if _lib.op_params(op).mode == 2]
+    assert len(stem_wg) == 1 and _lib.op_params(stem_wg[0]).cin_real == 3 and stem_wg[0] is not None
+    assert _lib.op_params(stem_wg[0]).dw == m._grad_arena.data_ptr() + 4 * m._grad_offsets["encoder.conv1.weight"]
+    # the stem's pack op lives in the last bucket (layer1 + stem), behind that bucket's pack_all
+    per_bucket = [[op.kind for op in ol] if ol is not None else [] for ol in plan.pack_bucket_ops]
+    assert [k.count(_lib.OP_PACK_STEM) for k in per_bucket] == [0, 0, 0, 0, 1] and per_bucket[-1][0] == _lib.OP_PACK_ALL
+    # eval plan: same stem, one layout op, no weight gradient
+    plan_e = UnetPlan(dict(m.named_parameters()), dict(m.named_buffers()), 2, 64, 64, _lib.BF16, "cpu", False)
+    assert plan_e.stem_s2d and [op.kind for op in plan_e.fwd_ops].count(_lib.OP_NCHW2S2D) == 1
+    assert plan_e.in_op_index == plan_e.in_op_indices[0] and plan_e.bwd_segments is None
+    # 96 x 96: the stem's 128-pixel tile is not a (w, h, n) box -> gather form on the 8-channel NHWC image
+    plan_g = UnetPlan(dict(m.named_parameters()), dict(m.named_buffers()), 1, 96, 96, _lib.BF16, "cpu", False)
+    assert not plan_g.stem_s2d and [op.kind for op in plan_g.fwd_ops].count(_lib.OP_NCHW2NHWC) == 1
+    assert _lib.op_params(next(op for op in plan_g.fwd_ops if op.kind == _lib.OP_CONV)).mode == 0
