@@ -298,7 +298,12 @@ static int run_list(const d3fk_op* ops, int n_ops, cudaStream_t main_stream, boo
     }
     const bool is_wgrad = ops[i].kind == D3FK_OP_WGRAD || ops[i].kind == D3FK_OP_WGRAD_GROUP;
 #ifdef D3FK_DEBUG
-    if (is_wgrad && g_skip_wgrad) continue;   // timing experiment only (D3FK_SKIP_WGRAD=1)
+    if (is_wgrad && g_skip_wgrad) {           // timing experiment only (D3FK_SKIP_WGRAD: 1 = all; else 2 << class, class by pixel count)
+      const d3fk_wgrad_params* wp = ops[i].kind == D3FK_OP_WGRAD ? &ops[i].u.wgrad : &ops[i].u.wgrad_group.base;
+      const long long M = (long long)wp->B * wp->Ho * wp->Wo;
+      const int cls = M >= 262144 ? 0 : M >= 65536 ? 1 : M >= 16384 ? 2 : M >= 4096 ? 3 : 4;
+      if ((g_skip_wgrad & 1) || ((g_skip_wgrad >> (1 + cls)) & 1)) continue;
+    }
 #endif
     if (is_wgrad && g_fork_wgrad && n_ops > 1) {
       cudaEvent_t ev = g_fork_events[g_fork_cursor++ % g_n_fork_events];

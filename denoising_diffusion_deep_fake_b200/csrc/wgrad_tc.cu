@@ -439,6 +439,8 @@ struct WgSlabSched {
   int total, tiles_per_img;
   int MB;                 // accumulator row blocks per kw: 1 (Cin <= 32: kh 0..2 in one M = 128) or 2 (Cin = 64)
   uint32_t a_layout, b_layout;
+  uint32_t coalesce;      // epilogue: 0 = one atomicAdd per lane and element, 1 = staged + coalesced, 2 = staged + 16-byte reductions
+  uint32_t ablate;        // -DD3FK_DEBUG builds only (D3FK_WGS_ABLATE): 1 = no atomic epilogue, 2 = no MMAs, 4 = no slab loads, 8 = no dY load
 };
 
 __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
@@ -504,8 +506,17 @@ __global__ void __launch_bounds__(WGS_THREADS) wgrad_slab_kernel(const __grid_co
         const int h0 = hb * rows, w0 = (rem - hb * ss.wtiles) * ss.Wt;
         const int st = it % ss.stages;
         if (it >= (uint32_t)ss.stages) mbar_wait(empty_bar(st), ((it / ss.stages) - 1) & 1, errflag);
-        mbar_arrive_expect_tx(full_bar(st), 3u * ss.slab_tx + (uint32_t)ss.dy_bytes);
         const uint32_t sb = stage_base + st * ss.stage_bytes;
+#ifdef D3FK_DEBUG
+        if (ss.ablate & 12u) {
+          const uint32_t tx = ((ss.ablate & 4u) ? 0u : 3u * ss.slab_tx) + ((ss.ablate & 8u) ? 0u : (uint32_t)ss.dy_bytes);
+          if (tx) mbar_arrive_expect_tx(full_bar(st), tx); else mbar_arrive(full_bar(st));
+          if (!(ss.ablate & 4u)) for (int sx = 0; sx < 3; ++sx) tma_load_4d(sb + sx * ss.slab_bytes, &tmA, 0, w0 + sx - 1, h0 - 1, n, full_bar(st));
+          if (!(ss.ablate & 8u)) tma_load_4d(sb + 3 * ss.slab_bytes, &tmD, 0, w0, h0, n, full_bar(st));
+          continue;
+        }
+#endif
+        mbar_arrive_expect_tx(full_bar(st), 3u * ss.slab_tx + (uint32_t)ss.dy_bytes);
         for (int sx = 0; sx < 3; ++sx) tma_load_4d(sb + sx * ss.slab_bytes, &tmA, 0, w0 + sx - 1, h0 - 1, n, full_bar(st));
         tma_load_4d(sb + 3 * ss.slab_bytes, &tmD, 0, w0, h0, n, full_bar(st));
       }
@@ -535,6 +546,9 @@ __global__ void __launch_bounds__(WGS_THREADS) wgrad_slab_kernel(const __grid_co
         const uint32_t sb = stage_base + st * ss.stage_bytes;
         const uint32_t b_lo = (blo0 | ((sb + 3u * ss.slab_bytes) >> 4)) + b_par;
         const uint32_t a_lo = (alo0 | ((sb + (uint32_t)(sx * ss.slab_bytes)) >> 4)) + a_par;
+#ifdef D3FK_DEBUG
+        if (ss.ablate & 2u) { umma_commit(empty_bar(st)); continue; }
+#endif
         for (int mb = 0; mb < ss.MB; ++mb) {
           const uint32_t d_addr = d_base + (uint32_t)(mb * ACC);
           uint32_t a_cur = a_lo + (uint32_t)mb * mb_off, b_cur = b_lo;
@@ -552,15 +566,22 @@ __global__ void __launch_bounds__(WGS_THREADS) wgrad_slab_kernel(const __grid_co
     }
     __syncwarp();
   } else if (has_work) {
-    // epilogue (once per CTA): accumulator row r of (kw, row block mb) = tap kh = mb*(128/C) + r / C, channel ci = r % C
+    // epilogue (once per CTA): accumulator row r of (kw, row block mb) = tap kh = mb*(128/C) + r / C, channel ci = r % C.
+    // The CTA's whole result is first laid out in shared memory (the pipeline stages are free by now) in dW's own order
+    // [co][ci][kh][kw], then added to dW with COALESCED reductions (red.global.add.v4.f32 where the alignment allows): a
+    // lane-per-row atomicAdd hits 32 different sectors per instruction, and 148 CTAs x 18 k of those cost more than the
+    // main loop (ablation, tools/gpu_run57.sh: 288 -> 173 us over the six decoder-tail layers with the atomics removed).
     mbar_wait(acc_full, 0, errflag);
     tc_fence_after();
     const int r = warp * 32 + lane;
     const int apm = 128 / ss.C;
+    const int ce = ss.C < cin_real ? ss.C : cin_real;      // channels of this launch that exist in dW
+    const int run = ce * 9;                                // contiguous floats of dW per output channel
+    float* stg = reinterpret_cast<float*>(smem_raw + (stage_base - smem_u32(smem_raw)));
     for (int sx = 0; sx < 3; ++sx) {
       for (int mb = 0; mb < ss.MB; ++mb) {
         const int kh = mb * apm + r / ss.C, ci = r % ss.C;
-        const bool ok = kh < 3 && ci < cin_real;
+        const bool ok = kh < 3 && ci < ce;
 #pragma unroll 1
         for (int cc = 0; cc < BN; cc += 16) {
           uint32_t raw[16], raw2[16];
@@ -568,14 +589,44 @@ __global__ void __launch_bounds__(WGS_THREADS) wgrad_slab_kernel(const __grid_co
           tmem_ld16(ta, raw);
           tmem_ld16(ta + (uint32_t)(nacc * ACC), raw2);     // the odd-K-step accumulator set
           tmem_ld_wait();
+#ifdef D3FK_DEBUG
+          if (ss.ablate & 1u) continue;
+#endif
           if (ok) {
+            if (ss.coalesce) {
+              float* q = stg + ci * 9 + kh * 3 + sx;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const int co = cc + i;
-              if (co < cout_real)
-                atomicAdd(dw + ((long long)co * cin_real + ci) * 9 + kh * 3 + sx, __uint_as_float(raw[i]) + __uint_as_float(raw2[i]));
+              for (int i = 0; i < 16; ++i)
+                if (cc + i < cout_real) q[(cc + i) * run] = __uint_as_float(raw[i]) + __uint_as_float(raw2[i]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const int co = cc + i;
+                if (co < cout_real)
+                  atomicAdd(dw + ((long long)co * cin_real + ci) * 9 + kh * 3 + sx, __uint_as_float(raw[i]) + __uint_as_float(raw2[i]));
+              }
             }
           }
+        }
+      }
+    }
+    if (ss.coalesce) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");        // the four epilogue warps only
+      const int total = cout_real * run;
+      const long long gstride = (long long)cin_real * 9;
+#ifdef D3FK_DEBUG
+      if (ss.ablate & 1u) { /* timing experiment: staging only */ } else
+#endif
+      if (ss.coalesce == 2) {                                // 16-byte aligned rows: vector reductions
+        for (int j = tid * 4; j < total; j += 128 * 4) {
+          const int co = j / run, o = j - co * run;
+          const float4 v = *reinterpret_cast<const float4*>(stg + j);
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dw + co * gstride + o), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+        }
+      } else {
+        for (int j = tid; j < total; j += 128) {
+          const int co = j / run, o = j - co * run;
+          atomicAdd(dw + co * gstride + o, stg[j]);
         }
       }
     }
@@ -589,6 +640,8 @@ __global__ void __launch_bounds__(WGS_THREADS) wgrad_slab_kernel(const __grid_co
 static int g_use_wg_slab = 1;   // D3FK_WG_SLAB=0: never take the slab weight-gradient path
 static int g_wgs_smax = 4;      // D3FK_WGS_SMAX (debug builds): largest super-tile (sub-tiles of 128 pixels) of the slab weight gradient
 static int g_wgs_stages = 3;    // D3FK_WGS_STAGES (debug builds): deepest pipeline tried (<= 4)
+static int g_wgs_coalesce = 2;  // D3FK_WGS_COALESCE (debug builds): 0 = per-lane atomics, 1 = staged scalar, 2 = staged 16-byte reductions
+static int g_wgs_ablate = 0;    // D3FK_WGS_ABLATE (debug builds): see WgSlabSched::ablate
 
 template <int BN>
 static int launch_wgrad_slab_bn(const Gather& g, const d3fk_wgrad_params* p, cudaStream_t s, WgSlabSched& ss) {
@@ -600,6 +653,7 @@ static int launch_wgrad_slab_bn(const Gather& g, const d3fk_wgrad_params* p, cud
   ss.a_layout = C == 64 ? 2u : C == 32 ? 4u : 6u;
   ss.b_layout = BN == 64 ? 2u : BN == 32 ? 4u : 6u;
   ss.MB = C == 64 ? 2 : 1;
+  ss.ablate = (uint32_t)g_wgs_ablate;
   const int ACC = BN < 32 ? 32 : BN;
   if (2 * 3 * ss.MB * ACC > 512) return 0;
   int smem = 0;
@@ -625,6 +679,14 @@ static int launch_wgrad_slab_bn(const Gather& g, const d3fk_wgrad_params* p, cud
     }
   }
   if (!found) return 0;
+  {
+    // staged epilogue: the CTA's [cout_real][min(C, cin_real) * 9] result must fit the (then idle) pipeline stages
+    const int ce = C < p->cin_real ? C : p->cin_real;
+    const size_t need = (size_t)p->cout_real * ce * 9 * sizeof(float);
+    ss.coalesce = 0;
+    if (g_wgs_coalesce && need <= (size_t)ss.stages * ss.stage_bytes)
+      ss.coalesce = (g_wgs_coalesce > 1 && ce % 4 == 0 && p->cin_real % 4 == 0 && ((uintptr_t)p->dw & 15) == 0) ? 2u : 1u;
+  }
   alignas(64) CUtensorMap tmA, tmD;
   {
     uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)p->B};
@@ -703,6 +765,8 @@ int wgrad_init() {
 #ifdef D3FK_DEBUG
   if (const char* v = getenv("D3FK_WG_SLAB")) g_use_wg_slab = atoi(v);
   if (const char* v = getenv("D3FK_WGS_SMAX")) g_wgs_smax = atoi(v);
+  if (const char* v = getenv("D3FK_WGS_ABLATE")) g_wgs_ablate = atoi(v);
+  if (const char* v = getenv("D3FK_WGS_COALESCE")) g_wgs_coalesce = atoi(v);
   if (const char* v = getenv("D3FK_WGS_STAGES")) { g_wgs_stages = atoi(v); if (g_wgs_stages > 4) g_wgs_stages = 4; if (g_wgs_stages < 2) g_wgs_stages = 2; }
   if (const char* v = getenv("D3FK_WG_OCC")) g_wg_ctas_per_sm = atoi(v);
   if (const char* v = getenv("D3FK_WG_TMA")) g_wg_tma = atoi(v);

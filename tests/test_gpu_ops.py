@@ -378,6 +378,40 @@ WGRAD_GROUP_CASES = [
 ]
 
 
+@pytest.mark.parametrize("variant", ["halves_accumulate", "misaligned_dw", "narrow_out_misaligned"])
+def test_wgrad_slab_epilogue_paths(variant):
+    """The slab weight gradient's epilogue stages the CTA's result in dW order and adds it with coalesced reductions
+    (16-byte `red.global.add.v4.f32` when dW rows are 16-byte aligned, scalar otherwise).  Covered here: the two 64-channel
+    halves of a 128-channel input accumulating into one NON-ZERO dW (plan.py `_wgrad_ops`), and dW at a 4-byte offset."""
+    _lib.init(0)
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(11)
+    if variant == "halves_accumulate":
+        B, H, W, cin, C, Cout, cout_real, off = 76, 32, 32, 128, 64, 32, 32, 0
+    elif variant == "misaligned_dw":
+        B, H, W, cin, C, Cout, cout_real, off = 76, 32, 32, 32, 32, 32, 32, 1
+    else:
+        B, H, W, cin, C, Cout, cout_real, off = 19, 64, 64, 16, 16, 16, 3, 3
+    x = torch.randn(B, H, W, cin, generator=g).bfloat16().to(dev)
+    dy = torch.randn(B, H, W, Cout, generator=g).bfloat16().to(dev)
+    n = cout_real * cin * 9
+    arena = torch.ones(n + 8, device=dev)
+    dw = arena[off:off + n]
+    s = torch.cuda.current_stream().cuda_stream
+    for half in range(cin // C):
+        op = _lib.make_op(_lib.OP_WGRAD, dtype=_lib.BF16, src0=x.data_ptr() + half * C * 2, c0=C, c1=0, ld0=cin, ld1=0, up0=0,
+                          B=B, Hi=H, Wi=W, Ho=H, Wo=W, kh=3, kw=3, stride=1, pad=1, dy=dy.data_ptr(), ldy=Cout, Cout=Cout,
+                          cin_real=cin, cout_real=cout_real, dw=dw.data_ptr() + half * C * 9 * 4)
+        _lib.run_single(op, s)
+    torch.cuda.synchronize()
+    assert _lib.load().d3fk_device_error_flag() == 0, "kernel watchdog tripped"
+    ref = torch.nn.grad.conv2d_weight(x.float().cpu().permute(0, 3, 1, 2).double(), (Cout, cin, 3, 3),
+                                      dy.float().cpu().permute(0, 3, 1, 2).double(), stride=1, padding=1)[:cout_real]
+    got = dw.cpu().double().view(cout_real, cin, 3, 3) - 1.0        # dW started at one: the launch accumulates
+    assert rel_err(got, ref) < 1e-4, rel_err(got, ref)
+    assert float(arena[:off].sub(1).abs().sum() + arena[off + n:].sub(1).abs().sum()) == 0.0   # nothing outside dW touched
+
+
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("count,B,H,C", WGRAD_GROUP_CASES)
 def test_wgrad_group(dtype, count, B, H, C):
