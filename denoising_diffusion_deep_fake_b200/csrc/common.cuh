@@ -61,8 +61,10 @@ static inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 blo
 #ifdef __CUDACC__
 // grid-wide barrier for a co-resident grid (called by ONE thread per CTA, after its CTA's global writes / atomics)
 __device__ __forceinline__ void grid_barrier_arrive_wait(unsigned* counter, unsigned expected, int* errflag) {
-  __threadfence();
-  atomicAdd(counter, 1u);
+  // arrive: a RELEASE reduction at gpu scope (cumulative over what the CTA's other threads wrote before the CTA barrier that
+  // precedes this call) — no returned value to wait for; wait: acquire loads, which order everything after them (the CTA
+  // barrier that follows hands that order to the other threads), so no trailing fence.
+  asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
   const long long t0 = clock64();
   while (true) {
     unsigned v;
@@ -74,9 +76,7 @@ __device__ __forceinline__ void grid_barrier_arrive_wait(unsigned* counter, unsi
              expected, (void*)counter);
       __trap();
     }
-    __nanosleep(64);
   }
-  __threadfence();
 }
 
 __device__ __forceinline__ void pdl_enter() {

@@ -392,6 +392,8 @@ static int launch_wgrad_tc_bn(const Gather& g, const d3fk_wgrad_params* p, cudaS
       const int sp = cand[i];
       // cluster reduction: (c - 1) / c of each CTA's 128 x BN fp32 tile crosses the SM-to-SM network (~19 B / cycle / SM, two CTAs per SM)
       const double dsmem_us = c > 1 ? 0.5 + (double)(c - 1) / c * (128.0 * BN * 4 * g_wg_ctas_per_sm) / (19.0 * 1965.0) : 0.0;
+      // (an epilogue-store term — 128 x BN / c scattered 4-byte accesses per CTA — was tried: it only moves layer4 to a 2-CTA
+      // cluster split, 20.3 -> 23.5 us; those kernels are bound by L2 -> SM operand traffic, 512 KB per CTA)
       const double est = (double)cdiv(nblk, sp) * stage_us + (sp > c ? (sp / c) * elems / 216e3 : 0.0) + dsmem_us;
       if (est < best) { best = est; cl = c; splits = sp; }
     }
