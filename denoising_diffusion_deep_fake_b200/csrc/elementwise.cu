@@ -535,21 +535,35 @@ __global__ void maxpool_fwd_kernel(d3fk_pool_params p) {
     unsigned char bi[V];
 #pragma unroll
     for (int i = 0; i < V; ++i) { best[i] = -INFINITY; bi[i] = 0; }
-    bool first = true;
-    for (int kh = 0; kh < 3; ++kh) {
-      int h = 2 * ho - 1 + kh;
-      if ((unsigned)h >= (unsigned)p.H) continue;
-      for (int kw = 0; kw < 3; ++kw) {
-        int w = 2 * wo - 1 + kw;
-        if ((unsigned)w >= (unsigned)p.W) continue;
-        float v[V];
-        load_vec<T>(x + ((long long)(n * p.H + h) * p.W + w) * p.ldx + c, v);
+    // all nine 16-byte loads are issued before the first compare (out-of-image taps load a clamped, valid address and are
+    // skipped by predicate): nine independent requests in flight per thread instead of a branchy load-compare chain
+    uint4 raw[9];
+    bool ok[9];
 #pragma unroll
-        for (int i = 0; i < V; ++i) {
-          if (first || v[i] > best[i] || v[i] != v[i]) { best[i] = v[i]; bi[i] = (unsigned char)(kh * 3 + kw); }
-        }
-        first = false;
+    for (int kh = 0; kh < 3; ++kh) {
+      const int h = 2 * ho - 1 + kh;
+      const bool hok = (unsigned)h < (unsigned)p.H;
+      const int hc = hok ? h : 2 * ho;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int w = 2 * wo - 1 + kw;
+        const bool wok = (unsigned)w < (unsigned)p.W;
+        const int wc = wok ? w : 2 * wo;
+        ok[kh * 3 + kw] = hok && wok;
+        raw[kh * 3 + kw] = *reinterpret_cast<const uint4*>(x + ((long long)(n * p.H + hc) * p.W + wc) * p.ldx + c);
       }
+    }
+    bool first = true;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      if (!ok[t]) continue;
+      const T* e8 = reinterpret_cast<const T*>(&raw[t]);
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const float v = to_f<T>(e8[i]);
+        if (first || v > best[i] || v != v) { best[i] = v; bi[i] = (unsigned char)t; }
+      }
+      first = false;
     }
     store_vec<T>(y + pix * p.ldy + c, best);
     if (p.idx) {
