@@ -643,6 +643,7 @@ static int g_use_wg_slab = 1;   // D3FK_WG_SLAB=0: never take the slab weight-gr
 static int g_wgs_smax = 4;      // D3FK_WGS_SMAX (debug builds): largest super-tile (sub-tiles of 128 pixels) of the slab weight gradient
 static int g_wgs_stages = 3;    // D3FK_WGS_STAGES (debug builds): deepest pipeline tried (<= 4)
 static int g_wgs_coalesce = 2;  // D3FK_WGS_COALESCE (debug builds): 0 = per-lane atomics, 1 = staged scalar, 2 = staged 16-byte reductions
+static int g_wgs_grid = 0;      // D3FK_WGS_GRID (debug builds): cap of the persistent grid (SMs left to the main chain)
 static int g_wgs_ablate = 0;    // D3FK_WGS_ABLATE (debug builds): see WgSlabSched::ablate
 
 template <int BN>
@@ -705,6 +706,7 @@ static int launch_wgrad_slab_bn(const Gather& g, const d3fk_wgrad_params* p, cud
     if (rc) return rc;
   }
   int grid = ss.total < g_num_sms ? ss.total : g_num_sms;
+  if (g_wgs_grid > 0 && grid > g_wgs_grid) grid = g_wgs_grid;
   if (g_verbose) fprintf(stderr, "[d3fk] wgrad_slab<%d> M=%d C=%d W=%d S=%d stages=%d smem=%d grid=%d total=%d\n", BN, g.M, C, W, ss.S, ss.stages, smem, grid, ss.total);
   launch_k(wgrad_slab_kernel<BN>, dim3(grid), dim3(WGS_THREADS), (size_t)smem, s, dim3(1, 1, 1), tmA, tmD, ss, p->dw, p->cin_real,
            p->cout_real, g_dev_error_flag);
@@ -768,6 +770,7 @@ int wgrad_init() {
   if (const char* v = getenv("D3FK_WG_SLAB")) g_use_wg_slab = atoi(v);
   if (const char* v = getenv("D3FK_WGS_SMAX")) g_wgs_smax = atoi(v);
   if (const char* v = getenv("D3FK_WGS_ABLATE")) g_wgs_ablate = atoi(v);
+  if (const char* v = getenv("D3FK_WGS_GRID")) g_wgs_grid = atoi(v);
   if (const char* v = getenv("D3FK_WGS_COALESCE")) g_wgs_coalesce = atoi(v);
   if (const char* v = getenv("D3FK_WGS_STAGES")) { g_wgs_stages = atoi(v); if (g_wgs_stages > 4) g_wgs_stages = 4; if (g_wgs_stages < 2) g_wgs_stages = 2; }
   if (const char* v = getenv("D3FK_WG_OCC")) g_wg_ctas_per_sm = atoi(v);
