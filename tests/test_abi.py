@@ -78,3 +78,33 @@ def test_space_to_depth_stem_is_chosen_where_its_tile_is_a_box():
     ok = UnetPlan._stem_box_ok
     assert ok(32, 32) and ok(64, 64) and ok(128, 128) and ok(16, 16) and ok(32, 16) and ok(16, 256)
     assert not ok(48, 48) and not ok(80, 80)                 # 96 x 96 / 160 x 160 inputs keep the gather-form stem
+
+
+def test_library_is_blackwell_tensor_core_code():
+    """The shipped libd3fk.so is tcgen05 / TMA code, not a recompiled mma.sync port: every convolution / weight-gradient kernel
+    carries UTCHMMA (tcgen05.mma) and LDTM (tcgen05.ld); the TMA-fed ones carry UTMALDG and no LDGSTS; MMA / TMA issue sits in
+    elect.sync regions (no R2UR.BROADCAST waterfall loops); the slab weight gradient reduces with 16-byte
+    REDG (item 8e); the only warp-level HMMA user is the N = 3 head (item 8h).  Reads SASS with cuobjdump: no GPU needed."""
+    import shutil, subprocess, sys
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "sass_opcodes.py"), _lib.LIB_PATH], capture_output=True, text=True,
+                         check=True).stdout.splitlines()
+    cols = out[0].split()[4:]            # after "kernel (mangled, d3fk:: stripped)"
+    rows = {}
+    for line in out[1:]:
+        parts = line.split()
+        rows[parts[0]] = dict(zip(cols, map(int, parts[1:])))
+    fam = {k: v for k, v in rows.items() if any(n in k for n in ("conv_tc_kernel", "conv_slab_kernel", "wgrad_tc_kernel", "wgrad_slab_kernel"))}
+    assert len(fam) >= 20
+    for k, v in fam.items():
+        assert v["UTCHMMA"] > 0 and v["LDTM"] > 0 and v["UTCBAR"] > 0, k
+        assert v["R2UR.BROADCAST"] == 0 and v["HMMA"] == 0, k
+    slab = [v for k, v in fam.items() if "slab" in k]
+    assert all(v["UTMALDG"] > 0 and v["LDGSTS"] == 0 for v in slab)
+    tma_wgrad = [v for k, v in fam.items() if "wgrad_tc_kernel" in k and "ELb1E" in k]
+    assert tma_wgrad and all(v["UTMALDG"] > 0 and v["LDGSTS"] == 0 for v in tma_wgrad)
+    assert all(v["RED.E.ADD.F32x4"] > 0 for k, v in fam.items() if "wgrad_slab" in k)
+    head = [v for k, v in rows.items() if "head_conv_mma" in k]
+    assert head and all(v["HMMA"] == 9 and v["LDSM"] == 9 for v in head)

@@ -14,7 +14,7 @@ for line in out.splitlines():
     if m:
         cur = m.group(1)
         continue
-    m = re.match(r"\s+/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Za-z0-9_.]*)", line)
+    m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Za-z0-9_.]*)", line)
     if not (cur and m):
         continue
     op = m.group(1)
