@@ -195,3 +195,25 @@ def test_bf16_plan_structure_space_to_depth_stem_and_materialised_concats():
     plan_g = UnetPlan(dict(m.named_parameters()), dict(m.named_buffers()), 1, 96, 96, _lib.BF16, "cpu", False)
     assert not plan_g.stem_s2d and [op.kind for op in plan_g.fwd_ops].count(_lib.OP_NCHW2NHWC) == 1
     assert _lib.op_params(next(op for op in plan_g.fwd_ops if op.kind == _lib.OP_CONV)).mode == 0
+
+
+def test_slab_weight_gradient_contract_halves_and_alignment():
+    """What the slab weight gradient's coalesced epilogue (csrc/wgrad_tc.cu) relies on, checked on the host: every gradient of
+    the flat arena starts on a 16-byte boundary (so dW rows take the 16-byte `red.global.add.v4.f32` form), and the 128 -> 32
+    channel layer of decoder block 3 is emitted as two 64-channel launches that accumulate into disjoint channel ranges of ONE
+    dW (cin_real = 128 for both, dW offset 64 * 9 floats, source offset 64 channels, pixel stride unchanged)."""
+    m = d3.Unet(precision="bf16")
+    m._ensure_grad_arena(torch.device("cpu"))
+    assert all(off % 4 == 0 for off in m._grad_offsets.values()) and m._grad_arena.data_ptr() % 16 == 0
+    B = 76                                   # 76 * 32 * 32 = 77 824 pixels >= 128 * 148 * 4: the slab path's threshold
+    plan = UnetPlan(dict(m.named_parameters()), dict(m.named_buffers()), B, 64, 64, _lib.BF16, "cpu", True,
+                    grad_arena=m._grad_arena, grad_offsets=m._grad_offsets)
+    dw0 = m._grad_arena.data_ptr() + 4 * m._grad_offsets["decoder.blocks.3.conv1.0.weight"]
+    halves = [_lib.op_params(op) for seg in plan.bwd_segments for op in seg
+              if op.kind == _lib.OP_WGRAD and dw0 <= _lib.op_params(op).dw < dw0 + 4 * 32 * 128 * 9]
+    assert len(halves) == 2
+    a, b = sorted(halves, key=lambda p: p.dw)
+    assert (a.c0, b.c0, a.c1, b.c1, a.cin_real, b.cin_real, a.ld0, b.ld0) == (64, 64, 0, 0, 128, 128, 128, 128)
+    assert a.dw == dw0 and b.dw - a.dw == 64 * 9 * 4 and b.src0 - a.src0 == 64 * 2 and a.dy == b.dy
+    assert (a.Cout, a.cout_real, a.kh, a.kw, a.stride, a.pad, a.Hi, a.Wi) == (32, 32, 3, 3, 1, 1, 32, 32)
+    assert a.dw % 16 == 0 and b.dw % 16 == 0
